@@ -1,0 +1,196 @@
+"""fmm_bem_relaxed_b200 -- B200-native FMM matvec engine behind the fmm-bem-relaxed plan API.
+
+Python mirror of the reference's boundary for the hot path (the reference itself is C++;
+the C++ mirror lives in fmm_bem_relaxed_b200/hostcxx/):
+
+    reference (C++)                                   here
+    ------------------------------------------------  ---------------------------------------
+    FMMOptions opts; opts.set_mac_theta(.5);          opts = FMMOptions(); opts.set_mac_theta(.5)
+    opts.set_max_per_box(64)   (FMMOptions.hpp)       opts.set_max_per_box(64)
+    LaplaceSpherical K(5)      (LaplaceSpherical.hpp) K = LaplaceSpherical(5)
+    FMM_plan<K> plan(K, points, opts) (FMM_plan.hpp)  plan = FMM_plan(K, points, opts)
+    plan.kernel().set_p(p)                            plan.kernel().set_p(p)
+    result = plan.execute(charges)                    result = plan.execute(charges)
+    Direct::matvec(K, pts, charges, targets, exact)   exact = Direct.matvec(plan, charges, targets)
+
+All computation happens in libfmmb200.so (CUDA, sm_100a) through the C ABI of include/fmmb.h.
+"""
+import ctypes
+
+import numpy as np
+
+from . import capi
+from .capi import FmmbError
+
+__all__ = ["FMMOptions", "LaplaceSpherical", "FMM_plan", "Direct", "FmmbError", "capi"]
+
+
+class FMMOptions:
+    """Mirror of reference include/FMMOptions.hpp:9-76 (fields and setters used on the hot path)."""
+    FMM, TREECODE = 0, 1
+
+    def __init__(self):
+        self.lazy_evaluation = True
+        self.local_evaluation = False
+        self.sparse_local = False
+        self.block_diagonal = False
+        self.evaluator = FMMOptions.FMM
+        self.theta = 0.5
+        self.NCRIT_ = 64
+        self.printTree = False
+        self.device = -1
+
+    def set_mac_theta(self, theta):
+        self.theta = float(theta)
+
+    def set_max_per_box(self, ncrit):
+        self.NCRIT_ = int(ncrit)
+
+    def max_per_box(self):
+        return self.NCRIT_
+
+
+def get_options(argv):
+    """Mirror of get_options(argc, argv), reference include/FMMOptions.hpp:78-106."""
+    opts = FMMOptions()
+    i = 1
+    while i < len(argv):
+        a = argv[i]
+        if a == "-theta":
+            i += 1
+            opts.set_mac_theta(float(argv[i]))
+        elif a == "-eval":
+            i += 1
+            if argv[i] == "FMM":
+                opts.evaluator = FMMOptions.FMM
+            elif argv[i] == "TREE":
+                opts.evaluator = FMMOptions.TREECODE
+            else:
+                print('[W]: Unknown evaluator type: "%s"' % argv[i])
+        elif a == "-lazy_eval":
+            opts.lazy_evaluation = True
+        elif a == "-ncrit":
+            i += 1
+            opts.set_max_per_box(int(argv[i]))
+        elif a == "-printtree":
+            opts.printTree = True
+        i += 1
+    return opts
+
+
+class LaplaceSpherical:
+    """Mirror of reference kernel/LaplaceSpherical.hpp:14-128: order P, set_p; 1 charge, 4 results."""
+    kind = capi.LAPLACE_SPHERICAL
+    dimension = 3
+    charge_dim = 1
+    result_dim = 4
+
+    def __init__(self, p=5):
+        self.P = int(p)
+        self._plan = None
+
+    def set_p(self, p):
+        self.P = int(p)
+        if self._plan is not None:
+            capi.check(capi.load().fmmb_plan_set_p(self._plan._h, self.P))
+
+
+class FMM_plan:
+    """Mirror of reference include/FMM_plan.hpp:15-128 for source == target plans."""
+
+    def __init__(self, kernel, sources, opts=None):
+        lib = capi.load()
+        opts = opts or FMMOptions()
+        pts = np.ascontiguousarray(np.asarray(sources, dtype=np.float64).reshape(-1, 3))
+        self._n = pts.shape[0]
+        self.K = LaplaceSpherical(kernel.P)      # the plan owns a COPY of the kernel (FMM_plan.hpp:37)
+        self.opts_ = opts
+        kd = capi.KernelDesc(kernel.kind, kernel.P, 0.0, 0, 0)
+        src = capi.Sources(self._n, capi.ptr(pts))
+        op = capi.Options(opts.theta, opts.NCRIT_, opts.evaluator, opts.device, 0)
+        h = ctypes.c_void_p()
+        capi.check(lib.fmmb_plan_create(ctypes.byref(kd), ctypes.byref(src), ctypes.byref(op), ctypes.byref(h)))
+        self._h = h
+        self._lib = lib
+        self.K._plan = self
+
+    def __del__(self):
+        self.close()
+
+    def close(self):
+        h = getattr(self, "_h", None)
+        if h is not None and h.value:
+            self._lib.fmmb_plan_destroy(h)
+            self._h = None
+
+    def kernel(self):
+        return self.K
+
+    def options(self):
+        return self.opts_
+
+    def execute(self, charges):
+        """results = A * charges; (n, 4) array: potential, fx, fy, fz in the caller's order."""
+        q = np.ascontiguousarray(np.asarray(charges, dtype=np.float64).reshape(-1))
+        if q.shape[0] != self._n:
+            raise ValueError("charges.size() != sources.size()")
+        out = np.empty((self._n, 4), dtype=np.float64)
+        capi.check(self._lib.fmmb_plan_execute(self._h, capi.ptr(q), capi.ptr(out)))
+        return out
+
+    def execute_device(self, charges_ptr, results_ptr):
+        """Device-pointer variant (ints / ctypes pointers), asynchronous on the plan stream."""
+        capi.check(self._lib.fmmb_plan_execute_device(self._h, ctypes.c_void_p(charges_ptr),
+                                                      ctypes.c_void_p(results_ptr)))
+
+    def sync(self):
+        capi.check(self._lib.fmmb_plan_sync(self._h))
+
+    def stream(self):
+        return self._lib.fmmb_plan_stream(self._h)
+
+    def info(self):
+        info = capi.PlanInfo()
+        capi.check(self._lib.fmmb_plan_get_info(self._h, ctypes.byref(info)))
+        return info
+
+    def phase_times(self):
+        ms = np.zeros(capi.T_COUNT)
+        capi.check(self._lib.fmmb_plan_phase_times(self._h, capi.ptr(ms), capi.T_COUNT))
+        return {"total": ms[0], "upward": ms[1], "m2l": ms[2], "downward": ms[3], "p2p": ms[4],
+                "h2d": ms[5], "d2h": ms[6]}
+
+    def tree(self):
+        """Copies of the device tree and lists (see include/fmmb.h: fmmb_plan_get_tree)."""
+        i = self.info()
+        n, nb = i.n_bodies, i.n_boxes
+        t = {
+            "perm": np.zeros(n, np.uint32), "codes": np.zeros(n, np.uint32),
+            "boxes": np.zeros((nb, 8), np.uint32), "geom": np.zeros((nb, 4)),
+            "lr": np.zeros((i.n_m2l_pairs, 2), np.int32), "p2p_off": np.zeros(nb + 1, np.int32),
+            "p2p_idx": np.zeros(i.n_p2p_box_pairs, np.int32),
+        }
+        capi.check(self._lib.fmmb_plan_get_tree(self._h, capi.ptr(t["perm"]), capi.ptr(t["codes"]),
+                                                capi.ptr(t["boxes"]), capi.ptr(t["geom"]), capi.ptr(t["lr"]),
+                                                capi.ptr(t["p2p_off"]), capi.ptr(t["p2p_idx"])))
+        return t
+
+    def expansions(self):
+        i = self.info()
+        nc = i.p * (i.p + 1) // 2
+        M = np.zeros((i.n_boxes, nc, 2))
+        L = np.zeros((i.n_boxes, nc, 2))
+        capi.check(self._lib.fmmb_plan_get_expansions(self._h, capi.ptr(M), capi.ptr(L)))
+        return M, L
+
+
+class Direct:
+    """Mirror of Direct::matvec (reference include/Direct.hpp:273-288), evaluated on the GPU."""
+
+    @staticmethod
+    def matvec(plan, charges, targets):
+        q = np.ascontiguousarray(np.asarray(charges, dtype=np.float64).reshape(-1))
+        t = np.ascontiguousarray(np.asarray(targets, dtype=np.float64).reshape(-1, 3))
+        out = np.empty((t.shape[0], 4))
+        capi.check(plan._lib.fmmb_plan_direct(plan._h, capi.ptr(q), t.shape[0], capi.ptr(t), capi.ptr(out)))
+        return out

@@ -1,0 +1,255 @@
+// csrc/capi.cu -- extern "C" entry points declared in include/fmmb.h.
+// No torch, no C++ types across the boundary; every failure becomes a negative status plus a
+// thread-local message (the reference prints and exit()s instead: include/executor/P2M.hpp:13-17).
+#include "common.cuh"
+#include <cstring>
+#include <new>
+
+namespace fmmb {
+static thread_local std::string g_last_error;
+void set_error(const std::string& msg) { g_last_error = msg; }
+
+template <typename F>
+static int guarded(F&& f) {
+  try {
+    f();
+    return FMMB_OK;
+  } catch (const CudaError& e) {
+    char buf[512];
+    snprintf(buf, sizeof buf, "CUDA error %d (%s) in %s at %s:%d", (int)e.err, cudaGetErrorString(e.err), e.what,
+             e.file, e.line);
+    set_error(buf);
+    return FMMB_ERR_CUDA;
+  } catch (const StatusError& e) {
+    set_error(e.msg);
+    return e.status;
+  } catch (const std::bad_alloc&) {
+    set_error("host allocation failed");
+    return FMMB_ERR_INVALID;
+  }
+}
+
+static void update_phase_times(fmmb_plan* plan) {
+  if (!plan->timed) return;
+  auto ms = [&](int a, int b) {
+    float t = 0;
+    if (cudaEventElapsedTime(&t, plan->ev[a], plan->ev[b]) != cudaSuccess) { cudaGetLastError(); return 0.0; }
+    return (double)t;
+  };
+  plan->phase_ms[FMMB_T_TOTAL] = ms(0, 5);
+  plan->phase_ms[FMMB_T_UPWARD] = ms(0, 2);
+  plan->phase_ms[FMMB_T_M2L] = ms(2, 3);
+  plan->phase_ms[FMMB_T_DOWNWARD] = ms(3, 4);
+  plan->phase_ms[FMMB_T_P2P] = ms(6, 7);
+}
+}  // namespace fmmb
+
+using namespace fmmb;
+
+extern "C" {
+
+const char* fmmb_last_error(void) { return g_last_error.c_str(); }
+const char* fmmb_version(void) { return "fmmb200 0.1 sm_100a"; }
+
+int fmmb_plan_create(const fmmb_kernel_desc* kernel, const fmmb_sources* sources, const fmmb_options* options,
+                     fmmb_plan** out_plan) {
+  if (!kernel || !sources || !out_plan) { set_error("null argument"); return FMMB_ERR_INVALID; }
+  *out_plan = nullptr;
+  if (kernel->kind != FMMB_LAPLACE_SPHERICAL) {
+    set_error("only FMMB_LAPLACE_SPHERICAL is built in this version");
+    return FMMB_ERR_UNSUPPORTED;
+  }
+  if (kernel->p < 1 || kernel->p > FMMB_MAX_P) { set_error("expansion order must be in 1..16"); return FMMB_ERR_INVALID; }
+  if (sources->n < 1 || !sources->points) { set_error("need at least one source point"); return FMMB_ERR_INVALID; }
+  fmmb_options opts;
+  std::memset(&opts, 0, sizeof opts);
+  opts.theta = 0.5; opts.ncrit = 64; opts.evaluator = FMMB_EVAL_FMM; opts.device = -1;
+  if (options) opts = *options;
+  if (!(opts.theta > 0)) { set_error("theta must be positive"); return FMMB_ERR_INVALID; }
+  if (opts.ncrit < 1) { set_error("ncrit must be at least 1"); return FMMB_ERR_INVALID; }
+  if (opts.evaluator != FMMB_EVAL_FMM) { set_error("treecode evaluator is not built"); return FMMB_ERR_UNSUPPORTED; }
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    set_error("no CUDA device: this engine has no CPU path");
+    return FMMB_ERR_NO_DEVICE;
+  }
+  fmmb_plan* plan = new (std::nothrow) fmmb_plan();
+  if (!plan) { set_error("host allocation failed"); return FMMB_ERR_INVALID; }
+  int rc = guarded([&] {
+    if (opts.device >= 0) FMMB_CUDA(cudaSetDevice(opts.device));
+    FMMB_CUDA(cudaGetDevice(&plan->device));
+    plan->opts = opts;
+    plan->kind = kernel->kind;
+    plan->p = kernel->p;
+    FMMB_CUDA(cudaStreamCreateWithFlags(&plan->stream, cudaStreamNonBlocking));
+    FMMB_CUDA(cudaStreamCreateWithFlags(&plan->stream2, cudaStreamNonBlocking));
+    for (auto& e : plan->ev) FMMB_CUDA(cudaEventCreate(&e));
+    laplace_init_tables(plan);
+    build_tree(plan, sources->points, sources->n);
+  });
+  if (rc != FMMB_OK) { fmmb_plan_destroy(plan); return rc; }
+  *out_plan = plan;
+  return FMMB_OK;
+}
+
+void fmmb_plan_destroy(fmmb_plan* plan) {
+  if (!plan) return;
+  cudaSetDevice(plan->device);
+  if (plan->stream) cudaStreamSynchronize(plan->stream);
+  if (plan->stream2) cudaStreamSynchronize(plan->stream2);
+  for (auto& kv : plan->m2l_coeff) delete kv.second;
+  for (auto& e : plan->ev) if (e) cudaEventDestroy(e);
+  if (plan->stream) cudaStreamDestroy(plan->stream);
+  if (plan->stream2) cudaStreamDestroy(plan->stream2);
+  delete plan;
+}
+
+int fmmb_plan_set_p(fmmb_plan* plan, int p) {
+  if (!plan) { set_error("null plan"); return FMMB_ERR_INVALID; }
+  if (p < 1 || p > FMMB_MAX_P) { set_error("expansion order must be in 1..16"); return FMMB_ERR_INVALID; }
+  plan->p = p;
+  return FMMB_OK;
+}
+
+int fmmb_plan_execute_device(fmmb_plan* plan, const double* charges_dev, double* results_dev) {
+  if (!plan || !charges_dev || !results_dev) { set_error("null argument"); return FMMB_ERR_INVALID; }
+  return guarded([&] {
+    FMMB_CUDA(cudaSetDevice(plan->device));
+    laplace_execute(plan, charges_dev, results_dev);
+  });
+}
+
+int fmmb_plan_execute(fmmb_plan* plan, const double* charges_host, double* results_host) {
+  if (!plan || !charges_host || !results_host) { set_error("null argument"); return FMMB_ERR_INVALID; }
+  return guarded([&] {
+    FMMB_CUDA(cudaSetDevice(plan->device));
+    const int64_t n = plan->tree.n;
+    cudaStream_t s = plan->stream;
+    plan->charges.resize(n);
+    plan->results.resize(4 * (size_t)n);
+    FMMB_CUDA(cudaEventRecord(plan->ev[8], s));
+    FMMB_CUDA(cudaMemcpyAsync(plan->charges.p, charges_host, n * sizeof(double), cudaMemcpyHostToDevice, s));
+    FMMB_CUDA(cudaEventRecord(plan->ev[9], s));
+    laplace_execute(plan, plan->charges.p, plan->results.p);
+    FMMB_CUDA(cudaEventRecord(plan->ev[10], s));
+    FMMB_CUDA(cudaMemcpyAsync(results_host, plan->results.p, 4 * (size_t)n * sizeof(double),
+                              cudaMemcpyDeviceToHost, s));
+    FMMB_CUDA(cudaEventRecord(plan->ev[11], s));
+    FMMB_CUDA(cudaStreamSynchronize(s));
+    update_phase_times(plan);
+    float t = 0;
+    FMMB_CUDA(cudaEventElapsedTime(&t, plan->ev[8], plan->ev[9])); plan->phase_ms[FMMB_T_H2D] = t;
+    FMMB_CUDA(cudaEventElapsedTime(&t, plan->ev[10], plan->ev[11])); plan->phase_ms[FMMB_T_D2H] = t;
+  });
+}
+
+int fmmb_plan_direct(fmmb_plan* plan, const double* charges_host, int64_t nt, const double* targets_host,
+                     double* results_host) {
+  if (!plan || !charges_host || !targets_host || !results_host || nt < 0) { set_error("bad argument"); return FMMB_ERR_INVALID; }
+  return guarded([&] {
+    FMMB_CUDA(cudaSetDevice(plan->device));
+    cudaStream_t s = plan->stream;
+    DevBuf<double> q, t, out;
+    q.from_host(charges_host, plan->tree.n, s);
+    t.from_host(targets_host, 3 * (size_t)nt, s);
+    out.resize(4 * (size_t)nt);
+    if (nt) laplace_direct_raw(plan->tree.pts_orig.p, q.p, plan->tree.n, t.p, nt, out.p, s);
+    if (nt) FMMB_CUDA(cudaMemcpyAsync(results_host, out.p, 4 * (size_t)nt * sizeof(double), cudaMemcpyDeviceToHost, s));
+    FMMB_CUDA(cudaStreamSynchronize(s));
+  });
+}
+
+int fmmb_plan_sync(fmmb_plan* plan) {
+  if (!plan) { set_error("null plan"); return FMMB_ERR_INVALID; }
+  return guarded([&] {
+    FMMB_CUDA(cudaSetDevice(plan->device));
+    FMMB_CUDA(cudaStreamSynchronize(plan->stream));
+    update_phase_times(plan);
+  });
+}
+
+void* fmmb_plan_stream(fmmb_plan* plan) { return plan ? (void*)plan->stream : nullptr; }
+
+int fmmb_plan_get_info(fmmb_plan* plan, fmmb_plan_info* info) {
+  if (!plan || !info) { set_error("null argument"); return FMMB_ERR_INVALID; }
+  std::memset(info, 0, sizeof *info);
+  const Tree& T = plan->tree;
+  info->n_bodies = T.n; info->n_boxes = T.nboxes; info->n_leaves = T.nleaves; info->n_levels = T.nlevels;
+  info->n_m2l_pairs = T.n_lr; info->n_p2p_box_pairs = T.n_p2p; info->n_p2p_body_pairs = T.n_p2p_body_pairs;
+  info->n_m2l_classes = plan->cls.n_classes; info->n_m2l_pairs_batched = plan->cls.n_pairs;
+  info->p = plan->p; info->charge_dim = 1; info->result_dim = 4; info->device = plan->device;
+  return FMMB_OK;
+}
+
+int fmmb_plan_get_tree(fmmb_plan* plan, uint32_t* perm, uint32_t* codes, uint32_t* boxes, double* geom,
+                       int32_t* m2l_pairs, int32_t* p2p_off, int32_t* p2p_idx) {
+  if (!plan) { set_error("null plan"); return FMMB_ERR_INVALID; }
+  return guarded([&] {
+    FMMB_CUDA(cudaSetDevice(plan->device));
+    const Tree& T = plan->tree;
+    cudaStream_t s = plan->stream;
+    auto d2h = [&](void* dst, const void* src, size_t bytes) {
+      if (dst && bytes) FMMB_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, s));
+    };
+    d2h(perm, T.perm.p, T.n * sizeof(unsigned));
+    d2h(codes, T.code.p, T.n * sizeof(unsigned));
+    d2h(m2l_pairs, T.lr.p, T.n_lr * sizeof(int2));
+    d2h(p2p_off, T.p2p_off.p, (size_t)(T.nboxes + 1) * sizeof(int));
+    d2h(p2p_idx, T.p2p_src.p, T.n_p2p * sizeof(int));
+    FMMB_CUDA(cudaStreamSynchronize(s));
+    const int nb = T.nboxes;
+    if (boxes) {
+      std::vector<unsigned> key = T.key.to_host(s), par = T.parent.to_host(s), cb = T.cbegin.to_host(s),
+                            ce = T.cend.to_host(s), bb = T.bbegin.to_host(s), be = T.bend.to_host(s),
+                            lv = T.level.to_host(s);
+      for (int b = 0; b < nb; ++b) {
+        uint32_t* r = boxes + 8 * (size_t)b;
+        r[0] = key[b]; r[1] = par[b]; r[2] = cb[b]; r[3] = ce[b]; r[4] = bb[b]; r[5] = be[b]; r[6] = lv[b];
+        r[7] = key[b] >> 31;
+      }
+    }
+    if (geom) {
+      std::vector<double4> c = T.center.to_host(s);
+      for (int b = 0; b < nb; ++b) {
+        geom[4 * (size_t)b] = c[b].x; geom[4 * (size_t)b + 1] = c[b].y; geom[4 * (size_t)b + 2] = c[b].z;
+        geom[4 * (size_t)b + 3] = c[b].w;
+      }
+    }
+  });
+}
+
+int fmmb_plan_get_expansions(fmmb_plan* plan, double* multipoles, double* locals) {
+  if (!plan) { set_error("null plan"); return FMMB_ERR_INVALID; }
+  return guarded([&] {
+    FMMB_CUDA(cudaSetDevice(plan->device));
+    cudaStream_t s = plan->stream;
+    FMMB_CUDA(cudaStreamSynchronize(s));
+    size_t bytes = (size_t)plan->tree.nboxes * (plan->p * (plan->p + 1) / 2) * sizeof(double2);
+    if (multipoles && plan->M.n) FMMB_CUDA(cudaMemcpyAsync(multipoles, plan->M.p, bytes, cudaMemcpyDeviceToHost, s));
+    if (locals && plan->L.n) FMMB_CUDA(cudaMemcpyAsync(locals, plan->L.p, bytes, cudaMemcpyDeviceToHost, s));
+    FMMB_CUDA(cudaStreamSynchronize(s));
+  });
+}
+
+int fmmb_plan_phase_times(fmmb_plan* plan, double* ms, int count) {
+  if (!plan || !ms) { set_error("null argument"); return FMMB_ERR_INVALID; }
+  for (int i = 0; i < count && i < FMMB_T_COUNT; ++i) ms[i] = plan->phase_ms[i];
+  return FMMB_OK;
+}
+
+int fmmb_measure_fp64_peak(int device, double* tflops) {
+  if (!tflops) { set_error("null argument"); return FMMB_ERR_INVALID; }
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    set_error("no CUDA device");
+    return FMMB_ERR_NO_DEVICE;
+  }
+  return guarded([&] {
+    if (device >= 0) FMMB_CUDA(cudaSetDevice(device));
+    *tflops = measure_fp64_peak();
+  });
+}
+
+}  // extern "C"

@@ -1,0 +1,165 @@
+// csrc/common.cuh -- shared plumbing for the B200 FMM engine (device buffers, error handling,
+// the plan object).  sm_100a only.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <string>
+#include <vector>
+#include <map>
+#include "../../include/fmmb.h"
+
+namespace fmmb {
+
+void set_error(const std::string& msg);
+
+struct CudaError {
+  cudaError_t err;
+  const char* what;
+  const char* file;
+  int line;
+};
+
+#define FMMB_CUDA(call)                                                        \
+  do {                                                                         \
+    cudaError_t e_ = (call);                                                   \
+    if (e_ != cudaSuccess) throw ::fmmb::CudaError{e_, #call, __FILE__, __LINE__}; \
+  } while (0)
+
+struct StatusError {
+  int status;
+  std::string msg;
+};
+
+// Plain device buffer.  resize() discards contents; grow() preserves them.
+template <typename T>
+struct DevBuf {
+  T* p = nullptr;
+  size_t cap = 0;   // elements allocated
+  size_t n = 0;     // elements in use
+  DevBuf() {}
+  DevBuf(const DevBuf&) = delete;
+  DevBuf& operator=(const DevBuf&) = delete;
+  ~DevBuf() { release(); }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr; cap = n = 0;
+  }
+  void resize(size_t count) {
+    if (count > cap) {
+      if (p) cudaFree(p);
+      p = nullptr;
+      FMMB_CUDA(cudaMalloc((void**)&p, (count ? count : 1) * sizeof(T)));
+      cap = count ? count : 1;
+    }
+    n = count;
+  }
+  void grow(size_t count, cudaStream_t s) {
+    if (count > cap) {
+      size_t ncap = cap * 2 > count ? cap * 2 : count;
+      T* q = nullptr;
+      FMMB_CUDA(cudaMalloc((void**)&q, ncap * sizeof(T)));
+      if (p && n) FMMB_CUDA(cudaMemcpyAsync(q, p, n * sizeof(T), cudaMemcpyDeviceToDevice, s));
+      if (p) { FMMB_CUDA(cudaStreamSynchronize(s)); cudaFree(p); }
+      p = q; cap = ncap;
+    }
+    n = count;
+  }
+  void zero(cudaStream_t s) { if (n) FMMB_CUDA(cudaMemsetAsync(p, 0, n * sizeof(T), s)); }
+  std::vector<T> to_host(cudaStream_t s) const {
+    std::vector<T> h(n);
+    if (n) {
+      FMMB_CUDA(cudaMemcpyAsync(h.data(), p, n * sizeof(T), cudaMemcpyDeviceToHost, s));
+      FMMB_CUDA(cudaStreamSynchronize(s));
+    }
+    return h;
+  }
+  void from_host(const T* h, size_t count, cudaStream_t s) {
+    resize(count);
+    if (count) FMMB_CUDA(cudaMemcpyAsync(p, h, count * sizeof(T), cudaMemcpyHostToDevice, s));
+  }
+};
+
+// Octree + interaction lists, device resident (built by tree.cu).
+struct Tree {
+  int64_t n = 0;
+  unsigned ncrit = 64;
+  double theta = 0.5;
+  double pmin[3], cell[3];
+  int nboxes = 0, nlevels = 0, nleaves = 0;
+  std::vector<int> level_off;        // host copy: boxes of level l are [level_off[l], level_off[l+1])
+
+  DevBuf<double> pts_orig;           // the caller's points, original order (3n)
+  DevBuf<unsigned> perm;             // tree index -> original index
+  DevBuf<unsigned> code;             // Morton code, tree order
+  DevBuf<double4> body;              // tree order: x, y, z, (charge slot written per matvec)
+  // box table (SoA)
+  DevBuf<unsigned> key, parent, cbegin, cend, bbegin, bend, level;
+  DevBuf<double4> center;            // cx, cy, cz, side
+  DevBuf<int> leaves;                // indices of leaf boxes, ascending
+  DevBuf<unsigned char> has_local;   // box carries a local expansion (M2L target or descendant of one)
+  // M2L: reference-order pair list and target-major CSR (sources in list order per target)
+  DevBuf<int2> lr;                   // (source, target) in LR_list order
+  DevBuf<int> m2l_off, m2l_src;
+  int64_t n_lr = 0;
+  // P2P: target-major CSR of source leaf boxes in P2P_lists order
+  DevBuf<int> p2p_off, p2p_src;
+  int64_t n_p2p = 0, n_p2p_body_pairs = 0;
+};
+
+// Batched-M2L structures (built by m2l_classes.cu)
+struct M2LClasses {
+  int64_t n_classes = 0;
+  int64_t n_pairs = 0;               // pairs covered by the batched path
+  int built_p = 0;                   // order the matrices were built for (0 = none)
+  DevBuf<double> T;                  // n_classes * built_p^2 * built_p^2 real translation matrices
+  DevBuf<double4> class_vec;         // representative translation vector per class
+  // work items: (tile, class) groups
+  DevBuf<int> item_class, item_off;  // per item: class id, offset into pair arrays (n_items+1)
+  DevBuf<int> pair_tgt, pair_src;    // per pair: target box, source box
+  DevBuf<int> tile_item_off;         // per target tile: range of items
+  int n_items = 0, n_tiles = 0;
+  // residual pairs that stay on the per-pair kernel (target-major CSR)
+  DevBuf<int> res_off, res_src;
+  int64_t n_res = 0;
+};
+
+struct LaplaceTables {
+  int pmax = 0;
+  DevBuf<double> pref;               // sqrt((n-|m|)!/(n+|m|)!), index n^2+n+m, n < 2*pmax
+  DevBuf<double> anm;                // (-1)^n / sqrt((n-m)!(n+m)!)
+};
+
+}  // namespace fmmb
+
+struct fmmb_plan {
+  int device = 0;
+  int kind = 0;
+  int p = 5;
+  int p_alloc = 0;                   // order the expansion buffers are sized for
+  fmmb_options opts;
+  cudaStream_t stream = nullptr, stream2 = nullptr;
+  cudaEvent_t ev[12];
+  fmmb::Tree tree;
+  fmmb::LaplaceTables tab;
+  fmmb::M2LClasses cls;
+  std::map<int, fmmb::DevBuf<double>*> m2l_coeff;  // per-order real M2L coefficient tables
+  fmmb::DevBuf<double2> M, L;        // box-major, nc(p) complex per box
+  fmmb::DevBuf<double> charges;      // original order staging
+  fmmb::DevBuf<double4> res_near, res_far;  // tree order
+  fmmb::DevBuf<double> results;      // original order staging, 4n
+  double phase_ms[FMMB_T_COUNT] = {0};
+  bool timed = false;
+};
+
+namespace fmmb {
+// tree.cu
+void build_tree(fmmb_plan* plan, const double* points_host, int64_t n);
+// laplace.cu
+void laplace_init_tables(fmmb_plan* plan);
+void laplace_execute(fmmb_plan* plan, const double* d_charges, double* d_results);
+void laplace_direct_raw(const double* d_spts, const double* d_q, int64_t ns, const double* d_tpts, int64_t nt,
+                        double* d_out, cudaStream_t s);
+double measure_fp64_peak();
+}  // namespace fmmb

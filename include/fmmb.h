@@ -1,0 +1,171 @@
+/* include/fmmb.h -- C ABI of the B200 FMM matvec engine (libfmmb200.so).
+ *
+ * This is the drop-in boundary for the hot path of barbagroup/fmm-bem-relaxed:
+ *     FMM_plan<Kernel>::FMM_plan(K, sources, opts)       reference include/FMM_plan.hpp:34-43
+ *     FMM_plan<Kernel>::execute(charges) -> results       reference include/FMM_plan.hpp:75-90
+ *     plan.kernel().set_p(p)                              reference kernel/LaplaceSpherical.hpp:119-128,
+ *                                                         called per GMRES iteration, examples/BEM/GMRES.hpp:195-196
+ * Everything below that boundary in the reference (include/executor/ *, include/tree/ *,
+ * kernel/ *.hpp operator bodies) is replaced by CUDA kernels for sm_100a behind these
+ * entry points.  Plain pointers and sizes only; no C++ or torch types.
+ *
+ * Conventions
+ *   - every function returns 0 on success or a negative fmmb_status; fmmb_last_error()
+ *     returns a thread-local message for the last failure on the calling thread.
+ *   - "host" pointers are ordinary host memory (pinned memory makes copies faster),
+ *     "device" pointers are CUDA device memory on the plan's device.
+ *   - charges arrive and results leave in the caller's ORIGINAL body order, like
+ *     std::vector<charge_type> / std::vector<result_type> in the reference
+ *     (reference include/executor/ExecutorSingleTree.hpp:81-90).
+ *   - one plan = one CUDA stream; calls on one plan must be serialised by the caller
+ *     (the reference's plan is not re-entrant either: ExecutorSingleTree.hpp:153-160).
+ *   - there is NO CPU fallback: every entry point that computes needs a CUDA device.
+ */
+#ifndef FMMB_H_
+#define FMMB_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct fmmb_plan fmmb_plan;
+
+typedef enum {
+  FMMB_OK = 0,
+  FMMB_ERR_INVALID = -1,      /* bad argument */
+  FMMB_ERR_CUDA = -2,         /* a CUDA call failed (message has the CUDA error) */
+  FMMB_ERR_TREE_DEPTH = -3,   /* input needs more than 10 octree levels; the reference loops
+                                 forever on such input (include/tree/Octree.hpp:85-92,649) */
+  FMMB_ERR_UNSUPPORTED = -4,  /* kernel kind / option not built yet */
+  FMMB_ERR_NO_DEVICE = -5     /* no CUDA device: the engine has no CPU path */
+} fmmb_status;
+
+/* Kernel classes of the reference (kernel/ *.hpp) that a plan can be built for. */
+typedef enum {
+  FMMB_LAPLACE_SPHERICAL = 0,          /* kernel/LaplaceSpherical.hpp: charge 1, result 4 */
+  FMMB_LAPLACE_SPHERICAL_BEM = 1,      /* kernel/LaplaceSphericalBEM.hpp (not built yet) */
+  FMMB_STOKES_SPHERICAL_STRESSLET = 2, /* kernel/StokesSpherical.hpp, STRESSLET (not built yet) */
+  FMMB_YUKAWA_CARTESIAN = 3,           /* kernel/YukawaCartesian.hpp (not built yet) */
+  FMMB_YUKAWA_CARTESIAN_BEM = 4        /* kernel/YukawaCartesianBEM.hpp (not built yet) */
+} fmmb_kernel_kind;
+
+/* Mirrors the kernel constructor arguments: LaplaceSpherical(int p) etc. */
+typedef struct {
+  int32_t kind;    /* fmmb_kernel_kind */
+  int32_t p;       /* expansion order the kernel object was constructed with (1..FMMB_MAX_P) */
+  double kappa;    /* Yukawa screening parameter (unused for Laplace) */
+  int32_t quad_k;  /* BEM Gauss points per panel (unused for point kernels) */
+  int32_t reserved;
+} fmmb_kernel_desc;
+
+#define FMMB_MAX_P 16 /* SolverOptions::max_p default, examples/BEM/SolverOptions.hpp:23 */
+
+/* Mirrors FMMOptions (reference include/FMMOptions.hpp:9-49). */
+typedef enum { FMMB_EVAL_FMM = 0, FMMB_EVAL_TREECODE = 1 } fmmb_evaluator;
+
+typedef struct {
+  double theta;        /* FMMOptions::set_mac_theta, default 0.5 */
+  uint32_t ncrit;      /* FMMOptions::set_max_per_box, default 64 */
+  int32_t evaluator;   /* fmmb_evaluator; only FMMB_EVAL_FMM is built */
+  int32_t device;      /* CUDA device ordinal, -1 = current device */
+  int32_t m2l_mode;    /* 0 = auto, 1 = per-pair kernel only, 2 = prefer batched translation classes */
+  int32_t reserved[3];
+} fmmb_options;
+
+/* Point sources (source_type == point_type kernels).  points: 3*n doubles, point-major
+ * (x0,y0,z0,x1,...), host memory, borrowed for the duration of the call. */
+typedef struct {
+  int64_t n;
+  const double* points;
+} fmmb_sources;
+
+/* Sizes a caller needs for fmmb_plan_get_tree and for recomputing work counts. */
+typedef struct {
+  int64_t n_bodies;
+  int64_t n_boxes;
+  int64_t n_leaves;
+  int64_t n_levels;        /* Octree::levels(): max level + 1 ... see reference Octree.hpp:510-512 */
+  int64_t n_m2l_pairs;     /* |LR_list|, reference EvalInteractionLazy.hpp:231 */
+  int64_t n_p2p_box_pairs; /* sum |P2P_lists[b]|, reference EvalInteractionLazy.hpp:79 */
+  int64_t n_p2p_body_pairs;
+  int64_t n_m2l_classes;   /* distinct translation vectors handled by the batched M2L */
+  int64_t n_m2l_pairs_batched;
+  int32_t p;               /* current expansion order */
+  int32_t charge_dim;      /* doubles per charge (Laplace 1) */
+  int32_t result_dim;      /* doubles per result (Laplace 4: potential, fx, fy, fz) */
+  int32_t device;
+} fmmb_plan_info;
+
+/* Phase indices for fmmb_plan_phase_times (milliseconds, CUDA events, last execute). */
+enum {
+  FMMB_T_TOTAL = 0, FMMB_T_UPWARD = 1, FMMB_T_M2L = 2, FMMB_T_DOWNWARD = 3, FMMB_T_P2P = 4,
+  FMMB_T_H2D = 5, FMMB_T_D2H = 6, FMMB_T_COUNT = 8
+};
+
+/* FMM_plan<K>(K, sources, opts): builds the octree and all interaction lists on the device.
+ * Replaces reference include/FMM_plan.hpp:34-43 -> make_executor (executor/make_executor.hpp:67-78)
+ * -> Octree ctor (tree/Octree.hpp:485-488) + EvalInteractionLazy ctor (:59-117). */
+int fmmb_plan_create(const fmmb_kernel_desc* kernel, const fmmb_sources* sources,
+                     const fmmb_options* options, fmmb_plan** out_plan);
+
+/* plan.kernel().set_p(p): takes effect at the next execute.  1 <= p <= FMMB_MAX_P.
+ * Replaces reference kernel/LaplaceSpherical.hpp:119-128. */
+int fmmb_plan_set_p(fmmb_plan* plan, int p);
+
+/* results = A * charges, host buffers, original order; blocks until results are written.
+ * charges: n*charge_dim doubles; results: n*result_dim doubles (overwritten).
+ * Replaces reference include/FMM_plan.hpp:75-90. */
+int fmmb_plan_execute(fmmb_plan* plan, const double* charges_host, double* results_host);
+
+/* Same with device buffers; asynchronous on the plan's stream (see fmmb_plan_stream /
+ * fmmb_plan_sync).  This is what a device-resident GMRES feeds. */
+int fmmb_plan_execute_device(fmmb_plan* plan, const double* charges_dev, double* results_dev);
+
+/* Brute force reference sum on the GPU for accuracy checks:
+ * Direct::matvec(K, sources, charges, targets, results), reference include/Direct.hpp:273-288.
+ * targets: 3*nt doubles (host); results: nt*result_dim doubles (host). */
+int fmmb_plan_direct(fmmb_plan* plan, const double* charges_host, int64_t nt,
+                     const double* targets_host, double* results_host);
+
+int fmmb_plan_sync(fmmb_plan* plan);
+void* fmmb_plan_stream(fmmb_plan* plan); /* cudaStream_t */
+
+int fmmb_plan_get_info(fmmb_plan* plan, fmmb_plan_info* info);
+
+/* Copies the tree and lists to host arrays (any pointer may be NULL to skip it):
+ *   perm[n]        tree index -> original index (Octree::permute_, reference Octree.hpp:687-691)
+ *   codes[n]       Morton code per tree-ordered body (Octree::mc_)
+ *   boxes[8*nb]    key(with leaf bit 31), parent, child_begin, child_end (raw box_data fields,
+ *                  reference Octree.hpp:196-210), body_begin, body_end, level, is_leaf
+ *   geom[4*nb]     centre x,y,z and side length (reference Octree.hpp:243-248,334-355)
+ *   m2l_pairs[2*n_m2l_pairs]  (source box, target box) in the reference's LR_list order
+ *   p2p_off[nb+1], p2p_idx[n_p2p_box_pairs]  per TARGET box, the source boxes in P2P_lists order
+ */
+int fmmb_plan_get_tree(fmmb_plan* plan, uint32_t* perm, uint32_t* codes, uint32_t* boxes,
+                       double* geom, int32_t* m2l_pairs, int32_t* p2p_off, int32_t* p2p_idx);
+
+/* Multipole / local expansions of the last execute, box-major, nc = p(p+1)/2 complex numbers
+ * (re,im interleaved) per box, packed index n(n+1)/2+m as in the reference
+ * (kernel/LaplaceSpherical.hpp:193-198).  Host arrays of 2*nc*nb doubles; NULL skips. */
+int fmmb_plan_get_expansions(fmmb_plan* plan, double* multipoles, double* locals);
+
+int fmmb_plan_phase_times(fmmb_plan* plan, double* ms, int count);
+
+void fmmb_plan_destroy(fmmb_plan* plan);
+
+const char* fmmb_last_error(void);
+
+/* Library build info: "fmmb200 <version> sm_100a". */
+const char* fmmb_version(void);
+
+/* Utility used by bench.py for the FP64 roofline: runs a dependent-free DFMA loop on every SM
+ * and returns achieved FP64 TFLOP/s (2 flop per DFMA). */
+int fmmb_measure_fp64_peak(int device, double* tflops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FMMB_H_ */

@@ -1,0 +1,134 @@
+"""ctypes wrapper of oracle/libfmm_oracle.so (the CPU restatement).  TEST INFRASTRUCTURE ONLY."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORACLE_DIR = os.path.join(ROOT, "oracle")
+LIB = os.path.join(ORACLE_DIR, "libfmm_oracle.so")
+REF_BIN = os.path.join(ORACLE_DIR, "_ref", "ref_laplace")
+
+_lib = None
+
+
+def build():
+    subprocess.check_call(["make", "-s", "-C", ORACLE_DIR, "port"])
+
+
+def load():
+    global _lib
+    if _lib is None:
+        src = os.path.join(ORACLE_DIR, "fmm_oracle.cpp")
+        if not os.path.exists(LIB) or os.path.getmtime(LIB) < os.path.getmtime(src):
+            build()
+        L = ctypes.CDLL(LIB)
+        vp = ctypes.c_void_p
+        L.fmmo_create.restype = vp
+        L.fmmo_create.argtypes = [ctypes.c_int, vp, ctypes.c_uint, ctypes.c_double]
+        L.fmmo_destroy.argtypes = [vp]
+        L.fmmo_destroy.restype = None
+        for name in ("fmmo_error", "fmmo_nboxes", "fmmo_nlevels"):
+            getattr(L, name).argtypes = [vp]
+        for name in ("fmmo_lr_count", "fmmo_p2p_count"):
+            getattr(L, name).argtypes = [vp]
+            getattr(L, name).restype = ctypes.c_long
+        L.fmmo_list_count.argtypes = [vp, ctypes.c_int]
+        L.fmmo_list_count.restype = ctypes.c_long
+        L.fmmo_get_level_offsets.argtypes = [vp, vp]
+        L.fmmo_get_bounds.argtypes = [vp, vp, vp]
+        L.fmmo_get_perm.argtypes = [vp, vp, vp]
+        L.fmmo_get_boxes.argtypes = [vp, vp, vp]
+        L.fmmo_get_lr.argtypes = [vp, vp]
+        L.fmmo_get_p2p.argtypes = [vp, vp, vp]
+        L.fmmo_get_list.argtypes = [vp, ctypes.c_int, vp]
+        L.fmmo_laplace_execute.argtypes = [vp, ctypes.c_int, vp, vp, ctypes.c_int, ctypes.c_int]
+        L.fmmo_get_expansions.argtypes = [vp, vp, vp]
+        L.fmmo_laplace_direct.argtypes = [ctypes.c_int, vp, vp, ctypes.c_int, vp, vp, ctypes.c_int]
+        L.fmmo_drand48_inputs.argtypes = [ctypes.c_int, vp, vp]
+        _lib = L
+    return _lib
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(ctypes.c_void_p)
+
+
+def drand48_inputs(n):
+    """The reference tests' input: glibc drand48 default state, n points then n charges
+    (reference tests/scaling.cpp:29-38 as compiled by g++)."""
+    pts = np.zeros((n, 3))
+    q = np.zeros(n)
+    load().fmmo_drand48_inputs(n, _p(pts), _p(q))
+    return pts, q
+
+
+class Oracle:
+    def __init__(self, points, ncrit=64, theta=0.5):
+        L = load()
+        self.L = L
+        self.pts = np.ascontiguousarray(np.asarray(points, dtype=np.float64).reshape(-1, 3))
+        self.n = self.pts.shape[0]
+        self.h = ctypes.c_void_p(L.fmmo_create(self.n, _p(self.pts), ncrit, theta))
+        self.error = L.fmmo_error(self.h)
+        self.nboxes = L.fmmo_nboxes(self.h)
+        self.nlevels = L.fmmo_nlevels(self.h)
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.L.fmmo_destroy(self.h)
+            self.h = None
+
+    def tree(self):
+        L, h, n, nb = self.L, self.h, self.n, self.nboxes
+        t = {"perm": np.zeros(n, np.uint32), "codes": np.zeros(n, np.uint32),
+             "boxes": np.zeros((nb, 8), np.uint32), "geom": np.zeros((nb, 4))}
+        L.fmmo_get_perm(h, _p(t["perm"]), _p(t["codes"]))
+        L.fmmo_get_boxes(h, _p(t["boxes"]), _p(t["geom"]))
+        nlr = L.fmmo_lr_count(h)
+        t["lr"] = np.zeros((nlr, 2), np.int32)
+        L.fmmo_get_lr(h, _p(t["lr"]))
+        np2p = L.fmmo_p2p_count(h)
+        t["p2p_off"] = np.zeros(nb + 1, np.int32)
+        t["p2p_idx"] = np.zeros(np2p, np.int32)
+        L.fmmo_get_p2p(h, _p(t["p2p_off"]), _p(t["p2p_idx"]))
+        return t
+
+    def call_list(self, which):
+        width = {0: 1, 1: 2, 2: 2, 3: 1}[which]
+        c = self.L.fmmo_list_count(self.h, which)
+        a = np.zeros(c * width, np.int32)
+        self.L.fmmo_get_list(self.h, which, _p(a))
+        return a.reshape(-1, width) if width == 2 else a
+
+    def execute(self, charges, P, mode=1, threads=None):
+        q = np.ascontiguousarray(np.asarray(charges, dtype=np.float64).reshape(-1))
+        res = np.zeros((self.n, 4))
+        threads = threads or os.cpu_count() or 1
+        rc = self.L.fmmo_laplace_execute(self.h, P, _p(q), _p(res), mode, threads)
+        if rc != 0:
+            raise RuntimeError("oracle execute failed: %d" % rc)
+        self.P = P
+        return res
+
+    def expansions(self):
+        nc = self.P * (self.P + 1) // 2
+        M = np.zeros((self.nboxes, nc, 2))
+        Lx = np.zeros((self.nboxes, nc, 2))
+        self.L.fmmo_get_expansions(self.h, _p(M), _p(Lx))
+        return M, Lx
+
+
+def direct(spts, q, tpts, threads=None):
+    spts = np.ascontiguousarray(np.asarray(spts, dtype=np.float64).reshape(-1, 3))
+    tpts = np.ascontiguousarray(np.asarray(tpts, dtype=np.float64).reshape(-1, 3))
+    q = np.ascontiguousarray(np.asarray(q, dtype=np.float64).reshape(-1))
+    out = np.zeros((tpts.shape[0], 4))
+    load().fmmo_laplace_direct(spts.shape[0], _p(spts), _p(q), tpts.shape[0], _p(tpts), _p(out),
+                               threads or os.cpu_count() or 1)
+    return out
+
+
+def rel_l2(a, b):
+    return float(np.linalg.norm(np.asarray(a) - np.asarray(b)) / np.linalg.norm(np.asarray(b)))
