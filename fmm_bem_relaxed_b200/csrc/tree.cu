@@ -77,6 +77,8 @@ __global__ void morton_codes(const double* __restrict__ pts, int64_t n, double3 
   double vx = __ddiv_rn(__dsub_rn(pts[3 * i], pmin.x), cell.x);
   double vy = __ddiv_rn(__dsub_rn(pts[3 * i + 1], pmin.y), cell.y);
   double vz = __ddiv_rn(__dsub_rn(pts[3 * i + 2], pmin.z), cell.z);
+  // all bodies coincide (zero-size cube): the reference would assert; put them in cell 0 instead
+  if (cell.x == 0.0 && cell.y == 0.0 && cell.z == 0.0) vx = vy = vz = 0.0;
   unsigned qx = (unsigned)vx, qy = (unsigned)vy, qz = (unsigned)vz;
   if (!(vx >= 0.0 && vy >= 0.0 && vz >= 0.0) || qx >= 1024u || qy >= 1024u || qz >= 1024u) {
     atomicOr(err, 1);

@@ -1,0 +1,93 @@
+"""Generates the golden fixtures in this directory from the UNMODIFIED reference.
+
+Run in the build container (needs /root/reference, which does not exist on the GPU box):
+    make -C oracle ref && python tests/golden/make_golden.py
+It runs oracle/_ref/ref_laplace (the reference's own FMM_plan / LaplaceSpherical / Octree /
+EvalInteractionLazy compiled against oracle/boost_shim) single-threaded (the reference's
+multi-threaded M2L loop has a data race) and stores what it dumps.
+"""
+import json
+import os
+import subprocess
+import sys
+import tempfile
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+REF = os.path.join(ROOT, "oracle", "_ref", "ref_laplace")
+
+
+def run_ref(n, p, ncrit, theta, infile=None, dump=None, direct=0):
+    cmd = [REF, "-N", str(n), "-P", str(p), "-ncrit", str(ncrit), "-theta", repr(theta)]
+    if infile:
+        cmd += ["-in", infile]
+    if dump:
+        cmd += ["-dump", dump]
+    if direct:
+        cmd += ["-direct", str(direct)]
+    env = dict(os.environ, OMP_NUM_THREADS="1")
+    out = subprocess.check_output(cmd, env=env).decode()
+    line = [l for l in out.splitlines() if l.startswith("REF_JSON")][0]
+    return json.loads(line[len("REF_JSON "):])
+
+
+def case(name, n, p, ncrit, theta, points=None, charges=None):
+    with tempfile.TemporaryDirectory() as tmp:
+        infile = None
+        if points is not None:
+            infile = os.path.join(tmp, "in.f64")
+            np.concatenate([points.ravel(), charges]).tofile(infile)
+        pre = os.path.join(tmp, "d")
+        meta = run_ref(n, p, ncrit, theta, infile, pre, direct=min(n, 500))
+        nc = p * (p + 1) // 2
+        inp = np.fromfile(pre + ".input.f64")
+        data = dict(
+            meta=json.dumps(meta),
+            points=inp[:3 * n].reshape(n, 3), charges=inp[3 * n:],
+            results=np.fromfile(pre + ".results.f64").reshape(n, 4),
+            perm=np.fromfile(pre + ".perm.u32", np.uint32),
+            codes=np.fromfile(pre + ".codes.u32", np.uint32),
+            boxes=np.fromfile(pre + ".boxes.u32", np.uint32).reshape(-1, 8),
+            geom=np.fromfile(pre + ".geom.f64").reshape(-1, 4),
+            lr=np.fromfile(pre + ".lr.i32", np.int32).reshape(-1, 2),
+            p2p_off=np.fromfile(pre + ".p2p_off.i32", np.int32),
+            p2p_idx=np.fromfile(pre + ".p2p_idx.i32", np.int32),
+            p2m=np.fromfile(pre + ".p2m.i32", np.int32),
+            m2m=np.fromfile(pre + ".m2m.i32", np.int32).reshape(-1, 2),
+            l2l=np.fromfile(pre + ".l2l.i32", np.int32).reshape(-1, 2),
+            l2p=np.fromfile(pre + ".l2p.i32", np.int32),
+            M=np.fromfile(pre + ".M.f64").reshape(-1, nc, 2),
+            L=np.fromfile(pre + ".L.f64").reshape(-1, nc, 2),
+        )
+        np.savez_compressed(os.path.join(HERE, name + ".npz"), **data)
+        print(name, meta["boxes"], "boxes", meta["lr_pairs"], "M2L pairs")
+
+
+def main():
+    if not os.path.exists(REF):
+        sys.exit("oracle/_ref/ref_laplace missing: run `make -C oracle ref` in the build container")
+    # 1. the reference's own test input (drand48 points then charges), small
+    case("laplace_drand48_n3000_p4", 3000, 4, 32, 0.5)
+    # 2. strongly adaptive two-scale cloud, signed charges, non-default theta
+    rng = np.random.default_rng(20261018)
+    n = 4000
+    pts = rng.random((n, 3))
+    pts[n // 2:] = 0.3 + 0.04 * rng.random((n - n // 2, 3))
+    q = rng.random(n) - 0.4
+    case("laplace_two_scale_n4000_p6", n, 6, 12, 0.6, pts, q)
+    # 3. checksums only, larger sizes
+    sums = {}
+    for key, (nn, pp) in {"n10000_p5": (10000, 5), "c1_n100000_p5": (100000, 5)}.items():
+        sums[key] = run_ref(nn, pp, 64, 0.5, direct=1000)
+    if "--full" in sys.argv:
+        sums["cm_n1000000_p8"] = run_ref(1000000, 8, 64, 0.5, direct=1000)
+    path = os.path.join(HERE, "checksums.json")
+    old = json.load(open(path)) if os.path.exists(path) else {}
+    old.update(sums)
+    json.dump(old, open(path, "w"), indent=1, sort_keys=True)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,186 @@
+"""GPU suite (-m gpu): the CUDA engine, called through the C ABI, against the oracle and the
+golden fixtures of the reference.
+
+Tolerances.  Tree, permutation, box table, box geometry and interaction lists: BIT-EXACT
+(integer and double fields).  Floating-point results: relative L2 <= 1e-10 as BASELINE.json's
+north_star states (potential and force separately); in practice the engine agrees to ~1e-15.
+"""
+import json
+
+import numpy as np
+import pytest
+
+import oracle_lib as O
+import fmm_bem_relaxed_b200 as F
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-10
+TREE_KEYS = ("perm", "codes", "boxes", "geom", "lr", "p2p_off", "p2p_idx")
+
+
+def make_plan(points, P, ncrit=64, theta=0.5):
+    opts = F.FMMOptions()
+    opts.set_mac_theta(theta)
+    opts.set_max_per_box(ncrit)
+    return F.FMM_plan(F.LaplaceSpherical(P), points, opts)
+
+
+def assert_parity(res, ref, tol=TOL):
+    assert O.rel_l2(res[:, 0], ref[:, 0]) <= tol
+    assert O.rel_l2(res[:, 1:], ref[:, 1:]) <= tol
+
+
+@pytest.mark.parametrize("which", ["golden_drand48", "golden_two_scale"])
+def test_golden_fixture_tree_bit_exact_and_results(which, request):
+    g = request.getfixturevalue(which)
+    m = json.loads(str(g["meta"]))
+    plan = make_plan(g["points"], m["P"], m["ncrit"], m["theta"])
+    t = plan.tree()
+    for k in TREE_KEYS:
+        assert t[k].shape == g[k].shape, k
+        assert np.array_equal(t[k], g[k]), k
+    i = plan.info()
+    assert (i.n_boxes, i.n_levels, i.n_m2l_pairs, i.n_p2p_box_pairs) == (
+        m["boxes"], m["levels"], m["lr_pairs"], m["p2p_pairs"])
+    res = plan.execute(g["charges"])
+    assert_parity(res, g["results"])
+    M, L = plan.expansions()
+    used = np.abs(g["M"]).sum(axis=(1, 2)) > 0       # the reference only fills multipoles it needs
+    assert O.rel_l2(M[used], g["M"][used]) <= TOL
+    assert O.rel_l2(L, g["L"]) <= TOL
+    # deterministic: a second execute returns the same bits (target ownership, no atomics)
+    assert np.array_equal(plan.execute(g["charges"]), res)
+
+
+@pytest.mark.parametrize("n,P,ncrit,theta", [(10000, 5, 64, 0.5), (20000, 3, 125, 0.5), (5000, 8, 16, 0.7),
+                                             (100000, 5, 64, 0.5)])
+def test_uniform_cube_vs_oracle(n, P, ncrit, theta):
+    pts, q = O.drand48_inputs(n)
+    orc = O.Oracle(pts, ncrit, theta)
+    plan = make_plan(pts, P, ncrit, theta)
+    ot, gt = orc.tree(), plan.tree()
+    for k in TREE_KEYS:
+        assert np.array_equal(gt[k], ot[k]), k
+    assert_parity(plan.execute(q), orc.execute(q, P, mode=0))
+
+
+def test_c1_known_answer_checksums(checksums):
+    """Config C1 of BASELINE.json: N=100k, P=5 against the reference's own checksums."""
+    c = checksums["c1_n100000_p5"]
+    pts, q = O.drand48_inputs(100000)
+    plan = make_plan(pts, 5)
+    res = plan.execute(q)
+    w = (np.arange(100000) % 7 + 1).astype(float)
+    assert abs(res[:, 0].sum() - c["pot"]) <= TOL * abs(c["pot"])
+    assert abs((res[:, 1] * w).sum() - c["fxw"]) <= 1e-8 * abs(c["fxw"])   # signed sum: looser
+    assert np.allclose(res[0], c["r0"], rtol=1e-11, atol=0)
+    d = F.Direct.matvec(plan, q, pts[:1000])
+    assert abs(O.rel_l2(res[:1000, 0], d[:, 0]) - c["err_pot"]) < 1e-8
+    assert abs(O.rel_l2(res[:1000, 1:], d[:, 1:]) - c["err_force"]) < 1e-7
+
+
+def test_per_iteration_p_relaxation():
+    """GMRES calls K.set_p(p) before every matvec (reference examples/BEM/GMRES.hpp:195-201)."""
+    pts, q = O.drand48_inputs(8000)
+    orc = O.Oracle(pts, 64, 0.5)
+    plan = make_plan(pts, 8)
+    for p in (8, 6, 5, 5, 4, 3, 2, 1, 12, 16, 8):
+        plan.kernel().set_p(p)
+        assert plan.info().p == p
+        assert_parity(plan.execute(q), orc.execute(q, p, mode=0))
+
+
+def test_adaptive_clustered_cloud():
+    rng = np.random.default_rng(3)
+    n = 30000
+    pts = rng.random((n, 3))
+    pts[n // 2:] = 0.3 + 0.05 * rng.random((n - n // 2, 3))
+    q = rng.random(n) - 0.3
+    orc = O.Oracle(pts, 20, 0.5)
+    plan = make_plan(pts, 6, 20, 0.5)
+    ot, gt = orc.tree(), plan.tree()
+    for k in TREE_KEYS:
+        assert np.array_equal(gt[k], ot[k]), k
+    assert plan.info().n_levels >= 8
+    assert_parity(plan.execute(q), orc.execute(q, 6, mode=0))
+
+
+def test_sphere_surface_points():
+    rng = np.random.default_rng(5)
+    v = rng.normal(size=(20000, 3))
+    pts = v / np.linalg.norm(v, axis=1)[:, None]
+    q = rng.random(20000)
+    orc = O.Oracle(pts, 64, 0.5)
+    plan = make_plan(pts, 7)
+    assert np.array_equal(plan.tree()["lr"], orc.tree()["lr"])
+    assert_parity(plan.execute(q), orc.execute(q, 7, mode=0))
+
+
+def test_direct_sum_matches_oracle():
+    pts, q = O.drand48_inputs(3000)
+    plan = make_plan(pts, 4)
+    tg = np.vstack([pts[:200], np.array([[3.0, 3.0, 3.0]])])
+    assert O.rel_l2(F.Direct.matvec(plan, q, tg), O.direct(pts, q, tg)) < 1e-13
+
+
+def test_edge_cases():
+    # fewer bodies than ncrit: the root is a leaf, pure P2P
+    pts, q = O.drand48_inputs(50)
+    plan = make_plan(pts, 5)
+    assert plan.info().n_boxes == 1
+    assert O.rel_l2(plan.execute(q), O.direct(pts, q, pts)) < 1e-13
+    # one body: zero (self interaction excluded, LaplaceSpherical.hpp:158)
+    one = make_plan(np.array([[0.2, 0.4, 0.6]]), 5)
+    assert np.all(one.execute(np.array([3.0])) == 0)
+    # coincident bodies are dropped from each other's sums like the reference does
+    pts2 = np.vstack([pts, pts[:5]])
+    q2 = np.concatenate([q, q[:5]])
+    assert_parity(make_plan(pts2, 5).execute(q2), O.Oracle(pts2, 64, 0.5).execute(q2, 5, mode=0))
+    # ncrit = 1 (deep tree) and a huge ncrit
+    pts3, q3 = O.drand48_inputs(600)
+    for ncrit in (1, 100000):
+        assert_parity(make_plan(pts3, 4, ncrit).execute(q3), O.Oracle(pts3, ncrit, 0.5).execute(q3, 4, mode=0))
+    # zero and negative charges
+    assert np.all(make_plan(pts3, 4).execute(np.zeros(600)) == 0)
+    # wrong charge count
+    with pytest.raises(ValueError):
+        plan.execute(np.ones(7))
+
+
+def test_tree_depth_limit_is_an_error_not_a_hang():
+    cl = np.full((100, 3), 0.5) + 1e-9 * np.arange(300).reshape(100, 3)
+    cl = np.vstack([cl, [[0, 0, 0], [1, 1, 1]]])
+    with pytest.raises(F.FmmbError) as e:
+        make_plan(cl, 4, ncrit=8)
+    assert e.value.status == -3
+
+
+def test_metric_config_properties_n1m_p8(checksums):
+    """BASELINE.json metric config (N=1M, P=8): size-independent properties + the reference's
+    known-answer checksums when they were generated (make_golden.py --full)."""
+    n = 1000000
+    pts, q = O.drand48_inputs(n)
+    plan = make_plan(pts, 8)
+    i = plan.info()
+    assert (i.n_boxes, i.n_leaves, i.n_m2l_pairs, i.n_p2p_box_pairs, i.n_p2p_body_pairs) == (
+        37449, 32768, 3873584, 935032, 871763628)
+    res = plan.execute(q)
+    c = checksums.get("cm_n1000000_p8")
+    if c:
+        assert abs(res[:, 0].sum() - c["pot"]) <= TOL * abs(c["pot"])
+        assert np.allclose(res[0], c["r0"], rtol=1e-10, atol=0)
+    # accuracy vs brute force on a target sample matches the reference's own figures
+    d = F.Direct.matvec(plan, q, pts[:1000])
+    assert abs(O.rel_l2(res[:1000, 0], d[:, 0]) - 1.367046e-06) < 1e-9
+    assert abs(O.rel_l2(res[:1000, 1:], d[:, 1:]) - 4.666262e-05) < 1e-8
+    # linearity: A(2q) = 2 A(q) exactly (scaling by 2 is exact in binary floating point)
+    assert np.array_equal(plan.execute(2.0 * q), 2.0 * res)
+    # superposition within rounding
+    rng = np.random.default_rng(1)
+    q2 = rng.random(n) - 0.5
+    r2 = plan.execute(q2)
+    r12 = plan.execute(q + q2)
+    assert O.rel_l2(r12, res + r2) < 1e-12
+    # oracle on a subset of targets is too slow at this size; the sampled leaves' near field is
+    # covered by the Direct comparison above.

@@ -1,0 +1,141 @@
+"""CPU suite: pins oracle/fmm_oracle.cpp (the restatement) to the reference.
+
+Golden fixtures come from the unmodified reference compiled into oracle/_ref
+(tests/golden/make_golden.py); checksums are the known-answer values of SURVEY.md 8(c).
+"""
+import json
+
+import numpy as np
+import pytest
+
+import oracle_lib as O
+
+TREE_KEYS = ("perm", "codes", "boxes", "geom", "lr", "p2p_off", "p2p_idx")
+
+
+def _meta(g):
+    return json.loads(str(g["meta"]))
+
+
+@pytest.mark.parametrize("which", ["golden_drand48", "golden_two_scale"])
+def test_tree_and_lists_bit_exact(which, request):
+    g = request.getfixturevalue(which)
+    m = _meta(g)
+    orc = O.Oracle(g["points"], m["ncrit"], m["theta"])
+    assert orc.error == 0
+    t = orc.tree()
+    for k in TREE_KEYS:
+        assert t[k].shape == g[k].shape, k
+        assert np.array_equal(t[k], g[k]), k          # integer AND floating-point fields bit for bit
+    assert orc.nlevels == m["levels"]
+    assert np.array_equal(orc.call_list(0), g["p2m"])
+    assert np.array_equal(orc.call_list(1), g["m2m"])
+    assert np.array_equal(orc.call_list(2), g["l2l"])
+    assert np.array_equal(orc.call_list(3), g["l2p"])
+
+
+@pytest.mark.parametrize("which", ["golden_drand48", "golden_two_scale"])
+def test_matvec_matches_reference_bitwise(which, request):
+    g = request.getfixturevalue(which)
+    m = _meta(g)
+    orc = O.Oracle(g["points"], m["ncrit"], m["theta"])
+    # mode 0 = the reference's lazy call lists: same operations in the same order
+    res = orc.execute(g["charges"], m["P"], mode=0, threads=1)
+    assert np.array_equal(res, g["results"])
+    M, L = orc.expansions()
+    assert np.array_equal(M, g["M"])
+    assert np.array_equal(L, g["L"])
+    # thread count must not change a single bit (per-target ownership)
+    res4 = orc.execute(g["charges"], m["P"], mode=0, threads=4)
+    assert np.array_equal(res4, g["results"])
+
+
+@pytest.mark.parametrize("which", ["golden_drand48", "golden_two_scale"])
+def test_level_sweep_equals_lazy_lists(which, request):
+    """The CUDA engine runs level sweeps; the reference runs lazily derived call lists
+    (SURVEY.md Q13).  They must agree on the local expansions and the results."""
+    g = request.getfixturevalue(which)
+    m = _meta(g)
+    orc = O.Oracle(g["points"], m["ncrit"], m["theta"])
+    res = orc.execute(g["charges"], m["P"], mode=1)
+    assert O.rel_l2(res, g["results"]) < 1e-14
+    _, L = orc.expansions()
+    assert O.rel_l2(L, g["L"]) < 1e-14
+
+
+def test_drand48_inputs_match_reference(golden_drand48):
+    pts, q = O.drand48_inputs(3000)
+    assert np.array_equal(pts, golden_drand48["points"])
+    assert np.array_equal(q, golden_drand48["charges"])
+    # first draw of the process is X1 = 0xB / 2^48 and lands in z of point 0
+    assert pts[0, 2] == 11.0 / 2.0 ** 48
+
+
+def test_known_answer_checksums_n10000(checksums):
+    c = checksums["n10000_p5"]
+    # values also listed in SURVEY.md section 8(c)
+    assert c["pot"] == 93919201.031089067
+    assert c["fxw"] == -127294.38807026327
+    pts, q = O.drand48_inputs(10000)
+    orc = O.Oracle(pts, 64, 0.5)
+    res = orc.execute(q, 5, mode=0, threads=1)
+    k = np.arange(10000)
+    pot = 0.0
+    fxw = 0.0
+    for i in range(10000):                # same sequential sums as the reference driver
+        pot += res[i, 0]
+        fxw += res[i, 1] * (i % 7 + 1)
+    assert pot == c["pot"]
+    assert fxw == c["fxw"]
+    assert list(res[0]) == c["r0"]
+    assert orc.nboxes == c["boxes"]
+    t = orc.tree()
+    assert len(t["lr"]) == c["lr_pairs"] and len(t["p2p_idx"]) == c["p2p_pairs"]
+    # accuracy vs brute force, as the reference's tests/scaling.cpp reports it
+    d = O.direct(pts, q, pts[:1000])
+    assert abs(O.rel_l2(res[:1000, 0], d[:, 0]) - c["err_pot"]) < 2e-6
+    assert O.rel_l2(res[:1000, 1:], d[:, 1:]) < 2e-3
+
+
+def test_known_answer_checksums_c1(checksums):
+    c = checksums["c1_n100000_p5"]
+    assert c["pot"] == 9432714514.34655 and c["fxw"] == 15721525.037560632
+    pts, q = O.drand48_inputs(100000)
+    orc = O.Oracle(pts, 64, 0.5)
+    res = orc.execute(q, 5, mode=0)
+    assert list(res[0]) == c["r0"]
+    assert abs(res[:, 0].sum() - c["pot"]) <= 1e-12 * abs(c["pot"])
+    w = (np.arange(100000) % 7 + 1).astype(float)
+    assert abs((res[:, 1] * w).sum() - c["fxw"]) <= 1e-9 * abs(c["fxw"])
+    assert (orc.nboxes, len(orc.tree()["lr"])) == (4681, 417728)
+
+
+def test_mac_boundary_decisions_are_rounding_sensitive():
+    """same-level boxes at offset (+-2,0,0) sit exactly on the MAC boundary for
+    theta = 0.5; the restatement must reproduce the reference's rounding, not exact arithmetic."""
+    pts, _ = O.drand48_inputs(20000)
+    t = O.Oracle(pts, 64, 0.5).tree()
+    geom, lr = t["geom"], t["lr"]
+    d = geom[lr[:, 1], :3] - geom[lr[:, 0], :3]
+    side = geom[lr[:, 1], 3]
+    same = geom[lr[:, 0], 3] == side
+    off = np.abs(d[same] / side[same, None])
+    axis2 = (np.sort(off, axis=1)[:, 2] < 2.5) & (np.sort(off, axis=1)[:, 1] < 0.5)
+    # some (not all, not none) of the exactly-distance-2 neighbours are accepted
+    assert axis2.sum() > 0
+
+
+def test_edge_cases():
+    # a single body: root is a leaf, one self P2P pair, result exactly zero (self term excluded)
+    one = O.Oracle(np.array([[0.25, 0.5, 0.75], [0.3, 0.1, 0.2]]), 64, 0.5)
+    res = one.execute(np.array([2.0, 0.0]), 3)
+    assert one.nboxes == 1 and np.all(res[0] == 0.0)
+    # coincident points contribute nothing to each other (R2 < 1e-8 rule)
+    pts = np.array([[0.1, 0.1, 0.1], [0.1, 0.1, 0.1 + 1e-5], [0.9, 0.9, 0.9]])
+    res = O.direct(pts, np.ones(3), pts)
+    far = 1.0 / np.linalg.norm(pts[2] - pts[0])
+    assert abs(res[0, 0] - far) < 1e-9
+    # more than 10 levels needed: reported, not a hang (the reference loops forever)
+    cl = np.full((100, 3), 0.5) + 1e-9 * np.arange(300).reshape(100, 3)
+    cl = np.vstack([cl, [[0, 0, 0], [1, 1, 1]]])
+    assert O.Oracle(cl, 8, 0.5).error == -3
