@@ -1,0 +1,348 @@
+#!/usr/bin/env python
+"""bench.py -- FMM matvecs/s on the BASELINE.json metric config (LaplaceSpherical, N=1M, P=8,
+theta=0.5, ncrit=64, uniform cube, drand48 inputs as in the reference's tests/scaling.cpp).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+One JSON line on stdout (rank 0).  A "step" is one FMM matvec (FMM_plan::execute) over the whole
+point set.
+  value     matvecs/s with charges and results resident in HBM (fmmb_plan_execute_device),
+            per-step CUDA events on the plan stream, L2 flushed between steps.
+  e2e       the same through the host-buffer call fmmb_plan_execute (H2D of the charges and D2H of
+            the results inside the timed region, pinned host memory).
+  roofline  the dominant kernel (M2L) against the FP64 FMA peak measured by a DFMA microbenchmark
+            in the same process (MEASURED_PEAKS.json carries HBM and bf16 only).
+  cpu_baseline  the reference itself (oracle/_ref/ref_laplace, unmodified reference headers
+            compiled with the reference's flags) timed on this host's cores.
+--impl reference times only that CPU implementation.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+METRIC = "fmm_matvecs_per_s"
+UNIT = "matvec/s"
+
+
+def workload(args):
+    return {"workload": "LaplaceSpherical FMM matvec, N=%d uniform cube (drand48), P=%d, theta=%g, ncrit=%d"
+                        % (args.n, args.p, args.theta, args.ncrit),
+            "N": args.n, "P": args.p, "theta": args.theta, "ncrit": args.ncrit}
+
+
+def ref_binary():
+    return os.path.join(ROOT, "oracle", "_ref", "ref_laplace")
+
+
+def run_reference(args, reps, threads=None):
+    """Times the unmodified reference on the host cores.  Returns (dict from REF_JSON, per-execute
+    seconds parsed from its own timing)."""
+    exe = ref_binary()
+    if not os.path.exists(exe):
+        return None
+    threads = threads or os.cpu_count() or 1
+    env = dict(os.environ, OMP_NUM_THREADS=str(threads))
+    cmd = [exe, "-N", str(args.n), "-P", str(args.p), "-ncrit", str(args.ncrit), "-theta", repr(args.theta),
+           "-reps", str(reps)]
+    out = subprocess.check_output(cmd, env=env).decode()
+    line = [l for l in out.splitlines() if l.startswith("REF_JSON")][0]
+    return json.loads(line[len("REF_JSON "):])
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+
+    def __init__(self, index=0):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for l in self.lines:
+            f = [x.strip() for x in l.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, v in zip(names, f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def bench_reference(args, rank, world):
+    if rank != 0:
+        return
+    steps, warmup = args.steps, args.warmup
+    probe = run_reference(args, 1)
+    if probe is None:
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/ref_laplace not built"}))
+        return
+    # bounded: each step is one full matvec of the workload; keep the whole run within ~5 minutes
+    t1 = probe["best_s"] + probe["plan_s"]
+    budget = 300.0
+    max_total = max(1, int((budget - t1) / max(probe["best_s"], 1e-3)))
+    total = min(steps + warmup, max_total)
+    warm = min(warmup, max(0, total - 1))
+    run_steps = total - warm
+    r = run_reference(args, total)
+    # the reference driver reports best and mean over all reps; use the mean of all executes
+    sec = r["mean_s"]
+    val = 1.0 / sec
+    threads = r["threads"]
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": run_steps, "warmup": warm, "ms_per_step": sec * 1e3, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload(args),
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "reference",
+                         "sample": "%d full matvecs of the workload (mean), unmodified reference FMM_plan::execute, "
+                                   "OMP threads=%d; requested steps=%d warmup=%d" % (total, threads, steps, warmup)},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def bench_ours(args, rank, world, local_rank):
+    import numpy as np
+    import torch
+    import oracle_lib as O          # inputs (drand48 restatement) and the cpu_baseline leg only
+    import fmm_bem_relaxed_b200 as F
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the engine has no CPU path")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    pts, q = O.drand48_inputs(args.n)
+    opts = F.FMMOptions()
+    opts.set_mac_theta(args.theta)
+    opts.set_max_per_box(args.ncrit)
+    opts.device = local_rank
+    t0 = time.perf_counter()
+    plan = F.FMM_plan(F.LaplaceSpherical(args.p), pts, opts)
+    plan_s = time.perf_counter() - t0
+    if world > 1:
+        plan.set_partition(rank, world)
+    info = plan.info()
+    n = info.n_bodies
+
+    stream = torch.cuda.ExternalStream(plan.stream(), device=torch.device("cuda", local_rank))
+    d_q = torch.from_numpy(q).cuda()
+    d_res = torch.empty((n, 4), dtype=torch.float64, device="cuda")
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    torch.cuda.synchronize()
+
+    def step_device():
+        plan.execute_device(d_q.data_ptr(), d_res.data_ptr())
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step_device()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    ends = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    phase_acc = {}
+    barrier()
+    for i in range(args.steps):
+        with torch.cuda.stream(stream):
+            flush.zero_()                       # L2 flush, outside the per-step event pair
+            starts[i].record(stream)
+            step_device()
+            ends[i].record(stream)
+    barrier()
+    ms = sum(s.elapsed_time(e) for s, e in zip(starts, ends))
+    clocks = sampler.stop() if rank == 0 else None
+    # per-kernel times for the roofline: a few extra steps with every kernel on ONE stream, so the
+    # CUDA events around M2L / P2P are not disturbed by the concurrent near-field stream
+    plan.set_option("overlap_p2p", 0)
+    phase_acc = {}
+    nser = max(3, min(args.steps, 10))
+    for i in range(nser + 1):
+        with torch.cuda.stream(stream):
+            flush.zero_()
+        step_device()
+        plan.sync()
+        if i > 0:
+            for k, v in plan.phase_times().items():
+                phase_acc[k] = phase_acc.get(k, 0.0) + v
+    phase_acc = {k: v / nser * args.steps for k, v in phase_acc.items()}
+    plan.set_option("overlap_p2p", 1)
+    launches = int(plan.phase_times()["launches"]) * args.steps
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    ms_per_step = ms / args.steps
+    value = 1e3 / ms_per_step
+
+    # end to end through the public host-buffer API (pinned host memory)
+    hq = torch.from_numpy(q).pin_memory()
+    hres = torch.empty((n, 4), dtype=torch.float64).pin_memory()
+    hq_np, hres_np = hq.numpy(), hres.numpy()
+    lib = F.capi.load()
+
+    def step_host():
+        F.capi.check(lib.fmmb_plan_execute(plan._h, F.capi.ptr(hq_np), F.capi.ptr(hres_np)))
+
+    for _ in range(max(1, min(args.warmup, 3))):
+        step_host()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step_host()
+    barrier()
+    e2e_s = (time.perf_counter() - t0) / args.steps
+    te = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_s = float(te.item())
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    # rooflines (algorithmic flops from SURVEY.md section 8(d): 7 P^3 (P+1) per M2L pair, 22 per P2P body pair)
+    P = args.p
+    peak = np.zeros(1)
+    import ctypes
+    pk = ctypes.c_double()
+    F.capi.check(lib.fmmb_measure_fp64_peak(local_rank, ctypes.byref(pk)))
+    fp64_peak = pk.value
+    m2l_ms = phase_acc["m2l"] / args.steps
+    p2p_ms = phase_acc["p2p"] / args.steps
+    m2l_flop = 7.0 * P ** 3 * (P + 1) * info.n_m2l_pairs
+    p2p_flop = 22.0 * info.n_p2p_body_pairs
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    dominant = "m2l" if m2l_ms >= p2p_ms else "p2p"
+    dom_ms, dom_flop = (m2l_ms, m2l_flop) if dominant == "m2l" else (p2p_ms, p2p_flop)
+    roofline = {
+        "kernel": dominant, "bound": "fp64", "achieved": dom_flop / (dom_ms * 1e-3) / 1e12, "peak": fp64_peak,
+        "unit": "TFLOP/s", "frac": dom_flop / (dom_ms * 1e-3) / 1e12 / fp64_peak, "traffic": None,
+        "peak_source": "DFMA microbenchmark in this process (fmmb_measure_fp64_peak); MEASURED_PEAKS.json has no FP64 entry",
+        "algorithmic_flop_per_launch": dom_flop, "ms_per_launch": dom_ms,
+        "hbm_gbs_measured": peaks.get("hbm_gbs"),
+    }
+    others = {
+        "m2l": {"ms": m2l_ms, "tflops_algorithmic": m2l_flop / (m2l_ms * 1e-3) / 1e12,
+                "frac_fp64_peak": m2l_flop / (m2l_ms * 1e-3) / 1e12 / fp64_peak, "pairs": info.n_m2l_pairs},
+        "p2p": {"ms": p2p_ms, "tflops_algorithmic": p2p_flop / (p2p_ms * 1e-3) / 1e12,
+                "frac_fp64_peak": p2p_flop / (p2p_ms * 1e-3) / 1e12 / fp64_peak, "body_pairs": info.n_p2p_body_pairs},
+        "upward_ms": phase_acc["upward"] / args.steps, "downward_ms": phase_acc["downward"] / args.steps,
+        "total_ms": phase_acc["total"] / args.steps,
+    }
+
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        r = run_reference(args, 1)
+        if r is not None:
+            cpu = {"value": 1.0 / r["best_s"], "unit": UNIT, "cores": r["threads"], "kind": "reference",
+                   "sample": "1 full matvec of the same workload by the unmodified reference "
+                             "(oracle/_ref/ref_laplace, FMM_plan::execute, %.2f s; plan %.2f s), OMP threads=%d"
+                             % (r["best_s"], r["plan_s"], r["threads"])}
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": dict(workload(args), l2="256 MiB memset between steps, outside the per-step event pairs",
+                       parallelism="1 GPU" if world == 1 else "target-leaf Morton ranges x%d" % world,
+                       plan_build_s=plan_s, boxes=info.n_boxes, m2l_pairs=info.n_m2l_pairs,
+                       p2p_body_pairs=info.n_p2p_body_pairs),
+        "e2e": {"value": 1.0 / e2e_s, "unit": UNIT, "h2d_bytes_per_step": 8 * n, "d2h_bytes_per_step": 32 * n,
+                "ms_per_step": e2e_s * 1e3},
+        "gpu_launches": launches,
+        "roofline": roofline, "phases": others, "clocks": clocks,
+    }
+    if cpu is not None:
+        line["cpu_baseline"] = cpu
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=None)
+    ap.add_argument("--warmup", type=int, default=None)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--n", type=int, default=1000000)
+    ap.add_argument("--p", type=int, default=8)
+    ap.add_argument("--theta", type=float, default=0.5)
+    ap.add_argument("--ncrit", type=int, default=64)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        if args.steps is None:
+            args.steps = 3
+        if args.warmup is None:
+            args.warmup = 1
+        bench_reference(args, rank, world)
+        return
+    if args.steps is None:
+        args.steps = 20
+    if args.warmup is None:
+        args.warmup = 5
+    args.warmup = max(args.warmup, 3)
+    bench_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

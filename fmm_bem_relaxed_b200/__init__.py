@@ -143,6 +143,9 @@ class FMM_plan:
         capi.check(self._lib.fmmb_plan_execute_device(self._h, ctypes.c_void_p(charges_ptr),
                                                       ctypes.c_void_p(results_ptr)))
 
+    def set_option(self, name, value):
+        capi.check(self._lib.fmmb_plan_set_option(self._h, name.encode(), int(value)))
+
     def sync(self):
         capi.check(self._lib.fmmb_plan_sync(self._h))
 
@@ -158,7 +161,7 @@ class FMM_plan:
         ms = np.zeros(capi.T_COUNT)
         capi.check(self._lib.fmmb_plan_phase_times(self._h, capi.ptr(ms), capi.T_COUNT))
         return {"total": ms[0], "upward": ms[1], "m2l": ms[2], "downward": ms[3], "p2p": ms[4],
-                "h2d": ms[5], "d2h": ms[6]}
+                "h2d": ms[5], "d2h": ms[6], "launches": int(ms[7])}
 
     def tree(self):
         """Copies of the device tree and lists (see include/fmmb.h: fmmb_plan_get_tree)."""

@@ -49,7 +49,7 @@ class PlanInfo(ctypes.Structure):
 # every symbol include/fmmb.h declares
 EXPORTS = [
     "fmmb_plan_create", "fmmb_plan_set_p", "fmmb_plan_execute", "fmmb_plan_execute_device",
-    "fmmb_plan_direct", "fmmb_plan_sync", "fmmb_plan_stream", "fmmb_plan_get_info", "fmmb_plan_get_tree",
+    "fmmb_plan_direct", "fmmb_plan_set_option", "fmmb_plan_sync", "fmmb_plan_stream", "fmmb_plan_get_info", "fmmb_plan_get_tree",
     "fmmb_plan_get_expansions", "fmmb_plan_phase_times", "fmmb_plan_destroy", "fmmb_last_error",
     "fmmb_version", "fmmb_measure_fp64_peak",
 ]
@@ -74,6 +74,7 @@ def load():
     lib.fmmb_plan_execute_device.argtypes = [vp, dp, dp]
     lib.fmmb_plan_direct.argtypes = [vp, dp, i64, dp, dp]
     lib.fmmb_plan_sync.argtypes = [vp]
+    lib.fmmb_plan_set_option.argtypes = [vp, ctypes.c_char_p, i64]
     lib.fmmb_plan_stream.argtypes = [vp]
     lib.fmmb_plan_stream.restype = vp
     lib.fmmb_plan_get_info.argtypes = [vp, ctypes.POINTER(PlanInfo)]

@@ -41,6 +41,7 @@ static void update_phase_times(fmmb_plan* plan) {
   plan->phase_ms[FMMB_T_M2L] = ms(2, 3);
   plan->phase_ms[FMMB_T_DOWNWARD] = ms(3, 4);
   plan->phase_ms[FMMB_T_P2P] = ms(6, 7);
+  plan->phase_ms[FMMB_T_LAUNCHES] = plan->launches;
 }
 }  // namespace fmmb
 
@@ -158,6 +159,14 @@ int fmmb_plan_direct(fmmb_plan* plan, const double* charges_host, int64_t nt, co
     if (nt) FMMB_CUDA(cudaMemcpyAsync(results_host, out.p, 4 * (size_t)nt * sizeof(double), cudaMemcpyDeviceToHost, s));
     FMMB_CUDA(cudaStreamSynchronize(s));
   });
+}
+
+int fmmb_plan_set_option(fmmb_plan* plan, const char* name, int64_t value) {
+  if (!plan || !name) { set_error("null argument"); return FMMB_ERR_INVALID; }
+  if (!std::strcmp(name, "overlap_p2p")) { plan->overlap_p2p = value != 0; return FMMB_OK; }
+  if (!std::strcmp(name, "m2l_mode")) { plan->opts.m2l_mode = (int32_t)value; return FMMB_OK; }
+  set_error(std::string("unknown option: ") + name);
+  return FMMB_ERR_INVALID;
 }
 
 int fmmb_plan_sync(fmmb_plan* plan) {

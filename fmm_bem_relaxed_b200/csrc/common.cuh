@@ -151,6 +151,8 @@ struct fmmb_plan {
   fmmb::DevBuf<double> results;      // original order staging, 4n
   double phase_ms[FMMB_T_COUNT] = {0};
   bool timed = false;
+  bool overlap_p2p = true;
+  int launches = 0;                  // kernel launches of the last execute
 };
 
 namespace fmmb {

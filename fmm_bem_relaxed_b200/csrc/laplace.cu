@@ -536,32 +536,37 @@ void laplace_execute(fmmb_plan* plan, const double* d_charges, double* d_results
   const int P = plan->p, nc = P * (P + 1) / 2, pp = P * P;
   const int nb = T.nboxes;
   const int64_t n = T.n;
-  cudaStream_t s = plan->stream, s2 = plan->stream2;
+  cudaStream_t s = plan->stream, s2 = plan->overlap_p2p ? plan->stream2 : plan->stream;
   plan->M.resize((size_t)nb * nc);
   plan->L.resize((size_t)nb * nc);
   plan->res_near.resize(n);
   plan->res_far.resize(n);
   const double* C = m2l_coeffs(plan, P);
   cudaEvent_t* ev = plan->ev;
+  plan->launches = 0;
 
   FMMB_CUDA(cudaEventRecord(ev[0], s));
   gather_charges<<<nblk(n, 256), 256, 0, s>>>(d_charges, T.perm.p, n, T.body.p);
+  ++plan->launches;
   FMMB_CUDA(cudaEventRecord(ev[1], s));
 
   // near field on the second stream: needs only the charges
-  FMMB_CUDA(cudaStreamWaitEvent(s2, ev[1], 0));
+  if (s2 != s) FMMB_CUDA(cudaStreamWaitEvent(s2, ev[1], 0));
   FMMB_CUDA(cudaEventRecord(ev[6], s2));
   p2p_kernel<<<T.nleaves, kP2PThreads, 0, s2>>>(T.leaves.p, T.nleaves, T.bbegin.p, T.bend.p, T.p2p_off.p,
                                                T.p2p_src.p, T.body.p, plan->res_near.p);
+       ++plan->launches;
   FMMB_CUDA(cudaEventRecord(ev[7], s2));
 
   // upward sweep
   p2m_kernel<<<nblk((int64_t)T.nleaves * 32, 128), 128, 0, s>>>(T.leaves.p, T.nleaves, T.bbegin.p, T.bend.p,
                                                                T.center.p, T.body.p, P, plan->M.p);
+                       ++plan->launches;
   size_t sh_mm = (size_t)(pp + nc) * sizeof(double2);
   for (int l = T.nlevels - 2; l >= 0; --l) {
     int lo = T.level_off[l], hi = T.level_off[l + 1];
     m2m_kernel<<<hi - lo, 64, sh_mm, s>>>(lo, hi, T.key.p, T.cbegin.p, T.cend.p, T.center.p, P, plan->M.p);
+    ++plan->launches;
   }
   FMMB_CUDA(cudaEventRecord(ev[2], s));
 
@@ -574,6 +579,7 @@ void laplace_execute(fmmb_plan* plan, const double* d_charges, double* d_results
     if (red > sh) sh = red;
     m2l_pair_kernel<<<nb, threads, sh, s>>>(nb, T.m2l_off.p, T.m2l_src.p, T.center.p, P, C, plan->M.p,
                                            plan->L.p, 0);
+   ++plan->launches;
   }
   FMMB_CUDA(cudaEventRecord(ev[3], s));
 
@@ -581,15 +587,18 @@ void laplace_execute(fmmb_plan* plan, const double* d_charges, double* d_results
   for (int l = 1; l < T.nlevels; ++l) {
     int lo = T.level_off[l], hi = T.level_off[l + 1];
     l2l_kernel<<<hi - lo, 64, sh_mm, s>>>(lo, hi, T.parent.p, T.has_local.p, T.center.p, P, plan->L.p);
+    ++plan->launches;
   }
   l2p_kernel<<<nblk(T.nleaves, 4), 128, 4 * nc * sizeof(double2), s>>>(T.leaves.p, T.nleaves, T.bbegin.p, T.bend.p,
                                                                      T.center.p, T.has_local.p, T.body.p, P,
                                                                      plan->L.p, plan->res_far.p);
+                             ++plan->launches;
   FMMB_CUDA(cudaEventRecord(ev[4], s));
 
-  FMMB_CUDA(cudaStreamWaitEvent(s, ev[7], 0));
+  if (s2 != s) FMMB_CUDA(cudaStreamWaitEvent(s, ev[7], 0));
   scatter_results<<<nblk(n, 256), 256, 0, s>>>(plan->res_near.p, plan->res_far.p, T.perm.p, n,
                                               reinterpret_cast<double4*>(d_results));
+      ++plan->launches;
   FMMB_CUDA(cudaEventRecord(ev[5], s));
   FMMB_CUDA(cudaGetLastError());
   plan->timed = true;

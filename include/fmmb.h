@@ -102,7 +102,9 @@ typedef struct {
 /* Phase indices for fmmb_plan_phase_times (milliseconds, CUDA events, last execute). */
 enum {
   FMMB_T_TOTAL = 0, FMMB_T_UPWARD = 1, FMMB_T_M2L = 2, FMMB_T_DOWNWARD = 3, FMMB_T_P2P = 4,
-  FMMB_T_H2D = 5, FMMB_T_D2H = 6, FMMB_T_COUNT = 8
+  FMMB_T_H2D = 5, FMMB_T_D2H = 6,
+  FMMB_T_LAUNCHES = 7, /* number of kernel launches of the last execute (a count, not ms) */
+  FMMB_T_COUNT = 8
 };
 
 /* FMM_plan<K>(K, sources, opts): builds the octree and all interaction lists on the device.
@@ -129,6 +131,13 @@ int fmmb_plan_execute_device(fmmb_plan* plan, const double* charges_dev, double*
  * targets: 3*nt doubles (host); results: nt*result_dim doubles (host). */
 int fmmb_plan_direct(fmmb_plan* plan, const double* charges_host, int64_t nt,
                      const double* targets_host, double* results_host);
+
+/* Engine knobs that have no counterpart in the reference (all default to the fast setting):
+ *   "overlap_p2p"  1 = near field runs on a second stream concurrently with the far field (default),
+ *                  0 = every kernel on one stream, so per-kernel CUDA-event times are undisturbed
+ *                      (used by bench.py for the roofline figures).
+ *   "m2l_mode"     see fmmb_options.m2l_mode. */
+int fmmb_plan_set_option(fmmb_plan* plan, const char* name, int64_t value);
 
 int fmmb_plan_sync(fmmb_plan* plan);
 void* fmmb_plan_stream(fmmb_plan* plan); /* cudaStream_t */
