@@ -88,6 +88,7 @@ int fmmb_plan_create(const fmmb_kernel_desc* kernel, const fmmb_sources* sources
     for (auto& e : plan->ev) FMMB_CUDA(cudaEventCreate(&e));
     laplace_init_tables(plan);
     build_tree(plan, sources->points, sources->n);
+    build_m2l_classes(plan);
   });
   if (rc != FMMB_OK) { fmmb_plan_destroy(plan); return rc; }
   *out_plan = plan;

@@ -108,21 +108,22 @@ struct Tree {
   int64_t n_p2p = 0, n_p2p_body_pairs = 0;
 };
 
-// Batched-M2L structures (built by m2l_classes.cu)
+// Batched-M2L structures (built by m2l_classes.cu).  "slot" = position of a pair in the
+// target-major CSR (Tree::m2l_src); the scratch columns of phase 1 are indexed by slot.
 struct M2LClasses {
-  int64_t n_classes = 0;
+  int64_t n_classes = 0;             // distinct translation vectors
   int64_t n_pairs = 0;               // pairs covered by the batched path
+  int64_t n_res = 0;                 // pairs left to the per-pair kernel
+  int n_items = 0;                   // (class, <=128 pairs) GEMM tiles
   int built_p = 0;                   // order the matrices were built for (0 = none)
-  DevBuf<double> T;                  // n_classes * built_p^2 * built_p^2 real translation matrices
+  DevBuf<double> T;                  // [class][k][row], leading dimension built_p^2
   DevBuf<double4> class_vec;         // representative translation vector per class
-  // work items: (tile, class) groups
-  DevBuf<int> item_class, item_off;  // per item: class id, offset into pair arrays (n_items+1)
-  DevBuf<int> pair_tgt, pair_src;    // per pair: target box, source box
-  DevBuf<int> tile_item_off;         // per target tile: range of items
-  int n_items = 0, n_tiles = 0;
-  // residual pairs that stay on the per-pair kernel (target-major CSR)
-  DevBuf<int> res_off, res_src;
-  int64_t n_res = 0;
+  DevBuf<int> slot_tgt;              // target box of each slot
+  DevBuf<int> sorted_slot;           // slots ordered by class (stable: target-major inside a class)
+  DevBuf<int> item_class, item_start, item_count;
+  DevBuf<unsigned char> batched;     // per slot: handled by the batched path
+  DevBuf<int> res_off, res_src;      // residual pairs, target-major CSR in list order
+  DevBuf<double> tmp;                // phase-1 output columns, [slot][p^2]
 };
 
 struct LaplaceTables {
@@ -164,4 +165,8 @@ void laplace_execute(fmmb_plan* plan, const double* d_charges, double* d_results
 void laplace_direct_raw(const double* d_spts, const double* d_q, int64_t ns, const double* d_tpts, int64_t nt,
                         double* d_out, cudaStream_t s);
 double measure_fp64_peak();
+// m2l_classes.cu
+void m2l_init_tables();
+void build_m2l_classes(fmmb_plan* plan);
+bool m2l_batched(fmmb_plan* plan, cudaStream_t s);
 }  // namespace fmmb

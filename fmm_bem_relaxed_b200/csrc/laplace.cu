@@ -16,13 +16,10 @@
 // cos/sin of the polar angle come from z/r and sqrt((1-x)(1+x)) instead of cos(acos(.)), and
 // exp(i m phi) from (x+iy)/|xy| by recurrence; sums run in a different order.
 #include "common.cuh"
+#include "laplace_tables.cuh"
 #include <cmath>
 
 namespace fmmb {
-
-// sqrt((n-|m|)!/(n+|m|)!) and (-1)^n/sqrt((n-m)!(n+m)!), index n^2+n+m, n < 2*FMMB_MAX_P
-__constant__ double c_pref[4 * FMMB_MAX_P * FMMB_MAX_P];
-__constant__ double c_anm[4 * FMMB_MAX_P * FMMB_MAX_P];
 
 namespace {
 
@@ -500,21 +497,8 @@ inline int nblk(int64_t n, int t) { return (int)((n + t - 1) / t); }
 }  // namespace
 
 void laplace_init_tables(fmmb_plan* plan) {
-  const int top = 2 * FMMB_MAX_P;
-  std::vector<double> pref(top * top), anm(top * top);
-  for (int n = 0; n < top; ++n)
-    for (int m = -n; m <= n; ++m) {
-      int nm = n * n + n + m, am = std::abs(m);
-      double fnmm = 1, fnpm = 1, fnma = 1, fnpa = 1;
-      for (int i = 1; i <= n - m; ++i) fnmm *= i;
-      for (int i = 1; i <= n + m; ++i) fnpm *= i;
-      for (int i = 1; i <= n - am; ++i) fnma *= i;
-      for (int i = 1; i <= n + am; ++i) fnpa *= i;
-      pref[nm] = std::sqrt(fnma / fnpa);
-      anm[nm] = ((n & 1) ? -1.0 : 1.0) / std::sqrt(fnmm * fnpm);
-    }
-  FMMB_CUDA(cudaMemcpyToSymbol(c_pref, pref.data(), pref.size() * sizeof(double)));
-  FMMB_CUDA(cudaMemcpyToSymbol(c_anm, anm.data(), anm.size() * sizeof(double)));
+  upload_laplace_tables();
+  m2l_init_tables();
   plan->tab.pmax = FMMB_MAX_P;
 }
 
@@ -570,16 +554,23 @@ void laplace_execute(fmmb_plan* plan, const double* d_charges, double* d_results
   }
   FMMB_CUDA(cudaEventRecord(ev[2], s));
 
-  // far field translations
+  // far field translations: batched translation classes, then the per-pair kernel for the rest
   {
     int threads = 128;
     while (threads < nc) threads += 32;
     size_t sh = (size_t)(5 * pp) * sizeof(double2);
     size_t red = (size_t)(threads / nc) * nc * sizeof(double2);
     if (red > sh) sh = red;
-    m2l_pair_kernel<<<nb, threads, sh, s>>>(nb, T.m2l_off.p, T.m2l_src.p, T.center.p, P, C, plan->M.p,
-                                           plan->L.p, 0);
-   ++plan->launches;
+    bool batched = plan->opts.m2l_mode != 1 && m2l_batched(plan, s);
+    if (!batched) {
+      m2l_pair_kernel<<<nb, threads, sh, s>>>(nb, T.m2l_off.p, T.m2l_src.p, T.center.p, P, C, plan->M.p,
+                                             plan->L.p, 0);
+      ++plan->launches;
+    } else if (plan->cls.n_res > 0) {
+      m2l_pair_kernel<<<nb, threads, sh, s>>>(nb, plan->cls.res_off.p, plan->cls.res_src.p, T.center.p, P, C,
+                                             plan->M.p, plan->L.p, 1);
+      ++plan->launches;
+    }
   }
   FMMB_CUDA(cudaEventRecord(ev[3], s));
 

@@ -14,6 +14,7 @@ def run(n, P, ncrit=64, theta=0.5, pts=None, q=None, label=""):
     t = time.time(); plan = F.FMM_plan(F.LaplaceSpherical(P), pts, opts); t_pl = time.time() - t
     gt = plan.tree()
     i = plan.info()
+    print("   m2l classes %d, batched pairs %d of %d" % (i.n_m2l_classes, i.n_m2l_pairs_batched, i.n_m2l_pairs))
     print("== %s N=%d P=%d ncrit=%d: boxes %d levels %d lr %d p2p %d bodypairs %d | plan %.3fs (oracle tree %.3fs)" % (
         label, n, P, ncrit, i.n_boxes, i.n_levels, i.n_m2l_pairs, i.n_p2p_box_pairs, i.n_p2p_body_pairs, t_pl, t_or))
     ok = True
