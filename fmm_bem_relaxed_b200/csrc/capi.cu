@@ -37,7 +37,7 @@ static void update_phase_times(fmmb_plan* plan) {
     return (double)t;
   };
   plan->phase_ms[FMMB_T_TOTAL] = ms(0, 5);
-  plan->phase_ms[FMMB_T_UPWARD] = ms(0, 2);
+  plan->phase_ms[FMMB_T_UPWARD] = ms(12, 2);
   plan->phase_ms[FMMB_T_M2L] = ms(2, 3);
   plan->phase_ms[FMMB_T_DOWNWARD] = ms(3, 4);
   plan->phase_ms[FMMB_T_P2P] = ms(6, 7);
@@ -235,10 +235,24 @@ int fmmb_plan_get_expansions(fmmb_plan* plan, double* multipoles, double* locals
     FMMB_CUDA(cudaSetDevice(plan->device));
     cudaStream_t s = plan->stream;
     FMMB_CUDA(cudaStreamSynchronize(s));
-    size_t bytes = (size_t)plan->tree.nboxes * (plan->p * (plan->p + 1) / 2) * sizeof(double2);
-    if (multipoles && plan->M.n) FMMB_CUDA(cudaMemcpyAsync(multipoles, plan->M.p, bytes, cudaMemcpyDeviceToHost, s));
-    if (locals && plan->L.n) FMMB_CUDA(cudaMemcpyAsync(locals, plan->L.p, bytes, cudaMemcpyDeviceToHost, s));
-    FMMB_CUDA(cudaStreamSynchronize(s));
+    // device layout: P^2 reals per box (stride padded to even); API layout: packed complex
+    const int P = plan->p, pp = P * P, xs = (pp + 1) & ~1, nc = P * (P + 1) / 2;
+    const size_t nb = plan->tree.nboxes;
+    auto convert = [&](const DevBuf<double>& X, double* out) {
+      if (!out || X.n < nb * xs) return;
+      std::vector<double> h(nb * xs);
+      FMMB_CUDA(cudaMemcpyAsync(h.data(), X.p, h.size() * sizeof(double), cudaMemcpyDeviceToHost, s));
+      FMMB_CUDA(cudaStreamSynchronize(s));
+      for (size_t b = 0; b < nb; ++b)
+        for (int n = 0; n < P; ++n)
+          for (int m = 0; m <= n; ++m) {
+            size_t o = 2 * (b * nc + n * (n + 1) / 2 + m);
+            out[o] = h[b * xs + n * n + n + m];
+            out[o + 1] = m > 0 ? h[b * xs + n * n + n - m] : 0.0;
+          }
+    };
+    convert(plan->M, multipoles);
+    convert(plan->L, locals);
   });
 }
 

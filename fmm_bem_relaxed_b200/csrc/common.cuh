@@ -108,21 +108,25 @@ struct Tree {
   int64_t n_p2p = 0, n_p2p_body_pairs = 0;
 };
 
-// Batched-M2L structures (built by m2l_classes.cu).  "slot" = position of a pair in the
-// target-major CSR (Tree::m2l_src); the scratch columns of phase 1 are indexed by slot.
-struct M2LClasses {
+// One family of box-to-box translations (M2L, M2M or L2L) evaluated as class-batched GEMMs
+// (built by m2l_classes.cu).  "slot" = position of a pair in the family's slot space: for M2L the
+// index into the target-major CSR (Tree::m2l_src); for M2M/L2L the child box index.
+struct TransBatch {
+  int kind = 0;                      // 0 = M2L, 1 = M2M, 2 = L2L
   int64_t n_classes = 0;             // distinct translation vectors
   int64_t n_pairs = 0;               // pairs covered by the batched path
-  int64_t n_res = 0;                 // pairs left to the per-pair kernel
+  int64_t n_res = 0;                 // M2L pairs left to the per-pair kernel
   int n_items = 0;                   // (class, <=128 pairs) GEMM tiles
   int built_p = 0;                   // order the matrices were built for (0 = none)
   DevBuf<double> T;                  // [class][k][row], leading dimension built_p^2
   DevBuf<double4> class_vec;         // representative translation vector per class
-  DevBuf<int> slot_tgt;              // target box of each slot
-  DevBuf<int> sorted_slot;           // slots ordered by class (stable: target-major inside a class)
+  DevBuf<int> slot_tgt, slot_src;    // target / source box of each slot
+  const int* slot_src_p = nullptr;   // = slot_src.p, or Tree::m2l_src.p for M2L
+  DevBuf<int> sorted_slot;           // slots ordered by class (stable: slot order inside a class)
   DevBuf<int> item_class, item_start, item_count;
-  DevBuf<unsigned char> batched;     // per slot: handled by the batched path
-  DevBuf<int> res_off, res_src;      // residual pairs, target-major CSR in list order
+  std::vector<int> level_item_off;   // M2M/L2L: items whose target level is l
+  DevBuf<unsigned char> batched;     // M2L, per slot: handled by the batched path
+  DevBuf<int> res_off, res_src;      // M2L residual pairs, target-major CSR in list order
   DevBuf<double> tmp;                // phase-1 output columns, [slot][p^2]
 };
 
@@ -141,12 +145,12 @@ struct fmmb_plan {
   int p_alloc = 0;                   // order the expansion buffers are sized for
   fmmb_options opts;
   cudaStream_t stream = nullptr, stream2 = nullptr;
-  cudaEvent_t ev[12];
+  cudaEvent_t ev[16];
   fmmb::Tree tree;
   fmmb::LaplaceTables tab;
-  fmmb::M2LClasses cls;
+  fmmb::TransBatch cls, m2m, l2l;    // batched M2L / M2M / L2L
   std::map<int, fmmb::DevBuf<double>*> m2l_coeff;  // per-order real M2L coefficient tables
-  fmmb::DevBuf<double2> M, L;        // box-major, nc(p) complex per box
+  fmmb::DevBuf<double> M, L;         // box-major, real layout (laplace_ops.cuh), stride xstride(p)
   fmmb::DevBuf<double> charges;      // original order staging
   fmmb::DevBuf<double4> res_near, res_far;  // tree order
   fmmb::DevBuf<double> results;      // original order staging, 4n
@@ -169,4 +173,6 @@ double measure_fp64_peak();
 void m2l_init_tables();
 void build_m2l_classes(fmmb_plan* plan);
 bool m2l_batched(fmmb_plan* plan, cudaStream_t s);
+bool m2m_batched(fmmb_plan* plan, cudaStream_t s);
+bool l2l_batched(fmmb_plan* plan, cudaStream_t s);
 }  // namespace fmmb

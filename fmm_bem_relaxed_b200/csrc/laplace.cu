@@ -16,108 +16,14 @@
 // cos/sin of the polar angle come from z/r and sqrt((1-x)(1+x)) instead of cos(acos(.)), and
 // exp(i m phi) from (x+iy)/|xy| by recurrence; sums run in a different order.
 #include "common.cuh"
-#include "laplace_tables.cuh"
+#include "laplace_ops.cuh"
 #include <cmath>
 
 namespace fmmb {
 
 namespace {
 
-constexpr double kEps = 1e-12;
-
-struct Sph { double r, x, y, cp, sp; };
-
-// cart2sph (LaplaceSpherical.hpp:528-541) without the inverse trig round trip
-__device__ __forceinline__ Sph to_sph(double dx, double dy, double dz) {
-  Sph s;
-  s.r = sqrt(dx * dx + dy * dy + dz * dz) + kEps;
-  s.x = __ddiv_rn(dz, s.r);
-  s.y = sqrt((1.0 - s.x) * (1.0 + s.x));
-  double ax = fabs(dx), ay = fabs(dy);
-  if (ax + ay < kEps) { s.cp = 1.0; s.sp = 0.0; }
-  else if (ax < kEps) { s.cp = 0.0; s.sp = dy > 0 ? 1.0 : -1.0; }
-  else { double h = sqrt(dx * dx + dy * dy); s.cp = dx / h; s.sp = dy / h; }
-  return s;
-}
-
-// All rho^n Y_n^m, 0 <= m <= n < P, visited m-major exactly like evalMultipole (:455-488).
-// f(n, m, Yre, Yim, Ytre, Ytim); sign = +1 for e^{+i m phi}, -1 for e^{-i m phi}.
-template <bool THETA, typename F>
-__device__ __forceinline__ void regular_harmonics(int P, const Sph& s, double sign, F&& f) {
-  double fact = 1, pn = 1, rhom = 1;
-  double er = 1, ei = 0;
-  const double cp = s.cp, sp = sign * s.sp;
-  for (int m = 0; m < P; ++m) {
-    double p = pn;
-    int npn = m * m + 2 * m;
-    double a = rhom * p * c_pref[npn];
-    double p1 = p;
-    p = s.x * (2 * m + 1) * p1;
-    double at = 0;
-    if (THETA) at = rhom * (p - (m + 1) * s.x * p1) / s.y * c_pref[npn];
-    f(m, m, a * er, a * ei, at * er, at * ei);
-    rhom *= s.r;
-    double rhon = rhom;
-    for (int n = m + 1; n < P; ++n) {
-      int npm = n * n + n + m;
-      a = rhon * p * c_pref[npm];
-      double p2 = p1;
-      p1 = p;
-      p = (s.x * (2 * n + 1) * p1 - (n + m) * p2) / (n - m + 1);
-      if (THETA) at = rhon * ((n - m + 1) * p - (n + 1) * s.x * p1) / s.y * c_pref[npm];
-      f(n, m, a * er, a * ei, at * er, at * ei);
-      rhon *= s.r;
-    }
-    pn = -pn * fact * s.y;
-    fact += 2;
-    double t = er * cp - ei * sp;
-    ei = er * sp + ei * cp;
-    er = t;
-  }
-}
-
-// One column (fixed m >= 0) of the harmonics table, written for +m and -m (conjugate).
-// SINGULAR: rho^{-n-1} Y_n^m for n < top (evalLocal :491-524); else rho^n Y_n^m.
-template <bool SINGULAR>
-__device__ __forceinline__ void harmonics_column(int m, int top, const Sph& s, double sign, double2* Y) {
-  double pn = 1, fact = 1, er = 1, ei = 0;
-  double rhom = SINGULAR ? 1.0 / s.r : 1.0;
-  const double cp = s.cp, sp = sign * s.sp;
-  for (int k = 0; k < m; ++k) {
-    pn = -pn * fact * s.y;
-    fact += 2;
-    double t = er * cp - ei * sp;
-    ei = er * sp + ei * cp;
-    er = t;
-    if (SINGULAR) rhom /= s.r; else rhom *= s.r;
-  }
-  double p = pn;
-  int npn = m * m + 2 * m, nmn = m * m;
-  double a = rhom * p * c_pref[npn];
-  Y[npn] = make_double2(a * er, a * ei);
-  Y[nmn] = make_double2(a * er, -a * ei);
-  double p1 = p;
-  p = s.x * (2 * m + 1) * p1;
-  if (SINGULAR) rhom /= s.r; else rhom *= s.r;
-  double rhon = rhom;
-  for (int n = m + 1; n < top; ++n) {
-    int npm = n * n + n + m, nmm = n * n + n - m;
-    a = rhon * p * c_pref[npm];
-    Y[npm] = make_double2(a * er, a * ei);
-    Y[nmm] = make_double2(a * er, -a * ei);
-    double p2 = p1;
-    p1 = p;
-    p = (s.x * (2 * n + 1) * p1 - (n + m) * p2) / (n - m + 1);
-    if (SINGULAR) rhon /= s.r; else rhon *= s.r;
-  }
-}
-
-__device__ __forceinline__ double warp_sum(double v) {
-#pragma unroll
-  for (int s = 16; s > 0; s >>= 1) v += __shfl_xor_sync(0xffffffffu, v, s);
-  return v;
-}
-__device__ __forceinline__ double oddeven(int n) { return (n & 1) ? -1.0 : 1.0; }
+using namespace ops;
 
 // ---- charges into tree order ------------------------------------------------------------------
 __global__ void gather_charges(const double* __restrict__ q, const unsigned* __restrict__ perm, int64_t n,
@@ -130,14 +36,14 @@ __global__ void gather_charges(const double* __restrict__ q, const unsigned* __r
 __global__ void __launch_bounds__(128)
 p2m_kernel(const int* __restrict__ leaves, int nleaves, const unsigned* __restrict__ bb,
            const unsigned* __restrict__ be, const double4* __restrict__ center,
-           const double4* __restrict__ body, int P, double2* __restrict__ M) {
+           const double4* __restrict__ body, int P, double* __restrict__ M) {
   int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (w >= nleaves) return;
   int b = leaves[w];
   const int nc = P * (P + 1) / 2;
   double4 c = center[b];
   unsigned b0 = bb[b], b1 = be[b];
-  double2* Mb = M + (size_t)b * nc;
+  double* Mb = M + (size_t)b * xstride(P);
   for (unsigned base = b0; base < b1; base += 32) {
     unsigned i = base + lane;
     double q = 0;
@@ -151,9 +57,8 @@ p2m_kernel(const int* __restrict__ leaves, int nleaves, const unsigned* __restri
     regular_harmonics<false>(P, s, -1.0, [&](int n, int m, double yr, double yi, double, double) {
       double vr = warp_sum(q * yr), vi = warp_sum(q * yi);
       if (lane == 0) {
-        int nms = n * (n + 1) / 2 + m;
-        if (first) Mb[nms] = make_double2(vr, vi);
-        else { double2 o = Mb[nms]; Mb[nms] = make_double2(o.x + vr, o.y + vi); }
+        if (first) store_coef(Mb, n, m, make_double2(vr, vi));
+        else add_coef(Mb, n, m, make_double2(vr, vi));
       }
     });
   }
@@ -163,7 +68,7 @@ p2m_kernel(const int* __restrict__ leaves, int nleaves, const unsigned* __restri
 __global__ void __launch_bounds__(64)
 m2m_kernel(int lo, int hi, const unsigned* __restrict__ key, const unsigned* __restrict__ cbegin,
            const unsigned* __restrict__ cend, const double4* __restrict__ center, int P,
-           double2* __restrict__ M) {
+           double* __restrict__ M) {
   int b = lo + blockIdx.x;
   if (b >= hi || (key[b] >> 31)) return;   // leaves got their multipole from P2M
   extern __shared__ double2 sh[];
@@ -171,50 +76,24 @@ m2m_kernel(int lo, int hi, const unsigned* __restrict__ key, const unsigned* __r
   double2* Y = sh;          // pp
   double2* Ms = sh + pp;    // nc
   double4 cpar = center[b];
-  for (int jks = threadIdx.x; jks < nc; jks += blockDim.x) M[(size_t)b * nc + jks] = make_double2(0, 0);
+  const int xs = xstride(P);
+  for (int r = threadIdx.x; r < pp; r += blockDim.x) M[(size_t)b * xs + r] = 0.0;
   for (unsigned c = cbegin[b]; c < cend[b]; ++c) {
     double4 cc = center[c];
     Sph s = to_sph(cpar.x - cc.x, cpar.y - cc.y, cpar.z - cc.z);
     __syncthreads();
     for (int m = threadIdx.x; m < P; m += blockDim.x) harmonics_column<false>(m, P, s, -1.0, Y);
-    for (int i = threadIdx.x; i < nc; i += blockDim.x) Ms[i] = M[(size_t)c * nc + i];
+    for (int i = threadIdx.x; i < nc; i += blockDim.x) {
+      int n, m;
+      unpack_nm(i, n, m);
+      Ms[i] = load_coef(M + (size_t)c * xs, n, m);
+    }
     __syncthreads();
     for (int jks = threadIdx.x; jks < nc; jks += blockDim.x) {
-      int j = (int)((sqrt(8.0 * jks + 1.0) - 1.0) * 0.5);
-      while (j * (j + 1) / 2 > jks) --j;
-      while ((j + 1) * (j + 2) / 2 <= jks) ++j;
-      int k = jks - j * (j + 1) / 2;
-      int jk = j * j + j + k;
-      double inv_ajk = 1.0 / c_anm[jk];
-      double ar = 0, ai = 0;
-      for (int n = 0; n <= j; ++n) {
-        int mtop = min(k - 1, n);
-        for (int m = -n; m <= mtop; ++m) {
-          if (j - n >= k - m) {
-            int jnkm = (j - n) * (j - n) + j - n + k - m;
-            int jnkms = (j - n) * (j - n + 1) / 2 + k - m;
-            int nm = n * n + n + m;
-            // i^(m-|m|) = (-1)^m for m < 0, 1 otherwise
-            double f = ((m < 0 && (m & 1)) ? -1.0 : 1.0) * oddeven(n) * c_anm[nm] * c_anm[jnkm] * inv_ajk;
-            double2 a = Ms[jnkms], y = Y[nm];
-            ar += f * (a.x * y.x - a.y * y.y);
-            ai += f * (a.x * y.y + a.y * y.x);
-          }
-        }
-        for (int m = k; m <= n; ++m) {
-          if (j - n >= m - k) {
-            int jnkm = (j - n) * (j - n) + j - n + k - m;
-            int jnkms = (j - n) * (j - n + 1) / 2 - k + m;
-            int nm = n * n + n + m;
-            double f = oddeven(k + n + m) * c_anm[nm] * c_anm[jnkm] * inv_ajk;
-            double2 a = Ms[jnkms], y = Y[nm];   // conj(a) * y
-            ar += f * (a.x * y.x + a.y * y.y);
-            ai += f * (a.x * y.y - a.y * y.x);
-          }
-        }
-      }
-      double2 o = M[(size_t)b * nc + jks];
-      M[(size_t)b * nc + jks] = make_double2(o.x + ar, o.y + ai);
+      int j, k;
+      unpack_nm(jks, j, k);
+      double2 v = m2m_entry(Ms, Y, j, k);
+      add_coef(M + (size_t)b * xs, j, k, v);
     }
   }
 }
@@ -239,7 +118,7 @@ __global__ void m2l_coeff_kernel(int P, double* __restrict__ C) {
 __global__ void __launch_bounds__(256)
 m2l_pair_kernel(int nboxes, const int* __restrict__ off, const int* __restrict__ src,
                 const double4* __restrict__ center, int P, const double* __restrict__ C,
-                const double2* __restrict__ M, double2* __restrict__ L, int accumulate) {
+                const double* __restrict__ M, double* __restrict__ L, int accumulate) {
   int b = blockIdx.x;
   if (b >= nboxes) return;
   extern __shared__ double2 sh[];
@@ -264,7 +143,7 @@ m2l_pair_kernel(int nboxes, const int* __restrict__ off, const int* __restrict__
     for (int nm = threadIdx.x; nm < pp; nm += blockDim.x) {
       int n = 0; while ((n + 1) * (n + 1) <= nm) ++n;
       int m = nm - n * n - n;
-      double2 v = M[(size_t)sb * nc + n * (n + 1) / 2 + abs(m)];
+      double2 v = load_coef(M + (size_t)sb * xstride(P), n, abs(m));
       if (m < 0) v.y = -v.y;
       Mf[nm] = v;
     }
@@ -291,16 +170,16 @@ m2l_pair_kernel(int nboxes, const int* __restrict__ off, const int* __restrict__
   if (threadIdx.x < nc) {
     double rr = 0, ri = 0;
     for (int q = 0; q < groups; ++q) { rr += red[q * nc + threadIdx.x].x; ri += red[q * nc + threadIdx.x].y; }
-    size_t o = (size_t)b * nc + threadIdx.x;
-    if (accumulate) { double2 old = L[o]; rr += old.x; ri += old.y; }
-    L[o] = make_double2(rr, ri);
+    double* Lb = L + (size_t)b * xstride(P);
+    if (accumulate) add_coef(Lb, j, k, make_double2(rr, ri));
+    else store_coef(Lb, j, k, make_double2(rr, ri));
   }
 }
 
 // ---- L2L: block per child box of one level -------------------------------------------------------
 __global__ void __launch_bounds__(64)
 l2l_kernel(int lo, int hi, const unsigned* __restrict__ parent, const unsigned char* __restrict__ has_local,
-           const double4* __restrict__ center, int P, double2* __restrict__ L) {
+           const double4* __restrict__ center, int P, double* __restrict__ L) {
   int b = lo + blockIdx.x;
   if (b >= hi) return;
   int par = parent[b];
@@ -312,37 +191,18 @@ l2l_kernel(int lo, int hi, const unsigned* __restrict__ parent, const unsigned c
   double4 cc = center[b], cp = center[par];
   Sph s = to_sph(cc.x - cp.x, cc.y - cp.y, cc.z - cp.z);
   for (int m = threadIdx.x; m < P; m += blockDim.x) harmonics_column<false>(m, P, s, 1.0, Y);
-  for (int i = threadIdx.x; i < nc; i += blockDim.x) Ls[i] = L[(size_t)par * nc + i];
+  const int xs = xstride(P);
+  for (int i = threadIdx.x; i < nc; i += blockDim.x) {
+    int n, m;
+    unpack_nm(i, n, m);
+    Ls[i] = load_coef(L + (size_t)par * xs, n, m);
+  }
   __syncthreads();
   for (int jks = threadIdx.x; jks < nc; jks += blockDim.x) {
-    int j = 0; while ((j + 1) * (j + 2) / 2 <= jks) ++j;
-    int k = jks - j * (j + 1) / 2;
-    int jk = j * j + j + k;
-    double ajk = c_anm[jk];
-    double ar = 0, ai = 0;
-    for (int n = j; n < P; ++n) {
-      for (int m = j + k - n; m < 0; ++m) {
-        int jnkm = (n - j) * (n - j) + n - j + m - k;
-        int nm = n * n + n - m, nms = n * (n + 1) / 2 - m;
-        double f = oddeven(k) * c_anm[jnkm] * ajk / c_anm[nm];
-        double2 a = Ls[nms], y = Y[jnkm];       // conj(a) * y
-        ar += f * (a.x * y.x + a.y * y.y);
-        ai += f * (a.x * y.y - a.y * y.x);
-      }
-      for (int m = 0; m <= n; ++m) {
-        if (n - j >= abs(m - k)) {
-          int jnkm = (n - j) * (n - j) + n - j + m - k;
-          int nm = n * n + n + m, nms = n * (n + 1) / 2 + m;
-          // i^(m-k-|m-k|) = (-1)^(m-k) for m < k, 1 otherwise
-          double f = ((m < k && ((k - m) & 1)) ? -1.0 : 1.0) * c_anm[jnkm] * ajk / c_anm[nm];
-          double2 a = Ls[nms], y = Y[jnkm];
-          ar += f * (a.x * y.x - a.y * y.y);
-          ai += f * (a.x * y.y + a.y * y.x);
-        }
-      }
-    }
-    double2 o = L[(size_t)b * nc + jks];
-    L[(size_t)b * nc + jks] = make_double2(o.x + ar, o.y + ai);
+    int j, k;
+    unpack_nm(jks, j, k);
+    double2 v = l2l_entry(Ls, Y, j, k, P);
+    add_coef(L + (size_t)b * xs, j, k, v);
   }
 }
 
@@ -351,7 +211,7 @@ __global__ void __launch_bounds__(128)
 l2p_kernel(const int* __restrict__ leaves, int nleaves, const unsigned* __restrict__ bb,
            const unsigned* __restrict__ be, const double4* __restrict__ center,
            const unsigned char* __restrict__ has_local, const double4* __restrict__ body, int P,
-           const double2* __restrict__ L, double4* __restrict__ res) {
+           const double* __restrict__ L, double4* __restrict__ res) {
   extern __shared__ double2 sh[];
   const int nc = P * (P + 1) / 2;
   int wl = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -364,7 +224,11 @@ l2p_kernel(const int* __restrict__ leaves, int nleaves, const unsigned* __restri
     return;
   }
   double2* Ls = sh + wl * nc;
-  for (int i = lane; i < nc; i += 32) Ls[i] = L[(size_t)b * nc + i];
+  for (int i = lane; i < nc; i += 32) {
+    int n, m;
+    unpack_nm(i, n, m);
+    Ls[i] = load_coef(L + (size_t)b * xstride(P), n, m);
+  }
   __syncwarp();
   double4 c = center[b];
   for (unsigned i = b0 + lane; i < b1; i += 32) {
@@ -521,8 +385,9 @@ void laplace_execute(fmmb_plan* plan, const double* d_charges, double* d_results
   const int nb = T.nboxes;
   const int64_t n = T.n;
   cudaStream_t s = plan->stream, s2 = plan->overlap_p2p ? plan->stream2 : plan->stream;
-  plan->M.resize((size_t)nb * nc);
-  plan->L.resize((size_t)nb * nc);
+  const int xs = (pp + 1) & ~1;       // doubles per box (real layout, padded to 16 B)
+  plan->M.resize((size_t)nb * xs);
+  plan->L.resize((size_t)nb * xs);
   plan->res_near.resize(n);
   plan->res_far.resize(n);
   const double* C = m2l_coeffs(plan, P);
@@ -543,11 +408,13 @@ void laplace_execute(fmmb_plan* plan, const double* d_charges, double* d_results
   FMMB_CUDA(cudaEventRecord(ev[7], s2));
 
   // upward sweep
+  FMMB_CUDA(cudaEventRecord(ev[12], s));
   p2m_kernel<<<nblk((int64_t)T.nleaves * 32, 128), 128, 0, s>>>(T.leaves.p, T.nleaves, T.bbegin.p, T.bend.p,
                                                                T.center.p, T.body.p, P, plan->M.p);
                        ++plan->launches;
   size_t sh_mm = (size_t)(pp + nc) * sizeof(double2);
-  for (int l = T.nlevels - 2; l >= 0; --l) {
+  const bool up_batched = m2m_batched(plan, s);
+  for (int l = T.nlevels - 2; l >= 0 && !up_batched; --l) {
     int lo = T.level_off[l], hi = T.level_off[l + 1];
     m2m_kernel<<<hi - lo, 64, sh_mm, s>>>(lo, hi, T.key.p, T.cbegin.p, T.cend.p, T.center.p, P, plan->M.p);
     ++plan->launches;
@@ -575,7 +442,8 @@ void laplace_execute(fmmb_plan* plan, const double* d_charges, double* d_results
   FMMB_CUDA(cudaEventRecord(ev[3], s));
 
   // downward sweep
-  for (int l = 1; l < T.nlevels; ++l) {
+  const bool down_batched = l2l_batched(plan, s);
+  for (int l = 1; l < T.nlevels && !down_batched; ++l) {
     int lo = T.level_off[l], hi = T.level_off[l + 1];
     l2l_kernel<<<hi - lo, 64, sh_mm, s>>>(lo, hi, T.parent.p, T.has_local.p, T.center.p, P, plan->L.p);
     ++plan->launches;

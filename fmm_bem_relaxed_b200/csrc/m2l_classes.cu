@@ -18,15 +18,18 @@
 // Pairs whose class is too small to batch (tails of adaptive trees, top levels) stay on the
 // per-pair kernel in laplace.cu, which accumulates on top.
 #include "common.cuh"
-#include "laplace_tables.cuh"
+#include "laplace_ops.cuh"
 #include <cub/cub.cuh>
+#include <algorithm>
 
 namespace fmmb {
 
 namespace {
 
-constexpr int kNB = 128;          // pairs (columns) per CTA
-constexpr int kMinPop = 24;       // smallest class that is worth a GEMM tile
+using namespace ops;
+
+constexpr int kNB = 64;           // pairs (columns) per pipeline stage
+constexpr int kMinPopM2L = 24;    // smallest M2L class that is worth a GEMM tile
 
 __host__ __device__ __forceinline__ unsigned compact10(unsigned x) {
   x &= 0x09249249u;
@@ -57,25 +60,38 @@ __global__ void slot_targets(const int* __restrict__ off, int nb, int* __restric
   if (b >= nb) return;
   for (int e = off[b] + threadIdx.x; e < off[b + 1]; e += blockDim.x) tgt[e] = b;
 }
+// M2M: slot = child box c, pair (src = c, tgt = parent[c]); L2L: (src = parent[c], tgt = c)
+__global__ void parent_child_pairs(const unsigned* __restrict__ parent, int nb, int child_is_target,
+                                   int* __restrict__ tgt, int* __restrict__ src) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= nb) return;
+  int p = c == 0 ? 0 : (int)parent[c];
+  tgt[c] = child_is_target ? c : p;
+  src[c] = child_is_target ? p : c;
+}
 
-__global__ void class_keys(const int* __restrict__ tgt, const int* __restrict__ src, int64_t n,
-                           const unsigned* __restrict__ key, const unsigned* __restrict__ lvl,
+// class key of slot first+e: integer centre offset (36 bits) [+ target level above it]
+__global__ void class_keys(const int* __restrict__ tgt, const int* __restrict__ src, int first, int64_t n,
+                           const unsigned* __restrict__ key, const unsigned* __restrict__ lvl, int with_level,
                            unsigned long long* __restrict__ ckey, int* __restrict__ slot) {
   int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (e >= n) return;
-  int t = tgt[e], s = src[e];
+  int sl = first + (int)e;
+  int t = tgt[sl], s = src[sl];
   int3 a = centre_half_cells(key[t], lvl[t]), b = centre_half_cells(key[s], lvl[s]);
   unsigned long long dx = (unsigned)(a.x - b.x + 2048), dy = (unsigned)(a.y - b.y + 2048),
                      dz = (unsigned)(a.z - b.z + 2048);
-  ckey[e] = (dx << 24) | (dy << 12) | dz;
-  slot[e] = (int)e;
+  unsigned long long k = (dx << 24) | (dy << 12) | dz;
+  if (with_level) k |= (unsigned long long)lvl[t] << 36;
+  ckey[e] = k;
+  slot[e] = sl;
 }
 
 // per class: number of GEMM items (0 if the class is too small)
-__global__ void class_items(const int* __restrict__ count, int nclasses, int* __restrict__ nitems) {
+__global__ void class_items(const int* __restrict__ count, int nclasses, int minpop, int* __restrict__ nitems) {
   int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c > nclasses) return;
-  nitems[c] = (c < nclasses && count[c] >= kMinPop) ? (count[c] + kNB - 1) / kNB : 0;
+  nitems[c] = (c < nclasses && count[c] >= minpop) ? (count[c] + kNB - 1) / kNB : 0;
 }
 __global__ void fill_items(const int* __restrict__ count, const int* __restrict__ start,
                            const int* __restrict__ item_off, int nclasses, int* __restrict__ item_class,
@@ -91,11 +107,11 @@ __global__ void fill_items(const int* __restrict__ count, const int* __restrict_
   }
 }
 // mark slots that the batched path covers; the rest go to the per-pair kernel
-__global__ void mark_batched(const int* __restrict__ count, const int* __restrict__ start, int nclasses,
+__global__ void mark_batched(const int* __restrict__ count, const int* __restrict__ start, int nclasses, int minpop,
                              const int* __restrict__ sorted_slot, unsigned char* __restrict__ batched) {
   int c = blockIdx.x;
   if (c >= nclasses) return;
-  unsigned char v = count[c] >= kMinPop;
+  unsigned char v = count[c] >= minpop;
   for (int i = threadIdx.x; i < count[c]; i += blockDim.x) batched[sorted_slot[start[c] + i]] = v;
 }
 __global__ void residual_flags(const unsigned char* __restrict__ batched, int64_t n, int* __restrict__ flag) {
@@ -123,60 +139,15 @@ __global__ void class_vectors(const int* __restrict__ start, int nclasses, const
   vec[c] = make_double4(a.x - b.x, a.y - b.y, a.z - b.z, 0.0);
 }
 
-// ---- translation matrices ------------------------------------------------------------------------
-struct Sph { double r, x, y, cp, sp; };
-__device__ __forceinline__ Sph to_sph(double dx, double dy, double dz) {
-  Sph s;
-  s.r = sqrt(dx * dx + dy * dy + dz * dz) + 1e-12;
-  s.x = __ddiv_rn(dz, s.r);
-  s.y = sqrt((1.0 - s.x) * (1.0 + s.x));
-  double ax = fabs(dx), ay = fabs(dy);
-  if (ax + ay < 1e-12) { s.cp = 1.0; s.sp = 0.0; }
-  else if (ax < 1e-12) { s.cp = 0.0; s.sp = dy > 0 ? 1.0 : -1.0; }
-  else { double h = sqrt(dx * dx + dy * dy); s.cp = dx / h; s.sp = dy / h; }
-  return s;
-}
-// singular harmonics rho^{-n-1} Y_n^m, n < top, column m (evalLocal, LaplaceSpherical.hpp:491-524)
-__device__ void local_column(int m, int top, const Sph& s, double2* Y) {
-  double pn = 1, fact = 1, er = 1, ei = 0, rhom = 1.0 / s.r;
-  for (int k = 0; k < m; ++k) {
-    pn = -pn * fact * s.y; fact += 2;
-    double t = er * s.cp - ei * s.sp; ei = er * s.sp + ei * s.cp; er = t;
-    rhom /= s.r;
-  }
-  double p = pn;
-  int npn = m * m + 2 * m, nmn = m * m;
-  double a = rhom * p * c_pref[npn];
-  Y[npn] = make_double2(a * er, a * ei);
-  Y[nmn] = make_double2(a * er, -a * ei);
-  double p1 = p;
-  p = s.x * (2 * m + 1) * p1;
-  rhom /= s.r;
-  double rhon = rhom;
-  for (int n = m + 1; n < top; ++n) {
-    int npm = n * n + n + m, nmm = n * n + n - m;
-    a = rhon * p * c_pref[npm];
-    Y[npm] = make_double2(a * er, a * ei);
-    Y[nmm] = make_double2(a * er, -a * ei);
-    double p2 = p1; p1 = p;
-    p = (s.x * (2 * n + 1) * p1 - (n + m) * p2) / (n - m + 1);
-    rhon /= s.r;
-  }
-}
-__device__ __forceinline__ double cnm_real(int j, int k, int n, int m) {
-  int e = abs(k - m) - abs(k) - abs(m);
-  double sgn = ((e / 2) & 1) ? -1.0 : 1.0;
-  double oj = (j & 1) ? -1.0 : 1.0;
-  return sgn * oj * c_anm[n * n + n + m] * c_anm[j * j + j + k] / c_anm[(j + n) * (j + n) + j + n + m - k];
-}
-// Tt[c][col][row] (column-major in the GEMM sense: k-major, rows contiguous), ld = P^2
+// ---- translation matrices: Tt[c][col][row], rows contiguous, ld = P^2 -------------------------------
+// real layout of an expansion: Re X_n^m at n^2+n+m (m >= 0), Im X_n^m at n^2+n-m (m > 0)
 __global__ void __launch_bounds__(256)
-build_T(int P, const double4* __restrict__ vec, double* __restrict__ Tt) {
+build_T_m2l(int P, const double4* __restrict__ vec, double* __restrict__ Tt) {
   extern __shared__ double2 Y[];       // (2P)^2
   const int pp = P * P, c = blockIdx.x;
   double4 v = vec[c];
   Sph s = to_sph(v.x, v.y, v.z);
-  for (int m = threadIdx.x; m < 2 * P; m += blockDim.x) local_column(m, 2 * P, s, Y);
+  for (int m = threadIdx.x; m < 2 * P; m += blockDim.x) harmonics_column<true>(m, 2 * P, s, 1.0, Y);
   __syncthreads();
   double* T = Tt + (size_t)c * pp * pp;
   for (int idx = threadIdx.x; idx < pp * pp; idx += blockDim.x) {
@@ -187,13 +158,13 @@ build_T(int P, const double4* __restrict__ vec, double* __restrict__ Tt) {
     int mm = col - n * n - n;            // >= 0: Re M_n^m, < 0: Im M_n^{-mm}
     int k = abs(kk), m = abs(mm);
     int base = (j + n) * (j + n) + j + n - k;
-    // W(+m) and W(-m) = Cnm * Y_{j+n}^{+-m-k}
+    // W(+-m) = Cnm(+-m) * Y_{j+n}^{+-m-k};  M = a + ib contributes a (W+ + W-) + i b (W+ - W-)
     double cp_ = cnm_real(j, k, n, m);
     double2 yp = Y[base + m];
     double wpr = cp_ * yp.x, wpi = cp_ * yp.y;
     double val;
     if (m == 0) {
-      val = (mm < 0) ? 0.0 : (kk >= 0 ? wpr : wpi);
+      val = kk >= 0 ? wpr : wpi;
     } else {
       double cm_ = cnm_real(j, k, n, -m);
       double2 ym = Y[base - m];
@@ -201,151 +172,274 @@ build_T(int P, const double4* __restrict__ vec, double* __restrict__ Tt) {
       if (kk >= 0) val = (mm >= 0) ? (wpr + wmr) : -(wpi - wmi);
       else val = (mm >= 0) ? (wpi + wmi) : (wpr - wmr);
     }
-    if (kk < 0 && k == 0) val = 0.0;
     T[(size_t)col * pp + row] = val;
   }
 }
 
-// ---- phase 1: C[rows x 128] = T_c * B -------------------------------------------------------------
-// 256 threads: warp w owns rows [w*RPT, (w+1)*RPT), lane l owns columns l, l+32, l+64, l+96.
-template <int RPT>
-__global__ void __launch_bounds__(256, 2)
-m2l_gemm_kernel(int P, int ldT, const double* __restrict__ Tt, const int* __restrict__ item_class,
-                const int* __restrict__ item_start, const int* __restrict__ item_count,
-                const int* __restrict__ sorted_slot, const int* __restrict__ slot_src,
-                const double2* __restrict__ M, double* __restrict__ tmp) {
-  constexpr int ROWS = 8 * RPT;
-  const int pp = P * P, nc = P * (P + 1) / 2, ldb = pp + 1;
-  extern __shared__ double smem[];
-  double* Ts = smem;                       // [pp][ROWS]
-  double* Bs = smem + (size_t)pp * ROWS;   // [kNB][ldb]
-  __shared__ int s_slot[kNB];
-  const int item = blockIdx.x;
-  const int c = item_class[item], start = item_start[item], cnt = item_count[item];
-  const double* Tc = Tt + (size_t)c * ldT * ldT;
-  for (int idx = threadIdx.x; idx < pp * ROWS; idx += 256) {
-    int k = idx / ROWS, row = idx % ROWS;
-    Ts[idx] = row < pp ? Tc[(size_t)k * ldT + row] : 0.0;
-  }
-  if (threadIdx.x < kNB) s_slot[threadIdx.x] = threadIdx.x < cnt ? sorted_slot[start + threadIdx.x] : -1;
-  __syncthreads();
-  // gather: thread per (column, packed coefficient)
-  for (int idx = threadIdx.x; idx < kNB * nc; idx += 256) {
-    int col = idx / nc, nms = idx % nc;
-    int n = 0; while ((n + 1) * (n + 2) / 2 <= nms) ++n;
-    int m = nms - n * (n + 1) / 2;
-    double2 v = make_double2(0, 0);
-    int sl = s_slot[col];
-    if (sl >= 0) v = M[(size_t)slot_src[sl] * nc + nms];
-    Bs[col * ldb + n * n + n + m] = v.x;
-    if (m > 0) Bs[col * ldb + n * n + n - m] = v.y;
-  }
-  __syncthreads();
-  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  double acc[RPT][4];
-#pragma unroll
-  for (int r = 0; r < RPT; ++r)
-#pragma unroll
-    for (int j = 0; j < 4; ++j) acc[r][j] = 0.0;
-  const double* a_ptr = Ts + w * RPT;
-  const double* b_ptr = Bs + lane * ldb;
-#pragma unroll 4
-  for (int k = 0; k < pp; ++k) {
-    double a[RPT], b[4];
-#pragma unroll
-    for (int r = 0; r < RPT; ++r) a[r] = a_ptr[k * ROWS + r];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) b[j] = b_ptr[j * 32 * ldb + k];
-#pragma unroll
-    for (int r = 0; r < RPT; ++r)
-#pragma unroll
-      for (int j = 0; j < 4; ++j) acc[r][j] = fma(a[r], b[j], acc[r][j]);
-  }
-  __syncthreads();
-  // stage through shared memory (reuse Bs as [col][ldb]) for coalesced column stores
-#pragma unroll
-  for (int j = 0; j < 4; ++j)
-#pragma unroll
-    for (int r = 0; r < RPT; ++r) {
-      int row = w * RPT + r;
-      if (row < pp) Bs[(lane + 32 * j) * ldb + row] = acc[r][j];
+// M2M / L2L matrices by probing the operator with unit vectors (the operators contain a complex
+// conjugation, so they are linear over the reals only).
+template <int KIND>   // 1 = M2M, 2 = L2L
+__global__ void __launch_bounds__(128)
+build_T_probe(int P, const double4* __restrict__ vec, double* __restrict__ Tt) {
+  extern __shared__ double2 shp[];
+  const int pp = P * P, nc = P * (P + 1) / 2, c = blockIdx.x;
+  double2* Y = shp;          // pp
+  double2* E = shp + pp;     // nc
+  double4 v = vec[c];
+  Sph s = to_sph(v.x, v.y, v.z);
+  for (int m = threadIdx.x; m < P; m += blockDim.x) harmonics_column<false>(m, P, s, KIND == 1 ? -1.0 : 1.0, Y);
+  double* T = Tt + (size_t)c * pp * pp;
+  for (int col = 0; col < pp; ++col) {
+    int n = 0; while ((n + 1) * (n + 1) <= col) ++n;
+    int mm = col - n * n - n;
+    int hot = n * (n + 1) / 2 + abs(mm);
+    __syncthreads();
+    for (int i = threadIdx.x; i < nc; i += blockDim.x)
+      E[i] = i == hot ? (mm >= 0 ? make_double2(1, 0) : make_double2(0, 1)) : make_double2(0, 0);
+    __syncthreads();
+    for (int jks = threadIdx.x; jks < nc; jks += blockDim.x) {
+      int j, k;
+      unpack_nm(jks, j, k);
+      double2 o = KIND == 1 ? m2m_entry(E, Y, j, k) : l2l_entry(E, Y, j, k, P);
+      T[(size_t)col * pp + j * j + j + k] = o.x;
+      if (k > 0) T[(size_t)col * pp + j * j + j - k] = o.y;
     }
-  __syncthreads();
-  for (int idx = threadIdx.x; idx < cnt * pp; idx += 256) {
-    int col = idx / pp, row = idx % pp;
-    tmp[(size_t)s_slot[col] * pp + row] = Bs[col * ldb + row];
   }
 }
 
-// ---- phase 2: L[t] = sum of its columns -------------------------------------------------------------
+// ---- phase 1: C[rows x 64] = T_c * B, persistent and software pipelined --------------------------------
+// A CTA owns a contiguous range of items (an item = one class x <=64 pairs).  T_c stays in shared
+// memory while consecutive items share the class; the source expansions of the NEXT item are
+// fetched with cp.async (16 B = one complex coefficient per copy, raw packed layout) while the
+// current one is multiplied.  256 threads = 8 warps as 4 (rows) x 2 (columns); inside a warp lanes
+// are 4 (rows) x 8 (columns); a thread owns RT x 4 outputs: rows wr*4RT + rg*RT + r, columns
+// wc*32 + cg + 8j.  Shared-memory reads per k: RT doubles of T (4 distinct addresses per warp) and
+// 4 doubles of B (8 distinct, conflict-free because the column stride is an odd multiple of 16 B).
+// ACC = false: column of slot s goes to tmp[s][0..pp);  ACC = true: it is added to the packed
+// complex expansion Out[s] (L2L: every slot is written exactly once).
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+  unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gmem_src));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+
+// column stride of a staged tile: even (16-byte rows) with an odd number of 16-byte units, so the
+// 8 column groups of a warp hit distinct banks
+__host__ __device__ inline int gemm_ldb(int xs) { return ((xs / 2) & 1) ? xs : xs + 2; }
+
+template <int RT, bool ACC>
+__global__ void __launch_bounds__(256, 2)
+trans_gemm_kernel(int P, int ldT, const double* __restrict__ Tt, int n_items, const int* __restrict__ item_class,
+                  const int* __restrict__ item_start, const int* __restrict__ item_count,
+                  const int* __restrict__ sorted_slot, const int* __restrict__ slot_src,
+                  const double* __restrict__ X, double* __restrict__ tmp, double* __restrict__ Out) {
+  constexpr int ROWS = 16 * RT;
+  const int pp = P * P, xs = xstride(P), ldb = gemm_ldb(xs);
+  extern __shared__ __align__(16) double smem[];
+  double* Ts = smem;                              // [xs][ROWS], row k = pp is zero when pp is odd
+  double* Bs0 = smem + (size_t)xs * ROWS;         // 2 x [kNB][ldb], real layout as in global memory
+  __shared__ int s_slot[2][kNB], s_src[2][kNB];
+  const int per = (n_items + gridDim.x - 1) / gridDim.x;
+  const int i0 = blockIdx.x * per, i1 = min(n_items, i0 + per);
+  if (i0 >= i1) return;
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int wr = w & 3, wc = w >> 2, rg = lane & 3, cg = lane >> 2;
+  const int row0 = wr * 4 * RT + rg * RT;
+  const int col0 = wc * 32 + cg;
+  const int chunks = xs / 2;                      // 16-byte pieces per expansion
+
+  auto stage_indices = [&](int it, int buf) {
+    if (threadIdx.x < kNB) {
+      int cnt = item_count[it];
+      int sl = threadIdx.x < cnt ? sorted_slot[item_start[it] + threadIdx.x] : -1;
+      s_slot[buf][threadIdx.x] = sl;
+      s_src[buf][threadIdx.x] = sl >= 0 ? slot_src[sl] : -1;
+    }
+  };
+  auto stage_copy = [&](int buf) {
+    double* Bs = Bs0 + (size_t)buf * kNB * ldb;
+    for (int idx = threadIdx.x; idx < kNB * chunks; idx += 256) {
+      int col = idx / chunks, ch = idx - col * chunks;
+      int src = s_src[buf][col];
+      double* dst = Bs + col * ldb + 2 * ch;
+      if (src >= 0) cp_async16(dst, X + (size_t)src * xs + 2 * ch);
+      else { dst[0] = 0.0; dst[1] = 0.0; }
+    }
+    cp_async_commit();
+  };
+
+  int cur = -1, buf = 0;
+  stage_indices(i0, 0);
+  __syncthreads();
+  stage_copy(0);
+  for (int it = i0; it < i1; ++it, buf ^= 1) {
+    const int c = item_class[it];
+    if (c != cur) {
+      const double* Tc = Tt + (size_t)c * ldT * ldT;
+      for (int idx = threadIdx.x; idx < xs * ROWS; idx += 256) {
+        int k = idx / ROWS, row = idx - k * ROWS;
+        Ts[idx] = (row < pp && k < pp) ? Tc[(size_t)k * ldT + row] : 0.0;
+      }
+      cur = c;
+    }
+    const bool more = it + 1 < i1;
+    if (more) stage_indices(it + 1, buf ^ 1);
+    __syncthreads();
+    if (more) { stage_copy(buf ^ 1); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
+    __syncthreads();
+
+    const double* Bs = Bs0 + (size_t)buf * kNB * ldb;
+    double acc[RT][4];
+#pragma unroll
+    for (int r = 0; r < RT; ++r)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[r][j] = 0.0;
+    const double* a_ptr = Ts + row0;
+    const double* b_ptr = Bs + col0 * ldb;
+    const int kend = pp & ~1;
+#pragma unroll 2
+    for (int k = 0; k < kend; k += 2) {
+      double a0[RT], a1[RT];
+      double2 b[4];
+#pragma unroll
+      for (int r = 0; r < RT; ++r) { a0[r] = a_ptr[k * ROWS + r]; a1[r] = a_ptr[(k + 1) * ROWS + r]; }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) b[j] = *reinterpret_cast<const double2*>(b_ptr + j * 8 * ldb + k);
+#pragma unroll
+      for (int r = 0; r < RT; ++r)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[r][j] = fma(a0[r], b[j].x, acc[r][j]);
+#pragma unroll
+      for (int r = 0; r < RT; ++r)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[r][j] = fma(a1[r], b[j].y, acc[r][j]);
+    }
+    if (pp & 1) {
+      const int k = pp - 1;
+#pragma unroll
+      for (int r = 0; r < RT; ++r)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[r][j] = fma(a_ptr[k * ROWS + r], b_ptr[j * 8 * ldb + k], acc[r][j]);
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int sl = s_slot[buf][col0 + 8 * j];
+      if (sl < 0) continue;
+      if (!ACC) {
+        double* o = tmp + (size_t)sl * xs + row0;
+        if (RT % 2 == 0 && row0 + RT <= pp) {
+#pragma unroll
+          for (int r = 0; r < RT; r += 2) *reinterpret_cast<double2*>(o + r) = make_double2(acc[r][j], acc[r + 1][j]);
+        } else {
+#pragma unroll
+          for (int r = 0; r < RT; ++r)
+            if (row0 + r < pp) o[r] = acc[r][j];
+        }
+      } else {
+        double* o = Out + (size_t)sl * xs + row0;
+#pragma unroll
+        for (int r = 0; r < RT; ++r)
+          if (row0 + r < pp) o[r] += acc[r][j];
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// ---- phase 2 (M2L): L[t] = sum of its columns -------------------------------------------------------
 __global__ void __launch_bounds__(256)
 m2l_reduce_kernel(int nboxes, const int* __restrict__ off, const unsigned char* __restrict__ batched, int P,
-                  const double* __restrict__ tmp, double2* __restrict__ L) {
-  extern __shared__ double sum[];
+                  const double* __restrict__ tmp, double* __restrict__ L) {
   int b = blockIdx.x;
   if (b >= nboxes) return;
-  const int pp = P * P, nc = P * (P + 1) / 2;
+  const int pp = P * P, xs = xstride(P);
   int e0 = off[b], e1 = off[b + 1];
   for (int row = threadIdx.x; row < pp; row += blockDim.x) {
+    double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+    int e = e0;
+    for (; e + 4 <= e1; e += 4) {
+      double v0 = batched[e] ? tmp[(size_t)e * xs + row] : 0.0;
+      double v1 = batched[e + 1] ? tmp[(size_t)(e + 1) * xs + row] : 0.0;
+      double v2 = batched[e + 2] ? tmp[(size_t)(e + 2) * xs + row] : 0.0;
+      double v3 = batched[e + 3] ? tmp[(size_t)(e + 3) * xs + row] : 0.0;
+      s0 += v0; s1 += v1; s2 += v2; s3 += v3;
+    }
+    for (; e < e1; ++e)
+      if (batched[e]) s0 += tmp[(size_t)e * xs + row];
+    L[(size_t)b * xs + row] = (s0 + s1) + (s2 + s3);
+  }
+}
+
+// ---- phase 2 (M2M): M[parent] = sum over its children's columns, in child order ---------------------
+__global__ void __launch_bounds__(64)
+m2m_reduce_kernel(int lo, int hi, const unsigned* __restrict__ key, const unsigned* __restrict__ cbegin,
+                  const unsigned* __restrict__ cend, int P, const double* __restrict__ tmp,
+                  double* __restrict__ M) {
+  int b = lo + blockIdx.x;
+  if (b >= hi || (key[b] >> 31)) return;
+  const int pp = P * P, xs = xstride(P);
+  unsigned c0 = cbegin[b], c1 = cend[b];
+  for (int row = threadIdx.x; row < pp; row += blockDim.x) {
     double s = 0;
-    for (int e = e0; e < e1; ++e)
-      if (batched[e]) s += tmp[(size_t)e * pp + row];
-    sum[row] = s;
-  }
-  __syncthreads();
-  for (int nms = threadIdx.x; nms < nc; nms += blockDim.x) {
-    int n = 0; while ((n + 1) * (n + 2) / 2 <= nms) ++n;
-    int m = nms - n * (n + 1) / 2;
-    L[(size_t)b * nc + nms] = make_double2(sum[n * n + n + m], m > 0 ? sum[n * n + n - m] : 0.0);
+    for (unsigned c = c0; c < c1; ++c) s += tmp[(size_t)c * xs + row];
+    M[(size_t)b * xs + row] = s;
   }
 }
 
-template <int RPT>
-void launch_gemm(fmmb_plan* plan, int P, double* tmp, cudaStream_t s) {
-  M2LClasses& C = plan->cls;
-  const int pp = P * P;
-  size_t sh = ((size_t)pp * 8 * RPT + (size_t)kNB * (pp + 1)) * sizeof(double);
-  static bool attr_set = false;
-  if (!attr_set) {
-    FMMB_CUDA(cudaFuncSetAttribute(m2l_gemm_kernel<RPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh));
-    attr_set = true;
+template <int RT, bool ACC>
+void launch_gemm_t(const TransBatch& B, int P, int first, int count, const double* X, double* tmp,
+                   double* out, cudaStream_t s) {
+  const int xs = xstride(P);
+  size_t sh = ((size_t)xs * 16 * RT + (size_t)2 * kNB * gemm_ldb(xs)) * sizeof(double);
+  static size_t attr = 0;
+  static int sms = 0;
+  if (sh > attr) {
+    FMMB_CUDA(cudaFuncSetAttribute(trans_gemm_kernel<RT, ACC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh));
+    attr = sh;
   }
-  m2l_gemm_kernel<RPT><<<C.n_items, 256, sh, s>>>(P, C.built_p * C.built_p, C.T.p, C.item_class.p, C.item_start.p,
-                                                 C.item_count.p, C.sorted_slot.p, plan->tree.m2l_src.p,
-                                                 plan->M.p, tmp);
+  if (!sms) {
+    int dev = 0;
+    FMMB_CUDA(cudaGetDevice(&dev));
+    FMMB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  }
+  int grid = std::min(count, 2 * sms);
+  trans_gemm_kernel<RT, ACC><<<grid, 256, sh, s>>>(P, B.built_p * B.built_p, B.T.p, count, B.item_class.p + first,
+                                                  B.item_start.p + first, B.item_count.p + first,
+                                                  B.sorted_slot.p, B.slot_src_p, X, tmp, out);
+  FMMB_CUDA(cudaGetLastError());
+}
+template <bool ACC>
+void launch_gemm(const TransBatch& B, int P, int first, int count, const double* X, double* tmp, double* out,
+                 cudaStream_t s) {
+  if (count <= 0) return;
+  switch (P) {
+    case 1: case 2: case 3: case 4: launch_gemm_t<1, ACC>(B, P, first, count, X, tmp, out, s); break;
+    case 5: launch_gemm_t<2, ACC>(B, P, first, count, X, tmp, out, s); break;
+    case 6: launch_gemm_t<3, ACC>(B, P, first, count, X, tmp, out, s); break;
+    default: launch_gemm_t<4, ACC>(B, P, first, count, X, tmp, out, s); break;
+  }
 }
 
-}  // namespace
-
-void m2l_init_tables() { upload_laplace_tables(); }
-
-// Plan-time: classify the M2L pairs and build the work items.
-void build_m2l_classes(fmmb_plan* plan) {
+// Sorts the pairs of a batch by class, builds classes / items / (for M2L) the residual lists.
+// tgt/src are indexed by slot; slots [first, first+n) take part.
+void classify(fmmb_plan* plan, TransBatch& B, const int* tgt, const int* src, int first, int64_t n,
+              int minpop, bool by_level) {
   Tree& T = plan->tree;
-  M2LClasses& C = plan->cls;
   cudaStream_t s = plan->stream;
-  const int64_t n = T.n_lr;
-  const int nb = T.nboxes;
-  C.n_classes = 0; C.n_pairs = 0; C.n_items = 0; C.n_res = n; C.built_p = 0;
-  if (n == 0 || plan->opts.m2l_mode == 1) return;
-  if (n >= (1ll << 31)) throw StatusError{FMMB_ERR_INVALID, "more than 2^31 M2L pairs"};
   Temp tmp;
-  C.slot_tgt.resize(n);
-  slot_targets<<<nb, 64, 0, s>>>(T.m2l_off.p, nb, C.slot_tgt.p);
-  DevBuf<unsigned long long> k0, k1;
-  DevBuf<int> v0;
-  k0.resize(n); k1.resize(n); v0.resize(n); C.sorted_slot.resize(n);
-  class_keys<<<nblk(n, 256), 256, 0, s>>>(C.slot_tgt.p, T.m2l_src.p, n, T.key.p, T.level.p, k0.p, v0.p);
+  DevBuf<unsigned long long> k0, k1, uniq;
+  DevBuf<int> v0, count, nruns;
+  k0.resize(n); k1.resize(n); v0.resize(n); B.sorted_slot.resize(n);
+  class_keys<<<nblk(n, 256), 256, 0, s>>>(tgt, src, first, n, T.key.p, T.level.p, by_level ? 1 : 0, k0.p, v0.p);
   FMMB_CUDA(cudaGetLastError());
   {
     size_t bytes = 0;
-    FMMB_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, bytes, k0.p, k1.p, v0.p, C.sorted_slot.p, n, 0, 36, s));
+    FMMB_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, bytes, k0.p, k1.p, v0.p, B.sorted_slot.p, n, 0, 40, s));
     void* t = tmp.get(bytes);
-    FMMB_CUDA(cub::DeviceRadixSort::SortPairs(t, bytes, k0.p, k1.p, v0.p, C.sorted_slot.p, n, 0, 36, s));
+    FMMB_CUDA(cub::DeviceRadixSort::SortPairs(t, bytes, k0.p, k1.p, v0.p, B.sorted_slot.p, n, 0, 40, s));
   }
-  // run-length encode -> classes
-  DevBuf<unsigned long long> uniq;
-  DevBuf<int> count, nruns;
   uniq.resize(n); count.resize(n + 1); nruns.resize(1);
   {
     size_t bytes = 0;
@@ -361,7 +455,7 @@ void build_m2l_classes(fmmb_plan* plan) {
     FMMB_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, bytes, count.p, start.p, ncls + 1, s));
     void* t = tmp.get(bytes);
     FMMB_CUDA(cub::DeviceScan::ExclusiveSum(t, bytes, count.p, start.p, ncls + 1, s));
-    class_items<<<nblk(ncls + 1, 256), 256, 0, s>>>(count.p, ncls, nitems.p);
+    class_items<<<nblk(ncls + 1, 256), 256, 0, s>>>(count.p, ncls, minpop, nitems.p);
     FMMB_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, bytes, nitems.p, item_off.p, ncls + 1, s));
     t = tmp.get(bytes);
     FMMB_CUDA(cub::DeviceScan::ExclusiveSum(t, bytes, nitems.p, item_off.p, ncls + 1, s));
@@ -369,72 +463,156 @@ void build_m2l_classes(fmmb_plan* plan) {
   int n_items = 0;
   FMMB_CUDA(cudaMemcpyAsync(&n_items, item_off.p + ncls, sizeof(int), cudaMemcpyDeviceToHost, s));
   FMMB_CUDA(cudaStreamSynchronize(s));
-  C.n_classes = ncls;
-  C.n_items = n_items;
-  C.item_class.resize(n_items); C.item_start.resize(n_items); C.item_count.resize(n_items);
+  B.n_classes = ncls;
+  B.n_items = n_items;
+  B.item_class.resize(n_items); B.item_start.resize(n_items); B.item_count.resize(n_items);
   if (n_items)
-    fill_items<<<nblk(ncls, 128), 128, 0, s>>>(count.p, start.p, item_off.p, ncls, C.item_class.p, C.item_start.p,
-                                              C.item_count.p);
-  C.batched.resize(n);
-  mark_batched<<<ncls, 128, 0, s>>>(count.p, start.p, ncls, C.sorted_slot.p, C.batched.p);
-  // residual CSR (target-major, list order preserved)
-  DevBuf<int> flag, pos;
-  flag.resize(n + 1); pos.resize(n + 1);
-  residual_flags<<<nblk(n + 1, 256), 256, 0, s>>>(C.batched.p, n, flag.p);
-  {
-    size_t bytes = 0;
-    FMMB_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, bytes, flag.p, pos.p, n + 1, s));
-    void* t = tmp.get(bytes);
-    FMMB_CUDA(cub::DeviceScan::ExclusiveSum(t, bytes, flag.p, pos.p, n + 1, s));
+    fill_items<<<nblk(ncls, 128), 128, 0, s>>>(count.p, start.p, item_off.p, ncls, B.item_class.p, B.item_start.p,
+                                              B.item_count.p);
+  B.class_vec.resize(ncls);
+  class_vectors<<<nblk(ncls, 128), 128, 0, s>>>(start.p, ncls, B.sorted_slot.p, tgt, src, T.center.p,
+                                               B.class_vec.p);
+  FMMB_CUDA(cudaGetLastError());
+  if (by_level) {
+    // items are sorted by target level (top bits of the class key): record the ranges on the host
+    B.level_item_off.assign(T.nlevels + 1, 0);
+    std::vector<unsigned long long> hk(ncls);
+    FMMB_CUDA(cudaMemcpyAsync(hk.data(), uniq.p, ncls * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+    std::vector<int> hoff = item_off.to_host(s);
+    for (int c = 0; c < ncls; ++c) {
+      int l = (int)(hk[c] >> 36);
+      if (l + 1 <= T.nlevels) B.level_item_off[l + 1] = hoff[c + 1];
+    }
+    for (int l = 1; l <= T.nlevels; ++l) B.level_item_off[l] = std::max(B.level_item_off[l], B.level_item_off[l - 1]);
+  } else {
+    // M2L: slots of small classes stay on the per-pair kernel
+    B.batched.resize(n);
+    mark_batched<<<ncls, 128, 0, s>>>(count.p, start.p, ncls, minpop, B.sorted_slot.p, B.batched.p);
+    DevBuf<int> flag, pos;
+    flag.resize(n + 1); pos.resize(n + 1);
+    residual_flags<<<nblk(n + 1, 256), 256, 0, s>>>(B.batched.p, n, flag.p);
+    {
+      size_t bytes = 0;
+      FMMB_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, bytes, flag.p, pos.p, n + 1, s));
+      void* t = tmp.get(bytes);
+      FMMB_CUDA(cub::DeviceScan::ExclusiveSum(t, bytes, flag.p, pos.p, n + 1, s));
+    }
+    int n_res = 0;
+    FMMB_CUDA(cudaMemcpyAsync(&n_res, pos.p + n, sizeof(int), cudaMemcpyDeviceToHost, s));
+    FMMB_CUDA(cudaStreamSynchronize(s));
+    B.n_res = n_res;
+    B.n_pairs = n - n_res;
+    B.res_src.resize(n_res); B.res_off.resize(T.nboxes + 1);
+    if (n_res) residual_compact<<<nblk(n, 256), 256, 0, s>>>(flag.p, pos.p, n, src, B.res_src.p);
+    residual_offsets<<<nblk(T.nboxes + 1, 256), 256, 0, s>>>(T.m2l_off.p, pos.p, T.nboxes, B.res_off.p);
   }
-  int n_res = 0;
-  FMMB_CUDA(cudaMemcpyAsync(&n_res, pos.p + n, sizeof(int), cudaMemcpyDeviceToHost, s));
-  FMMB_CUDA(cudaStreamSynchronize(s));
-  C.n_res = n_res;
-  C.n_pairs = n - n_res;
-  C.res_src.resize(n_res); C.res_off.resize(nb + 1);
-  if (n_res) residual_compact<<<nblk(n, 256), 256, 0, s>>>(flag.p, pos.p, n, T.m2l_src.p, C.res_src.p);
-  residual_offsets<<<nblk(nb + 1, 256), 256, 0, s>>>(T.m2l_off.p, pos.p, nb, C.res_off.p);
-  // representative translation vector per class
-  C.class_vec.resize(ncls);
-  class_vectors<<<nblk(ncls, 128), 128, 0, s>>>(start.p, ncls, C.sorted_slot.p, C.slot_tgt.p, T.m2l_src.p,
-                                               T.center.p, C.class_vec.p);
   FMMB_CUDA(cudaGetLastError());
   FMMB_CUDA(cudaStreamSynchronize(s));
+}
+
+void ensure_T(fmmb_plan* plan, TransBatch& B, cudaStream_t s) {
+  if (B.built_p >= plan->p || B.n_classes == 0) return;
+  const int bp = 8;   // largest order of the GEMM family; smaller orders use the leading sub-block
+  B.T.resize((size_t)B.n_classes * bp * bp * bp * bp);
+  if (B.kind == 0)
+    build_T_m2l<<<(int)B.n_classes, 256, (size_t)4 * bp * bp * sizeof(double2), s>>>(bp, B.class_vec.p, B.T.p);
+  else if (B.kind == 1)
+    build_T_probe<1><<<(int)B.n_classes, 128, (size_t)(bp * bp + bp * (bp + 1) / 2) * sizeof(double2), s>>>(
+        bp, B.class_vec.p, B.T.p);
+  else
+    build_T_probe<2><<<(int)B.n_classes, 128, (size_t)(bp * bp + bp * (bp + 1) / 2) * sizeof(double2), s>>>(
+        bp, B.class_vec.p, B.T.p);
+  FMMB_CUDA(cudaGetLastError());
+  B.built_p = bp;
+  ++plan->launches;
+}
+
+}  // namespace
+
+void m2l_init_tables() { upload_laplace_tables(); }
+
+// Plan-time: classify M2L, M2M and L2L translations and build the GEMM work items.
+void build_m2l_classes(fmmb_plan* plan) {
+  Tree& T = plan->tree;
+  cudaStream_t s = plan->stream;
+  const int nb = T.nboxes;
+  TransBatch& C = plan->cls;
+  C.kind = 0; C.n_classes = 0; C.n_pairs = 0; C.n_items = 0; C.n_res = T.n_lr; C.built_p = 0;
+  plan->m2m.kind = 1; plan->m2m.n_items = 0; plan->m2m.built_p = 0;
+  plan->l2l.kind = 2; plan->l2l.n_items = 0; plan->l2l.built_p = 0;
+  if (plan->opts.m2l_mode == 1) return;
+  if (T.n_lr >= (1ll << 31)) throw StatusError{FMMB_ERR_INVALID, "more than 2^31 M2L pairs"};
+  if (T.n_lr > 0) {
+    C.slot_tgt.resize(T.n_lr);
+    slot_targets<<<nb, 64, 0, s>>>(T.m2l_off.p, nb, C.slot_tgt.p);
+    C.slot_src_p = T.m2l_src.p;
+    classify(plan, C, C.slot_tgt.p, T.m2l_src.p, 0, T.n_lr, kMinPopM2L, false);
+  }
+  if (nb > 1) {
+    for (int kind = 1; kind <= 2; ++kind) {
+      TransBatch& B = kind == 1 ? plan->m2m : plan->l2l;
+      B.slot_tgt.resize(nb); B.slot_src.resize(nb);
+      parent_child_pairs<<<nblk(nb, 256), 256, 0, s>>>(T.parent.p, nb, kind == 2, B.slot_tgt.p, B.slot_src.p);
+      B.slot_src_p = B.slot_src.p;
+      classify(plan, B, B.slot_tgt.p, B.slot_src.p, 1, nb - 1, 1, true);
+      B.n_pairs = nb - 1;
+    }
+  }
 }
 
 // Batched far field for the current order.  Returns false if there is nothing batched
 // (the caller then runs the per-pair kernel over the full lists).
 bool m2l_batched(fmmb_plan* plan, cudaStream_t s) {
-  M2LClasses& C = plan->cls;
+  TransBatch& C = plan->cls;
   Tree& T = plan->tree;
-  const int P = plan->p, pp = P * P;
+  const int P = plan->p, pp = P * P, xs = xstride(P);
   if (C.n_items == 0 || P > 8) return false;
-  if (C.built_p < P) {
-    // build for the largest order this kernel family handles, once
-    int bp = 8;
-    C.T.resize((size_t)C.n_classes * bp * bp * bp * bp);
-    build_T<<<(int)C.n_classes, 256, (size_t)4 * bp * bp * sizeof(double2), s>>>(bp, C.class_vec.p, C.T.p);
-    FMMB_CUDA(cudaGetLastError());
-    C.built_p = bp;
-    ++plan->launches;
-  }
-  C.tmp.resize((size_t)T.n_lr * pp);
-  switch (P) {
-    case 1: case 2: launch_gemm<1>(plan, P, C.tmp.p, s); break;
-    case 3: case 4: launch_gemm<2>(plan, P, C.tmp.p, s); break;
-    case 5: launch_gemm<4>(plan, P, C.tmp.p, s); break;
-    case 6: launch_gemm<5>(plan, P, C.tmp.p, s); break;
-    case 7: launch_gemm<7>(plan, P, C.tmp.p, s); break;
-    default: launch_gemm<8>(plan, P, C.tmp.p, s); break;
-  }
-  FMMB_CUDA(cudaGetLastError());
+  ensure_T(plan, C, s);
+  C.tmp.resize((size_t)T.n_lr * xs);
+  launch_gemm<false>(C, P, 0, C.n_items, plan->M.p, C.tmp.p, nullptr, s);
   ++plan->launches;
   int threads = pp < 64 ? 64 : (pp > 256 ? 256 : pp);
-  m2l_reduce_kernel<<<T.nboxes, threads, pp * sizeof(double), s>>>(T.nboxes, T.m2l_off.p, C.batched.p, P,
+  m2l_reduce_kernel<<<T.nboxes, threads, 0, s>>>(T.nboxes, T.m2l_off.p, C.batched.p, P,
                                                                   C.tmp.p, plan->L.p);
   FMMB_CUDA(cudaGetLastError());
   ++plan->launches;
+  return true;
+}
+
+// Batched M2M level sweep (finest parents first).  False -> caller uses the per-box kernels.
+bool m2m_batched(fmmb_plan* plan, cudaStream_t s) {
+  TransBatch& B = plan->m2m;
+  Tree& T = plan->tree;
+  const int P = plan->p, xs = xstride(P);
+  if (B.n_items == 0 || P > 8 || plan->opts.m2l_mode == 1) return false;
+  ensure_T(plan, B, s);
+  B.tmp.resize((size_t)T.nboxes * xs);
+  for (int l = T.nlevels - 2; l >= 0; --l) {
+    int i0 = B.level_item_off[l], i1 = B.level_item_off[l + 1];
+    if (i1 <= i0) continue;
+    launch_gemm<false>(B, P, i0, i1 - i0, plan->M.p, B.tmp.p, nullptr, s);
+    int lo = T.level_off[l], hi = T.level_off[l + 1];
+    m2m_reduce_kernel<<<hi - lo, 64, 0, s>>>(
+        lo, hi, T.key.p, T.cbegin.p, T.cend.p, P, B.tmp.p, plan->M.p);
+    plan->launches += 2;
+  }
+  FMMB_CUDA(cudaGetLastError());
+  return true;
+}
+
+// Batched L2L level sweep (coarsest children first); adds into the locals M2L left behind.
+bool l2l_batched(fmmb_plan* plan, cudaStream_t s) {
+  TransBatch& B = plan->l2l;
+  Tree& T = plan->tree;
+  const int P = plan->p;
+  if (B.n_items == 0 || P > 8 || plan->opts.m2l_mode == 1) return false;
+  ensure_T(plan, B, s);
+  for (int l = 1; l < T.nlevels; ++l) {
+    int i0 = B.level_item_off[l], i1 = B.level_item_off[l + 1];
+    if (i1 <= i0) continue;
+    launch_gemm<true>(B, P, i0, i1 - i0, plan->L.p, nullptr, plan->L.p, s);
+    ++plan->launches;
+  }
   return true;
 }
 
