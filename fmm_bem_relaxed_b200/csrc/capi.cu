@@ -89,6 +89,7 @@ int fmmb_plan_create(const fmmb_kernel_desc* kernel, const fmmb_sources* sources
     laplace_init_tables(plan);
     build_tree(plan, sources->points, sources->n);
     build_m2l_classes(plan);
+    build_p2p_items(plan);
   });
   if (rc != FMMB_OK) { fmmb_plan_destroy(plan); return rc; }
   *out_plan = plan;

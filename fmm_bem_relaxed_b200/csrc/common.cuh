@@ -106,6 +106,8 @@ struct Tree {
   // P2P: target-major CSR of source leaf boxes in P2P_lists order
   DevBuf<int> p2p_off, p2p_src;
   int64_t n_p2p = 0, n_p2p_body_pairs = 0;
+  DevBuf<int4> p2p_items;            // (target leaf, first target body, #targets <= 32, 0), leaf order
+  int n_p2p_items = 0;
 };
 
 // One family of box-to-box translations (M2L, M2M or L2L) evaluated as class-batched GEMMs
@@ -127,6 +129,8 @@ struct TransBatch {
   std::vector<int> level_item_off;   // M2M/L2L: items whose target level is l
   DevBuf<unsigned char> batched;     // M2L, per slot: handled by the batched path
   DevBuf<int> res_off, res_src;      // M2L residual pairs, target-major CSR in list order
+  DevBuf<int> res_boxes;             // target boxes that have residual pairs
+  int n_res_boxes = 0;
   DevBuf<double> tmp;                // phase-1 output columns, [slot][p^2]
 };
 
@@ -166,6 +170,7 @@ void build_tree(fmmb_plan* plan, const double* points_host, int64_t n);
 // laplace.cu
 void laplace_init_tables(fmmb_plan* plan);
 void laplace_execute(fmmb_plan* plan, const double* d_charges, double* d_results);
+void build_p2p_items(fmmb_plan* plan);
 void laplace_direct_raw(const double* d_spts, const double* d_q, int64_t ns, const double* d_tpts, int64_t nt,
                         double* d_out, cudaStream_t s);
 double measure_fp64_peak();

@@ -40,7 +40,6 @@ p2m_kernel(const int* __restrict__ leaves, int nleaves, const unsigned* __restri
   int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (w >= nleaves) return;
   int b = leaves[w];
-  const int nc = P * (P + 1) / 2;
   double4 c = center[b];
   unsigned b0 = bb[b], b1 = be[b];
   double* Mb = M + (size_t)b * xstride(P);
@@ -116,11 +115,11 @@ __global__ void m2l_coeff_kernel(int P, double* __restrict__ C) {
 }
 
 __global__ void __launch_bounds__(256)
-m2l_pair_kernel(int nboxes, const int* __restrict__ off, const int* __restrict__ src,
+m2l_pair_kernel(int nboxes, const int* __restrict__ box_list, const int* __restrict__ off, const int* __restrict__ src,
                 const double4* __restrict__ center, int P, const double* __restrict__ C,
                 const double* __restrict__ M, double* __restrict__ L, int accumulate) {
-  int b = blockIdx.x;
-  if (b >= nboxes) return;
+  if (blockIdx.x >= nboxes) return;
+  const int b = box_list ? box_list[blockIdx.x] : blockIdx.x;
   extern __shared__ double2 sh[];
   const int nc = P * (P + 1) / 2, pp = P * P;
   double2* Y = sh;                 // 4 pp
@@ -252,9 +251,12 @@ l2p_kernel(const int* __restrict__ leaves, int nleaves, const unsigned* __restri
   }
 }
 
-// ---- P2P: block per target leaf; source leaves staged through shared memory -----------------------
-constexpr int kP2PThreads = 64;
-constexpr int kP2PTile = 256;
+// ---- P2P: one warp per (target leaf, chunk of <= 32 targets) ---------------------------------------
+// Sources stream through a warp-private shared tile (32 bodies = 1 KB), so there is no block
+// barrier.  A chunk with r < 32 targets is replicated S = 32/r times across the lanes and every
+// replica takes every S-th source; the replicas are summed with shuffles at the end.  That keeps
+// the FP64 pipe fed for leaves whose body count is not a multiple of 32.
+constexpr int kP2PWarps = 4;
 
 __device__ __forceinline__ void p2p_accumulate(const double4 t, const double4 sq, double& pot, double& fx,
                                                double& fy, double& fz) {
@@ -263,51 +265,74 @@ __device__ __forceinline__ void p2p_accumulate(const double4 t, const double4 sq
   double inv = rsqrt(r2);
   if (r2 < 1e-8) inv = 0.0;                        // LaplaceSpherical.hpp:158
   double qi = sq.w * inv;
-  double qi3 = qi * inv * inv;
+  double qi3 = qi * (inv * inv);
   pot += qi;
-  fx += dx * qi3; fy += dy * qi3; fz += dz * qi3;
+  fx = fma(dx, qi3, fx); fy = fma(dy, qi3, fy); fz = fma(dz, qi3, fz);
 }
 
-__global__ void __launch_bounds__(kP2PThreads)
-p2p_kernel(const int* __restrict__ leaves, int nleaves, const unsigned* __restrict__ bb,
+// work items: x = target box, y = first target body, z = number of targets (<= 32)
+__global__ void p2p_count_items(const int* __restrict__ leaves, int nleaves, const unsigned* __restrict__ bb,
+                                const unsigned* __restrict__ be, int* __restrict__ cnt) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i > nleaves) return;
+  cnt[i] = i < nleaves ? (int)((be[leaves[i]] - bb[leaves[i]] + 31) / 32) : 0;
+}
+__global__ void p2p_fill_items(const int* __restrict__ leaves, int nleaves, const unsigned* __restrict__ bb,
+                               const unsigned* __restrict__ be, const int* __restrict__ off,
+                               int4* __restrict__ items) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nleaves) return;
+  int b = leaves[i];
+  unsigned t0 = bb[b], t1 = be[b];
+  int o = off[i];
+  for (unsigned t = t0; t < t1; t += 32) items[o++] = make_int4(b, (int)t, (int)min(32u, t1 - t), 0);
+}
+
+__global__ void __launch_bounds__(32 * kP2PWarps)
+p2p_kernel(const int4* __restrict__ items, int nitems, const unsigned* __restrict__ bb,
            const unsigned* __restrict__ be, const int* __restrict__ off, const int* __restrict__ src,
            const double4* __restrict__ body, double4* __restrict__ res) {
-  __shared__ double4 tile[kP2PTile];
-  int lf = blockIdx.x;
-  if (lf >= nleaves) return;
-  int b = leaves[lf];
-  unsigned t0 = bb[b], t1 = be[b];
-  int s0 = off[b], s1 = off[b + 1];
-  for (unsigned tb = t0; tb < t1; tb += kP2PThreads) {
-    unsigned ti = tb + threadIdx.x;
-    bool act = ti < t1;
-    double4 t = act ? body[ti] : make_double4(0, 0, 0, 0);
-    double pot = 0, fx = 0, fy = 0, fz = 0;
-    // stream all source bodies of all source leaves through the tile
-    int it = s0;
-    unsigned cur = 0, cur_end = 0;
-    if (it < s1) { cur = bb[src[it]]; cur_end = be[src[it]]; }
-    while (it < s1) {
-      // fill
-      int filled = 0;
-      __syncthreads();
-      while (it < s1 && filled < kP2PTile) {
-        unsigned take = min((unsigned)(kP2PTile - filled), cur_end - cur);
-        for (unsigned k = threadIdx.x; k < take; k += kP2PThreads) tile[filled + k] = body[cur + k];
-        filled += take; cur += take;
-        if (cur == cur_end) {
-          ++it;
-          if (it < s1) { cur = bb[src[it]]; cur_end = be[src[it]]; }
+  __shared__ double4 tiles[kP2PWarps][32];
+  const int wl = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int item = blockIdx.x * kP2PWarps + wl;
+  if (item >= nitems) return;
+  double4* tile = tiles[wl];
+  const int4 it = items[item];
+  const int r = it.z;                      // targets in this chunk
+  const int S = 32 / r;                    // source splits (1 when r > 16)
+  const int ti = lane % r, sp = lane / r;
+  const bool act = sp < S;
+  const double4 t = body[it.y + ti];
+  double pot = 0, fx = 0, fy = 0, fz = 0;
+  const int s0 = off[it.x], s1 = off[it.x + 1];
+  for (int e = s0; e < s1; ++e) {
+    const int sb = src[e];
+    const unsigned c0 = bb[sb], c1 = be[sb];
+    for (unsigned base = c0; base < c1; base += 32) {
+      const int cnt = (int)min(32u, c1 - base);
+      __syncwarp();
+      if (lane < cnt) tile[lane] = body[base + lane];
+      __syncwarp();
+      if (act) {
+        if (S == 1) {
+#pragma unroll 4
+          for (int k = 0; k < cnt; ++k) p2p_accumulate(t, tile[k], pot, fx, fy, fz);
+        } else {
+          for (int k = sp; k < cnt; k += S) p2p_accumulate(t, tile[k], pot, fx, fy, fz);
         }
       }
-      __syncthreads();
-      if (act) {
-#pragma unroll 4
-        for (int k = 0; k < filled; ++k) p2p_accumulate(t, tile[k], pot, fx, fy, fz);
-      }
     }
-    if (act) res[ti] = make_double4(pot, fx, fy, fz);
   }
+  if (S > 1) {
+    // lanes ti, ti + r, ti + 2r, ... hold partial sums of the same target
+    for (int q = 1; q < S; ++q) {
+      int from = lane + q * r;
+      double a = __shfl_sync(0xffffffffu, pot, from & 31), bx = __shfl_sync(0xffffffffu, fx, from & 31),
+             by = __shfl_sync(0xffffffffu, fy, from & 31), bz = __shfl_sync(0xffffffffu, fz, from & 31);
+      if (lane < r) { pot += a; fx += bx; fy += by; fz += bz; }
+    }
+  }
+  if (lane < r) res[it.y + lane] = make_double4(pot, fx, fy, fz);
 }
 
 // ---- results back to the caller's order ----------------------------------------------------------
@@ -388,6 +413,12 @@ void laplace_execute(fmmb_plan* plan, const double* d_charges, double* d_results
   const int xs = (pp + 1) & ~1;       // doubles per box (real layout, padded to 16 B)
   plan->M.resize((size_t)nb * xs);
   plan->L.resize((size_t)nb * xs);
+  if (plan->p_alloc != P) {
+    // the padding double of odd-sized expansions is read (times zero) by the GEMM: keep it finite
+    plan->M.zero(plan->stream);
+    plan->L.zero(plan->stream);
+    plan->p_alloc = P;
+  }
   plan->res_near.resize(n);
   plan->res_far.resize(n);
   const double* C = m2l_coeffs(plan, P);
@@ -402,8 +433,9 @@ void laplace_execute(fmmb_plan* plan, const double* d_charges, double* d_results
   // near field on the second stream: needs only the charges
   if (s2 != s) FMMB_CUDA(cudaStreamWaitEvent(s2, ev[1], 0));
   FMMB_CUDA(cudaEventRecord(ev[6], s2));
-  p2p_kernel<<<T.nleaves, kP2PThreads, 0, s2>>>(T.leaves.p, T.nleaves, T.bbegin.p, T.bend.p, T.p2p_off.p,
-                                               T.p2p_src.p, T.body.p, plan->res_near.p);
+  p2p_kernel<<<nblk(T.n_p2p_items, kP2PWarps), 32 * kP2PWarps, 0, s2>>>(T.p2p_items.p, T.n_p2p_items, T.bbegin.p,
+                                                                       T.bend.p, T.p2p_off.p, T.p2p_src.p,
+                                                                       T.body.p, plan->res_near.p);
        ++plan->launches;
   FMMB_CUDA(cudaEventRecord(ev[7], s2));
 
@@ -430,12 +462,13 @@ void laplace_execute(fmmb_plan* plan, const double* d_charges, double* d_results
     if (red > sh) sh = red;
     bool batched = plan->opts.m2l_mode != 1 && m2l_batched(plan, s);
     if (!batched) {
-      m2l_pair_kernel<<<nb, threads, sh, s>>>(nb, T.m2l_off.p, T.m2l_src.p, T.center.p, P, C, plan->M.p,
+      m2l_pair_kernel<<<nb, threads, sh, s>>>(nb, nullptr, T.m2l_off.p, T.m2l_src.p, T.center.p, P, C, plan->M.p,
                                              plan->L.p, 0);
       ++plan->launches;
     } else if (plan->cls.n_res > 0) {
-      m2l_pair_kernel<<<nb, threads, sh, s>>>(nb, plan->cls.res_off.p, plan->cls.res_src.p, T.center.p, P, C,
-                                             plan->M.p, plan->L.p, 1);
+      m2l_pair_kernel<<<plan->cls.n_res_boxes, threads, sh, s>>>(plan->cls.n_res_boxes, plan->cls.res_boxes.p,
+                                                                plan->cls.res_off.p, plan->cls.res_src.p,
+                                                                T.center.p, P, C, plan->M.p, plan->L.p, 1);
       ++plan->launches;
     }
   }
@@ -461,6 +494,27 @@ void laplace_execute(fmmb_plan* plan, const double* d_charges, double* d_results
   FMMB_CUDA(cudaEventRecord(ev[5], s));
   FMMB_CUDA(cudaGetLastError());
   plan->timed = true;
+}
+
+// Plan-time: P2P work items (target leaf chunks of <= 32 bodies), in leaf order.
+void build_p2p_items(fmmb_plan* plan) {
+  Tree& T = plan->tree;
+  cudaStream_t s = plan->stream;
+  DevBuf<int> cnt;
+  cnt.resize(T.nleaves + 1);
+  p2p_count_items<<<nblk(T.nleaves + 1, 256), 256, 0, s>>>(T.leaves.p, T.nleaves, T.bbegin.p, T.bend.p, cnt.p);
+  FMMB_CUDA(cudaGetLastError());
+  std::vector<int> h = cnt.to_host(s);
+  std::vector<int> off(T.nleaves + 1, 0);
+  for (int i = 0; i < T.nleaves; ++i) off[i + 1] = off[i] + h[i];
+  T.n_p2p_items = off[T.nleaves];
+  DevBuf<int> doff;
+  doff.from_host(off.data(), off.size(), s);
+  T.p2p_items.resize(T.n_p2p_items);
+  p2p_fill_items<<<nblk(T.nleaves, 256), 256, 0, s>>>(T.leaves.p, T.nleaves, T.bbegin.p, T.bend.p, doff.p,
+                                                     T.p2p_items.p);
+  FMMB_CUDA(cudaGetLastError());
+  FMMB_CUDA(cudaStreamSynchronize(s));
 }
 
 void laplace_direct_raw(const double* d_spts, const double* d_q, int64_t ns, const double* d_tpts, int64_t nt,

@@ -29,7 +29,7 @@ namespace {
 using namespace ops;
 
 constexpr int kNB = 64;           // pairs (columns) per pipeline stage
-constexpr int kMinPopM2L = 24;    // smallest M2L class that is worth a GEMM tile
+constexpr int kMinPopM2L = 1;     // smallest M2L class that is worth a GEMM tile
 
 __host__ __device__ __forceinline__ unsigned compact10(unsigned x) {
   x &= 0x09249249u;
@@ -225,30 +225,58 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
 
-// column stride of a staged tile: even (16-byte rows) with an odd number of 16-byte units, so the
-// 8 column groups of a warp hit distinct banks
-__host__ __device__ inline int gemm_ldb(int xs) { return ((xs / 2) & 1) ? xs : xs + 2; }
+// Tile geometry per expansion order.  8 warps = WR (rows) x WC (columns); a warp owns RB row blocks
+// and CB column blocks of 8x8 (the DMMA shape), CB = WR so that WC * CB * 8 = 64 columns.
+template <int P>
+struct GemmCfg {
+  static constexpr int PP = P * P;
+  static constexpr int XS = (PP + 1) & ~1;              // doubles per expansion in global memory
+  static constexpr int KB = (PP + 3) / 4;               // k blocks of 4
+  static constexpr int WR = PP > 32 ? 4 : (PP > 16 ? 2 : 1);
+  static constexpr int RB = PP > 48 ? 2 : (PP > 32 ? 2 : (PP > 24 ? 3 : (PP > 8 ? 2 : 1)));
+  static constexpr int WC = 8 / WR;
+  static constexpr int CB = WR;
+  static constexpr int KMAX = KB * 4 > XS ? KB * 4 : XS;
+  // column stride: multiple of 2 (16-byte cp.async rows), congruent 4 mod 16 so that the 8 columns x 4 k
+  // of one B fragment cover all 16 eight-byte banks exactly twice
+  static constexpr int LDB = KMAX + ((4 - KMAX % 16) + 16) % 16;
+  static_assert(WR * RB * 8 >= PP, "row tiles must cover the expansion");
+};
 
-template <int RT, bool ACC>
+__device__ __forceinline__ void dmma8x8x4(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+               : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+// C[rows x 64] = T_c * B with FP64 tensor-core MMAs (DMMA.8x8x4).  The T_c fragments of a warp live in
+// REGISTERS for as long as consecutive items share the class; only the source expansions pass through
+// shared memory (cp.async double buffer).
+template <int P, bool ACC>
 __global__ void __launch_bounds__(256, 2)
-trans_gemm_kernel(int P, int ldT, const double* __restrict__ Tt, int n_items, const int* __restrict__ item_class,
+trans_gemm_kernel(int ldT, const double* __restrict__ Tt, int n_items, const int* __restrict__ item_class,
                   const int* __restrict__ item_start, const int* __restrict__ item_count,
                   const int* __restrict__ sorted_slot, const int* __restrict__ slot_src,
                   const double* __restrict__ X, double* __restrict__ tmp, double* __restrict__ Out) {
-  constexpr int ROWS = 16 * RT;
-  const int pp = P * P, xs = xstride(P), ldb = gemm_ldb(xs);
-  extern __shared__ __align__(16) double smem[];
-  double* Ts = smem;                              // [xs][ROWS], row k = pp is zero when pp is odd
-  double* Bs0 = smem + (size_t)xs * ROWS;         // 2 x [kNB][ldb], real layout as in global memory
+  using G = GemmCfg<P>;
+  constexpr int PP = G::PP, XS = G::XS, KB = G::KB, RB = G::RB, CB = G::CB, LDB = G::LDB;
+  extern __shared__ __align__(16) double smem[];        // 2 x [kNB][LDB]
   __shared__ int s_slot[2][kNB], s_src[2][kNB];
   const int per = (n_items + gridDim.x - 1) / gridDim.x;
   const int i0 = blockIdx.x * per, i1 = min(n_items, i0 + per);
   if (i0 >= i1) return;
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int wr = w & 3, wc = w >> 2, rg = lane & 3, cg = lane >> 2;
-  const int row0 = wr * 4 * RT + rg * RT;
-  const int col0 = wc * 32 + cg;
-  const int chunks = xs / 2;                      // 16-byte pieces per expansion
+  const int wr = w % G::WR, wc = w / G::WR;
+  const int lr = lane >> 2, lk = lane & 3;
+  const int row_base = wr * RB * 8 + lr;                 // + 8 rb
+  const int col_base = wc * CB * 8;                      // + 8 cb
+  constexpr int chunks = XS / 2;
+
+  // k positions beyond the copied expansion (k-block padding) stay zero for the whole kernel
+  if (G::KMAX > XS)
+    for (int idx = threadIdx.x; idx < 2 * kNB * (G::KMAX - XS); idx += 256) {
+      int colb = idx / (G::KMAX - XS), k = XS + idx % (G::KMAX - XS);
+      smem[(size_t)colb * LDB + k] = 0.0;
+    }
 
   auto stage_indices = [&](int it, int buf) {
     if (threadIdx.x < kNB) {
@@ -259,17 +287,18 @@ trans_gemm_kernel(int P, int ldT, const double* __restrict__ Tt, int n_items, co
     }
   };
   auto stage_copy = [&](int buf) {
-    double* Bs = Bs0 + (size_t)buf * kNB * ldb;
+    double* Bs = smem + (size_t)buf * kNB * LDB;
     for (int idx = threadIdx.x; idx < kNB * chunks; idx += 256) {
       int col = idx / chunks, ch = idx - col * chunks;
       int src = s_src[buf][col];
-      double* dst = Bs + col * ldb + 2 * ch;
-      if (src >= 0) cp_async16(dst, X + (size_t)src * xs + 2 * ch);
+      double* dst = Bs + col * LDB + 2 * ch;
+      if (src >= 0) cp_async16(dst, X + (size_t)src * XS + 2 * ch);
       else { dst[0] = 0.0; dst[1] = 0.0; }
     }
     cp_async_commit();
   };
 
+  double A[RB][KB];
   int cur = -1, buf = 0;
   stage_indices(i0, 0);
   __syncthreads();
@@ -278,10 +307,13 @@ trans_gemm_kernel(int P, int ldT, const double* __restrict__ Tt, int n_items, co
     const int c = item_class[it];
     if (c != cur) {
       const double* Tc = Tt + (size_t)c * ldT * ldT;
-      for (int idx = threadIdx.x; idx < xs * ROWS; idx += 256) {
-        int k = idx / ROWS, row = idx - k * ROWS;
-        Ts[idx] = (row < pp && k < pp) ? Tc[(size_t)k * ldT + row] : 0.0;
-      }
+#pragma unroll
+      for (int rb = 0; rb < RB; ++rb)
+#pragma unroll
+        for (int kb = 0; kb < KB; ++kb) {
+          int row = row_base + 8 * rb, k = kb * 4 + lk;
+          A[rb][kb] = (row < PP && k < PP) ? Tc[(size_t)k * ldT + row] : 0.0;
+        }
       cur = c;
     }
     const bool more = it + 1 < i1;
@@ -290,60 +322,38 @@ trans_gemm_kernel(int P, int ldT, const double* __restrict__ Tt, int n_items, co
     if (more) { stage_copy(buf ^ 1); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
     __syncthreads();
 
-    const double* Bs = Bs0 + (size_t)buf * kNB * ldb;
-    double acc[RT][4];
+    const double* Bs = smem + (size_t)buf * kNB * LDB + (size_t)(col_base + lr) * LDB + lk;
+    double C[RB][CB][2];
 #pragma unroll
-    for (int r = 0; r < RT; ++r)
+    for (int rb = 0; rb < RB; ++rb)
 #pragma unroll
-      for (int j = 0; j < 4; ++j) acc[r][j] = 0.0;
-    const double* a_ptr = Ts + row0;
-    const double* b_ptr = Bs + col0 * ldb;
-    const int kend = pp & ~1;
-#pragma unroll 2
-    for (int k = 0; k < kend; k += 2) {
-      double a0[RT], a1[RT];
-      double2 b[4];
+      for (int cb = 0; cb < CB; ++cb) C[rb][cb][0] = C[rb][cb][1] = 0.0;
 #pragma unroll
-      for (int r = 0; r < RT; ++r) { a0[r] = a_ptr[k * ROWS + r]; a1[r] = a_ptr[(k + 1) * ROWS + r]; }
+    for (int kb = 0; kb < KB; ++kb) {
+      double bf[CB];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) b[j] = *reinterpret_cast<const double2*>(b_ptr + j * 8 * ldb + k);
+      for (int cb = 0; cb < CB; ++cb) bf[cb] = Bs[cb * 8 * LDB + kb * 4];
 #pragma unroll
-      for (int r = 0; r < RT; ++r)
+      for (int rb = 0; rb < RB; ++rb)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[r][j] = fma(a0[r], b[j].x, acc[r][j]);
-#pragma unroll
-      for (int r = 0; r < RT; ++r)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) acc[r][j] = fma(a1[r], b[j].y, acc[r][j]);
-    }
-    if (pp & 1) {
-      const int k = pp - 1;
-#pragma unroll
-      for (int r = 0; r < RT; ++r)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) acc[r][j] = fma(a_ptr[k * ROWS + r], b_ptr[j * 8 * ldb + k], acc[r][j]);
+        for (int cb = 0; cb < CB; ++cb) dmma8x8x4(C[rb][cb][0], C[rb][cb][1], A[rb][kb], bf[cb]);
     }
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int sl = s_slot[buf][col0 + 8 * j];
-      if (sl < 0) continue;
-      if (!ACC) {
-        double* o = tmp + (size_t)sl * xs + row0;
-        if (RT % 2 == 0 && row0 + RT <= pp) {
+    for (int cb = 0; cb < CB; ++cb)
 #pragma unroll
-          for (int r = 0; r < RT; r += 2) *reinterpret_cast<double2*>(o + r) = make_double2(acc[r][j], acc[r + 1][j]);
-        } else {
+      for (int i = 0; i < 2; ++i) {
+        const int sl = s_slot[buf][col_base + cb * 8 + 2 * lk + i];
+        if (sl < 0) continue;
+        double* o = (ACC ? Out : tmp) + (size_t)sl * XS;
 #pragma unroll
-          for (int r = 0; r < RT; ++r)
-            if (row0 + r < pp) o[r] = acc[r][j];
+        for (int rb = 0; rb < RB; ++rb) {
+          int row = row_base + 8 * rb;
+          if (row < PP) {
+            if (ACC) o[row] += C[rb][cb][i];
+            else o[row] = C[rb][cb][i];
+          }
         }
-      } else {
-        double* o = Out + (size_t)sl * xs + row0;
-#pragma unroll
-        for (int r = 0; r < RT; ++r)
-          if (row0 + r < pp) o[r] += acc[r][j];
       }
-    }
     __syncthreads();
   }
 }
@@ -388,26 +398,23 @@ m2m_reduce_kernel(int lo, int hi, const unsigned* __restrict__ key, const unsign
   }
 }
 
-template <int RT, bool ACC>
-void launch_gemm_t(const TransBatch& B, int P, int first, int count, const double* X, double* tmp,
-                   double* out, cudaStream_t s) {
-  const int xs = xstride(P);
-  size_t sh = ((size_t)xs * 16 * RT + (size_t)2 * kNB * gemm_ldb(xs)) * sizeof(double);
-  static size_t attr = 0;
+template <int P, bool ACC>
+void launch_gemm_t(const TransBatch& B, int first, int count, const double* X, double* tmp, double* out,
+                   cudaStream_t s) {
+  size_t sh = (size_t)2 * kNB * GemmCfg<P>::LDB * sizeof(double);
+  static bool attr = false;
   static int sms = 0;
-  if (sh > attr) {
-    FMMB_CUDA(cudaFuncSetAttribute(trans_gemm_kernel<RT, ACC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh));
-    attr = sh;
-  }
-  if (!sms) {
+  if (!attr) {
+    FMMB_CUDA(cudaFuncSetAttribute(trans_gemm_kernel<P, ACC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh));
     int dev = 0;
     FMMB_CUDA(cudaGetDevice(&dev));
     FMMB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    attr = true;
   }
   int grid = std::min(count, 2 * sms);
-  trans_gemm_kernel<RT, ACC><<<grid, 256, sh, s>>>(P, B.built_p * B.built_p, B.T.p, count, B.item_class.p + first,
-                                                  B.item_start.p + first, B.item_count.p + first,
-                                                  B.sorted_slot.p, B.slot_src_p, X, tmp, out);
+  trans_gemm_kernel<P, ACC><<<grid, 256, sh, s>>>(B.built_p * B.built_p, B.T.p, count, B.item_class.p + first,
+                                                 B.item_start.p + first, B.item_count.p + first,
+                                                 B.sorted_slot.p, B.slot_src_p, X, tmp, out);
   FMMB_CUDA(cudaGetLastError());
 }
 template <bool ACC>
@@ -415,10 +422,14 @@ void launch_gemm(const TransBatch& B, int P, int first, int count, const double*
                  cudaStream_t s) {
   if (count <= 0) return;
   switch (P) {
-    case 1: case 2: case 3: case 4: launch_gemm_t<1, ACC>(B, P, first, count, X, tmp, out, s); break;
-    case 5: launch_gemm_t<2, ACC>(B, P, first, count, X, tmp, out, s); break;
-    case 6: launch_gemm_t<3, ACC>(B, P, first, count, X, tmp, out, s); break;
-    default: launch_gemm_t<4, ACC>(B, P, first, count, X, tmp, out, s); break;
+    case 1: launch_gemm_t<1, ACC>(B, first, count, X, tmp, out, s); break;
+    case 2: launch_gemm_t<2, ACC>(B, first, count, X, tmp, out, s); break;
+    case 3: launch_gemm_t<3, ACC>(B, first, count, X, tmp, out, s); break;
+    case 4: launch_gemm_t<4, ACC>(B, first, count, X, tmp, out, s); break;
+    case 5: launch_gemm_t<5, ACC>(B, first, count, X, tmp, out, s); break;
+    case 6: launch_gemm_t<6, ACC>(B, first, count, X, tmp, out, s); break;
+    case 7: launch_gemm_t<7, ACC>(B, first, count, X, tmp, out, s); break;
+    default: launch_gemm_t<8, ACC>(B, first, count, X, tmp, out, s); break;
   }
 }
 
@@ -505,6 +516,13 @@ void classify(fmmb_plan* plan, TransBatch& B, const int* tgt, const int* src, in
     B.res_src.resize(n_res); B.res_off.resize(T.nboxes + 1);
     if (n_res) residual_compact<<<nblk(n, 256), 256, 0, s>>>(flag.p, pos.p, n, src, B.res_src.p);
     residual_offsets<<<nblk(T.nboxes + 1, 256), 256, 0, s>>>(T.m2l_off.p, pos.p, T.nboxes, B.res_off.p);
+    {
+      // boxes that own residual pairs (few): the per-pair kernel is launched over these only
+      std::vector<int> ho = B.res_off.to_host(s), list;
+      for (int b = 0; b < T.nboxes; ++b) if (ho[b + 1] > ho[b]) list.push_back(b);
+      B.n_res_boxes = (int)list.size();
+      B.res_boxes.from_host(list.data(), list.size(), s);
+    }
   }
   FMMB_CUDA(cudaGetLastError());
   FMMB_CUDA(cudaStreamSynchronize(s));
