@@ -252,38 +252,59 @@ def bench_ours(args, rank, world, local_rank):
             dist.destroy_process_group()
         return
 
-    # rooflines (algorithmic flops from SURVEY.md section 8(d): 7 P^3 (P+1) per M2L pair, 22 per P2P body pair)
-    P = args.p
-    peak = np.zeros(1)
+    # rooflines.  Algorithmic work per matvec as defined in SURVEY.md section 8(d):
+    #   M2L 7 P^3 (P+1) flop per pair (the reference's complex O(P^4) contraction), P2P 22 flop per body pair.
+    # "executed" = flops the sm_100a kernels actually issue: the batched M2L multiplies a real P^2 x P^2
+    # translation matrix (2 P^4 flop per pair); P2P issues 19 FP64 instructions (25 flop) per body pair.
     import ctypes
-    pk = ctypes.c_double()
-    F.capi.check(lib.fmmb_measure_fp64_peak(local_rank, ctypes.byref(pk)))
-    fp64_peak = pk.value
+    P = args.p
+    pk_fma, pk_mma = ctypes.c_double(), ctypes.c_double()
+    F.capi.check(lib.fmmb_measure_fp64_peak(local_rank, ctypes.byref(pk_fma), ctypes.byref(pk_mma)))
+    fp64_peak = max(pk_fma.value, pk_mma.value)
     m2l_ms = phase_acc["m2l"] / args.steps
+    gemm_ms = phase_acc["m2l_gemm"] / args.steps
     p2p_ms = phase_acc["p2p"] / args.steps
     m2l_flop = 7.0 * P ** 3 * (P + 1) * info.n_m2l_pairs
+    gemm_exec_flop = 2.0 * P ** 4 * info.n_m2l_pairs_batched
     p2p_flop = 22.0 * info.n_p2p_body_pairs
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
-    dominant = "m2l" if m2l_ms >= p2p_ms else "p2p"
-    dom_ms, dom_flop = (m2l_ms, m2l_flop) if dominant == "m2l" else (p2p_ms, p2p_flop)
+    tf = lambda flop, ms_: flop / (ms_ * 1e-3) / 1e12 if ms_ > 0 else 0.0
+    kernels = {
+        "p2p_kernel": {"ms": p2p_ms, "algorithmic_flop": p2p_flop, "achieved": tf(p2p_flop, p2p_ms)},
+        "trans_gemm_kernel(M2L)": {"ms": gemm_ms if gemm_ms > 0 else m2l_ms, "algorithmic_flop": m2l_flop,
+                                   "achieved": tf(m2l_flop, gemm_ms if gemm_ms > 0 else m2l_ms),
+                                   "executed_flop": gemm_exec_flop,
+                                   "executed_tflops": tf(gemm_exec_flop, gemm_ms) if gemm_ms > 0 else None},
+    }
+    dominant = max(kernels, key=lambda k: kernels[k]["ms"])
+    dk = kernels[dominant]
     roofline = {
-        "kernel": dominant, "bound": "fp64", "achieved": dom_flop / (dom_ms * 1e-3) / 1e12, "peak": fp64_peak,
-        "unit": "TFLOP/s", "frac": dom_flop / (dom_ms * 1e-3) / 1e12 / fp64_peak, "traffic": None,
-        "peak_source": "DFMA microbenchmark in this process (fmmb_measure_fp64_peak); MEASURED_PEAKS.json has no FP64 entry",
-        "algorithmic_flop_per_launch": dom_flop, "ms_per_launch": dom_ms,
+        "kernel": dominant, "bound": "fp64", "achieved": dk["achieved"], "peak": fp64_peak, "unit": "TFLOP/s",
+        "frac": dk["achieved"] / fp64_peak, "traffic": None,
+        "peak_source": "measured in this process by fmmb_measure_fp64_peak: DFMA %.1f, DMMA.8x8x4 %.1f TFLOP/s "
+                       "(MEASURED_PEAKS.json has no FP64 entry)" % (pk_fma.value, pk_mma.value),
+        "algorithmic_flop_per_launch": dk["algorithmic_flop"], "ms_per_launch": dk["ms"],
         "hbm_gbs_measured": peaks.get("hbm_gbs"),
     }
     others = {
-        "m2l": {"ms": m2l_ms, "tflops_algorithmic": m2l_flop / (m2l_ms * 1e-3) / 1e12,
-                "frac_fp64_peak": m2l_flop / (m2l_ms * 1e-3) / 1e12 / fp64_peak, "pairs": info.n_m2l_pairs},
-        "p2p": {"ms": p2p_ms, "tflops_algorithmic": p2p_flop / (p2p_ms * 1e-3) / 1e12,
-                "frac_fp64_peak": p2p_flop / (p2p_ms * 1e-3) / 1e12 / fp64_peak, "body_pairs": info.n_p2p_body_pairs},
+        "m2l": {"ms": m2l_ms, "gemm_ms": gemm_ms, "reduce_ms": m2l_ms - gemm_ms if gemm_ms > 0 else None,
+                "tflops_algorithmic_gemm": kernels["trans_gemm_kernel(M2L)"]["achieved"],
+                "tflops_executed_gemm": kernels["trans_gemm_kernel(M2L)"]["executed_tflops"],
+                "frac_fp64_peak_executed": (kernels["trans_gemm_kernel(M2L)"]["executed_tflops"] or 0) / fp64_peak,
+                "pairs": info.n_m2l_pairs, "pairs_batched": info.n_m2l_pairs_batched, "classes": info.n_m2l_classes,
+                "reduce_gbs": (info.n_m2l_pairs * ((P * P + 1) // 2 * 2) * 8) / ((m2l_ms - gemm_ms) * 1e-3) / 1e9
+                if gemm_ms > 0 and m2l_ms > gemm_ms else None},
+        "p2p": {"ms": p2p_ms, "tflops_algorithmic": tf(p2p_flop, p2p_ms),
+                "frac_fp64_peak": tf(p2p_flop, p2p_ms) / fp64_peak,
+                "fp64_instr_issue_frac": 19.0 * info.n_p2p_body_pairs / (p2p_ms * 1e-3) / (pk_fma.value * 1e12 / 2)
+                if p2p_ms > 0 else None,
+                "body_pairs": info.n_p2p_body_pairs},
         "upward_ms": phase_acc["upward"] / args.steps, "downward_ms": phase_acc["downward"] / args.steps,
-        "total_ms": phase_acc["total"] / args.steps,
+        "total_ms_serialised": phase_acc["total"] / args.steps,
     }
 
     cpu = None

@@ -161,7 +161,7 @@ class FMM_plan:
         ms = np.zeros(capi.T_COUNT)
         capi.check(self._lib.fmmb_plan_phase_times(self._h, capi.ptr(ms), capi.T_COUNT))
         return {"total": ms[0], "upward": ms[1], "m2l": ms[2], "downward": ms[3], "p2p": ms[4],
-                "h2d": ms[5], "d2h": ms[6], "launches": int(ms[7])}
+                "h2d": ms[5], "d2h": ms[6], "launches": int(ms[7]), "m2l_gemm": ms[8]}
 
     def tree(self):
         """Copies of the device tree and lists (see include/fmmb.h: fmmb_plan_get_tree)."""

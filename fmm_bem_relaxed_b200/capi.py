@@ -13,7 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libfmmb200.so")
 
 FMMB_MAX_P = 16
-T_TOTAL, T_UPWARD, T_M2L, T_DOWNWARD, T_P2P, T_H2D, T_D2H, T_COUNT = 0, 1, 2, 3, 4, 5, 6, 8
+T_TOTAL, T_UPWARD, T_M2L, T_DOWNWARD, T_P2P, T_H2D, T_D2H, T_LAUNCHES, T_M2L_GEMM, T_COUNT = 0, 1, 2, 3, 4, 5, 6, 7, 8, 10
 LAPLACE_SPHERICAL = 0
 
 
@@ -85,7 +85,7 @@ def load():
     lib.fmmb_plan_destroy.restype = None
     lib.fmmb_last_error.restype = ctypes.c_char_p
     lib.fmmb_version.restype = ctypes.c_char_p
-    lib.fmmb_measure_fp64_peak.argtypes = [i32, ctypes.POINTER(ctypes.c_double)]
+    lib.fmmb_measure_fp64_peak.argtypes = [i32, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]
     _lib = lib
     return lib
 

@@ -42,6 +42,7 @@ static void update_phase_times(fmmb_plan* plan) {
   plan->phase_ms[FMMB_T_DOWNWARD] = ms(3, 4);
   plan->phase_ms[FMMB_T_P2P] = ms(6, 7);
   plan->phase_ms[FMMB_T_LAUNCHES] = plan->launches;
+  plan->phase_ms[FMMB_T_M2L_GEMM] = plan->m2l_gemm_timed ? ms(13, 14) : 0.0;
 }
 }  // namespace fmmb
 
@@ -263,8 +264,7 @@ int fmmb_plan_phase_times(fmmb_plan* plan, double* ms, int count) {
   return FMMB_OK;
 }
 
-int fmmb_measure_fp64_peak(int device, double* tflops) {
-  if (!tflops) { set_error("null argument"); return FMMB_ERR_INVALID; }
+int fmmb_measure_fp64_peak(int device, double* tflops_dfma, double* tflops_dmma) {
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
     cudaGetLastError();
@@ -273,7 +273,10 @@ int fmmb_measure_fp64_peak(int device, double* tflops) {
   }
   return guarded([&] {
     if (device >= 0) FMMB_CUDA(cudaSetDevice(device));
-    *tflops = measure_fp64_peak();
+    double a = 0, b = 0;
+    measure_fp64_peak(&a, &b);
+    if (tflops_dfma) *tflops_dfma = a;
+    if (tflops_dmma) *tflops_dmma = b;
   });
 }
 

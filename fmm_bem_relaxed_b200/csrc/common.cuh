@@ -160,6 +160,7 @@ struct fmmb_plan {
   fmmb::DevBuf<double> results;      // original order staging, 4n
   double phase_ms[FMMB_T_COUNT] = {0};
   bool timed = false;
+  bool m2l_gemm_timed = false;
   bool overlap_p2p = true;
   int launches = 0;                  // kernel launches of the last execute
 };
@@ -173,7 +174,7 @@ void laplace_execute(fmmb_plan* plan, const double* d_charges, double* d_results
 void build_p2p_items(fmmb_plan* plan);
 void laplace_direct_raw(const double* d_spts, const double* d_q, int64_t ns, const double* d_tpts, int64_t nt,
                         double* d_out, cudaStream_t s);
-double measure_fp64_peak();
+void measure_fp64_peak(double* dfma, double* dmma);
 // m2l_classes.cu
 void m2l_init_tables();
 void build_m2l_classes(fmmb_plan* plan);

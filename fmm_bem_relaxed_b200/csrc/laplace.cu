@@ -366,18 +366,39 @@ direct_kernel(const double* __restrict__ spts, const double* __restrict__ q, int
   if (act) out[i] = make_double4(pot, fx, fy, fz);
 }
 
-// ---- FP64 FMA peak: 8 independent chains per thread -----------------------------------------------
+// ---- FP64 peaks: independent chains of DFMA, and of DMMA.8x8x4 (FP64 tensor core) ------------------
 __global__ void __launch_bounds__(256)
 dfma_peak_kernel(double* out, int iters, double a, double b) {
-  double x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
-  for (int i = 0; i < iters; ++i) {
+  double x[8];
 #pragma unroll
-    for (int u = 0; u < 8; ++u) {
-      x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
-      x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
-    }
+  for (int i = 0; i < 8; ++i) x[i] = threadIdx.x + i;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int u = 0; u < 8; ++u)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) x[i] = fma(x[i], a, b);
   }
-  double s = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
+  double s = 0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s += x[i];
+  if (s == 12345.678) out[0] = s;
+}
+__global__ void __launch_bounds__(256)
+dmma_peak_kernel(double* out, int iters, double a, double b) {
+  double c[8][2];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) c[i][0] = c[i][1] = threadIdx.x + i;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                     : "+d"(c[i][0]), "+d"(c[i][1]) : "d"(a), "d"(b));
+  }
+  double s = 0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s += c[i][0] + c[i][1];
   if (s == 12345.678) out[0] = s;
 }
 
@@ -523,7 +544,7 @@ void laplace_direct_raw(const double* d_spts, const double* d_q, int64_t ns, con
   FMMB_CUDA(cudaGetLastError());
 }
 
-double measure_fp64_peak() {
+void measure_fp64_peak(double* dfma, double* dmma) {
   int dev = 0, sms = 0;
   FMMB_CUDA(cudaGetDevice(&dev));
   FMMB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
@@ -532,21 +553,26 @@ double measure_fp64_peak() {
   cudaEvent_t a, b;
   FMMB_CUDA(cudaEventCreate(&a));
   FMMB_CUDA(cudaEventCreate(&b));
-  const int iters = 4096, blocks = sms * 8, threads = 256;
-  double best = 0;
-  for (int rep = 0; rep < 5; ++rep) {
-    FMMB_CUDA(cudaEventRecord(a));
-    dfma_peak_kernel<<<blocks, threads>>>(out, iters, 1.0000001, 1e-9);
-    FMMB_CUDA(cudaEventRecord(b));
-    FMMB_CUDA(cudaEventSynchronize(b));
-    float ms = 0;
-    FMMB_CUDA(cudaEventElapsedTime(&ms, a, b));
-    double flops = 2.0 * 64.0 * iters * (double)blocks * threads;
-    double tf = flops / (ms * 1e-3) / 1e12;
-    if (rep > 0 && tf > best) best = tf;
-  }
+  const int iters = 2048, blocks = sms * 8, threads = 256;
+  double best[2] = {0, 0};
+  for (int rep = 0; rep < 4; ++rep)
+    for (int which = 0; which < 2; ++which) {
+      FMMB_CUDA(cudaEventRecord(a));
+      if (which == 0) dfma_peak_kernel<<<blocks, threads>>>(out, iters, 1.0000001, 1e-9);
+      else dmma_peak_kernel<<<blocks, threads>>>(out, iters, 1.0000001, 1e-9);
+      FMMB_CUDA(cudaEventRecord(b));
+      FMMB_CUDA(cudaEventSynchronize(b));
+      float ms = 0;
+      FMMB_CUDA(cudaEventElapsedTime(&ms, a, b));
+      // DFMA: 64 fma per thread per iteration; DMMA: 32 mma x 256 fma per warp per iteration
+      double flops = which == 0 ? 2.0 * 64.0 * iters * (double)blocks * threads
+                                : 2.0 * 256.0 * 32.0 * iters * (double)blocks * (threads / 32);
+      double tf = flops / (ms * 1e-3) / 1e12;
+      if (rep > 0 && tf > best[which]) best[which] = tf;
+    }
   cudaEventDestroy(a); cudaEventDestroy(b); cudaFree(out);
-  return best;
+  *dfma = best[0];
+  *dmma = best[1];
 }
 
 }  // namespace fmmb

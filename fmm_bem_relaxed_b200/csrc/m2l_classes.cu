@@ -265,18 +265,21 @@ trans_gemm_kernel(int ldT, const double* __restrict__ Tt, int n_items, const int
   const int i0 = blockIdx.x * per, i1 = min(n_items, i0 + per);
   if (i0 >= i1) return;
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int wr = w % G::WR, wc = w / G::WR;
+  const int wr = w % G::WR, wc = w / G::WR;              // wc < G::WC
+  static_assert(G::WR * G::WC == 8, "8 warps");
   const int lr = lane >> 2, lk = lane & 3;
   const int row_base = wr * RB * 8 + lr;                 // + 8 rb
   const int col_base = wc * CB * 8;                      // + 8 cb
   constexpr int chunks = XS / 2;
 
   // k positions beyond the copied expansion (k-block padding) stay zero for the whole kernel
-  if (G::KMAX > XS)
-    for (int idx = threadIdx.x; idx < 2 * kNB * (G::KMAX - XS); idx += 256) {
-      int colb = idx / (G::KMAX - XS), k = XS + idx % (G::KMAX - XS);
+  if constexpr (G::KMAX > XS) {
+    constexpr int extra = G::KMAX - XS;
+    for (int idx = threadIdx.x; idx < 2 * kNB * extra; idx += 256) {
+      int colb = idx / extra, k = XS + idx % extra;
       smem[(size_t)colb * LDB + k] = 0.0;
     }
+  }
 
   auto stage_indices = [&](int it, int buf) {
     if (threadIdx.x < kNB) {
@@ -587,7 +590,10 @@ bool m2l_batched(fmmb_plan* plan, cudaStream_t s) {
   if (C.n_items == 0 || P > 8) return false;
   ensure_T(plan, C, s);
   C.tmp.resize((size_t)T.n_lr * xs);
+  FMMB_CUDA(cudaEventRecord(plan->ev[13], s));
   launch_gemm<false>(C, P, 0, C.n_items, plan->M.p, C.tmp.p, nullptr, s);
+  FMMB_CUDA(cudaEventRecord(plan->ev[14], s));
+  plan->m2l_gemm_timed = true;
   ++plan->launches;
   int threads = pp < 64 ? 64 : (pp > 256 ? 256 : pp);
   m2l_reduce_kernel<<<T.nboxes, threads, 0, s>>>(T.nboxes, T.m2l_off.p, C.batched.p, P,

@@ -101,10 +101,11 @@ typedef struct {
 
 /* Phase indices for fmmb_plan_phase_times (milliseconds, CUDA events, last execute). */
 enum {
-  FMMB_T_TOTAL = 0, FMMB_T_UPWARD = 1, FMMB_T_M2L = 2, FMMB_T_DOWNWARD = 3, FMMB_T_P2P = 4,
+  FMMB_T_TOTAL = 0, FMMB_T_UPWARD = 1, FMMB_T_M2L = 2 /* GEMM + reduction */, FMMB_T_DOWNWARD = 3, FMMB_T_P2P = 4,
   FMMB_T_H2D = 5, FMMB_T_D2H = 6,
   FMMB_T_LAUNCHES = 7, /* number of kernel launches of the last execute (a count, not ms) */
-  FMMB_T_COUNT = 8
+  FMMB_T_M2L_GEMM = 8,  /* the batched M2L contraction kernel alone */
+  FMMB_T_COUNT = 10
 };
 
 /* FMM_plan<K>(K, sources, opts): builds the octree and all interaction lists on the device.
@@ -170,9 +171,10 @@ const char* fmmb_last_error(void);
 /* Library build info: "fmmb200 <version> sm_100a". */
 const char* fmmb_version(void);
 
-/* Utility used by bench.py for the FP64 roofline: runs a dependent-free DFMA loop on every SM
- * and returns achieved FP64 TFLOP/s (2 flop per DFMA). */
-int fmmb_measure_fp64_peak(int device, double* tflops);
+/* Utility used by bench.py for the FP64 roofline: runs dependent-free loops of (a) DFMA and (b) FP64
+ * tensor-core MMAs (mma.sync m8n8k4 f64 = DMMA.8x8x4) on every SM and returns the achieved FP64
+ * TFLOP/s of each (2 flop per multiply-add).  Either pointer may be NULL. */
+int fmmb_measure_fp64_peak(int device, double* tflops_dfma, double* tflops_dmma);
 
 #ifdef __cplusplus
 }

@@ -60,7 +60,7 @@ def test_no_cpu_fallback():
         F.FMM_plan(F.LaplaceSpherical(5), np.random.rand(100, 3))
     assert e.value.status == -5
     t = ctypes.c_double()
-    assert capi.load().fmmb_measure_fp64_peak(0, ctypes.byref(t)) == -5
+    assert capi.load().fmmb_measure_fp64_peak(0, ctypes.byref(t), None) == -5
 
 
 def test_product_does_not_import_the_oracle():
