@@ -1,0 +1,90 @@
+#pragma once
+/** @file FMM_plan.hpp
+ * FMM_plan<Kernel> with the reference's surface (reference include/FMM_plan.hpp:15-128):
+ *   FMM_plan(const Kernel&, const std::vector<source_type>&, FMMOptions&)
+ *   std::vector<result_type> execute(const std::vector<charge_type>&)
+ *   kernel_type& kernel();   FMMOptions& options();
+ * Everything below it -- octree, interaction lists, P2M/M2M/M2L/L2L/L2P/P2P -- runs on the GPU
+ * through the C ABI of include/fmmb.h (libfmmb200.so).  The plan copies the kernel and the options
+ * like the reference does; kernel().set_p(p) is picked up by the next execute.
+ * Differences on purpose: move-only (the reference's implicit copy would double free);
+ * no per-matvec printf; errors are reported on stderr and leave an empty result like the
+ * reference's "[E]" path (:79-82).
+ */
+#include <cstdio>
+#include <iostream>
+#include <vector>
+
+#include "Vec.hpp"
+#include "FMMOptions.hpp"
+#include "Direct.hpp"
+#include "timing.hpp"
+#include "../../include/fmmb.h"
+
+template <class Kernel>
+class FMM_plan {
+ public:
+  typedef Kernel kernel_type;
+  typedef typename kernel_type::point_type point_type;
+  typedef typename kernel_type::source_type source_type;
+  typedef typename kernel_type::target_type target_type;
+  typedef typename kernel_type::charge_type charge_type;
+  typedef typename kernel_type::result_type result_type;
+
+  FMM_plan(const kernel_type& k, const std::vector<source_type>& source, FMMOptions& opts)
+      : plan_(nullptr), K(k), opts_(opts), n_(source.size()) {
+    // sources -> plain point array (point kernels: source_type == point_type)
+    std::vector<double> pts(3 * n_);
+    for (size_t i = 0; i < n_; ++i) {
+      const point_type p = static_cast<point_type>(source[i]);
+      pts[3 * i] = p[0]; pts[3 * i + 1] = p[1]; pts[3 * i + 2] = p[2];
+    }
+    fmmb_kernel_desc kd = {Kernel::fmmb_kind, K.order(), K.kappa(), 0, 0};
+    fmmb_sources src = {(int64_t)n_, pts.data()};
+    fmmb_options fo = {};
+    fo.theta = opts_.MAC().theta_;
+    fo.ncrit = opts_.max_per_box();
+    fo.evaluator = opts_.evaluator == FMMOptions::FMM ? FMMB_EVAL_FMM : FMMB_EVAL_TREECODE;
+    fo.device = opts_.device;
+    if (fmmb_plan_create(&kd, &src, &fo, &plan_) != FMMB_OK) {
+      std::cerr << "[E]: FMM_plan: " << fmmb_last_error() << "\n";
+      plan_ = nullptr;
+    }
+  }
+  FMM_plan(const FMM_plan&) = delete;
+  FMM_plan& operator=(const FMM_plan&) = delete;
+  FMM_plan(FMM_plan&& o) : plan_(o.plan_), K(o.K), opts_(o.opts_), n_(o.n_) { o.plan_ = nullptr; }
+  ~FMM_plan() { fmmb_plan_destroy(plan_); }
+
+  kernel_type& kernel() { return K; }
+  const kernel_type& kernel() const { return K; }
+  FMMOptions& options() { return opts_; }
+
+  /** results = A * charges, original body order */
+  std::vector<result_type> execute(const std::vector<charge_type>& charges) {
+    if (!plan_) {
+      printf("[E]: Executor not initialised -- returning..\n");
+      return std::vector<result_type>(0);
+    }
+    static_assert(sizeof(result_type) == Kernel::result_dim * sizeof(double), "result_type must be packed doubles");
+    static_assert(sizeof(charge_type) == Kernel::charge_dim * sizeof(double), "charge_type must be packed doubles");
+    std::vector<result_type> results(charges.size());
+    if (charges.size() != n_ || fmmb_plan_set_p(plan_, K.order()) != FMMB_OK ||
+        fmmb_plan_execute(plan_, reinterpret_cast<const double*>(charges.data()),
+                          reinterpret_cast<double*>(results.data())) != FMMB_OK) {
+      std::cerr << "[E]: FMM_plan::execute: "
+                << (charges.size() != n_ ? "charges.size() != sources.size()" : fmmb_last_error()) << "\n";
+      return std::vector<result_type>(0);
+    }
+    return results;
+  }
+
+  /** extension: the C handle, for fmmb_plan_get_info / phase times */
+  fmmb_plan* handle() { return plan_; }
+
+ private:
+  fmmb_plan* plan_;
+  kernel_type K;
+  FMMOptions opts_;
+  size_t n_;
+};

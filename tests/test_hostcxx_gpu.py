@@ -1,0 +1,45 @@
+"""GPU suite: the C++ host mirror (fmm_bem_relaxed_b200/hostcxx) drives the engine.
+
+bin/ref_scaling is the REFERENCE's tests/scaling.cpp compiled unchanged against our headers
+(built in the build container, where /root/reference exists); bin/laplace_scaling is our own driver.
+"""
+import os
+import re
+import subprocess
+
+import pytest
+
+from conftest import ROOT
+
+pytestmark = pytest.mark.gpu
+BIN = os.path.join(ROOT, "fmm_bem_relaxed_b200", "hostcxx", "bin")
+
+
+def run(exe, *args):
+    path = os.path.join(BIN, exe)
+    if not os.path.exists(path):
+        pytest.skip(path + " not built")
+    env = dict(os.environ)
+    env["LD_LIBRARY_PATH"] = os.path.join(ROOT, "fmm_bem_relaxed_b200") + ":" + env.get("LD_LIBRARY_PATH", "")
+    return subprocess.check_output([path] + list(args), env=env, timeout=600).decode()
+
+
+def test_reference_scaling_driver_unchanged():
+    """Reference tests/scaling.cpp: N=10000, P=5, ncrit=125, prints the force error vs Direct.
+    The unmodified reference prints 8.130425e-04 for this case (oracle/_ref, 1 thread)."""
+    out = run("ref_scaling")
+    m = re.search(r"relative error of Laplace force: ([0-9.eE+-]+)", out)
+    assert m, out
+    assert abs(float(m.group(1)) - 8.130425e-04) < 1e-8
+    assert "FMM execution time" in out
+
+
+def test_own_driver_c1():
+    out = run("laplace_scaling", "100000", "5", "64", "1000")
+    pot = float(re.search(r"Laplace potential: ([0-9.eE+-]+)", out).group(1))
+    force = float(re.search(r"Laplace force: ([0-9.eE+-]+)", out).group(1))
+    chk = float(re.search(r"checksum pot ([0-9.eE+-]+)", out).group(1))
+    # reference figures for C1 (tests/golden/checksums.json)
+    assert abs(pot - 2.038194e-05) < 1e-10
+    assert abs(force - 7.702187e-04) < 1e-9
+    assert abs(chk - 9432714514.34655) <= 1e-10 * 9432714514.34655
