@@ -161,11 +161,17 @@ def bench_ours(args, rank, world, local_rank):
     opts.set_mac_theta(args.theta)
     opts.set_max_per_box(args.ncrit)
     opts.device = local_rank
+    opts.rank, opts.nranks = rank, world
     t0 = time.perf_counter()
     plan = F.FMM_plan(F.LaplaceSpherical(args.p), pts, opts)
     plan_s = time.perf_counter() - t0
     if world > 1:
-        plan.set_partition(rank, world)
+        # ship the NCCL unique id of the engine's own communicator from rank 0 to everyone
+        idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            idt.copy_(torch.frombuffer(bytearray(F.comm_unique_id()), dtype=torch.uint8))
+        dist.broadcast(idt, 0)
+        plan.comm_init(bytes(idt.cpu().numpy().tobytes()))
     info = plan.info()
     n = info.n_bodies
 
@@ -320,7 +326,9 @@ def bench_ours(args, rank, world, local_rank):
         "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": dict(workload(args), l2="256 MiB memset between steps, outside the per-step event pairs",
-                       parallelism="1 GPU" if world == 1 else "target-leaf Morton ranges x%d" % world,
+                       parallelism="1 GPU" if world == 1 else
+                       "target leaves in %d Morton-contiguous ranges of equal estimated work, tree and upward pass "
+                       "replicated, NCCL all-gather of the result slices each step" % world,
                        plan_build_s=plan_s, boxes=info.n_boxes, m2l_pairs=info.n_m2l_pairs,
                        p2p_body_pairs=info.n_p2p_body_pairs),
         "e2e": {"value": 1.0 / e2e_s, "unit": UNIT, "h2d_bytes_per_step": 8 * n, "d2h_bytes_per_step": 32 * n,

@@ -22,7 +22,8 @@ import numpy as np
 from . import capi
 from .capi import FmmbError
 
-__all__ = ["FMMOptions", "LaplaceSpherical", "FMM_plan", "Direct", "FmmbError", "capi"]
+__all__ = ["FMMOptions", "LaplaceSpherical", "FMM_plan", "Direct", "FmmbError", "capi", "comm_unique_id",
+           "partition_ranges", "get_options"]
 
 
 class FMMOptions:
@@ -107,7 +108,8 @@ class FMM_plan:
         self.opts_ = opts
         kd = capi.KernelDesc(kernel.kind, kernel.P, 0.0, 0, 0)
         src = capi.Sources(self._n, capi.ptr(pts))
-        op = capi.Options(opts.theta, opts.NCRIT_, opts.evaluator, opts.device, 0)
+        op = capi.Options(opts.theta, opts.NCRIT_, opts.evaluator, opts.device, 0,
+                          getattr(opts, "rank", 0), getattr(opts, "nranks", 1), 0)
         h = ctypes.c_void_p()
         capi.check(lib.fmmb_plan_create(ctypes.byref(kd), ctypes.byref(src), ctypes.byref(op), ctypes.byref(h)))
         self._h = h
@@ -142,6 +144,11 @@ class FMM_plan:
         """Device-pointer variant (ints / ctypes pointers), asynchronous on the plan stream."""
         capi.check(self._lib.fmmb_plan_execute_device(self._h, ctypes.c_void_p(charges_ptr),
                                                       ctypes.c_void_p(results_ptr)))
+
+    def comm_init(self, unique_id):
+        """Join the NCCL communicator of a partitioned plan (unique_id: 128 bytes from comm_unique_id)."""
+        buf = (ctypes.c_ubyte * 128).from_buffer_copy(bytes(unique_id))
+        capi.check(self._lib.fmmb_plan_comm_init(self._h, ctypes.cast(buf, ctypes.c_void_p)))
 
     def set_option(self, name, value):
         capi.check(self._lib.fmmb_plan_set_option(self._h, name.encode(), int(value)))
@@ -185,6 +192,21 @@ class FMM_plan:
         L = np.zeros((i.n_boxes, nc, 2))
         capi.check(self._lib.fmmb_plan_get_expansions(self._h, capi.ptr(M), capi.ptr(L)))
         return M, L
+
+
+def comm_unique_id():
+    """128-byte NCCL unique id (create on rank 0, ship to the other ranks)."""
+    buf = (ctypes.c_ubyte * 128)()
+    capi.check(capi.load().fmmb_comm_unique_id(ctypes.cast(buf, ctypes.c_void_p)))
+    return bytes(buf)
+
+
+def partition_ranges(weights, nranks):
+    """Contiguous ranges of nearly equal total weight (host only)."""
+    w = np.ascontiguousarray(np.asarray(weights, dtype=np.float64))
+    cuts = np.zeros(nranks + 1, np.int64)
+    capi.check(capi.load().fmmb_partition_ranges(capi.ptr(w), w.shape[0], nranks, capi.ptr(cuts)))
+    return cuts
 
 
 class Direct:

@@ -30,7 +30,8 @@ class KernelDesc(ctypes.Structure):
 
 class Options(ctypes.Structure):
     _fields_ = [("theta", ctypes.c_double), ("ncrit", ctypes.c_uint32), ("evaluator", ctypes.c_int32),
-                ("device", ctypes.c_int32), ("m2l_mode", ctypes.c_int32), ("reserved", ctypes.c_int32 * 3)]
+                ("device", ctypes.c_int32), ("m2l_mode", ctypes.c_int32), ("rank", ctypes.c_int32),
+                ("nranks", ctypes.c_int32), ("reserved", ctypes.c_int32)]
 
 
 class Sources(ctypes.Structure):
@@ -42,6 +43,7 @@ class PlanInfo(ctypes.Structure):
                 ("n_levels", ctypes.c_int64), ("n_m2l_pairs", ctypes.c_int64),
                 ("n_p2p_box_pairs", ctypes.c_int64), ("n_p2p_body_pairs", ctypes.c_int64),
                 ("n_m2l_classes", ctypes.c_int64), ("n_m2l_pairs_batched", ctypes.c_int64),
+                ("own_body_begin", ctypes.c_int64), ("own_body_end", ctypes.c_int64),
                 ("p", ctypes.c_int32), ("charge_dim", ctypes.c_int32), ("result_dim", ctypes.c_int32),
                 ("device", ctypes.c_int32)]
 
@@ -49,7 +51,8 @@ class PlanInfo(ctypes.Structure):
 # every symbol include/fmmb.h declares
 EXPORTS = [
     "fmmb_plan_create", "fmmb_plan_set_p", "fmmb_plan_execute", "fmmb_plan_execute_device",
-    "fmmb_plan_direct", "fmmb_plan_set_option", "fmmb_plan_sync", "fmmb_plan_stream", "fmmb_plan_get_info", "fmmb_plan_get_tree",
+    "fmmb_plan_direct", "fmmb_plan_set_option", "fmmb_plan_sync", "fmmb_comm_unique_id", "fmmb_plan_comm_init",
+    "fmmb_partition_ranges", "fmmb_plan_stream", "fmmb_plan_get_info", "fmmb_plan_get_tree",
     "fmmb_plan_get_expansions", "fmmb_plan_phase_times", "fmmb_plan_destroy", "fmmb_last_error",
     "fmmb_version", "fmmb_measure_fp64_peak",
 ]
@@ -74,6 +77,9 @@ def load():
     lib.fmmb_plan_execute_device.argtypes = [vp, dp, dp]
     lib.fmmb_plan_direct.argtypes = [vp, dp, i64, dp, dp]
     lib.fmmb_plan_sync.argtypes = [vp]
+    lib.fmmb_comm_unique_id.argtypes = [dp]
+    lib.fmmb_plan_comm_init.argtypes = [vp, dp]
+    lib.fmmb_partition_ranges.argtypes = [dp, i64, i32, dp]
     lib.fmmb_plan_set_option.argtypes = [vp, ctypes.c_char_p, i64]
     lib.fmmb_plan_stream.argtypes = [vp]
     lib.fmmb_plan_stream.restype = vp

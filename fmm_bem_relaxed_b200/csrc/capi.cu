@@ -67,6 +67,7 @@ int fmmb_plan_create(const fmmb_kernel_desc* kernel, const fmmb_sources* sources
   std::memset(&opts, 0, sizeof opts);
   opts.theta = 0.5; opts.ncrit = 64; opts.evaluator = FMMB_EVAL_FMM; opts.device = -1;
   if (options) opts = *options;
+  if (opts.nranks < 1) { opts.nranks = 1; opts.rank = 0; }
   if (!(opts.theta > 0)) { set_error("theta must be positive"); return FMMB_ERR_INVALID; }
   if (opts.ncrit < 1) { set_error("ncrit must be at least 1"); return FMMB_ERR_INVALID; }
   if (opts.evaluator != FMMB_EVAL_FMM) { set_error("treecode evaluator is not built"); return FMMB_ERR_UNSUPPORTED; }
@@ -102,6 +103,7 @@ void fmmb_plan_destroy(fmmb_plan* plan) {
   cudaSetDevice(plan->device);
   if (plan->stream) cudaStreamSynchronize(plan->stream);
   if (plan->stream2) cudaStreamSynchronize(plan->stream2);
+  comm_destroy(plan);
   for (auto& kv : plan->m2l_coeff) delete kv.second;
   for (auto& e : plan->ev) if (e) cudaEventDestroy(e);
   if (plan->stream) cudaStreamDestroy(plan->stream);
@@ -132,6 +134,7 @@ int fmmb_plan_execute(fmmb_plan* plan, const double* charges_host, double* resul
     cudaStream_t s = plan->stream;
     plan->charges.resize(n);
     plan->results.resize(4 * (size_t)n);
+    if (plan->tree.nranks > 1 && !plan->comm) plan->results.zero(s);   // only the owned slice gets written
     FMMB_CUDA(cudaEventRecord(plan->ev[8], s));
     FMMB_CUDA(cudaMemcpyAsync(plan->charges.p, charges_host, n * sizeof(double), cudaMemcpyHostToDevice, s));
     FMMB_CUDA(cudaEventRecord(plan->ev[9], s));
@@ -172,6 +175,25 @@ int fmmb_plan_set_option(fmmb_plan* plan, const char* name, int64_t value) {
   return FMMB_ERR_INVALID;
 }
 
+int fmmb_comm_unique_id(unsigned char id[128]) {
+  if (!id) { set_error("null argument"); return FMMB_ERR_INVALID; }
+  return guarded([&] { comm_unique_id(id); });
+}
+
+int fmmb_plan_comm_init(fmmb_plan* plan, const unsigned char id[128]) {
+  if (!plan || !id) { set_error("null argument"); return FMMB_ERR_INVALID; }
+  return guarded([&] {
+    FMMB_CUDA(cudaSetDevice(plan->device));
+    comm_init(plan, id);
+  });
+}
+
+int fmmb_partition_ranges(const double* weights, int64_t n, int nranks, int64_t* cuts) {
+  if (!weights || !cuts || n < 0 || nranks < 1) { set_error("bad argument"); return FMMB_ERR_INVALID; }
+  partition_ranges(weights, n, nranks, cuts);
+  return FMMB_OK;
+}
+
 int fmmb_plan_sync(fmmb_plan* plan) {
   if (!plan) { set_error("null plan"); return FMMB_ERR_INVALID; }
   return guarded([&] {
@@ -190,6 +212,7 @@ int fmmb_plan_get_info(fmmb_plan* plan, fmmb_plan_info* info) {
   info->n_bodies = T.n; info->n_boxes = T.nboxes; info->n_leaves = T.nleaves; info->n_levels = T.nlevels;
   info->n_m2l_pairs = T.n_lr; info->n_p2p_box_pairs = T.n_p2p; info->n_p2p_body_pairs = T.n_p2p_body_pairs;
   info->n_m2l_classes = plan->cls.n_classes; info->n_m2l_pairs_batched = plan->cls.n_pairs;
+  info->own_body_begin = T.own_b0; info->own_body_end = T.own_b1;
   info->p = plan->p; info->charge_dim = 1; info->result_dim = 4; info->device = plan->device;
   return FMMB_OK;
 }

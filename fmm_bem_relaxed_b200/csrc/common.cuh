@@ -98,6 +98,14 @@ struct Tree {
   DevBuf<unsigned> key, parent, cbegin, cend, bbegin, bend, level;
   DevBuf<double4> center;            // cx, cy, cz, side
   DevBuf<int> leaves;                // indices of leaf boxes, ascending
+  // multi-GPU partition (rank owns the tree-order bodies [own_b0, own_b1), whole leaves)
+  int rank = 0, nranks = 1;
+  int64_t own_b0 = 0, own_b1 = 0;
+  std::vector<int64_t> body_cuts;    // nranks + 1 body offsets, identical on every rank
+  DevBuf<int> own_leaves;            // leaf boxes inside the owned range, ascending
+  int n_own_leaves = 0;
+  DevBuf<unsigned char> active;      // box intersects the owned range (is a target on this rank)
+  int64_t n_lr_local = 0;            // M2L pairs whose target is active here (= n_lr on one GPU)
   DevBuf<unsigned char> has_local;   // box carries a local expansion (M2L target or descendant of one)
   // M2L: reference-order pair list and target-major CSR (sources in list order per target)
   DevBuf<int2> lr;                   // (source, target) in LR_list order
@@ -157,6 +165,8 @@ struct fmmb_plan {
   fmmb::DevBuf<double> M, L;         // box-major, real layout (laplace_ops.cuh), stride xstride(p)
   fmmb::DevBuf<double> charges;      // original order staging
   fmmb::DevBuf<double4> res_near, res_far;  // tree order
+  fmmb::DevBuf<double4> res_tree;    // multi-GPU: near + far in tree order, all-gathered over NCCL
+  void* comm = nullptr;              // ncclComm_t once fmmb_plan_comm_init ran
   fmmb::DevBuf<double> results;      // original order staging, 4n
   double phase_ms[FMMB_T_COUNT] = {0};
   bool timed = false;
@@ -168,6 +178,11 @@ struct fmmb_plan {
 namespace fmmb {
 // tree.cu
 void build_tree(fmmb_plan* plan, const double* points_host, int64_t n);
+void partition_ranges(const double* w, int64_t n, int nranks, int64_t* cuts);
+void comm_unique_id(unsigned char* id);
+void comm_init(fmmb_plan* plan, const unsigned char* id);
+void comm_destroy(fmmb_plan* plan);
+void allgather_results(fmmb_plan* plan, cudaStream_t s);
 // laplace.cu
 void laplace_init_tables(fmmb_plan* plan);
 void laplace_execute(fmmb_plan* plan, const double* d_charges, double* d_results);

@@ -337,11 +337,25 @@ p2p_kernel(const int4* __restrict__ items, int nitems, const unsigned* __restric
 
 // ---- results back to the caller's order ----------------------------------------------------------
 __global__ void scatter_results(const double4* __restrict__ near, const double4* __restrict__ far,
-                                const unsigned* __restrict__ perm, int64_t n, double4* __restrict__ out) {
-  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (i >= n) return;
+                                const unsigned* __restrict__ perm, int64_t i0, int64_t i1,
+                                double4* __restrict__ out) {
+  int64_t i = i0 + blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= i1) return;
   double4 a = near[i], b = far[i];
   out[perm[i]] = make_double4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
+}
+// multi-GPU: near + far of the owned range in tree order, ready for the all-gather
+__global__ void combine_results(const double4* __restrict__ near, const double4* __restrict__ far, int64_t i0,
+                                int64_t i1, double4* __restrict__ tree) {
+  int64_t i = i0 + blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= i1) return;
+  double4 a = near[i], b = far[i];
+  tree[i] = make_double4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
+}
+__global__ void scatter_tree(const double4* __restrict__ tree, const unsigned* __restrict__ perm, int64_t n,
+                             double4* __restrict__ out) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < n) out[perm[i]] = tree[i];
 }
 
 // ---- brute force (Direct.hpp:99-125) ---------------------------------------------------------------
@@ -502,15 +516,27 @@ void laplace_execute(fmmb_plan* plan, const double* d_charges, double* d_results
     l2l_kernel<<<hi - lo, 64, sh_mm, s>>>(lo, hi, T.parent.p, T.has_local.p, T.center.p, P, plan->L.p);
     ++plan->launches;
   }
-  l2p_kernel<<<nblk(T.nleaves, 4), 128, 4 * nc * sizeof(double2), s>>>(T.leaves.p, T.nleaves, T.bbegin.p, T.bend.p,
+  l2p_kernel<<<nblk(T.n_own_leaves, 4), 128, 4 * nc * sizeof(double2), s>>>(T.own_leaves.p, T.n_own_leaves, T.bbegin.p, T.bend.p,
                                                                      T.center.p, T.has_local.p, T.body.p, P,
                                                                      plan->L.p, plan->res_far.p);
                              ++plan->launches;
   FMMB_CUDA(cudaEventRecord(ev[4], s));
 
   if (s2 != s) FMMB_CUDA(cudaStreamWaitEvent(s, ev[7], 0));
-  scatter_results<<<nblk(n, 256), 256, 0, s>>>(plan->res_near.p, plan->res_far.p, T.perm.p, n,
-                                              reinterpret_cast<double4*>(d_results));
+  if (T.nranks > 1 && plan->comm) {
+    // the one exchange step: all-gather the per-rank result slices (tree order), then un-permute
+    plan->res_tree.resize(n);
+    if (T.own_b1 > T.own_b0)
+      combine_results<<<nblk(T.own_b1 - T.own_b0, 256), 256, 0, s>>>(plan->res_near.p, plan->res_far.p, T.own_b0,
+                                                                    T.own_b1, plan->res_tree.p);
+    allgather_results(plan, s);
+    scatter_tree<<<nblk(n, 256), 256, 0, s>>>(plan->res_tree.p, T.perm.p, n, reinterpret_cast<double4*>(d_results));
+    ++plan->launches;
+  } else if (T.own_b1 > T.own_b0) {
+    scatter_results<<<nblk(T.own_b1 - T.own_b0, 256), 256, 0, s>>>(plan->res_near.p, plan->res_far.p, T.perm.p,
+                                                                  T.own_b0, T.own_b1,
+                                                                  reinterpret_cast<double4*>(d_results));
+  }
       ++plan->launches;
   FMMB_CUDA(cudaEventRecord(ev[5], s));
   FMMB_CUDA(cudaGetLastError());
@@ -522,18 +548,18 @@ void build_p2p_items(fmmb_plan* plan) {
   Tree& T = plan->tree;
   cudaStream_t s = plan->stream;
   DevBuf<int> cnt;
-  cnt.resize(T.nleaves + 1);
-  p2p_count_items<<<nblk(T.nleaves + 1, 256), 256, 0, s>>>(T.leaves.p, T.nleaves, T.bbegin.p, T.bend.p, cnt.p);
+  const int nl = T.n_own_leaves;
+  cnt.resize(nl + 1);
+  p2p_count_items<<<nblk(nl + 1, 256), 256, 0, s>>>(T.own_leaves.p, nl, T.bbegin.p, T.bend.p, cnt.p);
   FMMB_CUDA(cudaGetLastError());
   std::vector<int> h = cnt.to_host(s);
-  std::vector<int> off(T.nleaves + 1, 0);
-  for (int i = 0; i < T.nleaves; ++i) off[i + 1] = off[i] + h[i];
-  T.n_p2p_items = off[T.nleaves];
+  std::vector<int> off(nl + 1, 0);
+  for (int i = 0; i < nl; ++i) off[i + 1] = off[i] + h[i];
+  T.n_p2p_items = off[nl];
   DevBuf<int> doff;
   doff.from_host(off.data(), off.size(), s);
   T.p2p_items.resize(T.n_p2p_items);
-  p2p_fill_items<<<nblk(T.nleaves, 256), 256, 0, s>>>(T.leaves.p, T.nleaves, T.bbegin.p, T.bend.p, doff.p,
-                                                     T.p2p_items.p);
+  if (nl) p2p_fill_items<<<nblk(nl, 256), 256, 0, s>>>(T.own_leaves.p, nl, T.bbegin.p, T.bend.p, doff.p, T.p2p_items.p);
   FMMB_CUDA(cudaGetLastError());
   FMMB_CUDA(cudaStreamSynchronize(s));
 }

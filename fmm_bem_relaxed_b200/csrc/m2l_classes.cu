@@ -71,12 +71,13 @@ __global__ void parent_child_pairs(const unsigned* __restrict__ parent, int nb, 
 }
 
 // class key of slot first+e: integer centre offset (36 bits) [+ target level above it]
-__global__ void class_keys(const int* __restrict__ tgt, const int* __restrict__ src, int first, int64_t n,
+__global__ void class_keys(const int* __restrict__ tgt, const int* __restrict__ src, int first,
+                           const int* __restrict__ slot_list, int64_t n,
                            const unsigned* __restrict__ key, const unsigned* __restrict__ lvl, int with_level,
                            unsigned long long* __restrict__ ckey, int* __restrict__ slot) {
   int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (e >= n) return;
-  int sl = first + (int)e;
+  int sl = slot_list ? slot_list[e] : first + (int)e;
   int t = tgt[sl], s = src[sl];
   int3 a = centre_half_cells(key[t], lvl[t]), b = centre_half_cells(key[s], lvl[s]);
   unsigned long long dx = (unsigned)(a.x - b.x + 2048), dy = (unsigned)(a.y - b.y + 2048),
@@ -129,14 +130,19 @@ __global__ void residual_offsets(const int* __restrict__ off, const int* __restr
   int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b <= nb) res_off[b] = pos[off[b]];
 }
+// Representative translation vector of a class: the integer centre offset times half a finest cell.
+// (The floating-point centre differences of the pairs of one class agree with it to ~1e-16 relative;
+// using the lattice value makes T_c independent of which pairs a rank happens to hold.)
 __global__ void class_vectors(const int* __restrict__ start, int nclasses, const int* __restrict__ sorted_slot,
                               const int* __restrict__ tgt, const int* __restrict__ src,
-                              const double4* __restrict__ center, double4* __restrict__ vec) {
+                              const unsigned* __restrict__ key, const unsigned* __restrict__ lvl, double3 half_cell,
+                              double4* __restrict__ vec) {
   int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= nclasses) return;
   int e = sorted_slot[start[c]];
-  double4 a = center[tgt[e]], b = center[src[e]];
-  vec[c] = make_double4(a.x - b.x, a.y - b.y, a.z - b.z, 0.0);
+  int t = tgt[e], s = src[e];
+  int3 a = centre_half_cells(key[t], lvl[t]), b = centre_half_cells(key[s], lvl[s]);
+  vec[c] = make_double4((a.x - b.x) * half_cell.x, (a.y - b.y) * half_cell.y, (a.z - b.z) * half_cell.z, 0.0);
 }
 
 // ---- translation matrices: Tt[c][col][row], rows contiguous, ld = P^2 -------------------------------
@@ -438,15 +444,16 @@ void launch_gemm(const TransBatch& B, int P, int first, int count, const double*
 
 // Sorts the pairs of a batch by class, builds classes / items / (for M2L) the residual lists.
 // tgt/src are indexed by slot; slots [first, first+n) take part.
-void classify(fmmb_plan* plan, TransBatch& B, const int* tgt, const int* src, int first, int64_t n,
-              int minpop, bool by_level) {
+void classify(fmmb_plan* plan, TransBatch& B, const int* tgt, const int* src, int first, const int* slot_list,
+              int64_t n, int minpop, bool by_level) {
   Tree& T = plan->tree;
   cudaStream_t s = plan->stream;
   Temp tmp;
   DevBuf<unsigned long long> k0, k1, uniq;
   DevBuf<int> v0, count, nruns;
   k0.resize(n); k1.resize(n); v0.resize(n); B.sorted_slot.resize(n);
-  class_keys<<<nblk(n, 256), 256, 0, s>>>(tgt, src, first, n, T.key.p, T.level.p, by_level ? 1 : 0, k0.p, v0.p);
+  class_keys<<<nblk(n, 256), 256, 0, s>>>(tgt, src, first, slot_list, n, T.key.p, T.level.p, by_level ? 1 : 0, k0.p,
+                                          v0.p);
   FMMB_CUDA(cudaGetLastError());
   {
     size_t bytes = 0;
@@ -484,7 +491,8 @@ void classify(fmmb_plan* plan, TransBatch& B, const int* tgt, const int* src, in
     fill_items<<<nblk(ncls, 128), 128, 0, s>>>(count.p, start.p, item_off.p, ncls, B.item_class.p, B.item_start.p,
                                               B.item_count.p);
   B.class_vec.resize(ncls);
-  class_vectors<<<nblk(ncls, 128), 128, 0, s>>>(start.p, ncls, B.sorted_slot.p, tgt, src, T.center.p,
+  class_vectors<<<nblk(ncls, 128), 128, 0, s>>>(start.p, ncls, B.sorted_slot.p, tgt, src, T.key.p, T.level.p,
+                                               make_double3(0.5 * T.cell[0], 0.5 * T.cell[1], 0.5 * T.cell[2]),
                                                B.class_vec.p);
   FMMB_CUDA(cudaGetLastError());
   if (by_level) {
@@ -558,16 +566,16 @@ void build_m2l_classes(fmmb_plan* plan) {
   cudaStream_t s = plan->stream;
   const int nb = T.nboxes;
   TransBatch& C = plan->cls;
-  C.kind = 0; C.n_classes = 0; C.n_pairs = 0; C.n_items = 0; C.n_res = T.n_lr; C.built_p = 0;
+  C.kind = 0; C.n_classes = 0; C.n_pairs = 0; C.n_items = 0; C.n_res = T.n_lr_local; C.built_p = 0;
   plan->m2m.kind = 1; plan->m2m.n_items = 0; plan->m2m.built_p = 0;
   plan->l2l.kind = 2; plan->l2l.n_items = 0; plan->l2l.built_p = 0;
   if (plan->opts.m2l_mode == 1) return;
   if (T.n_lr >= (1ll << 31)) throw StatusError{FMMB_ERR_INVALID, "more than 2^31 M2L pairs"};
-  if (T.n_lr > 0) {
-    C.slot_tgt.resize(T.n_lr);
+  if (T.n_lr_local > 0) {
+    C.slot_tgt.resize(T.n_lr_local);
     slot_targets<<<nb, 64, 0, s>>>(T.m2l_off.p, nb, C.slot_tgt.p);
     C.slot_src_p = T.m2l_src.p;
-    classify(plan, C, C.slot_tgt.p, T.m2l_src.p, 0, T.n_lr, kMinPopM2L, false);
+    classify(plan, C, C.slot_tgt.p, T.m2l_src.p, 0, nullptr, T.n_lr_local, kMinPopM2L, false);
   }
   if (nb > 1) {
     for (int kind = 1; kind <= 2; ++kind) {
@@ -575,8 +583,19 @@ void build_m2l_classes(fmmb_plan* plan) {
       B.slot_tgt.resize(nb); B.slot_src.resize(nb);
       parent_child_pairs<<<nblk(nb, 256), 256, 0, s>>>(T.parent.p, nb, kind == 2, B.slot_tgt.p, B.slot_src.p);
       B.slot_src_p = B.slot_src.p;
-      classify(plan, B, B.slot_tgt.p, B.slot_src.p, 1, nb - 1, 1, true);
-      B.n_pairs = nb - 1;
+      if (kind == 2 && T.nranks > 1) {
+        // L2L only into boxes that are targets on this rank
+        std::vector<unsigned char> act = T.active.to_host(s);
+        std::vector<int> list;
+        for (int c = 1; c < nb; ++c) if (act[c]) list.push_back(c);
+        DevBuf<int> dl;
+        dl.from_host(list.data(), list.size(), s);
+        if (!list.empty()) classify(plan, B, B.slot_tgt.p, B.slot_src.p, 0, dl.p, (int64_t)list.size(), 1, true);
+        B.n_pairs = (int64_t)list.size();
+      } else {
+        classify(plan, B, B.slot_tgt.p, B.slot_src.p, 1, nullptr, nb - 1, 1, true);
+        B.n_pairs = nb - 1;
+      }
     }
   }
 }
@@ -589,7 +608,7 @@ bool m2l_batched(fmmb_plan* plan, cudaStream_t s) {
   const int P = plan->p, pp = P * P, xs = xstride(P);
   if (C.n_items == 0 || P > 8) return false;
   ensure_T(plan, C, s);
-  C.tmp.resize((size_t)T.n_lr * xs);
+  C.tmp.resize((size_t)T.n_lr_local * xs);
   FMMB_CUDA(cudaEventRecord(plan->ev[13], s));
   launch_gemm<false>(C, P, 0, C.n_items, plan->M.p, C.tmp.p, nullptr, s);
   FMMB_CUDA(cudaEventRecord(plan->ev[14], s));

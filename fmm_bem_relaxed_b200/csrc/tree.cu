@@ -371,6 +371,85 @@ void pairs_to_csr(Temp& tmp, const DevBuf<int2>& pairs, int64_t n, int key_is_y,
 
 }  // namespace
 
+void partition_ranges(const double* w, int64_t n, int nranks, int64_t* cuts) {
+  double total = 0;
+  for (int64_t i = 0; i < n; ++i) total += w[i];
+  cuts[0] = 0;
+  double run = 0;
+  int64_t i = 0;
+  for (int r = 1; r < nranks; ++r) {
+    double goal = total * r / nranks;
+    while (i < n && run + 0.5 * w[i] < goal) run += w[i++];
+    cuts[r] = i;
+  }
+  cuts[nranks] = n;
+  for (int r = 1; r <= nranks; ++r) cuts[r] = std::max(cuts[r], cuts[r - 1]);
+}
+
+// Multi-GPU: choose this rank's leaf range and restrict the target-major M2L lists to it.
+static void partition_tree(fmmb_plan* plan) {
+  Tree& T = plan->tree;
+  cudaStream_t s = plan->stream;
+  const int nb = T.nboxes;
+  T.rank = plan->opts.nranks > 1 ? plan->opts.rank : 0;
+  T.nranks = plan->opts.nranks > 1 ? plan->opts.nranks : 1;
+  T.n_lr_local = T.n_lr;
+  T.body_cuts.assign(T.nranks + 1, 0);
+  T.body_cuts[T.nranks] = T.n;
+  T.own_b0 = 0; T.own_b1 = T.n;
+  T.active.resize(nb);
+  if (T.nranks == 1) {
+    T.n_own_leaves = T.nleaves;
+    T.own_leaves.resize(T.nleaves);
+    FMMB_CUDA(cudaMemcpyAsync(T.own_leaves.p, T.leaves.p, T.nleaves * sizeof(int), cudaMemcpyDeviceToDevice, s));
+    FMMB_CUDA(cudaMemsetAsync(T.active.p, 1, nb, s));
+    return;
+  }
+  if (T.rank < 0 || T.rank >= T.nranks) throw StatusError{FMMB_ERR_INVALID, "rank must be in [0, nranks)"};
+  std::vector<int> leaves = T.leaves.to_host(s), m2l_off = T.m2l_off.to_host(s), m2l_src = T.m2l_src.to_host(s),
+                   p2p_off = T.p2p_off.to_host(s), p2p_src = T.p2p_src.to_host(s);
+  std::vector<unsigned> bb = T.bbegin.to_host(s), be = T.bend.to_host(s), par = T.parent.to_host(s);
+  // work estimate per box: M2L pairs into it, inherited from the ancestors in proportion to the bodies
+  // (one M2L pair costs about as much as 230 P2P body pairs at P = 8 on a B200)
+  std::vector<double> far(nb, 0.0);
+  for (int b = 0; b < nb; ++b) {
+    double own = m2l_off[b + 1] - m2l_off[b];
+    double inh = b == 0 ? 0.0 : far[par[b]] * double(be[b] - bb[b]) / double(be[par[b]] - bb[par[b]]);
+    far[b] = own + inh;   // parents precede children in BFS order
+  }
+  std::vector<int> order(leaves);
+  std::sort(order.begin(), order.end(), [&](int a, int b) { return bb[a] < bb[b]; });
+  std::vector<double> w(order.size());
+  for (size_t i = 0; i < order.size(); ++i) {
+    int b = order[i];
+    double near = 0;
+    for (int e = p2p_off[b]; e < p2p_off[b + 1]; ++e) near += double(be[p2p_src[e]] - bb[p2p_src[e]]);
+    w[i] = near * double(be[b] - bb[b]) + 230.0 * far[b];
+  }
+  std::vector<int64_t> cuts(T.nranks + 1);
+  partition_ranges(w.data(), (int64_t)w.size(), T.nranks, cuts.data());
+  for (int r = 0; r <= T.nranks; ++r)
+    T.body_cuts[r] = cuts[r] >= (int64_t)order.size() ? T.n : (int64_t)bb[order[cuts[r]]];
+  T.own_b0 = T.body_cuts[T.rank];
+  T.own_b1 = T.body_cuts[T.rank + 1];
+  std::vector<int> own;
+  for (int b : leaves) if (bb[b] >= T.own_b0 && bb[b] < T.own_b1) own.push_back(b);
+  T.n_own_leaves = (int)own.size();
+  T.own_leaves.from_host(own.data(), own.size(), s);
+  std::vector<unsigned char> act(nb);
+  std::vector<int> noff(nb + 1, 0), nsrc;
+  for (int b = 0; b < nb; ++b) {
+    act[b] = (int64_t)bb[b] < T.own_b1 && (int64_t)be[b] > T.own_b0;
+    if (act[b]) nsrc.insert(nsrc.end(), m2l_src.begin() + m2l_off[b], m2l_src.begin() + m2l_off[b + 1]);
+    noff[b + 1] = (int)nsrc.size();
+  }
+  T.active.from_host(act.data(), act.size(), s);
+  T.m2l_off.from_host(noff.data(), noff.size(), s);
+  T.m2l_src.from_host(nsrc.data(), nsrc.size(), s);
+  T.n_lr_local = (int64_t)nsrc.size();
+  FMMB_CUDA(cudaStreamSynchronize(s));
+}
+
 void build_tree(fmmb_plan* plan, const double* points_host, int64_t n) {
   Tree& T = plan->tree;
   cudaStream_t s = plan->stream;
@@ -572,6 +651,8 @@ void build_tree(fmmb_plan* plan, const double* points_host, int64_t n) {
     std::vector<unsigned long long> h = total.to_host(s);
     T.n_p2p_body_pairs = (int64_t)h[0];
   }
+  FMMB_CUDA(cudaStreamSynchronize(s));
+  partition_tree(plan);
   FMMB_CUDA(cudaStreamSynchronize(s));
 }
 

@@ -72,7 +72,9 @@ typedef struct {
   int32_t evaluator;   /* fmmb_evaluator; only FMMB_EVAL_FMM is built */
   int32_t device;      /* CUDA device ordinal, -1 = current device */
   int32_t m2l_mode;    /* 0 = auto, 1 = per-pair kernel only, 2 = prefer batched translation classes */
-  int32_t reserved[3];
+  int32_t rank;        /* multi-GPU: this process's rank (0 when nranks <= 1) */
+  int32_t nranks;      /* multi-GPU: number of ranks sharing the matvec; 0 or 1 = single GPU */
+  int32_t reserved;
 } fmmb_options;
 
 /* Point sources (source_type == point_type kernels).  points: 3*n doubles, point-major
@@ -93,6 +95,8 @@ typedef struct {
   int64_t n_p2p_body_pairs;
   int64_t n_m2l_classes;   /* distinct translation vectors handled by the batched M2L */
   int64_t n_m2l_pairs_batched;
+  int64_t own_body_begin;  /* multi-GPU: tree-order body range whose results this rank computes */
+  int64_t own_body_end;
   int32_t p;               /* current expansion order */
   int32_t charge_dim;      /* doubles per charge (Laplace 1) */
   int32_t result_dim;      /* doubles per result (Laplace 4: potential, fx, fy, fz) */
@@ -139,6 +143,22 @@ int fmmb_plan_direct(fmmb_plan* plan, const double* charges_host, int64_t nt,
  *                      (used by bench.py for the roofline figures).
  *   "m2l_mode"     see fmmb_options.m2l_mode. */
 int fmmb_plan_set_option(fmmb_plan* plan, const char* name, int64_t value);
+
+/* ---- multi-GPU (one process per GPU, single node) ---------------------------------------------
+ * The matvec shards by TARGET leaves: every rank builds the same tree (replicated), owns a
+ * Morton-contiguous range of leaves of equal estimated work (fmmb_partition_ranges), and computes
+ * M2L / L2L / L2P / P2P only for its targets.  The one exchange step of a matvec is an all-gather of
+ * the result slices over NCCL (NVLink); charges are replicated by the caller (a GMRES vector is).
+ *   rank 0:       fmmb_comm_unique_id(id)         -> ship the 128 bytes to the other ranks
+ *   every rank:   options.rank / options.nranks at fmmb_plan_create, then fmmb_plan_comm_init(plan, id)
+ * Without fmmb_plan_comm_init a partitioned plan writes only its own slice of the results. */
+int fmmb_comm_unique_id(unsigned char id[128]);
+int fmmb_plan_comm_init(fmmb_plan* plan, const unsigned char id[128]);
+
+/* Host-only helper (no GPU needed): cut n non-negative work weights into nranks contiguous ranges of
+ * nearly equal sum.  cuts has nranks+1 entries, cuts[0] = 0, cuts[nranks] = n; rank r owns
+ * [cuts[r], cuts[r+1]). */
+int fmmb_partition_ranges(const double* weights, int64_t n, int nranks, int64_t* cuts);
 
 int fmmb_plan_sync(fmmb_plan* plan);
 void* fmmb_plan_stream(fmmb_plan* plan); /* cudaStream_t */

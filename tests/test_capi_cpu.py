@@ -33,7 +33,7 @@ def test_struct_layouts_match_header():
     assert ctypes.sizeof(capi.KernelDesc) == 24
     assert ctypes.sizeof(capi.Options) == 40
     assert ctypes.sizeof(capi.Sources) == 16
-    assert ctypes.sizeof(capi.PlanInfo) == 9 * 8 + 4 * 4
+    assert ctypes.sizeof(capi.PlanInfo) == 11 * 8 + 4 * 4
 
 
 def test_argument_validation_needs_no_gpu():

@@ -1,0 +1,103 @@
+"""Multi-GPU sharding: target leaves in Morton-contiguous ranges.
+
+CPU part (gloo, world_size 2): the host-side partition helper and the slice / all-gather / un-permute
+logic, with the oracle standing in for the per-rank compute.
+GPU part: partitioned plans on ONE device, without a communicator -- every rank writes only its own slice
+and the slices must tile the single-GPU result bit for bit (per-target sums do not depend on the rank).
+"""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+import oracle_lib as O
+import fmm_bem_relaxed_b200 as F
+from conftest import ROOT
+
+
+def test_partition_ranges_balanced():
+    rng = np.random.default_rng(0)
+    w = rng.random(1000) + 0.1
+    for r in (1, 2, 3, 8):
+        cuts = F.partition_ranges(w, r)
+        assert cuts[0] == 0 and cuts[-1] == 1000 and np.all(np.diff(cuts) >= 0)
+        sums = np.array([w[cuts[i]:cuts[i + 1]].sum() for i in range(r)])
+        assert sums.max() - sums.min() <= 2 * w.max() + 1e-12
+    # degenerate: more ranks than items, zero weights
+    cuts = F.partition_ranges(np.ones(3), 8)
+    assert cuts[-1] == 3 and np.all(np.diff(cuts) >= 0)
+    cuts = F.partition_ranges(np.zeros(10), 4)
+    assert cuts[0] == 0 and cuts[-1] == 10
+
+
+def _gloo_worker(rank, world, port, ret):
+    import torch
+    import torch.distributed as dist
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    n, P = 4000, 4
+    pts, q = O.drand48_inputs(n)
+    orc = O.Oracle(pts, 32, 0.5)
+    t = orc.tree()
+    boxes = t["boxes"]
+    leaves = np.nonzero(boxes[:, 7])[0]
+    leaves = leaves[np.argsort(boxes[leaves, 4])]            # body order
+    counts = (boxes[leaves, 5] - boxes[leaves, 4]).astype(float)
+    cuts = F.partition_ranges(counts * counts, world)         # any positive work estimate will do here
+    body_cuts = [int(boxes[leaves[c], 4]) if c < len(leaves) else n for c in cuts]
+    b0, b1 = body_cuts[rank], body_cuts[rank + 1]
+    full = orc.execute(q, P, mode=1, threads=1)               # stands in for the per-rank GPU compute
+    mine = torch.from_numpy(full[t["perm"][b0:b1].astype(np.int64)].copy())   # owned slice, tree order
+    # all-gather of unequal slices = one broadcast per owner (what csrc/comm.cu does with NCCL)
+    tree_res = torch.zeros((n, 4), dtype=torch.float64)
+    tree_res[b0:b1] = mine
+    for r in range(world):
+        dist.broadcast(tree_res[body_cuts[r]:body_cuts[r + 1]], r)
+    out = np.zeros((n, 4))
+    out[t["perm"].astype(np.int64)] = tree_res.numpy()
+    ok = np.array_equal(out, full) and sum(body_cuts[i + 1] - body_cuts[i] for i in range(world)) == n
+    dist.destroy_process_group()
+    ret[rank] = bool(ok)
+
+
+def test_gloo_world2_slices_tile_the_result():
+    import torch.multiprocessing as mp
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    port = 29500 + os.getpid() % 2000
+    mp.spawn(_gloo_worker, args=(2, port, ret), nprocs=2, join=True)
+    assert ret[0] and ret[1]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("world", [2, 3, 8])
+def test_partitioned_plans_tile_single_gpu_result(world):
+    n, P = 60000, 6
+    pts, q = O.drand48_inputs(n)
+    ref_plan = F.FMM_plan(F.LaplaceSpherical(P), pts)
+    full = ref_plan.execute(q)
+    perm = ref_plan.tree()["perm"].astype(np.int64)
+    merged = np.zeros_like(full)
+    covered = np.zeros(n, dtype=int)
+    work = []
+    for r in range(world):
+        opts = F.FMMOptions()
+        opts.rank, opts.nranks = r, world
+        plan = F.FMM_plan(F.LaplaceSpherical(P), pts, opts)
+        i = plan.info()
+        part = plan.execute(q)                       # no communicator: only the owned slice is written
+        own = perm[i.own_body_begin:i.own_body_end]
+        covered[own] += 1
+        mask = np.ones(n, bool)
+        mask[own] = False
+        assert np.all(part[mask] == 0)
+        merged += part
+        work.append(i.n_m2l_pairs_batched)
+    assert np.all(covered == 1)
+    assert np.array_equal(merged, full)              # same per-target sums on every rank: bit identical
+    # far-field work is split (the top of the tree is shared, so the sum exceeds the single-GPU count a little)
+    assert max(work) < 0.75 * ref_plan.info().n_m2l_pairs_batched
