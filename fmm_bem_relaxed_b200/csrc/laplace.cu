@@ -32,34 +32,55 @@ __global__ void gather_charges(const double* __restrict__ q, const unsigned* __r
   if (i < n) body[i].w = q[perm[i]];
 }
 
-// ---- P2M: one warp per leaf, lane per body, coefficient-wise warp reduction ---------------------
+// ---- P2M: one warp per leaf -----------------------------------------------------------------------
+// Lane = body: evaluates q * rho^n Y_n^m(alpha,-beta) into a warp-private shared tile [body][P^2]
+// (real layout).  Then lane = coefficient: sums its column over the bodies.  One pass per 32 bodies.
 __global__ void __launch_bounds__(128)
 p2m_kernel(const int* __restrict__ leaves, int nleaves, const unsigned* __restrict__ bb,
            const unsigned* __restrict__ be, const double4* __restrict__ center,
            const double4* __restrict__ body, int P, double* __restrict__ M) {
-  int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  extern __shared__ double p2m_sh[];
+  const int pp = P * P, ld = pp | 1;               // odd stride: conflict-free row writes and column reads
+  const int wl = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int w = blockIdx.x * (blockDim.x >> 5) + wl;
   if (w >= nleaves) return;
-  int b = leaves[w];
-  double4 c = center[b];
-  unsigned b0 = bb[b], b1 = be[b];
-  double* Mb = M + (size_t)b * xstride(P);
+  double* tile = p2m_sh + (size_t)wl * 32 * ld;
+  const int b = leaves[w];
+  const double4 c = center[b];
+  const unsigned b0 = bb[b], b1 = be[b];
+  double acc[(FMMB_MAX_P * FMMB_MAX_P + 31) / 32];
+#pragma unroll
+  for (int i = 0; i < (FMMB_MAX_P * FMMB_MAX_P + 31) / 32; ++i) acc[i] = 0.0;
   for (unsigned base = b0; base < b1; base += 32) {
-    unsigned i = base + lane;
-    double q = 0;
-    Sph s = to_sph(0, 0, 1);
+    const unsigned i = base + lane;
+    const int cnt = (int)min(32u, b1 - base);
+    __syncwarp();
     if (i < b1) {
-      double4 p = body[i];
-      q = p.w;
-      s = to_sph(p.x - c.x, p.y - c.y, p.z - c.z);
+      const double4 p = body[i];
+      const double q = p.w;
+      const Sph s = to_sph(p.x - c.x, p.y - c.y, p.z - c.z);
+      double* row = tile + lane * ld;
+      regular_harmonics<false>(P, s, -1.0, [&](int n, int m, double yr, double yi, double, double) {
+        row[n * n + n + m] = q * yr;
+        if (m > 0) row[n * n + n - m] = q * yi;
+      });
     }
-    bool first = base == b0;
-    regular_harmonics<false>(P, s, -1.0, [&](int n, int m, double yr, double yi, double, double) {
-      double vr = warp_sum(q * yr), vi = warp_sum(q * yi);
-      if (lane == 0) {
-        if (first) store_coef(Mb, n, m, make_double2(vr, vi));
-        else add_coef(Mb, n, m, make_double2(vr, vi));
+    __syncwarp();
+#pragma unroll
+    for (int i2 = 0; i2 < (FMMB_MAX_P * FMMB_MAX_P + 31) / 32; ++i2) {
+      const int col = lane + 32 * i2;
+      if (col < pp) {
+        double sum = 0;
+        for (int k = 0; k < cnt; ++k) sum += tile[k * ld + col];
+        acc[i2] += sum;
       }
-    });
+    }
+  }
+  double* Mb = M + (size_t)b * xstride(P);
+#pragma unroll
+  for (int i2 = 0; i2 < (FMMB_MAX_P * FMMB_MAX_P + 31) / 32; ++i2) {
+    const int col = lane + 32 * i2;
+    if (col < pp) Mb[col] = acc[i2];
   }
 }
 
@@ -234,19 +255,21 @@ l2p_kernel(const int* __restrict__ leaves, int nleaves, const unsigned* __restri
     double4 p = body[i];
     Sph s = to_sph(p.x - c.x, p.y - c.y, p.z - c.z);
     double pot = 0, s0 = 0, s1 = 0, s2 = 0;
+    const double inv_r = 1.0 / s.r;
     regular_harmonics<true>(P, s, 1.0, [&](int n, int m, double yr, double yi, double tr, double ti) {
       double2 l = Ls[n * (n + 1) / 2 + m];
       double w2 = m == 0 ? 1.0 : 2.0;
       double re = l.x * yr - l.y * yi;             // Re(L Y)
       pot += w2 * re;
-      s0 += w2 * re / s.r * n;
+      s0 += w2 * re * inv_r * n;
       s1 += w2 * (l.x * tr - l.y * ti);            // Re(L Ytheta)
       s2 -= w2 * (l.x * yi + l.y * yr) * m;        // Re(L Y i) m = -Im(L Y) m
     });
     // sph2cart (:546-561): theta -> (s.x = cos, s.y = sin), phi -> (cp, sp)
-    double fx = s.y * s.cp * s0 + s.x * s.cp / s.r * s1 - s.sp / s.r / s.y * s2;
-    double fy = s.y * s.sp * s0 + s.x * s.sp / s.r * s1 + s.cp / s.r / s.y * s2;
-    double fz = s.x * s0 - s.y / s.r * s1;
+    const double inv_ry = inv_r / s.y;
+    double fx = s.y * s.cp * s0 + s.x * s.cp * inv_r * s1 - s.sp * inv_ry * s2;
+    double fy = s.y * s.sp * s0 + s.x * s.sp * inv_r * s1 + s.cp * inv_ry * s2;
+    double fz = s.x * s0 - s.y * inv_r * s1;
     res[i] = make_double4(pot, fx, fy, fz);
   }
 }
@@ -476,7 +499,15 @@ void laplace_execute(fmmb_plan* plan, const double* d_charges, double* d_results
 
   // upward sweep
   FMMB_CUDA(cudaEventRecord(ev[12], s));
-  p2m_kernel<<<nblk((int64_t)T.nleaves * 32, 128), 128, 0, s>>>(T.leaves.p, T.nleaves, T.bbegin.p, T.bend.p,
+  const int p2m_warps = pp <= 64 ? 4 : 1;          // shared tile: warps x 32 bodies x P^2 doubles
+  const size_t p2m_sh = (size_t)p2m_warps * 32 * (pp | 1) * sizeof(double);
+  static bool p2m_attr = false;
+  if (!p2m_attr) {
+    FMMB_CUDA(cudaFuncSetAttribute(p2m_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024));
+    p2m_attr = true;
+  }
+  p2m_kernel<<<nblk(T.nleaves, p2m_warps), 32 * p2m_warps, p2m_sh, s>>>(
+      T.leaves.p, T.nleaves, T.bbegin.p, T.bend.p,
                                                                T.center.p, T.body.p, P, plan->M.p);
                        ++plan->launches;
   size_t sh_mm = (size_t)(pp + nc) * sizeof(double2);

@@ -33,6 +33,8 @@ __device__ __forceinline__ void regular_harmonics(int P, const Sph& s, double si
   double fact = 1, pn = 1, rhom = 1;
   double er = 1, ei = 0;
   const double cp = s.cp, sp = sign * s.sp;
+  // divisions of the recurrences become multiplications by tabulated 1/k and one 1/sin(alpha)
+  const double inv_y = THETA ? 1.0 / s.y : 0.0;
   for (int m = 0; m < P; ++m) {
     double p = pn;
     int npn = m * m + 2 * m;
@@ -40,7 +42,7 @@ __device__ __forceinline__ void regular_harmonics(int P, const Sph& s, double si
     double p1 = p;
     p = s.x * (2 * m + 1) * p1;
     double at = 0;
-    if (THETA) at = rhom * (p - (m + 1) * s.x * p1) / s.y * c_pref[npn];
+    if (THETA) at = rhom * (p - (m + 1) * s.x * p1) * inv_y * c_pref[npn];
     f(m, m, a * er, a * ei, at * er, at * ei);
     rhom *= s.r;
     double rhon = rhom;
@@ -49,8 +51,8 @@ __device__ __forceinline__ void regular_harmonics(int P, const Sph& s, double si
       a = rhon * p * c_pref[npm];
       double p2 = p1;
       p1 = p;
-      p = (s.x * (2 * n + 1) * p1 - (n + m) * p2) / (n - m + 1);
-      if (THETA) at = rhon * ((n - m + 1) * p - (n + 1) * s.x * p1) / s.y * c_pref[npm];
+      p = (s.x * (2 * n + 1) * p1 - (n + m) * p2) * c_rcp[n - m + 1];
+      if (THETA) at = rhon * ((n - m + 1) * p - (n + 1) * s.x * p1) * inv_y * c_pref[npm];
       f(n, m, a * er, a * ei, at * er, at * ei);
       rhon *= s.r;
     }

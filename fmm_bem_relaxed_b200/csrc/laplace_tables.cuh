@@ -10,6 +10,7 @@ namespace fmmb {
 // The reference carries an extra factor 1/EPS in Anm that cancels in every use; dropped here.
 static __constant__ double c_pref[4 * FMMB_MAX_P * FMMB_MAX_P];
 static __constant__ double c_anm[4 * FMMB_MAX_P * FMMB_MAX_P];
+static __constant__ double c_rcp[2 * FMMB_MAX_P + 2];   // 1/k
 
 static inline void upload_laplace_tables() {
   const int top = 2 * FMMB_MAX_P;
@@ -27,5 +28,9 @@ static inline void upload_laplace_tables() {
     }
   FMMB_CUDA(cudaMemcpyToSymbol(c_pref, pref.data(), pref.size() * sizeof(double)));
   FMMB_CUDA(cudaMemcpyToSymbol(c_anm, anm.data(), anm.size() * sizeof(double)));
+  double rcp[2 * FMMB_MAX_P + 2];
+  rcp[0] = 0.0;
+  for (int k = 1; k < 2 * FMMB_MAX_P + 2; ++k) rcp[k] = 1.0 / k;
+  FMMB_CUDA(cudaMemcpyToSymbol(c_rcp, rcp, sizeof rcp));
 }
 }  // namespace fmmb
