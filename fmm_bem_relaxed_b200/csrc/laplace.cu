@@ -285,7 +285,12 @@ __device__ __forceinline__ void p2p_accumulate(const double4 t, const double4 sq
                                                double& fy, double& fz) {
   double dx = sq.x - t.x, dy = sq.y - t.y, dz = sq.z - t.z;
   double r2 = dx * dx + dy * dy + dz * dz;
-  double inv = rsqrt(r2);
+  // 1/sqrt(r2): MUFU.RSQ64H seed (relative error < 2^-22) + one cubic step, branch free so that the
+  // unrolled sources interleave.  r2 = 0 gives inf/NaN here and is discarded by the select below.
+  double y0;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y0) : "d"(r2));
+  double e = fma(-(r2 * y0), y0, 1.0);
+  double inv = fma(y0 * e, fma(0.375, e, 0.5), y0);
   if (r2 < 1e-8) inv = 0.0;                        // LaplaceSpherical.hpp:158
   double qi = sq.w * inv;
   double qi3 = qi * (inv * inv);
