@@ -22,7 +22,7 @@ import numpy as np
 from . import capi
 from .capi import FmmbError
 
-__all__ = ["FMMOptions", "LaplaceSpherical", "FMM_plan", "Direct", "FmmbError", "capi", "comm_unique_id",
+__all__ = ["FMMOptions", "LaplaceSpherical", "LaplaceSphericalBEM", "Panels", "FMM_plan", "Direct", "FmmbError", "capi", "comm_unique_id",
            "partition_ranges", "get_options"]
 
 
@@ -96,18 +96,62 @@ class LaplaceSpherical:
             capi.check(capi.load().fmmb_plan_set_p(self._plan._h, self.P))
 
 
+class LaplaceSphericalBEM(LaplaceSpherical):
+    """Mirror of reference kernel/LaplaceSphericalBEM.hpp:14-157: order P and K Gauss points per panel.
+    Sources are panels: an (n, 3, 3) array of vertices (p0, p1, p2) plus one boundary-condition flag per
+    panel (Panels.POTENTIAL / Panels.NORMAL_DERIV); charges and results are scalars."""
+    kind = capi.LAPLACE_SPHERICAL_BEM
+    result_dim = 1
+
+    def __init__(self, p=5, k=3):
+        super().__init__(p)
+        self.K = int(k)
+
+
+class Panels:
+    """A set of triangular panels (the std::vector<Panel> a reference driver builds)."""
+    POTENTIAL, NORMAL_DERIV = 0, 1
+
+    def __init__(self, vertices, bc=None):
+        self.vertices = np.ascontiguousarray(np.asarray(vertices, dtype=np.float64).reshape(-1, 3, 3))
+        n = self.vertices.shape[0]
+        self.bc = np.zeros(n, np.int32) if bc is None else np.ascontiguousarray(np.broadcast_to(bc, (n,)), np.int32)
+
+    def switch_BC(self):
+        """Panel::switch_BC on every panel (examples/LaplaceBEM.cpp:218-232)."""
+        self.bc = (1 - self.bc).astype(np.int32)
+
+    @property
+    def centers(self):
+        v = self.vertices
+        return ((v[:, 0] + v[:, 1]) + v[:, 2]) / 3
+
+    def __len__(self):
+        return self.vertices.shape[0]
+
+
 class FMM_plan:
     """Mirror of reference include/FMM_plan.hpp:15-128 for source == target plans."""
 
     def __init__(self, kernel, sources, opts=None):
         lib = capi.load()
         opts = opts or FMMOptions()
-        pts = np.ascontiguousarray(np.asarray(sources, dtype=np.float64).reshape(-1, 3))
-        self._n = pts.shape[0]
-        self.K = LaplaceSpherical(kernel.P)      # the plan owns a COPY of the kernel (FMM_plan.hpp:37)
         self.opts_ = opts
-        kd = capi.KernelDesc(kernel.kind, kernel.P, 0.0, 0, 0)
-        src = capi.Sources(self._n, capi.ptr(pts))
+        verts = bc = None
+        if isinstance(kernel, LaplaceSphericalBEM):
+            if not isinstance(sources, Panels):
+                sources = Panels(sources)
+            pts = np.ascontiguousarray(sources.centers)
+            verts, bc = sources.vertices, np.ascontiguousarray(sources.bc)
+            self.K = LaplaceSphericalBEM(kernel.P, kernel.K)
+            kd = capi.KernelDesc(kernel.kind, kernel.P, 0.0, kernel.K, 0)
+        else:
+            pts = np.ascontiguousarray(np.asarray(sources, dtype=np.float64).reshape(-1, 3))
+            self.K = LaplaceSpherical(kernel.P)      # the plan owns a COPY of the kernel (FMM_plan.hpp:37)
+            kd = capi.KernelDesc(kernel.kind, kernel.P, 0.0, 0, 0)
+        self._n = pts.shape[0]
+        self._rdim = self.K.result_dim
+        src = capi.Sources(self._n, capi.ptr(pts), capi.ptr(verts), capi.ptr(bc))
         op = capi.Options(opts.theta, opts.NCRIT_, opts.evaluator, opts.device, 0,
                           getattr(opts, "rank", 0), getattr(opts, "nranks", 1), 0)
         h = ctypes.c_void_p()
@@ -136,7 +180,7 @@ class FMM_plan:
         q = np.ascontiguousarray(np.asarray(charges, dtype=np.float64).reshape(-1))
         if q.shape[0] != self._n:
             raise ValueError("charges.size() != sources.size()")
-        out = np.empty((self._n, 4), dtype=np.float64)
+        out = np.empty((self._n, 4) if self._rdim == 4 else (self._n,), dtype=np.float64)
         capi.check(self._lib.fmmb_plan_execute(self._h, capi.ptr(q), capi.ptr(out)))
         return out
 

@@ -15,6 +15,7 @@ LIB_PATH = os.path.join(_HERE, "libfmmb200.so")
 FMMB_MAX_P = 16
 T_TOTAL, T_UPWARD, T_M2L, T_DOWNWARD, T_P2P, T_H2D, T_D2H, T_LAUNCHES, T_M2L_GEMM, T_COUNT = 0, 1, 2, 3, 4, 5, 6, 7, 8, 10
 LAPLACE_SPHERICAL = 0
+LAPLACE_SPHERICAL_BEM = 1
 
 
 class FmmbError(RuntimeError):
@@ -35,7 +36,8 @@ class Options(ctypes.Structure):
 
 
 class Sources(ctypes.Structure):
-    _fields_ = [("n", ctypes.c_int64), ("points", ctypes.c_void_p)]
+    _fields_ = [("n", ctypes.c_int64), ("points", ctypes.c_void_p), ("vertices", ctypes.c_void_p),
+                ("bc", ctypes.c_void_p)]
 
 
 class PlanInfo(ctypes.Structure):
@@ -43,6 +45,7 @@ class PlanInfo(ctypes.Structure):
                 ("n_levels", ctypes.c_int64), ("n_m2l_pairs", ctypes.c_int64),
                 ("n_p2p_box_pairs", ctypes.c_int64), ("n_p2p_body_pairs", ctypes.c_int64),
                 ("n_m2l_classes", ctypes.c_int64), ("n_m2l_pairs_batched", ctypes.c_int64),
+                ("n_near_entries", ctypes.c_int64),
                 ("own_body_begin", ctypes.c_int64), ("own_body_end", ctypes.c_int64),
                 ("p", ctypes.c_int32), ("charge_dim", ctypes.c_int32), ("result_dim", ctypes.c_int32),
                 ("device", ctypes.c_int32)]

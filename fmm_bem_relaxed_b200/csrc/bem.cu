@@ -1,0 +1,393 @@
+// csrc/bem.cu -- LaplaceSphericalBEM on the GPU: panel sources, Gauss-quadrature P2M, cached near field.
+//
+// Replaces (reference paths):
+//   kernel/LaplaceSphericalBEM.hpp:61-97     Panel geometry                 -> bem_setup_kernel
+//   :273-297 operator() + :159-264 eval_G / eval_dGdn + examples/BEM/SemiAnalytical.hpp
+//        evaluated for every near pair by executor/EvalP2P.hpp:47-97        -> bem_assemble_kernel (once per plan)
+//   include/Matvec.hpp:14-33 CSR matvec in EvalInteractionLazySparse.hpp:134-151 -> bem_near_kernel (per matvec)
+//   :307-352 P2M with K quadrature points per panel, two expansion sets     -> bem_p2m_kernel<SET>
+//   :448-476 L2P (scalar result, set and sign picked by the target's BC)     -> bem_l2p_kernel<SET>
+//   M2M / M2L / L2L of each set (:362-383,432-437) are the Laplace translations -> laplace_translations()
+//
+// Near field layout.  All targets of a leaf share one source list (the P2P list of the leaf), so the
+// cached near-field matrix is block dense: for a work item (<= 32 targets of one leaf) the block is
+// stored source-major, val[base + j * cnt + lane], without column indices; the per-matvec kernel
+// streams it once (8 bytes per entry) with coalesced loads -- HBM bound.
+//
+// Expansion sets: set 0 = single layer (G), fed by POTENTIAL panels and read by
+// POTENTIAL targets; set 1 = double layer (dG/dn), fed and read by NORMAL_DERIV panels.  Only the sets
+// that have panels are run (the reference's examples use one boundary condition at a time).
+#include "common.cuh"
+#include "laplace_ops.cuh"
+#include "../hostcxx/bem_math.hpp"
+
+namespace fmmb {
+
+struct BemData {
+  int K = 4;
+  bool set_active[2] = {false, false};
+  DevBuf<bem::Panel> pan;        // tree order
+  DevBuf<int> bc;                // tree order: 0 POTENTIAL, 1 NORMAL_DERIV
+  DevBuf<double> nf_val;         // cached near field, block layout (see above)
+  DevBuf<long long> nf_base;     // per P2P work item: offset of its block
+  DevBuf<double> res_near, res_far;
+  int64_t nnz = 0;
+};
+
+void bem_free(BemData* b) { delete b; }
+int64_t bem_nnz(const BemData* b) { return b->nnz; }
+
+namespace {
+
+using namespace ops;
+
+__constant__ bem::Rule c_rule;   // K-point panel rule
+__constant__ bem::Rule c_fine;   // 16-point rule for the near-singular double layer
+
+inline int nblk(int64_t n, int t) { return (int)((n + t - 1) / t); }
+
+__global__ void bem_setup_kernel(const double* __restrict__ verts, const int* __restrict__ bc,
+                                 const unsigned* __restrict__ perm, int64_t n, bem::Panel* __restrict__ pan,
+                                 int* __restrict__ bc_tree) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double* v = verts + 9 * (size_t)perm[i];
+  bem::Panel p;
+  bem::make_panel(v, v + 3, v + 6, p);
+  pan[i] = p;
+  bc_tree[i] = bc ? bc[perm[i]] : 0;
+}
+
+// per work item: number of cached entries = targets x total source bodies of the leaf's list
+__global__ void bem_count_kernel(const int4* __restrict__ items, int nitems, const unsigned* __restrict__ bb,
+                                 const unsigned* __restrict__ be, const int* __restrict__ off,
+                                 const int* __restrict__ src, long long* __restrict__ cnt) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i > nitems) return;
+  long long c = 0;
+  if (i < nitems) {
+    int4 it = items[i];
+    long long ns = 0;
+    for (int e = off[it.x]; e < off[it.x + 1]; ++e) ns += be[src[e]] - bb[src[e]];
+    c = ns * it.z;
+  }
+  cnt[i] = c;
+}
+
+constexpr int kBemWarps = 4;
+
+// one warp per work item: lane = target, sources staged through a warp-private tile of panels
+__global__ void __launch_bounds__(32 * kBemWarps)
+bem_assemble_kernel(const int4* __restrict__ items, int nitems, const unsigned* __restrict__ bb,
+                    const unsigned* __restrict__ be, const int* __restrict__ off, const int* __restrict__ src,
+                    const bem::Panel* __restrict__ pan, const int* __restrict__ bc,
+                    const long long* __restrict__ base, double* __restrict__ val) {
+  __shared__ bem::Panel tiles[kBemWarps][32];
+  const int wl = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int item = blockIdx.x * kBemWarps + wl;
+  if (item >= nitems) return;
+  bem::Panel* tile = tiles[wl];
+  const int4 it = items[item];
+  const int cnt = it.z;
+  const bool act = lane < cnt;
+  double tc[3] = {0, 0, 0};
+  int tbc = 0;
+  if (act) {
+    const bem::Panel& t = pan[it.y + lane];
+    tc[0] = t.c[0]; tc[1] = t.c[1]; tc[2] = t.c[2];
+    tbc = bc[it.y + lane];
+  }
+  double* out = val + base[item];
+  long long j = 0;
+  for (int e = off[it.x]; e < off[it.x + 1]; ++e) {
+    const int sb = src[e];
+    const unsigned c0 = bb[sb], c1 = be[sb];
+    for (unsigned b0 = c0; b0 < c1; b0 += 32) {
+      const int ns = (int)min(32u, c1 - b0);
+      __syncwarp();
+      if (lane < ns) tile[lane] = pan[b0 + lane];
+      __syncwarp();
+      if (act)
+        for (int k = 0; k < ns; ++k) out[(j + k) * cnt + lane] = bem::kernel(tbc, tc, tile[k], c_rule, c_fine);
+      j += ns;
+    }
+  }
+}
+
+// results(targets of the item) = block * charges(sources); same traversal order as the assembly
+__global__ void __launch_bounds__(32 * kBemWarps)
+bem_near_kernel(const int4* __restrict__ items, int nitems, const unsigned* __restrict__ bb,
+                const unsigned* __restrict__ be, const int* __restrict__ off, const int* __restrict__ src,
+                const double4* __restrict__ body, const long long* __restrict__ base,
+                const double* __restrict__ val, double* __restrict__ res) {
+  __shared__ double tiles[kBemWarps][32];
+  const int wl = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int item = blockIdx.x * kBemWarps + wl;
+  if (item >= nitems) return;
+  double* tile = tiles[wl];
+  const int4 it = items[item];
+  const int cnt = it.z;
+  const bool act = lane < cnt;
+  const double* in = val + base[item] + lane;
+  double a0 = 0, a1 = 0;
+  long long j = 0;
+  for (int e = off[it.x]; e < off[it.x + 1]; ++e) {
+    const int sb = src[e];
+    const unsigned c0 = bb[sb], c1 = be[sb];
+    for (unsigned b0 = c0; b0 < c1; b0 += 32) {
+      const int ns = (int)min(32u, c1 - b0);
+      __syncwarp();
+      if (lane < ns) tile[lane] = body[b0 + lane].w;
+      __syncwarp();
+      if (act) {
+        int k = 0;
+        for (; k + 2 <= ns; k += 2) {
+          a0 = fma(in[(j + k) * cnt], tile[k], a0);
+          a1 = fma(in[(j + k + 1) * cnt], tile[k + 1], a1);
+        }
+        if (k < ns) a0 = fma(in[(j + k) * cnt], tile[k], a0);
+      }
+      j += ns;
+    }
+  }
+  if (act) res[it.y + lane] = a0 + a1;
+}
+
+// P2M: warp per leaf; lane = (panel, quadrature point); rows go through a shared tile, then lane = coefficient
+template <int SET>
+__global__ void __launch_bounds__(128)
+bem_p2m_kernel(const int* __restrict__ leaves, int nleaves, const unsigned* __restrict__ bb,
+               const unsigned* __restrict__ be, const double4* __restrict__ center,
+               const double4* __restrict__ body, const bem::Panel* __restrict__ pan, const int* __restrict__ bc,
+               int P, double* __restrict__ M) {
+  extern __shared__ double bem_sh[];
+  const int pp = P * P, ld = pp | 1;
+  const int wl = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int w = blockIdx.x * (blockDim.x >> 5) + wl;
+  if (w >= nleaves) return;
+  double* tile = bem_sh + (size_t)wl * 32 * ld;
+  const int b = leaves[w];
+  const double4 c = center[b];
+  const unsigned b0 = bb[b], b1 = be[b];
+  const int K = c_rule.n;
+  const int nent = (int)(b1 - b0) * K;
+  double acc[(FMMB_MAX_P * FMMB_MAX_P + 31) / 32];
+#pragma unroll
+  for (int i = 0; i < (FMMB_MAX_P * FMMB_MAX_P + 31) / 32; ++i) acc[i] = 0.0;
+  for (int base = 0; base < nent; base += 32) {
+    const int ent = base + lane;
+    const int cnt = min(32, nent - base);
+    __syncwarp();
+    if (ent < nent) {
+      const unsigned i = b0 + ent / K;
+      const int qi = ent % K;
+      double* row = tile + lane * ld;
+      if (bc[i] != SET) {
+        for (int r = 0; r < pp; ++r) row[r] = 0.0;
+      } else {
+        const bem::Panel& s = pan[i];
+        double q[3];
+        bem::quad_point(s, c_rule.pt[qi], q);
+        const double mult = body[i].w * c_rule.w[qi] * s.area;
+        const Sph sp = to_sph(q[0] - c.x, q[1] - c.y, q[2] - c.z);
+        if (SET == 0) {
+          regular_harmonics<false>(P, sp, -1.0, [&](int n, int m, double yr, double yi, double, double) {
+            row[n * n + n + m] = mult * yr;
+            if (m > 0) row[n * n + n - m] = mult * yi;
+          });
+        } else {
+          // (n . grad)(rho^n Y_n^m): spherical components -> Cartesian, LaplaceSphericalBEM.hpp:331-344
+          const double ir = 1.0 / sp.r, iry = ir / sp.y;
+          const double ax = sp.y * sp.cp, ay = sp.y * sp.sp, az = sp.x;                       // d/d rho
+          const double bx = sp.x * sp.cp * ir, by = sp.x * sp.sp * ir, bz = -sp.y * ir;        // d/d alpha
+          const double cx = -sp.sp * iry, cy = sp.cp * iry;                                    // d/d beta
+          const double na = s.nrm[0] * ax + s.nrm[1] * ay + s.nrm[2] * az;
+          const double nb_ = s.nrm[0] * bx + s.nrm[1] * by + s.nrm[2] * bz;
+          const double ncc = s.nrm[0] * cx + s.nrm[1] * cy;
+          regular_harmonics<true>(P, sp, -1.0, [&](int n, int m, double yr, double yi, double tr, double ti) {
+            // brh = n/rho Y, bal = Ytheta, bbe = -i m Y = (m yi, -m yr)
+            const double fr = n * ir;
+            const double vr = na * fr * yr + nb_ * tr + ncc * (m * yi);
+            const double vi = na * fr * yi + nb_ * ti - ncc * (m * yr);
+            row[n * n + n + m] = mult * vr;
+            if (m > 0) row[n * n + n - m] = mult * vi;
+          });
+        }
+      }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int i2 = 0; i2 < (FMMB_MAX_P * FMMB_MAX_P + 31) / 32; ++i2) {
+      const int col = lane + 32 * i2;
+      if (col < pp) {
+        double sum = 0;
+        for (int k = 0; k < cnt; ++k) sum += tile[k * ld + col];
+        acc[i2] += sum;
+      }
+    }
+  }
+  double* Mb = M + (size_t)b * xstride(P);
+#pragma unroll
+  for (int i2 = 0; i2 < (FMMB_MAX_P * FMMB_MAX_P + 31) / 32; ++i2) {
+    const int col = lane + 32 * i2;
+    if (col < pp) Mb[col] = acc[i2];
+  }
+}
+
+// L2P: warp per leaf, lane per target panel; only panels whose BC selects this set are touched
+template <int SET>
+__global__ void __launch_bounds__(128)
+bem_l2p_kernel(const int* __restrict__ leaves, int nleaves, const unsigned* __restrict__ bb,
+               const unsigned* __restrict__ be, const double4* __restrict__ center,
+               const unsigned char* __restrict__ has_local, const bem::Panel* __restrict__ pan,
+               const int* __restrict__ bc, int P, const double* __restrict__ L, double* __restrict__ res) {
+  extern __shared__ double2 bem_ls[];
+  const int nc = P * (P + 1) / 2;
+  const int wl = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int w = blockIdx.x * (blockDim.x >> 5) + wl;
+  if (w >= nleaves) return;
+  const int b = leaves[w];
+  if (!has_local[b]) return;
+  double2* Ls = bem_ls + wl * nc;
+  for (int i = lane; i < nc; i += 32) {
+    int n, m;
+    unpack_nm(i, n, m);
+    Ls[i] = load_coef(L + (size_t)b * xstride(P), n, m);
+  }
+  __syncwarp();
+  const double4 c = center[b];
+  for (unsigned i = bb[b] + lane; i < be[b]; i += 32) {
+    if (bc[i] != SET) continue;
+    const bem::Panel& t = pan[i];
+    const Sph s = to_sph(t.c[0] - c.x, t.c[1] - c.y, t.c[2] - c.z);
+    double acc = 0;
+    regular_harmonics<false>(P, s, 1.0, [&](int n, int m, double yr, double yi, double, double) {
+      const double2 l = Ls[n * (n + 1) / 2 + m];
+      acc += (m == 0 ? 1.0 : 2.0) * (l.x * yr - l.y * yi);
+    });
+    res[i] = SET == 0 ? acc : -acc;
+  }
+}
+
+__global__ void bem_gather_charges(const double* __restrict__ q, const unsigned* __restrict__ perm, int64_t n,
+                                   double4* __restrict__ body) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < n) body[i].w = q[perm[i]];
+}
+__global__ void bem_scatter(const double* __restrict__ near, const double* __restrict__ far,
+                            const unsigned* __restrict__ perm, int64_t i0, int64_t i1, double* __restrict__ out) {
+  int64_t i = i0 + blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < i1) out[perm[i]] = near[i] + far[i];
+}
+
+}  // namespace
+
+// Plan-time: panel geometry in tree order, then the cached near field.
+void bem_setup(fmmb_plan* plan, const double* verts_host, const int32_t* bc_host, int quad_k) {
+  Tree& T = plan->tree;
+  cudaStream_t s = plan->stream;
+  if (!bem::rule_supported(quad_k))
+    throw StatusError{FMMB_ERR_UNSUPPORTED, "Gauss rules with 1, 3, 4 (or 7, aliased to 4 like the reference) points are built"};
+  if (T.nranks > 1) throw StatusError{FMMB_ERR_UNSUPPORTED, "multi-GPU BEM plans are not built yet"};
+  BemData* B = new BemData();
+  plan->bem = B;
+  B->K = quad_k == 7 ? 4 : quad_k;
+  upload_laplace_tables();   // this translation unit's copy of the factorial tables
+  bem::Rule rule = bem::make_rule(B->K), fine = bem::make_rule(17);
+  FMMB_CUDA(cudaMemcpyToSymbol(c_rule, &rule, sizeof rule));
+  FMMB_CUDA(cudaMemcpyToSymbol(c_fine, &fine, sizeof fine));
+  const int64_t n = T.n;
+  DevBuf<double> verts;
+  DevBuf<int> bc;
+  verts.from_host(verts_host, 9 * (size_t)n, s);
+  for (int64_t i = 0; i < n; ++i) {
+    int v = bc_host ? bc_host[i] : 0;
+    if (v != 0 && v != 1) throw StatusError{FMMB_ERR_INVALID, "bc entries must be 0 (POTENTIAL) or 1 (NORMAL_DERIV)"};
+    B->set_active[v] = true;
+  }
+  if (bc_host) bc.from_host(bc_host, n, s);
+  B->pan.resize(n); B->bc.resize(n);
+  bem_setup_kernel<<<nblk(n, 128), 128, 0, s>>>(verts.p, bc_host ? bc.p : nullptr, T.perm.p, n, B->pan.p, B->bc.p);
+  FMMB_CUDA(cudaGetLastError());
+  // block offsets of the cached near field
+  const int ni = T.n_p2p_items;
+  DevBuf<long long> cnt;
+  cnt.resize(ni + 1);
+  bem_count_kernel<<<nblk(ni + 1, 128), 128, 0, s>>>(T.p2p_items.p, ni, T.bbegin.p, T.bend.p, T.p2p_off.p,
+                                                    T.p2p_src.p, cnt.p);
+  FMMB_CUDA(cudaGetLastError());
+  std::vector<long long> h = cnt.to_host(s), off(ni + 1, 0);
+  for (int i = 0; i < ni; ++i) off[i + 1] = off[i] + h[i];
+  B->nnz = off[ni];
+  B->nf_base.from_host(off.data(), off.size(), s);
+  B->nf_val.resize((size_t)B->nnz);
+  if (ni)
+    bem_assemble_kernel<<<nblk(ni, kBemWarps), 32 * kBemWarps, 0, s>>>(T.p2p_items.p, ni, T.bbegin.p, T.bend.p,
+                                                                      T.p2p_off.p, T.p2p_src.p, B->pan.p, B->bc.p,
+                                                                      B->nf_base.p, B->nf_val.p);
+  FMMB_CUDA(cudaGetLastError());
+  FMMB_CUDA(cudaStreamSynchronize(s));
+}
+
+void bem_execute(fmmb_plan* plan, const double* d_charges, double* d_results) {
+  Tree& T = plan->tree;
+  BemData* B = plan->bem;
+  const int P = plan->p, nc = P * (P + 1) / 2, pp = P * P;
+  const int64_t n = T.n;
+  cudaStream_t s = plan->stream;
+  cudaEvent_t* ev = plan->ev;
+  laplace_prepare_expansions(plan);
+  B->res_near.resize(n); B->res_far.resize(n);
+  plan->launches = 0;
+  FMMB_CUDA(cudaEventRecord(ev[0], s));
+  bem_gather_charges<<<nblk(n, 256), 256, 0, s>>>(d_charges, T.perm.p, n, T.body.p);
+  FMMB_CUDA(cudaEventRecord(ev[1], s));
+  FMMB_CUDA(cudaEventRecord(ev[6], s));
+  const int ni = T.n_p2p_items;
+  if (ni)
+    bem_near_kernel<<<nblk(ni, kBemWarps), 32 * kBemWarps, 0, s>>>(T.p2p_items.p, ni, T.bbegin.p, T.bend.p,
+                                                                  T.p2p_off.p, T.p2p_src.p, T.body.p,
+                                                                  B->nf_base.p, B->nf_val.p, B->res_near.p);
+  FMMB_CUDA(cudaEventRecord(ev[7], s));
+  B->res_far.zero(s);
+  plan->launches += 3;
+  FMMB_CUDA(cudaEventRecord(ev[12], s));
+  const int warps = pp <= 64 ? 4 : 1;
+  const size_t sh = (size_t)warps * 32 * (pp | 1) * sizeof(double);
+  static bool attr = false;
+  if (!attr) {
+    FMMB_CUDA(cudaFuncSetAttribute(bem_p2m_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024));
+    FMMB_CUDA(cudaFuncSetAttribute(bem_p2m_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024));
+    attr = true;
+  }
+  for (int set = 0; set < 2; ++set) {
+    if (!B->set_active[set]) continue;
+    if (set == 0)
+      bem_p2m_kernel<0><<<nblk(T.nleaves, warps), 32 * warps, sh, s>>>(T.leaves.p, T.nleaves, T.bbegin.p, T.bend.p,
+                                                                      T.center.p, T.body.p, B->pan.p, B->bc.p, P,
+                                                                      plan->M.p);
+    else
+      bem_p2m_kernel<1><<<nblk(T.nleaves, warps), 32 * warps, sh, s>>>(T.leaves.p, T.nleaves, T.bbegin.p, T.bend.p,
+                                                                      T.center.p, T.body.p, B->pan.p, B->bc.p, P,
+                                                                      plan->M.p);
+    ++plan->launches;
+    laplace_translations(plan, s);
+    if (set == 0)
+      bem_l2p_kernel<0><<<nblk(T.n_own_leaves, 4), 128, 4 * nc * sizeof(double2), s>>>(
+          T.own_leaves.p, T.n_own_leaves, T.bbegin.p, T.bend.p, T.center.p, T.has_local.p, B->pan.p, B->bc.p, P,
+          plan->L.p, B->res_far.p);
+    else
+      bem_l2p_kernel<1><<<nblk(T.n_own_leaves, 4), 128, 4 * nc * sizeof(double2), s>>>(
+          T.own_leaves.p, T.n_own_leaves, T.bbegin.p, T.bend.p, T.center.p, T.has_local.p, B->pan.p, B->bc.p, P,
+          plan->L.p, B->res_far.p);
+    ++plan->launches;
+  }
+  FMMB_CUDA(cudaEventRecord(ev[4], s));
+  bem_scatter<<<nblk(n, 256), 256, 0, s>>>(B->res_near.p, B->res_far.p, T.perm.p, 0, n, d_results);
+  ++plan->launches;
+  FMMB_CUDA(cudaEventRecord(ev[5], s));
+  FMMB_CUDA(cudaGetLastError());
+  plan->timed = true;
+}
+
+}  // namespace fmmb

@@ -57,12 +57,17 @@ int fmmb_plan_create(const fmmb_kernel_desc* kernel, const fmmb_sources* sources
                      fmmb_plan** out_plan) {
   if (!kernel || !sources || !out_plan) { set_error("null argument"); return FMMB_ERR_INVALID; }
   *out_plan = nullptr;
-  if (kernel->kind != FMMB_LAPLACE_SPHERICAL) {
-    set_error("only FMMB_LAPLACE_SPHERICAL is built in this version");
+  if (kernel->kind != FMMB_LAPLACE_SPHERICAL && kernel->kind != FMMB_LAPLACE_SPHERICAL_BEM) {
+    set_error("only FMMB_LAPLACE_SPHERICAL and FMMB_LAPLACE_SPHERICAL_BEM are built in this version");
     return FMMB_ERR_UNSUPPORTED;
   }
+  const bool is_bem = kernel->kind == FMMB_LAPLACE_SPHERICAL_BEM;
+  if (is_bem && !sources->vertices) { set_error("BEM kernels need the panel vertices"); return FMMB_ERR_INVALID; }
   if (kernel->p < 1 || kernel->p > FMMB_MAX_P) { set_error("expansion order must be in 1..16"); return FMMB_ERR_INVALID; }
-  if (sources->n < 1 || !sources->points) { set_error("need at least one source point"); return FMMB_ERR_INVALID; }
+  if (sources->n < 1 || (!sources->points && !(kernel->kind == FMMB_LAPLACE_SPHERICAL_BEM && sources->vertices))) {
+    set_error("need at least one source point");
+    return FMMB_ERR_INVALID;
+  }
   fmmb_options opts;
   std::memset(&opts, 0, sizeof opts);
   opts.theta = 0.5; opts.ncrit = 64; opts.evaluator = FMMB_EVAL_FMM; opts.device = -1;
@@ -88,10 +93,25 @@ int fmmb_plan_create(const fmmb_kernel_desc* kernel, const fmmb_sources* sources
     FMMB_CUDA(cudaStreamCreateWithFlags(&plan->stream, cudaStreamNonBlocking));
     FMMB_CUDA(cudaStreamCreateWithFlags(&plan->stream2, cudaStreamNonBlocking));
     for (auto& e : plan->ev) FMMB_CUDA(cudaEventCreate(&e));
+    plan->charge_dim = 1;
+    plan->result_dim = is_bem ? 1 : 4;
     laplace_init_tables(plan);
-    build_tree(plan, sources->points, sources->n);
+    std::vector<double> centres;
+    const double* pts = sources->points;
+    if (!pts) {
+      // panel centres in the reference's operation order: ((p0 + p1) + p2) / 3
+      centres.resize(3 * (size_t)sources->n);
+      for (int64_t i = 0; i < sources->n; ++i)
+        for (int k = 0; k < 3; ++k) {
+          const double* v = sources->vertices + 9 * (size_t)i;
+          centres[3 * (size_t)i + k] = ((v[k] + v[3 + k]) + v[6 + k]) / 3;
+        }
+      pts = centres.data();
+    }
+    build_tree(plan, pts, sources->n);
     build_m2l_classes(plan);
     build_p2p_items(plan);
+    if (is_bem) bem_setup(plan, sources->vertices, sources->bc, kernel->quad_k);
   });
   if (rc != FMMB_OK) { fmmb_plan_destroy(plan); return rc; }
   *out_plan = plan;
@@ -104,6 +124,7 @@ void fmmb_plan_destroy(fmmb_plan* plan) {
   if (plan->stream) cudaStreamSynchronize(plan->stream);
   if (plan->stream2) cudaStreamSynchronize(plan->stream2);
   comm_destroy(plan);
+  bem_free(plan->bem);
   for (auto& kv : plan->m2l_coeff) delete kv.second;
   for (auto& e : plan->ev) if (e) cudaEventDestroy(e);
   if (plan->stream) cudaStreamDestroy(plan->stream);
@@ -122,7 +143,8 @@ int fmmb_plan_execute_device(fmmb_plan* plan, const double* charges_dev, double*
   if (!plan || !charges_dev || !results_dev) { set_error("null argument"); return FMMB_ERR_INVALID; }
   return guarded([&] {
     FMMB_CUDA(cudaSetDevice(plan->device));
-    laplace_execute(plan, charges_dev, results_dev);
+    if (plan->bem) bem_execute(plan, charges_dev, results_dev);
+    else laplace_execute(plan, charges_dev, results_dev);
   });
 }
 
@@ -132,15 +154,17 @@ int fmmb_plan_execute(fmmb_plan* plan, const double* charges_host, double* resul
     FMMB_CUDA(cudaSetDevice(plan->device));
     const int64_t n = plan->tree.n;
     cudaStream_t s = plan->stream;
+    const size_t rd = plan->result_dim;
     plan->charges.resize(n);
-    plan->results.resize(4 * (size_t)n);
+    plan->results.resize(rd * (size_t)n);
     if (plan->tree.nranks > 1 && !plan->comm) plan->results.zero(s);   // only the owned slice gets written
     FMMB_CUDA(cudaEventRecord(plan->ev[8], s));
     FMMB_CUDA(cudaMemcpyAsync(plan->charges.p, charges_host, n * sizeof(double), cudaMemcpyHostToDevice, s));
     FMMB_CUDA(cudaEventRecord(plan->ev[9], s));
-    laplace_execute(plan, plan->charges.p, plan->results.p);
+    if (plan->bem) bem_execute(plan, plan->charges.p, plan->results.p);
+    else laplace_execute(plan, plan->charges.p, plan->results.p);
     FMMB_CUDA(cudaEventRecord(plan->ev[10], s));
-    FMMB_CUDA(cudaMemcpyAsync(results_host, plan->results.p, 4 * (size_t)n * sizeof(double),
+    FMMB_CUDA(cudaMemcpyAsync(results_host, plan->results.p, rd * (size_t)n * sizeof(double),
                               cudaMemcpyDeviceToHost, s));
     FMMB_CUDA(cudaEventRecord(plan->ev[11], s));
     FMMB_CUDA(cudaStreamSynchronize(s));
@@ -154,6 +178,7 @@ int fmmb_plan_execute(fmmb_plan* plan, const double* charges_host, double* resul
 int fmmb_plan_direct(fmmb_plan* plan, const double* charges_host, int64_t nt, const double* targets_host,
                      double* results_host) {
   if (!plan || !charges_host || !targets_host || !results_host || nt < 0) { set_error("bad argument"); return FMMB_ERR_INVALID; }
+  if (plan->bem) { set_error("fmmb_plan_direct is built for point kernels only"); return FMMB_ERR_UNSUPPORTED; }
   return guarded([&] {
     FMMB_CUDA(cudaSetDevice(plan->device));
     cudaStream_t s = plan->stream;
@@ -213,7 +238,8 @@ int fmmb_plan_get_info(fmmb_plan* plan, fmmb_plan_info* info) {
   info->n_m2l_pairs = T.n_lr; info->n_p2p_box_pairs = T.n_p2p; info->n_p2p_body_pairs = T.n_p2p_body_pairs;
   info->n_m2l_classes = plan->cls.n_classes; info->n_m2l_pairs_batched = plan->cls.n_pairs;
   info->own_body_begin = T.own_b0; info->own_body_end = T.own_b1;
-  info->p = plan->p; info->charge_dim = 1; info->result_dim = 4; info->device = plan->device;
+  info->n_near_entries = plan->bem ? bem_nnz(plan->bem) : 0;
+  info->p = plan->p; info->charge_dim = plan->charge_dim; info->result_dim = plan->result_dim; info->device = plan->device;
   return FMMB_OK;
 }
 

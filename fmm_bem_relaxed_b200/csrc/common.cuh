@@ -142,6 +142,8 @@ struct TransBatch {
   DevBuf<double> tmp;                // phase-1 output columns, [slot][p^2]
 };
 
+struct BemData;
+
 struct LaplaceTables {
   int pmax = 0;
   DevBuf<double> pref;               // sqrt((n-|m|)!/(n+|m|)!), index n^2+n+m, n < 2*pmax
@@ -166,6 +168,8 @@ struct fmmb_plan {
   fmmb::DevBuf<double> charges;      // original order staging
   fmmb::DevBuf<double4> res_near, res_far;  // tree order
   fmmb::DevBuf<double4> res_tree;    // multi-GPU: near + far in tree order, all-gathered over NCCL
+  fmmb::BemData* bem = nullptr;      // LaplaceSphericalBEM plans only
+  int charge_dim = 1, result_dim = 4;
   void* comm = nullptr;              // ncclComm_t once fmmb_plan_comm_init ran
   fmmb::DevBuf<double> results;      // original order staging, 4n
   double phase_ms[FMMB_T_COUNT] = {0};
@@ -187,6 +191,13 @@ void allgather_results(fmmb_plan* plan, cudaStream_t s);
 void laplace_init_tables(fmmb_plan* plan);
 void laplace_execute(fmmb_plan* plan, const double* d_charges, double* d_results);
 void build_p2p_items(fmmb_plan* plan);
+void laplace_translations(fmmb_plan* plan, cudaStream_t s);
+void laplace_prepare_expansions(fmmb_plan* plan);
+// bem.cu
+void bem_setup(fmmb_plan* plan, const double* verts_host, const int32_t* bc_host, int quad_k);
+void bem_execute(fmmb_plan* plan, const double* d_charges, double* d_results);
+void bem_free(BemData* b);
+int64_t bem_nnz(const BemData* b);
 void laplace_direct_raw(const double* d_spts, const double* d_q, int64_t ns, const double* d_tpts, int64_t nt,
                         double* d_out, cudaStream_t s);
 void measure_fp64_peak(double* dfma, double* dmma);

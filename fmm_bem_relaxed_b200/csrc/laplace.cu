@@ -467,54 +467,14 @@ static const double* m2l_coeffs(fmmb_plan* plan, int P) {
   return buf->p;
 }
 
-void laplace_execute(fmmb_plan* plan, const double* d_charges, double* d_results) {
+// M2M sweep -> M2L -> L2L sweep on plan->M / plan->L at the current order (expects the leaf multipoles
+// in plan->M; leaves the complete local expansions in plan->L).  Records ev[2] / ev[3] around M2L.
+void laplace_translations(fmmb_plan* plan, cudaStream_t s) {
   Tree& T = plan->tree;
   const int P = plan->p, nc = P * (P + 1) / 2, pp = P * P;
   const int nb = T.nboxes;
-  const int64_t n = T.n;
-  cudaStream_t s = plan->stream, s2 = plan->overlap_p2p ? plan->stream2 : plan->stream;
-  const int xs = (pp + 1) & ~1;       // doubles per box (real layout, padded to 16 B)
-  plan->M.resize((size_t)nb * xs);
-  plan->L.resize((size_t)nb * xs);
-  if (plan->p_alloc != P) {
-    // the padding double of odd-sized expansions is read (times zero) by the GEMM: keep it finite
-    plan->M.zero(plan->stream);
-    plan->L.zero(plan->stream);
-    plan->p_alloc = P;
-  }
-  plan->res_near.resize(n);
-  plan->res_far.resize(n);
   const double* C = m2l_coeffs(plan, P);
   cudaEvent_t* ev = plan->ev;
-  plan->launches = 0;
-
-  FMMB_CUDA(cudaEventRecord(ev[0], s));
-  gather_charges<<<nblk(n, 256), 256, 0, s>>>(d_charges, T.perm.p, n, T.body.p);
-  ++plan->launches;
-  FMMB_CUDA(cudaEventRecord(ev[1], s));
-
-  // near field on the second stream: needs only the charges
-  if (s2 != s) FMMB_CUDA(cudaStreamWaitEvent(s2, ev[1], 0));
-  FMMB_CUDA(cudaEventRecord(ev[6], s2));
-  p2p_kernel<<<nblk(T.n_p2p_items, kP2PWarps), 32 * kP2PWarps, 0, s2>>>(T.p2p_items.p, T.n_p2p_items, T.bbegin.p,
-                                                                       T.bend.p, T.p2p_off.p, T.p2p_src.p,
-                                                                       T.body.p, plan->res_near.p);
-       ++plan->launches;
-  FMMB_CUDA(cudaEventRecord(ev[7], s2));
-
-  // upward sweep
-  FMMB_CUDA(cudaEventRecord(ev[12], s));
-  const int p2m_warps = pp <= 64 ? 4 : 1;          // shared tile: warps x 32 bodies x P^2 doubles
-  const size_t p2m_sh = (size_t)p2m_warps * 32 * (pp | 1) * sizeof(double);
-  static bool p2m_attr = false;
-  if (!p2m_attr) {
-    FMMB_CUDA(cudaFuncSetAttribute(p2m_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024));
-    p2m_attr = true;
-  }
-  p2m_kernel<<<nblk(T.nleaves, p2m_warps), 32 * p2m_warps, p2m_sh, s>>>(
-      T.leaves.p, T.nleaves, T.bbegin.p, T.bend.p,
-                                                               T.center.p, T.body.p, P, plan->M.p);
-                       ++plan->launches;
   size_t sh_mm = (size_t)(pp + nc) * sizeof(double2);
   const bool up_batched = m2m_batched(plan, s);
   for (int l = T.nlevels - 2; l >= 0 && !up_batched; --l) {
@@ -552,6 +512,62 @@ void laplace_execute(fmmb_plan* plan, const double* d_charges, double* d_results
     l2l_kernel<<<hi - lo, 64, sh_mm, s>>>(lo, hi, T.parent.p, T.has_local.p, T.center.p, P, plan->L.p);
     ++plan->launches;
   }
+}
+
+// Sizes the expansion buffers for the current order (real layout, see laplace_ops.cuh).
+void laplace_prepare_expansions(fmmb_plan* plan) {
+  const int P = plan->p, pp = P * P;
+  const int xs = (pp + 1) & ~1;
+  plan->M.resize((size_t)plan->tree.nboxes * xs);
+  plan->L.resize((size_t)plan->tree.nboxes * xs);
+  if (plan->p_alloc != P) {
+    // the padding double of odd-sized expansions is read (times zero) by the GEMM: keep it finite
+    plan->M.zero(plan->stream);
+    plan->L.zero(plan->stream);
+    plan->p_alloc = P;
+  }
+}
+
+void laplace_execute(fmmb_plan* plan, const double* d_charges, double* d_results) {
+  Tree& T = plan->tree;
+  const int P = plan->p, nc = P * (P + 1) / 2, pp = P * P;
+  const int nb = T.nboxes;
+  const int64_t n = T.n;
+  cudaStream_t s = plan->stream, s2 = plan->overlap_p2p ? plan->stream2 : plan->stream;
+  laplace_prepare_expansions(plan);
+  plan->res_near.resize(n);
+  plan->res_far.resize(n);
+  cudaEvent_t* ev = plan->ev;
+  plan->launches = 0;
+
+  FMMB_CUDA(cudaEventRecord(ev[0], s));
+  gather_charges<<<nblk(n, 256), 256, 0, s>>>(d_charges, T.perm.p, n, T.body.p);
+  ++plan->launches;
+  FMMB_CUDA(cudaEventRecord(ev[1], s));
+
+  // near field on the second stream: needs only the charges
+  if (s2 != s) FMMB_CUDA(cudaStreamWaitEvent(s2, ev[1], 0));
+  FMMB_CUDA(cudaEventRecord(ev[6], s2));
+  p2p_kernel<<<nblk(T.n_p2p_items, kP2PWarps), 32 * kP2PWarps, 0, s2>>>(T.p2p_items.p, T.n_p2p_items, T.bbegin.p,
+                                                                       T.bend.p, T.p2p_off.p, T.p2p_src.p,
+                                                                       T.body.p, plan->res_near.p);
+       ++plan->launches;
+  FMMB_CUDA(cudaEventRecord(ev[7], s2));
+
+  // upward sweep
+  FMMB_CUDA(cudaEventRecord(ev[12], s));
+  const int p2m_warps = pp <= 64 ? 4 : 1;          // shared tile: warps x 32 bodies x P^2 doubles
+  const size_t p2m_sh = (size_t)p2m_warps * 32 * (pp | 1) * sizeof(double);
+  static bool p2m_attr = false;
+  if (!p2m_attr) {
+    FMMB_CUDA(cudaFuncSetAttribute(p2m_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024));
+    p2m_attr = true;
+  }
+  p2m_kernel<<<nblk(T.nleaves, p2m_warps), 32 * p2m_warps, p2m_sh, s>>>(
+      T.leaves.p, T.nleaves, T.bbegin.p, T.bend.p,
+                                                               T.center.p, T.body.p, P, plan->M.p);
+                       ++plan->launches;
+  laplace_translations(plan, s);
   l2p_kernel<<<nblk(T.n_own_leaves, 4), 128, 4 * nc * sizeof(double2), s>>>(T.own_leaves.p, T.n_own_leaves, T.bbegin.p, T.bend.p,
                                                                      T.center.p, T.has_local.p, T.body.p, P,
                                                                      plan->L.p, plan->res_far.p);

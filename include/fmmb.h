@@ -46,7 +46,7 @@ typedef enum {
 /* Kernel classes of the reference (kernel/ *.hpp) that a plan can be built for. */
 typedef enum {
   FMMB_LAPLACE_SPHERICAL = 0,          /* kernel/LaplaceSpherical.hpp: charge 1, result 4 */
-  FMMB_LAPLACE_SPHERICAL_BEM = 1,      /* kernel/LaplaceSphericalBEM.hpp (not built yet) */
+  FMMB_LAPLACE_SPHERICAL_BEM = 1,      /* kernel/LaplaceSphericalBEM.hpp: panels, charge 1, result 1 */
   FMMB_STOKES_SPHERICAL_STRESSLET = 2, /* kernel/StokesSpherical.hpp, STRESSLET (not built yet) */
   FMMB_YUKAWA_CARTESIAN = 3,           /* kernel/YukawaCartesian.hpp (not built yet) */
   FMMB_YUKAWA_CARTESIAN_BEM = 4        /* kernel/YukawaCartesianBEM.hpp (not built yet) */
@@ -77,11 +77,19 @@ typedef struct {
   int32_t reserved;
 } fmmb_options;
 
-/* Point sources (source_type == point_type kernels).  points: 3*n doubles, point-major
- * (x0,y0,z0,x1,...), host memory, borrowed for the duration of the call. */
+/* Sources, host memory, borrowed for the duration of the call.
+ *   points    3*n doubles, point-major (x0,y0,z0,x1,...): the positions the octree is built on.
+ *             Point kernels: the sources themselves.  BEM kernels: the panel centres,
+ *             static_cast<point_type>(panel) as the reference's tree sees them
+ *             (kernel/LaplaceSphericalBEM.hpp:99); NULL = computed from the vertices.
+ *   vertices  BEM kernels only: 9*n doubles, (p0, p1, p2) per panel as passed to Panel(p0,p1,p2)
+ *             (kernel/LaplaceSphericalBEM.hpp:61-97).
+ *   bc        BEM kernels only: n entries, 0 = Panel::POTENTIAL, 1 = Panel::NORMAL_DERIV; NULL = all 0. */
 typedef struct {
   int64_t n;
   const double* points;
+  const double* vertices;
+  const int32_t* bc;
 } fmmb_sources;
 
 /* Sizes a caller needs for fmmb_plan_get_tree and for recomputing work counts. */
@@ -95,6 +103,7 @@ typedef struct {
   int64_t n_p2p_body_pairs;
   int64_t n_m2l_classes;   /* distinct translation vectors handled by the batched M2L */
   int64_t n_m2l_pairs_batched;
+  int64_t n_near_entries;  /* BEM: cached near-field matrix entries (= n_p2p_body_pairs) */
   int64_t own_body_begin;  /* multi-GPU: tree-order body range whose results this rank computes */
   int64_t own_body_end;
   int32_t p;               /* current expansion order */

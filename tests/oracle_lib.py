@@ -47,6 +47,10 @@ def load():
         L.fmmo_get_expansions.argtypes = [vp, vp, vp]
         L.fmmo_laplace_direct.argtypes = [ctypes.c_int, vp, vp, ctypes.c_int, vp, vp, ctypes.c_int]
         L.fmmo_drand48_inputs.argtypes = [ctypes.c_int, vp, vp]
+        L.fmmo_unit_sphere.argtypes = [ctypes.c_int, vp]
+        L.fmmo_panel_centers.argtypes = [ctypes.c_int, vp, vp]
+        L.fmmo_bem_execute.argtypes = [vp, ctypes.c_int, ctypes.c_int, vp, vp, vp, vp, ctypes.c_int]
+        L.fmmo_bem_direct.argtypes = [ctypes.c_int, ctypes.c_int, vp, vp, vp, vp, ctypes.c_int]
         _lib = L
     return _lib
 
@@ -118,6 +122,47 @@ class Oracle:
         Lx = np.zeros((self.nboxes, nc, 2))
         self.L.fmmo_get_expansions(self.h, _p(M), _p(Lx))
         return M, Lx
+
+
+def unit_sphere(recursions):
+    """Octahedron-subdivision sphere of the reference (Triangulation::UnitSphere): (n, 3, 3) vertices."""
+    L = load()
+    n = L.fmmo_unit_sphere(recursions, None)
+    v = np.zeros((n, 3, 3))
+    L.fmmo_unit_sphere(recursions, _p(v))
+    return v
+
+
+def panel_centers(verts):
+    verts = np.ascontiguousarray(np.asarray(verts, dtype=np.float64).reshape(-1, 9))
+    c = np.zeros((verts.shape[0], 3))
+    load().fmmo_panel_centers(verts.shape[0], _p(verts), _p(c))
+    return c
+
+
+class BemOracle(Oracle):
+    """Oracle tree on the panel centres + the restated LaplaceSphericalBEM matvec."""
+
+    def __init__(self, verts, bc, ncrit=64, theta=0.5):
+        self.verts = np.ascontiguousarray(np.asarray(verts, dtype=np.float64).reshape(-1, 9))
+        n = self.verts.shape[0]
+        self.bc = np.ascontiguousarray(np.broadcast_to(bc, (n,)), np.int32)
+        super().__init__(panel_centers(self.verts), ncrit, theta)
+
+    def execute(self, charges, P, K=4, threads=None):
+        q = np.ascontiguousarray(np.asarray(charges, dtype=np.float64).reshape(-1))
+        res = np.zeros(self.n)
+        rc = self.L.fmmo_bem_execute(self.h, P, K, _p(self.verts), _p(self.bc), _p(q), _p(res),
+                                     threads or os.cpu_count() or 1)
+        if rc != 0:
+            raise RuntimeError("oracle BEM execute failed: %d" % rc)
+        return res
+
+    def direct(self, charges, K=4, threads=None):
+        q = np.ascontiguousarray(np.asarray(charges, dtype=np.float64).reshape(-1))
+        out = np.zeros(self.n)
+        self.L.fmmo_bem_direct(self.n, K, _p(self.verts), _p(self.bc), _p(q), _p(out), threads or os.cpu_count() or 1)
+        return out
 
 
 def direct(spts, q, tpts, threads=None):

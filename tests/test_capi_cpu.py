@@ -32,21 +32,21 @@ def test_library_exports_every_declared_symbol():
 def test_struct_layouts_match_header():
     assert ctypes.sizeof(capi.KernelDesc) == 24
     assert ctypes.sizeof(capi.Options) == 40
-    assert ctypes.sizeof(capi.Sources) == 16
-    assert ctypes.sizeof(capi.PlanInfo) == 11 * 8 + 4 * 4
+    assert ctypes.sizeof(capi.Sources) == 32
+    assert ctypes.sizeof(capi.PlanInfo) == 12 * 8 + 4 * 4
 
 
 def test_argument_validation_needs_no_gpu():
     lib = capi.load()
     h = ctypes.c_void_p()
     pts = np.random.rand(10, 3)
-    src = capi.Sources(10, capi.ptr(pts))
+    src = capi.Sources(10, capi.ptr(pts), None, None)
     bad_kind = capi.KernelDesc(3, 5, 0.0, 0, 0)
     assert lib.fmmb_plan_create(ctypes.byref(bad_kind), ctypes.byref(src), None, ctypes.byref(h)) == -4
     assert b"LAPLACE" in lib.fmmb_last_error()
     bad_p = capi.KernelDesc(0, 17, 0.0, 0, 0)
     assert lib.fmmb_plan_create(ctypes.byref(bad_p), ctypes.byref(src), None, ctypes.byref(h)) == -1
-    empty = capi.Sources(0, None)
+    empty = capi.Sources(0, None, None, None)
     ok_k = capi.KernelDesc(0, 5, 0.0, 0, 0)
     assert lib.fmmb_plan_create(ctypes.byref(ok_k), ctypes.byref(empty), None, ctypes.byref(h)) == -1
     assert lib.fmmb_plan_set_p(None, 3) == -1
