@@ -32,15 +32,14 @@ class FMM_plan {
   typedef typename kernel_type::result_type result_type;
 
   FMM_plan(const kernel_type& k, const std::vector<source_type>& source, FMMOptions& opts)
-      : plan_(nullptr), K(k), opts_(opts), n_(source.size()) {
-    // sources -> plain point array (point kernels: source_type == point_type)
-    std::vector<double> pts(3 * n_);
-    for (size_t i = 0; i < n_; ++i) {
-      const point_type p = static_cast<point_type>(source[i]);
-      pts[3 * i] = p[0]; pts[3 * i + 1] = p[1]; pts[3 * i + 2] = p[2];
-    }
-    fmmb_kernel_desc kd = {Kernel::fmmb_kind, K.order(), K.kappa(), 0, 0};
-    fmmb_sources src = {(int64_t)n_, pts.data()};
+      : plan_(nullptr), K(k), opts_(opts), n_(source.size()), sources_(source) {
+    // sources -> plain arrays: positions (panel centres for BEM kernels), panel vertices, boundary conditions
+    std::vector<double> pts, verts;
+    std::vector<int32_t> bc;
+    Kernel::pack_sources(source, pts, verts, bc);
+    fmmb_kernel_desc kd = {Kernel::fmmb_kind, K.order(), K.kappa(), K.quad_k(), 0};
+    fmmb_sources src = {(int64_t)n_, pts.data(), verts.empty() ? nullptr : verts.data(),
+                        bc.empty() ? nullptr : bc.data()};
     fmmb_options fo = {};
     fo.theta = opts_.MAC().theta_;
     fo.ncrit = opts_.max_per_box();
@@ -53,7 +52,9 @@ class FMM_plan {
   }
   FMM_plan(const FMM_plan&) = delete;
   FMM_plan& operator=(const FMM_plan&) = delete;
-  FMM_plan(FMM_plan&& o) : plan_(o.plan_), K(o.K), opts_(o.opts_), n_(o.n_) { o.plan_ = nullptr; }
+  FMM_plan(FMM_plan&& o) : plan_(o.plan_), K(o.K), opts_(o.opts_), n_(o.n_), sources_(std::move(o.sources_)) {
+    o.plan_ = nullptr;
+  }
   ~FMM_plan() { fmmb_plan_destroy(plan_); }
 
   kernel_type& kernel() { return K; }
@@ -79,12 +80,26 @@ class FMM_plan {
     return results;
   }
 
+  /** The plan's copies of the sources in TREE order (reference include/FMM_plan.hpp:100-107; used by
+   * Preconditioners::Diagonal, examples/LaplaceBEM.cpp:241-244) */
+  typedef typename std::vector<source_type>::iterator body_source_iterator;
+  body_source_iterator source_begin() { tree_order(); return tree_sources_.begin(); }
+  body_source_iterator source_end() { tree_order(); return tree_sources_.end(); }
+
   /** extension: the C handle, for fmmb_plan_get_info / phase times */
   fmmb_plan* handle() { return plan_; }
 
  private:
+  void tree_order() {
+    if (!tree_sources_.empty() || !plan_) return;
+    std::vector<uint32_t> perm(n_);
+    if (fmmb_plan_get_tree(plan_, perm.data(), nullptr, nullptr, nullptr, nullptr, nullptr, nullptr) != FMMB_OK) return;
+    tree_sources_.reserve(n_);
+    for (size_t i = 0; i < n_; ++i) tree_sources_.push_back(sources_[perm[i]]);
+  }
   fmmb_plan* plan_;
   kernel_type K;
   FMMOptions opts_;
   size_t n_;
+  std::vector<source_type> sources_, tree_sources_;
 };

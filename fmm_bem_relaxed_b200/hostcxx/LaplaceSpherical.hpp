@@ -8,6 +8,8 @@
  * K(t,s) = 1/|s-t| (potential), (s-t)/|s-t|^3 (force)
  */
 #include <cmath>
+#include <cstdint>
+#include <vector>
 #include <Vec.hpp>
 
 #include "../../include/fmmb.h"
@@ -51,4 +53,13 @@ class LaplaceSpherical {
   kernel_value_type transpose(const kernel_value_type& kst) const {
     return kernel_value_type(kst[0], -kst[1], -kst[2], -kst[3]);
   }
+
+  /** what FMM_plan ships through the C ABI for point sources */
+  static void pack_sources(const std::vector<source_type>& src, std::vector<double>& pts, std::vector<double>& verts,
+                           std::vector<int32_t>& bc) {
+    pts.resize(3 * src.size());
+    verts.clear(); bc.clear();
+    for (size_t i = 0; i < src.size(); ++i) { pts[3 * i] = src[i][0]; pts[3 * i + 1] = src[i][1]; pts[3 * i + 2] = src[i][2]; }
+  }
+  int quad_k() const { return 0; }
 };

@@ -1,0 +1,89 @@
+// LaplaceBEM on the unit sphere with relaxed GMRES, in the manner of the reference's
+// examples/LaplaceBEM.cpp:166-373 (first-kind equation unless -second_kind): phi = 1 on the sphere,
+// solve for d(phi)/dn (exact solution 1), check the exterior potential at (3,3,3) against 1/|x|.
+//   laplace_bem -recursions 7 -p 8 -k 4 -ncrit 64 -theta 0.5 -solver_tol 1e-6 [-fixed_p] [-second_kind] [-diagonal]
+// With -DREF_GMRES_HEADER=... the REFERENCE's own GMRES.hpp is compiled in unchanged instead of ours.
+#include <FMM_plan.hpp>
+#include <LaplaceSphericalBEM.hpp>
+#include <Triangulation.hpp>
+#ifdef REF_GMRES_HEADER
+#include REF_GMRES_HEADER
+#else
+#include <GMRES.hpp>
+#endif
+
+#include <cmath>
+#include <cstring>
+
+int main(int argc, char** argv) {
+  int recursions = 4, p = 5, k = 3, max_iterations = 500;
+  FMMOptions opts = get_options(argc, argv);
+  opts.sparse_local = true;
+  SolverOptions solver_options;
+  bool second_kind = false, diagonal = false;
+  for (int i = 1; i < argc; ++i) {
+    if (!strcmp(argv[i], "-recursions")) recursions = atoi(argv[++i]);
+    else if (!strcmp(argv[i], "-p")) { p = atoi(argv[++i]); solver_options.max_p = p; }
+    else if (!strcmp(argv[i], "-k")) k = atoi(argv[++i]);
+    else if (!strcmp(argv[i], "-second_kind")) second_kind = true;
+    else if (!strcmp(argv[i], "-fixed_p")) solver_options.variable_p = false;
+    else if (!strcmp(argv[i], "-solver_tol")) solver_options.residual = atof(argv[++i]);
+    else if (!strcmp(argv[i], "-max_iters")) max_iterations = atoi(argv[++i]);
+    else if (!strcmp(argv[i], "-diagonal")) diagonal = true;
+    else if (!strcmp(argv[i], "-theta") || !strcmp(argv[i], "-ncrit") || !strcmp(argv[i], "-eval")) ++i;
+  }
+  solver_options.max_iters = max_iterations;
+  solver_options.restart = max_iterations;
+
+  typedef LaplaceSphericalBEM kernel_type;
+  typedef kernel_type::point_type point_type;
+  typedef kernel_type::source_type source_type;
+  typedef kernel_type::target_type target_type;
+  typedef kernel_type::charge_type charge_type;
+  typedef kernel_type::result_type result_type;
+  kernel_type K(p, k);
+  std::vector<source_type> panels;
+  Triangulation::UnitSphere(panels, recursions);
+  if (second_kind) for (auto& it : panels) it.switch_BC();
+  std::vector<charge_type> charges(panels.size(), 1.);
+
+  double tic = get_time();
+  FMM_plan<kernel_type> plan(K, panels, opts);
+  std::vector<charge_type> x(panels.size(), 0.);
+  std::vector<result_type> b;
+  {
+    for (auto& it : panels) it.switch_BC();
+    FMM_plan<kernel_type> rhs_plan(K, panels, opts);
+    b = rhs_plan.execute(charges);
+    for (auto& it : panels) it.switch_BC();
+  }
+  double setup_time = get_time() - tic;
+  if (b.empty()) return 1;
+
+  tic = get_time();
+  printf(second_kind ? "2nd-kind equation being solved\n" : "1st-kind equation being solved\n");
+  if (diagonal) {
+    Preconditioners::Diagonal<charge_type> M(K, plan.source_begin(), plan.source_end());
+    printf("Solver: GMRES\nPreconditioner: Diagonal\n");
+    GMRES(plan, x, b, solver_options, M);
+  } else {
+    printf("Solver: GMRES\nPreconditioner: Identity\n");
+    GMRES(plan, x, b, solver_options);
+  }
+  double solve_time = get_time() - tic;
+  printf("\nTIMING:\n\tsetup : %.4es\n\tsolve : %.4es\n", setup_time, solve_time);
+
+  double e = 0., e2 = 0.;
+  for (auto xi : x) { e += (xi - 1.) * (xi - 1.); e2 += 1.; }
+  std::vector<target_type> outside(1, target_type(point_type(3., 3., 3.), point_type(3., 3., 3.), point_type(3., 3., 3.)));
+  outside[0].center = point_type(3., 3., 3.);
+  std::vector<result_type> r1(1, 0.), r2(1, 0.);
+  Direct::matvec(K, panels.begin(), panels.end(), x.begin(), outside.begin(), outside.end(), r2.begin());
+  for (auto& op : outside) op.switch_BC();
+  Direct::matvec(K, panels.begin(), panels.end(), charges.begin(), outside.begin(), outside.end(), r1.begin());
+  double exact = 1. / norm(static_cast<point_type>(outside[0]));
+  double outside_result = (r2[0] - r1[0]) / 4 / M_PI;
+  printf("external phi: %.5g, exact: %.5g, error: %.4e\n", outside_result, exact, fabs(outside_result - exact) / fabs(exact));
+  printf("relative error: %.3e\n", sqrt(e / e2));
+  return 0;
+}
