@@ -108,6 +108,42 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def bench_gmres_c2():
+    """Second half of the BASELINE metric ("GMRES solve s"): config C2, LaplaceBEM on a 32 768-panel sphere,
+    relaxed GMRES to 1e-6 with p <= 8, through the C++ host mirror (fmm_bem_relaxed_b200/hostcxx) and -- as the
+    CPU baseline -- the reference's unmodified examples/LaplaceBEM.cpp (oracle/_ref/LaplaceBEM)."""
+    import re
+    import tempfile
+    args = ["-recursions", "7", "-p", "8", "-k", "4", "-ncrit", "64", "-theta", "0.5", "-solver_tol", "1e-6"]
+
+    def run(exe, env=None):
+        if not os.path.exists(exe):
+            return None
+        with tempfile.TemporaryDirectory() as tmp:     # the reference writes test.vert / test.face into cwd
+            out = subprocess.check_output([exe] + args, env=env, cwd=tmp).decode()
+        m = re.search(r"Final residual: ([0-9.eE+-]+), after (\d+) iterations", out)
+        return {"solve_s": float(re.search(r"solve : ([0-9.eE+-]+)s", out).group(1)),
+                "setup_s": float(re.search(r"setup : ([0-9.eE+-]+)s", out).group(1)),
+                "iterations": int(m.group(2)), "final_residual": float(m.group(1)),
+                "p_schedule": [int(x) for x in re.findall(r"fmm_req_p: (\d+)", out)]}
+    env = dict(os.environ)
+    env["LD_LIBRARY_PATH"] = os.path.join(ROOT, "fmm_bem_relaxed_b200") + ":" + env.get("LD_LIBRARY_PATH", "")
+    exe = os.path.join(ROOT, "fmm_bem_relaxed_b200", "hostcxx", "bin", "laplace_bem")
+    ours = run(exe, env)
+    if ours is None:
+        return None
+    ours = min((run(exe, env) for _ in range(3)), key=lambda r: r["solve_s"])   # first call pays CUDA start-up
+    threads = os.cpu_count() or 1
+    ref = run(os.path.join(ROOT, "oracle", "_ref", "LaplaceBEM"), dict(os.environ, OMP_NUM_THREADS=str(threads)))
+    out = {"config": "LaplaceBEM sphere 32768 panels, K=4, relaxed GMRES to 1e-6, p<=8 (BASELINE config 2)",
+           "solve_s": ours["solve_s"], "setup_s": ours["setup_s"], "iterations": ours["iterations"],
+           "final_residual": ours["final_residual"], "p_schedule": ours["p_schedule"]}
+    if ref is not None:
+        out["reference"] = dict(ref, cores=threads, kind="reference",
+                                note="multi-threaded reference M2L has a data race (SURVEY F5): time only")
+    return out
+
+
 def bench_reference(args, rank, world):
     if rank != 0:
         return
@@ -321,6 +357,9 @@ def bench_ours(args, rank, world, local_rank):
                    "sample": "1 full matvec of the same workload by the unmodified reference "
                              "(oracle/_ref/ref_laplace, FMM_plan::execute, %.2f s; plan %.2f s), OMP threads=%d"
                              % (r["best_s"], r["plan_s"], r["threads"])}
+    gmres = None
+    if world == 1 and not args.no_cpu_baseline:
+        gmres = bench_gmres_c2()
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
@@ -338,6 +377,8 @@ def bench_ours(args, rank, world, local_rank):
     }
     if cpu is not None:
         line["cpu_baseline"] = cpu
+    if gmres is not None:
+        line["gmres_c2"] = gmres
     print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()
