@@ -339,10 +339,10 @@ void bem_execute(fmmb_plan* plan, const double* d_charges, double* d_results) {
   laplace_prepare_expansions(plan);
   B->res_near.resize(n); B->res_far.resize(n);
   plan->launches = 0;
-  FMMB_CUDA(cudaEventRecord(ev[0], s));
+  if (!plan->capturing) FMMB_CUDA(cudaEventRecord(ev[0], s));
   bem_gather_charges<<<nblk(n, 256), 256, 0, s>>>(d_charges, T.perm.p, n, T.body.p);
   FMMB_CUDA(cudaEventRecord(ev[1], s));
-  FMMB_CUDA(cudaEventRecord(ev[6], s));
+  if (!plan->capturing) FMMB_CUDA(cudaEventRecord(ev[6], s));
   const int ni = T.n_p2p_items;
   if (ni)
     bem_near_kernel<<<nblk(ni, kBemWarps), 32 * kBemWarps, 0, s>>>(T.p2p_items.p, ni, T.bbegin.p, T.bend.p,
@@ -351,7 +351,7 @@ void bem_execute(fmmb_plan* plan, const double* d_charges, double* d_results) {
   FMMB_CUDA(cudaEventRecord(ev[7], s));
   B->res_far.zero(s);
   plan->launches += 3;
-  FMMB_CUDA(cudaEventRecord(ev[12], s));
+  if (!plan->capturing) FMMB_CUDA(cudaEventRecord(ev[12], s));
   const int warps = pp <= 64 ? 4 : 1;
   const size_t sh = (size_t)warps * 32 * (pp | 1) * sizeof(double);
   static bool attr = false;
@@ -382,10 +382,10 @@ void bem_execute(fmmb_plan* plan, const double* d_charges, double* d_results) {
           plan->L.p, B->res_far.p);
     ++plan->launches;
   }
-  FMMB_CUDA(cudaEventRecord(ev[4], s));
+  if (!plan->capturing) FMMB_CUDA(cudaEventRecord(ev[4], s));
   bem_scatter<<<nblk(n, 256), 256, 0, s>>>(B->res_near.p, B->res_far.p, T.perm.p, 0, n, d_results);
   ++plan->launches;
-  FMMB_CUDA(cudaEventRecord(ev[5], s));
+  if (!plan->capturing) FMMB_CUDA(cudaEventRecord(ev[5], s));
   FMMB_CUDA(cudaGetLastError());
   plan->timed = true;
 }

@@ -30,6 +30,14 @@ static int guarded(F&& f) {
 }
 
 static void update_phase_times(fmmb_plan* plan) {
+  if (plan->graph_timed && !plan->timed) {
+    // graph launch: only the total is observable (per-kernel events are not recorded inside a capture)
+    float t = 0;
+    if (cudaEventElapsedTime(&t, plan->ev[0], plan->ev[5]) != cudaSuccess) { cudaGetLastError(); t = 0; }
+    for (int i = 0; i < FMMB_T_COUNT; ++i) if (i != FMMB_T_LAUNCHES && i != FMMB_T_H2D && i != FMMB_T_D2H) plan->phase_ms[i] = 0;
+    plan->phase_ms[FMMB_T_TOTAL] = t;
+    return;
+  }
   if (!plan->timed) return;
   auto ms = [&](int a, int b) {
     float t = 0;
@@ -123,6 +131,7 @@ void fmmb_plan_destroy(fmmb_plan* plan) {
   cudaSetDevice(plan->device);
   if (plan->stream) cudaStreamSynchronize(plan->stream);
   if (plan->stream2) cudaStreamSynchronize(plan->stream2);
+  for (auto& kv : plan->graphs) cudaGraphExecDestroy(kv.second);
   comm_destroy(plan);
   bem_free(plan->bem);
   for (auto& kv : plan->m2l_coeff) delete kv.second;
@@ -139,12 +148,53 @@ int fmmb_plan_set_p(fmmb_plan* plan, int p) {
   return FMMB_OK;
 }
 
+namespace fmmb {
+// One matvec on the plan stream.  The second time a (order, charges, results) combination is seen the
+// kernel sequence -- including the second stream and the NCCL collectives -- is captured into a CUDA
+// graph; from then on a matvec is a single graph launch (no per-kernel launch gaps).
+static void run_matvec(fmmb_plan* plan, const double* q, double* r) {
+  auto direct = [&] {
+    if (plan->bem) bem_execute(plan, q, r);
+    else laplace_execute(plan, q, r);
+  };
+  if (!plan->use_graph || !plan->overlap_p2p) { direct(); return; }
+  fmmb_plan::GraphKey key{plan->p, q, r};
+  cudaStream_t s = plan->stream;
+  auto it = plan->graphs.find(key);
+  if (it == plan->graphs.end()) {
+    if (plan->graph_seen[key]++ == 0) { direct(); return; }   // first call allocates buffers, builds tables
+    cudaGraph_t g = nullptr;
+    plan->capturing = true;
+    cudaError_t e = cudaStreamBeginCapture(s, cudaStreamCaptureModeRelaxed);
+    if (e == cudaSuccess) {
+      try { direct(); } catch (...) { plan->capturing = false; cudaStreamEndCapture(s, &g); if (g) cudaGraphDestroy(g); plan->use_graph = false; throw; }
+      e = cudaStreamEndCapture(s, &g);
+    }
+    plan->capturing = false;
+    cudaGraphExec_t ex = nullptr;
+    if (e == cudaSuccess && g) e = cudaGraphInstantiate(&ex, g, 0);
+    if (g) cudaGraphDestroy(g);
+    if (e != cudaSuccess || !ex) {          // graphs are an optimisation: fall back to plain launches
+      cudaGetLastError();
+      plan->use_graph = false;
+      direct();
+      return;
+    }
+    it = plan->graphs.emplace(key, ex).first;
+  }
+  FMMB_CUDA(cudaEventRecord(plan->ev[0], s));
+  FMMB_CUDA(cudaGraphLaunch(it->second, s));
+  FMMB_CUDA(cudaEventRecord(plan->ev[5], s));
+  plan->timed = false;
+  plan->graph_timed = true;
+}
+}  // namespace fmmb
+
 int fmmb_plan_execute_device(fmmb_plan* plan, const double* charges_dev, double* results_dev) {
   if (!plan || !charges_dev || !results_dev) { set_error("null argument"); return FMMB_ERR_INVALID; }
   return guarded([&] {
     FMMB_CUDA(cudaSetDevice(plan->device));
-    if (plan->bem) bem_execute(plan, charges_dev, results_dev);
-    else laplace_execute(plan, charges_dev, results_dev);
+    run_matvec(plan, charges_dev, results_dev);
   });
 }
 
@@ -161,8 +211,7 @@ int fmmb_plan_execute(fmmb_plan* plan, const double* charges_host, double* resul
     FMMB_CUDA(cudaEventRecord(plan->ev[8], s));
     FMMB_CUDA(cudaMemcpyAsync(plan->charges.p, charges_host, n * sizeof(double), cudaMemcpyHostToDevice, s));
     FMMB_CUDA(cudaEventRecord(plan->ev[9], s));
-    if (plan->bem) bem_execute(plan, plan->charges.p, plan->results.p);
-    else laplace_execute(plan, plan->charges.p, plan->results.p);
+    run_matvec(plan, plan->charges.p, plan->results.p);
     FMMB_CUDA(cudaEventRecord(plan->ev[10], s));
     FMMB_CUDA(cudaMemcpyAsync(results_host, plan->results.p, rd * (size_t)n * sizeof(double),
                               cudaMemcpyDeviceToHost, s));
@@ -196,6 +245,7 @@ int fmmb_plan_set_option(fmmb_plan* plan, const char* name, int64_t value) {
   if (!plan || !name) { set_error("null argument"); return FMMB_ERR_INVALID; }
   if (!std::strcmp(name, "overlap_p2p")) { plan->overlap_p2p = value != 0; return FMMB_OK; }
   if (!std::strcmp(name, "m2l_mode")) { plan->opts.m2l_mode = (int32_t)value; return FMMB_OK; }
+  if (!std::strcmp(name, "use_graph")) { plan->use_graph = value != 0; return FMMB_OK; }
   set_error(std::string("unknown option: ") + name);
   return FMMB_ERR_INVALID;
 }

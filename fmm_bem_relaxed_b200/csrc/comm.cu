@@ -49,4 +49,48 @@ void allgather_results(fmmb_plan* plan, cudaStream_t s) {
   FMMB_NCCL(ncclGroupEnd());
 }
 
+namespace {
+__global__ void pack_boxes(const int* __restrict__ list, int count, int xs, const double* __restrict__ M,
+                           double* __restrict__ out) {
+  int i = blockIdx.x;
+  if (i >= count) return;
+  const double* src = M + (size_t)list[i] * xs;
+  for (int k = threadIdx.x; k < xs; k += blockDim.x) out[(size_t)i * xs + k] = src[k];
+}
+__global__ void unpack_boxes(const int* __restrict__ list, const int* __restrict__ off, int nranks, int me, int chunk,
+                             int xs, const double* __restrict__ in, double* __restrict__ M) {
+  // blockIdx.y = owner rank, blockIdx.x = box slot inside the owner's chunk
+  int q = blockIdx.y, i = blockIdx.x;
+  if (q == me || i >= off[q + 1] - off[q]) return;
+  const double* src = in + ((size_t)q * chunk + i) * xs;
+  double* dst = M + (size_t)list[off[q] + i] * xs;
+  for (int k = threadIdx.x; k < xs; k += blockDim.x) dst[k] = src[k];
+}
+}  // namespace
+
+// Owned upward pass: every rank holds the multipoles of the boxes inside its range; one padded
+// ncclAllGather makes them all visible everywhere.
+void exchange_multipoles(fmmb_plan* plan, cudaStream_t s) {
+  Tree& T = plan->tree;
+  ncclComm_t c = (ncclComm_t)plan->comm;
+  const int P = plan->p, xs = (P * P + 1) & ~1;
+  const size_t chunk = (size_t)T.xchg_max * xs;
+  plan->xchg_off_dev.resize(T.nranks + 1);
+  if (!plan->xchg_off_ready) {
+    FMMB_CUDA(cudaMemcpyAsync(plan->xchg_off_dev.p, T.xchg_off.data(), (T.nranks + 1) * sizeof(int),
+                              cudaMemcpyHostToDevice, s));
+    plan->xchg_off_ready = true;
+  }
+  T.xchg_send.resize(chunk);
+  T.xchg_recv.resize(chunk * T.nranks);
+  const int mine = T.xchg_off[T.rank + 1] - T.xchg_off[T.rank];
+  if (mine) pack_boxes<<<mine, 64, 0, s>>>(T.xchg_list.p + T.xchg_off[T.rank], mine, xs, plan->M.p, T.xchg_send.p);
+  FMMB_NCCL(ncclAllGather(T.xchg_send.p, T.xchg_recv.p, chunk, ncclDouble, c, s));
+  dim3 grid(T.xchg_max, T.nranks);
+  unpack_boxes<<<grid, 64, 0, s>>>(T.xchg_list.p, plan->xchg_off_dev.p, T.nranks, T.rank, T.xchg_max, xs,
+                                  T.xchg_recv.p, plan->M.p);
+  FMMB_CUDA(cudaGetLastError());
+  plan->launches += 2;
+}
+
 }  // namespace fmmb

@@ -105,7 +105,17 @@ struct Tree {
   DevBuf<int> own_leaves;            // leaf boxes inside the owned range, ascending
   int n_own_leaves = 0;
   DevBuf<unsigned char> active;      // box intersects the owned range (is a target on this rank)
+  // owned upward pass (used once a communicator exists): a box is "inside" a rank when all its bodies
+  // belong to that rank; boxes that straddle a cut are recomputed by every rank after the exchange
+  DevBuf<unsigned char> up_inside;   // inside MY range
+  std::vector<DevBuf<int>*> strad_parents;   // per level: non-leaf straddling boxes
+  std::vector<int> strad_count;
+  DevBuf<int> xchg_list;             // boxes inside rank q, concatenated rank-major
+  std::vector<int> xchg_off;         // nranks + 1 offsets into xchg_list
+  int xchg_max = 0;                  // largest per-rank box count (all-gather chunk)
+  DevBuf<double> xchg_send, xchg_recv;
   int64_t n_lr_local = 0;            // M2L pairs whose target is active here (= n_lr on one GPU)
+  ~Tree() { for (auto* p : strad_parents) delete p; }
   DevBuf<unsigned char> has_local;   // box carries a local expansion (M2L target or descendant of one)
   // M2L: reference-order pair list and target-major CSR (sources in list order per target)
   DevBuf<int2> lr;                   // (source, target) in LR_list order
@@ -163,6 +173,7 @@ struct fmmb_plan {
   fmmb::Tree tree;
   fmmb::LaplaceTables tab;
   fmmb::TransBatch cls, m2m, l2l;    // batched M2L / M2M / L2L
+  fmmb::TransBatch m2m_own;          // multi-GPU: M2M restricted to parents inside this rank's range
   std::map<int, fmmb::DevBuf<double>*> m2l_coeff;  // per-order real M2L coefficient tables
   fmmb::DevBuf<double> M, L;         // box-major, real layout (laplace_ops.cuh), stride xstride(p)
   fmmb::DevBuf<double> charges;      // original order staging
@@ -171,11 +182,27 @@ struct fmmb_plan {
   fmmb::BemData* bem = nullptr;      // LaplaceSphericalBEM plans only
   int charge_dim = 1, result_dim = 4;
   void* comm = nullptr;              // ncclComm_t once fmmb_plan_comm_init ran
+  fmmb::DevBuf<int> xchg_off_dev;
+  bool xchg_off_ready = false;
   fmmb::DevBuf<double> results;      // original order staging, 4n
   double phase_ms[FMMB_T_COUNT] = {0};
   bool timed = false;
   bool m2l_gemm_timed = false;
+  bool graph_timed = false;
   bool overlap_p2p = true;
+  // CUDA graphs: one captured matvec per (order, charge pointer, result pointer)
+  bool use_graph = true;
+  bool capturing = false;
+  struct GraphKey {
+    int p; const void* q; void* r;
+    bool operator<(const GraphKey& o) const {
+      if (p != o.p) return p < o.p;
+      if (q != o.q) return q < o.q;
+      return r < o.r;
+    }
+  };
+  std::map<GraphKey, cudaGraphExec_t> graphs;
+  std::map<GraphKey, int> graph_seen;
   int launches = 0;                  // kernel launches of the last execute
 };
 
@@ -187,6 +214,7 @@ void comm_unique_id(unsigned char* id);
 void comm_init(fmmb_plan* plan, const unsigned char* id);
 void comm_destroy(fmmb_plan* plan);
 void allgather_results(fmmb_plan* plan, cudaStream_t s);
+void exchange_multipoles(fmmb_plan* plan, cudaStream_t s);
 // laplace.cu
 void laplace_init_tables(fmmb_plan* plan);
 void laplace_execute(fmmb_plan* plan, const double* d_charges, double* d_results);
@@ -205,6 +233,6 @@ void measure_fp64_peak(double* dfma, double* dmma);
 void m2l_init_tables();
 void build_m2l_classes(fmmb_plan* plan);
 bool m2l_batched(fmmb_plan* plan, cudaStream_t s);
-bool m2m_batched(fmmb_plan* plan, cudaStream_t s);
+bool m2m_batched(fmmb_plan* plan, cudaStream_t s, bool owned_only = false);
 bool l2l_batched(fmmb_plan* plan, cudaStream_t s);
 }  // namespace fmmb

@@ -86,11 +86,11 @@ p2m_kernel(const int* __restrict__ leaves, int nleaves, const unsigned* __restri
 
 // ---- M2M: block per parent box of one level; children accumulate in index order ----------------
 __global__ void __launch_bounds__(64)
-m2m_kernel(int lo, int hi, const unsigned* __restrict__ key, const unsigned* __restrict__ cbegin,
-           const unsigned* __restrict__ cend, const double4* __restrict__ center, int P,
-           double* __restrict__ M) {
-  int b = lo + blockIdx.x;
-  if (b >= hi || (key[b] >> 31)) return;   // leaves got their multipole from P2M
+m2m_kernel(int lo, int hi, const int* __restrict__ box_list, const unsigned* __restrict__ key,
+           const unsigned* __restrict__ cbegin, const unsigned* __restrict__ cend,
+           const double4* __restrict__ center, int P, double* __restrict__ M) {
+  int b = box_list ? box_list[blockIdx.x] : lo + blockIdx.x;
+  if ((!box_list && b >= hi) || (key[b] >> 31)) return;   // leaves got their multipole from P2M
   extern __shared__ double2 sh[];
   const int nc = P * (P + 1) / 2, pp = P * P;
   double2* Y = sh;          // pp
@@ -476,13 +476,25 @@ void laplace_translations(fmmb_plan* plan, cudaStream_t s) {
   const double* C = m2l_coeffs(plan, P);
   cudaEvent_t* ev = plan->ev;
   size_t sh_mm = (size_t)(pp + nc) * sizeof(double2);
-  const bool up_batched = m2m_batched(plan, s);
+  const bool owned_up = T.nranks > 1 && plan->comm && P <= 8 && plan->opts.m2l_mode != 1 && plan->m2m_own.n_items > 0;
+  if (owned_up) {
+    // multi-GPU: M2M inside the owned subtrees, exchange, then the few boxes that straddle a cut
+    m2m_batched(plan, s, /*owned_only=*/true);
+    exchange_multipoles(plan, s);
+    for (int l = T.nlevels - 2; l >= 0; --l)
+      if (T.strad_count[l]) {
+        m2m_kernel<<<T.strad_count[l], 64, sh_mm, s>>>(0, 0, T.strad_parents[l]->p, T.key.p, T.cbegin.p, T.cend.p,
+                                                      T.center.p, P, plan->M.p);
+        ++plan->launches;
+      }
+  }
+  const bool up_batched = owned_up || m2m_batched(plan, s);
   for (int l = T.nlevels - 2; l >= 0 && !up_batched; --l) {
     int lo = T.level_off[l], hi = T.level_off[l + 1];
-    m2m_kernel<<<hi - lo, 64, sh_mm, s>>>(lo, hi, T.key.p, T.cbegin.p, T.cend.p, T.center.p, P, plan->M.p);
+    m2m_kernel<<<hi - lo, 64, sh_mm, s>>>(lo, hi, nullptr, T.key.p, T.cbegin.p, T.cend.p, T.center.p, P, plan->M.p);
     ++plan->launches;
   }
-  FMMB_CUDA(cudaEventRecord(ev[2], s));
+  if (!plan->capturing) FMMB_CUDA(cudaEventRecord(ev[2], s));
 
   // far field translations: batched translation classes, then the per-pair kernel for the rest
   {
@@ -503,7 +515,7 @@ void laplace_translations(fmmb_plan* plan, cudaStream_t s) {
       ++plan->launches;
     }
   }
-  FMMB_CUDA(cudaEventRecord(ev[3], s));
+  if (!plan->capturing) FMMB_CUDA(cudaEventRecord(ev[3], s));
 
   // downward sweep
   const bool down_batched = l2l_batched(plan, s);
@@ -540,14 +552,14 @@ void laplace_execute(fmmb_plan* plan, const double* d_charges, double* d_results
   cudaEvent_t* ev = plan->ev;
   plan->launches = 0;
 
-  FMMB_CUDA(cudaEventRecord(ev[0], s));
+  if (!plan->capturing) FMMB_CUDA(cudaEventRecord(ev[0], s));
   gather_charges<<<nblk(n, 256), 256, 0, s>>>(d_charges, T.perm.p, n, T.body.p);
   ++plan->launches;
   FMMB_CUDA(cudaEventRecord(ev[1], s));
 
   // near field on the second stream: needs only the charges
   if (s2 != s) FMMB_CUDA(cudaStreamWaitEvent(s2, ev[1], 0));
-  FMMB_CUDA(cudaEventRecord(ev[6], s2));
+  if (!plan->capturing) FMMB_CUDA(cudaEventRecord(ev[6], s2));
   p2p_kernel<<<nblk(T.n_p2p_items, kP2PWarps), 32 * kP2PWarps, 0, s2>>>(T.p2p_items.p, T.n_p2p_items, T.bbegin.p,
                                                                        T.bend.p, T.p2p_off.p, T.p2p_src.p,
                                                                        T.body.p, plan->res_near.p);
@@ -555,7 +567,7 @@ void laplace_execute(fmmb_plan* plan, const double* d_charges, double* d_results
   FMMB_CUDA(cudaEventRecord(ev[7], s2));
 
   // upward sweep
-  FMMB_CUDA(cudaEventRecord(ev[12], s));
+  if (!plan->capturing) FMMB_CUDA(cudaEventRecord(ev[12], s));
   const int p2m_warps = pp <= 64 ? 4 : 1;          // shared tile: warps x 32 bodies x P^2 doubles
   const size_t p2m_sh = (size_t)p2m_warps * 32 * (pp | 1) * sizeof(double);
   static bool p2m_attr = false;
@@ -563,8 +575,11 @@ void laplace_execute(fmmb_plan* plan, const double* d_charges, double* d_results
     FMMB_CUDA(cudaFuncSetAttribute(p2m_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024));
     p2m_attr = true;
   }
-  p2m_kernel<<<nblk(T.nleaves, p2m_warps), 32 * p2m_warps, p2m_sh, s>>>(
-      T.leaves.p, T.nleaves, T.bbegin.p, T.bend.p,
+  const bool p2m_owned = T.nranks > 1 && plan->comm && P <= 8 && plan->opts.m2l_mode != 1 && plan->m2m_own.n_items > 0;
+  const int* p2m_list = p2m_owned ? T.own_leaves.p : T.leaves.p;
+  const int p2m_n = p2m_owned ? T.n_own_leaves : T.nleaves;
+  p2m_kernel<<<nblk(p2m_n, p2m_warps), 32 * p2m_warps, p2m_sh, s>>>(
+      p2m_list, p2m_n, T.bbegin.p, T.bend.p,
                                                                T.center.p, T.body.p, P, plan->M.p);
                        ++plan->launches;
   laplace_translations(plan, s);
@@ -572,7 +587,7 @@ void laplace_execute(fmmb_plan* plan, const double* d_charges, double* d_results
                                                                      T.center.p, T.has_local.p, T.body.p, P,
                                                                      plan->L.p, plan->res_far.p);
                              ++plan->launches;
-  FMMB_CUDA(cudaEventRecord(ev[4], s));
+  if (!plan->capturing) FMMB_CUDA(cudaEventRecord(ev[4], s));
 
   if (s2 != s) FMMB_CUDA(cudaStreamWaitEvent(s, ev[7], 0));
   if (T.nranks > 1 && plan->comm) {
@@ -590,7 +605,7 @@ void laplace_execute(fmmb_plan* plan, const double* d_charges, double* d_results
                                                                   reinterpret_cast<double4*>(d_results));
   }
       ++plan->launches;
-  FMMB_CUDA(cudaEventRecord(ev[5], s));
+  if (!plan->capturing) FMMB_CUDA(cudaEventRecord(ev[5], s));
   FMMB_CUDA(cudaGetLastError());
   plan->timed = true;
 }

@@ -394,10 +394,10 @@ m2l_reduce_kernel(int nboxes, const int* __restrict__ off, const unsigned char* 
 // ---- phase 2 (M2M): M[parent] = sum over its children's columns, in child order ---------------------
 __global__ void __launch_bounds__(64)
 m2m_reduce_kernel(int lo, int hi, const unsigned* __restrict__ key, const unsigned* __restrict__ cbegin,
-                  const unsigned* __restrict__ cend, int P, const double* __restrict__ tmp,
-                  double* __restrict__ M) {
+                  const unsigned* __restrict__ cend, const unsigned char* __restrict__ mask, int P,
+                  const double* __restrict__ tmp, double* __restrict__ M) {
   int b = lo + blockIdx.x;
-  if (b >= hi || (key[b] >> 31)) return;
+  if (b >= hi || (key[b] >> 31) || (mask && !mask[b])) return;
   const int pp = P * P, xs = xstride(P);
   unsigned c0 = cbegin[b], c1 = cend[b];
   for (int row = threadIdx.x; row < pp; row += blockDim.x) {
@@ -577,6 +577,23 @@ void build_m2l_classes(fmmb_plan* plan) {
     C.slot_src_p = T.m2l_src.p;
     classify(plan, C, C.slot_tgt.p, T.m2l_src.p, 0, nullptr, T.n_lr_local, kMinPopM2L, false);
   }
+  if (nb > 1 && T.nranks > 1) {
+    // M2M restricted to parents whose bodies all belong to this rank (owned upward pass)
+    TransBatch& B = plan->m2m_own;
+    B.kind = 1; B.n_items = 0; B.built_p = 0;
+    B.slot_tgt.resize(nb); B.slot_src.resize(nb);
+    parent_child_pairs<<<nblk(nb, 256), 256, 0, s>>>(T.parent.p, nb, 0, B.slot_tgt.p, B.slot_src.p);
+    B.slot_src_p = B.slot_src.p;
+    std::vector<unsigned char> ins = T.up_inside.to_host(s);
+    std::vector<unsigned> par = T.parent.to_host(s);
+    std::vector<int> list;
+    for (int c = 1; c < nb; ++c) if (ins[par[c]]) list.push_back(c);
+    DevBuf<int> dl;
+    dl.from_host(list.data(), list.size(), s);
+    if (!list.empty()) classify(plan, B, B.slot_tgt.p, B.slot_src.p, 0, dl.p, (int64_t)list.size(), 1, true);
+    else B.level_item_off.assign(T.nlevels + 1, 0);
+    B.n_pairs = (int64_t)list.size();
+  }
   if (nb > 1) {
     for (int kind = 1; kind <= 2; ++kind) {
       TransBatch& B = kind == 1 ? plan->m2m : plan->l2l;
@@ -609,9 +626,9 @@ bool m2l_batched(fmmb_plan* plan, cudaStream_t s) {
   if (C.n_items == 0 || P > 8) return false;
   ensure_T(plan, C, s);
   C.tmp.resize((size_t)T.n_lr_local * xs);
-  FMMB_CUDA(cudaEventRecord(plan->ev[13], s));
+  if (!plan->capturing) FMMB_CUDA(cudaEventRecord(plan->ev[13], s));
   launch_gemm<false>(C, P, 0, C.n_items, plan->M.p, C.tmp.p, nullptr, s);
-  FMMB_CUDA(cudaEventRecord(plan->ev[14], s));
+  if (!plan->capturing) FMMB_CUDA(cudaEventRecord(plan->ev[14], s));
   plan->m2l_gemm_timed = true;
   ++plan->launches;
   int threads = pp < 64 ? 64 : (pp > 256 ? 256 : pp);
@@ -623,8 +640,8 @@ bool m2l_batched(fmmb_plan* plan, cudaStream_t s) {
 }
 
 // Batched M2M level sweep (finest parents first).  False -> caller uses the per-box kernels.
-bool m2m_batched(fmmb_plan* plan, cudaStream_t s) {
-  TransBatch& B = plan->m2m;
+bool m2m_batched(fmmb_plan* plan, cudaStream_t s, bool owned_only) {
+  TransBatch& B = owned_only ? plan->m2m_own : plan->m2m;
   Tree& T = plan->tree;
   const int P = plan->p, xs = xstride(P);
   if (B.n_items == 0 || P > 8 || plan->opts.m2l_mode == 1) return false;
@@ -636,7 +653,7 @@ bool m2m_batched(fmmb_plan* plan, cudaStream_t s) {
     launch_gemm<false>(B, P, i0, i1 - i0, plan->M.p, B.tmp.p, nullptr, s);
     int lo = T.level_off[l], hi = T.level_off[l + 1];
     m2m_reduce_kernel<<<hi - lo, 64, 0, s>>>(
-        lo, hi, T.key.p, T.cbegin.p, T.cend.p, P, B.tmp.p, plan->M.p);
+        lo, hi, T.key.p, T.cbegin.p, T.cend.p, owned_only ? T.up_inside.p : nullptr, P, B.tmp.p, plan->M.p);
     plan->launches += 2;
   }
   FMMB_CUDA(cudaGetLastError());

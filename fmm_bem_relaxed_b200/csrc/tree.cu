@@ -443,6 +443,38 @@ static void partition_tree(fmmb_plan* plan) {
     if (act[b]) nsrc.insert(nsrc.end(), m2l_src.begin() + m2l_off[b], m2l_src.begin() + m2l_off[b + 1]);
     noff[b + 1] = (int)nsrc.size();
   }
+  // upward-pass ownership
+  {
+    std::vector<unsigned char> inside_me(nb, 0);
+    std::vector<int> owner(nb, -1);        // rank whose range contains the whole box, -1 = straddles a cut
+    for (int b = 0; b < nb; ++b) {
+      int q = (int)(std::upper_bound(T.body_cuts.begin(), T.body_cuts.end(), (int64_t)bb[b]) - T.body_cuts.begin()) - 1;
+      if (q >= 0 && q < T.nranks && (int64_t)be[b] <= T.body_cuts[q + 1]) owner[b] = q;
+      inside_me[b] = owner[b] == T.rank;
+    }
+    T.up_inside.from_host(inside_me.data(), inside_me.size(), s);
+    std::vector<unsigned> key = T.key.to_host(s);
+    for (auto* p : T.strad_parents) delete p;
+    T.strad_parents.assign(T.nlevels, nullptr);
+    T.strad_count.assign(T.nlevels, 0);
+    for (int l = 0; l < T.nlevels; ++l) {
+      std::vector<int> list;
+      for (int b = T.level_off[l]; b < T.level_off[l + 1]; ++b)
+        if (owner[b] < 0 && !(key[b] >> 31)) list.push_back(b);
+      T.strad_count[l] = (int)list.size();
+      T.strad_parents[l] = new DevBuf<int>();
+      T.strad_parents[l]->from_host(list.data(), list.size(), s);
+    }
+    std::vector<int> xl;
+    T.xchg_off.assign(T.nranks + 1, 0);
+    T.xchg_max = 0;
+    for (int q = 0; q < T.nranks; ++q) {
+      for (int b = 0; b < nb; ++b) if (owner[b] == q) xl.push_back(b);
+      T.xchg_off[q + 1] = (int)xl.size();
+      T.xchg_max = std::max(T.xchg_max, T.xchg_off[q + 1] - T.xchg_off[q]);
+    }
+    T.xchg_list.from_host(xl.data(), xl.size(), s);
+  }
   T.active.from_host(act.data(), act.size(), s);
   T.m2l_off.from_host(noff.data(), noff.size(), s);
   T.m2l_src.from_host(nsrc.data(), nsrc.size(), s);

@@ -150,6 +150,8 @@ int fmmb_plan_direct(fmmb_plan* plan, const double* charges_host, int64_t nt,
  *   "overlap_p2p"  1 = near field runs on a second stream concurrently with the far field (default),
  *                  0 = every kernel on one stream, so per-kernel CUDA-event times are undisturbed
  *                      (used by bench.py for the roofline figures).
+ *   "use_graph"    1 = from the second identical call on, a matvec is replayed as one CUDA graph (default);
+ *                  per-kernel phase times are then unavailable (only FMMB_T_TOTAL).  0 = plain launches.
  *   "m2l_mode"     see fmmb_options.m2l_mode. */
 int fmmb_plan_set_option(fmmb_plan* plan, const char* name, int64_t value);
 
