@@ -16,6 +16,7 @@ the C++ mirror lives in fmm_bem_relaxed_b200/hostcxx/):
 All computation happens in libfmmb200.so (CUDA, sm_100a) through the C ABI of include/fmmb.h.
 """
 import ctypes
+import weakref
 
 import numpy as np
 
@@ -92,8 +93,9 @@ class LaplaceSpherical:
 
     def set_p(self, p):
         self.P = int(p)
-        if self._plan is not None:
-            capi.check(capi.load().fmmb_plan_set_p(self._plan._h, self.P))
+        plan = self._plan() if self._plan is not None else None     # weak reference: no plan <-> kernel cycle,
+        if plan is not None and plan._h is not None:                 # so a plan is destroyed when it is dropped
+            capi.check(capi.load().fmmb_plan_set_p(plan._h, self.P))
 
 
 class LaplaceSphericalBEM(LaplaceSpherical):
@@ -158,7 +160,7 @@ class FMM_plan:
         capi.check(lib.fmmb_plan_create(ctypes.byref(kd), ctypes.byref(src), ctypes.byref(op), ctypes.byref(h)))
         self._h = h
         self._lib = lib
-        self.K._plan = self
+        self.K._plan = weakref.ref(self)
 
     def __del__(self):
         self.close()

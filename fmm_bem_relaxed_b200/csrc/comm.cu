@@ -4,6 +4,7 @@
 #include "common.cuh"
 #include <nccl.h>
 #include <cstring>
+#include <algorithm>
 
 namespace fmmb {
 
@@ -37,16 +38,35 @@ void comm_destroy(fmmb_plan* plan) {
   plan->comm = nullptr;
 }
 
+// Result slices differ in length (ranges are balanced by work): one ncclAllGather of chunks padded to the
+// longest slice into a staging buffer, then every slice is copied to its place in tree order.
+__global__ void place_slices(const double4* __restrict__ stage, const long long* __restrict__ cuts, int nranks,
+                             long long chunk, double4* __restrict__ tree) {
+  const int q = blockIdx.y;
+  const long long b0 = cuts[q], len = cuts[q + 1] - b0;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < len; i += (long long)gridDim.x * blockDim.x)
+    tree[b0 + i] = stage[(size_t)q * chunk + i];
+}
+
 void allgather_results(fmmb_plan* plan, cudaStream_t s) {
   Tree& T = plan->tree;
   ncclComm_t c = (ncclComm_t)plan->comm;
-  double* base = reinterpret_cast<double*>(plan->res_tree.p);
-  FMMB_NCCL(ncclGroupStart());
-  for (int q = 0; q < T.nranks; ++q) {
-    int64_t b0 = T.body_cuts[q], b1 = T.body_cuts[q + 1];
-    if (b1 > b0) FMMB_NCCL(ncclBroadcast(base + 4 * b0, base + 4 * b0, (size_t)(4 * (b1 - b0)), ncclDouble, q, c, s));
+  long long chunk = 0;
+  for (int q = 0; q < T.nranks; ++q) chunk = std::max<long long>(chunk, T.body_cuts[q + 1] - T.body_cuts[q]);
+  plan->res_stage.resize((size_t)chunk * T.nranks);
+  if (!plan->cuts_ready) {
+    std::vector<long long> h(T.body_cuts.begin(), T.body_cuts.end());
+    plan->cuts_dev.resize(h.size());
+    FMMB_CUDA(cudaMemcpyAsync(plan->cuts_dev.p, h.data(), h.size() * sizeof(long long), cudaMemcpyHostToDevice, s));
+    FMMB_CUDA(cudaStreamSynchronize(s));
+    plan->cuts_ready = true;
   }
-  FMMB_NCCL(ncclGroupEnd());
+  // send buffer = my slice inside res_tree (reads past the slice end stay inside res_tree or the pad)
+  const double* send = reinterpret_cast<const double*>(plan->res_tree.p + T.own_b0);
+  FMMB_NCCL(ncclAllGather(send, plan->res_stage.p, (size_t)chunk * 4, ncclDouble, c, s));
+  dim3 grid(64, T.nranks);
+  place_slices<<<grid, 256, 0, s>>>(plan->res_stage.p, plan->cuts_dev.p, T.nranks, chunk, plan->res_tree.p);
+  FMMB_CUDA(cudaGetLastError());
 }
 
 namespace {

@@ -108,14 +108,16 @@ struct Tree {
   // owned upward pass (used once a communicator exists): a box is "inside" a rank when all its bodies
   // belong to that rank; boxes that straddle a cut are recomputed by every rank after the exchange
   DevBuf<unsigned char> up_inside;   // inside MY range
-  std::vector<DevBuf<int>*> strad_parents;   // per level: non-leaf straddling boxes
-  std::vector<int> strad_count;
+  // straddling (non-leaf) boxes and, for each, its maximal descendants that lie inside one rank:
+  // M[straddler] = sum of direct (multi-level) M2M translations of those descendants
+  DevBuf<int> strad_box, strad_off, strad_desc, strad_pair_box;
+  int n_strad = 0, n_strad_pairs = 0;
+  DevBuf<double> strad_tmp;
   DevBuf<int> xchg_list;             // boxes inside rank q, concatenated rank-major
   std::vector<int> xchg_off;         // nranks + 1 offsets into xchg_list
   int xchg_max = 0;                  // largest per-rank box count (all-gather chunk)
   DevBuf<double> xchg_send, xchg_recv;
   int64_t n_lr_local = 0;            // M2L pairs whose target is active here (= n_lr on one GPU)
-  ~Tree() { for (auto* p : strad_parents) delete p; }
   DevBuf<unsigned char> has_local;   // box carries a local expansion (M2L target or descendant of one)
   // M2L: reference-order pair list and target-major CSR (sources in list order per target)
   DevBuf<int2> lr;                   // (source, target) in LR_list order
@@ -183,6 +185,9 @@ struct fmmb_plan {
   int charge_dim = 1, result_dim = 4;
   void* comm = nullptr;              // ncclComm_t once fmmb_plan_comm_init ran
   fmmb::DevBuf<int> xchg_off_dev;
+  fmmb::DevBuf<double4> res_stage;   // padded all-gather staging for the result slices
+  fmmb::DevBuf<long long> cuts_dev;
+  bool cuts_ready = false;
   bool xchg_off_ready = false;
   fmmb::DevBuf<double> results;      // original order staging, 4n
   double phase_ms[FMMB_T_COUNT] = {0};

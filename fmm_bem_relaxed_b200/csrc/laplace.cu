@@ -18,6 +18,7 @@
 #include "common.cuh"
 #include "laplace_ops.cuh"
 #include <cmath>
+#include <algorithm>
 
 namespace fmmb {
 
@@ -115,6 +116,47 @@ m2m_kernel(int lo, int hi, const int* __restrict__ box_list, const unsigned* __r
       double2 v = m2m_entry(Ms, Y, j, k);
       add_coef(M + (size_t)b * xs, j, k, v);
     }
+  }
+}
+
+// ---- multi-GPU: multipoles of the boxes that straddle a partition cut ------------------------------
+// One block per (straddling box, descendant) pair: direct M2M over any number of levels (M2M composes
+// exactly), written to a scratch column; a second kernel sums the columns of a box in list order.
+__global__ void __launch_bounds__(64)
+m2m_direct_kernel(const int* __restrict__ pair_box, const int* __restrict__ strad_box,
+                  const int* __restrict__ desc, const double4* __restrict__ center, int P,
+                  const double* __restrict__ M, double* __restrict__ tmp) {
+  extern __shared__ double2 sh[];
+  const int nc = P * (P + 1) / 2, pp = P * P, xs = xstride(P);
+  double2* Y = sh;
+  double2* Ms = sh + pp;
+  const int e = blockIdx.x;
+  const int b = strad_box[pair_box[e]], d = desc[e];
+  const double4 cb = center[b], cd = center[d];
+  const Sph s = to_sph(cb.x - cd.x, cb.y - cd.y, cb.z - cd.z);
+  for (int m = threadIdx.x; m < P; m += blockDim.x) harmonics_column<false>(m, P, s, -1.0, Y);
+  for (int i = threadIdx.x; i < nc; i += blockDim.x) {
+    int n, m;
+    unpack_nm(i, n, m);
+    Ms[i] = load_coef(M + (size_t)d * xs, n, m);
+  }
+  __syncthreads();
+  double* out = tmp + (size_t)e * xs;
+  for (int jks = threadIdx.x; jks < nc; jks += blockDim.x) {
+    int j, k;
+    unpack_nm(jks, j, k);
+    store_coef(out, j, k, m2m_entry(Ms, Y, j, k));
+  }
+}
+__global__ void __launch_bounds__(64)
+strad_reduce_kernel(const int* __restrict__ strad_box, const int* __restrict__ off, int P,
+                    const double* __restrict__ tmp, double* __restrict__ M) {
+  const int i = blockIdx.x, pp = P * P, xs = xstride(P);
+  const int b = strad_box[i];
+  for (int r = threadIdx.x; r < pp; r += blockDim.x) {
+    double sum = 0;
+    for (int e = off[i]; e < off[i + 1]; ++e) sum += tmp[(size_t)e * xs + r];
+    M[(size_t)b * xs + r] = sum;
   }
 }
 
@@ -481,12 +523,13 @@ void laplace_translations(fmmb_plan* plan, cudaStream_t s) {
     // multi-GPU: M2M inside the owned subtrees, exchange, then the few boxes that straddle a cut
     m2m_batched(plan, s, /*owned_only=*/true);
     exchange_multipoles(plan, s);
-    for (int l = T.nlevels - 2; l >= 0; --l)
-      if (T.strad_count[l]) {
-        m2m_kernel<<<T.strad_count[l], 64, sh_mm, s>>>(0, 0, T.strad_parents[l]->p, T.key.p, T.cbegin.p, T.cend.p,
-                                                      T.center.p, P, plan->M.p);
-        ++plan->launches;
-      }
+    if (T.n_strad_pairs) {
+      T.strad_tmp.resize((size_t)T.n_strad_pairs * xstride(P));
+      m2m_direct_kernel<<<T.n_strad_pairs, 64, sh_mm, s>>>(T.strad_pair_box.p, T.strad_box.p, T.strad_desc.p, T.center.p,
+                                                          P, plan->M.p, T.strad_tmp.p);
+      strad_reduce_kernel<<<T.n_strad, 64, 0, s>>>(T.strad_box.p, T.strad_off.p, P, T.strad_tmp.p, plan->M.p);
+      plan->launches += 2;
+    }
   }
   const bool up_batched = owned_up || m2m_batched(plan, s);
   for (int l = T.nlevels - 2; l >= 0 && !up_batched; --l) {
@@ -592,7 +635,12 @@ void laplace_execute(fmmb_plan* plan, const double* d_charges, double* d_results
   if (s2 != s) FMMB_CUDA(cudaStreamWaitEvent(s, ev[7], 0));
   if (T.nranks > 1 && plan->comm) {
     // the one exchange step: all-gather the per-rank result slices (tree order), then un-permute
-    plan->res_tree.resize(n);
+    {
+      // + pad: the padded all-gather reads a full chunk starting at the owned slice
+      long long chunk = 0;
+      for (int q = 0; q < T.nranks; ++q) chunk = std::max<long long>(chunk, T.body_cuts[q + 1] - T.body_cuts[q]);
+      plan->res_tree.resize((size_t)n + (size_t)chunk);
+    }
     if (T.own_b1 > T.own_b0)
       combine_results<<<nblk(T.own_b1 - T.own_b0, 256), 256, 0, s>>>(plan->res_near.p, plan->res_far.p, T.own_b0,
                                                                     T.own_b1, plan->res_tree.p);

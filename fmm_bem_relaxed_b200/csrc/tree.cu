@@ -408,7 +408,8 @@ static void partition_tree(fmmb_plan* plan) {
   if (T.rank < 0 || T.rank >= T.nranks) throw StatusError{FMMB_ERR_INVALID, "rank must be in [0, nranks)"};
   std::vector<int> leaves = T.leaves.to_host(s), m2l_off = T.m2l_off.to_host(s), m2l_src = T.m2l_src.to_host(s),
                    p2p_off = T.p2p_off.to_host(s), p2p_src = T.p2p_src.to_host(s);
-  std::vector<unsigned> bb = T.bbegin.to_host(s), be = T.bend.to_host(s), par = T.parent.to_host(s);
+  std::vector<unsigned> bb = T.bbegin.to_host(s), be = T.bend.to_host(s), par = T.parent.to_host(s),
+                        hcb = T.cbegin.to_host(s), hce = T.cend.to_host(s);
   // work estimate per box: M2L pairs into it, inherited from the ancestors in proportion to the bodies
   // (one M2L pair costs about as much as 230 P2P body pairs at P = 8 on a B200)
   std::vector<double> far(nb, 0.0);
@@ -454,17 +455,31 @@ static void partition_tree(fmmb_plan* plan) {
     }
     T.up_inside.from_host(inside_me.data(), inside_me.size(), s);
     std::vector<unsigned> key = T.key.to_host(s);
-    for (auto* p : T.strad_parents) delete p;
-    T.strad_parents.assign(T.nlevels, nullptr);
-    T.strad_count.assign(T.nlevels, 0);
-    for (int l = 0; l < T.nlevels; ++l) {
-      std::vector<int> list;
-      for (int b = T.level_off[l]; b < T.level_off[l + 1]; ++b)
-        if (owner[b] < 0 && !(key[b] >> 31)) list.push_back(b);
-      T.strad_count[l] = (int)list.size();
-      T.strad_parents[l] = new DevBuf<int>();
-      T.strad_parents[l]->from_host(list.data(), list.size(), s);
+    // straddlers and their maximal single-rank descendants (children of straddlers that are not straddlers)
+    std::vector<int> sb, soff(1, 0), sdesc, spair;
+    for (int b = 0; b < nb; ++b) {
+      if (owner[b] >= 0 || (key[b] >> 31)) continue;
+      // descendants of b form contiguous index ranges per level; walk down through straddling children only
+      std::vector<int> stack(1, b);
+      while (!stack.empty()) {
+        int x = stack.back();
+        stack.pop_back();
+        std::vector<unsigned> cb1 = {}, ce1 = {};
+        (void)cb1; (void)ce1;
+        for (unsigned c = hcb[x]; c < hce[x]; ++c) {
+          if (owner[c] >= 0) { sdesc.push_back((int)c); spair.push_back((int)sb.size()); }
+          else stack.push_back((int)c);
+        }
+      }
+      sb.push_back(b);
+      soff.push_back((int)sdesc.size());
     }
+    T.n_strad = (int)sb.size();
+    T.n_strad_pairs = (int)sdesc.size();
+    T.strad_box.from_host(sb.data(), sb.size(), s);
+    T.strad_off.from_host(soff.data(), soff.size(), s);
+    T.strad_desc.from_host(sdesc.data(), sdesc.size(), s);
+    T.strad_pair_box.from_host(spair.data(), spair.size(), s);
     std::vector<int> xl;
     T.xchg_off.assign(T.nranks + 1, 0);
     T.xchg_max = 0;

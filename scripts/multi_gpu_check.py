@@ -1,0 +1,47 @@
+"""Run under torchrun on N GPUs: the sharded matvec (NCCL all-gather of results, owned upward pass with
+multipole exchange) must agree with the single-GPU plan on every rank.  Prints one line per rank."""
+import os, sys, faulthandler
+faulthandler.dump_traceback_later(int(os.environ.get('CHECK_TIMEOUT', '240')), exit=True)
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
+import numpy as np
+import torch
+import torch.distributed as dist
+import oracle_lib as O
+import fmm_bem_relaxed_b200 as F
+
+rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(local)
+dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+ok = True
+for n, P in ((200000, 8), (60000, 5), (30000, 7)):
+    if n == 30000:
+        rng = np.random.default_rng(7)
+        pts = rng.random((n, 3)); pts[n // 2:] = 0.3 + 0.05 * rng.random((n - n // 2, 3)); q = rng.random(n) - 0.3
+    else:
+        pts, q = O.drand48_inputs(n)
+    print("rank %d: config N=%d P=%d" % (rank, n, P), flush=True)
+    single = F.FMMOptions(); single.device = local
+    ref = F.FMM_plan(F.LaplaceSpherical(P), pts, single).execute(q)
+    opts = F.FMMOptions(); opts.device = local; opts.rank, opts.nranks = rank, world
+    plan = F.FMM_plan(F.LaplaceSpherical(P), pts, opts)
+    idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
+    if rank == 0:
+        idt.copy_(torch.frombuffer(bytearray(F.comm_unique_id()), dtype=torch.uint8))
+    dist.broadcast(idt, 0)
+    plan.comm_init(bytes(idt.cpu().numpy().tobytes()))
+    print("rank %d: comm ready" % rank, flush=True)
+    for rep in range(3):            # third call replays the captured CUDA graph
+        res = plan.execute(q)
+        print("rank %d: execute %d done" % (rank, rep), flush=True)
+        err = O.rel_l2(res, ref)
+        ok &= err < 1e-12
+    i = plan.info()
+    own = (i.own_body_begin, i.own_body_end)
+    plan.close()          # teardown (ncclCommDestroy) at the same point on every rank
+    print("rank %d/%d N=%d P=%d own [%d,%d) rel-L2 vs single GPU %.2e" % (rank, world, n, P, own[0], own[1], err), flush=True)
+dist.barrier()
+if rank == 0:
+    print("MULTI_GPU_CHECK", "OK" if ok else "FAILED")
+dist.destroy_process_group()
+sys.exit(0 if ok else 1)
