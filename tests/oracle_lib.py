@@ -47,6 +47,8 @@ def load():
         L.fmmo_get_expansions.argtypes = [vp, vp, vp]
         L.fmmo_laplace_direct.argtypes = [ctypes.c_int, vp, vp, ctypes.c_int, vp, vp, ctypes.c_int]
         L.fmmo_drand48_inputs.argtypes = [ctypes.c_int, vp, vp]
+        L.fmmo_stokes_execute.argtypes = [vp, ctypes.c_int, ctypes.c_int, vp, vp, ctypes.c_int]
+        L.fmmo_stokes_direct.argtypes = [ctypes.c_int, vp, ctypes.c_int, vp, ctypes.c_int, vp, vp, ctypes.c_int]
         L.fmmo_unit_sphere.argtypes = [ctypes.c_int, vp]
         L.fmmo_panel_centers.argtypes = [ctypes.c_int, vp, vp]
         L.fmmo_bem_execute.argtypes = [vp, ctypes.c_int, ctypes.c_int, vp, vp, vp, vp, ctypes.c_int]
@@ -116,6 +118,16 @@ class Oracle:
         self.P = P
         return res
 
+    def stokes_execute(self, charges, P, stresslet, threads=None):
+        """StokesSpherical matvec: charges (n, 3) Stokeslet or (n, 6) stresslet (g, n); results (n, 3)."""
+        cd = 6 if stresslet else 3
+        q = np.ascontiguousarray(np.asarray(charges, dtype=np.float64).reshape(-1, cd))
+        res = np.zeros((self.n, 3))
+        rc = self.L.fmmo_stokes_execute(self.h, P, int(bool(stresslet)), _p(q), _p(res), threads or os.cpu_count() or 1)
+        if rc != 0:
+            raise RuntimeError("oracle stokes execute failed: %d" % rc)
+        return res
+
     def expansions(self):
         nc = self.P * (self.P + 1) // 2
         M = np.zeros((self.nboxes, nc, 2))
@@ -172,6 +184,16 @@ def direct(spts, q, tpts, threads=None):
     out = np.zeros((tpts.shape[0], 4))
     load().fmmo_laplace_direct(spts.shape[0], _p(spts), _p(q), tpts.shape[0], _p(tpts), _p(out),
                                threads or os.cpu_count() or 1)
+    return out
+
+
+def stokes_direct(spts, q, tpts, stresslet, threads=None):
+    spts = np.ascontiguousarray(np.asarray(spts, dtype=np.float64).reshape(-1, 3))
+    tpts = np.ascontiguousarray(np.asarray(tpts, dtype=np.float64).reshape(-1, 3))
+    q = np.ascontiguousarray(np.asarray(q, dtype=np.float64).reshape(spts.shape[0], -1))
+    out = np.zeros((tpts.shape[0], 3))
+    load().fmmo_stokes_direct(spts.shape[0], _p(spts), int(bool(stresslet)), _p(q), tpts.shape[0], _p(tpts), _p(out),
+                              threads or os.cpu_count() or 1)
     return out
 
 
