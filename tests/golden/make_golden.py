@@ -65,6 +65,27 @@ def case(name, n, p, ncrit, theta, points=None, charges=None):
         print(name, meta["boxes"], "boxes", meta["lr_pairs"], "M2L pairs")
 
 
+def stokes_case(name, stresslet, n, p, ncrit, theta, points=None, charges=None, direct=300):
+    """StokesSpherical through oracle/_ref/ref_stokeslet (unmodified reference) or ref_stresslet (the
+    reference with the two compile patches of SURVEY.md section 8(c)); stores inputs, results, checksums."""
+    exe = os.path.join(ROOT, "oracle", "_ref", "ref_stresslet" if stresslet else "ref_stokeslet")
+    with tempfile.TemporaryDirectory() as tmp:
+        cmd = [exe, "-N", str(n), "-P", str(p), "-ncrit", str(ncrit), "-theta", repr(theta), "-direct", str(direct)]
+        if points is not None:
+            infile = os.path.join(tmp, "in.f64")
+            np.concatenate([points.ravel(), charges.ravel()]).tofile(infile)
+            cmd += ["-in", infile]
+        pre = os.path.join(tmp, "d")
+        cmd += ["-dump", pre]
+        out = subprocess.check_output(cmd, env=dict(os.environ, OMP_NUM_THREADS="1")).decode()
+        meta = json.loads([l for l in out.splitlines() if l.startswith("REF_JSON")][0][len("REF_JSON "):])
+        cd = 6 if stresslet else 3
+        inp = np.fromfile(pre + ".input.f64")
+        np.savez_compressed(os.path.join(HERE, name + ".npz"), meta=json.dumps(meta), points=inp[:3 * n].reshape(n, 3),
+                            charges=inp[3 * n:].reshape(n, cd), results=np.fromfile(pre + ".results.f64").reshape(n, 3))
+        print(name, meta["sum"], "err vs direct", meta["err_vs_direct"])
+
+
 def main():
     if not os.path.exists(REF):
         sys.exit("oracle/_ref/ref_laplace missing: run `make -C oracle ref` in the build container")
@@ -77,6 +98,14 @@ def main():
     pts[n // 2:] = 0.3 + 0.04 * rng.random((n - n // 2, 3))
     q = rng.random(n) - 0.4
     case("laplace_two_scale_n4000_p6", n, 6, 12, 0.6, pts, q)
+    # 2b. StokesSpherical: Stokeslet (unmodified reference) and stresslet (patched reference)
+    stokes_case("stokeslet_drand48_n3000_p5", False, 3000, 5, 32, 0.5)
+    stokes_case("stresslet_drand48_n3000_p6", True, 3000, 6, 32, 0.5)
+    g = rng.random((n, 3)) - 0.5
+    nr = rng.normal(size=(n, 3))
+    nr /= np.linalg.norm(nr, axis=1)[:, None]
+    stokes_case("stresslet_two_scale_n4000_p7", True, n, 7, 12, 0.6, pts, np.hstack([g, nr]))
+    stokes_case("stokeslet_two_scale_n4000_p4", False, n, 4, 12, 0.6, pts, g)
     # 3. checksums only, larger sizes
     sums = {}
     for key, (nn, pp) in {"n10000_p5": (10000, 5), "c1_n100000_p5": (100000, 5)}.items():

@@ -4,11 +4,13 @@ Golden fixtures come from the unmodified reference compiled into oracle/_ref
 (tests/golden/make_golden.py); checksums are the known-answer values of SURVEY.md 8(c).
 """
 import json
+import os
 
 import numpy as np
 import pytest
 
 import oracle_lib as O
+from conftest import GOLDEN
 
 TREE_KEYS = ("perm", "codes", "boxes", "geom", "lr", "p2p_off", "p2p_idx")
 
@@ -139,3 +141,24 @@ def test_edge_cases():
     cl = np.full((100, 3), 0.5) + 1e-9 * np.arange(300).reshape(100, 3)
     cl = np.vstack([cl, [[0, 0, 0], [1, 1, 1]]])
     assert O.Oracle(cl, 8, 0.5).error == -3
+
+
+# ---- StokesSpherical restatement pinned to the reference (oracle/_ref/ref_stokeslet: unmodified;
+# ---- ref_stresslet: the two compile patches of SURVEY.md section 8(c)) ------------------------------
+@pytest.mark.parametrize("name,stresslet,P,ncrit,theta", [
+    ("stokeslet_drand48_n3000_p5", False, 5, 32, 0.5),
+    ("stresslet_drand48_n3000_p6", True, 6, 32, 0.5),
+    ("stresslet_two_scale_n4000_p7", True, 7, 12, 0.6),
+    ("stokeslet_two_scale_n4000_p4", False, 4, 12, 0.6),
+])
+def test_stokes_restatement_matches_reference(name, stresslet, P, ncrit, theta):
+    g = dict(np.load(os.path.join(GOLDEN, name + ".npz")))
+    orc = O.Oracle(g["points"], ncrit, theta)
+    res = orc.stokes_execute(g["charges"], P, stresslet, threads=1)
+    # same operations in the same order as the reference: bit-identical, not merely close
+    assert np.array_equal(res, g["results"])
+    # the multi-threaded oracle (parallel over target boxes only) gives the same bits
+    assert np.array_equal(orc.stokes_execute(g["charges"], P, stresslet, threads=4), g["results"])
+    meta = json.loads(str(g["meta"]))
+    d = O.stokes_direct(g["points"], g["charges"], g["points"][:300], stresslet)
+    assert abs(O.rel_l2(res[:300], d) - meta["err_vs_direct"]) < 1e-6 * max(1.0, meta["err_vs_direct"] / 1e-4)
