@@ -23,7 +23,7 @@ import numpy as np
 from . import capi
 from .capi import FmmbError
 
-__all__ = ["FMMOptions", "LaplaceSpherical", "LaplaceSphericalBEM", "Panels", "FMM_plan", "Direct", "FmmbError", "capi", "comm_unique_id",
+__all__ = ["FMMOptions", "LaplaceSpherical", "LaplaceSphericalBEM", "StokesSpherical", "Panels", "FMM_plan", "Direct", "FmmbError", "capi", "comm_unique_id",
            "partition_ranges", "get_options"]
 
 
@@ -110,6 +110,20 @@ class LaplaceSphericalBEM(LaplaceSpherical):
         self.K = int(k)
 
 
+class StokesSpherical(LaplaceSpherical):
+    """Mirror of reference kernel/StokesSpherical.hpp:11-45.  The reference selects the flavour at compile
+    time (-DSTRESSLET, Makefile target serialrun_stresslet); here it is a constructor flag:
+    stresslet=False: charge (f0, f1, f2), the Stokeslet;  stresslet=True: charge (g0, g1, g2, n0, n1, n2).
+    Results are velocities (n, 3)."""
+    result_dim = 3
+
+    def __init__(self, p=5, stresslet=False):
+        super().__init__(p)
+        self.stresslet = bool(stresslet)
+        self.kind = capi.STOKES_SPHERICAL_STRESSLET if self.stresslet else capi.STOKES_SPHERICAL
+        self.charge_dim = 6 if self.stresslet else 3
+
+
 class Panels:
     """A set of triangular panels (the std::vector<Panel> a reference driver builds)."""
     POTENTIAL, NORMAL_DERIV = 0, 1
@@ -149,10 +163,13 @@ class FMM_plan:
             kd = capi.KernelDesc(kernel.kind, kernel.P, 0.0, kernel.K, 0)
         else:
             pts = np.ascontiguousarray(np.asarray(sources, dtype=np.float64).reshape(-1, 3))
-            self.K = LaplaceSpherical(kernel.P)      # the plan owns a COPY of the kernel (FMM_plan.hpp:37)
+            # the plan owns a COPY of the kernel (FMM_plan.hpp:37)
+            self.K = StokesSpherical(kernel.P, kernel.stresslet) if isinstance(kernel, StokesSpherical) \
+                else LaplaceSpherical(kernel.P)
             kd = capi.KernelDesc(kernel.kind, kernel.P, 0.0, 0, 0)
         self._n = pts.shape[0]
         self._rdim = self.K.result_dim
+        self._cdim = self.K.charge_dim
         src = capi.Sources(self._n, capi.ptr(pts), capi.ptr(verts), capi.ptr(bc))
         op = capi.Options(opts.theta, opts.NCRIT_, opts.evaluator, opts.device, 0,
                           getattr(opts, "rank", 0), getattr(opts, "nranks", 1), 0)
@@ -180,9 +197,9 @@ class FMM_plan:
     def execute(self, charges):
         """results = A * charges; (n, 4) array: potential, fx, fy, fz in the caller's order."""
         q = np.ascontiguousarray(np.asarray(charges, dtype=np.float64).reshape(-1))
-        if q.shape[0] != self._n:
+        if q.shape[0] != self._n * self._cdim:
             raise ValueError("charges.size() != sources.size()")
-        out = np.empty((self._n, 4) if self._rdim == 4 else (self._n,), dtype=np.float64)
+        out = np.empty((self._n, self._rdim) if self._rdim > 1 else (self._n,), dtype=np.float64)
         capi.check(self._lib.fmmb_plan_execute(self._h, capi.ptr(q), capi.ptr(out)))
         return out
 
@@ -262,6 +279,6 @@ class Direct:
     def matvec(plan, charges, targets):
         q = np.ascontiguousarray(np.asarray(charges, dtype=np.float64).reshape(-1))
         t = np.ascontiguousarray(np.asarray(targets, dtype=np.float64).reshape(-1, 3))
-        out = np.empty((t.shape[0], 4))
+        out = np.empty((t.shape[0], plan._rdim))
         capi.check(plan._lib.fmmb_plan_direct(plan._h, capi.ptr(q), t.shape[0], capi.ptr(t), capi.ptr(out)))
         return out

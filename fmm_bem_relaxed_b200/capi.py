@@ -16,6 +16,8 @@ FMMB_MAX_P = 16
 T_TOTAL, T_UPWARD, T_M2L, T_DOWNWARD, T_P2P, T_H2D, T_D2H, T_LAUNCHES, T_M2L_GEMM, T_COUNT = 0, 1, 2, 3, 4, 5, 6, 7, 8, 10
 LAPLACE_SPHERICAL = 0
 LAPLACE_SPHERICAL_BEM = 1
+STOKES_SPHERICAL_STRESSLET = 2
+STOKES_SPHERICAL = 5
 
 
 class FmmbError(RuntimeError):

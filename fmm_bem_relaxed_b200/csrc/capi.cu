@@ -65,8 +65,10 @@ int fmmb_plan_create(const fmmb_kernel_desc* kernel, const fmmb_sources* sources
                      fmmb_plan** out_plan) {
   if (!kernel || !sources || !out_plan) { set_error("null argument"); return FMMB_ERR_INVALID; }
   *out_plan = nullptr;
-  if (kernel->kind != FMMB_LAPLACE_SPHERICAL && kernel->kind != FMMB_LAPLACE_SPHERICAL_BEM) {
-    set_error("only FMMB_LAPLACE_SPHERICAL and FMMB_LAPLACE_SPHERICAL_BEM are built in this version");
+  const bool is_stokes = kernel->kind == FMMB_STOKES_SPHERICAL || kernel->kind == FMMB_STOKES_SPHERICAL_STRESSLET;
+  if (kernel->kind != FMMB_LAPLACE_SPHERICAL && kernel->kind != FMMB_LAPLACE_SPHERICAL_BEM && !is_stokes) {
+    set_error("built kernel kinds: FMMB_LAPLACE_SPHERICAL, FMMB_LAPLACE_SPHERICAL_BEM, FMMB_STOKES_SPHERICAL, "
+              "FMMB_STOKES_SPHERICAL_STRESSLET");
     return FMMB_ERR_UNSUPPORTED;
   }
   const bool is_bem = kernel->kind == FMMB_LAPLACE_SPHERICAL_BEM;
@@ -101,8 +103,8 @@ int fmmb_plan_create(const fmmb_kernel_desc* kernel, const fmmb_sources* sources
     FMMB_CUDA(cudaStreamCreateWithFlags(&plan->stream, cudaStreamNonBlocking));
     FMMB_CUDA(cudaStreamCreateWithFlags(&plan->stream2, cudaStreamNonBlocking));
     for (auto& e : plan->ev) FMMB_CUDA(cudaEventCreate(&e));
-    plan->charge_dim = 1;
-    plan->result_dim = is_bem ? 1 : 4;
+    plan->charge_dim = is_stokes ? (kernel->kind == FMMB_STOKES_SPHERICAL_STRESSLET ? 6 : 3) : 1;
+    plan->result_dim = is_bem ? 1 : (is_stokes ? 3 : 4);
     laplace_init_tables(plan);
     std::vector<double> centres;
     const double* pts = sources->points;
@@ -118,8 +120,10 @@ int fmmb_plan_create(const fmmb_kernel_desc* kernel, const fmmb_sources* sources
     }
     build_tree(plan, pts, sources->n);
     build_m2l_classes(plan);
+    if (is_bem) plan->p2p_item_mode = 0;   // one cached near-field block per chunk of <= 32 targets
     build_p2p_items(plan);
     if (is_bem) bem_setup(plan, sources->vertices, sources->bc, kernel->quad_k);
+    if (is_stokes) stokes_setup(plan, kernel->kind == FMMB_STOKES_SPHERICAL_STRESSLET);
   });
   if (rc != FMMB_OK) { fmmb_plan_destroy(plan); return rc; }
   *out_plan = plan;
@@ -134,6 +138,7 @@ void fmmb_plan_destroy(fmmb_plan* plan) {
   for (auto& kv : plan->graphs) cudaGraphExecDestroy(kv.second);
   comm_destroy(plan);
   bem_free(plan->bem);
+  stokes_free(plan->stokes);
   for (auto& kv : plan->m2l_coeff) delete kv.second;
   for (auto& e : plan->ev) if (e) cudaEventDestroy(e);
   if (plan->stream) cudaStreamDestroy(plan->stream);
@@ -155,6 +160,7 @@ namespace fmmb {
 static void run_matvec(fmmb_plan* plan, const double* q, double* r) {
   auto direct = [&] {
     if (plan->bem) bem_execute(plan, q, r);
+    else if (plan->stokes) stokes_execute(plan, q, r);
     else laplace_execute(plan, q, r);
   };
   if (!plan->use_graph || !plan->overlap_p2p) { direct(); return; }
@@ -205,11 +211,12 @@ int fmmb_plan_execute(fmmb_plan* plan, const double* charges_host, double* resul
     const int64_t n = plan->tree.n;
     cudaStream_t s = plan->stream;
     const size_t rd = plan->result_dim;
-    plan->charges.resize(n);
+    const size_t cd = plan->charge_dim;
+    plan->charges.resize(cd * (size_t)n);
     plan->results.resize(rd * (size_t)n);
     if (plan->tree.nranks > 1 && !plan->comm) plan->results.zero(s);   // only the owned slice gets written
     FMMB_CUDA(cudaEventRecord(plan->ev[8], s));
-    FMMB_CUDA(cudaMemcpyAsync(plan->charges.p, charges_host, n * sizeof(double), cudaMemcpyHostToDevice, s));
+    FMMB_CUDA(cudaMemcpyAsync(plan->charges.p, charges_host, cd * (size_t)n * sizeof(double), cudaMemcpyHostToDevice, s));
     FMMB_CUDA(cudaEventRecord(plan->ev[9], s));
     run_matvec(plan, plan->charges.p, plan->results.p);
     FMMB_CUDA(cudaEventRecord(plan->ev[10], s));
@@ -232,11 +239,14 @@ int fmmb_plan_direct(fmmb_plan* plan, const double* charges_host, int64_t nt, co
     FMMB_CUDA(cudaSetDevice(plan->device));
     cudaStream_t s = plan->stream;
     DevBuf<double> q, t, out;
-    q.from_host(charges_host, plan->tree.n, s);
+    const size_t rd = plan->result_dim;
+    q.from_host(charges_host, (size_t)plan->charge_dim * plan->tree.n, s);
     t.from_host(targets_host, 3 * (size_t)nt, s);
-    out.resize(4 * (size_t)nt);
-    if (nt) laplace_direct_raw(plan->tree.pts_orig.p, q.p, plan->tree.n, t.p, nt, out.p, s);
-    if (nt) FMMB_CUDA(cudaMemcpyAsync(results_host, out.p, 4 * (size_t)nt * sizeof(double), cudaMemcpyDeviceToHost, s));
+    out.resize(rd * (size_t)nt);
+    if (nt && plan->stokes)
+      stokes_direct_raw(stokes_is_stresslet(plan->stokes), plan->tree.pts_orig.p, q.p, plan->tree.n, t.p, nt, out.p, s);
+    else if (nt) laplace_direct_raw(plan->tree.pts_orig.p, q.p, plan->tree.n, t.p, nt, out.p, s);
+    if (nt) FMMB_CUDA(cudaMemcpyAsync(results_host, out.p, rd * (size_t)nt * sizeof(double), cudaMemcpyDeviceToHost, s));
     FMMB_CUDA(cudaStreamSynchronize(s));
   });
 }
@@ -246,6 +256,38 @@ int fmmb_plan_set_option(fmmb_plan* plan, const char* name, int64_t value) {
   if (!std::strcmp(name, "overlap_p2p")) { plan->overlap_p2p = value != 0; return FMMB_OK; }
   if (!std::strcmp(name, "m2l_mode")) { plan->opts.m2l_mode = (int32_t)value; return FMMB_OK; }
   if (!std::strcmp(name, "use_graph")) { plan->use_graph = value != 0; return FMMB_OK; }
+  if (!std::strcmp(name, "p2p_kernel") || !std::strcmp(name, "p2p_unroll")) {
+    const bool kern = !std::strcmp(name, "p2p_kernel");
+    if (kern ? (value != 0 && value != 1) : (value != 4 && value != 8)) {
+      set_error("p2p_kernel: 0 or 1; p2p_unroll: 4 or 8");
+      return FMMB_ERR_INVALID;
+    }
+    return guarded([&] {
+      FMMB_CUDA(cudaSetDevice(plan->device));
+      FMMB_CUDA(cudaStreamSynchronize(plan->stream));
+      for (auto& kv : plan->graphs) cudaGraphExecDestroy(kv.second);
+      plan->graphs.clear();
+      plan->graph_seen.clear();
+      if (kern) plan->p2p_kernel = (int)value; else plan->p2p_unroll = (int)value;
+    });
+  }
+  if (!std::strcmp(name, "p2p_warps") || !std::strcmp(name, "p2p_items")) {
+    const bool items = !std::strcmp(name, "p2p_items");
+    if (items && plan->bem) { set_error("BEM plans keep one near-field block per chunk"); return FMMB_ERR_UNSUPPORTED; }
+    if (items ? (value != 0 && value != 1) : (value != 1 && value != 2 && value != 4)) {
+      set_error("p2p_items: 0 or 1; p2p_warps: 1, 2 or 4");
+      return FMMB_ERR_INVALID;
+    }
+    return guarded([&] {
+      FMMB_CUDA(cudaSetDevice(plan->device));
+      FMMB_CUDA(cudaStreamSynchronize(plan->stream));
+      for (auto& kv : plan->graphs) cudaGraphExecDestroy(kv.second);   // captured launches are stale
+      plan->graphs.clear();
+      plan->graph_seen.clear();
+      if (items) { plan->p2p_item_mode = (int)value; build_p2p_items(plan); }
+      else plan->p2p_warps = (int)value;
+    });
+  }
   set_error(std::string("unknown option: ") + name);
   return FMMB_ERR_INVALID;
 }

@@ -128,6 +128,9 @@ struct Tree {
   int64_t n_p2p = 0, n_p2p_body_pairs = 0;
   DevBuf<int4> p2p_items;            // (target leaf, first target body, #targets <= 32, 0), leaf order
   int n_p2p_items = 0;
+  DevBuf<int> p2p_run_off;           // per target box: its merged source body runs (laplace.cu: p2p_run_kernel)
+  DevBuf<int2> p2p_runs;             // [begin, end) in tree-ordered bodies
+  int n_p2p_runs = 0;
 };
 
 // One family of box-to-box translations (M2L, M2M or L2L) evaluated as class-batched GEMMs
@@ -155,6 +158,7 @@ struct TransBatch {
 };
 
 struct BemData;
+struct StokesData;
 
 struct LaplaceTables {
   int pmax = 0;
@@ -182,6 +186,7 @@ struct fmmb_plan {
   fmmb::DevBuf<double4> res_near, res_far;  // tree order
   fmmb::DevBuf<double4> res_tree;    // multi-GPU: near + far in tree order, all-gathered over NCCL
   fmmb::BemData* bem = nullptr;      // LaplaceSphericalBEM plans only
+  fmmb::StokesData* stokes = nullptr;  // StokesSpherical plans only
   int charge_dim = 1, result_dim = 4;
   void* comm = nullptr;              // ncclComm_t once fmmb_plan_comm_init ran
   fmmb::DevBuf<int> xchg_off_dev;
@@ -195,6 +200,10 @@ struct fmmb_plan {
   bool m2l_gemm_timed = false;
   bool graph_timed = false;
   bool overlap_p2p = true;
+  int p2p_item_mode = 0;             // see p2p_fill_items (laplace.cu); BEM plans use 0
+  int p2p_warps = 1;                 // warps per block of the near-field pair kernels
+  int p2p_kernel = 0;                // 1 = merged source runs with prefetch (p2p_run_kernel), 0 = per source leaf
+  int p2p_unroll = 4;
   // CUDA graphs: one captured matvec per (order, charge pointer, result pointer)
   bool use_graph = true;
   bool capturing = false;
@@ -234,6 +243,13 @@ int64_t bem_nnz(const BemData* b);
 void laplace_direct_raw(const double* d_spts, const double* d_q, int64_t ns, const double* d_tpts, int64_t nt,
                         double* d_out, cudaStream_t s);
 void measure_fp64_peak(double* dfma, double* dmma);
+// stokes.cu
+void stokes_setup(fmmb_plan* plan, bool stresslet);
+void stokes_execute(fmmb_plan* plan, const double* d_charges, double* d_results);
+void stokes_free(StokesData* d);
+bool stokes_is_stresslet(const StokesData* d);
+void stokes_direct_raw(bool stresslet, const double* d_spts, const double* d_q, int64_t ns, const double* d_tpts,
+                       int64_t nt, double* d_out, cudaStream_t s);
 // m2l_classes.cu
 void m2l_init_tables();
 void build_m2l_classes(fmmb_plan* plan);

@@ -17,6 +17,7 @@
 // exp(i m phi) from (x+iy)/|xy| by recurrence; sums run in a different order.
 #include "common.cuh"
 #include "laplace_ops.cuh"
+#include <cub/cub.cuh>
 #include <cmath>
 #include <algorithm>
 
@@ -333,7 +334,9 @@ __device__ __forceinline__ void p2p_accumulate(const double4 t, const double4 sq
   asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y0) : "d"(r2));
   double e = fma(-(r2 * y0), y0, 1.0);
   double inv = fma(y0 * e, fma(0.375, e, 0.5), y0);
-  if (r2 < 1e-8) inv = 0.0;                        // LaplaceSpherical.hpp:158
+  // LaplaceSpherical.hpp:158, R2 < 1e-8 -> 0.  r2 >= 0, so the ordering of the doubles is the ordering of their
+  // bit patterns: the compare runs on the integer pipe and leaves the FP64 pipe to the arithmetic.
+  if (__double_as_longlong(r2) < __double_as_longlong(1e-8)) inv = 0.0;
   double qi = sq.w * inv;
   double qi3 = qi * (inv * inv);
   pot += qi;
@@ -341,30 +344,50 @@ __device__ __forceinline__ void p2p_accumulate(const double4 t, const double4 sq
 }
 
 // work items: x = target box, y = first target body, z = number of targets (<= 32)
+// mode 0: chunks of 32 and one remainder chunk (BEM: one cached block per chunk).
+// mode 1: chunks of 32, then the remainder in power-of-two pieces: a piece of r = 2^k targets is replicated
+//         32/r times across the lanes (source splitting), so every lane of every warp does useful pairs.
 __global__ void p2p_count_items(const int* __restrict__ leaves, int nleaves, const unsigned* __restrict__ bb,
-                                const unsigned* __restrict__ be, int* __restrict__ cnt) {
+                                const unsigned* __restrict__ be, int mode, int* __restrict__ cnt) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i > nleaves) return;
-  cnt[i] = i < nleaves ? (int)((be[leaves[i]] - bb[leaves[i]] + 31) / 32) : 0;
+  int c = i < nleaves ? (int)(be[leaves[i]] - bb[leaves[i]]) : 0;
+  cnt[i] = mode ? c / 32 + __popc(c % 32) : (c + 31) / 32;
 }
 __global__ void p2p_fill_items(const int* __restrict__ leaves, int nleaves, const unsigned* __restrict__ bb,
                                const unsigned* __restrict__ be, const int* __restrict__ off,
-                               int4* __restrict__ items) {
+                               const int* __restrict__ p2p_off, const int* __restrict__ p2p_src, int mode,
+                               int4* __restrict__ items, unsigned* __restrict__ work) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= nleaves) return;
   int b = leaves[i];
   unsigned t0 = bb[b], t1 = be[b];
   int o = off[i];
-  for (unsigned t = t0; t < t1; t += 32) items[o++] = make_int4(b, (int)t, (int)min(32u, t1 - t), 0);
+  unsigned ns = 0;                       // source bodies of this leaf's list = sequential pair steps of a full chunk
+  for (int e = p2p_off[b]; e < p2p_off[b + 1]; ++e) ns += be[p2p_src[e]] - bb[p2p_src[e]];
+  unsigned t = t0;
+  for (; t + 32 <= t1 || (!mode && t < t1); t += 32) {
+    int r = (int)min(32u, t1 - t);
+    work[o] = ns;
+    items[o++] = make_int4(b, (int)t, r, 0);
+  }
+  if (mode)
+    for (int r = 16; r >= 1; r >>= 1)
+      if ((t1 - t) & r) {
+        work[o] = (ns * r + 31) / 32;
+        items[o++] = make_int4(b, (int)t, r, 0);
+        t += r;
+      }
 }
 
-__global__ void __launch_bounds__(32 * kP2PWarps)
+template <int WARPS>
+__global__ void __launch_bounds__(32 * WARPS)
 p2p_kernel(const int4* __restrict__ items, int nitems, const unsigned* __restrict__ bb,
            const unsigned* __restrict__ be, const int* __restrict__ off, const int* __restrict__ src,
            const double4* __restrict__ body, double4* __restrict__ res) {
-  __shared__ double4 tiles[kP2PWarps][32];
+  __shared__ double4 tiles[WARPS][32];
   const int wl = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int item = blockIdx.x * kP2PWarps + wl;
+  const int item = blockIdx.x * WARPS + wl;
   if (item >= nitems) return;
   double4* tile = tiles[wl];
   const int4 it = items[item];
@@ -395,6 +418,115 @@ p2p_kernel(const int4* __restrict__ items, int nitems, const unsigned* __restric
   }
   if (S > 1) {
     // lanes ti, ti + r, ti + 2r, ... hold partial sums of the same target
+    for (int q = 1; q < S; ++q) {
+      int from = lane + q * r;
+      double a = __shfl_sync(0xffffffffu, pot, from & 31), bx = __shfl_sync(0xffffffffu, fx, from & 31),
+             by = __shfl_sync(0xffffffffu, fy, from & 31), bz = __shfl_sync(0xffffffffu, fz, from & 31);
+      if (lane < r) { pot += a; fx += bx; fy += by; fz += bz; }
+    }
+  }
+  if (lane < r) res[it.y + lane] = make_double4(pot, fx, fy, fz);
+}
+
+// ---- P2P over merged source runs --------------------------------------------------------------------
+// Plan time: the source leaves of a target leaf are sorted by body index and adjacent body ranges are merged
+// into runs (Morton neighbours are contiguous in the tree-ordered body array: ~27 leaves become ~10 runs).
+// The kernel walks the runs as ONE virtual source stream: every tile holds exactly 32 sources (only the last
+// one is padded, with zero-charge dummies far outside the domain, which contribute exactly 0), the pair loop
+// has a fixed trip count (fully unrolled in groups, no remainder path), and the next tile is fetched into
+// registers while the current one is being used.
+__global__ void run_keys_kernel(const int* __restrict__ off, const int* __restrict__ src,
+                                const unsigned* __restrict__ bb, int nb, unsigned long long* __restrict__ key,
+                                int* __restrict__ val) {
+  int b = blockIdx.x;
+  if (b >= nb) return;
+  for (int e = off[b] + threadIdx.x; e < off[b + 1]; e += blockDim.x) {
+    key[e] = ((unsigned long long)b << 32) | bb[src[e]];
+    val[e] = src[e];
+  }
+}
+__global__ void run_flags_kernel(const unsigned long long* __restrict__ key, const int* __restrict__ val,
+                                 const unsigned* __restrict__ bb, const unsigned* __restrict__ be, int64_t n,
+                                 int* __restrict__ flag) {
+  int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (e > n) return;
+  if (e == n) { flag[e] = 0; return; }
+  flag[e] = (e == 0 || (key[e] >> 32) != (key[e - 1] >> 32) || bb[val[e]] != be[val[e - 1]]) ? 1 : 0;
+}
+__global__ void run_fill_kernel(const int* __restrict__ val, const unsigned* __restrict__ bb,
+                                const unsigned* __restrict__ be, const int* __restrict__ flag,
+                                const int* __restrict__ pos, int64_t n, int2* __restrict__ runs) {
+  int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (e >= n) return;
+  if (flag[e]) runs[pos[e]].x = (int)bb[val[e]];
+  if (flag[e + 1] || e + 1 == n) runs[pos[e + 1] - 1].y = (int)be[val[e]];
+}
+__global__ void run_offsets_kernel(const int* __restrict__ off, const int* __restrict__ pos, int nb,
+                                   int* __restrict__ run_off) {
+  int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b <= nb) run_off[b] = pos[off[b]];
+}
+
+template <int WARPS, int UNROLL>
+__global__ void __launch_bounds__(32 * WARPS)
+p2p_run_kernel(const int4* __restrict__ items, int nitems, const int* __restrict__ run_off,
+               const int2* __restrict__ runs, const double4* __restrict__ body, double4 dummy,
+               double4* __restrict__ res) {
+  __shared__ double4 tiles[WARPS][32];
+  const int wl = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int item = blockIdx.x * WARPS + wl;
+  if (item >= nitems) return;
+  double4* tile = tiles[wl];
+  const int4 it = items[item];
+  const int r = it.z;                      // targets in this chunk
+  const int S = 32 / r;                    // source splits (1 when r > 16)
+  const int ti = lane % r, sp = lane / r;
+  const bool act = sp < S;
+  const double4 t = body[it.y + ti];
+  double pot = 0, fx = 0, fy = 0, fz = 0;
+  int j = run_off[it.x];
+  const int j1 = run_off[it.x + 1];
+  // cursor over the virtual source stream: current run [p, pend), descriptor of the following run prefetched
+  int p = 0, pend = 0;
+  int2 rnext = make_int2(0, 0);
+  if (j < j1) { const int2 rr = runs[j]; p = rr.x; pend = rr.y; }
+  if (j + 1 < j1) rnext = runs[j + 1];
+  auto fetch = [&]() -> double4 {          // next 32 sources (warp-uniform control flow)
+    double4 v = dummy;
+    int filled = 0;
+    while (filled < 32 && j < j1) {
+      const int take = min(32 - filled, pend - p);
+      const int l = lane - filled;
+      if (l >= 0 && l < take) v = body[p + l];
+      p += take; filled += take;
+      if (p == pend) {
+        ++j;
+        p = rnext.x; pend = rnext.y;
+        if (j + 1 < j1) rnext = runs[j + 1];
+      }
+    }
+    return v;
+  };
+  bool have = j < j1;
+  double4 nxt = dummy;
+  if (have) nxt = fetch();
+  while (have) {
+    __syncwarp();
+    tile[lane] = nxt;
+    __syncwarp();
+    have = j < j1;
+    if (have) nxt = fetch();               // in flight while the current tile is consumed
+    if (act) {
+      if (S == 1) {
+#pragma unroll UNROLL
+        for (int k = 0; k < 32; ++k) p2p_accumulate(t, tile[k], pot, fx, fy, fz);
+      } else {
+#pragma unroll 2
+        for (int k = sp; k < 32; k += S) p2p_accumulate(t, tile[k], pot, fx, fy, fz);
+      }
+    }
+  }
+  if (S > 1) {
     for (int q = 1; q < S; ++q) {
       int from = lane + q * r;
       double a = __shfl_sync(0xffffffffu, pot, from & 31), bx = __shfl_sync(0xffffffffu, fx, from & 31),
@@ -603,10 +735,30 @@ void laplace_execute(fmmb_plan* plan, const double* d_charges, double* d_results
   // near field on the second stream: needs only the charges
   if (s2 != s) FMMB_CUDA(cudaStreamWaitEvent(s2, ev[1], 0));
   if (!plan->capturing) FMMB_CUDA(cudaEventRecord(ev[6], s2));
-  p2p_kernel<<<nblk(T.n_p2p_items, kP2PWarps), 32 * kP2PWarps, 0, s2>>>(T.p2p_items.p, T.n_p2p_items, T.bbegin.p,
-                                                                       T.bend.p, T.p2p_off.p, T.p2p_src.p,
-                                                                       T.body.p, plan->res_near.p);
-       ++plan->launches;
+  const double ext = 1024.0 * std::max(T.cell[0], std::max(T.cell[1], T.cell[2]));
+  const double4 dummy = make_double4(T.pmin[0] - 1000.0 * ext, T.pmin[1] - 1000.0 * ext, T.pmin[2] - 1000.0 * ext, 0.0);
+  const int ni_ = T.n_p2p_items;
+#define FMMB_P2P_RUN(W, U)                                                                                       \
+  p2p_run_kernel<W, U><<<nblk(ni_, W), 32 * W, 0, s2>>>(T.p2p_items.p, ni_, T.p2p_run_off.p, T.p2p_runs.p, T.body.p, \
+                                                        dummy, plan->res_near.p)
+  if (plan->p2p_kernel == 1 && ni_ > 0) {
+    const int w = plan->p2p_warps, u = plan->p2p_unroll;
+    if (w == 1 && u == 4) FMMB_P2P_RUN(1, 4);
+    else if (w == 1) FMMB_P2P_RUN(1, 8);
+    else if (w == 2 && u == 4) FMMB_P2P_RUN(2, 4);
+    else if (w == 2) FMMB_P2P_RUN(2, 8);
+    else if (u == 4) FMMB_P2P_RUN(4, 4);
+    else FMMB_P2P_RUN(4, 8);
+  } else if (plan->p2p_warps == 1)
+    p2p_kernel<1><<<T.n_p2p_items, 32, 0, s2>>>(T.p2p_items.p, T.n_p2p_items, T.bbegin.p, T.bend.p, T.p2p_off.p,
+                                                T.p2p_src.p, T.body.p, plan->res_near.p);
+  else if (plan->p2p_warps == 2)
+    p2p_kernel<2><<<nblk(T.n_p2p_items, 2), 64, 0, s2>>>(T.p2p_items.p, T.n_p2p_items, T.bbegin.p, T.bend.p,
+                                                         T.p2p_off.p, T.p2p_src.p, T.body.p, plan->res_near.p);
+  else
+    p2p_kernel<kP2PWarps><<<nblk(T.n_p2p_items, kP2PWarps), 32 * kP2PWarps, 0, s2>>>(
+        T.p2p_items.p, T.n_p2p_items, T.bbegin.p, T.bend.p, T.p2p_off.p, T.p2p_src.p, T.body.p, plan->res_near.p);
+  ++plan->launches;
   FMMB_CUDA(cudaEventRecord(ev[7], s2));
 
   // upward sweep
@@ -662,10 +814,41 @@ void laplace_execute(fmmb_plan* plan, const double* d_charges, double* d_results
 void build_p2p_items(fmmb_plan* plan) {
   Tree& T = plan->tree;
   cudaStream_t s = plan->stream;
+  if (T.p2p_run_off.n == 0 && T.n_p2p > 0) {
+    // merged source runs per target box (see p2p_run_kernel)
+    const int64_t ne = T.n_p2p;
+    const int nb = T.nboxes;
+    DevBuf<unsigned long long> k0, k1;
+    DevBuf<int> v0, v1, flag, pos;
+    DevBuf<char> tmp;
+    k0.resize(ne); k1.resize(ne); v0.resize(ne); v1.resize(ne); flag.resize(ne + 1); pos.resize(ne + 1);
+    run_keys_kernel<<<nb, 64, 0, s>>>(T.p2p_off.p, T.p2p_src.p, T.bbegin.p, nb, k0.p, v0.p);
+    int bits = 32;
+    while ((1ll << (bits - 32)) < nb) ++bits;
+    size_t bytes = 0;
+    FMMB_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, bytes, k0.p, k1.p, v0.p, v1.p, ne, 0, bits, s));
+    tmp.resize(bytes);
+    FMMB_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, bytes, k0.p, k1.p, v0.p, v1.p, ne, 0, bits, s));
+    run_flags_kernel<<<nblk(ne + 1, 256), 256, 0, s>>>(k1.p, v1.p, T.bbegin.p, T.bend.p, ne, flag.p);
+    FMMB_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, bytes, flag.p, pos.p, ne + 1, s));
+    tmp.resize(bytes);
+    FMMB_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, bytes, flag.p, pos.p, ne + 1, s));
+    int nruns = 0;
+    FMMB_CUDA(cudaMemcpyAsync(&nruns, pos.p + ne, sizeof(int), cudaMemcpyDeviceToHost, s));
+    FMMB_CUDA(cudaStreamSynchronize(s));
+    T.n_p2p_runs = nruns;
+    T.p2p_runs.resize(nruns);
+    T.p2p_run_off.resize(nb + 1);
+    run_fill_kernel<<<nblk(ne, 256), 256, 0, s>>>(v1.p, T.bbegin.p, T.bend.p, flag.p, pos.p, ne, T.p2p_runs.p);
+    run_offsets_kernel<<<nblk(nb + 1, 256), 256, 0, s>>>(T.p2p_off.p, pos.p, nb, T.p2p_run_off.p);
+    FMMB_CUDA(cudaGetLastError());
+    FMMB_CUDA(cudaStreamSynchronize(s));
+  }
   DevBuf<int> cnt;
   const int nl = T.n_own_leaves;
   cnt.resize(nl + 1);
-  p2p_count_items<<<nblk(nl + 1, 256), 256, 0, s>>>(T.own_leaves.p, nl, T.bbegin.p, T.bend.p, cnt.p);
+  const int mode = plan->p2p_item_mode;
+  p2p_count_items<<<nblk(nl + 1, 256), 256, 0, s>>>(T.own_leaves.p, nl, T.bbegin.p, T.bend.p, mode, cnt.p);
   FMMB_CUDA(cudaGetLastError());
   std::vector<int> h = cnt.to_host(s);
   std::vector<int> off(nl + 1, 0);
@@ -673,9 +856,26 @@ void build_p2p_items(fmmb_plan* plan) {
   T.n_p2p_items = off[nl];
   DevBuf<int> doff;
   doff.from_host(off.data(), off.size(), s);
-  T.p2p_items.resize(T.n_p2p_items);
-  if (nl) p2p_fill_items<<<nblk(nl, 256), 256, 0, s>>>(T.own_leaves.p, nl, T.bbegin.p, T.bend.p, doff.p, T.p2p_items.p);
+  const int ni = T.n_p2p_items;
+  DevBuf<int4> unsorted;
+  DevBuf<unsigned> work, work_sorted;
+  unsorted.resize(ni); work.resize(ni); work_sorted.resize(ni);
+  T.p2p_items.resize(ni);
+  int4* fill_to = mode ? unsorted.p : T.p2p_items.p;
+  if (nl) p2p_fill_items<<<nblk(nl, 256), 256, 0, s>>>(T.own_leaves.p, nl, T.bbegin.p, T.bend.p, doff.p, T.p2p_off.p,
+                                                       T.p2p_src.p, mode, fill_to, work.p);
   FMMB_CUDA(cudaGetLastError());
+  if (mode && ni) {
+    // longest items first: the tail of the grid is made of the short pieces (stable: ties keep leaf order)
+    size_t bytes = 0;
+    FMMB_CUDA(cub::DeviceRadixSort::SortPairsDescending(nullptr, bytes, work.p, work_sorted.p, unsorted.p,
+                                                        T.p2p_items.p, ni, 0, 32, s));
+    DevBuf<char> tmp;
+    tmp.resize(bytes);
+    FMMB_CUDA(cub::DeviceRadixSort::SortPairsDescending(tmp.p, bytes, work.p, work_sorted.p, unsorted.p,
+                                                        T.p2p_items.p, ni, 0, 32, s));
+    FMMB_CUDA(cudaStreamSynchronize(s));
+  }
   FMMB_CUDA(cudaStreamSynchronize(s));
 }
 

@@ -47,9 +47,11 @@ typedef enum {
 typedef enum {
   FMMB_LAPLACE_SPHERICAL = 0,          /* kernel/LaplaceSpherical.hpp: charge 1, result 4 */
   FMMB_LAPLACE_SPHERICAL_BEM = 1,      /* kernel/LaplaceSphericalBEM.hpp: panels, charge 1, result 1 */
-  FMMB_STOKES_SPHERICAL_STRESSLET = 2, /* kernel/StokesSpherical.hpp, STRESSLET (not built yet) */
+  FMMB_STOKES_SPHERICAL_STRESSLET = 2, /* kernel/StokesSpherical.hpp built with -DSTRESSLET: charge 6 (g, n),
+                                          result 3 (serialrun_stresslet.cpp) */
   FMMB_YUKAWA_CARTESIAN = 3,           /* kernel/YukawaCartesian.hpp (not built yet) */
-  FMMB_YUKAWA_CARTESIAN_BEM = 4        /* kernel/YukawaCartesianBEM.hpp (not built yet) */
+  FMMB_YUKAWA_CARTESIAN_BEM = 4,       /* kernel/YukawaCartesianBEM.hpp (not built yet) */
+  FMMB_STOKES_SPHERICAL = 5            /* kernel/StokesSpherical.hpp default build (Stokeslet): charge 3 (f), result 3 */
 } fmmb_kernel_kind;
 
 /* Mirrors the kernel constructor arguments: LaplaceSpherical(int p) etc. */
@@ -107,8 +109,8 @@ typedef struct {
   int64_t own_body_begin;  /* multi-GPU: tree-order body range whose results this rank computes */
   int64_t own_body_end;
   int32_t p;               /* current expansion order */
-  int32_t charge_dim;      /* doubles per charge (Laplace 1) */
-  int32_t result_dim;      /* doubles per result (Laplace 4: potential, fx, fy, fz) */
+  int32_t charge_dim;      /* doubles per charge (Laplace 1, Stokeslet 3, stresslet 6) */
+  int32_t result_dim;      /* doubles per result (Laplace 4: potential, fx, fy, fz; BEM 1; Stokes 3) */
   int32_t device;
 } fmmb_plan_info;
 
@@ -142,7 +144,8 @@ int fmmb_plan_execute_device(fmmb_plan* plan, const double* charges_dev, double*
 
 /* Brute force reference sum on the GPU for accuracy checks:
  * Direct::matvec(K, sources, charges, targets, results), reference include/Direct.hpp:273-288.
- * targets: 3*nt doubles (host); results: nt*result_dim doubles (host). */
+ * targets: 3*nt doubles (host); results: nt*result_dim doubles (host).  Point kernels only
+ * (Laplace, Stokeslet, stresslet). */
 int fmmb_plan_direct(fmmb_plan* plan, const double* charges_host, int64_t nt,
                      const double* targets_host, double* results_host);
 
@@ -152,7 +155,13 @@ int fmmb_plan_direct(fmmb_plan* plan, const double* charges_host, int64_t nt,
  *                      (used by bench.py for the roofline figures).
  *   "use_graph"    1 = from the second identical call on, a matvec is replayed as one CUDA graph (default);
  *                  per-kernel phase times are then unavailable (only FMMB_T_TOTAL).  0 = plain launches.
- *   "m2l_mode"     see fmmb_options.m2l_mode. */
+ *   "m2l_mode"     see fmmb_options.m2l_mode.
+ *   "p2p_items"    near-field work decomposition of point kernels: 0 = chunks of <= 32 targets in leaf order
+ *                  (default); 1 = chunks of 32 targets plus power-of-two pieces of the remainder, longest first.
+ *   "p2p_kernel"   0 = one tile per source leaf (default); 1 = merged source runs, fixed 32-source tiles, prefetch.
+ *   "p2p_unroll"   pair-loop unroll of p2p_kernel 1: 4 (default) or 8.
+ *   "p2p_warps"    warps per block of the near-field pair kernel: 1 (default), 2 or 4.
+ *   (measured on B200 at N = 1M: all combinations within 4 %; see profiles/README.md) */
 int fmmb_plan_set_option(fmmb_plan* plan, const char* name, int64_t value);
 
 /* ---- multi-GPU (one process per GPU, single node) ---------------------------------------------
