@@ -144,6 +144,48 @@ def bench_gmres_c2():
     return out
 
 
+def bench_stresslet_c4(device):
+    """BASELINE config 4: StokesSpherical stresslet FMM, N = 200 000, P = 8 (serialrun_stresslet.cpp:98-128 inputs:
+    drand48 points, charges (U, U, U, 1, 0, 0)); GPU matvec time next to the patched reference."""
+    import numpy as np
+    import torch
+    import oracle_lib as O
+    import fmm_bem_relaxed_b200 as F
+    n, P = 200000, 8
+    pts, _ = O.drand48_inputs(n)
+    rng = np.random.default_rng(4)
+    q = np.hstack([rng.random((n, 3)), np.tile([1.0, 0.0, 0.0], (n, 1))])
+    opts = F.FMMOptions()
+    opts.device = device
+    plan = F.FMM_plan(F.StokesSpherical(P, True), pts, opts)
+    d_q = torch.from_numpy(q).cuda()
+    d_r = torch.empty((n, 3), dtype=torch.float64, device="cuda")
+    for _ in range(4):
+        plan.execute_device(d_q.data_ptr(), d_r.data_ptr())
+    plan.sync()
+    t0 = time.perf_counter()
+    reps = 20
+    for _ in range(reps):
+        plan.execute_device(d_q.data_ptr(), d_r.data_ptr())
+    plan.sync()
+    ms = (time.perf_counter() - t0) / reps * 1e3
+    res = d_r.cpu().numpy()
+    m = 300
+    err = O.rel_l2(res[:m], F.Direct.matvec(plan, q, pts[:m]))
+    i = plan.info()
+    out = {"config": "StokesSpherical stresslet FMM, N=200000, P=8, theta=0.5, ncrit=64 (BASELINE config 4)",
+           "ms_per_matvec": ms, "matvec_per_s": 1e3 / ms, "m2l_pairs_x_sets": int(i.n_m2l_pairs) * 4,
+           "p2p_body_pairs": int(i.n_p2p_body_pairs), "rel_l2_vs_direct_first_300": err}
+    exe = os.path.join(ROOT, "oracle", "_ref", "ref_stresslet")
+    if os.path.exists(exe):
+        threads = os.cpu_count() or 1
+        o = subprocess.check_output([exe, "-N", str(n), "-P", str(P)], env=dict(os.environ, OMP_NUM_THREADS=str(threads)))
+        r = json.loads([l for l in o.decode().splitlines() if l.startswith("REF_JSON")][0][len("REF_JSON "):])
+        out["reference"] = {"exec_s": r["exec_s"], "plan_s": r["plan_s"], "cores": threads, "kind": "reference",
+                            "note": "reference with the two compile patches of SURVEY 8(c); drand48 charges"}
+    return out
+
+
 def bench_reference(args, rank, world):
     if rank != 0:
         return
@@ -217,8 +259,21 @@ def bench_ours(args, rank, world, local_rank):
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
     torch.cuda.synchronize()
 
+    # N > 1: the solver-facing sharded call -- every rank feeds the charges of its own bodies and keeps the
+    # results of its own bodies (tree order); the exchanges are NCCL all-gathers of charge slices and multipoles
+    # ("results stay sharded by target").  N = 1: full vectors in the caller's order.
+    sharded = world > 1 and not args.replicated_results
+    if sharded:
+        perm = plan.tree()["perm"].astype(np.int64)
+        b0, b1 = info.own_body_begin, info.own_body_end
+        d_q_own = torch.from_numpy(np.ascontiguousarray(q[perm[b0:b1]])).cuda()
+        d_res_own = torch.empty((b1 - b0, 4), dtype=torch.float64, device="cuda")
+
     def step_device():
-        plan.execute_device(d_q.data_ptr(), d_res.data_ptr())
+        if sharded:
+            plan.execute_sharded(d_q_own.data_ptr(), d_res_own.data_ptr())
+        else:
+            plan.execute_device(d_q.data_ptr(), d_res.data_ptr())
 
     def barrier():
         if dist is not None:
@@ -297,7 +352,7 @@ def bench_ours(args, rank, world, local_rank):
     # rooflines.  Algorithmic work per matvec as defined in SURVEY.md section 8(d):
     #   M2L 7 P^3 (P+1) flop per pair (the reference's complex O(P^4) contraction), P2P 22 flop per body pair.
     # "executed" = flops the sm_100a kernels actually issue: the batched M2L multiplies a real P^2 x P^2
-    # translation matrix (2 P^4 flop per pair); P2P issues 19 FP64 instructions (25 flop) per body pair.
+    # translation matrix (2 P^4 flop per pair); P2P issues 18 FP64 instructions per body pair.
     import ctypes
     P = args.p
     pk_fma, pk_mma = ctypes.c_double(), ctypes.c_double()
@@ -342,7 +397,7 @@ def bench_ours(args, rank, world, local_rank):
                 if gemm_ms > 0 and m2l_ms > gemm_ms else None},
         "p2p": {"ms": p2p_ms, "tflops_algorithmic": tf(p2p_flop, p2p_ms),
                 "frac_fp64_peak": tf(p2p_flop, p2p_ms) / fp64_peak,
-                "fp64_instr_issue_frac": 19.0 * info.n_p2p_body_pairs / (p2p_ms * 1e-3) / (pk_fma.value * 1e12 / 2)
+                "fp64_instr_issue_frac": 18.0 * info.n_p2p_body_pairs / (p2p_ms * 1e-3) / (pk_fma.value * 1e12 / 2)
                 if p2p_ms > 0 else None,
                 "body_pairs": info.n_p2p_body_pairs},
         "upward_ms": phase_acc["upward"] / args.steps, "downward_ms": phase_acc["downward"] / args.steps,
@@ -358,16 +413,22 @@ def bench_ours(args, rank, world, local_rank):
                              "(oracle/_ref/ref_laplace, FMM_plan::execute, %.2f s; plan %.2f s), OMP threads=%d"
                              % (r["best_s"], r["plan_s"], r["threads"])}
     gmres = None
+    stokes = None
     if world == 1 and not args.no_cpu_baseline:
         gmres = bench_gmres_c2()
+        stokes = bench_stresslet_c4(local_rank)
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": dict(workload(args), l2="256 MiB memset between steps, outside the per-step event pairs",
                        parallelism="1 GPU" if world == 1 else
-                       "target leaves in %d Morton-contiguous ranges of equal estimated work, tree and upward pass "
-                       "replicated, NCCL all-gather of the result slices each step" % world,
+                       ("target leaves in %d Morton-contiguous ranges of equal estimated work; per step: NCCL "
+                        "all-gather of the charge slices, owned upward pass, NCCL all-gather of the multipoles; "
+                        "results stay sharded by target (fmmb_plan_execute_sharded)" % world) if sharded else
+                       ("target leaves in %d Morton-contiguous ranges of equal estimated work; charges replicated, "
+                        "owned upward pass + NCCL all-gather of multipoles, NCCL all-gather of the result slices"
+                        % world),
                        plan_build_s=plan_s, boxes=info.n_boxes, m2l_pairs=info.n_m2l_pairs,
                        p2p_body_pairs=info.n_p2p_body_pairs),
         "e2e": {"value": 1.0 / e2e_s, "unit": UNIT, "h2d_bytes_per_step": 8 * n, "d2h_bytes_per_step": 32 * n,
@@ -379,6 +440,8 @@ def bench_ours(args, rank, world, local_rank):
         line["cpu_baseline"] = cpu
     if gmres is not None:
         line["gmres_c2"] = gmres
+    if stokes is not None:
+        line["stresslet_c4"] = stokes
     print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()
@@ -395,6 +458,9 @@ def main():
     ap.add_argument("--theta", type=float, default=0.5)
     ap.add_argument("--ncrit", type=int, default=64)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--replicated-results", action="store_true",
+                    help="N > 1: time fmmb_plan_execute_device (full result vector all-gathered to every rank) "
+                         "instead of the sharded call")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

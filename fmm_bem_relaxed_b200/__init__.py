@@ -208,6 +208,11 @@ class FMM_plan:
         capi.check(self._lib.fmmb_plan_execute_device(self._h, ctypes.c_void_p(charges_ptr),
                                                       ctypes.c_void_p(results_ptr)))
 
+    def execute_sharded(self, charges_own_ptr, results_own_ptr):
+        """Sharded matvec: this rank's charge / result slices (device pointers, tree order, owned range)."""
+        capi.check(self._lib.fmmb_plan_execute_sharded(self._h, ctypes.c_void_p(charges_own_ptr),
+                                                       ctypes.c_void_p(results_own_ptr)))
+
     def comm_init(self, unique_id):
         """Join the NCCL communicator of a partitioned plan (unique_id: 128 bytes from comm_unique_id)."""
         buf = (ctypes.c_ubyte * 128).from_buffer_copy(bytes(unique_id))

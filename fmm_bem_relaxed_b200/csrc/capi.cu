@@ -100,8 +100,12 @@ int fmmb_plan_create(const fmmb_kernel_desc* kernel, const fmmb_sources* sources
     plan->opts = opts;
     plan->kind = kernel->kind;
     plan->p = kernel->p;
-    FMMB_CUDA(cudaStreamCreateWithFlags(&plan->stream, cudaStreamNonBlocking));
-    FMMB_CUDA(cudaStreamCreateWithFlags(&plan->stream2, cudaStreamNonBlocking));
+    // the far-field chain (many short dependent kernels and the collectives) outranks the near-field kernel
+    // that runs beside it: its blocks take the SM slots first whenever both have work
+    int prio_lo = 0, prio_hi = 0;
+    FMMB_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+    FMMB_CUDA(cudaStreamCreateWithPriority(&plan->stream, cudaStreamNonBlocking, prio_hi));
+    FMMB_CUDA(cudaStreamCreateWithPriority(&plan->stream2, cudaStreamNonBlocking, prio_lo));
     for (auto& e : plan->ev) FMMB_CUDA(cudaEventCreate(&e));
     plan->charge_dim = is_stokes ? (kernel->kind == FMMB_STOKES_SPHERICAL_STRESSLET ? 6 : 3) : 1;
     plan->result_dim = is_bem ? 1 : (is_stokes ? 3 : 4);
@@ -164,7 +168,7 @@ static void run_matvec(fmmb_plan* plan, const double* q, double* r) {
     else laplace_execute(plan, q, r);
   };
   if (!plan->use_graph || !plan->overlap_p2p) { direct(); return; }
-  fmmb_plan::GraphKey key{plan->p, q, r};
+  fmmb_plan::GraphKey key{plan->p, q, r, plan->call_sharded ? 1 : 0};
   cudaStream_t s = plan->stream;
   auto it = plan->graphs.find(key);
   if (it == plan->graphs.end()) {
@@ -201,6 +205,21 @@ int fmmb_plan_execute_device(fmmb_plan* plan, const double* charges_dev, double*
   return guarded([&] {
     FMMB_CUDA(cudaSetDevice(plan->device));
     run_matvec(plan, charges_dev, results_dev);
+  });
+}
+
+int fmmb_plan_execute_sharded(fmmb_plan* plan, const double* charges_own_dev, double* results_own_dev) {
+  if (!plan || !charges_own_dev || !results_own_dev) { set_error("null argument"); return FMMB_ERR_INVALID; }
+  if (plan->kind != FMMB_LAPLACE_SPHERICAL) {
+    set_error("fmmb_plan_execute_sharded is built for FMMB_LAPLACE_SPHERICAL plans");
+    return FMMB_ERR_UNSUPPORTED;
+  }
+  if (plan->tree.nranks > 1 && !plan->comm) { set_error("call fmmb_plan_comm_init first"); return FMMB_ERR_INVALID; }
+  return guarded([&] {
+    FMMB_CUDA(cudaSetDevice(plan->device));
+    plan->call_sharded = true;
+    try { run_matvec(plan, charges_own_dev, results_own_dev); } catch (...) { plan->call_sharded = false; throw; }
+    plan->call_sharded = false;
   });
 }
 
@@ -258,8 +277,8 @@ int fmmb_plan_set_option(fmmb_plan* plan, const char* name, int64_t value) {
   if (!std::strcmp(name, "use_graph")) { plan->use_graph = value != 0; return FMMB_OK; }
   if (!std::strcmp(name, "p2p_kernel") || !std::strcmp(name, "p2p_unroll")) {
     const bool kern = !std::strcmp(name, "p2p_kernel");
-    if (kern ? (value != 0 && value != 1) : (value != 4 && value != 8)) {
-      set_error("p2p_kernel: 0 or 1; p2p_unroll: 4 or 8");
+    if (kern ? (value < 0 || value > 2) : (value != 4 && value != 8)) {
+      set_error("p2p_kernel: 0, 1 or 2; p2p_unroll: 4 or 8");
       return FMMB_ERR_INVALID;
     }
     return guarded([&] {

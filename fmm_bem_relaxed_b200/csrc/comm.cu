@@ -48,12 +48,8 @@ __global__ void place_slices(const double4* __restrict__ stage, const long long*
     tree[b0 + i] = stage[(size_t)q * chunk + i];
 }
 
-void allgather_results(fmmb_plan* plan, cudaStream_t s) {
+static void ensure_cuts(fmmb_plan* plan, cudaStream_t s) {
   Tree& T = plan->tree;
-  ncclComm_t c = (ncclComm_t)plan->comm;
-  long long chunk = 0;
-  for (int q = 0; q < T.nranks; ++q) chunk = std::max<long long>(chunk, T.body_cuts[q + 1] - T.body_cuts[q]);
-  plan->res_stage.resize((size_t)chunk * T.nranks);
   if (!plan->cuts_ready) {
     std::vector<long long> h(T.body_cuts.begin(), T.body_cuts.end());
     plan->cuts_dev.resize(h.size());
@@ -61,6 +57,32 @@ void allgather_results(fmmb_plan* plan, cudaStream_t s) {
     FMMB_CUDA(cudaStreamSynchronize(s));
     plan->cuts_ready = true;
   }
+}
+
+// Sharded call: every rank contributes the charges of its own bodies (tree order); slices are padded to the
+// longest one and gathered with one ncclAllGather (8 bytes per body instead of 32 for the results).
+void allgather_charges(fmmb_plan* plan, const double* d_own, cudaStream_t s) {
+  Tree& T = plan->tree;
+  ncclComm_t c = (ncclComm_t)plan->comm;
+  long long chunk = 0;
+  for (int q = 0; q < T.nranks; ++q) chunk = std::max<long long>(chunk, T.body_cuts[q + 1] - T.body_cuts[q]);
+  plan->chg_chunk = chunk;
+  plan->chg_stage.resize((size_t)chunk * T.nranks);
+  plan->chg_send.resize((size_t)chunk);
+  ensure_cuts(plan, s);
+  // the caller's slice is exactly own_n long: stage it so the padded send never reads past its end
+  const long long own = T.own_b1 - T.own_b0;
+  if (own) FMMB_CUDA(cudaMemcpyAsync(plan->chg_send.p, d_own, own * sizeof(double), cudaMemcpyDeviceToDevice, s));
+  FMMB_NCCL(ncclAllGather(plan->chg_send.p, plan->chg_stage.p, (size_t)chunk, ncclDouble, c, s));
+}
+
+void allgather_results(fmmb_plan* plan, cudaStream_t s) {
+  Tree& T = plan->tree;
+  ncclComm_t c = (ncclComm_t)plan->comm;
+  long long chunk = 0;
+  for (int q = 0; q < T.nranks; ++q) chunk = std::max<long long>(chunk, T.body_cuts[q + 1] - T.body_cuts[q]);
+  plan->res_stage.resize((size_t)chunk * T.nranks);
+  ensure_cuts(plan, s);
   // send buffer = my slice inside res_tree (reads past the slice end stay inside res_tree or the pad)
   const double* send = reinterpret_cast<const double*>(plan->res_tree.p + T.own_b0);
   FMMB_NCCL(ncclAllGather(send, plan->res_stage.p, (size_t)chunk * 4, ncclDouble, c, s));

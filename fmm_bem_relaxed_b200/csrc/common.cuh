@@ -131,6 +131,8 @@ struct Tree {
   DevBuf<int> p2p_run_off;           // per target box: its merged source body runs (laplace.cu: p2p_run_kernel)
   DevBuf<int2> p2p_runs;             // [begin, end) in tree-ordered bodies
   int n_p2p_runs = 0;
+  DevBuf<int4> p2p_items_ext;        // per item: run range, own body range, close flag (p2p_pair2_kernel)
+  DevBuf<unsigned char> p2p_close;   // per box: a source of another leaf lies within 1e-4 of one of its bodies
 };
 
 // One family of box-to-box translations (M2L, M2M or L2L) evaluated as class-batched GEMMs
@@ -192,6 +194,9 @@ struct fmmb_plan {
   fmmb::DevBuf<int> xchg_off_dev;
   fmmb::DevBuf<double4> res_stage;   // padded all-gather staging for the result slices
   fmmb::DevBuf<long long> cuts_dev;
+  fmmb::DevBuf<double> chg_stage, chg_send;  // sharded call: padded all-gather of the charge slices
+  long long chg_chunk = 0;
+  bool call_sharded = false;         // the current call is fmmb_plan_execute_sharded
   bool cuts_ready = false;
   bool xchg_off_ready = false;
   fmmb::DevBuf<double> results;      // original order staging, 4n
@@ -202,15 +207,17 @@ struct fmmb_plan {
   bool overlap_p2p = true;
   int p2p_item_mode = 0;             // see p2p_fill_items (laplace.cu); BEM plans use 0
   int p2p_warps = 1;                 // warps per block of the near-field pair kernels
-  int p2p_kernel = 0;                // 1 = merged source runs with prefetch (p2p_run_kernel), 0 = per source leaf
+  int p2p_kernel = 2;                // 1 = merged source runs with prefetch (p2p_run_kernel), 0 = per source leaf
   int p2p_unroll = 4;
+  int p2p_chunk = 32, p2p_min_chunk = 8;  // targets per near-field work item (chosen at plan time)
   // CUDA graphs: one captured matvec per (order, charge pointer, result pointer)
   bool use_graph = true;
   bool capturing = false;
   struct GraphKey {
-    int p; const void* q; void* r;
+    int p; const void* q; void* r; int mode;
     bool operator<(const GraphKey& o) const {
       if (p != o.p) return p < o.p;
+      if (mode != o.mode) return mode < o.mode;
       if (q != o.q) return q < o.q;
       return r < o.r;
     }
@@ -228,6 +235,7 @@ void comm_unique_id(unsigned char* id);
 void comm_init(fmmb_plan* plan, const unsigned char* id);
 void comm_destroy(fmmb_plan* plan);
 void allgather_results(fmmb_plan* plan, cudaStream_t s);
+void allgather_charges(fmmb_plan* plan, const double* d_own, cudaStream_t s);
 void exchange_multipoles(fmmb_plan* plan, cudaStream_t s);
 // laplace.cu
 void laplace_init_tables(fmmb_plan* plan);

@@ -348,16 +348,16 @@ __device__ __forceinline__ void p2p_accumulate(const double4 t, const double4 sq
 // mode 1: chunks of 32, then the remainder in power-of-two pieces: a piece of r = 2^k targets is replicated
 //         32/r times across the lanes (source splitting), so every lane of every warp does useful pairs.
 __global__ void p2p_count_items(const int* __restrict__ leaves, int nleaves, const unsigned* __restrict__ bb,
-                                const unsigned* __restrict__ be, int mode, int* __restrict__ cnt) {
+                                const unsigned* __restrict__ be, int mode, int chunk, int* __restrict__ cnt) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i > nleaves) return;
   int c = i < nleaves ? (int)(be[leaves[i]] - bb[leaves[i]]) : 0;
-  cnt[i] = mode ? c / 32 + __popc(c % 32) : (c + 31) / 32;
+  cnt[i] = mode ? c / 32 + __popc(c % 32) : (c + chunk - 1) / chunk;
 }
 __global__ void p2p_fill_items(const int* __restrict__ leaves, int nleaves, const unsigned* __restrict__ bb,
                                const unsigned* __restrict__ be, const int* __restrict__ off,
                                const int* __restrict__ p2p_off, const int* __restrict__ p2p_src, int mode,
-                               int4* __restrict__ items, unsigned* __restrict__ work) {
+                               int chunk, int4* __restrict__ items, unsigned* __restrict__ work) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= nleaves) return;
   int b = leaves[i];
@@ -366,8 +366,9 @@ __global__ void p2p_fill_items(const int* __restrict__ leaves, int nleaves, cons
   unsigned ns = 0;                       // source bodies of this leaf's list = sequential pair steps of a full chunk
   for (int e = p2p_off[b]; e < p2p_off[b + 1]; ++e) ns += be[p2p_src[e]] - bb[p2p_src[e]];
   unsigned t = t0;
-  for (; t + 32 <= t1 || (!mode && t < t1); t += 32) {
-    int r = (int)min(32u, t1 - t);
+  if (!mode) chunk = min(chunk, 32); else chunk = 32;
+  for (; t + chunk <= t1 || (!mode && t < t1); t += chunk) {
+    int r = (int)min((unsigned)chunk, t1 - t);
     work[o] = ns;
     items[o++] = make_int4(b, (int)t, r, 0);
   }
@@ -537,6 +538,181 @@ p2p_run_kernel(const int4* __restrict__ items, int nitems, const int* __restrict
   if (lane < r) res[it.y + lane] = make_double4(pot, fx, fy, fz);
 }
 
+// ---- P2P, two targets per lane ------------------------------------------------------------------------
+// Measured on B200 (scripts/micro/p2p_loop.cu): the pair loop is bound by FP64 issue (18 FP64 instructions per
+// pair); everything else in the loop body costs issue slots on top.  Two measures cut that overhead:
+//  * every lane owns TWO targets, so one shared-memory source load feeds two pairs.  A chunk of r targets uses
+//    G = ceil(r/2) lanes per replica and S = 32/G replicas that split the sources (S = 2 for a full chunk);
+//  * the R2 < 1e-8 select (LaplaceSpherical.hpp:158) only runs on tiles that can contain such a pair: tiles
+//    that overlap the target leaf's own bodies (self pairs) and, for leaves that the plan found to have a
+//    source of ANOTHER leaf closer than 1e-4 (p2p_close_kernel), every tile.  All other tiles take the
+//    select-free loop.  r2 = 0 cannot occur there: equal positions have equal Morton codes, hence one leaf.
+template <bool MASKED>
+__device__ __forceinline__ void p2p_pair(const double tx, const double ty, const double tz, const double4 sq,
+                                         double& pot, double& fx, double& fy, double& fz) {
+  const double dx = sq.x - tx, dy = sq.y - ty, dz = sq.z - tz;
+  const double r2 = dx * dx + dy * dy + dz * dz;
+  double y0;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y0) : "d"(r2));
+  const double e = fma(-(r2 * y0), y0, 1.0);
+  double inv = fma(y0 * e, fma(0.375, e, 0.5), y0);
+  if (MASKED) { if (__double_as_longlong(r2) < __double_as_longlong(1e-8)) inv = 0.0; }
+  const double qi = sq.w * inv;
+  const double qi3 = qi * (inv * inv);
+  pot += qi;
+  fx = fma(dx, qi3, fx); fy = fma(dy, qi3, fy); fz = fma(dz, qi3, fz);
+}
+
+// plan time: per target leaf, the number of (target, source) pairs with R2 < 1e-8 over its whole P2P list
+__global__ void __launch_bounds__(128)
+p2p_close_kernel(const int* __restrict__ leaves, int nleaves, const unsigned* __restrict__ bb,
+                 const unsigned* __restrict__ be, const int* __restrict__ off, const int* __restrict__ src,
+                 const double4* __restrict__ body, unsigned char* __restrict__ close_flag) {
+  const int wl = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int w = blockIdx.x * (blockDim.x >> 5) + wl;
+  if (w >= nleaves) return;
+  const int b = leaves[w];
+  const unsigned t0 = bb[b], t1 = be[b];
+  int cnt = 0;
+  for (unsigned ti = t0 + lane; ti < t1; ti += 32) {
+    const double4 t = body[ti];
+    for (int e = off[b]; e < off[b + 1]; ++e) {
+      const int sb = src[e];
+      if (sb == b) continue;
+      for (unsigned k = bb[sb]; k < be[sb]; ++k) {
+        const double4 s = body[k];
+        const double dx = s.x - t.x, dy = s.y - t.y, dz = s.z - t.z;
+        if (dx * dx + dy * dy + dz * dz < 1e-8) ++cnt;
+      }
+    }
+  }
+  cnt = __reduce_add_sync(0xffffffffu, cnt);
+  if (lane == 0) close_flag[b] = cnt > 0;
+}
+
+__global__ void p2p_items_ext_kernel(int4* __restrict__ items, int n, const unsigned* __restrict__ bb,
+                                     const unsigned* __restrict__ be, const int* __restrict__ run_off,
+                                     const int2* __restrict__ runs, const unsigned char* __restrict__ close_flag,
+                                     int4* __restrict__ ext) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int4 it = items[i];
+  const int b = it.x, j0 = run_off[b], j1 = run_off[b + 1];
+  it.w = j0 < j1 ? runs[j0].x : 0;
+  items[i] = it;
+  ext[i] = make_int4(j0, j1, (int)bb[b], (int)((be[b] - bb[b]) << 1) | (close_flag[b] ? 1 : 0));
+}
+
+template <int UNROLL>
+__global__ void __launch_bounds__(32)
+p2p_pair2_kernel(const int4* __restrict__ items, const int4* __restrict__ items_ext, int nitems,
+                 const int2* __restrict__ runs, const double4* __restrict__ body, double4 dummy,
+                 double4* __restrict__ res) {
+  __shared__ double4 tile[32];
+  const int lane = threadIdx.x;
+  const int item = blockIdx.x;
+  if (item >= nitems) return;
+  const int4 it = items[item];
+  const int r = it.z;                      // targets in this chunk (<= 32)
+  const int G = (r + 1) >> 1;              // lanes per replica, two targets each
+  const int S = 32 / G;                    // replicas: each takes every S-th source
+  const int g = lane % G, sp = lane / G;
+  const bool act = sp < S;
+  const bool even_split = (32 % S) == 0;
+  const int steps = 32 / S;
+  const bool hasb = g + G < r;
+  const double4 ta = body[it.y + g];
+  const double4 tb = hasb ? body[it.y + g + G] : ta;
+  double pa = 0, ax = 0, ay = 0, az = 0, pb = 0, bx = 0, by = 0, bz = 0;
+  // everything needed to start streaming sits in the two item words: no dependent index loads
+  const int4 ix = items_ext[item];         // x, y: run range; z: own bodies begin; w: (own count << 1) | close flag
+  const int self0 = ix.z, self1 = ix.z + (ix.w >> 1);
+  const bool all_masked = (ix.w & 1) != 0;
+  int j = ix.x;
+  const int j1 = ix.y;
+  int p = 0, pend = 0;
+  int2 rnext = make_int2(0, 0);
+  if (j < j1) { p = it.w; pend = runs[j].y; }    // it.w = begin of the first run
+  if (j + 1 < j1) rnext = runs[j + 1];
+  bool mask_nxt = false;
+  auto fetch = [&]() -> double4 {          // next 32 sources of the virtual stream (warp-uniform control flow)
+    double4 v = dummy;
+    int filled = 0;
+    mask_nxt = all_masked;
+    while (filled < 32 && j < j1) {
+      const int take = min(32 - filled, pend - p);
+      const int l = lane - filled;
+      if (l >= 0 && l < take) v = body[p + l];
+      mask_nxt = mask_nxt || (p < self1 && p + take > self0);
+      p += take; filled += take;
+      if (p == pend) {
+        ++j;
+        p = rnext.x; pend = rnext.y;
+        if (j + 1 < j1) rnext = runs[j + 1];
+      }
+    }
+    return v;
+  };
+  bool have = j < j1;
+  double4 nxt = dummy;
+  if (have) nxt = fetch();
+  while (have) {
+    __syncwarp();
+    tile[lane] = nxt;
+    const bool masked = mask_nxt;
+    __syncwarp();
+    have = j < j1;
+    if (have) nxt = fetch();               // in flight while the current tile is consumed
+    if (act) {
+      if (even_split) {                    // S divides 32: every replica takes exactly 32 / S sources of the tile
+        const double4* ts = tile + sp;
+        if (masked) {
+#pragma unroll UNROLL
+          for (int kk = 0; kk < steps; ++kk) {
+            const double4 s = ts[kk * S];
+            p2p_pair<true>(ta.x, ta.y, ta.z, s, pa, ax, ay, az);
+            p2p_pair<true>(tb.x, tb.y, tb.z, s, pb, bx, by, bz);
+          }
+        } else {
+#pragma unroll UNROLL
+          for (int kk = 0; kk < steps; ++kk) {
+            const double4 s = ts[kk * S];
+            p2p_pair<false>(ta.x, ta.y, ta.z, s, pa, ax, ay, az);
+            p2p_pair<false>(tb.x, tb.y, tb.z, s, pb, bx, by, bz);
+          }
+        }
+      } else if (masked) {
+#pragma unroll 2
+        for (int k = sp; k < 32; k += S) {
+          const double4 s = tile[k];
+          p2p_pair<true>(ta.x, ta.y, ta.z, s, pa, ax, ay, az);
+          p2p_pair<true>(tb.x, tb.y, tb.z, s, pb, bx, by, bz);
+        }
+      } else {
+#pragma unroll 2
+        for (int k = sp; k < 32; k += S) {
+          const double4 s = tile[k];
+          p2p_pair<false>(ta.x, ta.y, ta.z, s, pa, ax, ay, az);
+          p2p_pair<false>(tb.x, tb.y, tb.z, s, pb, bx, by, bz);
+        }
+      }
+    }
+  }
+  // replicas sp = 1..S-1 hold partial sums of the same targets as replica 0
+  for (int q = 1; q < S; ++q) {
+    const int from = (lane + q * G) & 31;
+    const double a0 = __shfl_sync(0xffffffffu, pa, from), a1 = __shfl_sync(0xffffffffu, ax, from),
+                 a2 = __shfl_sync(0xffffffffu, ay, from), a3 = __shfl_sync(0xffffffffu, az, from),
+                 b0 = __shfl_sync(0xffffffffu, pb, from), b1 = __shfl_sync(0xffffffffu, bx, from),
+                 b2 = __shfl_sync(0xffffffffu, by, from), b3 = __shfl_sync(0xffffffffu, bz, from);
+    if (lane < G) { pa += a0; ax += a1; ay += a2; az += a3; pb += b0; bx += b1; by += b2; bz += b3; }
+  }
+  if (lane < G) {
+    res[it.y + g] = make_double4(pa, ax, ay, az);
+    if (hasb) res[it.y + g + G] = make_double4(pb, bx, by, bz);
+  }
+}
+
 // ---- results back to the caller's order ----------------------------------------------------------
 __global__ void scatter_results(const double4* __restrict__ near, const double4* __restrict__ far,
                                 const unsigned* __restrict__ perm, int64_t i0, int64_t i1,
@@ -545,6 +721,26 @@ __global__ void scatter_results(const double4* __restrict__ near, const double4*
   if (i >= i1) return;
   double4 a = near[i], b = far[i];
   out[perm[i]] = make_double4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
+}
+// sharded call: charges arrive as per-rank slices in tree order (padded all-gather staging) -> body[].w
+__global__ void place_charges(const double* __restrict__ stage, const long long* __restrict__ cuts, int nranks,
+                              long long chunk, double4* __restrict__ body) {
+  const int q = blockIdx.y;
+  const long long b0 = cuts[q], len = cuts[q + 1] - b0;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < len; i += (long long)gridDim.x * blockDim.x)
+    body[b0 + i].w = stage[(size_t)q * chunk + i];
+}
+__global__ void place_charges_local(const double* __restrict__ q, int64_t n, double4* __restrict__ body) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < n) body[i].w = q[i];
+}
+// sharded call: near + far of the owned range, written as the rank's result slice (tree order)
+__global__ void combine_slice(const double4* __restrict__ near, const double4* __restrict__ far, int64_t i0,
+                              int64_t i1, double4* __restrict__ out) {
+  int64_t i = i0 + blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= i1) return;
+  double4 a = near[i], b = far[i];
+  out[i - i0] = make_double4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
 }
 // multi-GPU: near + far of the owned range in tree order, ready for the all-gather
 __global__ void combine_results(const double4* __restrict__ near, const double4* __restrict__ far, int64_t i0,
@@ -728,7 +924,18 @@ void laplace_execute(fmmb_plan* plan, const double* d_charges, double* d_results
   plan->launches = 0;
 
   if (!plan->capturing) FMMB_CUDA(cudaEventRecord(ev[0], s));
-  gather_charges<<<nblk(n, 256), 256, 0, s>>>(d_charges, T.perm.p, n, T.body.p);
+  if (plan->call_sharded) {
+    // charges = this rank's slice in tree order: all-gather the slices (NCCL), no permutation
+    if (T.nranks > 1 && plan->comm) {
+      allgather_charges(plan, d_charges, s);
+      dim3 grid(64, T.nranks);
+      place_charges<<<grid, 256, 0, s>>>(plan->chg_stage.p, plan->cuts_dev.p, T.nranks, plan->chg_chunk, T.body.p);
+    } else {
+      place_charges_local<<<nblk(n, 256), 256, 0, s>>>(d_charges, n, T.body.p);
+    }
+  } else {
+    gather_charges<<<nblk(n, 256), 256, 0, s>>>(d_charges, T.perm.p, n, T.body.p);
+  }
   ++plan->launches;
   FMMB_CUDA(cudaEventRecord(ev[1], s));
 
@@ -741,7 +948,14 @@ void laplace_execute(fmmb_plan* plan, const double* d_charges, double* d_results
 #define FMMB_P2P_RUN(W, U)                                                                                       \
   p2p_run_kernel<W, U><<<nblk(ni_, W), 32 * W, 0, s2>>>(T.p2p_items.p, ni_, T.p2p_run_off.p, T.p2p_runs.p, T.body.p, \
                                                         dummy, plan->res_near.p)
-  if (plan->p2p_kernel == 1 && ni_ > 0) {
+  if (plan->p2p_kernel == 2 && ni_ > 0) {
+    if (plan->p2p_unroll == 8)
+      p2p_pair2_kernel<8><<<ni_, 32, 0, s2>>>(T.p2p_items.p, T.p2p_items_ext.p, ni_, T.p2p_runs.p, T.body.p, dummy,
+                                              plan->res_near.p);
+    else
+      p2p_pair2_kernel<4><<<ni_, 32, 0, s2>>>(T.p2p_items.p, T.p2p_items_ext.p, ni_, T.p2p_runs.p, T.body.p, dummy,
+                                              plan->res_near.p);
+  } else if (plan->p2p_kernel == 1 && ni_ > 0) {
     const int w = plan->p2p_warps, u = plan->p2p_unroll;
     if (w == 1 && u == 4) FMMB_P2P_RUN(1, 4);
     else if (w == 1) FMMB_P2P_RUN(1, 8);
@@ -785,7 +999,12 @@ void laplace_execute(fmmb_plan* plan, const double* d_charges, double* d_results
   if (!plan->capturing) FMMB_CUDA(cudaEventRecord(ev[4], s));
 
   if (s2 != s) FMMB_CUDA(cudaStreamWaitEvent(s, ev[7], 0));
-  if (T.nranks > 1 && plan->comm) {
+  if (plan->call_sharded) {
+    // results stay sharded by target: the rank's slice in tree order, no collective
+    if (T.own_b1 > T.own_b0)
+      combine_slice<<<nblk(T.own_b1 - T.own_b0, 256), 256, 0, s>>>(plan->res_near.p, plan->res_far.p, T.own_b0,
+                                                                  T.own_b1, reinterpret_cast<double4*>(d_results));
+  } else if (T.nranks > 1 && plan->comm) {
     // the one exchange step: all-gather the per-rank result slices (tree order), then un-permute
     {
       // + pad: the padded all-gather reads a full chunk starting at the owned slice
@@ -841,6 +1060,11 @@ void build_p2p_items(fmmb_plan* plan) {
     T.p2p_run_off.resize(nb + 1);
     run_fill_kernel<<<nblk(ne, 256), 256, 0, s>>>(v1.p, T.bbegin.p, T.bend.p, flag.p, pos.p, ne, T.p2p_runs.p);
     run_offsets_kernel<<<nblk(nb + 1, 256), 256, 0, s>>>(T.p2p_off.p, pos.p, nb, T.p2p_run_off.p);
+    // leaves with a foreign source closer than 1e-4 to one of their bodies (see p2p_pair2_kernel)
+    T.p2p_close.resize(nb);
+    T.p2p_close.zero(s);
+    p2p_close_kernel<<<nblk(T.nleaves, 4), 128, 0, s>>>(T.leaves.p, T.nleaves, T.bbegin.p, T.bend.p, T.p2p_off.p,
+                                                       T.p2p_src.p, T.body.p, T.p2p_close.p);
     FMMB_CUDA(cudaGetLastError());
     FMMB_CUDA(cudaStreamSynchronize(s));
   }
@@ -848,11 +1072,21 @@ void build_p2p_items(fmmb_plan* plan) {
   const int nl = T.n_own_leaves;
   cnt.resize(nl + 1);
   const int mode = plan->p2p_item_mode;
-  p2p_count_items<<<nblk(nl + 1, 256), 256, 0, s>>>(T.own_leaves.p, nl, T.bbegin.p, T.bend.p, mode, cnt.p);
-  FMMB_CUDA(cudaGetLastError());
-  std::vector<int> h = cnt.to_host(s);
-  std::vector<int> off(nl + 1, 0);
-  for (int i = 0; i < nl; ++i) off[i + 1] = off[i] + h[i];
+  // Target chunk per warp: 32 bodies, or less when the rank has too few leaves to fill the GPU several times over
+  // (multi-GPU shards, small problems): a chunk of 16 or 8 targets splits its sources 4 or 8 ways across the
+  // lanes at the same lane efficiency, and the shorter items even out the tail of the grid.
+  int chunk = 32, sms = 148;
+  FMMB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, plan->device));
+  std::vector<int> h, off(nl + 1, 0);
+  for (;;) {
+    p2p_count_items<<<nblk(nl + 1, 256), 256, 0, s>>>(T.own_leaves.p, nl, T.bbegin.p, T.bend.p, mode, chunk, cnt.p);
+    FMMB_CUDA(cudaGetLastError());
+    h = cnt.to_host(s);
+    for (int i = 0; i < nl; ++i) off[i + 1] = off[i] + h[i];
+    if (plan->kind == FMMB_LAPLACE_SPHERICAL_BEM || mode != 0 || chunk <= plan->p2p_min_chunk || off[nl] >= 6 * 20 * sms) break;
+    chunk >>= 1;
+  }
+  plan->p2p_chunk = chunk;
   T.n_p2p_items = off[nl];
   DevBuf<int> doff;
   doff.from_host(off.data(), off.size(), s);
@@ -863,7 +1097,7 @@ void build_p2p_items(fmmb_plan* plan) {
   T.p2p_items.resize(ni);
   int4* fill_to = mode ? unsorted.p : T.p2p_items.p;
   if (nl) p2p_fill_items<<<nblk(nl, 256), 256, 0, s>>>(T.own_leaves.p, nl, T.bbegin.p, T.bend.p, doff.p, T.p2p_off.p,
-                                                       T.p2p_src.p, mode, fill_to, work.p);
+                                                       T.p2p_src.p, mode, chunk, fill_to, work.p);
   FMMB_CUDA(cudaGetLastError());
   if (mode && ni) {
     // longest items first: the tail of the grid is made of the short pieces (stable: ties keep leaf order)
@@ -876,6 +1110,11 @@ void build_p2p_items(fmmb_plan* plan) {
                                                         T.p2p_items.p, ni, 0, 32, s));
     FMMB_CUDA(cudaStreamSynchronize(s));
   }
+  T.p2p_items_ext.resize(ni);
+  if (ni && T.n_p2p > 0)
+    p2p_items_ext_kernel<<<nblk(ni, 256), 256, 0, s>>>(T.p2p_items.p, ni, T.bbegin.p, T.bend.p, T.p2p_run_off.p,
+                                                      T.p2p_runs.p, T.p2p_close.p, T.p2p_items_ext.p);
+  FMMB_CUDA(cudaGetLastError());
   FMMB_CUDA(cudaStreamSynchronize(s));
 }
 

@@ -142,6 +142,15 @@ int fmmb_plan_execute(fmmb_plan* plan, const double* charges_host, double* resul
  * fmmb_plan_sync).  This is what a device-resident GMRES feeds. */
 int fmmb_plan_execute_device(fmmb_plan* plan, const double* charges_dev, double* results_dev);
 
+/* Sharded matvec for a solver that keeps its vectors distributed ("results stay sharded by
+ * target"): every rank passes the charges of ITS bodies and receives the results of ITS bodies, both as device
+ * arrays in TREE order covering the plan's owned range [own_body_begin, own_body_end) of fmmb_plan_info
+ * (tree index -> original index: perm of fmmb_plan_get_tree).  The one data exchange besides the multipoles is
+ * an NCCL all-gather of the charge slices (8 bytes per body); no result collective, no permutation.
+ * Works on a single-GPU plan too (the slice is then the whole tree-ordered vector).  LaplaceSpherical plans.
+ * Asynchronous on the plan's stream. */
+int fmmb_plan_execute_sharded(fmmb_plan* plan, const double* charges_own_dev, double* results_own_dev);
+
 /* Brute force reference sum on the GPU for accuracy checks:
  * Direct::matvec(K, sources, charges, targets, results), reference include/Direct.hpp:273-288.
  * targets: 3*nt doubles (host); results: nt*result_dim doubles (host).  Point kernels only

@@ -20,7 +20,7 @@ plan = F.FMM_plan(F.LaplaceSpherical(P), pts, F.FMMOptions())
 d_q = torch.from_numpy(q).cuda()
 d_res = torch.empty((n, 4), dtype=torch.float64, device="cuda")
 ref = None
-variants = [(0, 0, 1, 4)] + [(1, i, w, u) for i in (0, 1) for w in (1, 2, 4) for u in (4, 8)]
+variants = [(0, 0, 1, 4), (1, 0, 1, 4), (2, 0, 1, 4), (2, 0, 1, 8), (2, 1, 1, 4), (2, 1, 1, 8)]
 for kern, items, warps, unroll in variants:
     if True:
         plan.set_option("p2p_kernel", kern)
