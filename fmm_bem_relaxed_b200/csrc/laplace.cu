@@ -664,7 +664,24 @@ p2p_pair2_kernel(const int4* __restrict__ items, const int4* __restrict__ items_
     have = j < j1;
     if (have) nxt = fetch();               // in flight while the current tile is consumed
     if (act) {
-      if (even_split) {                    // S divides 32: every replica takes exactly 32 / S sources of the tile
+      if (S == 2) {                        // full chunks (17..32 targets): compile-time trip count
+        const double4* ts = tile + sp;
+        if (masked) {
+#pragma unroll UNROLL
+          for (int kk = 0; kk < 16; ++kk) {
+            const double4 s = ts[2 * kk];
+            p2p_pair<true>(ta.x, ta.y, ta.z, s, pa, ax, ay, az);
+            p2p_pair<true>(tb.x, tb.y, tb.z, s, pb, bx, by, bz);
+          }
+        } else {
+#pragma unroll UNROLL
+          for (int kk = 0; kk < 16; ++kk) {
+            const double4 s = ts[2 * kk];
+            p2p_pair<false>(ta.x, ta.y, ta.z, s, pa, ax, ay, az);
+            p2p_pair<false>(tb.x, tb.y, tb.z, s, pb, bx, by, bz);
+          }
+        }
+      } else if (even_split) {             // S divides 32: every replica takes exactly 32 / S sources of the tile
         const double4* ts = tile + sp;
         if (masked) {
 #pragma unroll UNROLL

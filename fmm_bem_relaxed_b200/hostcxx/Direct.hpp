@@ -9,16 +9,28 @@
 #include <vector>
 
 class Direct {
+  // kernels that define a vector P2P (the stresslet) are evaluated through it, the others through operator(),
+  // like the reference's trait dispatch (reference include/Direct.hpp:30-97)
+  template <typename Kernel, typename SI, typename CI, typename TI, typename RI>
+  static auto eval(const Kernel& K, SI s0, SI s1, CI c0, TI t0, TI t1, RI r0, int)
+      -> decltype(K.P2P(s0, s1, c0, t0, t1, r0), void()) {
+    K.P2P(s0, s1, c0, t0, t1, r0);
+  }
+  template <typename Kernel, typename SI, typename CI, typename TI, typename RI>
+  static void eval(const Kernel& K, SI s0, SI s1, CI c0, TI t0, TI t1, RI r0, long) {
+    for (; t0 != t1; ++t0, ++r0) {
+      SI s = s0;
+      CI c = c0;
+      for (; s != s1; ++s, ++c) *r0 += K(*t0, *s) * (*c);
+    }
+  }
+
  public:
   /** r_i += sum_j K(t_i, s_j) c_j */
   template <typename Kernel, typename SourceIter, typename ChargeIter, typename TargetIter, typename ResultIter>
   inline static void matvec(const Kernel& K, SourceIter s_first, SourceIter s_last, ChargeIter c_first,
                             TargetIter t_first, TargetIter t_last, ResultIter r_first) {
-    for (; t_first != t_last; ++t_first, ++r_first) {
-      SourceIter s = s_first;
-      ChargeIter c = c_first;
-      for (; s != s_last; ++s, ++c) *r_first += K(*t_first, *s) * (*c);
-    }
+    eval(K, s_first, s_last, c_first, t_first, t_last, r_first, 0);
   }
   template <typename Kernel>
   inline static void matvec(const Kernel& K, const std::vector<typename Kernel::source_type>& s,

@@ -43,3 +43,16 @@ def test_own_driver_c1():
     assert abs(pot - 2.038194e-05) < 1e-10
     assert abs(force - 7.702187e-04) < 1e-9
     assert abs(chk - 9432714514.34655) <= 1e-10 * 9432714514.34655
+
+
+def test_reference_stresslet_driver_unchanged():
+    """Reference serialrun_stresslet.cpp (StokesSpherical, STRESSLET) compiled unchanged against hostcxx/:
+    N = 20 000, p = 8.  The patched reference prints 2.1859e-04, 5.2482e-06, 5.1619e-04 for this run
+    (its sample loop compares body 0 a thousand times, quirk Q1)."""
+    out = run("ref_serialrun_stresslet", "-N", "20000", "-p", "8")
+    m = re.search(r"Error \(u\) : ([0-9.eE+-]+), \(v\) : ([0-9.eE+-]+), \(w\) : ([0-9.eE+-]+)", out)
+    assert m, out
+    got = [float(m.group(i)) for i in (1, 2, 3)]
+    for g, want in zip(got, (2.1859e-04, 5.2482e-06, 5.1619e-04)):
+        assert abs(g - want) <= 2e-4 * want, (got, out)
+    assert "Stresslet calculation" in out
