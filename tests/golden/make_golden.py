@@ -86,6 +86,27 @@ def stokes_case(name, stresslet, n, p, ncrit, theta, points=None, charges=None, 
         print(name, meta["sum"], "err vs direct", meta["err_vs_direct"])
 
 
+def yukawa_case(name, n, p, kappa, ncrit, theta, points=None, charges=None, direct=300):
+    """YukawaCartesian through oracle/_ref/ref_yukawa: the unmodified reference class behind the arity adapter of
+    oracle/ref_yukawa.cpp."""
+    exe = os.path.join(ROOT, "oracle", "_ref", "ref_yukawa")
+    with tempfile.TemporaryDirectory() as tmp:
+        cmd = [exe, "-N", str(n), "-P", str(p), "-kappa", repr(kappa), "-ncrit", str(ncrit), "-theta", repr(theta),
+               "-direct", str(direct)]
+        if points is not None:
+            infile = os.path.join(tmp, "in.f64")
+            np.concatenate([points.ravel(), charges.ravel()]).tofile(infile)
+            cmd += ["-in", infile]
+        pre = os.path.join(tmp, "d")
+        cmd += ["-dump", pre]
+        out = subprocess.check_output(cmd, env=dict(os.environ, OMP_NUM_THREADS="1")).decode()
+        meta = json.loads([l for l in out.splitlines() if l.startswith("REF_JSON")][0][len("REF_JSON "):])
+        inp = np.fromfile(pre + ".input.f64")
+        np.savez_compressed(os.path.join(HERE, name + ".npz"), meta=json.dumps(meta), points=inp[:3 * n].reshape(n, 3),
+                            charges=inp[3 * n:], results=np.fromfile(pre + ".results.f64").reshape(n, 4))
+        print(name, meta["pot"], "err vs direct", meta["err_pot"], meta["err_force"])
+
+
 def main():
     if not os.path.exists(REF):
         sys.exit("oracle/_ref/ref_laplace missing: run `make -C oracle ref` in the build container")
@@ -106,6 +127,9 @@ def main():
     nr /= np.linalg.norm(nr, axis=1)[:, None]
     stokes_case("stresslet_two_scale_n4000_p7", True, n, 7, 12, 0.6, pts, np.hstack([g, nr]))
     stokes_case("stokeslet_two_scale_n4000_p4", False, n, 4, 12, 0.6, pts, g)
+    # 2c. YukawaCartesian (point kernel) through the arity adapter
+    yukawa_case("yukawa_drand48_n3000_p5", 3000, 5, 0.125, 32, 0.5)
+    yukawa_case("yukawa_two_scale_n4000_p6", n, 6, 2.0, 12, 0.6, pts, q)
     # 3. checksums only, larger sizes
     sums = {}
     for key, (nn, pp) in {"n10000_p5": (10000, 5), "c1_n100000_p5": (100000, 5)}.items():

@@ -49,6 +49,8 @@ def load():
         L.fmmo_drand48_inputs.argtypes = [ctypes.c_int, vp, vp]
         L.fmmo_stokes_execute.argtypes = [vp, ctypes.c_int, ctypes.c_int, vp, vp, ctypes.c_int]
         L.fmmo_stokes_direct.argtypes = [ctypes.c_int, vp, ctypes.c_int, vp, ctypes.c_int, vp, vp, ctypes.c_int]
+        L.fmmo_yukawa_execute.argtypes = [vp, ctypes.c_int, ctypes.c_double, vp, vp, ctypes.c_int]
+        L.fmmo_yukawa_direct.argtypes = [ctypes.c_int, vp, ctypes.c_double, vp, ctypes.c_int, vp, vp, ctypes.c_int]
         L.fmmo_unit_sphere.argtypes = [ctypes.c_int, vp]
         L.fmmo_panel_centers.argtypes = [ctypes.c_int, vp, vp]
         L.fmmo_bem_execute.argtypes = [vp, ctypes.c_int, ctypes.c_int, vp, vp, vp, vp, ctypes.c_int]
@@ -128,6 +130,15 @@ class Oracle:
             raise RuntimeError("oracle stokes execute failed: %d" % rc)
         return res
 
+    def yukawa_execute(self, charges, P, kappa, threads=None):
+        """YukawaCartesian matvec: results (n, 4) = potential and the three force-like components."""
+        q = np.ascontiguousarray(np.asarray(charges, dtype=np.float64).reshape(-1))
+        res = np.zeros((self.n, 4))
+        rc = self.L.fmmo_yukawa_execute(self.h, P, float(kappa), _p(q), _p(res), threads or os.cpu_count() or 1)
+        if rc != 0:
+            raise RuntimeError("oracle yukawa execute failed: %d" % rc)
+        return res
+
     def expansions(self):
         nc = self.P * (self.P + 1) // 2
         M = np.zeros((self.nboxes, nc, 2))
@@ -193,6 +204,16 @@ def stokes_direct(spts, q, tpts, stresslet, threads=None):
     q = np.ascontiguousarray(np.asarray(q, dtype=np.float64).reshape(spts.shape[0], -1))
     out = np.zeros((tpts.shape[0], 3))
     load().fmmo_stokes_direct(spts.shape[0], _p(spts), int(bool(stresslet)), _p(q), tpts.shape[0], _p(tpts), _p(out),
+                              threads or os.cpu_count() or 1)
+    return out
+
+
+def yukawa_direct(spts, q, tpts, kappa, threads=None):
+    spts = np.ascontiguousarray(np.asarray(spts, dtype=np.float64).reshape(-1, 3))
+    tpts = np.ascontiguousarray(np.asarray(tpts, dtype=np.float64).reshape(-1, 3))
+    q = np.ascontiguousarray(np.asarray(q, dtype=np.float64).reshape(-1))
+    out = np.zeros((tpts.shape[0], 4))
+    load().fmmo_yukawa_direct(spts.shape[0], _p(spts), float(kappa), _p(q), tpts.shape[0], _p(tpts), _p(out),
                               threads or os.cpu_count() or 1)
     return out
 

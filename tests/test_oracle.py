@@ -162,3 +162,23 @@ def test_stokes_restatement_matches_reference(name, stresslet, P, ncrit, theta):
     meta = json.loads(str(g["meta"]))
     d = O.stokes_direct(g["points"], g["charges"], g["points"][:300], stresslet)
     assert abs(O.rel_l2(res[:300], d) - meta["err_vs_direct"]) < 1e-6 * max(1.0, meta["err_vs_direct"] / 1e-4)
+
+
+# ---- YukawaCartesian restatement pinned to the reference class (oracle/_ref/ref_yukawa: unmodified
+# ---- kernel/YukawaCartesian.hpp behind the arity adapter the executor needs) -----
+@pytest.mark.parametrize("name,P,kappa,ncrit,theta", [
+    ("yukawa_drand48_n3000_p5", 5, 0.125, 32, 0.5),
+    ("yukawa_two_scale_n4000_p6", 6, 2.0, 12, 0.6),
+])
+def test_yukawa_restatement_matches_reference(name, P, kappa, ncrit, theta):
+    g = dict(np.load(os.path.join(GOLDEN, name + ".npz")))
+    orc = O.Oracle(g["points"], ncrit, theta)
+    res = orc.yukawa_execute(g["charges"], P, kappa, threads=1)
+    # the derivative table is restated through its general recurrence (different summation order than the
+    # reference's hand-unrolled cases): agreement to rounding, not bit for bit
+    assert O.rel_l2(res[:, 0], g["results"][:, 0]) <= 1e-14
+    assert O.rel_l2(res[:, 1:], g["results"][:, 1:]) <= 1e-14
+    assert np.array_equal(orc.yukawa_execute(g["charges"], P, kappa, threads=4), res)
+    meta = json.loads(str(g["meta"]))
+    d = O.yukawa_direct(g["points"], g["charges"], g["points"][:300], kappa)
+    assert abs(O.rel_l2(res[:300, 0], d[:, 0]) - meta["err_pot"]) <= 1e-6 * max(1.0, meta["err_pot"] / 1e-5)
