@@ -23,7 +23,7 @@ import numpy as np
 from . import capi
 from .capi import FmmbError
 
-__all__ = ["FMMOptions", "LaplaceSpherical", "LaplaceSphericalBEM", "StokesSpherical", "Panels", "FMM_plan", "Direct", "FmmbError", "capi", "comm_unique_id",
+__all__ = ["FMMOptions", "LaplaceSpherical", "LaplaceSphericalBEM", "StokesSpherical", "YukawaCartesian", "Panels", "FMM_plan", "Direct", "FmmbError", "capi", "comm_unique_id",
            "partition_ranges", "get_options"]
 
 
@@ -124,6 +124,18 @@ class StokesSpherical(LaplaceSpherical):
         self.charge_dim = 6 if self.stresslet else 3
 
 
+class YukawaCartesian(LaplaceSpherical):
+    """Mirror of reference kernel/YukawaCartesian.hpp:14-159: K(t,s) = exp(-kappa |t-s|) / |t-s|, order p, screening
+    parameter kappa (constructor YukawaCartesian(int p, double kappa = 0.125)); 1 charge, 4 results.
+    Orders 1..10.  set_p(p) means "the full order-p expansion" (the reference's own p < P path walks a wrong
+    coefficient subset)."""
+    kind = capi.YUKAWA_CARTESIAN
+
+    def __init__(self, p=4, kappa=0.125):
+        super().__init__(p)
+        self.Kappa = float(kappa)
+
+
 class Panels:
     """A set of triangular panels (the std::vector<Panel> a reference driver builds)."""
     POTENTIAL, NORMAL_DERIV = 0, 1
@@ -164,9 +176,13 @@ class FMM_plan:
         else:
             pts = np.ascontiguousarray(np.asarray(sources, dtype=np.float64).reshape(-1, 3))
             # the plan owns a COPY of the kernel (FMM_plan.hpp:37)
-            self.K = StokesSpherical(kernel.P, kernel.stresslet) if isinstance(kernel, StokesSpherical) \
-                else LaplaceSpherical(kernel.P)
-            kd = capi.KernelDesc(kernel.kind, kernel.P, 0.0, 0, 0)
+            if isinstance(kernel, StokesSpherical):
+                self.K = StokesSpherical(kernel.P, kernel.stresslet)
+            elif isinstance(kernel, YukawaCartesian):
+                self.K = YukawaCartesian(kernel.P, kernel.Kappa)
+            else:
+                self.K = LaplaceSpherical(kernel.P)
+            kd = capi.KernelDesc(kernel.kind, kernel.P, getattr(kernel, "Kappa", 0.0), 0, 0)
         self._n = pts.shape[0]
         self._rdim = self.K.result_dim
         self._cdim = self.K.charge_dim

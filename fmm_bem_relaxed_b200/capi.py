@@ -18,6 +18,7 @@ LAPLACE_SPHERICAL = 0
 LAPLACE_SPHERICAL_BEM = 1
 STOKES_SPHERICAL_STRESSLET = 2
 STOKES_SPHERICAL = 5
+YUKAWA_CARTESIAN = 3
 
 
 class FmmbError(RuntimeError):

@@ -66,9 +66,10 @@ int fmmb_plan_create(const fmmb_kernel_desc* kernel, const fmmb_sources* sources
   if (!kernel || !sources || !out_plan) { set_error("null argument"); return FMMB_ERR_INVALID; }
   *out_plan = nullptr;
   const bool is_stokes = kernel->kind == FMMB_STOKES_SPHERICAL || kernel->kind == FMMB_STOKES_SPHERICAL_STRESSLET;
-  if (kernel->kind != FMMB_LAPLACE_SPHERICAL && kernel->kind != FMMB_LAPLACE_SPHERICAL_BEM && !is_stokes) {
+  const bool is_yukawa = kernel->kind == FMMB_YUKAWA_CARTESIAN;
+  if (kernel->kind != FMMB_LAPLACE_SPHERICAL && kernel->kind != FMMB_LAPLACE_SPHERICAL_BEM && !is_stokes && !is_yukawa) {
     set_error("built kernel kinds: FMMB_LAPLACE_SPHERICAL, FMMB_LAPLACE_SPHERICAL_BEM, FMMB_STOKES_SPHERICAL, "
-              "FMMB_STOKES_SPHERICAL_STRESSLET");
+              "FMMB_STOKES_SPHERICAL_STRESSLET, FMMB_YUKAWA_CARTESIAN");
     return FMMB_ERR_UNSUPPORTED;
   }
   const bool is_bem = kernel->kind == FMMB_LAPLACE_SPHERICAL_BEM;
@@ -128,6 +129,7 @@ int fmmb_plan_create(const fmmb_kernel_desc* kernel, const fmmb_sources* sources
     build_p2p_items(plan);
     if (is_bem) bem_setup(plan, sources->vertices, sources->bc, kernel->quad_k);
     if (is_stokes) stokes_setup(plan, kernel->kind == FMMB_STOKES_SPHERICAL_STRESSLET);
+    if (is_yukawa) yukawa_setup(plan, kernel->kappa);
   });
   if (rc != FMMB_OK) { fmmb_plan_destroy(plan); return rc; }
   *out_plan = plan;
@@ -143,6 +145,7 @@ void fmmb_plan_destroy(fmmb_plan* plan) {
   comm_destroy(plan);
   bem_free(plan->bem);
   stokes_free(plan->stokes);
+  yukawa_free(plan->yukawa);
   for (auto& kv : plan->m2l_coeff) delete kv.second;
   for (auto& e : plan->ev) if (e) cudaEventDestroy(e);
   if (plan->stream) cudaStreamDestroy(plan->stream);
@@ -153,6 +156,7 @@ void fmmb_plan_destroy(fmmb_plan* plan) {
 int fmmb_plan_set_p(fmmb_plan* plan, int p) {
   if (!plan) { set_error("null plan"); return FMMB_ERR_INVALID; }
   if (p < 1 || p > FMMB_MAX_P) { set_error("expansion order must be in 1..16"); return FMMB_ERR_INVALID; }
+  if (plan->yukawa && p > 10) { set_error("YukawaCartesian is built for orders 1..10"); return FMMB_ERR_UNSUPPORTED; }
   plan->p = p;
   return FMMB_OK;
 }
@@ -165,6 +169,7 @@ static void run_matvec(fmmb_plan* plan, const double* q, double* r) {
   auto direct = [&] {
     if (plan->bem) bem_execute(plan, q, r);
     else if (plan->stokes) stokes_execute(plan, q, r);
+    else if (plan->yukawa) yukawa_execute(plan, q, r);
     else laplace_execute(plan, q, r);
   };
   if (!plan->use_graph || !plan->overlap_p2p) { direct(); return; }
@@ -262,7 +267,9 @@ int fmmb_plan_direct(fmmb_plan* plan, const double* charges_host, int64_t nt, co
     q.from_host(charges_host, (size_t)plan->charge_dim * plan->tree.n, s);
     t.from_host(targets_host, 3 * (size_t)nt, s);
     out.resize(rd * (size_t)nt);
-    if (nt && plan->stokes)
+    if (nt && plan->yukawa)
+      yukawa_direct_raw(yukawa_kappa(plan->yukawa), plan->tree.pts_orig.p, q.p, plan->tree.n, t.p, nt, out.p, s);
+    else if (nt && plan->stokes)
       stokes_direct_raw(stokes_is_stresslet(plan->stokes), plan->tree.pts_orig.p, q.p, plan->tree.n, t.p, nt, out.p, s);
     else if (nt) laplace_direct_raw(plan->tree.pts_orig.p, q.p, plan->tree.n, t.p, nt, out.p, s);
     if (nt) FMMB_CUDA(cudaMemcpyAsync(results_host, out.p, rd * (size_t)nt * sizeof(double), cudaMemcpyDeviceToHost, s));
@@ -393,6 +400,10 @@ int fmmb_plan_get_tree(fmmb_plan* plan, uint32_t* perm, uint32_t* codes, uint32_
 
 int fmmb_plan_get_expansions(fmmb_plan* plan, double* multipoles, double* locals) {
   if (!plan) { set_error("null plan"); return FMMB_ERR_INVALID; }
+  if (plan->stokes || plan->yukawa) {
+    set_error("fmmb_plan_get_expansions returns LaplaceSpherical[BEM] expansions only");
+    return FMMB_ERR_UNSUPPORTED;
+  }
   return guarded([&] {
     FMMB_CUDA(cudaSetDevice(plan->device));
     cudaStream_t s = plan->stream;

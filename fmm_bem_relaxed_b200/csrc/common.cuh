@@ -161,6 +161,7 @@ struct TransBatch {
 
 struct BemData;
 struct StokesData;
+struct YukawaData;
 
 struct LaplaceTables {
   int pmax = 0;
@@ -189,6 +190,7 @@ struct fmmb_plan {
   fmmb::DevBuf<double4> res_tree;    // multi-GPU: near + far in tree order, all-gathered over NCCL
   fmmb::BemData* bem = nullptr;      // LaplaceSphericalBEM plans only
   fmmb::StokesData* stokes = nullptr;  // StokesSpherical plans only
+  fmmb::YukawaData* yukawa = nullptr;  // YukawaCartesian plans only
   int charge_dim = 1, result_dim = 4;
   void* comm = nullptr;              // ncclComm_t once fmmb_plan_comm_init ran
   fmmb::DevBuf<int> xchg_off_dev;
@@ -251,6 +253,13 @@ int64_t bem_nnz(const BemData* b);
 void laplace_direct_raw(const double* d_spts, const double* d_q, int64_t ns, const double* d_tpts, int64_t nt,
                         double* d_out, cudaStream_t s);
 void measure_fp64_peak(double* dfma, double* dmma);
+// yukawa.cu
+void yukawa_setup(fmmb_plan* plan, double kappa);
+void yukawa_execute(fmmb_plan* plan, const double* d_charges, double* d_results);
+void yukawa_free(YukawaData* d);
+double yukawa_kappa(const YukawaData* d);
+void yukawa_direct_raw(double kappa, const double* d_spts, const double* d_q, int64_t ns, const double* d_tpts,
+                       int64_t nt, double* d_out, cudaStream_t s);
 // stokes.cu
 void stokes_setup(fmmb_plan* plan, bool stresslet);
 void stokes_execute(fmmb_plan* plan, const double* d_charges, double* d_results);

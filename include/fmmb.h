@@ -49,7 +49,8 @@ typedef enum {
   FMMB_LAPLACE_SPHERICAL_BEM = 1,      /* kernel/LaplaceSphericalBEM.hpp: panels, charge 1, result 1 */
   FMMB_STOKES_SPHERICAL_STRESSLET = 2, /* kernel/StokesSpherical.hpp built with -DSTRESSLET: charge 6 (g, n),
                                           result 3 (serialrun_stresslet.cpp) */
-  FMMB_YUKAWA_CARTESIAN = 3,           /* kernel/YukawaCartesian.hpp (not built yet) */
+  FMMB_YUKAWA_CARTESIAN = 3,           /* kernel/YukawaCartesian.hpp: charge 1, result 4, orders 1..10, kappa from
+                                          fmmb_kernel_desc */
   FMMB_YUKAWA_CARTESIAN_BEM = 4,       /* kernel/YukawaCartesianBEM.hpp (not built yet) */
   FMMB_STOKES_SPHERICAL = 5            /* kernel/StokesSpherical.hpp default build (Stokeslet): charge 3 (f), result 3 */
 } fmmb_kernel_kind;
