@@ -280,7 +280,16 @@ int fmmb_plan_direct(fmmb_plan* plan, const double* charges_host, int64_t nt, co
 int fmmb_plan_set_option(fmmb_plan* plan, const char* name, int64_t value) {
   if (!plan || !name) { set_error("null argument"); return FMMB_ERR_INVALID; }
   if (!std::strcmp(name, "overlap_p2p")) { plan->overlap_p2p = value != 0; return FMMB_OK; }
-  if (!std::strcmp(name, "m2l_mode")) { plan->opts.m2l_mode = (int32_t)value; return FMMB_OK; }
+  if (!std::strcmp(name, "m2l_mode")) {
+    return guarded([&] {
+      FMMB_CUDA(cudaSetDevice(plan->device));
+      FMMB_CUDA(cudaStreamSynchronize(plan->stream));
+      for (auto& kv : plan->graphs) cudaGraphExecDestroy(kv.second);   // graphs captured with the other path are stale
+      plan->graphs.clear();
+      plan->graph_seen.clear();
+      plan->opts.m2l_mode = (int32_t)value;
+    });
+  }
   if (!std::strcmp(name, "use_graph")) { plan->use_graph = value != 0; return FMMB_OK; }
   if (!std::strcmp(name, "p2p_kernel") || !std::strcmp(name, "p2p_unroll")) {
     const bool kern = !std::strcmp(name, "p2p_kernel");
