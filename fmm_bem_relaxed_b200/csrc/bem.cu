@@ -274,11 +274,6 @@ __global__ void bem_gather_charges(const double* __restrict__ q, const unsigned*
   int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i < n) body[i].w = q[perm[i]];
 }
-__global__ void bem_scatter(const double* __restrict__ near, const double* __restrict__ far,
-                            const unsigned* __restrict__ perm, int64_t i0, int64_t i1, double* __restrict__ out) {
-  int64_t i = i0 + blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (i < i1) out[perm[i]] = near[i] + far[i];
-}
 
 }  // namespace
 
@@ -288,7 +283,6 @@ void bem_setup(fmmb_plan* plan, const double* verts_host, const int32_t* bc_host
   cudaStream_t s = plan->stream;
   if (!bem::rule_supported(quad_k))
     throw StatusError{FMMB_ERR_UNSUPPORTED, "Gauss rules with 1, 3, 4 (or 7, aliased to 4 like the reference) points are built"};
-  if (T.nranks > 1) throw StatusError{FMMB_ERR_UNSUPPORTED, "multi-GPU BEM plans are not built yet"};
   BemData* B = new BemData();
   plan->bem = B;
   B->K = quad_k == 7 ? 4 : quad_k;
@@ -383,8 +377,7 @@ void bem_execute(fmmb_plan* plan, const double* d_charges, double* d_results) {
     ++plan->launches;
   }
   if (!plan->capturing) FMMB_CUDA(cudaEventRecord(ev[4], s));
-  bem_scatter<<<nblk(n, 256), 256, 0, s>>>(B->res_near.p, B->res_far.p, T.perm.p, 0, n, d_results);
-  ++plan->launches;
+  finish_results(plan, B->res_near.p, B->res_far.p, 1, d_results, s);
   if (!plan->capturing) FMMB_CUDA(cudaEventRecord(ev[5], s));
   FMMB_CUDA(cudaGetLastError());
   plan->timed = true;

@@ -91,6 +91,69 @@ void allgather_results(fmmb_plan* plan, cudaStream_t s) {
   FMMB_CUDA(cudaGetLastError());
 }
 
+// ---- generic result epilogue (BEM: 1, Stokes: 3, Yukawa: 4 doubles per body) ----------------------------------
+namespace {
+__global__ void gen_combine_scatter(const double* __restrict__ near, const double* __restrict__ far,
+                                    const unsigned* __restrict__ perm, int64_t i0, int64_t i1, int rd,
+                                    double* __restrict__ out) {
+  int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (t >= (i1 - i0) * rd) return;
+  const int64_t i = i0 + t / rd;
+  const int k = (int)(t % rd);
+  out[(size_t)perm[i] * rd + k] = near[(size_t)i * rd + k] + far[(size_t)i * rd + k];
+}
+__global__ void gen_combine(const double* __restrict__ near, const double* __restrict__ far, int64_t i0, int64_t i1,
+                            int rd, double* __restrict__ tree) {
+  int64_t t = i0 * rd + blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (t < i1 * rd) tree[t] = near[t] + far[t];
+}
+__global__ void gen_place(const double* __restrict__ stage, const long long* __restrict__ cuts, long long chunk,
+                          int rd, double* __restrict__ tree) {
+  const int q = blockIdx.y;
+  const long long b0 = cuts[q] * rd, len = (cuts[q + 1] - cuts[q]) * rd;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < len; i += (long long)gridDim.x * blockDim.x)
+    tree[b0 + i] = stage[(size_t)q * chunk * rd + i];
+}
+__global__ void gen_scatter(const double* __restrict__ tree, const unsigned* __restrict__ perm, int64_t n, int rd,
+                            double* __restrict__ out) {
+  int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (t >= n * rd) return;
+  const int64_t i = t / rd;
+  out[(size_t)perm[i] * rd + t % rd] = tree[t];
+}
+}  // namespace
+
+// near + far (tree order, rd doubles per body, valid on the owned range) -> results in the caller's order.
+// Single GPU / no communicator: the owned range is scattered.  With a communicator the owned slices are
+// all-gathered (padded NCCL all-gather) so that every rank ends up with the full result vector.
+void finish_results(fmmb_plan* plan, const double* near, const double* far, int rd, double* d_results, cudaStream_t s) {
+  Tree& T = plan->tree;
+  const int64_t n = T.n;
+  auto nb = [](int64_t c, int t) { return (int)((c + t - 1) / t); };
+  if (!(T.nranks > 1 && plan->comm)) {
+    if (T.own_b1 > T.own_b0)
+      gen_combine_scatter<<<nb((T.own_b1 - T.own_b0) * rd, 256), 256, 0, s>>>(near, far, T.perm.p, T.own_b0, T.own_b1,
+                                                                             rd, d_results);
+    ++plan->launches;
+    FMMB_CUDA(cudaGetLastError());
+    return;
+  }
+  ncclComm_t c = (ncclComm_t)plan->comm;
+  long long chunk = 0;
+  for (int q = 0; q < T.nranks; ++q) chunk = std::max<long long>(chunk, T.body_cuts[q + 1] - T.body_cuts[q]);
+  plan->gen_tree.resize(((size_t)n + (size_t)chunk) * rd);     // + pad: the padded send reads a full chunk
+  plan->gen_stage.resize((size_t)chunk * T.nranks * rd);
+  ensure_cuts(plan, s);
+  if (T.own_b1 > T.own_b0)
+    gen_combine<<<nb((T.own_b1 - T.own_b0) * rd, 256), 256, 0, s>>>(near, far, T.own_b0, T.own_b1, rd, plan->gen_tree.p);
+  FMMB_NCCL(ncclAllGather(plan->gen_tree.p + (size_t)T.own_b0 * rd, plan->gen_stage.p, (size_t)chunk * rd, ncclDouble, c, s));
+  dim3 grid(64, T.nranks);
+  gen_place<<<grid, 256, 0, s>>>(plan->gen_stage.p, plan->cuts_dev.p, chunk, rd, plan->gen_tree.p);
+  gen_scatter<<<nb(n * rd, 256), 256, 0, s>>>(plan->gen_tree.p, T.perm.p, n, rd, d_results);
+  plan->launches += 3;
+  FMMB_CUDA(cudaGetLastError());
+}
+
 namespace {
 __global__ void pack_boxes(const int* __restrict__ list, int count, int xs, const double* __restrict__ M,
                            double* __restrict__ out) {

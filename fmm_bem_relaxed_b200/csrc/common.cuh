@@ -195,6 +195,7 @@ struct fmmb_plan {
   void* comm = nullptr;              // ncclComm_t once fmmb_plan_comm_init ran
   fmmb::DevBuf<int> xchg_off_dev;
   fmmb::DevBuf<double4> res_stage;   // padded all-gather staging for the result slices
+  fmmb::DevBuf<double> gen_tree, gen_stage;  // finish_results(): tree-ordered results and the all-gather staging
   fmmb::DevBuf<long long> cuts_dev;
   fmmb::DevBuf<double> chg_stage, chg_send;  // sharded call: padded all-gather of the charge slices
   long long chg_chunk = 0;
@@ -237,6 +238,7 @@ void comm_unique_id(unsigned char* id);
 void comm_init(fmmb_plan* plan, const unsigned char* id);
 void comm_destroy(fmmb_plan* plan);
 void allgather_results(fmmb_plan* plan, cudaStream_t s);
+void finish_results(fmmb_plan* plan, const double* near, const double* far, int rd, double* d_results, cudaStream_t s);
 void allgather_charges(fmmb_plan* plan, const double* d_own, cudaStream_t s);
 void exchange_multipoles(fmmb_plan* plan, cudaStream_t s);
 // laplace.cu

@@ -287,14 +287,6 @@ stokes_p2p_kernel(const int4* __restrict__ items, int nitems, const unsigned* __
   }
 }
 
-__global__ void stokes_scatter(const double* __restrict__ near, const double* __restrict__ far,
-                               const unsigned* __restrict__ perm, int64_t n, double* __restrict__ out) {
-  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const size_t o = 3 * (size_t)perm[i];
-#pragma unroll
-  for (int k = 0; k < 3; ++k) out[o + k] = near[3 * (size_t)i + k] + far[3 * (size_t)i + k];
-}
 
 // brute force over all sources (Direct::matvec with the kernel's own pair rule)
 template <bool STRESSLET>
@@ -338,7 +330,6 @@ struct SetGuard {            // plan->M / plan->L temporarily ARE set k of the S
 
 void stokes_setup(fmmb_plan* plan, bool stresslet) {
   Tree& T = plan->tree;
-  if (T.nranks > 1) throw StatusError{FMMB_ERR_UNSUPPORTED, "multi-GPU StokesSpherical plans are not built yet"};
   StokesData* d = new StokesData();
   plan->stokes = d;
   d->stresslet = stresslet;
@@ -399,12 +390,17 @@ void stokes_execute(fmmb_plan* plan, const double* d_charges, double* d_results)
     FMMB_CUDA(cudaFuncSetAttribute(stokes_p2m_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024));
     attr = true;
   }
-  const dim3 pg(nblk(T.nleaves, warps), 4);
-  if (d->stresslet)
-    stokes_p2m_kernel<true><<<pg, 32 * warps, sh, s>>>(T.leaves.p, T.nleaves, T.bbegin.p, T.bend.p, T.center.p,
+  // multi-GPU with a communicator: the upward pass is owned (own leaves, multipoles exchanged per set by
+  // laplace_translations); otherwise it is replicated
+  const bool p2m_owned = T.nranks > 1 && plan->comm && P <= 8 && plan->opts.m2l_mode != 1 && plan->m2m_own.n_items > 0;
+  const int* p2m_list = p2m_owned ? T.own_leaves.p : T.leaves.p;
+  const int p2m_n = p2m_owned ? T.n_own_leaves : T.nleaves;
+  const dim3 pg(nblk(p2m_n, warps), 4);
+  if (p2m_n && d->stresslet)
+    stokes_p2m_kernel<true><<<pg, 32 * warps, sh, s>>>(p2m_list, p2m_n, T.bbegin.p, T.bend.p, T.center.p,
                                                       d->src.p, P, d->M4[0].p, d->M4[1].p, d->M4[2].p, d->M4[3].p);
-  else
-    stokes_p2m_kernel<false><<<pg, 32 * warps, sh, s>>>(T.leaves.p, T.nleaves, T.bbegin.p, T.bend.p, T.center.p,
+  else if (p2m_n)
+    stokes_p2m_kernel<false><<<pg, 32 * warps, sh, s>>>(p2m_list, p2m_n, T.bbegin.p, T.bend.p, T.center.p,
                                                        d->src.p, P, d->M4[0].p, d->M4[1].p, d->M4[2].p, d->M4[3].p);
   ++plan->launches;
   // translations: the Laplace operators applied to each set (StokesSpherical.hpp:190-196,293-307)
@@ -412,6 +408,7 @@ void stokes_execute(fmmb_plan* plan, const double* d_charges, double* d_results)
     SetGuard g(plan, d, k);
     laplace_translations(plan, s);
   }
+  if (T.n_own_leaves)
   stokes_l2p_kernel<<<nblk(T.n_own_leaves, 4), 128, (size_t)4 * 4 * nc * sizeof(double2), s>>>(
       T.own_leaves.p, T.n_own_leaves, T.bbegin.p, T.bend.p, T.center.p, T.has_local.p, T.body.p, P, d->L4[0].p,
       d->L4[1].p, d->L4[2].p, d->L4[3].p, d->stresslet ? 1.0 / 6 : 1.0, d->res_far.p);
@@ -419,8 +416,7 @@ void stokes_execute(fmmb_plan* plan, const double* d_charges, double* d_results)
   if (!plan->capturing) FMMB_CUDA(cudaEventRecord(ev[4], s));
 
   if (s2 != s) FMMB_CUDA(cudaStreamWaitEvent(s, ev[7], 0));
-  stokes_scatter<<<nblk(n, 256), 256, 0, s>>>(d->res_near.p, d->res_far.p, T.perm.p, n, d_results);
-  ++plan->launches;
+  finish_results(plan, d->res_near.p, d->res_far.p, 3, d_results, s);
   if (!plan->capturing) FMMB_CUDA(cudaEventRecord(ev[5], s));
   FMMB_CUDA(cudaGetLastError());
   plan->timed = true;

@@ -409,13 +409,6 @@ yk_p2p_kernel(const int4* __restrict__ items, int nitems, const unsigned* __rest
   if (lane < r) res[it.y + lane] = make_double4(pot, fx, fy, fz);
 }
 
-__global__ void yk_scatter(const double4* __restrict__ near, const double4* __restrict__ far,
-                           const unsigned* __restrict__ perm, int64_t n, double4* __restrict__ out) {
-  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const double4 a = near[i], b = far[i];
-  out[perm[i]] = make_double4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
-}
 
 __global__ void __launch_bounds__(128)
 yk_direct_kernel(const double* __restrict__ spts, const double* __restrict__ q, int64_t ns,
@@ -443,7 +436,6 @@ yk_direct_kernel(const double* __restrict__ spts, const double* __restrict__ q, 
 
 void yukawa_setup(fmmb_plan* plan, double kappa) {
   Tree& T = plan->tree;
-  if (T.nranks > 1) throw StatusError{FMMB_ERR_UNSUPPORTED, "multi-GPU YukawaCartesian plans are not built yet"};
   if (plan->p > kYkMaxP) throw StatusError{FMMB_ERR_UNSUPPORTED, "YukawaCartesian is built for orders 1..10"};
   YukawaData* d = new YukawaData();
   plan->yukawa = d;
@@ -535,14 +527,14 @@ void yukawa_execute(fmmb_plan* plan, const double* d_charges, double* d_results)
   }
   {
     const size_t sh = (size_t)4 * (nt + 32 * 3 * (P + 1)) * sizeof(double);
+    if (T.n_own_leaves)
     yk_l2p_kernel<<<nblk(T.n_own_leaves, 4), 128, sh, s>>>(T.own_leaves.p, T.n_own_leaves, T.bbegin.p, T.bend.p,
                                                           T.center.p, T.has_local.p, T.body.p, P, d->L.p, far);
     ++plan->launches;
   }
   if (!plan->capturing) FMMB_CUDA(cudaEventRecord(ev[4], s));
   if (s2 != s) FMMB_CUDA(cudaStreamWaitEvent(s, ev[7], 0));
-  yk_scatter<<<nblk(n, 256), 256, 0, s>>>(near, far, T.perm.p, n, reinterpret_cast<double4*>(d_results));
-  ++plan->launches;
+  finish_results(plan, d->res_near.p, d->res_far.p, 4, d_results, s);   // multi-GPU: upward pass replicated
   if (!plan->capturing) FMMB_CUDA(cudaEventRecord(ev[5], s));
   FMMB_CUDA(cudaGetLastError());
   plan->timed = true;

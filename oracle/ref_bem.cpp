@@ -20,10 +20,38 @@
 using std::isnan;
 
 #include <FMM_plan.hpp>
+#ifdef YUKAWA_BEM
+// -DYUKAWA_BEM: kernel/YukawaCartesianBEM.hpp behind the arity adapter its executor needs (the shipped operators
+// carry a trailing `unsigned p`); all arithmetic is the reference's.
+#include <YukawaCartesianBEM.hpp>
+#include <Triangulation.hpp>
+static double g_kappa = 1.0;
+class YukawaBEMAdapter : public YukawaCartesianBEM {
+ public:
+  YukawaBEMAdapter(int p, unsigned k) : YukawaCartesianBEM(p, g_kappa, k) {}
+  kernel_value_type operator()(const source_type& t, const target_type& s) const { return YukawaCartesianBEM::operator()(t, s); }
+  void init_multipole(multipole_type& M, const point_type& e, unsigned l) const { YukawaCartesianBEM::init_multipole(M, e, l); }
+  void init_local(local_type& L, const point_type& e, unsigned l) const { YukawaCartesianBEM::init_local(L, e, l); }
+  void P2M(const source_type& s, const charge_type& c, const point_type& ctr, multipole_type& M) const {
+    YukawaCartesianBEM::P2M(s, c, ctr, M, (unsigned)P);
+  }
+  void M2M(const multipole_type& Ms, multipole_type& Mt, const point_type& t) const { YukawaCartesianBEM::M2M(Ms, Mt, t, (unsigned)P); }
+  void M2P(const multipole_type& M, const point_type& ctr, const target_type& t, result_type& r) const {
+    YukawaCartesianBEM::M2P(M, ctr, t, r, (unsigned)P);
+  }
+  void M2L(const multipole_type& Ms, local_type& Lt, const point_type& t) const { YukawaCartesianBEM::M2L(Ms, Lt, t, (unsigned)P); }
+  void L2L(const local_type& Ls, local_type& Lt, const point_type& t) const { YukawaCartesianBEM::L2L(Ls, Lt, t, (unsigned)P); }
+  void L2P(const local_type& L, const point_type& ctr, const target_type& t, result_type& r) const {
+    YukawaCartesianBEM::L2P(L, ctr, t, r, (unsigned)P);
+  }
+};
+typedef YukawaBEMAdapter kernel_type;
+#else
 #include <LaplaceSphericalBEM.hpp>
 #include <Triangulation.hpp>
 
 typedef LaplaceSphericalBEM kernel_type;
+#endif
 typedef kernel_type::point_type point_type;
 typedef kernel_type::source_type source_type;
 typedef kernel_type::charge_type charge_type;
@@ -38,7 +66,7 @@ static void dump(const std::string& path, const std::vector<T>& v) {
 }
 
 int main(int argc, char** argv) {
-  int recursions = 4, P = 8, K = 4, bc = 0, rnd = 0, sparse = 1, direct = 0, n_in = 0, reps = 1;
+  int recursions = 4, P = 8, K = 4, bc = 0, rnd = 0, sparse = 1, direct = 0, n_in = 0, reps = 1, tree = 0;
   unsigned ncrit = 64;
   double theta = 0.5;
   std::string dump_prefix, in_file;
@@ -56,6 +84,10 @@ int main(int argc, char** argv) {
     else if (!strcmp(argv[i], "-in")) in_file = argv[++i];
     else if (!strcmp(argv[i], "-n")) n_in = atoi(argv[++i]);
     else if (!strcmp(argv[i], "-dump")) dump_prefix = argv[++i];
+#ifdef YUKAWA_BEM
+    else if (!strcmp(argv[i], "-kappa")) g_kappa = atof(argv[++i]);
+    else if (!strcmp(argv[i], "-tree")) tree = 1;
+#endif
     else { fprintf(stderr, "unknown arg %s\n", argv[i]); return 2; }
   }
   kernel_type Kn(P, K);     // also sets the process-global quadrature order (BEMConfig)
@@ -81,6 +113,7 @@ int main(int argc, char** argv) {
   opts.set_mac_theta(theta);
   opts.set_max_per_box(ncrit);
   opts.sparse_local = sparse != 0;
+  if (tree) opts.evaluator = FMMOptions::TREECODE;
   double t0 = get_time();
   FMM_plan<kernel_type> plan(Kn, panels, opts);
   double t_plan = get_time() - t0;

@@ -40,6 +40,31 @@ for n, P in ((200000, 8), (60000, 5), (30000, 7)):
     own = (i.own_body_begin, i.own_body_end)
     plan.close()          # teardown (ncclCommDestroy) at the same point on every rank
     print("rank %d/%d N=%d P=%d own [%d,%d) rel-L2 vs single GPU %.2e" % (rank, world, n, P, own[0], own[1], err), flush=True)
+# the other kernel classes: owned upward pass per expansion set (BEM, Stokes) or replicated (Yukawa), NCCL all-gather
+# of the result slices
+rng = np.random.default_rng(11)
+n = 40000
+pts, q = O.drand48_inputs(n)
+verts = O.unit_sphere(6)
+cases = [("stokeslet", lambda: F.StokesSpherical(7, False), pts, rng.random((n, 3))),
+         ("stresslet", lambda: F.StokesSpherical(8, True), pts, np.hstack([rng.random((n, 3)), np.tile([1.0, 0, 0], (n, 1))])),
+         ("yukawa", lambda: F.YukawaCartesian(6, 1.0), pts, q),
+         ("laplace-bem", lambda: F.LaplaceSphericalBEM(8, 4), F.Panels(verts), rng.random(len(verts)))]
+for name, mk, src, chg in cases:
+    single = F.FMMOptions(); single.device = local
+    ref = F.FMM_plan(mk(), src, single).execute(chg)
+    opts = F.FMMOptions(); opts.device = local; opts.rank, opts.nranks = rank, world
+    plan = F.FMM_plan(mk(), src, opts)
+    idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
+    if rank == 0:
+        idt.copy_(torch.frombuffer(bytearray(F.comm_unique_id()), dtype=torch.uint8))
+    dist.broadcast(idt, 0)
+    plan.comm_init(bytes(idt.cpu().numpy().tobytes()))
+    for rep in range(3):
+        err = O.rel_l2(plan.execute(chg), ref)
+        ok &= err < 1e-12
+    plan.close()
+    print("rank %d/%d %s rel-L2 vs single GPU %.2e" % (rank, world, name, err), flush=True)
 dist.barrier()
 if rank == 0:
     print("MULTI_GPU_CHECK", "OK" if ok else "FAILED")

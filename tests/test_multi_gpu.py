@@ -128,3 +128,30 @@ def test_sharded_call_on_one_gpu_is_the_tree_ordered_matvec():
     part = F.FMM_plan(F.LaplaceSpherical(P), pts, opts)
     with pytest.raises(F.FmmbError):
         part.execute_sharded(d_q.data_ptr(), d_r.data_ptr())
+
+
+def _tile_check(make_kernel, sources, charges, world, tol=1e-13):
+    """Partitioned plans on one device without a communicator: each writes its own slice; the slices tile the
+    single-GPU result."""
+    full = F.FMM_plan(make_kernel(), sources).execute(charges)
+    merged = np.zeros_like(full)
+    for r in range(world):
+        opts = F.FMMOptions()
+        opts.rank, opts.nranks = r, world
+        merged += F.FMM_plan(make_kernel(), sources, opts).execute(charges)
+    assert O.rel_l2(merged, full) <= tol
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("world", [2, 3])
+def test_partitioned_plans_other_kernels(world):
+    n = 20000
+    pts, q = O.drand48_inputs(n)
+    rng = np.random.default_rng(3)
+    _tile_check(lambda: F.StokesSpherical(6, False), pts, rng.random((n, 3)), world)
+    g = np.hstack([rng.random((n, 3)), np.tile([0.0, 1.0, 0.0], (n, 1))])
+    _tile_check(lambda: F.StokesSpherical(5, True), pts, g, world)
+    _tile_check(lambda: F.YukawaCartesian(5, 0.5), pts, q, world)
+    verts = O.unit_sphere(5)                                   # 2048 panels
+    _tile_check(lambda: F.LaplaceSphericalBEM(6, 4), F.Panels(verts), rng.random(len(verts)), world)
+    _tile_check(lambda: F.LaplaceSphericalBEM(6, 4), F.Panels(verts, 1), rng.random(len(verts)), world)
