@@ -86,7 +86,11 @@ int fmmb_plan_create(const fmmb_kernel_desc* kernel, const fmmb_sources* sources
   if (opts.nranks < 1) { opts.nranks = 1; opts.rank = 0; }
   if (!(opts.theta > 0)) { set_error("theta must be positive"); return FMMB_ERR_INVALID; }
   if (opts.ncrit < 1) { set_error("ncrit must be at least 1"); return FMMB_ERR_INVALID; }
-  if (opts.evaluator != FMMB_EVAL_FMM) { set_error("treecode evaluator is not built"); return FMMB_ERR_UNSUPPORTED; }
+  if (opts.evaluator != FMMB_EVAL_FMM && opts.evaluator != FMMB_EVAL_TREECODE) { set_error("unknown evaluator"); return FMMB_ERR_INVALID; }
+  if (opts.evaluator == FMMB_EVAL_TREECODE && kernel->kind != FMMB_LAPLACE_SPHERICAL) {
+    set_error("the treecode evaluator (M2P) is built for FMMB_LAPLACE_SPHERICAL plans");
+    return FMMB_ERR_UNSUPPORTED;
+  }
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
     cudaGetLastError();

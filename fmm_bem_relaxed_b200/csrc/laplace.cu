@@ -317,6 +317,66 @@ l2p_kernel(const int* __restrict__ leaves, int nleaves, const unsigned* __restri
   }
 }
 
+// ---- M2P (treecode, FMMOptions::TREECODE): warp per leaf, lane per body ---------------------------------------
+// Every accepted pair (source box, target box) of the traversal evaluates the source multipole at the bodies of
+// the target box (LaplaceSpherical.hpp:340-368 through EvalInteractionLazy.hpp:271-282).  A body receives from
+// the lists of its leaf AND of every ancestor, so the warp walks up the parent chain; the source multipole is
+// staged in a warp-private shared tile and each lane sums its own body in a fixed order (no atomics).
+__global__ void __launch_bounds__(128)
+m2p_kernel(const int* __restrict__ leaves, int nleaves, const unsigned* __restrict__ bb,
+           const unsigned* __restrict__ be, const unsigned* __restrict__ parent, const int* __restrict__ off,
+           const int* __restrict__ src, const double4* __restrict__ center, const double4* __restrict__ body, int P,
+           const double* __restrict__ M, double4* __restrict__ res) {
+  extern __shared__ double2 sh[];
+  const int nc = P * (P + 1) / 2;
+  const int wl = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int w = blockIdx.x * (blockDim.x >> 5) + wl;
+  if (w >= nleaves) return;
+  double2* Ms = sh + wl * nc;
+  const int leaf = leaves[w];
+  const unsigned b0 = bb[leaf], b1 = be[leaf];
+  for (unsigned base = b0; base < b1; base += 32) {
+    const unsigned i = base + lane;
+    const bool act = i < b1;
+    const double4 p = act ? body[i] : make_double4(0, 0, 0, 0);
+    double pot = 0, fx = 0, fy = 0, fz = 0;
+    for (int a = leaf;; a = (int)parent[a]) {
+      for (int e = off[a]; e < off[a + 1]; ++e) {
+        const int sb = src[e];
+        __syncwarp();
+        for (int k = lane; k < nc; k += 32) {
+          int n, m;
+          unpack_nm(k, n, m);
+          Ms[k] = load_coef(M + (size_t)sb * xstride(P), n, m);
+        }
+        __syncwarp();
+        if (act) {
+          const double4 c = center[sb];
+          const Sph s = to_sph(p.x - c.x, p.y - c.y, p.z - c.z);
+          const double inv_r = 1.0 / s.r;
+          double v = 0, s0 = 0, s1 = 0, s2 = 0;
+          regular_harmonics<true, true>(P, s, 1.0, [&](int n, int m, double yr, double yi, double tr, double ti) {
+            const double2 c2 = Ms[n * (n + 1) / 2 + m];
+            const double w2 = m == 0 ? 1.0 : 2.0;
+            const double re = w2 * (c2.x * yr - c2.y * yi);   // Re(M Y)
+            v += re;
+            s0 -= re * inv_r * (n + 1);
+            s1 += w2 * (c2.x * tr - c2.y * ti);               // Re(M Ytheta)
+            s2 -= w2 * (c2.x * yi + c2.y * yr) * m;           // Re(M Y i) m
+          });
+          const double inv_ry = inv_r / s.y;
+          pot += v;
+          fx += s.y * s.cp * s0 + s.x * s.cp * inv_r * s1 - s.sp * inv_ry * s2;
+          fy += s.y * s.sp * s0 + s.x * s.sp * inv_r * s1 + s.cp * inv_ry * s2;
+          fz += s.x * s0 - s.y * inv_r * s1;
+        }
+      }
+      if (a == 0) break;
+    }
+    if (act) res[i] = make_double4(pot, fx, fy, fz);
+  }
+}
+
 // ---- P2P: one warp per (target leaf, chunk of <= 32 targets) ---------------------------------------
 // Sources stream through a warp-private shared tile (32 bodies = 1 KB), so there is no block
 // barrier.  A chunk with r < 32 targets is replicated S = 32/r times across the lanes and every
@@ -883,6 +943,10 @@ void laplace_translations(fmmb_plan* plan, cudaStream_t s) {
     ++plan->launches;
   }
   if (!plan->capturing) FMMB_CUDA(cudaEventRecord(ev[2], s));
+  if (plan->opts.evaluator == FMMB_EVAL_TREECODE) {        // treecode: multipoles only, M2P does the rest
+    if (!plan->capturing) FMMB_CUDA(cudaEventRecord(ev[3], s));
+    return;
+  }
 
   // far field translations: batched translation classes, then the per-pair kernel for the rest
   {
@@ -1009,10 +1073,17 @@ void laplace_execute(fmmb_plan* plan, const double* d_charges, double* d_results
                                                                T.center.p, T.body.p, P, plan->M.p);
                        ++plan->launches;
   laplace_translations(plan, s);
-  l2p_kernel<<<nblk(T.n_own_leaves, 4), 128, 4 * nc * sizeof(double2), s>>>(T.own_leaves.p, T.n_own_leaves, T.bbegin.p, T.bend.p,
-                                                                     T.center.p, T.has_local.p, T.body.p, P,
-                                                                     plan->L.p, plan->res_far.p);
-                             ++plan->launches;
+  if (plan->opts.evaluator == FMMB_EVAL_TREECODE) {
+    if (T.n_own_leaves)
+      m2p_kernel<<<nblk(T.n_own_leaves, 4), 128, 4 * nc * sizeof(double2), s>>>(
+          T.own_leaves.p, T.n_own_leaves, T.bbegin.p, T.bend.p, T.parent.p, T.m2l_off.p, T.m2l_src.p, T.center.p,
+          T.body.p, P, plan->M.p, plan->res_far.p);
+  } else if (T.n_own_leaves) {
+    l2p_kernel<<<nblk(T.n_own_leaves, 4), 128, 4 * nc * sizeof(double2), s>>>(
+        T.own_leaves.p, T.n_own_leaves, T.bbegin.p, T.bend.p, T.center.p, T.has_local.p, T.body.p, P, plan->L.p,
+        plan->res_far.p);
+  }
+  ++plan->launches;
   if (!plan->capturing) FMMB_CUDA(cudaEventRecord(ev[4], s));
 
   if (s2 != s) FMMB_CUDA(cudaStreamWaitEvent(s, ev[7], 0));

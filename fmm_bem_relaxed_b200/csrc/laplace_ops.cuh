@@ -28,9 +28,11 @@ __device__ __forceinline__ Sph to_sph(double dx, double dy, double dz) {
 
 // All rho^n Y_n^m, 0 <= m <= n < P, visited m-major exactly like evalMultipole (:455-488).
 // f(n, m, Yre, Yim, Ytre, Ytim); sign = +1 for e^{+i m phi}, -1 for e^{-i m phi}.
-template <bool THETA, typename F>
+// SINGULAR: rho^{-n-1} Y_n^m instead (evalLocal :491-524, used by M2P for n < P).
+template <bool THETA, bool SINGULAR = false, typename F>
 __device__ __forceinline__ void regular_harmonics(int P, const Sph& s, double sign, F&& f) {
-  double fact = 1, pn = 1, rhom = 1;
+  const double step = SINGULAR ? 1.0 / s.r : s.r;
+  double fact = 1, pn = 1, rhom = SINGULAR ? step : 1.0;
   double er = 1, ei = 0;
   const double cp = s.cp, sp = sign * s.sp;
   // divisions of the recurrences become multiplications by tabulated 1/k and one 1/sin(alpha)
@@ -44,7 +46,7 @@ __device__ __forceinline__ void regular_harmonics(int P, const Sph& s, double si
     double at = 0;
     if (THETA) at = rhom * (p - (m + 1) * s.x * p1) * inv_y * c_pref[npn];
     f(m, m, a * er, a * ei, at * er, at * ei);
-    rhom *= s.r;
+    rhom *= step;
     double rhon = rhom;
     for (int n = m + 1; n < P; ++n) {
       int npm = n * n + n + m;
@@ -54,7 +56,7 @@ __device__ __forceinline__ void regular_harmonics(int P, const Sph& s, double si
       p = (s.x * (2 * n + 1) * p1 - (n + m) * p2) * c_rcp[n - m + 1];
       if (THETA) at = rhon * ((n - m + 1) * p - (n + 1) * s.x * p1) * inv_y * c_pref[npm];
       f(n, m, a * er, a * ei, at * er, at * ei);
-      rhon *= s.r;
+      rhon *= step;
     }
     pn = -pn * fact * s.y;
     fact += 2;

@@ -67,7 +67,7 @@ static void dump(const std::string& path, const std::vector<T>& v) {
 }
 
 int main(int argc, char** argv) {
-  int N = 10000, P = 5, reps = 1, ndirect = 0, threads = 0, lazy = 1;
+  int N = 10000, P = 5, reps = 1, ndirect = 0, threads = 0, lazy = 1, treecode = 0;
   unsigned ncrit = 64;
   double theta = 0.5;
   std::string dump_prefix, in_file;
@@ -80,6 +80,7 @@ int main(int argc, char** argv) {
     else if (!strcmp(argv[i], "-direct")) ndirect = atoi(argv[++i]);
     else if (!strcmp(argv[i], "-threads")) threads = atoi(argv[++i]);
     else if (!strcmp(argv[i], "-lazy")) lazy = atoi(argv[++i]);
+    else if (!strcmp(argv[i], "-tree")) treecode = 1;
     else if (!strcmp(argv[i], "-dump")) dump_prefix = argv[++i];
     else if (!strcmp(argv[i], "-in")) in_file = argv[++i];
     else { fprintf(stderr, "unknown arg %s\n", argv[i]); return 2; }
@@ -119,6 +120,7 @@ int main(int argc, char** argv) {
   opts.set_mac_theta(theta);
   opts.set_max_per_box(ncrit);
   opts.lazy_evaluation = lazy != 0;
+  if (treecode) opts.evaluator = FMMOptions::TREECODE;   // -eval TREE (FMMOptions.hpp:86-92)
 
   double t0 = get_time();
   plan_type plan(K, points, opts);

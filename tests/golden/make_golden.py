@@ -65,6 +65,24 @@ def case(name, n, p, ncrit, theta, points=None, charges=None):
         print(name, meta["boxes"], "boxes", meta["lr_pairs"], "M2L pairs")
 
 
+def treecode_case(name, n, p, ncrit, theta, points=None, charges=None):
+    """LaplaceSpherical with FMMOptions::TREECODE (-eval TREE): P2M, M2M, M2P per accepted pair, P2P."""
+    with tempfile.TemporaryDirectory() as tmp:
+        cmd = [REF, "-N", str(n), "-P", str(p), "-ncrit", str(ncrit), "-theta", repr(theta), "-tree", "-direct", "300"]
+        if points is not None:
+            infile = os.path.join(tmp, "in.f64")
+            np.concatenate([points.ravel(), charges]).tofile(infile)
+            cmd += ["-in", infile]
+        pre = os.path.join(tmp, "d")
+        cmd += ["-dump", pre]
+        out = subprocess.check_output(cmd, env=dict(os.environ, OMP_NUM_THREADS="1")).decode()
+        meta = json.loads([l for l in out.splitlines() if l.startswith("REF_JSON")][0][len("REF_JSON "):])
+        inp = np.fromfile(pre + ".input.f64")
+        np.savez_compressed(os.path.join(HERE, name + ".npz"), meta=json.dumps(meta), points=inp[:3 * n].reshape(n, 3),
+                            charges=inp[3 * n:], results=np.fromfile(pre + ".results.f64").reshape(n, 4))
+        print(name, meta["pot"], "err vs direct", meta["err_pot"], meta["err_force"])
+
+
 def stokes_case(name, stresslet, n, p, ncrit, theta, points=None, charges=None, direct=300):
     """StokesSpherical through oracle/_ref/ref_stokeslet (unmodified reference) or ref_stresslet (the
     reference with the two compile patches of SURVEY.md section 8(c)); stores inputs, results, checksums."""
@@ -119,6 +137,8 @@ def main():
     pts[n // 2:] = 0.3 + 0.04 * rng.random((n - n // 2, 3))
     q = rng.random(n) - 0.4
     case("laplace_two_scale_n4000_p6", n, 6, 12, 0.6, pts, q)
+    treecode_case("laplace_treecode_n3000_p4", 3000, 4, 32, 0.5)
+    treecode_case("laplace_treecode_two_scale_n4000_p6", n, 6, 12, 0.6, pts, q)
     # 2b. StokesSpherical: Stokeslet (unmodified reference) and stresslet (patched reference)
     stokes_case("stokeslet_drand48_n3000_p5", False, 3000, 5, 32, 0.5)
     stokes_case("stresslet_drand48_n3000_p6", True, 3000, 6, 32, 0.5)

@@ -184,3 +184,37 @@ def test_metric_config_properties_n1m_p8(checksums):
     assert O.rel_l2(r12, res + r2) < 1e-12
     # oracle on a subset of targets is too slow at this size; the sampled leaves' near field is
     # covered by the Direct comparison above.
+
+
+@pytest.mark.parametrize("name,P,ncrit,theta", [("laplace_treecode_n3000_p4", 4, 32, 0.5),
+                                                ("laplace_treecode_two_scale_n4000_p6", 6, 12, 0.6)])
+def test_treecode_evaluator_golden(name, P, ncrit, theta):
+    """-eval TREE (FMMOptions::TREECODE): M2P for every accepted pair instead of M2L / L2L / L2P."""
+    import os
+    from conftest import GOLDEN
+    g = dict(np.load(os.path.join(GOLDEN, name + ".npz")))
+    opts = F.FMMOptions()
+    opts.set_mac_theta(theta)
+    opts.set_max_per_box(ncrit)
+    opts.evaluator = F.FMMOptions.TREECODE
+    plan = F.FMM_plan(F.LaplaceSpherical(P), g["points"], opts)
+    res = plan.execute(g["charges"])
+    assert_parity(res, g["results"])
+    assert np.array_equal(plan.execute(g["charges"]), res)
+    assert np.array_equal(plan.execute(g["charges"]), res)        # graph replay
+
+
+def test_treecode_vs_oracle_and_fmm():
+    n, P = 30000, 7
+    pts, q = O.drand48_inputs(n)
+    opts = F.FMMOptions()
+    opts.evaluator = F.FMMOptions.TREECODE
+    plan = F.FMM_plan(F.LaplaceSpherical(P), pts, opts)
+    res = plan.execute(q)
+    assert_parity(res, O.Oracle(pts, 64, 0.5).execute(q, P, mode=2))
+    # treecode and FMM approximate the same sum: they agree to the truncation error of the expansions
+    fmm = make_plan(pts, P).execute(q)
+    assert O.rel_l2(res[:, 0], fmm[:, 0]) < 1e-4
+    # other kernel classes do not have the treecode path yet
+    with pytest.raises(F.FmmbError):
+        F.FMM_plan(F.StokesSpherical(4), pts, opts)

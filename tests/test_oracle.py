@@ -182,3 +182,12 @@ def test_yukawa_restatement_matches_reference(name, P, kappa, ncrit, theta):
     meta = json.loads(str(g["meta"]))
     d = O.yukawa_direct(g["points"], g["charges"], g["points"][:300], kappa)
     assert abs(O.rel_l2(res[:300, 0], d[:, 0]) - meta["err_pot"]) <= 1e-6 * max(1.0, meta["err_pot"] / 1e-5)
+
+
+@pytest.mark.parametrize("name,P,ncrit,theta", [("laplace_treecode_n3000_p4", 4, 32, 0.5),
+                                                ("laplace_treecode_two_scale_n4000_p6", 6, 12, 0.6)])
+def test_treecode_restatement_matches_reference(name, P, ncrit, theta):
+    """FMMOptions::TREECODE (-eval TREE): P2M, M2M, then M2P for every accepted pair in LR_list order, P2P."""
+    g = dict(np.load(os.path.join(GOLDEN, name + ".npz")))
+    res = O.Oracle(g["points"], ncrit, theta).execute(g["charges"], P, mode=2, threads=1)
+    assert np.array_equal(res, g["results"])
