@@ -361,9 +361,12 @@ def bench_ours(args, rank, world, local_rank):
     m2l_ms = phase_acc["m2l"] / args.steps
     gemm_ms = phase_acc["m2l_gemm"] / args.steps
     p2p_ms = phase_acc["p2p"] / args.steps
-    m2l_flop = 7.0 * P ** 3 * (P + 1) * info.n_m2l_pairs
+    # N > 1: rank 0's kernels run on its share of the pairs (the plan reports global list sizes and this rank's
+    # batched M2L pairs); the P2P share is taken as 1 / world (ranges are balanced by estimated work)
+    m2l_flop = 7.0 * P ** 3 * (P + 1) * (info.n_m2l_pairs if world == 1 else info.n_m2l_pairs_batched)
     gemm_exec_flop = 2.0 * P ** 4 * info.n_m2l_pairs_batched
-    p2p_flop = 22.0 * info.n_p2p_body_pairs
+    p2p_pairs_rank = info.n_p2p_body_pairs / world
+    p2p_flop = 22.0 * p2p_pairs_rank
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -371,7 +374,7 @@ def bench_ours(args, rank, world, local_rank):
         pass
     tf = lambda flop, ms_: flop / (ms_ * 1e-3) / 1e12 if ms_ > 0 else 0.0
     kernels = {
-        "p2p_kernel": {"ms": p2p_ms, "algorithmic_flop": p2p_flop, "achieved": tf(p2p_flop, p2p_ms)},
+        "p2p_pair2_kernel": {"ms": p2p_ms, "algorithmic_flop": p2p_flop, "achieved": tf(p2p_flop, p2p_ms)},
         "trans_gemm_kernel(M2L)": {"ms": gemm_ms if gemm_ms > 0 else m2l_ms, "algorithmic_flop": m2l_flop,
                                    "achieved": tf(m2l_flop, gemm_ms if gemm_ms > 0 else m2l_ms),
                                    "executed_flop": gemm_exec_flop,
@@ -379,9 +382,19 @@ def bench_ours(args, rank, world, local_rank):
     }
     dominant = max(kernels, key=lambda k: kernels[k]["ms"])
     dk = kernels[dominant]
+    # DRAM traffic per launch of that kernel: from the committed `ncu --set full` capture of this round
+    # (profiles/traffic_r01.json, written by scripts/summarize_profiles.py from the .ncu-rep files)
+    traffic = None
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic_r01.json")))
+        key = "p2p" if dominant.startswith("p2p") else "m2l_gemm"
+        if world == 1 and args.n == 1000000 and P == 8 and key in tj:
+            traffic = tj[key]["dram_bytes_read"] + tj[key]["dram_bytes_write"]
+    except Exception:
+        pass
     roofline = {
         "kernel": dominant, "bound": "fp64", "achieved": dk["achieved"], "peak": fp64_peak, "unit": "TFLOP/s",
-        "frac": dk["achieved"] / fp64_peak, "traffic": None,
+        "frac": dk["achieved"] / fp64_peak, "traffic": traffic,
         "peak_source": "measured in this process by fmmb_measure_fp64_peak: DFMA %.1f, DMMA.8x8x4 %.1f TFLOP/s "
                        "(MEASURED_PEAKS.json has no FP64 entry)" % (pk_fma.value, pk_mma.value),
         "algorithmic_flop_per_launch": dk["algorithmic_flop"], "ms_per_launch": dk["ms"],
@@ -397,7 +410,7 @@ def bench_ours(args, rank, world, local_rank):
                 if gemm_ms > 0 and m2l_ms > gemm_ms else None},
         "p2p": {"ms": p2p_ms, "tflops_algorithmic": tf(p2p_flop, p2p_ms),
                 "frac_fp64_peak": tf(p2p_flop, p2p_ms) / fp64_peak,
-                "fp64_instr_issue_frac": 18.0 * info.n_p2p_body_pairs / (p2p_ms * 1e-3) / (pk_fma.value * 1e12 / 2)
+                "fp64_instr_issue_frac": 18.0 * p2p_pairs_rank / (p2p_ms * 1e-3) / (pk_fma.value * 1e12 / 2)
                 if p2p_ms > 0 else None,
                 "body_pairs": info.n_p2p_body_pairs},
         "upward_ms": phase_acc["upward"] / args.steps, "downward_ms": phase_acc["downward"] / args.steps,

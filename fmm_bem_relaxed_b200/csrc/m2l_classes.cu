@@ -265,8 +265,11 @@ trans_gemm_kernel(int ldT, const double* __restrict__ Tt, int n_items, const int
                   const double* __restrict__ X, double* __restrict__ tmp, double* __restrict__ Out) {
   using G = GemmCfg<P>;
   constexpr int PP = G::PP, XS = G::XS, KB = G::KB, RB = G::RB, CB = G::CB, LDB = G::LDB;
-  extern __shared__ __align__(16) double smem[];        // 2 x [kNB][LDB]
-  __shared__ int s_slot[2][kNB], s_src[2][kNB];
+  // Software pipeline with ONE block barrier per item: source expansions are copied two items ahead into a ring
+  // of three buffers, their slot / source indices are staged three items ahead into a ring of four.
+  constexpr int NBUF = 3, NIDX = 4;
+  extern __shared__ __align__(16) double smem[];        // NBUF x [kNB][LDB]
+  __shared__ int s_slot[NIDX][kNB], s_src[NIDX][kNB];
   const int per = (n_items + gridDim.x - 1) / gridDim.x;
   const int i0 = blockIdx.x * per, i1 = min(n_items, i0 + per);
   if (i0 >= i1) return;
@@ -281,7 +284,7 @@ trans_gemm_kernel(int ldT, const double* __restrict__ Tt, int n_items, const int
   // k positions beyond the copied expansion (k-block padding) stay zero for the whole kernel
   if constexpr (G::KMAX > XS) {
     constexpr int extra = G::KMAX - XS;
-    for (int idx = threadIdx.x; idx < 2 * kNB * extra; idx += 256) {
+    for (int idx = threadIdx.x; idx < NBUF * kNB * extra; idx += 256) {
       int colb = idx / extra, k = XS + idx % extra;
       smem[(size_t)colb * LDB + k] = 0.0;
     }
@@ -295,11 +298,11 @@ trans_gemm_kernel(int ldT, const double* __restrict__ Tt, int n_items, const int
       s_src[buf][threadIdx.x] = sl >= 0 ? slot_src[sl] : -1;
     }
   };
-  auto stage_copy = [&](int buf) {
+  auto stage_copy = [&](int ib, int buf) {
     double* Bs = smem + (size_t)buf * kNB * LDB;
     for (int idx = threadIdx.x; idx < kNB * chunks; idx += 256) {
       int col = idx / chunks, ch = idx - col * chunks;
-      int src = s_src[buf][col];
+      int src = s_src[ib][col];
       double* dst = Bs + col * LDB + 2 * ch;
       if (src >= 0) cp_async16(dst, X + (size_t)src * XS + 2 * ch);
       else { dst[0] = 0.0; dst[1] = 0.0; }
@@ -308,11 +311,15 @@ trans_gemm_kernel(int ldT, const double* __restrict__ Tt, int n_items, const int
   };
 
   double A[RB][KB];
-  int cur = -1, buf = 0;
+  int cur = -1;
   stage_indices(i0, 0);
+  if (i0 + 1 < i1) stage_indices(i0 + 1, 1);
+  if (i0 + 2 < i1) stage_indices(i0 + 2, 2);
   __syncthreads();
-  stage_copy(0);
-  for (int it = i0; it < i1; ++it, buf ^= 1) {
+  stage_copy(0, 0);
+  if (i0 + 1 < i1) stage_copy(1, 1); else cp_async_commit();
+  for (int it = i0; it < i1; ++it) {
+    const int j = it - i0, buf = j % NBUF, ib = j % NIDX;
     const int c = item_class[it];
     if (c != cur) {
       const double* Tc = Tt + (size_t)c * ldT * ldT;
@@ -325,11 +332,10 @@ trans_gemm_kernel(int ldT, const double* __restrict__ Tt, int n_items, const int
         }
       cur = c;
     }
-    const bool more = it + 1 < i1;
-    if (more) stage_indices(it + 1, buf ^ 1);
-    __syncthreads();
-    if (more) { stage_copy(buf ^ 1); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
-    __syncthreads();
+    cp_async_wait<1>();                 // this thread's copies of item `it` have landed (item it+1 may be in flight)
+    __syncthreads();                    // ... everyone's; all warps are done with item it-1
+    if (it + 3 < i1) stage_indices(it + 3, (j + 3) % NIDX);
+    if (it + 2 < i1) stage_copy((j + 2) % NIDX, (j + 2) % NBUF); else cp_async_commit();
 
     const double* Bs = smem + (size_t)buf * kNB * LDB + (size_t)(col_base + lr) * LDB + lk;
     double C[RB][CB][2];
@@ -351,7 +357,7 @@ trans_gemm_kernel(int ldT, const double* __restrict__ Tt, int n_items, const int
     for (int cb = 0; cb < CB; ++cb)
 #pragma unroll
       for (int i = 0; i < 2; ++i) {
-        const int sl = s_slot[buf][col_base + cb * 8 + 2 * lk + i];
+        const int sl = s_slot[ib][col_base + cb * 8 + 2 * lk + i];
         if (sl < 0) continue;
         double* o = (ACC ? Out : tmp) + (size_t)sl * XS;
 #pragma unroll
@@ -363,7 +369,6 @@ trans_gemm_kernel(int ldT, const double* __restrict__ Tt, int n_items, const int
           }
         }
       }
-    __syncthreads();
   }
 }
 
@@ -410,7 +415,7 @@ m2m_reduce_kernel(int lo, int hi, const unsigned* __restrict__ key, const unsign
 template <int P, bool ACC>
 void launch_gemm_t(const TransBatch& B, int first, int count, const double* X, double* tmp, double* out,
                    cudaStream_t s) {
-  size_t sh = (size_t)2 * kNB * GemmCfg<P>::LDB * sizeof(double);
+  size_t sh = (size_t)3 * kNB * GemmCfg<P>::LDB * sizeof(double);
   static bool attr = false;
   static int sms = 0;
   if (!attr) {

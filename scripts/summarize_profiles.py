@@ -76,9 +76,36 @@ def report(rep, tag):
                 f.write("| %s | %s | %s |\n" % (k, U[i], V[i]))
 
 
+def traffic(reps):
+    """profiles/traffic_r01.json: DRAM bytes per launch of the top kernels (read by bench.py for roofline.traffic)."""
+    import json
+    out = {}
+    for key, rep in reps.items():
+        path = os.path.join(GP, rep + ".ncu-rep")
+        if not os.path.exists(path):
+            continue
+        raw = subprocess.check_output(["ncu", "-i", path, "--page", "raw", "--csv"]).decode()
+        rows = list(csv.reader(io.StringIO(raw)))
+        H, U, V = rows[0], rows[1], rows[2]
+        scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+
+        def val(name):
+            i = H.index(name)
+            return float(V[i].replace(",", "")) * scale[U[i]]
+        out[key] = {"kernel": V[H.index("Kernel Name")][:80], "source": rep + ".ncu-rep",
+                    "dram_bytes_read": val("dram__bytes_read.sum"), "dram_bytes_write": val("dram__bytes_write.sum"),
+                    "duration_ms_under_ncu": float(V[H.index("gpu__time_duration.sum")].replace(",", "")) *
+                    {"ms": 1.0, "us": 1e-3, "ns": 1e-6}.get(U[H.index("gpu__time_duration.sum")].replace("second", "s")
+                                                          .replace("msecond", "ms"), 1.0)}
+    if out:
+        json.dump(out, open(os.path.join(OUT, "traffic_r01.json"), "w"), indent=1)
+
+
 if __name__ == "__main__":
     tag = sys.argv[1]
     os.makedirs(OUT, exist_ok=True)
     launches(tag)
-    for rep in sys.argv[2:]:
+    reps = [a for a in sys.argv[2:] if "=" not in a]
+    for rep in reps:
         report(rep, tag)
+    traffic(dict(a.split("=", 1) for a in sys.argv[2:] if "=" in a))
