@@ -8,6 +8,7 @@
 #include <string>
 #include <vector>
 #include <map>
+#include <functional>
 #include "../../include/fmmb.h"
 
 namespace fmmb {
@@ -199,6 +200,7 @@ struct fmmb_plan {
   fmmb::DevBuf<long long> cuts_dev;
   fmmb::DevBuf<double> chg_stage, chg_send;  // sharded call: padded all-gather of the charge slices
   long long chg_chunk = 0;
+  std::function<void()> hook_after_owned_m2m;  // set by laplace_execute around laplace_translations
   bool call_sharded = false;         // the current call is fmmb_plan_execute_sharded
   bool cuts_ready = false;
   bool xchg_off_ready = false;

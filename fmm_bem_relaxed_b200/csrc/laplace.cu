@@ -927,6 +927,7 @@ void laplace_translations(fmmb_plan* plan, cudaStream_t s) {
   if (owned_up) {
     // multi-GPU: M2M inside the owned subtrees, exchange, then the few boxes that straddle a cut
     m2m_batched(plan, s, /*owned_only=*/true);
+    if (plan->hook_after_owned_m2m) plan->hook_after_owned_m2m();   // laplace_execute: start the near field now
     exchange_multipoles(plan, s);
     if (T.n_strad_pairs) {
       T.strad_tmp.resize((size_t)T.n_strad_pairs * xstride(P));
@@ -1021,6 +1022,8 @@ void laplace_execute(fmmb_plan* plan, const double* d_charges, double* d_results
   FMMB_CUDA(cudaEventRecord(ev[1], s));
 
   // near field on the second stream: needs only the charges
+  const bool p2m_owned = T.nranks > 1 && plan->comm && P <= 8 && plan->opts.m2l_mode != 1 && plan->m2m_own.n_items > 0;
+  auto launch_p2p = [&]() {
   if (s2 != s) FMMB_CUDA(cudaStreamWaitEvent(s2, ev[1], 0));
   if (!plan->capturing) FMMB_CUDA(cudaEventRecord(ev[6], s2));
   const double ext = 1024.0 * std::max(T.cell[0], std::max(T.cell[1], T.cell[2]));
@@ -1055,6 +1058,12 @@ void laplace_execute(fmmb_plan* plan, const double* d_charges, double* d_results
         T.p2p_items.p, T.n_p2p_items, T.bbegin.p, T.bend.p, T.p2p_off.p, T.p2p_src.p, T.body.p, plan->res_near.p);
   ++plan->launches;
   FMMB_CUDA(cudaEventRecord(ev[7], s2));
+  };
+  // One GPU: the near field starts right away and fills the gaps of the latency-bound upward chain.  Sharded with
+  // an owned upward pass: it starts once the owned M2M sweep is enqueued (hook below), so that the short dependent
+  // kernels before the multipole exchange are not queued behind its blocks and it overlaps the exchange instead.
+  const bool defer_p2p = p2m_owned && s2 != s;
+  if (!defer_p2p) launch_p2p();
 
   // upward sweep
   if (!plan->capturing) FMMB_CUDA(cudaEventRecord(ev[12], s));
@@ -1065,14 +1074,21 @@ void laplace_execute(fmmb_plan* plan, const double* d_charges, double* d_results
     FMMB_CUDA(cudaFuncSetAttribute(p2m_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024));
     p2m_attr = true;
   }
-  const bool p2m_owned = T.nranks > 1 && plan->comm && P <= 8 && plan->opts.m2l_mode != 1 && plan->m2m_own.n_items > 0;
   const int* p2m_list = p2m_owned ? T.own_leaves.p : T.leaves.p;
   const int p2m_n = p2m_owned ? T.n_own_leaves : T.nleaves;
   p2m_kernel<<<nblk(p2m_n, p2m_warps), 32 * p2m_warps, p2m_sh, s>>>(
       p2m_list, p2m_n, T.bbegin.p, T.bend.p,
                                                                T.center.p, T.body.p, P, plan->M.p);
                        ++plan->launches;
-  laplace_translations(plan, s);
+  if (defer_p2p) {
+    plan->hook_after_owned_m2m = [&]() {
+      FMMB_CUDA(cudaEventRecord(ev[15], s));
+      FMMB_CUDA(cudaStreamWaitEvent(s2, ev[15], 0));
+      launch_p2p();
+    };
+  }
+  try { laplace_translations(plan, s); } catch (...) { plan->hook_after_owned_m2m = nullptr; throw; }
+  plan->hook_after_owned_m2m = nullptr;
   if (plan->opts.evaluator == FMMB_EVAL_TREECODE) {
     if (T.n_own_leaves)
       m2p_kernel<<<nblk(T.n_own_leaves, 4), 128, 4 * nc * sizeof(double2), s>>>(
