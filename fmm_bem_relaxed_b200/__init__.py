@@ -234,6 +234,18 @@ class FMM_plan:
         buf = (ctypes.c_ubyte * 128).from_buffer_copy(bytes(unique_id))
         capi.check(self._lib.fmmb_plan_comm_init(self._h, ctypes.cast(buf, ctypes.c_void_p)))
 
+    def peer_export(self):
+        """128-byte blob (IPC handle of the multipole array) for the peer-memory multipole exchange."""
+        buf = (ctypes.c_ubyte * 128)()
+        capi.check(self._lib.fmmb_plan_peer_export(self._h, ctypes.cast(buf, ctypes.c_void_p)))
+        return bytes(buf)
+
+    def peer_init(self, blobs):
+        """blobs: the peer_export() blobs of all ranks, concatenated in rank order."""
+        data = bytes(blobs)
+        buf = (ctypes.c_ubyte * len(data)).from_buffer_copy(data)
+        capi.check(self._lib.fmmb_plan_peer_init(self._h, ctypes.cast(buf, ctypes.c_void_p)))
+
     def set_option(self, name, value):
         capi.check(self._lib.fmmb_plan_set_option(self._h, name.encode(), int(value)))
 

@@ -146,6 +146,7 @@ void fmmb_plan_destroy(fmmb_plan* plan) {
   if (plan->stream) cudaStreamSynchronize(plan->stream);
   if (plan->stream2) cudaStreamSynchronize(plan->stream2);
   for (auto& kv : plan->graphs) cudaGraphExecDestroy(kv.second);
+  peer_close(plan);
   comm_destroy(plan);
   bem_free(plan->bem);
   stokes_free(plan->stokes);
@@ -341,6 +342,25 @@ int fmmb_plan_comm_init(fmmb_plan* plan, const unsigned char id[128]) {
   return guarded([&] {
     FMMB_CUDA(cudaSetDevice(plan->device));
     comm_init(plan, id);
+  });
+}
+
+int fmmb_plan_peer_export(fmmb_plan* plan, unsigned char blob[128]) {
+  if (!plan || !blob) { set_error("null argument"); return FMMB_ERR_INVALID; }
+  return guarded([&] {
+    FMMB_CUDA(cudaSetDevice(plan->device));
+    peer_export(plan, blob);
+  });
+}
+
+int fmmb_plan_peer_init(fmmb_plan* plan, const unsigned char* blobs) {
+  if (!plan || !blobs) { set_error("null argument"); return FMMB_ERR_INVALID; }
+  return guarded([&] {
+    FMMB_CUDA(cudaSetDevice(plan->device));
+    for (auto& kv : plan->graphs) cudaGraphExecDestroy(kv.second);
+    plan->graphs.clear();
+    plan->graph_seen.clear();
+    peer_init(plan, blobs);
   });
 }
 

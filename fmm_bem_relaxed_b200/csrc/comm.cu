@@ -198,4 +198,165 @@ void exchange_multipoles(fmmb_plan* plan, cudaStream_t s) {
   plan->launches += 2;
 }
 
+
+// ---- multipole exchange through peer memory (NVLink P2P stores, no NCCL, no staging) -----------------------------
+// Every rank exports the allocation that holds its multipole array (cudaIpcMemHandle) and opens the peers'.  After
+// its owned upward pass a rank PUSHES the multipoles of the boxes inside its range straight into every peer's
+// array, 512-byte rows over NVLink, from the kernel that reads them (one launch instead of pack / ncclAllGather /
+// unpack).  Synchronisation is two monotonic flag vectors per rank that the peers write with release stores at
+// system scope (they live in the tail of the exported allocation):
+//   pushed[q] = e   rank q's multipoles of matvec e have landed here     (waited on before M2L reads them)
+//   rdone[q]  = e   rank q has finished reading ITS array in matvec e     (waited on before pushing matvec e + 1,
+//                                                                          so nobody's array changes under a reader)
+// The matvec counter lives in device memory, so a captured CUDA graph replays correctly.
+namespace {
+constexpr int kPeerMaxRanks = 64;
+constexpr int kPeerTail = 4 * kPeerMaxRanks;       // doubles reserved behind the multipoles: pushed[64], rdone[64]
+
+struct PeerBlob {                                   // what travels between the ranks (128 bytes)
+  cudaIpcMemHandle_t mem;                           // 64 bytes
+  long long doubles;                                // size of the multipole part, for a consistency check
+  int rank, device;
+  char pad[128 - sizeof(cudaIpcMemHandle_t) - sizeof(long long) - 2 * sizeof(int)];
+};
+static_assert(sizeof(PeerBlob) == 128, "fmmb.h promises a 128-byte blob");
+
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+__global__ void __launch_bounds__(64)
+peer_push_kernel(const int* __restrict__ list, int count, int xs, const double* __restrict__ M,
+                 double* const* __restrict__ peerM, unsigned long long* const* __restrict__ peer_flags, int nranks, int me,
+                 const unsigned long long* __restrict__ local_flags, const unsigned long long* __restrict__ epoch,
+                 unsigned int* __restrict__ counter) {
+  __shared__ int s_last;
+  const unsigned long long e = *epoch;              // matvecs completed so far; this one is e + 1
+  // nobody may still be reading the previous multipoles out of the arrays this block is about to write
+  if ((int)threadIdx.x < nranks)
+    while (ld_acquire_sys(local_flags + kPeerMaxRanks + threadIdx.x) < e) {}
+  __syncthreads();
+  const int i = blockIdx.x;
+  if (i < count) {
+    const size_t o = (size_t)list[i] * xs;
+    for (int q = 0; q < nranks; ++q) {
+      if (q == me) continue;
+      double* dst = peerM[q] + o;
+      for (int k = threadIdx.x; k < xs; k += blockDim.x) dst[k] = M[o + k];
+    }
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = atomicAdd(counter, 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (s_last) {                                     // every block's rows are out: tell the peers (and myself)
+    __threadfence_system();
+    if ((int)threadIdx.x < nranks) st_release_sys(peer_flags[threadIdx.x] + me, e + 1);
+    if (threadIdx.x == 0) *counter = 0;
+  }
+}
+__global__ void peer_wait_kernel(const unsigned long long* __restrict__ local_flags, unsigned long long* __restrict__ epoch,
+                                 int nranks) {
+  const unsigned long long e = *epoch + 1;
+  if ((int)threadIdx.x < nranks)
+    while (ld_acquire_sys(local_flags + threadIdx.x) < e) {}
+  __syncthreads();
+  if (threadIdx.x == 0) *epoch = e;
+}
+__global__ void peer_read_done_kernel(unsigned long long* const* __restrict__ peer_flags, int nranks, int me,
+                                      const unsigned long long* __restrict__ epoch) {
+  if ((int)threadIdx.x < nranks) {
+    __threadfence_system();
+    st_release_sys(peer_flags[threadIdx.x] + kPeerMaxRanks + me, *epoch);
+  }
+}
+}  // namespace
+
+void peer_export(fmmb_plan* plan, unsigned char* blob) {
+  Tree& T = plan->tree;
+  if (T.nranks <= 1) throw StatusError{FMMB_ERR_INVALID, "plan was not created with nranks > 1"};
+  if (T.nranks > kPeerMaxRanks) throw StatusError{FMMB_ERR_UNSUPPORTED, "peer exchange is built for up to 64 ranks"};
+  if (plan->kind != FMMB_LAPLACE_SPHERICAL) throw StatusError{FMMB_ERR_UNSUPPORTED, "peer exchange: LaplaceSpherical plans"};
+  cudaStream_t s = plan->stream;
+  // one allocation for good: multipoles at the largest batched order (P = 8: 64 doubles per box) + the flag tail
+  const size_t md = (size_t)T.nboxes * 64;
+  if (!plan->peer_alloc) {
+    FMMB_CUDA(cudaStreamSynchronize(s));
+    plan->M.release();
+    plan->M.resize(md + kPeerTail);
+    plan->M.zero(s);
+    plan->M.n = 0;
+    plan->p_alloc = 0;
+    plan->peer_alloc = true;
+    plan->peer_state.resize(2);                       // [0] matvec counter, [1] block counter of the push kernel
+    plan->peer_state.zero(s);
+    FMMB_CUDA(cudaStreamSynchronize(s));
+  }
+  PeerBlob b;
+  std::memset(&b, 0, sizeof b);
+  FMMB_CUDA(cudaIpcGetMemHandle(&b.mem, plan->M.p));
+  b.doubles = (long long)md;
+  b.rank = T.rank;
+  b.device = plan->device;
+  std::memcpy(blob, &b, sizeof b);
+}
+
+void peer_init(fmmb_plan* plan, const unsigned char* blobs) {
+  Tree& T = plan->tree;
+  if (!plan->peer_alloc) throw StatusError{FMMB_ERR_INVALID, "call fmmb_plan_peer_export first"};
+  if (plan->peer_ready) return;
+  const size_t md = (size_t)T.nboxes * 64;
+  std::vector<double*> pm(T.nranks);
+  std::vector<unsigned long long*> pf(T.nranks);
+  for (int q = 0; q < T.nranks; ++q) {
+    PeerBlob b;
+    std::memcpy(&b, blobs + 128 * (size_t)q, sizeof b);
+    if (b.rank != q || b.doubles != (long long)md)
+      throw StatusError{FMMB_ERR_INVALID, "peer blobs must be ordered by rank and come from plans on the same tree"};
+    void* p = plan->M.p;
+    if (q != T.rank) {
+      FMMB_CUDA(cudaIpcOpenMemHandle(&p, b.mem, cudaIpcMemLazyEnablePeerAccess));
+      plan->peer_opened.push_back(p);
+    }
+    pm[q] = (double*)p;
+    pf[q] = (unsigned long long*)((double*)p + md);
+  }
+  plan->peer_M.from_host(pm.data(), pm.size(), plan->stream);
+  plan->peer_flags.from_host(pf.data(), pf.size(), plan->stream);
+  FMMB_CUDA(cudaStreamSynchronize(plan->stream));
+  plan->peer_ready = true;
+}
+
+void peer_close(fmmb_plan* plan) {
+  for (void* p : plan->peer_opened) cudaIpcCloseMemHandle(p);
+  plan->peer_opened.clear();
+  plan->peer_ready = false;
+}
+
+void exchange_multipoles_peer(fmmb_plan* plan, cudaStream_t s) {
+  Tree& T = plan->tree;
+  const int P = plan->p, xs = (P * P + 1) & ~1;
+  const int mine = T.xchg_off[T.rank + 1] - T.xchg_off[T.rank];
+  unsigned long long* local_flags = (unsigned long long*)(plan->M.p + (size_t)T.nboxes * 64);
+  unsigned long long* st = plan->peer_state.p;
+  peer_push_kernel<<<std::max(mine, 1), 64, 0, s>>>(T.xchg_list.p + T.xchg_off[T.rank], mine, xs, plan->M.p, plan->peer_M.p,
+                                                   plan->peer_flags.p, T.nranks, T.rank, local_flags, st,
+                                                   (unsigned int*)(st + 1));
+  peer_wait_kernel<<<1, 64, 0, s>>>(local_flags, st, T.nranks);
+  FMMB_CUDA(cudaGetLastError());
+  plan->launches += 2;
+}
+
+void peer_read_done(fmmb_plan* plan, cudaStream_t s) {
+  Tree& T = plan->tree;
+  peer_read_done_kernel<<<1, 64, 0, s>>>(plan->peer_flags.p, T.nranks, T.rank, plan->peer_state.p);
+  FMMB_CUDA(cudaGetLastError());
+  ++plan->launches;
+}
+
 }  // namespace fmmb

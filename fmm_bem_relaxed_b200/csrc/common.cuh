@@ -200,6 +200,12 @@ struct fmmb_plan {
   fmmb::DevBuf<long long> cuts_dev;
   fmmb::DevBuf<double> chg_stage, chg_send;  // sharded call: padded all-gather of the charge slices
   long long chg_chunk = 0;
+  // multipole exchange through peer memory (comm.cu): the M allocation is exported once and never reallocated
+  bool peer_alloc = false, peer_ready = false;
+  fmmb::DevBuf<double*> peer_M;                       // per rank: base of its multipole array (own: local pointer)
+  fmmb::DevBuf<unsigned long long*> peer_flags;       // per rank: its flag tail
+  fmmb::DevBuf<unsigned long long> peer_state;        // [0] matvec counter, [1] push-kernel block counter
+  std::vector<void*> peer_opened;
   std::function<void()> hook_after_owned_m2m;  // set by laplace_execute around laplace_translations
   bool call_sharded = false;         // the current call is fmmb_plan_execute_sharded
   bool cuts_ready = false;
@@ -243,6 +249,11 @@ void allgather_results(fmmb_plan* plan, cudaStream_t s);
 void finish_results(fmmb_plan* plan, const double* near, const double* far, int rd, double* d_results, cudaStream_t s);
 void allgather_charges(fmmb_plan* plan, const double* d_own, cudaStream_t s);
 void exchange_multipoles(fmmb_plan* plan, cudaStream_t s);
+void peer_export(fmmb_plan* plan, unsigned char* blob);
+void peer_init(fmmb_plan* plan, const unsigned char* blobs);
+void peer_close(fmmb_plan* plan);
+void exchange_multipoles_peer(fmmb_plan* plan, cudaStream_t s);
+void peer_read_done(fmmb_plan* plan, cudaStream_t s);
 // laplace.cu
 void laplace_init_tables(fmmb_plan* plan);
 void laplace_execute(fmmb_plan* plan, const double* d_charges, double* d_results);

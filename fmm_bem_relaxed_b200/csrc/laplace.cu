@@ -928,7 +928,8 @@ void laplace_translations(fmmb_plan* plan, cudaStream_t s) {
     // multi-GPU: M2M inside the owned subtrees, exchange, then the few boxes that straddle a cut
     m2m_batched(plan, s, /*owned_only=*/true);
     if (plan->hook_after_owned_m2m) plan->hook_after_owned_m2m();   // laplace_execute: start the near field now
-    exchange_multipoles(plan, s);
+    if (plan->peer_ready && plan->kind == FMMB_LAPLACE_SPHERICAL) exchange_multipoles_peer(plan, s);
+    else exchange_multipoles(plan, s);
     if (T.n_strad_pairs) {
       T.strad_tmp.resize((size_t)T.n_strad_pairs * xstride(P));
       m2m_direct_kernel<<<T.n_strad_pairs, 64, sh_mm, s>>>(T.strad_pair_box.p, T.strad_box.p, T.strad_desc.p, T.center.p,
@@ -986,8 +987,10 @@ void laplace_prepare_expansions(fmmb_plan* plan) {
   plan->M.resize((size_t)plan->tree.nboxes * xs);
   plan->L.resize((size_t)plan->tree.nboxes * xs);
   if (plan->p_alloc != P) {
-    // the padding double of odd-sized expansions is read (times zero) by the GEMM: keep it finite
-    plan->M.zero(plan->stream);
+    // the padding double of odd-sized expansions is read (times zero) by the GEMM: keep it finite.
+    // An exported (peer) multipole array was zeroed once and is never cleared again: a faster peer may already be
+    // writing the next matvec's rows into it.
+    if (!plan->peer_alloc) plan->M.zero(plan->stream);
     plan->L.zero(plan->stream);
     plan->p_alloc = P;
   }
@@ -1100,6 +1103,8 @@ void laplace_execute(fmmb_plan* plan, const double* d_charges, double* d_results
         plan->res_far.p);
   }
   ++plan->launches;
+  // peer exchange: this rank no longer reads its multipole array -> peers may push the next matvec's rows
+  if (plan->peer_ready && p2m_owned) peer_read_done(plan, s);
   if (!plan->capturing) FMMB_CUDA(cudaEventRecord(ev[4], s));
 
   if (s2 != s) FMMB_CUDA(cudaStreamWaitEvent(s, ev[7], 0));

@@ -186,6 +186,18 @@ int fmmb_plan_set_option(fmmb_plan* plan, const char* name, int64_t value);
 int fmmb_comm_unique_id(unsigned char id[128]);
 int fmmb_plan_comm_init(fmmb_plan* plan, const unsigned char id[128]);
 
+/* Multipole exchange through peer memory instead of NCCL (optional, LaplaceSpherical plans, GPUs of one node with
+ * NVLink / P2P access): after the owned upward pass every rank stores the multipoles of its boxes straight into
+ * the peers' arrays from the producing side (one kernel, no pack / all-gather / unpack), ordered by flag vectors
+ * that the peers write with system-scope release stores.
+ *   every rank:  fmmb_plan_peer_export(plan, blob)            128 bytes (cudaIpcMemHandle of the multipole array)
+ *   caller:      all-gather the blobs, ordered by rank        (any transport; bench.py uses torch.distributed)
+ *   every rank:  fmmb_plan_peer_init(plan, blobs)             nranks * 128 bytes
+ * Call after fmmb_plan_comm_init (charges / results still travel over NCCL) and before the first matvec that
+ * should use it.  All ranks must run the same sequence of matvecs (as with any collective). */
+int fmmb_plan_peer_export(fmmb_plan* plan, unsigned char blob[128]);
+int fmmb_plan_peer_init(fmmb_plan* plan, const unsigned char* blobs);
+
 /* Host-only helper (no GPU needed): cut n non-negative work weights into nranks contiguous ranges of
  * nearly equal sum.  cuts has nranks+1 entries, cuts[0] = 0, cuts[nranks] = n; rank r owns
  * [cuts[r], cuts[r+1]). */
