@@ -250,6 +250,12 @@ def bench_ours(args, rank, world, local_rank):
             idt.copy_(torch.frombuffer(bytearray(F.comm_unique_id()), dtype=torch.uint8))
         dist.broadcast(idt, 0)
         plan.comm_init(bytes(idt.cpu().numpy().tobytes()))
+        if not args.no_peer:
+            # multipoles travel through peer memory (NVLink P2P stores from the producing rank) instead of NCCL
+            mine = torch.frombuffer(bytearray(plan.peer_export()), dtype=torch.uint8).cuda()
+            blobs = [torch.zeros(128, dtype=torch.uint8, device="cuda") for _ in range(world)]
+            dist.all_gather(blobs, mine)
+            plan.peer_init(b"".join(bytes(t.cpu().numpy().tobytes()) for t in blobs))
     info = plan.info()
     n = info.n_bodies
 
@@ -437,8 +443,10 @@ def bench_ours(args, rank, world, local_rank):
         "config": dict(workload(args), l2="256 MiB memset between steps, outside the per-step event pairs",
                        parallelism="1 GPU" if world == 1 else
                        ("target leaves in %d Morton-contiguous ranges of equal estimated work; per step: NCCL "
-                        "all-gather of the charge slices, owned upward pass, NCCL all-gather of the multipoles; "
-                        "results stay sharded by target (fmmb_plan_execute_sharded)" % world) if sharded else
+                        "all-gather of the charge slices, owned upward pass, multipoles %s; "
+                        "results stay sharded by target (fmmb_plan_execute_sharded)"
+                        % (world, "all-gathered over NCCL" if args.no_peer else
+                           "pushed into the peers' arrays over NVLink (P2P stores + flag vectors)")) if sharded else
                        ("target leaves in %d Morton-contiguous ranges of equal estimated work; charges replicated, "
                         "owned upward pass + NCCL all-gather of multipoles, NCCL all-gather of the result slices"
                         % world),
@@ -471,6 +479,8 @@ def main():
     ap.add_argument("--theta", type=float, default=0.5)
     ap.add_argument("--ncrit", type=int, default=64)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-peer", action="store_true",
+                    help="N > 1: exchange the multipoles with an NCCL all-gather instead of peer-memory stores")
     ap.add_argument("--replicated-results", action="store_true",
                     help="N > 1: time fmmb_plan_execute_device (full result vector all-gathered to every rank) "
                          "instead of the sharded call")

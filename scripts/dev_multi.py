@@ -28,7 +28,19 @@ b0, b1 = info.own_body_begin, info.own_body_end
 perm = plan.tree()["perm"].astype(np.int64)
 d_q_own = torch.from_numpy(np.ascontiguousarray(q[perm[b0:b1]])).cuda()
 d_res_own = torch.empty((b1 - b0, 4), dtype=torch.float64, device="cuda")
-for mode in sys.argv[3:] or ["full", "sharded"]:
+def enable_peer():
+    mine = torch.frombuffer(bytearray(plan.peer_export()), dtype=torch.uint8).cuda()
+    allb = [torch.zeros(128, dtype=torch.uint8, device="cuda") for _ in range(world)]
+    dist.all_gather(allb, mine)
+    plan.peer_init(b"".join(bytes(t.cpu().numpy().tobytes()) for t in allb))
+
+
+for mode in sys.argv[3:] or ["full", "sharded", "sharded+peer"]:
+    if mode.endswith("+peer"):
+        enable_peer()
+        if rank == 0:
+            print("peer-memory multipole exchange enabled", flush=True)
+
     def run():
         if mode == "full":
             plan.execute_device(d_q.data_ptr(), d_res.data_ptr())

@@ -36,6 +36,22 @@ for n, P in ((200000, 8), (60000, 5), (30000, 7)):
         print("rank %d: execute %d done" % (rank, rep), flush=True)
         err = O.rel_l2(res, ref)
         ok &= err < 1e-12
+    # the same matvec with the multipoles pushed through peer memory (NVLink P2P stores) instead of NCCL, including
+    # an order change and back (GMRES relaxation) and the captured-graph replay
+    mine = torch.frombuffer(bytearray(plan.peer_export()), dtype=torch.uint8).cuda()
+    allb = [torch.zeros(128, dtype=torch.uint8, device="cuda") for _ in range(world)]
+    dist.all_gather(allb, mine)
+    plan.peer_init(b"".join(bytes(t.cpu().numpy().tobytes()) for t in allb))
+    for rep in range(4):
+        perr = O.rel_l2(plan.execute(q), ref)
+        ok &= perr < 1e-12
+    plan.kernel().set_p(max(1, P - 2))
+    low = plan.execute(q)
+    plan.kernel().set_p(P)
+    for rep in range(3):
+        perr = max(perr, O.rel_l2(plan.execute(q), ref))
+    ok &= perr < 1e-12 and O.rel_l2(low, ref) < 1e-2
+    print("rank %d: peer-memory exchange rel-L2 vs single GPU %.2e" % (rank, perr), flush=True)
     i = plan.info()
     own = (i.own_body_begin, i.own_body_end)
     plan.close()          # teardown (ncclCommDestroy) at the same point on every rank
