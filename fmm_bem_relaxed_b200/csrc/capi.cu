@@ -224,7 +224,10 @@ int fmmb_plan_execute_sharded(fmmb_plan* plan, const double* charges_own_dev, do
     set_error("fmmb_plan_execute_sharded is built for FMMB_LAPLACE_SPHERICAL plans");
     return FMMB_ERR_UNSUPPORTED;
   }
-  if (plan->tree.nranks > 1 && !plan->comm) { set_error("call fmmb_plan_comm_init first"); return FMMB_ERR_INVALID; }
+  if (plan->tree.nranks > 1 && !plan->comm && !plan->peer_ready) {
+    set_error("call fmmb_plan_comm_init or fmmb_plan_peer_init first");
+    return FMMB_ERR_INVALID;
+  }
   return guarded([&] {
     FMMB_CUDA(cudaSetDevice(plan->device));
     plan->call_sharded = true;

@@ -205,13 +205,16 @@ void exchange_multipoles(fmmb_plan* plan, cudaStream_t s) {
 // array, 512-byte rows over NVLink, from the kernel that reads them (one launch instead of pack / ncclAllGather /
 // unpack).  Synchronisation is two monotonic flag vectors per rank that the peers write with release stores at
 // system scope (they live in the tail of the exported allocation):
-//   pushed[q] = e   rank q's multipoles of matvec e have landed here     (waited on before M2L reads them)
-//   rdone[q]  = e   rank q has finished reading ITS array in matvec e     (waited on before pushing matvec e + 1,
-//                                                                          so nobody's array changes under a reader)
-// The matvec counter lives in device memory, so a captured CUDA graph replays correctly.
+//   pushed[q]  = e   rank q's multipoles of matvec e have landed here     (waited on before M2L reads them)
+//   rdone[q]   = e   rank q has finished reading ITS array in matvec e     (waited on before pushing matvec e + 1,
+//                                                                           so nobody's array changes under a reader)
+//   qpushed[q] = e   rank q's charge slice of matvec e has landed here     (sharded call; waited on before it is used)
+// The same allocation carries a tree-ordered charge vector that the peers fill in the sharded call, which replaces
+// the NCCL all-gather of the charge slices.  The matvec counter lives in device memory (advanced by the last
+// kernel of every matvec), so a captured CUDA graph replays correctly.
 namespace {
 constexpr int kPeerMaxRanks = 64;
-constexpr int kPeerTail = 4 * kPeerMaxRanks;       // doubles reserved behind the multipoles: pushed[64], rdone[64]
+constexpr int kPeerTail = 4 * kPeerMaxRanks;       // doubles behind the multipoles: pushed[64], rdone[64], qpushed[64]
 
 struct PeerBlob {                                   // what travels between the ranks (128 bytes)
   cudaIpcMemHandle_t mem;                           // 64 bytes
@@ -260,20 +263,54 @@ peer_push_kernel(const int* __restrict__ list, int count, int xs, const double* 
     if (threadIdx.x == 0) *counter = 0;
   }
 }
-__global__ void peer_wait_kernel(const unsigned long long* __restrict__ local_flags, unsigned long long* __restrict__ epoch,
-                                 int nranks) {
+__global__ void peer_wait_kernel(const unsigned long long* __restrict__ local_flags,
+                                 const unsigned long long* __restrict__ epoch, int nranks) {
   const unsigned long long e = *epoch + 1;
   if ((int)threadIdx.x < nranks)
     while (ld_acquire_sys(local_flags + threadIdx.x) < e) {}
+}
+// last kernel of a matvec: this rank no longer reads its multipole array; the matvec counter advances
+__global__ void peer_read_done_kernel(unsigned long long* const* __restrict__ peer_flags, int nranks, int me,
+                                      unsigned long long* __restrict__ epoch) {
+  const unsigned long long e = *epoch + 1;
+  if ((int)threadIdx.x < nranks) {
+    __threadfence_system();
+    st_release_sys(peer_flags[threadIdx.x] + kPeerMaxRanks + me, e);
+  }
   __syncthreads();
   if (threadIdx.x == 0) *epoch = e;
 }
-__global__ void peer_read_done_kernel(unsigned long long* const* __restrict__ peer_flags, int nranks, int me,
-                                      const unsigned long long* __restrict__ epoch) {
-  if ((int)threadIdx.x < nranks) {
-    __threadfence_system();
-    st_release_sys(peer_flags[threadIdx.x] + kPeerMaxRanks + me, *epoch);
+// sharded call: my charge slice (tree order) goes straight into every rank's tree-ordered charge vector
+__global__ void __launch_bounds__(256)
+peer_push_charges_kernel(const double* __restrict__ own, long long b0, long long len, double* const* __restrict__ peerM,
+                         size_t q_off, unsigned long long* const* __restrict__ peer_flags, int nranks, int me,
+                         const unsigned long long* __restrict__ epoch, unsigned int* __restrict__ counter) {
+  __shared__ int s_last;
+  const unsigned long long e = *epoch;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < len; i += (long long)gridDim.x * blockDim.x) {
+    const double v = own[i];
+    for (int q = 0; q < nranks; ++q) peerM[q][q_off + b0 + i] = v;
   }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = atomicAdd(counter, 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (s_last) {
+    __threadfence_system();
+    if ((int)threadIdx.x < nranks) st_release_sys(peer_flags[threadIdx.x] + 2 * kPeerMaxRanks + me, e + 1);
+    if (threadIdx.x == 0) *counter = 0;
+  }
+}
+// ... and, once every rank's slice has landed, into the charge slot of the bodies
+__global__ void __launch_bounds__(256)
+peer_place_charges_kernel(const unsigned long long* __restrict__ local_flags, const unsigned long long* __restrict__ epoch,
+                          int nranks, const double* __restrict__ qtree, long long n, double4* __restrict__ body) {
+  const unsigned long long e = *epoch + 1;
+  if ((int)threadIdx.x < nranks)
+    while (ld_acquire_sys(local_flags + 2 * kPeerMaxRanks + threadIdx.x) < e) {}
+  __syncthreads();
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    body[i].w = qtree[i];
 }
 }  // namespace
 
@@ -288,12 +325,12 @@ void peer_export(fmmb_plan* plan, unsigned char* blob) {
   if (!plan->peer_alloc) {
     FMMB_CUDA(cudaStreamSynchronize(s));
     plan->M.release();
-    plan->M.resize(md + kPeerTail);
+    plan->M.resize(md + kPeerTail + (size_t)T.n);     // multipoles | flag vectors | tree-ordered charges
     plan->M.zero(s);
     plan->M.n = 0;
     plan->p_alloc = 0;
     plan->peer_alloc = true;
-    plan->peer_state.resize(2);                       // [0] matvec counter, [1] block counter of the push kernel
+    plan->peer_state.resize(3);                       // [0] matvec counter, [1], [2] block counters of the push kernels
     plan->peer_state.zero(s);
     FMMB_CUDA(cudaStreamSynchronize(s));
   }
@@ -348,6 +385,21 @@ void exchange_multipoles_peer(fmmb_plan* plan, cudaStream_t s) {
                                                    plan->peer_flags.p, T.nranks, T.rank, local_flags, st,
                                                    (unsigned int*)(st + 1));
   peer_wait_kernel<<<1, 64, 0, s>>>(local_flags, st, T.nranks);
+  FMMB_CUDA(cudaGetLastError());
+  plan->launches += 2;
+}
+
+// sharded call: d_own = the charges of this rank's bodies (tree order) -> body[].w on every rank
+void peer_exchange_charges(fmmb_plan* plan, const double* d_own, cudaStream_t s) {
+  Tree& T = plan->tree;
+  const size_t md = (size_t)T.nboxes * 64;
+  unsigned long long* local_flags = (unsigned long long*)(plan->M.p + md);
+  unsigned long long* st = plan->peer_state.p;
+  const long long own = T.own_b1 - T.own_b0;
+  const int blocks = (int)std::max<long long>(1, std::min<long long>(296, (own + 255) / 256));
+  peer_push_charges_kernel<<<blocks, 256, 0, s>>>(d_own, T.own_b0, own, plan->peer_M.p, md + kPeerTail, plan->peer_flags.p,
+                                                 T.nranks, T.rank, st, (unsigned int*)(st + 2));
+  peer_place_charges_kernel<<<296, 256, 0, s>>>(local_flags, st, T.nranks, plan->M.p + md + kPeerTail, T.n, T.body.p);
   FMMB_CUDA(cudaGetLastError());
   plan->launches += 2;
 }

@@ -253,6 +253,7 @@ void peer_export(fmmb_plan* plan, unsigned char* blob);
 void peer_init(fmmb_plan* plan, const unsigned char* blobs);
 void peer_close(fmmb_plan* plan);
 void exchange_multipoles_peer(fmmb_plan* plan, cudaStream_t s);
+void peer_exchange_charges(fmmb_plan* plan, const double* d_own, cudaStream_t s);
 void peer_read_done(fmmb_plan* plan, cudaStream_t s);
 // laplace.cu
 void laplace_init_tables(fmmb_plan* plan);

@@ -923,7 +923,8 @@ void laplace_translations(fmmb_plan* plan, cudaStream_t s) {
   const double* C = m2l_coeffs(plan, P);
   cudaEvent_t* ev = plan->ev;
   size_t sh_mm = (size_t)(pp + nc) * sizeof(double2);
-  const bool owned_up = T.nranks > 1 && plan->comm && P <= 8 && plan->opts.m2l_mode != 1 && plan->m2m_own.n_items > 0;
+  const bool owned_up = T.nranks > 1 && (plan->comm || plan->peer_ready) && P <= 8 && plan->opts.m2l_mode != 1 &&
+                        plan->m2m_own.n_items > 0;
   if (owned_up) {
     // multi-GPU: M2M inside the owned subtrees, exchange, then the few boxes that straddle a cut
     m2m_batched(plan, s, /*owned_only=*/true);
@@ -1011,7 +1012,9 @@ void laplace_execute(fmmb_plan* plan, const double* d_charges, double* d_results
   if (!plan->capturing) FMMB_CUDA(cudaEventRecord(ev[0], s));
   if (plan->call_sharded) {
     // charges = this rank's slice in tree order: all-gather the slices (NCCL), no permutation
-    if (T.nranks > 1 && plan->comm) {
+    if (T.nranks > 1 && plan->peer_ready) {
+      peer_exchange_charges(plan, d_charges, s);       // slices written straight into the peers (NVLink), no NCCL
+    } else if (T.nranks > 1 && plan->comm) {
       allgather_charges(plan, d_charges, s);
       dim3 grid(64, T.nranks);
       place_charges<<<grid, 256, 0, s>>>(plan->chg_stage.p, plan->cuts_dev.p, T.nranks, plan->chg_chunk, T.body.p);
@@ -1025,7 +1028,8 @@ void laplace_execute(fmmb_plan* plan, const double* d_charges, double* d_results
   FMMB_CUDA(cudaEventRecord(ev[1], s));
 
   // near field on the second stream: needs only the charges
-  const bool p2m_owned = T.nranks > 1 && plan->comm && P <= 8 && plan->opts.m2l_mode != 1 && plan->m2m_own.n_items > 0;
+  const bool p2m_owned = T.nranks > 1 && (plan->comm || plan->peer_ready) && P <= 8 && plan->opts.m2l_mode != 1 &&
+                         plan->m2m_own.n_items > 0;
   auto launch_p2p = [&]() {
   if (s2 != s) FMMB_CUDA(cudaStreamWaitEvent(s2, ev[1], 0));
   if (!plan->capturing) FMMB_CUDA(cudaEventRecord(ev[6], s2));
@@ -1104,7 +1108,7 @@ void laplace_execute(fmmb_plan* plan, const double* d_charges, double* d_results
   }
   ++plan->launches;
   // peer exchange: this rank no longer reads its multipole array -> peers may push the next matvec's rows
-  if (plan->peer_ready && p2m_owned) peer_read_done(plan, s);
+  if (plan->peer_ready) peer_read_done(plan, s);
   if (!plan->capturing) FMMB_CUDA(cudaEventRecord(ev[4], s));
 
   if (s2 != s) FMMB_CUDA(cudaStreamWaitEvent(s, ev[7], 0));

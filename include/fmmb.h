@@ -193,8 +193,10 @@ int fmmb_plan_comm_init(fmmb_plan* plan, const unsigned char id[128]);
  *   every rank:  fmmb_plan_peer_export(plan, blob)            128 bytes (cudaIpcMemHandle of the multipole array)
  *   caller:      all-gather the blobs, ordered by rank        (any transport; bench.py uses torch.distributed)
  *   every rank:  fmmb_plan_peer_init(plan, blobs)             nranks * 128 bytes
- * Call after fmmb_plan_comm_init (charges / results still travel over NCCL) and before the first matvec that
- * should use it.  All ranks must run the same sequence of matvecs (as with any collective). */
+ * With it, fmmb_plan_execute_sharded needs no NCCL communicator at all: the charge slices are stored into the
+ * peers' tree-ordered charge vectors the same way.  (fmmb_plan_execute[_device] still all-gathers the result slices
+ * over NCCL and needs fmmb_plan_comm_init.)  All ranks must run the same sequence of matvecs (as with any
+ * collective). */
 int fmmb_plan_peer_export(fmmb_plan* plan, unsigned char blob[128]);
 int fmmb_plan_peer_init(fmmb_plan* plan, const unsigned char* blobs);
 

@@ -64,10 +64,13 @@ for mode in sys.argv[3:] or ["full", "sharded", "sharded+peer"]:
     for _ in range(4):
         run()
     plan.sync(); dist.barrier(); torch.cuda.synchronize()
-    if mode != "full":
-        full = d_res.cpu().numpy()
-        err = np.abs(d_res_own.cpu().numpy() - full[perm[b0:b1]]).max() / np.abs(full).max()
-        print("rank %d sharded vs full slice: max rel diff %.2e" % (rank, err), flush=True)
+    if mode == "full":
+        ref_own = d_res.cpu().numpy()[perm[b0:b1]]
+    elif "ref_own" not in globals():
+        ref_own = d_res_own.cpu().numpy().copy()
+    else:
+        err = np.abs(d_res_own.cpu().numpy() - ref_own).max() / np.abs(ref_own).max()
+        print("rank %d %s vs first mode: max rel diff %.2e" % (rank, mode, err), flush=True)
     t0 = time.perf_counter()
     for _ in range(50):
         run()
