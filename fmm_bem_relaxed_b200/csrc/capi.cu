@@ -104,6 +104,7 @@ int fmmb_plan_create(const fmmb_kernel_desc* kernel, const fmmb_sources* sources
     FMMB_CUDA(cudaGetDevice(&plan->device));
     plan->opts = opts;
     plan->kind = kernel->kind;
+    if (const char* g = std::getenv("FMMB_USE_GRAPH")) plan->use_graph = std::atoi(g) != 0;   // same as set_option
     plan->p = kernel->p;
     // the far-field chain (many short dependent kernels and the collectives) outranks the near-field kernel
     // that runs beside it: its blocks take the SM slots first whenever both have work

@@ -155,3 +155,15 @@ def test_partitioned_plans_other_kernels(world):
     verts = O.unit_sphere(5)                                   # 2048 panels
     _tile_check(lambda: F.LaplaceSphericalBEM(6, 4), F.Panels(verts), rng.random(len(verts)), world)
     _tile_check(lambda: F.LaplaceSphericalBEM(6, 4), F.Panels(verts, 1), rng.random(len(verts)), world)
+
+
+@pytest.mark.gpu
+def test_two_ranks_on_one_gpu_peer_memory_exchange():
+    """Two processes on ONE device: sharded matvec with the peer-memory exchange only (IPC-exported multipole /
+    charge arrays, P2P stores, system-scope flag vectors; no NCCL).  scripts/peer_one_gpu.py spawns the ranks and
+    compares every rank's slice with the single-GPU result (including an order change and the graph replay)."""
+    import subprocess
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "peer_one_gpu.py"), "30000", "6"],
+                         capture_output=True, text=True, timeout=240)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    assert "PEER_ONE_GPU" in out.stdout
