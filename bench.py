@@ -116,11 +116,11 @@ def bench_gmres_c2():
     import tempfile
     args = ["-recursions", "7", "-p", "8", "-k", "4", "-ncrit", "64", "-theta", "0.5", "-solver_tol", "1e-6"]
 
-    def run(exe, env=None):
+    def run(exe, env=None, extra=()):
         if not os.path.exists(exe):
             return None
         with tempfile.TemporaryDirectory() as tmp:     # the reference writes test.vert / test.face into cwd
-            out = subprocess.check_output([exe] + args, env=env, cwd=tmp).decode()
+            out = subprocess.check_output([exe] + args + list(extra), env=env, cwd=tmp).decode()
         m = re.search(r"Final residual: ([0-9.eE+-]+), after (\d+) iterations", out)
         return {"solve_s": float(re.search(r"solve : ([0-9.eE+-]+)s", out).group(1)),
                 "setup_s": float(re.search(r"setup : ([0-9.eE+-]+)s", out).group(1)),
@@ -133,11 +133,16 @@ def bench_gmres_c2():
     if ours is None:
         return None
     ours = min((run(exe, env) for _ in range(3)), key=lambda r: r["solve_s"])   # first call pays CUDA start-up
+    dev = min((run(exe, env, ("-device_gmres",)) for _ in range(3)), key=lambda r: r["solve_s"])
     threads = os.cpu_count() or 1
     ref = run(os.path.join(ROOT, "oracle", "_ref", "LaplaceBEM"), dict(os.environ, OMP_NUM_THREADS=str(threads)))
     out = {"config": "LaplaceBEM sphere 32768 panels, K=4, relaxed GMRES to 1e-6, p<=8 (BASELINE config 2)",
            "solve_s": ours["solve_s"], "setup_s": ours["setup_s"], "iterations": ours["iterations"],
-           "final_residual": ours["final_residual"], "p_schedule": ours["p_schedule"]}
+           "final_residual": ours["final_residual"], "p_schedule": ours["p_schedule"],
+           "solver": "host GMRES (hostcxx/GMRES.hpp, the reference's algorithm line by line) over FMM_plan::execute",
+           "device_resident_gmres": {"solve_s": dev["solve_s"], "iterations": dev["iterations"],
+                                     "final_residual": dev["final_residual"], "p_schedule": dev["p_schedule"],
+                                     "solver": "fmmb_gmres: Krylov basis and BLAS-1 on the GPU, one host sync per iteration"}}
     if ref is not None:
         out["reference"] = dict(ref, cores=threads, kind="reference",
                                 note="multi-threaded reference M2L has a data race (SURVEY F5): time only")

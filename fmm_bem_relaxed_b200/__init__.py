@@ -23,7 +23,7 @@ import numpy as np
 from . import capi
 from .capi import FmmbError
 
-__all__ = ["FMMOptions", "LaplaceSpherical", "LaplaceSphericalBEM", "StokesSpherical", "YukawaCartesian", "Panels", "FMM_plan", "Direct", "FmmbError", "capi", "comm_unique_id",
+__all__ = ["FMMOptions", "LaplaceSpherical", "LaplaceSphericalBEM", "StokesSpherical", "YukawaCartesian", "SolverOptions", "GMRES", "Panels", "FMM_plan", "Direct", "FmmbError", "capi", "comm_unique_id",
            "partition_ranges", "get_options"]
 
 
@@ -288,6 +288,35 @@ class FMM_plan:
         L = np.zeros((i.n_boxes, nc, 2))
         capi.check(self._lib.fmmb_plan_get_expansions(self._h, capi.ptr(M), capi.ptr(L)))
         return M, L
+
+
+class SolverOptions:
+    """Mirror of reference examples/BEM/SolverOptions.hpp:9-38 (defaults of the default constructor)."""
+    BOURAS, SIMONCINI = 0, 1
+
+    def __init__(self, residual=1e-5, max_iters=500, restart=500, max_p=16, variable_p=True, relax_type=0):
+        self.residual, self.max_iters, self.restart = float(residual), int(max_iters), int(restart)
+        self.max_p, self.variable_p, self.relax_type = int(max_p), bool(variable_p), int(relax_type)
+
+
+def GMRES(plan, x, b, opts, diag=None, output=False):
+    """GMRES(plan, x, b, solver_options[, M]) of reference examples/BEM/GMRES.hpp:142-252, device resident
+    (fmmb_gmres).  x: initial guess, overwritten with the solution.  Returns a dict with the iteration record."""
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    b = np.ascontiguousarray(b, dtype=np.float64)
+    d = None if diag is None else np.ascontiguousarray(diag, dtype=np.float64)
+    so = capi.SolverOptions(opts.residual, opts.max_iters, opts.restart, opts.max_p, int(opts.variable_p),
+                            opts.relax_type, int(output))
+    info = capi.GmresInfo()
+    cap = 4096
+    ps = np.zeros(cap, np.int32)
+    rs = np.zeros(cap)
+    capi.check(plan._lib.fmmb_gmres(plan._h, capi.ptr(b), capi.ptr(x), capi.ptr(d), ctypes.byref(so), ctypes.byref(info),
+                                    capi.ptr(ps), capi.ptr(rs), cap))
+    k = min(cap, info.n_records)
+    plan.K.P = info.final_p           # like the reference, the kernel is left at the last relaxed order
+    return {"x": x, "iterations": info.iterations, "final_residual": info.final_residual,
+            "p_schedule": ps[:k].tolist(), "residuals": rs[:k].tolist()}
 
 
 def comm_unique_id():

@@ -43,6 +43,17 @@ class Sources(ctypes.Structure):
                 ("bc", ctypes.c_void_p)]
 
 
+class SolverOptions(ctypes.Structure):
+    _fields_ = [("residual", ctypes.c_double), ("max_iters", ctypes.c_int32), ("restart", ctypes.c_int32),
+                ("max_p", ctypes.c_uint32), ("variable_p", ctypes.c_int32), ("relax_type", ctypes.c_int32),
+                ("verbose", ctypes.c_int32)]
+
+
+class GmresInfo(ctypes.Structure):
+    _fields_ = [("iterations", ctypes.c_int32), ("n_records", ctypes.c_int32), ("final_p", ctypes.c_int32),
+                ("reserved", ctypes.c_int32), ("final_residual", ctypes.c_double)]
+
+
 class PlanInfo(ctypes.Structure):
     _fields_ = [("n_bodies", ctypes.c_int64), ("n_boxes", ctypes.c_int64), ("n_leaves", ctypes.c_int64),
                 ("n_levels", ctypes.c_int64), ("n_m2l_pairs", ctypes.c_int64),
@@ -57,7 +68,7 @@ class PlanInfo(ctypes.Structure):
 # every symbol include/fmmb.h declares
 EXPORTS = [
     "fmmb_plan_create", "fmmb_plan_set_p", "fmmb_plan_execute", "fmmb_plan_execute_device",
-    "fmmb_plan_execute_sharded", "fmmb_plan_peer_export", "fmmb_plan_peer_init",
+    "fmmb_plan_execute_sharded", "fmmb_gmres", "fmmb_plan_peer_export", "fmmb_plan_peer_init",
     "fmmb_plan_direct", "fmmb_plan_set_option", "fmmb_plan_sync", "fmmb_comm_unique_id", "fmmb_plan_comm_init",
     "fmmb_partition_ranges", "fmmb_plan_stream", "fmmb_plan_get_info", "fmmb_plan_get_tree",
     "fmmb_plan_get_expansions", "fmmb_plan_phase_times", "fmmb_plan_destroy", "fmmb_last_error",
@@ -83,6 +94,7 @@ def load():
     lib.fmmb_plan_execute.argtypes = [vp, dp, dp]
     lib.fmmb_plan_execute_device.argtypes = [vp, dp, dp]
     lib.fmmb_plan_execute_sharded.argtypes = [vp, dp, dp]
+    lib.fmmb_gmres.argtypes = [vp, dp, dp, dp, ctypes.POINTER(SolverOptions), ctypes.POINTER(GmresInfo), dp, dp, i32]
     lib.fmmb_plan_peer_export.argtypes = [vp, dp]
     lib.fmmb_plan_peer_init.argtypes = [vp, dp]
     lib.fmmb_plan_direct.argtypes = [vp, dp, i64, dp, dp]

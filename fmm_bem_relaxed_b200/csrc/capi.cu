@@ -211,6 +211,25 @@ static void run_matvec(fmmb_plan* plan, const double* q, double* r) {
 }
 }  // namespace fmmb
 
+extern "C++" {
+namespace fmmb {
+void run_matvec_for_solver(fmmb_plan* plan, const double* q, double* r) { run_matvec(plan, q, r); }
+}
+}
+
+int fmmb_gmres(fmmb_plan* plan, const double* b, double* x, const double* diag, const fmmb_solver_options* options,
+               fmmb_gmres_info* info, int32_t* p_schedule, double* residuals, int32_t capacity) {
+  if (!plan || !b || !x || !options) { set_error("null argument"); return FMMB_ERR_INVALID; }
+  if (options->max_p < 1 || options->max_p > FMMB_MAX_P || !(options->residual > 0) || options->restart < 1) {
+    set_error("solver options: residual > 0, restart >= 1, 1 <= max_p <= 16");
+    return FMMB_ERR_INVALID;
+  }
+  return guarded([&] {
+    FMMB_CUDA(cudaSetDevice(plan->device));
+    gmres_solve(plan, b, x, diag, *options, info, p_schedule, residuals, capacity < 0 ? 0 : capacity);
+  });
+}
+
 int fmmb_plan_execute_device(fmmb_plan* plan, const double* charges_dev, double* results_dev) {
   if (!plan || !charges_dev || !results_dev) { set_error("null argument"); return FMMB_ERR_INVALID; }
   return guarded([&] {

@@ -276,6 +276,9 @@ void yukawa_free(YukawaData* d);
 double yukawa_kappa(const YukawaData* d);
 void yukawa_direct_raw(double kappa, const double* d_spts, const double* d_q, int64_t ns, const double* d_tpts,
                        int64_t nt, double* d_out, cudaStream_t s);
+// gmres.cu
+void gmres_solve(fmmb_plan* plan, const double* b_host, double* x_host, const double* diag_host,
+                 const fmmb_solver_options& o, fmmb_gmres_info* info, int32_t* p_sched, double* res_hist, int cap);
 // stokes.cu
 void stokes_setup(fmmb_plan* plan, bool stresslet);
 void stokes_execute(fmmb_plan* plan, const double* d_charges, double* d_results);

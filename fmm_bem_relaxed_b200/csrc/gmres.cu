@@ -1,0 +1,209 @@
+// csrc/gmres.cu -- device-resident restarted GMRES with per-iteration relaxation of the expansion order: the caller
+// of the hot path (reference examples/BEM/GMRES.hpp:142-252 with examples/BEM/SolverOptions.hpp:25-38).
+//
+// Same algorithm and decisions as the reference: modified Gram-Schmidt, Givens rotations on host scalars,
+// convergence on the rotated residual estimate |s[i+1]| / ||b||, and before every inner matvec
+//     p = max(1, predict_p(|resid|));  kernel.set_p(p)
+// (the first matvec of a restart cycle runs at whatever order the kernel was left at, GMRES.hpp:174-175).
+// What moves: the Krylov basis, the work vectors and every BLAS-1 operation live on the GPU, the matvec is fed
+// from device-resident vectors (fmmb_plan_execute_device), and an inner iteration costs ONE host synchronisation:
+// the Gram-Schmidt coefficients stay in device memory between the dot product that produces them and the axpy
+// that consumes them, and come back to the host as one column when the iteration's norm is needed.
+#include "common.cuh"
+#include <cmath>
+#include <cstring>
+
+namespace fmmb {
+
+namespace {
+
+constexpr int kDotBlocks = 32;
+
+// out[slot] = sum a[i] b[i]: block partial sums, the last block to finish adds them in index order
+// (deterministic: the result does not depend on which block is last)
+__global__ void __launch_bounds__(256)
+dot_kernel(const double* __restrict__ a, const double* __restrict__ b, int64_t n, double* __restrict__ partial,
+           unsigned int* __restrict__ counter, double* __restrict__ out) {
+  __shared__ double sh[256];
+  __shared__ int last;
+  double s = 0;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) s += a[i] * b[i];
+  sh[threadIdx.x] = s;
+  __syncthreads();
+  for (int w = 128; w > 0; w >>= 1) {
+    if ((int)threadIdx.x < w) sh[threadIdx.x] += sh[threadIdx.x + w];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    partial[blockIdx.x] = sh[0];
+    __threadfence();
+    last = atomicAdd(counter, 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (last && threadIdx.x == 0) {
+    __threadfence();
+    double t = 0;
+    for (unsigned k = 0; k < gridDim.x; ++k) t += ((volatile double*)partial)[k];
+    *out = t;
+    *counter = 0;
+  }
+}
+// y += alpha x with alpha = sign * (*coef) read from device memory (sqrt / reciprocal variants for the norms)
+// mode 0: alpha = sign * coef;  1: y = y * (sign / sqrt(coef)) (x unused)
+__global__ void axpy_dev_kernel(const double* __restrict__ x, double* __restrict__ y, int64_t n,
+                                const double* __restrict__ coef, double sign, int mode) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  if (mode == 0) y[i] = fma(sign * *coef, x[i], y[i]);
+  else y[i] *= sign / sqrt(*coef);
+}
+__global__ void axpy_kernel(const double* __restrict__ x, double* __restrict__ y, int64_t n, double alpha) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < n) y[i] = fma(alpha, x[i], y[i]);
+}
+// z = d .* v (diagonal preconditioner) or z = v
+__global__ void precond_kernel(const double* __restrict__ v, const double* __restrict__ d, double* __restrict__ z, int64_t n) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < n) z[i] = d ? d[i] * v[i] : v[i];
+}
+inline int nblk(int64_t n, int t) { return (int)((n + t - 1) / t); }
+
+unsigned predict_p(const fmmb_solver_options& o, double eps) {      // SolverOptions::predict_p (:25-38)
+  if (!o.variable_p) return o.max_p;
+  if (o.relax_type == 0) {
+    const double alpha = 1. / std::min(eps, 1.);
+    const double nu = std::min(alpha * o.residual, 1.);
+    return std::min((unsigned)std::ceil(-std::log2(nu)), o.max_p);
+  }
+  return std::min((unsigned)std::ceil(-std::log2(eps)), o.max_p);
+}
+inline void apply_rotation(double& dx, double& dy, double cs, double sn) {
+  const double t = cs * dx + sn * dy;
+  dy = -sn * dx + cs * dy;
+  dx = t;
+}
+inline void make_rotation(double dx, double dy, double& cs, double& sn) {
+  if (dy == 0.0) { cs = 1.0; sn = 0.0; }
+  else if (std::fabs(dy) > std::fabs(dx)) { const double t = dx / dy; sn = 1.0 / std::sqrt(1.0 + t * t); cs = t * sn; }
+  else { const double t = dy / dx; cs = 1.0 / std::sqrt(1.0 + t * t); sn = t * cs; }
+}
+
+}  // namespace
+
+void run_matvec_for_solver(fmmb_plan* plan, const double* q, double* r);   // capi.cu
+
+void gmres_solve(fmmb_plan* plan, const double* b_host, double* x_host, const double* diag_host,
+                 const fmmb_solver_options& o, fmmb_gmres_info* info, int32_t* p_sched, double* res_hist, int cap) {
+  if (plan->charge_dim != 1 || plan->result_dim != 1)
+    throw StatusError{FMMB_ERR_UNSUPPORTED, "fmmb_gmres: plans with scalar charges and results (BEM kernels)"};
+  if (plan->tree.nranks > 1) throw StatusError{FMMB_ERR_UNSUPPORTED, "fmmb_gmres: single-GPU plans"};
+  const int64_t n = plan->tree.n;
+  const int R = std::max(1, o.restart);
+  cudaStream_t s = plan->stream;
+  DevBuf<double> x, b, w, z, diag, scal, partial;
+  DevBuf<unsigned int> counter;
+  x.from_host(x_host, n, s);
+  b.from_host(b_host, n, s);
+  if (diag_host) diag.from_host(diag_host, n, s);
+  w.resize(n); z.resize(n);
+  scal.resize(R + 4);                     // [0..R): Gram-Schmidt column, [R]: norm^2, [R+1]: scratch
+  partial.resize(kDotBlocks);
+  counter.resize(1);
+  counter.zero(s);
+  std::vector<DevBuf<double>*> V;
+  struct Cleanup { std::vector<DevBuf<double>*>& v; ~Cleanup() { for (auto* p : v) delete p; } } cleanup{V};
+  auto basis = [&](int k) -> double* {
+    while ((int)V.size() <= k) { V.push_back(new DevBuf<double>()); V.back()->resize(n); }
+    return V[k]->p;
+  };
+  const int g = nblk(n, 256);
+  auto dot_to = [&](const double* a, const double* c, double* out) {
+    dot_kernel<<<kDotBlocks, 256, 0, s>>>(a, c, n, partial.p, counter.p, out);
+  };
+  auto fetch = [&](const double* dev, double* host, int count) {
+    FMMB_CUDA(cudaMemcpyAsync(host, dev, count * sizeof(double), cudaMemcpyDeviceToHost, s));
+    FMMB_CUDA(cudaStreamSynchronize(s));
+  };
+  double normb2 = 0;
+  dot_to(b.p, b.p, scal.p + R);
+  fetch(scal.p + R, &normb2, 1);
+  const double normb = std::sqrt(normb2);
+
+  std::vector<std::vector<double>> H;
+  std::vector<double> sv(R + 1), cs(R), sn(R), col(R + 2);
+  double resid = 0;
+  int i = -1, iter = 0, rec = 0;
+  do {
+    // w = A x - b at the order the kernel currently has; V[0] = -w / |w|
+    run_matvec_for_solver(plan, x.p, w.p);
+    axpy_kernel<<<g, 256, 0, s>>>(b.p, w.p, n, -1.0);
+    dot_to(w.p, w.p, scal.p + R);
+    double beta2 = 0;
+    fetch(scal.p + R, &beta2, 1);
+    const double beta = std::sqrt(beta2);
+    FMMB_CUDA(cudaMemcpyAsync(basis(0), w.p, n * sizeof(double), cudaMemcpyDeviceToDevice, s));
+    axpy_dev_kernel<<<g, 256, 0, s>>>(nullptr, basis(0), n, scal.p + R, -1.0, 1);
+    H.clear();
+    std::fill(sv.begin(), sv.end(), 0.0);
+    sv[0] = beta;
+    i = -1;
+    resid = sv[0] / normb;
+    do {
+      ++i; ++iter;
+      const int p = (int)std::max(1u, predict_p(o, std::fabs(resid)));
+      if (p > FMMB_MAX_P) throw StatusError{FMMB_ERR_INVALID, "predicted expansion order exceeds FMMB_MAX_P"};
+      plan->p = p;
+      precond_kernel<<<g, 256, 0, s>>>(basis(i), diag_host ? diag.p : nullptr, z.p, n);
+      run_matvec_for_solver(plan, z.p, w.p);
+      // modified Gram-Schmidt: coefficient k is produced and consumed on the device
+      for (int k = 0; k <= i; ++k) {
+        dot_to(w.p, basis(k), scal.p + k);
+        axpy_dev_kernel<<<g, 256, 0, s>>>(basis(k), w.p, n, scal.p + k, -1.0, 0);
+      }
+      dot_to(w.p, w.p, scal.p + R);
+      double* vnext = basis(i + 1);
+      FMMB_CUDA(cudaMemcpyAsync(vnext, w.p, n * sizeof(double), cudaMemcpyDeviceToDevice, s));
+      axpy_dev_kernel<<<g, 256, 0, s>>>(nullptr, vnext, n, scal.p + R, 1.0, 1);
+      // the one synchronisation of the iteration: the new Hessenberg column
+      FMMB_CUDA(cudaMemcpyAsync(col.data(), scal.p, (i + 1) * sizeof(double), cudaMemcpyDeviceToHost, s));
+      FMMB_CUDA(cudaMemcpyAsync(col.data() + i + 1, scal.p + R, sizeof(double), cudaMemcpyDeviceToHost, s));
+      FMMB_CUDA(cudaStreamSynchronize(s));
+      H.push_back(std::vector<double>(col.begin(), col.begin() + i + 2));
+      H[i][i + 1] = std::sqrt(H[i][i + 1]);
+      for (int k = 0; k < i; ++k) apply_rotation(H[i][k], H[i][k + 1], cs[k], sn[k]);
+      make_rotation(H[i][i], H[i][i + 1], cs[i], sn[i]);
+      apply_rotation(H[i][i], H[i][i + 1], cs[i], sn[i]);
+      apply_rotation(sv[i], sv[i + 1], cs[i], sn[i]);
+      resid = sv[i + 1] / normb;
+      if (rec < cap) {
+        if (p_sched) p_sched[rec] = p;
+        if (res_hist) res_hist[rec] = std::fabs(resid);
+      }
+      ++rec;
+      if (std::fabs(resid) < o.residual) break;
+      if (o.verbose) printf("it: %03d, res: %.3e, fmm_req_p: %01d\n", iter, std::fabs(resid), p);
+    } while (i + 1 < R && i + 1 <= o.max_iters && std::fabs(resid) > o.residual);
+    // back substitution on the host, solution update on the device
+    for (int j = i; j >= 0; --j) {
+      sv[j] /= H[j][j];
+      for (int k = j - 1; k >= 0; --k) sv[k] -= H[j][k] * sv[j];
+    }
+    for (int j = 0; j <= i; ++j) {
+      precond_kernel<<<g, 256, 0, s>>>(basis(j), diag_host ? diag.p : nullptr, z.p, n);
+      axpy_kernel<<<g, 256, 0, s>>>(z.p, x.p, n, sv[j]);
+    }
+    if (o.verbose && iter % 10 == 0) printf("it: %04d, residual: %.3e\n", iter, std::fabs(resid));
+  } while (std::fabs(resid) > o.residual && iter < o.max_iters);
+  if (o.verbose) printf("Final residual: %.4e, after %d iterations\n", std::fabs(resid), iter);
+  FMMB_CUDA(cudaGetLastError());
+  FMMB_CUDA(cudaMemcpyAsync(x_host, x.p, n * sizeof(double), cudaMemcpyDeviceToHost, s));
+  FMMB_CUDA(cudaStreamSynchronize(s));
+  if (info) {
+    info->iterations = iter;
+    info->n_records = rec;
+    info->final_residual = std::fabs(resid);
+    info->final_p = plan->p;
+  }
+}
+
+}  // namespace fmmb

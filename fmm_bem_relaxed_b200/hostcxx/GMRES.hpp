@@ -14,6 +14,7 @@
 
 #include "Preconditioner.hpp"
 #include "SolverOptions.hpp"
+#include "../../include/fmmb.h"
 
 namespace gmres_detail {
 inline double dot(const std::vector<double>& a, const std::vector<double>& b) {
@@ -114,4 +115,32 @@ template <typename Matvec>
 GMRESReport GMRES(Matvec& MV, std::vector<typename Matvec::charge_type>& x,
                   std::vector<typename Matvec::result_type>& b, const SolverOptions& opts, bool output = true) {
   return GMRES(MV, x, b, opts, Preconditioners::Identity(), output);
+}
+
+/** The same solver, device resident (fmmb_gmres in include/fmmb.h): Krylov basis and BLAS-1 work stay on the GPU and
+ * the matvec is fed from device vectors; iteration counts and orders follow the same rule.  `diag`: optional
+ * reciprocals for the diagonal preconditioner, empty = identity.  Available when MV is an FMM_plan. */
+template <typename Matvec>
+GMRESReport GMRES_device(Matvec& MV, std::vector<double>& x, std::vector<double>& b, const SolverOptions& opts,
+                         const std::vector<double>& diag = std::vector<double>(), bool output = true) {
+  GMRESReport rep;
+  fmmb_solver_options so = {opts.residual, opts.max_iters, opts.restart, opts.max_p, opts.variable_p ? 1 : 0,
+                            opts.relax_type == SolverOptions::BOURAS ? 0 : 1, output ? 1 : 0};
+  fmmb_gmres_info info = {};
+  const int cap = 4096;
+  std::vector<int32_t> ps(cap);
+  std::vector<double> rs(cap);
+  if (fmmb_plan_set_p(MV.handle(), MV.kernel().order()) != FMMB_OK ||
+      fmmb_gmres(MV.handle(), b.data(), x.data(), diag.empty() ? nullptr : diag.data(), &so, &info, ps.data(), rs.data(),
+                 cap) != FMMB_OK) {
+    fprintf(stderr, "[E]: GMRES_device: %s\n", fmmb_last_error());
+    return rep;
+  }
+  MV.kernel().set_p(info.final_p);       // the reference leaves the kernel at the last relaxed order
+  rep.iterations = info.iterations;
+  rep.final_residual = info.final_residual;
+  const int k = info.n_records < cap ? info.n_records : cap;
+  rep.p_schedule.assign(ps.begin(), ps.begin() + k);
+  rep.residuals.assign(rs.begin(), rs.begin() + k);
+  return rep;
 }

@@ -20,7 +20,7 @@ int main(int argc, char** argv) {
   FMMOptions opts = get_options(argc, argv);
   opts.sparse_local = true;
   SolverOptions solver_options;
-  bool second_kind = false, diagonal = false;
+  bool second_kind = false, diagonal = false, device_gmres = false;
   for (int i = 1; i < argc; ++i) {
     if (!strcmp(argv[i], "-recursions")) recursions = atoi(argv[++i]);
     else if (!strcmp(argv[i], "-p")) { p = atoi(argv[++i]); solver_options.max_p = p; }
@@ -30,6 +30,7 @@ int main(int argc, char** argv) {
     else if (!strcmp(argv[i], "-solver_tol")) solver_options.residual = atof(argv[++i]);
     else if (!strcmp(argv[i], "-max_iters")) max_iterations = atoi(argv[++i]);
     else if (!strcmp(argv[i], "-diagonal")) diagonal = true;
+    else if (!strcmp(argv[i], "-device_gmres")) device_gmres = true;   // extension: fmmb_gmres (device-resident solver)
     else if (!strcmp(argv[i], "-theta") || !strcmp(argv[i], "-ncrit") || !strcmp(argv[i], "-eval")) ++i;
   }
   solver_options.max_iters = max_iterations;
@@ -62,6 +63,15 @@ int main(int argc, char** argv) {
 
   tic = get_time();
   printf(second_kind ? "2nd-kind equation being solved\n" : "1st-kind equation being solved\n");
+#ifndef REF_GMRES_HEADER
+  if (device_gmres) {
+    std::vector<double> diag;
+    if (diagonal)
+      for (auto it = plan.source_begin(); it != plan.source_end(); ++it) diag.push_back(1. / K(*it, *it));
+    printf("Solver: GMRES (device resident)\nPreconditioner: %s\n", diagonal ? "Diagonal" : "Identity");
+    GMRES_device(plan, x, b, solver_options, diag);
+  } else
+#endif
   if (diagonal) {
     Preconditioners::Diagonal<charge_type> M(K, plan.source_begin(), plan.source_end());
     printf("Solver: GMRES\nPreconditioner: Diagonal\n");

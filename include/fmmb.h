@@ -205,6 +205,36 @@ int fmmb_plan_peer_init(fmmb_plan* plan, const unsigned char* blobs);
  * [cuts[r], cuts[r+1]). */
 int fmmb_partition_ranges(const double* weights, int64_t n, int nranks, int64_t* cuts);
 
+/* ---- device-resident relaxed GMRES (the caller of the hot path) ------------------------------------------------
+ * Mirrors GMRES(plan, x, b, solver_options[, M]) of reference examples/BEM/GMRES.hpp:142-252 with
+ * SolverOptions (examples/BEM/SolverOptions.hpp:9-38): restarted GMRES, modified Gram-Schmidt, Givens rotations,
+ * convergence on the rotated residual estimate, and p = max(1, predict_p(|resid|)) set before every inner matvec.
+ * The Krylov basis and all BLAS-1 work stay on the GPU; one host synchronisation per inner iteration.
+ * Plans with scalar charges and results (BEM kernels), single GPU. */
+typedef struct {
+  double residual;       /* SolverOptions::residual (tolerance on |s[i+1]| / ||b||) */
+  int32_t max_iters;     /* SolverOptions::max_iters */
+  int32_t restart;       /* SolverOptions::restart */
+  uint32_t max_p;        /* SolverOptions::max_p */
+  int32_t variable_p;    /* SolverOptions::variable_p: 1 = relax the order with the residual, 0 = always max_p */
+  int32_t relax_type;    /* 0 = BOURAS (default), 1 = SIMONCINI */
+  int32_t verbose;       /* 1 = print the reference's progress lines ("it: 001, res: ..., fmm_req_p: ...") */
+} fmmb_solver_options;
+
+typedef struct {
+  int32_t iterations;    /* inner iterations performed */
+  int32_t n_records;     /* entries that p_schedule / residuals would hold (may exceed the capacity passed in) */
+  int32_t final_p;       /* expansion order the plan is left at (the reference leaves the kernel at the last relaxed p) */
+  int32_t reserved;
+  double final_residual;
+} fmmb_gmres_info;
+
+/* b, x: n doubles (host); x holds the initial guess on entry and the solution on return.
+ * diag: NULL (identity) or n doubles d with M(v)_i = d_i v_i (Preconditioners::Diagonal, examples/BEM/Preconditioner.hpp:24-38).
+ * p_schedule / residuals: optional arrays of `capacity` entries: order and |resid| of every inner iteration. */
+int fmmb_gmres(fmmb_plan* plan, const double* b, double* x, const double* diag, const fmmb_solver_options* options,
+               fmmb_gmres_info* info, int32_t* p_schedule, double* residuals, int32_t capacity);
+
 int fmmb_plan_sync(fmmb_plan* plan);
 void* fmmb_plan_stream(fmmb_plan* plan); /* cudaStream_t */
 

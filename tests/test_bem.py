@@ -144,3 +144,39 @@ def test_relaxed_gmres_c2_same_iterations_as_reference():
     out = run_bin("laplace_bem", "-recursions", "7", "-p", "8", "-k", "4", "-solver_tol", "1e-6", "-fixed_p")
     its, final, niter, rel, ext = parse_gmres(out)
     assert niter == 15 and final == 9.1278e-07 and rel == 4.847e-03
+
+
+@pytest.mark.gpu
+def test_device_resident_gmres_same_iterations_as_reference():
+    """fmmb_gmres (Krylov basis and BLAS-1 on the GPU, one host sync per iteration) takes the same decisions as the
+    reference's GMRES.hpp: iteration counts and the order of every iteration are identical; residuals agree to the
+    printed digits up to the rounding of the (parallel) dot products."""
+    its, final, niter, rel, ext = parse_gmres(run_bin("laplace_bem", "-recursions", "4", "-p", "8", "-k", "4",
+                                                      "-solver_tol", "1e-6", "-device_gmres"))
+    assert niter == 7 and [p for _, _, p in its] == [8, 8, 8, 7, 6, 4]
+    for (_, r, _), want in zip(its, [7.878e-04, 2.986e-04, 1.081e-04, 3.370e-05, 1.043e-05, 2.522e-06]):
+        assert abs(r - want) <= 2e-3 * want
+    assert abs(final - 3.1066e-07) <= 2e-3 * 3.1066e-07 and rel == 1.512e-02 and ext == 0.19071
+    out = run_bin("laplace_bem", "-recursions", "7", "-p", "8", "-k", "4", "-ncrit", "64", "-theta", "0.5",
+                  "-solver_tol", "1e-6", "-device_gmres")
+    its, final, niter, rel, ext = parse_gmres(out)
+    assert niter == 16 and [p for _, _, p in its] == [8, 6, 5, 5, 5, 4, 4, 3, 3, 3, 2, 2, 2, 1, 1]
+    assert abs(final - 8.4431e-07) <= 2e-3 * 8.4431e-07 and rel == 4.862e-03 and ext == 0.19242
+    out = run_bin("laplace_bem", "-recursions", "6", "-p", "8", "-k", "4", "-solver_tol", "1e-6", "-device_gmres", "-diagonal")
+    host = run_bin("laplace_bem", "-recursions", "6", "-p", "8", "-k", "4", "-solver_tol", "1e-6", "-diagonal")
+    a, b = parse_gmres(out), parse_gmres(host)
+    assert a[2] == b[2] and [p for _, _, p in a[0]] == [p for _, _, p in b[0]] and abs(a[1] - b[1]) <= 2e-3 * b[1]
+
+
+@pytest.mark.gpu
+def test_python_gmres_solves_the_first_kind_equation():
+    v = O.unit_sphere(5)
+    n = len(v)
+    plan = F.FMM_plan(F.LaplaceSphericalBEM(8, 4), F.Panels(v, 0))
+    b = F.FMM_plan(F.LaplaceSphericalBEM(8, 4), F.Panels(v, 1)).execute(np.ones(n))   # dphi/dn = 1 on the sphere
+    rep = F.GMRES(plan, np.zeros(n), b, F.SolverOptions(residual=1e-6, max_iters=200, restart=200, max_p=8))
+    assert rep["iterations"] < 30 and rep["final_residual"] < 1e-6
+    assert rep["p_schedule"][0] == 8 and min(rep["p_schedule"]) < 8          # the order was relaxed
+    assert abs(rep["x"].mean() - 1.0) < 3e-2                                    # exact solution: 1
+    plan.kernel().set_p(8)
+    assert O.rel_l2(plan.execute(rep["x"]), b) < 1e-3                           # true residual at full order
