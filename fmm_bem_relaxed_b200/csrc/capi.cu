@@ -152,6 +152,7 @@ void fmmb_plan_destroy(fmmb_plan* plan) {
   bem_free(plan->bem);
   stokes_free(plan->stokes);
   yukawa_free(plan->yukawa);
+  gmres_free(plan->gmres_ws);
   for (auto& kv : plan->m2l_coeff) delete kv.second;
   for (auto& e : plan->ev) if (e) cudaEventDestroy(e);
   if (plan->stream) cudaStreamDestroy(plan->stream);

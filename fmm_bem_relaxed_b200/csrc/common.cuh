@@ -163,6 +163,7 @@ struct TransBatch {
 struct BemData;
 struct StokesData;
 struct YukawaData;
+struct GmresWorkspace;
 
 struct LaplaceTables {
   int pmax = 0;
@@ -192,6 +193,7 @@ struct fmmb_plan {
   fmmb::BemData* bem = nullptr;      // LaplaceSphericalBEM plans only
   fmmb::StokesData* stokes = nullptr;  // StokesSpherical plans only
   fmmb::YukawaData* yukawa = nullptr;  // YukawaCartesian plans only
+  fmmb::GmresWorkspace* gmres_ws = nullptr;  // fmmb_gmres scratch, kept between solves
   int charge_dim = 1, result_dim = 4;
   void* comm = nullptr;              // ncclComm_t once fmmb_plan_comm_init ran
   fmmb::DevBuf<int> xchg_off_dev;
@@ -277,6 +279,7 @@ double yukawa_kappa(const YukawaData* d);
 void yukawa_direct_raw(double kappa, const double* d_spts, const double* d_q, int64_t ns, const double* d_tpts,
                        int64_t nt, double* d_out, cudaStream_t s);
 // gmres.cu
+void gmres_free(GmresWorkspace* w);
 void gmres_solve(fmmb_plan* plan, const double* b_host, double* x_host, const double* diag_host,
                  const fmmb_solver_options& o, fmmb_gmres_info* info, int32_t* p_sched, double* res_hist, int cap);
 // stokes.cu

@@ -15,6 +15,14 @@
 
 namespace fmmb {
 
+// Solver workspace, kept on the plan between solves (a cudaMalloc / cudaFree pair per Krylov vector would cost more
+// than the BLAS-1 work of a whole solve at BEM sizes).
+struct GmresWorkspace {
+  DevBuf<double> x, b, w, z, diag, scal, partial, basis;   // basis: vectors back to back, grown geometrically
+  DevBuf<unsigned int> counter;
+};
+void gmres_free(GmresWorkspace* w) { delete w; }
+
 namespace {
 
 constexpr int kDotBlocks = 32;
@@ -100,8 +108,10 @@ void gmres_solve(fmmb_plan* plan, const double* b_host, double* x_host, const do
   const int64_t n = plan->tree.n;
   const int R = std::max(1, o.restart);
   cudaStream_t s = plan->stream;
-  DevBuf<double> x, b, w, z, diag, scal, partial;
-  DevBuf<unsigned int> counter;
+  if (!plan->gmres_ws) plan->gmres_ws = new GmresWorkspace();
+  GmresWorkspace& ws = *plan->gmres_ws;
+  DevBuf<double>&x = ws.x, &b = ws.b, &w = ws.w, &z = ws.z, &diag = ws.diag, &scal = ws.scal, &partial = ws.partial;
+  DevBuf<unsigned int>& counter = ws.counter;
   x.from_host(x_host, n, s);
   b.from_host(b_host, n, s);
   if (diag_host) diag.from_host(diag_host, n, s);
@@ -110,11 +120,10 @@ void gmres_solve(fmmb_plan* plan, const double* b_host, double* x_host, const do
   partial.resize(kDotBlocks);
   counter.resize(1);
   counter.zero(s);
-  std::vector<DevBuf<double>*> V;
-  struct Cleanup { std::vector<DevBuf<double>*>& v; ~Cleanup() { for (auto* p : v) delete p; } } cleanup{V};
+  if (ws.basis.n < (size_t)n * 24) ws.basis.resize((size_t)n * 24);
   auto basis = [&](int k) -> double* {
-    while ((int)V.size() <= k) { V.push_back(new DevBuf<double>()); V.back()->resize(n); }
-    return V[k]->p;
+    if (ws.basis.n < (size_t)n * (k + 1)) ws.basis.grow(std::max((size_t)n * (k + 1), 2 * ws.basis.n), s);   // keeps the vectors
+    return ws.basis.p + (size_t)n * k;
   };
   const int g = nblk(n, 256);
   auto dot_to = [&](const double* a, const double* c, double* out) {

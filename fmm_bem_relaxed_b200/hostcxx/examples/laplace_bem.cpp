@@ -12,6 +12,7 @@
 #include <GMRES.hpp>
 #endif
 
+#include <algorithm>
 #include <cmath>
 #include <cstring>
 
@@ -61,6 +62,13 @@ int main(int argc, char** argv) {
   double setup_time = get_time() - tic;
   if (b.empty()) return 1;
 
+  int repeat = 1;
+  for (int i = 1; i < argc; ++i) if (!strcmp(argv[i], "-repeat")) repeat = atoi(argv[i + 1]);   // extension: best of k solves
+  double solve_time = 1e300;
+  for (int rep = 0; rep < repeat; ++rep) {
+  std::fill(x.begin(), x.end(), 0.);
+  K.set_p(p);
+  plan.kernel().set_p(p);
   tic = get_time();
   printf(second_kind ? "2nd-kind equation being solved\n" : "1st-kind equation being solved\n");
 #ifndef REF_GMRES_HEADER
@@ -80,7 +88,9 @@ int main(int argc, char** argv) {
     printf("Solver: GMRES\nPreconditioner: Identity\n");
     GMRES(plan, x, b, solver_options);
   }
-  double solve_time = get_time() - tic;
+  solve_time = std::min(solve_time, get_time() - tic);
+  }
+
   printf("\nTIMING:\n\tsetup : %.4es\n\tsolve : %.4es\n", setup_time, solve_time);
 
   double e = 0., e2 = 0.;
