@@ -23,7 +23,7 @@ import numpy as np
 from . import capi
 from .capi import FmmbError
 
-__all__ = ["FMMOptions", "LaplaceSpherical", "LaplaceSphericalBEM", "StokesSpherical", "YukawaCartesian", "SolverOptions", "GMRES", "Panels", "FMM_plan", "Direct", "FmmbError", "capi", "comm_unique_id",
+__all__ = ["FMMOptions", "LaplaceSpherical", "LaplaceSphericalBEM", "StokesSpherical", "YukawaCartesian", "YukawaCartesianBEM", "SolverOptions", "GMRES", "Panels", "FMM_plan", "Direct", "FmmbError", "capi", "comm_unique_id",
            "partition_ranges", "get_options"]
 
 
@@ -136,6 +136,16 @@ class YukawaCartesian(LaplaceSpherical):
         self.Kappa = float(kappa)
 
 
+class YukawaCartesianBEM(LaplaceSphericalBEM):
+    """Mirror of reference kernel/YukawaCartesianBEM.hpp:8-143: YukawaCartesianBEM(int p, double kappa, unsigned k).
+    Panel sources like LaplaceSphericalBEM; scalar charges and results; orders 1..10."""
+    kind = capi.YUKAWA_CARTESIAN_BEM
+
+    def __init__(self, p=5, kappa=0.125, k=3):
+        super().__init__(p, k)
+        self.Kappa = float(kappa)
+
+
 class Panels:
     """A set of triangular panels (the std::vector<Panel> a reference driver builds)."""
     POTENTIAL, NORMAL_DERIV = 0, 1
@@ -171,8 +181,11 @@ class FMM_plan:
                 sources = Panels(sources)
             pts = np.ascontiguousarray(sources.centers)
             verts, bc = sources.vertices, np.ascontiguousarray(sources.bc)
-            self.K = LaplaceSphericalBEM(kernel.P, kernel.K)
-            kd = capi.KernelDesc(kernel.kind, kernel.P, 0.0, kernel.K, 0)
+            if isinstance(kernel, YukawaCartesianBEM):
+                self.K = YukawaCartesianBEM(kernel.P, kernel.Kappa, kernel.K)
+            else:
+                self.K = LaplaceSphericalBEM(kernel.P, kernel.K)
+            kd = capi.KernelDesc(kernel.kind, kernel.P, getattr(kernel, "Kappa", 0.0), kernel.K, 0)
         else:
             pts = np.ascontiguousarray(np.asarray(sources, dtype=np.float64).reshape(-1, 3))
             # the plan owns a COPY of the kernel (FMM_plan.hpp:37)

@@ -19,6 +19,7 @@ LAPLACE_SPHERICAL_BEM = 1
 STOKES_SPHERICAL_STRESSLET = 2
 STOKES_SPHERICAL = 5
 YUKAWA_CARTESIAN = 3
+YUKAWA_CARTESIAN_BEM = 4
 
 
 class FmmbError(RuntimeError):

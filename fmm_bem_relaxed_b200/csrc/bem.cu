@@ -25,6 +25,7 @@ namespace fmmb {
 
 struct BemData {
   int K = 4;
+  double kappa = -1.0;           // >= 0: YukawaCartesianBEM near field; < 0: LaplaceSphericalBEM
   bool set_active[2] = {false, false};
   DevBuf<bem::Panel> pan;        // tree order
   DevBuf<int> bc;                // tree order: 0 POTENTIAL, 1 NORMAL_DERIV
@@ -81,7 +82,7 @@ __global__ void __launch_bounds__(32 * kBemWarps)
 bem_assemble_kernel(const int4* __restrict__ items, int nitems, const unsigned* __restrict__ bb,
                     const unsigned* __restrict__ be, const int* __restrict__ off, const int* __restrict__ src,
                     const bem::Panel* __restrict__ pan, const int* __restrict__ bc,
-                    const long long* __restrict__ base, double* __restrict__ val) {
+                    const long long* __restrict__ base, double kappa, double* __restrict__ val) {
   __shared__ bem::Panel tiles[kBemWarps][32];
   const int wl = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int item = blockIdx.x * kBemWarps + wl;
@@ -108,7 +109,9 @@ bem_assemble_kernel(const int4* __restrict__ items, int nitems, const unsigned* 
       if (lane < ns) tile[lane] = pan[b0 + lane];
       __syncwarp();
       if (act)
-        for (int k = 0; k < ns; ++k) out[(j + k) * cnt + lane] = bem::kernel(tbc, tc, tile[k], c_rule, c_fine);
+        for (int k = 0; k < ns; ++k)
+          out[(j + k) * cnt + lane] = kappa < 0 ? bem::kernel(tbc, tc, tile[k], c_rule, c_fine)
+                                                : bem::kernel_yk(tbc, tc, tile[k], c_rule, kappa);
       j += ns;
     }
   }
@@ -278,7 +281,7 @@ __global__ void bem_gather_charges(const double* __restrict__ q, const unsigned*
 }  // namespace
 
 // Plan-time: panel geometry in tree order, then the cached near field.
-void bem_setup(fmmb_plan* plan, const double* verts_host, const int32_t* bc_host, int quad_k) {
+void bem_setup(fmmb_plan* plan, const double* verts_host, const int32_t* bc_host, int quad_k, double kappa) {
   Tree& T = plan->tree;
   cudaStream_t s = plan->stream;
   if (!bem::rule_supported(quad_k))
@@ -286,6 +289,7 @@ void bem_setup(fmmb_plan* plan, const double* verts_host, const int32_t* bc_host
   BemData* B = new BemData();
   plan->bem = B;
   B->K = quad_k == 7 ? 4 : quad_k;
+  B->kappa = kappa;
   upload_laplace_tables();   // this translation unit's copy of the factorial tables
   bem::Rule rule = bem::make_rule(B->K), fine = bem::make_rule(17);
   FMMB_CUDA(cudaMemcpyToSymbol(c_rule, &rule, sizeof rule));
@@ -318,10 +322,34 @@ void bem_setup(fmmb_plan* plan, const double* verts_host, const int32_t* bc_host
   if (ni)
     bem_assemble_kernel<<<nblk(ni, kBemWarps), 32 * kBemWarps, 0, s>>>(T.p2p_items.p, ni, T.bbegin.p, T.bend.p,
                                                                       T.p2p_off.p, T.p2p_src.p, B->pan.p, B->bc.p,
-                                                                      B->nf_base.p, B->nf_val.p);
+                                                                      B->nf_base.p, B->kappa, B->nf_val.p);
   FMMB_CUDA(cudaGetLastError());
   FMMB_CUDA(cudaStreamSynchronize(s));
 }
+
+// pieces of the BEM matvec shared with YukawaCartesianBEM (csrc/yukawa.cu): charges into tree order + cached near
+// field, and access to the panel data
+void bem_begin(fmmb_plan* plan, const double* d_charges, cudaStream_t s) {
+  Tree& T = plan->tree;
+  BemData* B = plan->bem;
+  const int64_t n = T.n;
+  B->res_near.resize(n); B->res_far.resize(n);
+  bem_gather_charges<<<nblk(n, 256), 256, 0, s>>>(d_charges, T.perm.p, n, T.body.p);
+  const int ni = T.n_p2p_items;
+  if (ni)
+    bem_near_kernel<<<nblk(ni, kBemWarps), 32 * kBemWarps, 0, s>>>(T.p2p_items.p, ni, T.bbegin.p, T.bend.p,
+                                                                  T.p2p_off.p, T.p2p_src.p, T.body.p,
+                                                                  B->nf_base.p, B->nf_val.p, B->res_near.p);
+  B->res_far.zero(s);
+  plan->launches += 3;
+  FMMB_CUDA(cudaGetLastError());
+}
+const bem::Panel* bem_panels(const BemData* b) { return b->pan.p; }
+const int* bem_bc(const BemData* b) { return b->bc.p; }
+bool bem_set_active(const BemData* b, int set) { return b->set_active[set]; }
+double* bem_res_near(BemData* b) { return b->res_near.p; }
+double* bem_res_far(BemData* b) { return b->res_far.p; }
+int bem_rule_points(const BemData* b) { return b->K; }
 
 void bem_execute(fmmb_plan* plan, const double* d_charges, double* d_results) {
   Tree& T = plan->tree;

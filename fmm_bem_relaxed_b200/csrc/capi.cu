@@ -66,16 +66,16 @@ int fmmb_plan_create(const fmmb_kernel_desc* kernel, const fmmb_sources* sources
   if (!kernel || !sources || !out_plan) { set_error("null argument"); return FMMB_ERR_INVALID; }
   *out_plan = nullptr;
   const bool is_stokes = kernel->kind == FMMB_STOKES_SPHERICAL || kernel->kind == FMMB_STOKES_SPHERICAL_STRESSLET;
-  const bool is_yukawa = kernel->kind == FMMB_YUKAWA_CARTESIAN;
+  const bool is_yukawa = kernel->kind == FMMB_YUKAWA_CARTESIAN || kernel->kind == FMMB_YUKAWA_CARTESIAN_BEM;
   if (kernel->kind != FMMB_LAPLACE_SPHERICAL && kernel->kind != FMMB_LAPLACE_SPHERICAL_BEM && !is_stokes && !is_yukawa) {
     set_error("built kernel kinds: FMMB_LAPLACE_SPHERICAL, FMMB_LAPLACE_SPHERICAL_BEM, FMMB_STOKES_SPHERICAL, "
-              "FMMB_STOKES_SPHERICAL_STRESSLET, FMMB_YUKAWA_CARTESIAN");
+              "FMMB_STOKES_SPHERICAL_STRESSLET, FMMB_YUKAWA_CARTESIAN, FMMB_YUKAWA_CARTESIAN_BEM");
     return FMMB_ERR_UNSUPPORTED;
   }
-  const bool is_bem = kernel->kind == FMMB_LAPLACE_SPHERICAL_BEM;
+  const bool is_bem = kernel->kind == FMMB_LAPLACE_SPHERICAL_BEM || kernel->kind == FMMB_YUKAWA_CARTESIAN_BEM;
   if (is_bem && !sources->vertices) { set_error("BEM kernels need the panel vertices"); return FMMB_ERR_INVALID; }
   if (kernel->p < 1 || kernel->p > FMMB_MAX_P) { set_error("expansion order must be in 1..16"); return FMMB_ERR_INVALID; }
-  if (sources->n < 1 || (!sources->points && !(kernel->kind == FMMB_LAPLACE_SPHERICAL_BEM && sources->vertices))) {
+  if (sources->n < 1 || (!sources->points && !(is_bem && sources->vertices))) {
     set_error("need at least one source point");
     return FMMB_ERR_INVALID;
   }
@@ -132,7 +132,8 @@ int fmmb_plan_create(const fmmb_kernel_desc* kernel, const fmmb_sources* sources
     build_m2l_classes(plan);
     if (is_bem) plan->p2p_item_mode = 0;   // one cached near-field block per chunk of <= 32 targets
     build_p2p_items(plan);
-    if (is_bem) bem_setup(plan, sources->vertices, sources->bc, kernel->quad_k);
+    if (is_bem) bem_setup(plan, sources->vertices, sources->bc, kernel->quad_k,
+                          kernel->kind == FMMB_YUKAWA_CARTESIAN_BEM ? kernel->kappa : -1.0);
     if (is_stokes) stokes_setup(plan, kernel->kind == FMMB_STOKES_SPHERICAL_STRESSLET);
     if (is_yukawa) yukawa_setup(plan, kernel->kappa);
   });
@@ -174,7 +175,8 @@ namespace fmmb {
 // graph; from then on a matvec is a single graph launch (no per-kernel launch gaps).
 static void run_matvec(fmmb_plan* plan, const double* q, double* r) {
   auto direct = [&] {
-    if (plan->bem) bem_execute(plan, q, r);
+    if (plan->bem && plan->yukawa) yukawa_bem_execute(plan, q, r);
+    else if (plan->bem) bem_execute(plan, q, r);
     else if (plan->stokes) stokes_execute(plan, q, r);
     else if (plan->yukawa) yukawa_execute(plan, q, r);
     else laplace_execute(plan, q, r);

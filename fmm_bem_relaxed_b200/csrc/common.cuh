@@ -264,7 +264,13 @@ void build_p2p_items(fmmb_plan* plan);
 void laplace_translations(fmmb_plan* plan, cudaStream_t s);
 void laplace_prepare_expansions(fmmb_plan* plan);
 // bem.cu
-void bem_setup(fmmb_plan* plan, const double* verts_host, const int32_t* bc_host, int quad_k);
+void bem_setup(fmmb_plan* plan, const double* verts_host, const int32_t* bc_host, int quad_k, double kappa = -1.0);
+void bem_begin(fmmb_plan* plan, const double* d_charges, cudaStream_t s);
+bool bem_set_active(const BemData* b, int set);
+double* bem_res_near(BemData* b);
+double* bem_res_far(BemData* b);
+int bem_rule_points(const BemData* b);
+void yukawa_bem_execute(fmmb_plan* plan, const double* d_charges, double* d_results);
 void bem_execute(fmmb_plan* plan, const double* d_charges, double* d_results);
 void bem_free(BemData* b);
 int64_t bem_nnz(const BemData* b);

@@ -19,10 +19,15 @@
 // The reference's operators carry a trailing `unsigned p` that its own executor cannot supply; the
 // engine defines set_p(p) as "all tables at order p" (SURVEY Q16).  Orders 1..kYkMaxP are built.
 #include "common.cuh"
+#include "../hostcxx/bem_math.hpp"
 #include <algorithm>
 #include <cmath>
 
 namespace fmmb {
+
+// panel data of a BEM plan (csrc/bem.cu)
+const bem::Panel* bem_panels(const BemData* b);
+const int* bem_bc(const BemData* b);
 
 constexpr int kYkMaxP = 10;
 constexpr int kYkMaxT = (kYkMaxP + 1) * (kYkMaxP + 2) * (kYkMaxP + 3) / 6;   // 286
@@ -432,6 +437,148 @@ yk_direct_kernel(const double* __restrict__ spts, const double* __restrict__ q, 
   if (act) out[i] = make_double4(pot, fx, fy, fz);
 }
 
+// ---- YukawaCartesianBEM far field (reference kernel/YukawaCartesianBEM.hpp:240-273 P2M, :340-361 L2P) ------------
+// Two expansion sets, processed one after the other through the same M / L buffers: set 0 (single layer) is fed by
+// POTENTIAL panels and read by POTENTIAL targets, set 1 (double layer) by NORMAL_DERIV panels / targets.
+// P2M: warp per leaf; an entry is a (panel, quadrature point) pair; lanes stage (c - q)^e / e!, the weight
+// q w_j Area and the panel normal of 32 entries, then lane = coefficient sums over the entries:
+//   set 0:  M_n += mult C_n,               C_n = dX^n / n!
+//   set 1:  M_n -= mult (n . grad_dX) C_n   (the reference writes the derivative as C_n n_d / dX_d)
+template <int SET>
+__global__ void __launch_bounds__(128)
+yk_bem_p2m_kernel(const int* __restrict__ leaves, int nleaves, const unsigned* __restrict__ bb,
+                  const unsigned* __restrict__ be, const double4* __restrict__ center,
+                  const double4* __restrict__ body, const bem::Panel* __restrict__ pan, const int* __restrict__ bc,
+                  bem::Rule rule, int P, double* __restrict__ M) {
+  extern __shared__ double yk_sh[];
+  const int nt = yk_terms(P), pw = 3 * (P + 1) + 4;       // powers, mult, normal
+  const int wl = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int w = blockIdx.x * (blockDim.x >> 5) + wl;
+  if (w >= nleaves) return;
+  double* tile = yk_sh + (size_t)wl * 32 * pw;
+  const int b = leaves[w];
+  const double4 c = center[b];
+  const unsigned b0 = bb[b], b1 = be[b];
+  const int K = rule.n;
+  const int nent = (int)(b1 - b0) * K;
+  double acc[kYkAcc];
+#pragma unroll
+  for (int i = 0; i < kYkAcc; ++i) acc[i] = 0.0;
+  for (int base = 0; base < nent; base += 32) {
+    const int ent = base + lane;
+    const int cnt = min(32, nent - base);
+    __syncwarp();
+    if (ent < nent) {
+      const unsigned i = b0 + ent / K;
+      const int qi = ent % K;
+      double* r = tile + lane * pw;
+      const bem::Panel& s = pan[i];
+      double q[3];
+      bem::quad_point(s, rule.pt[qi], q);
+      scaled_powers(P, c.x - q[0], c.y - q[1], c.z - q[2], r);
+      r[3 * (P + 1)] = bc[i] == SET ? body[i].w * rule.w[qi] * s.area : 0.0;
+      r[3 * (P + 1) + 1] = s.nrm[0]; r[3 * (P + 1) + 2] = s.nrm[1]; r[3 * (P + 1) + 3] = s.nrm[2];
+    }
+    __syncwarp();
+#pragma unroll
+    for (int a = 0; a < kYkAcc; ++a) {
+      const int t = lane + 32 * a;
+      if (t < nt) {
+        const int I = c_yI[P][t], J = c_yJ[P][t], Kk = c_yK[P][t];
+        const int ix = I, iy = P + 1 + J, iz = 2 * (P + 1) + Kk;
+        double sum = 0;
+        for (int m = 0; m < cnt; ++m) {
+          const double* r = tile + m * pw;
+          const double mult = r[3 * (P + 1)];
+          if (SET == 0) {
+            sum += mult * r[ix] * r[iy] * r[iz];
+          } else {
+            double g = 0;
+            if (I > 0) g += r[3 * (P + 1) + 1] * r[ix - 1] * r[iy] * r[iz];
+            if (J > 0) g += r[3 * (P + 1) + 2] * r[ix] * r[iy - 1] * r[iz];
+            if (Kk > 0) g += r[3 * (P + 1) + 3] * r[ix] * r[iy] * r[iz - 1];
+            sum -= mult * g;
+          }
+        }
+        acc[a] += sum;
+      }
+    }
+  }
+  double* Mb = M + (size_t)b * nt;
+#pragma unroll
+  for (int a = 0; a < kYkAcc; ++a) {
+    const int t = lane + 32 * a;
+    if (t < nt) Mb[t] = acc[a];
+  }
+}
+
+// L2P: warp per leaf, lane per target panel whose boundary condition selects this set
+template <int SET>
+__global__ void __launch_bounds__(128)
+yk_bem_l2p_kernel(const int* __restrict__ leaves, int nleaves, const unsigned* __restrict__ bb,
+                  const unsigned* __restrict__ be, const double4* __restrict__ center,
+                  const unsigned char* __restrict__ has_local, const bem::Panel* __restrict__ pan,
+                  const int* __restrict__ bc, int P, const double* __restrict__ L, double* __restrict__ res) {
+  extern __shared__ double yk_sh[];
+  const int nt = yk_terms(P), pw = 3 * (P + 1);
+  const int wl = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int w = blockIdx.x * (blockDim.x >> 5) + wl;
+  if (w >= nleaves) return;
+  const int b = leaves[w];
+  if (!has_local[b]) return;
+  double* Ls = yk_sh + (size_t)wl * (nt + 32 * pw);
+  double* powers = Ls + nt + lane * pw;
+  for (int t = lane; t < nt; t += 32) Ls[t] = L[(size_t)b * nt + t];
+  __syncwarp();
+  const double4 c = center[b];
+  for (unsigned i = bb[b] + lane; i < be[b]; i += 32) {
+    if (bc[i] != SET) continue;
+    const bem::Panel& tp = pan[i];
+    scaled_powers(P, tp.c[0] - c.x, tp.c[1] - c.y, tp.c[2] - c.z, powers);
+    double acc = 0;
+    for (int t = 0; t < nt; ++t) acc += Ls[t] * powers[c_yI[P][t]] * powers[P + 1 + c_yJ[P][t]] * powers[2 * (P + 1) + c_yK[P][t]];
+    res[i] = SET == 0 ? acc : -acc;
+  }
+}
+
+// derivative tables of the translation classes at order P (built once per order, kept)
+const double* yk_class_tables(fmmb_plan* plan, YukawaData* d, int P, cudaStream_t s) {
+  const bool use_classes = d->have_classes && plan->opts.m2l_mode != 1;
+  if (!use_classes) return nullptr;
+  const int nt = yk_terms(P);
+  auto it = d->tables.find(P);
+  if (it != d->tables.end()) return it->second->p;
+  DevBuf<double>* buf = new DevBuf<double>();
+  d->tables[P] = buf;
+  buf->resize((size_t)plan->cls.n_classes * nt);
+  yk_table_kernel<<<(int)plan->cls.n_classes, 128, 0, s>>>(P, d->kappa, plan->cls.class_vec.p, buf->p);
+  FMMB_CUDA(cudaGetLastError());
+  ++plan->launches;
+  return buf->p;
+}
+
+// M2M sweep -> M2L -> L2L sweep on d->M / d->L (leaf multipoles in, complete locals out)
+void yk_translations(fmmb_plan* plan, YukawaData* d, int P, const double* table, cudaStream_t s) {
+  Tree& T = plan->tree;
+  const int nb = T.nboxes;
+  cudaEvent_t* ev = plan->ev;
+  for (int l = T.nlevels - 2; l >= 0; --l) {
+    const int lo = T.level_off[l], hi = T.level_off[l + 1];
+    yk_m2m_kernel<<<hi - lo, 128, 0, s>>>(lo, hi, T.key.p, T.cbegin.p, T.cend.p, T.center.p, P, d->M.p);
+    ++plan->launches;
+  }
+  if (!plan->capturing) FMMB_CUDA(cudaEventRecord(ev[2], s));
+  yk_m2l_kernel<<<nb, 128, 0, s>>>(nb, T.m2l_off.p, T.m2l_src.p, table ? d->slot_class.p : nullptr, table, T.center.p, P,
+                                  d->kappa, d->M.p, d->L.p);
+  ++plan->launches;
+  if (!plan->capturing) FMMB_CUDA(cudaEventRecord(ev[3], s));
+  for (int l = 1; l < T.nlevels; ++l) {
+    const int lo = T.level_off[l], hi = T.level_off[l + 1];
+    yk_l2l_kernel<<<hi - lo, 128, 0, s>>>(lo, hi, T.parent.p, T.has_local.p, T.center.p, P, d->L.p);
+    ++plan->launches;
+  }
+}
+
 }  // namespace
 
 void yukawa_setup(fmmb_plan* plan, double kappa) {
@@ -470,23 +617,7 @@ void yukawa_execute(fmmb_plan* plan, const double* d_charges, double* d_results)
   double4* near = reinterpret_cast<double4*>(d->res_near.p);
   double4* far = reinterpret_cast<double4*>(d->res_far.p);
   plan->launches = 0;
-  const bool use_classes = d->have_classes && plan->opts.m2l_mode != 1;
-  const double* table = nullptr;
-  if (use_classes) {
-    // one derivative table per translation class (not per pair), built once per order and kept
-    auto it = d->tables.find(P);
-    if (it == d->tables.end()) {
-      DevBuf<double>* buf = new DevBuf<double>();
-      d->tables[P] = buf;
-      buf->resize((size_t)plan->cls.n_classes * nt);
-      yk_table_kernel<<<(int)plan->cls.n_classes, 128, 0, s>>>(P, d->kappa, plan->cls.class_vec.p, buf->p);
-      FMMB_CUDA(cudaGetLastError());
-      ++plan->launches;
-      table = buf->p;
-    } else {
-      table = it->second->p;
-    }
-  }
+  const double* table = yk_class_tables(plan, d, P, s);
 
   if (!plan->capturing) FMMB_CUDA(cudaEventRecord(ev[0], s));
   yk_gather<<<nblk(n, 256), 256, 0, s>>>(d_charges, T.perm.p, n, T.body.p);
@@ -510,21 +641,7 @@ void yukawa_execute(fmmb_plan* plan, const double* d_charges, double* d_results)
                                                      P, d->M.p);
     ++plan->launches;
   }
-  for (int l = T.nlevels - 2; l >= 0; --l) {
-    const int lo = T.level_off[l], hi = T.level_off[l + 1];
-    yk_m2m_kernel<<<hi - lo, 128, 0, s>>>(lo, hi, T.key.p, T.cbegin.p, T.cend.p, T.center.p, P, d->M.p);
-    ++plan->launches;
-  }
-  if (!plan->capturing) FMMB_CUDA(cudaEventRecord(ev[2], s));
-  yk_m2l_kernel<<<nb, 128, 0, s>>>(nb, T.m2l_off.p, T.m2l_src.p, use_classes ? d->slot_class.p : nullptr,
-                                  table, T.center.p, P, d->kappa, d->M.p, d->L.p);
-  ++plan->launches;
-  if (!plan->capturing) FMMB_CUDA(cudaEventRecord(ev[3], s));
-  for (int l = 1; l < T.nlevels; ++l) {
-    const int lo = T.level_off[l], hi = T.level_off[l + 1];
-    yk_l2l_kernel<<<hi - lo, 128, 0, s>>>(lo, hi, T.parent.p, T.has_local.p, T.center.p, P, d->L.p);
-    ++plan->launches;
-  }
+  yk_translations(plan, d, P, table, s);
   {
     const size_t sh = (size_t)4 * (nt + 32 * 3 * (P + 1)) * sizeof(double);
     if (T.n_own_leaves)
@@ -544,6 +661,60 @@ void yukawa_direct_raw(double kappa, const double* d_spts, const double* d_q, in
                        int64_t nt, double* d_out, cudaStream_t s) {
   yk_direct_kernel<<<nblk(nt, 128), 128, 0, s>>>(d_spts, d_q, ns, d_tpts, nt, kappa, reinterpret_cast<double4*>(d_out));
   FMMB_CUDA(cudaGetLastError());
+}
+
+
+// YukawaCartesianBEM matvec: cached near field (csrc/bem.cu, assembled with the Yukawa panel integrals), then per
+// active expansion set P2M -> translations -> L2P.  Multi-GPU: upward pass replicated, results all-gathered.
+void yukawa_bem_execute(fmmb_plan* plan, const double* d_charges, double* d_results) {
+  Tree& T = plan->tree;
+  YukawaData* d = plan->yukawa;
+  BemData* B = plan->bem;
+  const int P = plan->p;
+  if (P > kYkMaxP) throw StatusError{FMMB_ERR_UNSUPPORTED, "YukawaCartesianBEM is built for orders 1..10"};
+  const int nt = yk_terms(P);
+  cudaStream_t s = plan->stream;
+  cudaEvent_t* ev = plan->ev;
+  d->M.resize((size_t)T.nboxes * nt);
+  d->L.resize((size_t)T.nboxes * nt);
+  plan->launches = 0;
+  const double* table = yk_class_tables(plan, d, P, s);
+  if (!plan->capturing) FMMB_CUDA(cudaEventRecord(ev[0], s));
+  FMMB_CUDA(cudaEventRecord(ev[1], s));
+  if (!plan->capturing) FMMB_CUDA(cudaEventRecord(ev[6], s));
+  bem_begin(plan, d_charges, s);                       // charges to tree order, cached near field, far = 0
+  FMMB_CUDA(cudaEventRecord(ev[7], s));
+  if (!plan->capturing) FMMB_CUDA(cudaEventRecord(ev[12], s));
+  const bem::Rule rule = bem::make_rule(bem_rule_points(B));
+  const size_t sh_p2m = (size_t)4 * 32 * (3 * (P + 1) + 4) * sizeof(double);
+  const size_t sh_l2p = (size_t)4 * (nt + 32 * 3 * (P + 1)) * sizeof(double);
+  for (int set = 0; set < 2; ++set) {
+    if (!bem_set_active(B, set)) continue;
+    if (set == 0)
+      yk_bem_p2m_kernel<0><<<nblk(T.nleaves, 4), 128, sh_p2m, s>>>(T.leaves.p, T.nleaves, T.bbegin.p, T.bend.p, T.center.p,
+                                                                  T.body.p, bem_panels(B), bem_bc(B), rule, P, d->M.p);
+    else
+      yk_bem_p2m_kernel<1><<<nblk(T.nleaves, 4), 128, sh_p2m, s>>>(T.leaves.p, T.nleaves, T.bbegin.p, T.bend.p, T.center.p,
+                                                                  T.body.p, bem_panels(B), bem_bc(B), rule, P, d->M.p);
+    ++plan->launches;
+    yk_translations(plan, d, P, table, s);
+    if (T.n_own_leaves) {
+      if (set == 0)
+        yk_bem_l2p_kernel<0><<<nblk(T.n_own_leaves, 4), 128, sh_l2p, s>>>(T.own_leaves.p, T.n_own_leaves, T.bbegin.p, T.bend.p,
+                                                                         T.center.p, T.has_local.p, bem_panels(B), bem_bc(B),
+                                                                         P, d->L.p, bem_res_far(B));
+      else
+        yk_bem_l2p_kernel<1><<<nblk(T.n_own_leaves, 4), 128, sh_l2p, s>>>(T.own_leaves.p, T.n_own_leaves, T.bbegin.p, T.bend.p,
+                                                                         T.center.p, T.has_local.p, bem_panels(B), bem_bc(B),
+                                                                         P, d->L.p, bem_res_far(B));
+      ++plan->launches;
+    }
+  }
+  if (!plan->capturing) FMMB_CUDA(cudaEventRecord(ev[4], s));
+  finish_results(plan, bem_res_near(B), bem_res_far(B), 1, d_results, s);
+  if (!plan->capturing) FMMB_CUDA(cudaEventRecord(ev[5], s));
+  FMMB_CUDA(cudaGetLastError());
+  plan->timed = true;
 }
 
 }  // namespace fmmb

@@ -190,6 +190,123 @@ BEM_HD double eval_dGdn(const Panel& s, const double* t, const Rule& rule, const
   }
   return r;
 }
+// ---- YukawaCartesianBEM near field (reference kernel/YukawaCartesianBEM.hpp:145-204 with the YUKAWA branch of
+// ---- examples/BEM/SemiAnalytical.hpp:13-203): exp(-kappa r) / r and its normal derivative ----------------------
+BEM_HD void line_int_yk(double& G, double& dGdn, double z, double x, double v1, double v2, double kappa) {
+  const double theta1 = atan2(v1, x), theta2 = atan2(v2, x);
+  const double dtheta = theta2 - theta1, thetam = (theta2 + theta1) / 2;
+  const double absZ = fabs(z), signZ = absZ < 1e-10 ? 0 : z / absZ;
+  const double expKz = exp(-kappa * absZ);
+  const double xk[5] = {-9.06179846e-01, -5.38469310e-01, 1.78162900e-17, 9.06179846e-01, 5.38469310e-01};
+  const double wk[5] = {0.23692689, 0.47862867, 0.56888889, 0.23692689, 0.47862867};
+  for (int i = 0; i < 5; ++i) {
+    const double thetak = dtheta / 2 * xk[i] + thetam;
+    const double Rtheta = x / cos(thetak);
+    const double R = sqrt(Rtheta * Rtheta + z * z);
+    const double expKr = exp(-kappa * R);
+    if (kappa > 1e-10) {
+      G += -wk[i] * (expKr - expKz) / kappa * dtheta / 2;
+      dGdn += wk[i] * (z / R * expKr - expKz * signZ) * dtheta / 2;
+    } else {                                          // devolves to Laplace
+      G += wk[i] * (R - absZ) * dtheta / 2;
+      dGdn += wk[i] * (z / R - signZ) * dtheta / 2;
+    }
+  }
+}
+BEM_HD void int_side_yk(double& G, double& dGdn, const double* v1, const double* v2, double p, double kappa) {
+  const double v21[3] = {v2[0] - v1[0], v2[1] - v1[1], v2[2] - v1[2]};
+  const double L21 = norm3(v21);
+  const double v21u[3] = {v21[0] / L21, v21[1] / L21, v21[2] / L21};
+  const double unit[3] = {0, 0, 1};
+  double orthog[3], rot[9], v1new[3], v2new[3];
+  cross3(unit, v21u, orthog);
+  for (int i = 0; i < 3; ++i) { rot[i * 3] = orthog[i]; rot[i * 3 + 1] = v21u[i]; rot[i * 3 + 2] = unit[i]; }
+  matvec3(rot, v1, v1new);
+  if (v1new[0] < 0) {
+    for (int i = 0; i < 9; ++i) rot[i] = -rot[i];
+    rot[8] = 1.;
+    matvec3(rot, v1, v1new);
+  }
+  matvec3(rot, v2, v2new);
+  const double x = v1new[0];
+  if ((v1new[1] > 0 && v2new[1] < 0) || (v1new[1] < 0 && v2new[1] > 0)) {
+    double G1 = 0, d1 = 0, G2 = 0, d2 = 0;
+    line_int_yk(G1, d1, p, x, 0, v1new[1], kappa);
+    line_int_yk(G2, d2, p, x, v2new[1], 0, kappa);
+    G += G1 + G2;
+    dGdn += d1 + d2;
+  } else {
+    double G1 = 0, d1 = 0;
+    line_int_yk(G1, d1, p, x, v1new[1], v2new[1], kappa);
+    G -= G1;
+    dGdn -= d1;
+  }
+}
+BEM_HD void semi_analytical_yk(const Panel& s, const double* x, double kappa, double& G, double& dGdn) {
+  double xp[3], y1p[3], y2p[3];
+  const double y0p[3] = {0, 0, 0};
+  for (int k = 0; k < 3; ++k) { xp[k] = x[k] - s.v[0][k]; y1p[k] = s.v[1][k] - s.v[0][k]; y2p[k] = s.v[2][k] - s.v[0][k]; }
+  double X[3] = {y1p[0], y1p[1], y1p[2]}, Y[3], Z[3];
+  cross3(y1p, y2p, Z);
+  const double Xn = norm3(X), Zn = norm3(Z);
+  for (int k = 0; k < 3; ++k) { X[k] /= Xn; Z[k] /= Zn; }
+  cross3(Z, X, Y);
+  const double rot[9] = {X[0], X[1], X[2], Y[0], Y[1], Y[2], Z[0], Z[1], Z[2]};
+  double p0[3], p1[3], p2[3], xpl[3], f0[3], f1[3], f2[3];
+  matvec3(rot, y0p, p0); matvec3(rot, y1p, p1); matvec3(rot, y2p, p2); matvec3(rot, xp, xpl);
+  for (int k = 0; k < 3; ++k) { f0[k] = p0[k] - xpl[k]; f1[k] = p1[k] - xpl[k]; f2[k] = p2[k] - xpl[k]; }
+  f0[2] = p0[2]; f1[2] = p1[2]; f2[2] = p2[2];
+  G = 0; dGdn = 0;
+  int_side_yk(G, dGdn, f0, f1, xpl[2], kappa);
+  int_side_yk(G, dGdn, f1, f2, xpl[2], kappa);
+  int_side_yk(G, dGdn, f2, f0, xpl[2], kappa);
+}
+BEM_HD double eval_G_yk(const Panel& s, const double* t, const Rule& rule, double kappa) {
+  const double d[3] = {t[0] - s.c[0], t[1] - s.c[1], t[2] - s.c[2]};
+  const double dist = norm3(d);
+  if (sqrt(2 * s.area) / dist >= 0.5) {
+    double G, dGdn;
+    semi_analytical_yk(s, t, kappa, G, dGdn);
+    return G;
+  }
+  double r = 0;
+  for (int i = 0; i < rule.n; ++i) {
+    double q[3];
+    quad_point(s, rule.pt[i], q);
+    const double e[3] = {t[0] - q[0], t[1] - q[1], t[2] - q[2]};
+    const double dd = norm3(e);
+    const double inv = dd < 1e-8 ? 0. : 1. / dd;
+    r += rule.w[i] * s.area * exp(-kappa * dd) * inv;
+  }
+  return r;
+}
+BEM_HD double eval_dGdn_yk(const Panel& s, const double* t, const Rule& rule, double kappa) {
+  const double d[3] = {t[0] - s.c[0], t[1] - s.c[1], t[2] - s.c[2]};
+  const double dist = norm3(d);
+  if (dist < 1e-8) return 2 * M_PI;
+  if (sqrt(2 * s.area) / dist >= 0.5) {
+    double G, dGdn;
+    semi_analytical_yk(s, t, kappa, G, dGdn);
+    return -dGdn;
+  }
+  double res = 0;
+  for (int i = 0; i < rule.n; ++i) {
+    double q[3];
+    quad_point(s, rule.pt[i], q);
+    const double dx[3] = {t[0] - q[0], t[1] - q[1], t[2] - q[2]};
+    const double r = norm3(dx);
+    double inv_r = 1. / r, inv_r2 = inv_r * inv_r;
+    if (r < 1e-8) { inv_r = 0.; inv_r2 = 0.; }
+    const double f = exp(-kappa * r) * inv_r * (kappa * r + 1) * inv_r2;
+    res += rule.w[i] * s.area * (-(dx[0] * f) * s.nrm[0] - (dx[1] * f) * s.nrm[1] - (dx[2] * f) * s.nrm[2]);
+  }
+  return res;
+}
+/** YukawaCartesianBEM::operator() (:213-230) */
+BEM_HD double kernel_yk(int target_bc, const double* target_centre, const Panel& s, const Rule& rule, double kappa) {
+  return target_bc == 0 ? eval_G_yk(s, target_centre, rule, kappa) : eval_dGdn_yk(s, target_centre, rule, kappa);
+}
+
 /** K(t, s): the TARGET's boundary condition picks the kernel (operator(), :273-297).
  * bc 0 = POTENTIAL (G), 1 = NORMAL_DERIV (dG/dn). */
 BEM_HD double kernel(int target_bc, const double* target_centre, const Panel& s, const Rule& rule, const Rule& fine) {

@@ -125,6 +125,23 @@ def yukawa_case(name, n, p, kappa, ncrit, theta, points=None, charges=None, dire
         print(name, meta["pot"], "err vs direct", meta["err_pot"], meta["err_force"])
 
 
+def yukawa_bem_case(name, recursions, p, k, kappa, ncrit, bc):
+    """YukawaCartesianBEM through oracle/_ref/ref_yukawa_bem (unmodified class behind the arity adapter): the TREECODE
+    evaluator and Direct::matvec.  (The reference's FMM evaluator is broken for this kernel, SURVEY 8c.)"""
+    exe = os.path.join(ROOT, "oracle", "_ref", "ref_yukawa_bem")
+    with tempfile.TemporaryDirectory() as tmp:
+        pre = os.path.join(tmp, "d")
+        cmd = [exe, "-recursions", str(recursions), "-P", str(p), "-K", str(k), "-kappa", repr(kappa), "-ncrit", str(ncrit),
+               "-bc", str(bc), "-rand", "-sparse", "0", "-tree", "-direct", "-dump", pre]
+        out = subprocess.check_output(cmd, env=dict(os.environ, OMP_NUM_THREADS="1"), cwd=tmp).decode()
+        meta = json.loads([l for l in out.splitlines() if l.startswith("REF_JSON")][0][len("REF_JSON "):])
+        meta["kappa"] = kappa
+        np.savez_compressed(os.path.join(HERE, name + ".npz"), meta=json.dumps(meta),
+                            verts=np.fromfile(pre + ".verts.f64").reshape(-1, 3, 3), charges=np.fromfile(pre + ".charges.f64"),
+                            results=np.fromfile(pre + ".results.f64"), direct=np.fromfile(pre + ".direct.f64"))
+        print(name, "treecode vs direct", meta["err_vs_direct"])
+
+
 def main():
     if not os.path.exists(REF):
         sys.exit("oracle/_ref/ref_laplace missing: run `make -C oracle ref` in the build container")
@@ -150,6 +167,8 @@ def main():
     # 2c. YukawaCartesian (point kernel) through the arity adapter
     yukawa_case("yukawa_drand48_n3000_p5", 3000, 5, 0.125, 32, 0.5)
     yukawa_case("yukawa_two_scale_n4000_p6", n, 6, 2.0, 12, 0.6, pts, q)
+    yukawa_bem_case("yukawa_bem_tree_2048_p6_bc0", 5, 6, 4, 1.0, 32, 0)
+    yukawa_bem_case("yukawa_bem_tree_2048_p6_bc1", 5, 6, 4, 1.0, 32, 1)
     # 3. checksums only, larger sizes
     sums = {}
     for key, (nn, pp) in {"n10000_p5": (10000, 5), "c1_n100000_p5": (100000, 5)}.items():

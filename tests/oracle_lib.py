@@ -51,6 +51,9 @@ def load():
         L.fmmo_stokes_direct.argtypes = [ctypes.c_int, vp, ctypes.c_int, vp, ctypes.c_int, vp, vp, ctypes.c_int]
         L.fmmo_yukawa_execute.argtypes = [vp, ctypes.c_int, ctypes.c_double, vp, vp, ctypes.c_int]
         L.fmmo_yukawa_direct.argtypes = [ctypes.c_int, vp, ctypes.c_double, vp, ctypes.c_int, vp, vp, ctypes.c_int]
+        L.fmmo_yukawa_bem_execute.argtypes = [vp, ctypes.c_int, ctypes.c_int, ctypes.c_double, vp, vp, vp, vp,
+                                              ctypes.c_int, ctypes.c_int]
+        L.fmmo_yukawa_bem_direct.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_double, vp, vp, vp, vp, ctypes.c_int]
         L.fmmo_unit_sphere.argtypes = [ctypes.c_int, vp]
         L.fmmo_panel_centers.argtypes = [ctypes.c_int, vp, vp]
         L.fmmo_bem_execute.argtypes = [vp, ctypes.c_int, ctypes.c_int, vp, vp, vp, vp, ctypes.c_int]
@@ -185,6 +188,31 @@ class BemOracle(Oracle):
         q = np.ascontiguousarray(np.asarray(charges, dtype=np.float64).reshape(-1))
         out = np.zeros(self.n)
         self.L.fmmo_bem_direct(self.n, K, _p(self.verts), _p(self.bc), _p(q), _p(out), threads or os.cpu_count() or 1)
+        return out
+
+
+class YukawaBemOracle(BemOracle):
+    """Oracle tree on the panel centres + the restated YukawaCartesianBEM matvec (FMM: parity unpinned, see
+    oracle/fmm_oracle.cpp; treecode and direct: pinned against the reference class)."""
+
+    def __init__(self, verts, bc, kappa, ncrit=64, theta=0.5):
+        super().__init__(verts, bc, ncrit, theta)
+        self.kappa = float(kappa)
+
+    def execute(self, charges, P, K=4, treecode=False, threads=None):
+        q = np.ascontiguousarray(np.asarray(charges, dtype=np.float64).reshape(-1))
+        res = np.zeros(self.n)
+        rc = self.L.fmmo_yukawa_bem_execute(self.h, P, K, self.kappa, _p(self.verts), _p(self.bc), _p(q), _p(res),
+                                            2 if treecode else 0, threads or os.cpu_count() or 1)
+        if rc != 0:
+            raise RuntimeError("oracle Yukawa BEM execute failed: %d" % rc)
+        return res
+
+    def direct(self, charges, K=4, threads=None):
+        q = np.ascontiguousarray(np.asarray(charges, dtype=np.float64).reshape(-1))
+        out = np.zeros(self.n)
+        self.L.fmmo_yukawa_bem_direct(self.n, K, self.kappa, _p(self.verts), _p(self.bc), _p(q), _p(out),
+                                      threads or os.cpu_count() or 1)
         return out
 
 

@@ -191,3 +191,20 @@ def test_treecode_restatement_matches_reference(name, P, ncrit, theta):
     g = dict(np.load(os.path.join(GOLDEN, name + ".npz")))
     res = O.Oracle(g["points"], ncrit, theta).execute(g["charges"], P, mode=2, threads=1)
     assert np.array_equal(res, g["results"])
+
+
+# ---- YukawaCartesianBEM: the near field (Direct::matvec) and the TREECODE evaluator are pinned to the reference class
+# ---- (oracle/_ref/ref_yukawa_bem); its FMM evaluator is broken for this kernel, so the restated FMM is checked
+# ---- against Direct and the treecode only ("parity unpinned" for the far field) ------------
+@pytest.mark.parametrize("bc", [0, 1])
+def test_yukawa_bem_restatement(bc):
+    g = dict(np.load(os.path.join(GOLDEN, "yukawa_bem_tree_2048_p6_bc%d.npz" % bc)))
+    orc = O.YukawaBemOracle(g["verts"], bc, 1.0, ncrit=32)
+    d = orc.direct(g["charges"], 4)
+    assert np.array_equal(d, g["direct"])                                   # operator(): bit-identical
+    t = orc.execute(g["charges"], 6, 4, treecode=True, threads=1)
+    assert O.rel_l2(t, g["results"]) <= 1e-14                               # treecode (getCoeff by its general recurrence)
+    f = orc.execute(g["charges"], 6, 4, treecode=False)
+    # the restated FMM approximates the same sum as the treecode, to the truncation error of order 6
+    assert O.rel_l2(f, d) < (1e-4 if bc == 0 else 1e-3)
+    assert O.rel_l2(t, d) < (1e-4 if bc == 0 else 1e-3)

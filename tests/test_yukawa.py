@@ -74,3 +74,41 @@ def test_accuracy_vs_direct_and_limits():
         plan.kernel().set_p(11)                          # orders 1..10 are built
     with pytest.raises(F.FmmbError):
         make_plan(pts[:1000], 12, kappa)
+
+
+# ---- YukawaCartesianBEM ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("rec,P,K,kappa", [(5, 6, 4, 1.0), (6, 8, 4, 0.125), (5, 4, 3, 2.0)])
+def test_bem_matvec_vs_oracle(rec, P, K, kappa):
+    """CUDA path against the oracle restatement (same algorithm: 1e-10) and against Direct (truncation error).
+    The oracle's near field and treecode are pinned to the reference class; the reference's own FMM evaluator is
+    broken for this kernel."""
+    v = O.unit_sphere(rec)
+    q = np.random.default_rng(rec).random(len(v)) - 0.3
+    for bc in (0, 1):
+        orc = O.YukawaBemOracle(v, bc, kappa, ncrit=32)
+        opts = F.FMMOptions()
+        opts.set_max_per_box(32)
+        plan = F.FMM_plan(F.YukawaCartesianBEM(P, kappa, K), F.Panels(v, bc), opts)
+        res = plan.execute(q)
+        assert res.shape == (len(v),)
+        assert O.rel_l2(res, orc.execute(q, P, K)) <= TOL
+        assert np.array_equal(plan.execute(q), res)
+        if rec == 5:
+            assert O.rel_l2(res, orc.direct(q, K)) < 5e-3
+
+
+def test_bem_golden_near_field_and_gmres():
+    """Fixture from the reference class: Direct::matvec values (pinned near field) and a relaxed GMRES solve."""
+    g = dict(np.load(os.path.join(GOLDEN, "yukawa_bem_tree_2048_p6_bc0.npz")))
+    v, q = g["verts"], g["charges"]
+    opts = F.FMMOptions()
+    opts.set_mac_theta(1e-3)                 # nothing is accepted: the whole matrix is near field
+    opts.set_max_per_box(4096)
+    plan = F.FMM_plan(F.YukawaCartesianBEM(6, 1.0, 4), F.Panels(v, 0), opts)
+    assert O.rel_l2(plan.execute(q), g["direct"]) <= 1e-12
+    # first-kind solve on the sphere with the device-resident relaxed GMRES
+    plan = F.FMM_plan(F.YukawaCartesianBEM(8, 1.0, 4), F.Panels(v, 0))
+    b = plan.execute(np.ones(len(v)))
+    rep = F.GMRES(plan, np.zeros(len(v)), b, F.SolverOptions(residual=1e-6, max_iters=100, restart=100, max_p=8))
+    assert rep["final_residual"] < 1e-6 and rep["iterations"] < 40
+    assert np.abs(rep["x"] - 1.0).max() < 5e-2
