@@ -200,8 +200,9 @@ class FMM_plan:
         self._rdim = self.K.result_dim
         self._cdim = self.K.charge_dim
         src = capi.Sources(self._n, capi.ptr(pts), capi.ptr(verts), capi.ptr(bc))
+        near_only = 2 if opts.block_diagonal else (1 if opts.local_evaluation else 0)
         op = capi.Options(opts.theta, opts.NCRIT_, opts.evaluator, opts.device, 0,
-                          getattr(opts, "rank", 0), getattr(opts, "nranks", 1), 0)
+                          getattr(opts, "rank", 0), getattr(opts, "nranks", 1), near_only)
         h = ctypes.c_void_p()
         capi.check(lib.fmmb_plan_create(ctypes.byref(kd), ctypes.byref(src), ctypes.byref(op), ctypes.byref(h)))
         self._h = h

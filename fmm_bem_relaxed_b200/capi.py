@@ -36,7 +36,7 @@ class KernelDesc(ctypes.Structure):
 class Options(ctypes.Structure):
     _fields_ = [("theta", ctypes.c_double), ("ncrit", ctypes.c_uint32), ("evaluator", ctypes.c_int32),
                 ("device", ctypes.c_int32), ("m2l_mode", ctypes.c_int32), ("rank", ctypes.c_int32),
-                ("nranks", ctypes.c_int32), ("reserved", ctypes.c_int32)]
+                ("nranks", ctypes.c_int32), ("near_only", ctypes.c_int32)]
 
 
 class Sources(ctypes.Structure):

@@ -383,7 +383,7 @@ void bem_execute(fmmb_plan* plan, const double* d_charges, double* d_results) {
     attr = true;
   }
   for (int set = 0; set < 2; ++set) {
-    if (!B->set_active[set]) continue;
+    if (!B->set_active[set] || plan->near_only) continue;   // near_only: plans for preconditioners, no far field
     if (set == 0)
       bem_p2m_kernel<0><<<nblk(T.nleaves, warps), 32 * warps, sh, s>>>(T.leaves.p, T.nleaves, T.bbegin.p, T.bend.p,
                                                                       T.center.p, T.body.p, B->pan.p, B->bc.p, P,

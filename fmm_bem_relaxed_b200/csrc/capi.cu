@@ -85,6 +85,11 @@ int fmmb_plan_create(const fmmb_kernel_desc* kernel, const fmmb_sources* sources
   if (options) opts = *options;
   if (opts.nranks < 1) { opts.nranks = 1; opts.rank = 0; }
   if (!(opts.theta > 0)) { set_error("theta must be positive"); return FMMB_ERR_INVALID; }
+  if (opts.near_only < 0 || opts.near_only > 2) { set_error("near_only: 0, 1 or 2"); return FMMB_ERR_INVALID; }
+  if (opts.near_only && (is_stokes || kernel->kind == FMMB_YUKAWA_CARTESIAN)) {
+    set_error("near-field-only plans are built for LaplaceSpherical and the BEM kernel classes");
+    return FMMB_ERR_UNSUPPORTED;
+  }
   if (opts.ncrit < 1) { set_error("ncrit must be at least 1"); return FMMB_ERR_INVALID; }
   if (opts.evaluator != FMMB_EVAL_FMM && opts.evaluator != FMMB_EVAL_TREECODE) { set_error("unknown evaluator"); return FMMB_ERR_INVALID; }
   if (opts.evaluator == FMMB_EVAL_TREECODE && kernel->kind != FMMB_LAPLACE_SPHERICAL) {
@@ -129,7 +134,9 @@ int fmmb_plan_create(const fmmb_kernel_desc* kernel, const fmmb_sources* sources
       pts = centres.data();
     }
     build_tree(plan, pts, sources->n);
-    build_m2l_classes(plan);
+    plan->near_only = opts.near_only;
+    if (opts.near_only == 2) restrict_p2p_to_self(plan);
+    if (!opts.near_only) build_m2l_classes(plan);
     if (is_bem) plan->p2p_item_mode = 0;   // one cached near-field block per chunk of <= 32 targets
     build_p2p_items(plan);
     if (is_bem) bem_setup(plan, sources->vertices, sources->bc, kernel->quad_k,

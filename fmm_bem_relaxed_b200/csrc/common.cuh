@@ -222,6 +222,7 @@ struct fmmb_plan {
   int p2p_warps = 1;                 // warps per block of the near-field pair kernels
   int p2p_kernel = 2;                // 1 = merged source runs with prefetch (p2p_run_kernel), 0 = per source leaf
   int p2p_unroll = 4;
+  int near_only = 0;                 // fmmb_options.near_only
   int p2p_chunk = 32, p2p_min_chunk = 8;  // targets per near-field work item (chosen at plan time)
   // CUDA graphs: one captured matvec per (order, charge pointer, result pointer)
   bool use_graph = true;
@@ -243,6 +244,7 @@ struct fmmb_plan {
 namespace fmmb {
 // tree.cu
 void build_tree(fmmb_plan* plan, const double* points_host, int64_t n);
+void restrict_p2p_to_self(fmmb_plan* plan);
 void partition_ranges(const double* w, int64_t n, int nranks, int64_t* cuts);
 void comm_unique_id(unsigned char* id);
 void comm_init(fmmb_plan* plan, const unsigned char* id);

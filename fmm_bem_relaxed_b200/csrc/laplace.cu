@@ -1069,11 +1069,16 @@ void laplace_execute(fmmb_plan* plan, const double* d_charges, double* d_results
   // One GPU: the near field starts right away and fills the gaps of the latency-bound upward chain.  Sharded with
   // an owned upward pass: it starts once the owned M2M sweep is enqueued (hook below), so that the short dependent
   // kernels before the multipole exchange are not queued behind its blocks and it overlaps the exchange instead.
-  const bool defer_p2p = p2m_owned && s2 != s;
+  const bool defer_p2p = p2m_owned && s2 != s && !plan->near_only;
   if (!defer_p2p) launch_p2p();
 
   // upward sweep
   if (!plan->capturing) FMMB_CUDA(cudaEventRecord(ev[12], s));
+  if (plan->near_only) {
+    // plans for preconditioners (FMMOptions::local_evaluation / block_diagonal): no far field at all
+    FMMB_CUDA(cudaMemsetAsync(plan->res_far.p, 0, (size_t)n * sizeof(double4), s));
+    if (!plan->capturing) { FMMB_CUDA(cudaEventRecord(ev[2], s)); FMMB_CUDA(cudaEventRecord(ev[3], s)); }
+  } else {
   const int p2m_warps = pp <= 64 ? 4 : 1;          // shared tile: warps x 32 bodies x P^2 doubles
   const size_t p2m_sh = (size_t)p2m_warps * 32 * (pp | 1) * sizeof(double);
   static bool p2m_attr = false;
@@ -1107,6 +1112,7 @@ void laplace_execute(fmmb_plan* plan, const double* d_charges, double* d_results
         plan->res_far.p);
   }
   ++plan->launches;
+  }
   // peer exchange: this rank no longer reads its multipole array -> peers may push the next matvec's rows
   if (plan->peer_ready) peer_read_done(plan, s);
   if (!plan->capturing) FMMB_CUDA(cudaEventRecord(ev[4], s));

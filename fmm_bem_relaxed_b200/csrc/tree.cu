@@ -703,4 +703,42 @@ void build_tree(fmmb_plan* plan, const double* points_host, int64_t n) {
   FMMB_CUDA(cudaStreamSynchronize(s));
 }
 
+
+// FMMOptions::block_diagonal (reference include/executor/EvalDiagonalSparse.hpp:32-47): the near field keeps only
+// the interaction of every leaf with itself.  Rewrites the target-major P2P lists in place; everything built from
+// them afterwards (work items, source runs, cached BEM blocks) follows.
+namespace {
+__global__ void self_list_offsets(const unsigned* __restrict__ key, int nb, int* __restrict__ flag) {
+  int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b <= nb) flag[b] = b < nb ? (int)(key[b] >> 31) : 0;
+}
+__global__ void self_list_fill(const unsigned* __restrict__ key, const int* __restrict__ off, int nb, int* __restrict__ src) {
+  int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b < nb && (key[b] >> 31)) src[off[b]] = b;
+}
+}  // namespace
+
+void restrict_p2p_to_self(fmmb_plan* plan) {
+  Tree& T = plan->tree;
+  cudaStream_t s = plan->stream;
+  const int nb = T.nboxes;
+  DevBuf<int> flag;
+  flag.resize(nb + 1);
+  self_list_offsets<<<(nb + 256) / 256, 256, 0, s>>>(T.key.p, nb, flag.p);
+  T.p2p_off.resize(nb + 1);
+  size_t bytes = 0;
+  FMMB_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, bytes, flag.p, T.p2p_off.p, nb + 1, s));
+  DevBuf<char> tmp;
+  tmp.resize(bytes);
+  FMMB_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, bytes, flag.p, T.p2p_off.p, nb + 1, s));
+  T.n_p2p = T.nleaves;
+  T.p2p_src.resize(T.n_p2p);
+  self_list_fill<<<(nb + 255) / 256, 256, 0, s>>>(T.key.p, T.p2p_off.p, nb, T.p2p_src.p);
+  FMMB_CUDA(cudaGetLastError());
+  std::vector<unsigned> key = T.key.to_host(s), b0 = T.bbegin.to_host(s), b1 = T.bend.to_host(s);
+  int64_t pairs = 0;
+  for (int b = 0; b < nb; ++b) if (key[b] >> 31) pairs += (int64_t)(b1[b] - b0[b]) * (b1[b] - b0[b]);
+  T.n_p2p_body_pairs = pairs;
+}
+
 }  // namespace fmmb

@@ -678,7 +678,7 @@ void yukawa_bem_execute(fmmb_plan* plan, const double* d_charges, double* d_resu
   d->M.resize((size_t)T.nboxes * nt);
   d->L.resize((size_t)T.nboxes * nt);
   plan->launches = 0;
-  const double* table = yk_class_tables(plan, d, P, s);
+  const double* table = plan->near_only ? nullptr : yk_class_tables(plan, d, P, s);
   if (!plan->capturing) FMMB_CUDA(cudaEventRecord(ev[0], s));
   FMMB_CUDA(cudaEventRecord(ev[1], s));
   if (!plan->capturing) FMMB_CUDA(cudaEventRecord(ev[6], s));
@@ -689,7 +689,7 @@ void yukawa_bem_execute(fmmb_plan* plan, const double* d_charges, double* d_resu
   const size_t sh_p2m = (size_t)4 * 32 * (3 * (P + 1) + 4) * sizeof(double);
   const size_t sh_l2p = (size_t)4 * (nt + 32 * 3 * (P + 1)) * sizeof(double);
   for (int set = 0; set < 2; ++set) {
-    if (!bem_set_active(B, set)) continue;
+    if (!bem_set_active(B, set) || plan->near_only) continue;
     if (set == 0)
       yk_bem_p2m_kernel<0><<<nblk(T.nleaves, 4), 128, sh_p2m, s>>>(T.leaves.p, T.nleaves, T.bbegin.p, T.bend.p, T.center.p,
                                                                   T.body.p, bem_panels(B), bem_bc(B), rule, P, d->M.p);

@@ -13,9 +13,9 @@
 class FMMOptions {
  public:
   bool lazy_evaluation;   // accepted; the GPU plan always replays precomputed lists
-  bool local_evaluation;  // near-field-only plans for preconditioners: not built yet
-  bool sparse_local;      // BEM cached near field: not built yet
-  bool block_diagonal;    // not built yet
+  bool local_evaluation;  // near-field-only plan (preconditioners): honoured
+  bool sparse_local;      // accepted; the BEM near field is always cached on the GPU
+  bool block_diagonal;    // leaf-with-itself blocks only (preconditioners): honoured
 
   enum EvalType { FMM, TREECODE };
   EvalType evaluator;

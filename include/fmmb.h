@@ -81,7 +81,10 @@ typedef struct {
   int32_t m2l_mode;    /* 0 = auto, 1 = per-pair kernel only, 2 = prefer batched translation classes */
   int32_t rank;        /* multi-GPU: this process's rank (0 when nranks <= 1) */
   int32_t nranks;      /* multi-GPU: number of ranks sharing the matvec; 0 or 1 = single GPU */
-  int32_t reserved;
+  int32_t near_only;   /* plans for preconditioners: 0 = full matvec; 1 = FMMOptions::local_evaluation, only the
+                          near field of the traversal (reference include/executor/EvalLocal.hpp:12-72,
+                          EvalLocalSparse.hpp); 2 = FMMOptions::block_diagonal, only leaf-with-itself blocks
+                          (EvalDiagonalSparse.hpp:12-80).  LaplaceSpherical and the BEM kernel classes. */
 } fmmb_options;
 
 /* Sources, host memory, borrowed for the duration of the call.

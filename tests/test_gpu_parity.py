@@ -218,3 +218,54 @@ def test_treecode_vs_oracle_and_fmm():
     # other kernel classes do not have the treecode path yet
     with pytest.raises(F.FmmbError):
         F.FMM_plan(F.StokesSpherical(4), pts, opts)
+
+
+def _near_field_numpy(t, pts, q, self_only):
+    """Sum of the Laplace pair kernel over the near-field lists of the tree (what EvalLocal evaluates)."""
+    boxes, perm = t["boxes"], t["perm"].astype(np.int64)
+    out = np.zeros((len(pts), 4))
+    for b in np.nonzero(boxes[:, 7])[0]:
+        tid = perm[boxes[b, 4]:boxes[b, 5]]
+        srcs = [b] if self_only else t["p2p_idx"][t["p2p_off"][b]:t["p2p_off"][b + 1]]
+        sid = np.concatenate([perm[boxes[s, 4]:boxes[s, 5]] for s in srcs])
+        d = pts[sid][None, :, :] - pts[tid][:, None, :]
+        r2 = (d * d).sum(-1)
+        inv = np.where(r2 < 1e-8, 0.0, 1.0 / np.sqrt(np.where(r2 < 1e-8, 1.0, r2)))
+        out[tid, 0] = (inv * q[sid]).sum(1)
+        out[tid, 1:] = (d * (inv ** 3 * q[sid])[:, :, None]).sum(1)
+    return out
+
+
+def test_near_field_only_plans_for_preconditioners():
+    """FMMOptions::local_evaluation (EvalLocal.hpp) and block_diagonal (EvalDiagonalSparse.hpp): the plans the
+    reference's LocalPC / BlockDiagonalPC preconditioners are built on."""
+    n = 6000
+    pts, q = O.drand48_inputs(n)
+    t = O.Oracle(pts, 24, 0.5).tree()
+    for attr, self_only in (("local_evaluation", False), ("block_diagonal", True)):
+        opts = F.FMMOptions()
+        opts.set_max_per_box(24)
+        setattr(opts, attr, True)
+        plan = F.FMM_plan(F.LaplaceSpherical(5), pts, opts)
+        res = plan.execute(q)
+        assert O.rel_l2(res, _near_field_numpy(t, pts, q, self_only)) <= 1e-12
+        assert np.array_equal(plan.execute(q), res)
+    # BEM kernels: the cached near-field matrix alone
+    v = O.unit_sphere(5)
+    qq = np.random.default_rng(2).random(len(v))
+    opts = F.FMMOptions()
+    opts.local_evaluation = True
+    near = F.FMM_plan(F.LaplaceSphericalBEM(6, 4), F.Panels(v), opts).execute(qq)
+    opts = F.FMMOptions()
+    opts.set_mac_theta(1e-3)                     # nothing accepted: the full matrix is near field
+    opts.set_max_per_box(4096)
+    full = F.FMM_plan(F.LaplaceSphericalBEM(6, 4), F.Panels(v), opts).execute(qq)
+    fmm = F.FMM_plan(F.LaplaceSphericalBEM(6, 4), F.Panels(v)).execute(qq)
+    assert O.rel_l2(fmm, full) < 1e-4 and 0.05 < O.rel_l2(near, full) < 0.9     # the near field is a part of it
+    opts = F.FMMOptions()
+    opts.block_diagonal = True
+    diag = F.FMM_plan(F.LaplaceSphericalBEM(6, 4), F.Panels(v), opts)
+    assert diag.info().n_p2p_box_pairs == diag.info().n_leaves
+    assert np.isfinite(diag.execute(qq)).all()
+    with pytest.raises(F.FmmbError):
+        F.FMM_plan(F.StokesSpherical(4), pts, opts)
