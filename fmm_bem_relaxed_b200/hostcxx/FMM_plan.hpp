@@ -18,7 +18,7 @@
 #include "Vec.hpp"
 #include "FMMOptions.hpp"
 #include "Direct.hpp"
-#include "timing.hpp"
+#include <timing.hpp>   // <>: a build that puts the reference's examples/BEM first gets that one, not both
 #include "../../include/fmmb.h"
 
 template <class Kernel>

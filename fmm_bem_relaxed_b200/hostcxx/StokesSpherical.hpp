@@ -8,23 +8,9 @@
  * (fmm_bem_relaxed_b200/csrc/stokes.cu).
  */
 #include "LaplaceSpherical.hpp"
+#include "Mat3.hpp"
 
 #include <iostream>
-
-/** 3x3 matrix, row major; only what `K(t,s) * charge` needs (reference include/Mat3.hpp) */
-template <typename T>
-struct Mat3 {
-  T m[9];
-  Mat3() { for (int i = 0; i < 9; ++i) m[i] = T(); }
-  explicit Mat3(T v) { for (int i = 0; i < 9; ++i) m[i] = v; }
-  T& operator()(int i, int j) { return m[3 * i + j]; }
-  const T& operator()(int i, int j) const { return m[3 * i + j]; }
-};
-template <typename T>
-Vec<3, T> operator*(const Mat3<T>& a, const Vec<3, T>& x) {
-  return Vec<3, T>(a(0, 0) * x[0] + a(0, 1) * x[1] + a(0, 2) * x[2], a(1, 0) * x[0] + a(1, 1) * x[1] + a(1, 2) * x[2],
-                   a(2, 0) * x[0] + a(2, 1) * x[1] + a(2, 2) * x[2]);
-}
 
 class StokesSpherical : public LaplaceSpherical {
  public:

@@ -180,3 +180,28 @@ def test_python_gmres_solves_the_first_kind_equation():
     assert abs(rep["x"].mean() - 1.0) < 3e-2                                    # exact solution: 1
     plan.kernel().set_p(8)
     assert O.rel_l2(plan.execute(rep["x"]), b) < 1e-3                           # true residual at full order
+
+
+@pytest.mark.gpu
+def test_reference_laplacebem_driver_unchanged():
+    """bin/ref_LaplaceBEM = the reference's examples/LaplaceBEM.cpp compiled UNCHANGED, with the reference's own
+    GMRES.hpp / fmgmres.hpp / LocalPC.hpp / BlockDiagonalPC.hpp / Preconditioner.hpp / Triangulation.hpp / MshReader.hpp;
+    only FMM_plan, FMMOptions, the kernel classes, Vec, Mat3 and Direct come from hostcxx/ (i.e. the GPU engine).
+    It must print what the reference prints."""
+    its, final, niter, rel, ext = parse_gmres(run_bin("ref_LaplaceBEM", "-recursions", "4", "-p", "8", "-k", "4",
+                                                      "-solver_tol", "1e-6"))
+    assert niter == 7 and [p for _, _, p in its] == [8, 8, 8, 7, 6, 4]
+    assert [r for _, r, _ in its] == [7.878e-04, 2.986e-04, 1.081e-04, 3.370e-05, 1.043e-05, 2.522e-06]
+    assert final == 3.1066e-07 and rel == 1.512e-02 and ext == 0.19071
+    out = run_bin("ref_LaplaceBEM", "-recursions", "7", "-p", "8", "-k", "4", "-ncrit", "64", "-theta", "0.5",
+                  "-solver_tol", "1e-6")
+    its, final, niter, rel, ext = parse_gmres(out)
+    assert niter == 16 and [p for _, _, p in its] == [8, 6, 5, 5, 5, 4, 4, 3, 3, 3, 2, 2, 2, 1, 1]
+    assert its[0][1] == 3.831e-05 and its[-1][1] == 1.007e-06
+    assert final == 8.4431e-07 and rel == 4.862e-03 and ext == 0.19242
+    # diagonal preconditioner (Preconditioners::Diagonal over plan.source_begin()/source_end()) and the 2nd-kind equation:
+    # same lines as our own driver with the same options
+    for extra in (("-diagonal",), ("-second_kind",)):
+        a = parse_gmres(run_bin("ref_LaplaceBEM", "-recursions", "5", "-p", "8", "-k", "4", "-solver_tol", "1e-6", *extra))
+        b = parse_gmres(run_bin("laplace_bem", "-recursions", "5", "-p", "8", "-k", "4", "-solver_tol", "1e-6", *extra))
+        assert a == b
