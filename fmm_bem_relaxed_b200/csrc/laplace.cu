@@ -997,10 +997,81 @@ void laplace_prepare_expansions(fmmb_plan* plan) {
   }
 }
 
+// Near-field launch on stream s2 (after the charges are in place, event ev[1]); records ev[6] / ev[7] around it.
+static void launch_near_field(fmmb_plan* plan, cudaStream_t s, cudaStream_t s2) {
+  Tree& T = plan->tree;
+  cudaEvent_t* ev = plan->ev;
+  if (s2 != s) FMMB_CUDA(cudaStreamWaitEvent(s2, ev[1], 0));
+  if (!plan->capturing) FMMB_CUDA(cudaEventRecord(ev[6], s2));
+  // zero-charge padding sources for the last tile of a source stream, far outside the domain
+  const double ext = 1024.0 * std::max(T.cell[0], std::max(T.cell[1], T.cell[2]));
+  const double4 dummy = make_double4(T.pmin[0] - 1000.0 * ext, T.pmin[1] - 1000.0 * ext, T.pmin[2] - 1000.0 * ext, 0.0);
+  const int ni = T.n_p2p_items;
+  const int w = plan->p2p_warps, u = plan->p2p_unroll;
+#define FMMB_P2P_RUN(W, U)                                                                                        \
+  p2p_run_kernel<W, U><<<nblk(ni, W), 32 * W, 0, s2>>>(T.p2p_items.p, ni, T.p2p_run_off.p, T.p2p_runs.p, T.body.p, \
+                                                       dummy, plan->res_near.p)
+#define FMMB_P2P_LEAF(W)                                                                                           \
+  p2p_kernel<W><<<nblk(ni, W), 32 * W, 0, s2>>>(T.p2p_items.p, ni, T.bbegin.p, T.bend.p, T.p2p_off.p, T.p2p_src.p, \
+                                                T.body.p, plan->res_near.p)
+  if (ni > 0) {
+    if (plan->p2p_kernel == 2) {                    // default: two targets per lane, merged runs, prefetch
+      if (u == 8)
+        p2p_pair2_kernel<8><<<ni, 32, 0, s2>>>(T.p2p_items.p, T.p2p_items_ext.p, ni, T.p2p_runs.p, T.body.p, dummy,
+                                               plan->res_near.p);
+      else
+        p2p_pair2_kernel<4><<<ni, 32, 0, s2>>>(T.p2p_items.p, T.p2p_items_ext.p, ni, T.p2p_runs.p, T.body.p, dummy,
+                                               plan->res_near.p);
+    } else if (plan->p2p_kernel == 1) {             // one target per lane over merged runs
+      if (w == 1 && u == 4) FMMB_P2P_RUN(1, 4);
+      else if (w == 1) FMMB_P2P_RUN(1, 8);
+      else if (w == 2 && u == 4) FMMB_P2P_RUN(2, 4);
+      else if (w == 2) FMMB_P2P_RUN(2, 8);
+      else if (u == 4) FMMB_P2P_RUN(4, 4);
+      else FMMB_P2P_RUN(4, 8);
+    } else {                                        // one tile per source leaf
+      if (w == 1) FMMB_P2P_LEAF(1);
+      else if (w == 2) FMMB_P2P_LEAF(2);
+      else FMMB_P2P_LEAF(kP2PWarps);
+    }
+  }
+#undef FMMB_P2P_RUN
+#undef FMMB_P2P_LEAF
+  ++plan->launches;
+  FMMB_CUDA(cudaEventRecord(ev[7], s2));
+}
+
+// Results of this rank (near + far, tree order) to the caller: sharded slice, all-gathered full vector, or the
+// owned part of the full vector when there is no communicator.
+static void deliver_results(fmmb_plan* plan, double* d_results, cudaStream_t s) {
+  Tree& T = plan->tree;
+  const int64_t n = T.n, own = T.own_b1 - T.own_b0;
+  double4* out = reinterpret_cast<double4*>(d_results);
+  if (plan->call_sharded) {
+    // results stay sharded by target (SURVEY 8e): the rank's slice in tree order, no collective
+    if (own > 0)
+      combine_slice<<<nblk(own, 256), 256, 0, s>>>(plan->res_near.p, plan->res_far.p, T.own_b0, T.own_b1, out);
+  } else if (T.nranks > 1 && plan->comm) {
+    // all-gather the per-rank result slices (tree order), then un-permute;
+    // + pad: the padded all-gather reads a full chunk starting at the owned slice
+    long long chunk = 0;
+    for (int q = 0; q < T.nranks; ++q) chunk = std::max<long long>(chunk, T.body_cuts[q + 1] - T.body_cuts[q]);
+    plan->res_tree.resize((size_t)n + (size_t)chunk);
+    if (own > 0)
+      combine_results<<<nblk(own, 256), 256, 0, s>>>(plan->res_near.p, plan->res_far.p, T.own_b0, T.own_b1,
+                                                    plan->res_tree.p);
+    allgather_results(plan, s);
+    scatter_tree<<<nblk(n, 256), 256, 0, s>>>(plan->res_tree.p, T.perm.p, n, out);
+    ++plan->launches;
+  } else if (own > 0) {
+    scatter_results<<<nblk(own, 256), 256, 0, s>>>(plan->res_near.p, plan->res_far.p, T.perm.p, T.own_b0, T.own_b1, out);
+  }
+  ++plan->launches;
+}
+
 void laplace_execute(fmmb_plan* plan, const double* d_charges, double* d_results) {
   Tree& T = plan->tree;
   const int P = plan->p, nc = P * (P + 1) / 2, pp = P * P;
-  const int nb = T.nboxes;
   const int64_t n = T.n;
   cudaStream_t s = plan->stream, s2 = plan->overlap_p2p ? plan->stream2 : plan->stream;
   laplace_prepare_expansions(plan);
@@ -1009,9 +1080,10 @@ void laplace_execute(fmmb_plan* plan, const double* d_charges, double* d_results
   cudaEvent_t* ev = plan->ev;
   plan->launches = 0;
 
+  // ---- charges into the tree-ordered bodies
   if (!plan->capturing) FMMB_CUDA(cudaEventRecord(ev[0], s));
   if (plan->call_sharded) {
-    // charges = this rank's slice in tree order: all-gather the slices (NCCL), no permutation
+    // charges = this rank's slice in tree order, no permutation
     if (T.nranks > 1 && plan->peer_ready) {
       peer_exchange_charges(plan, d_charges, s);       // slices written straight into the peers (NVLink), no NCCL
     } else if (T.nranks > 1 && plan->comm) {
@@ -1027,122 +1099,63 @@ void laplace_execute(fmmb_plan* plan, const double* d_charges, double* d_results
   ++plan->launches;
   FMMB_CUDA(cudaEventRecord(ev[1], s));
 
-  // near field on the second stream: needs only the charges
+  // ---- near field on the second stream: needs only the charges.
+  // One GPU: it starts right away and fills the gaps of the latency-bound upward chain.  Sharded with an owned
+  // upward pass: it starts once the owned M2M sweep is enqueued (hook below), so that the short dependent kernels
+  // before the multipole exchange are not queued behind its blocks and it overlaps the exchange instead.
   const bool p2m_owned = T.nranks > 1 && (plan->comm || plan->peer_ready) && P <= 8 && plan->opts.m2l_mode != 1 &&
                          plan->m2m_own.n_items > 0;
-  auto launch_p2p = [&]() {
-  if (s2 != s) FMMB_CUDA(cudaStreamWaitEvent(s2, ev[1], 0));
-  if (!plan->capturing) FMMB_CUDA(cudaEventRecord(ev[6], s2));
-  const double ext = 1024.0 * std::max(T.cell[0], std::max(T.cell[1], T.cell[2]));
-  const double4 dummy = make_double4(T.pmin[0] - 1000.0 * ext, T.pmin[1] - 1000.0 * ext, T.pmin[2] - 1000.0 * ext, 0.0);
-  const int ni_ = T.n_p2p_items;
-#define FMMB_P2P_RUN(W, U)                                                                                       \
-  p2p_run_kernel<W, U><<<nblk(ni_, W), 32 * W, 0, s2>>>(T.p2p_items.p, ni_, T.p2p_run_off.p, T.p2p_runs.p, T.body.p, \
-                                                        dummy, plan->res_near.p)
-  if (plan->p2p_kernel == 2 && ni_ > 0) {
-    if (plan->p2p_unroll == 8)
-      p2p_pair2_kernel<8><<<ni_, 32, 0, s2>>>(T.p2p_items.p, T.p2p_items_ext.p, ni_, T.p2p_runs.p, T.body.p, dummy,
-                                              plan->res_near.p);
-    else
-      p2p_pair2_kernel<4><<<ni_, 32, 0, s2>>>(T.p2p_items.p, T.p2p_items_ext.p, ni_, T.p2p_runs.p, T.body.p, dummy,
-                                              plan->res_near.p);
-  } else if (plan->p2p_kernel == 1 && ni_ > 0) {
-    const int w = plan->p2p_warps, u = plan->p2p_unroll;
-    if (w == 1 && u == 4) FMMB_P2P_RUN(1, 4);
-    else if (w == 1) FMMB_P2P_RUN(1, 8);
-    else if (w == 2 && u == 4) FMMB_P2P_RUN(2, 4);
-    else if (w == 2) FMMB_P2P_RUN(2, 8);
-    else if (u == 4) FMMB_P2P_RUN(4, 4);
-    else FMMB_P2P_RUN(4, 8);
-  } else if (plan->p2p_warps == 1)
-    p2p_kernel<1><<<T.n_p2p_items, 32, 0, s2>>>(T.p2p_items.p, T.n_p2p_items, T.bbegin.p, T.bend.p, T.p2p_off.p,
-                                                T.p2p_src.p, T.body.p, plan->res_near.p);
-  else if (plan->p2p_warps == 2)
-    p2p_kernel<2><<<nblk(T.n_p2p_items, 2), 64, 0, s2>>>(T.p2p_items.p, T.n_p2p_items, T.bbegin.p, T.bend.p,
-                                                         T.p2p_off.p, T.p2p_src.p, T.body.p, plan->res_near.p);
-  else
-    p2p_kernel<kP2PWarps><<<nblk(T.n_p2p_items, kP2PWarps), 32 * kP2PWarps, 0, s2>>>(
-        T.p2p_items.p, T.n_p2p_items, T.bbegin.p, T.bend.p, T.p2p_off.p, T.p2p_src.p, T.body.p, plan->res_near.p);
-  ++plan->launches;
-  FMMB_CUDA(cudaEventRecord(ev[7], s2));
-  };
-  // One GPU: the near field starts right away and fills the gaps of the latency-bound upward chain.  Sharded with
-  // an owned upward pass: it starts once the owned M2M sweep is enqueued (hook below), so that the short dependent
-  // kernels before the multipole exchange are not queued behind its blocks and it overlaps the exchange instead.
   const bool defer_p2p = p2m_owned && s2 != s && !plan->near_only;
-  if (!defer_p2p) launch_p2p();
+  if (!defer_p2p) launch_near_field(plan, s, s2);
 
-  // upward sweep
+  // ---- far field
   if (!plan->capturing) FMMB_CUDA(cudaEventRecord(ev[12], s));
   if (plan->near_only) {
     // plans for preconditioners (FMMOptions::local_evaluation / block_diagonal): no far field at all
     FMMB_CUDA(cudaMemsetAsync(plan->res_far.p, 0, (size_t)n * sizeof(double4), s));
     if (!plan->capturing) { FMMB_CUDA(cudaEventRecord(ev[2], s)); FMMB_CUDA(cudaEventRecord(ev[3], s)); }
   } else {
-  const int p2m_warps = pp <= 64 ? 4 : 1;          // shared tile: warps x 32 bodies x P^2 doubles
-  const size_t p2m_sh = (size_t)p2m_warps * 32 * (pp | 1) * sizeof(double);
-  static bool p2m_attr = false;
-  if (!p2m_attr) {
-    FMMB_CUDA(cudaFuncSetAttribute(p2m_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024));
-    p2m_attr = true;
-  }
-  const int* p2m_list = p2m_owned ? T.own_leaves.p : T.leaves.p;
-  const int p2m_n = p2m_owned ? T.n_own_leaves : T.nleaves;
-  p2m_kernel<<<nblk(p2m_n, p2m_warps), 32 * p2m_warps, p2m_sh, s>>>(
-      p2m_list, p2m_n, T.bbegin.p, T.bend.p,
-                                                               T.center.p, T.body.p, P, plan->M.p);
-                       ++plan->launches;
-  if (defer_p2p) {
-    plan->hook_after_owned_m2m = [&]() {
-      FMMB_CUDA(cudaEventRecord(ev[15], s));
-      FMMB_CUDA(cudaStreamWaitEvent(s2, ev[15], 0));
-      launch_p2p();
-    };
-  }
-  try { laplace_translations(plan, s); } catch (...) { plan->hook_after_owned_m2m = nullptr; throw; }
-  plan->hook_after_owned_m2m = nullptr;
-  if (plan->opts.evaluator == FMMB_EVAL_TREECODE) {
-    if (T.n_own_leaves)
-      m2p_kernel<<<nblk(T.n_own_leaves, 4), 128, 4 * nc * sizeof(double2), s>>>(
-          T.own_leaves.p, T.n_own_leaves, T.bbegin.p, T.bend.p, T.parent.p, T.m2l_off.p, T.m2l_src.p, T.center.p,
-          T.body.p, P, plan->M.p, plan->res_far.p);
-  } else if (T.n_own_leaves) {
-    l2p_kernel<<<nblk(T.n_own_leaves, 4), 128, 4 * nc * sizeof(double2), s>>>(
-        T.own_leaves.p, T.n_own_leaves, T.bbegin.p, T.bend.p, T.center.p, T.has_local.p, T.body.p, P, plan->L.p,
-        plan->res_far.p);
-  }
-  ++plan->launches;
+    const int p2m_warps = pp <= 64 ? 4 : 1;          // shared tile: warps x 32 bodies x P^2 doubles
+    const size_t p2m_sh = (size_t)p2m_warps * 32 * (pp | 1) * sizeof(double);
+    static bool p2m_attr = false;
+    if (!p2m_attr) {
+      FMMB_CUDA(cudaFuncSetAttribute(p2m_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024));
+      p2m_attr = true;
+    }
+    const int* p2m_list = p2m_owned ? T.own_leaves.p : T.leaves.p;
+    const int p2m_n = p2m_owned ? T.n_own_leaves : T.nleaves;
+    if (p2m_n)
+      p2m_kernel<<<nblk(p2m_n, p2m_warps), 32 * p2m_warps, p2m_sh, s>>>(p2m_list, p2m_n, T.bbegin.p, T.bend.p, T.center.p,
+                                                                       T.body.p, P, plan->M.p);
+    ++plan->launches;
+    if (defer_p2p) {
+      plan->hook_after_owned_m2m = [&]() {
+        FMMB_CUDA(cudaEventRecord(ev[15], s));
+        FMMB_CUDA(cudaStreamWaitEvent(s2, ev[15], 0));
+        launch_near_field(plan, s, s2);
+      };
+    }
+    try { laplace_translations(plan, s); } catch (...) { plan->hook_after_owned_m2m = nullptr; throw; }
+    plan->hook_after_owned_m2m = nullptr;
+    if (plan->opts.evaluator == FMMB_EVAL_TREECODE) {
+      if (T.n_own_leaves)
+        m2p_kernel<<<nblk(T.n_own_leaves, 4), 128, 4 * nc * sizeof(double2), s>>>(
+            T.own_leaves.p, T.n_own_leaves, T.bbegin.p, T.bend.p, T.parent.p, T.m2l_off.p, T.m2l_src.p, T.center.p,
+            T.body.p, P, plan->M.p, plan->res_far.p);
+    } else if (T.n_own_leaves) {
+      l2p_kernel<<<nblk(T.n_own_leaves, 4), 128, 4 * nc * sizeof(double2), s>>>(
+          T.own_leaves.p, T.n_own_leaves, T.bbegin.p, T.bend.p, T.center.p, T.has_local.p, T.body.p, P, plan->L.p,
+          plan->res_far.p);
+    }
+    ++plan->launches;
   }
   // peer exchange: this rank no longer reads its multipole array -> peers may push the next matvec's rows
   if (plan->peer_ready) peer_read_done(plan, s);
   if (!plan->capturing) FMMB_CUDA(cudaEventRecord(ev[4], s));
 
+  // ---- results
   if (s2 != s) FMMB_CUDA(cudaStreamWaitEvent(s, ev[7], 0));
-  if (plan->call_sharded) {
-    // results stay sharded by target (SURVEY 8e): the rank's slice in tree order, no collective
-    if (T.own_b1 > T.own_b0)
-      combine_slice<<<nblk(T.own_b1 - T.own_b0, 256), 256, 0, s>>>(plan->res_near.p, plan->res_far.p, T.own_b0,
-                                                                  T.own_b1, reinterpret_cast<double4*>(d_results));
-  } else if (T.nranks > 1 && plan->comm) {
-    // the one exchange step: all-gather the per-rank result slices (tree order), then un-permute
-    {
-      // + pad: the padded all-gather reads a full chunk starting at the owned slice
-      long long chunk = 0;
-      for (int q = 0; q < T.nranks; ++q) chunk = std::max<long long>(chunk, T.body_cuts[q + 1] - T.body_cuts[q]);
-      plan->res_tree.resize((size_t)n + (size_t)chunk);
-    }
-    if (T.own_b1 > T.own_b0)
-      combine_results<<<nblk(T.own_b1 - T.own_b0, 256), 256, 0, s>>>(plan->res_near.p, plan->res_far.p, T.own_b0,
-                                                                    T.own_b1, plan->res_tree.p);
-    allgather_results(plan, s);
-    scatter_tree<<<nblk(n, 256), 256, 0, s>>>(plan->res_tree.p, T.perm.p, n, reinterpret_cast<double4*>(d_results));
-    ++plan->launches;
-  } else if (T.own_b1 > T.own_b0) {
-    scatter_results<<<nblk(T.own_b1 - T.own_b0, 256), 256, 0, s>>>(plan->res_near.p, plan->res_far.p, T.perm.p,
-                                                                  T.own_b0, T.own_b1,
-                                                                  reinterpret_cast<double4*>(d_results));
-  }
-      ++plan->launches;
+  deliver_results(plan, d_results, s);
   if (!plan->capturing) FMMB_CUDA(cudaEventRecord(ev[5], s));
   FMMB_CUDA(cudaGetLastError());
   plan->timed = true;
