@@ -382,6 +382,10 @@ int fmmb_plan_peer_export(fmmb_plan* plan, unsigned char blob[128]) {
   if (!plan || !blob) { set_error("null argument"); return FMMB_ERR_INVALID; }
   return guarded([&] {
     FMMB_CUDA(cudaSetDevice(plan->device));
+    FMMB_CUDA(cudaStreamSynchronize(plan->stream));
+    for (auto& kv : plan->graphs) cudaGraphExecDestroy(kv.second);   // the multipole array moves: captured launches are stale
+    plan->graphs.clear();
+    plan->graph_seen.clear();
     peer_export(plan, blob);
   });
 }

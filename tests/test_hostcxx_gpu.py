@@ -56,3 +56,14 @@ def test_reference_stresslet_driver_unchanged():
     for g, want in zip(got, (2.1859e-04, 5.2482e-06, 5.1619e-04)):
         assert abs(g - want) <= 2e-4 * want, (got, out)
     assert "Stresslet calculation" in out
+
+
+def test_yukawa_bem_driver():
+    """hostcxx/examples/yukawa_bem.cpp (BASELINE config 3 shape, smaller mesh): the C++ YukawaCartesianBEM mirror through
+    FMM_plan, checked against Direct::matvec with the host kernel class, and a relaxed device-resident GMRES solve of a
+    manufactured first-kind problem."""
+    out = run("yukawa_bem", "-recursions", "6", "-p", "8", "-k", "4", "-kappa", "1", "-solver_tol", "1e-6", "-check", "200")
+    assert float(re.search(r"matvec vs Direct \(first 200 rows\): ([0-9.eE+-]+)", out).group(1)) < 1e-4
+    m = re.search(r"iterations: (\d+), final residual: ([0-9.eE+-]+), relative error of the solution: ([0-9.eE+-]+)", out)
+    assert m, out
+    assert int(m.group(1)) < 60 and float(m.group(2)) < 1e-6 and float(m.group(3)) < 5e-3
