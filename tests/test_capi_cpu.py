@@ -29,11 +29,31 @@ def test_library_exports_every_declared_symbol():
     assert b"sm_100a" in lib.fmmb_version()
 
 
-def test_struct_layouts_match_header():
+def test_struct_layouts_match_header(tmp_path):
     assert ctypes.sizeof(capi.KernelDesc) == 24
     assert ctypes.sizeof(capi.Options) == 40
     assert ctypes.sizeof(capi.Sources) == 32
     assert ctypes.sizeof(capi.PlanInfo) == 12 * 8 + 4 * 4
+    # every field of every structure, as a C compiler lays include/fmmb.h out (the header is plain C)
+    pairs = {"fmmb_kernel_desc": capi.KernelDesc, "fmmb_options": capi.Options, "fmmb_sources": capi.Sources,
+             "fmmb_plan_info": capi.PlanInfo, "fmmb_solver_options": capi.SolverOptions, "fmmb_gmres_info": capi.GmresInfo}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "fmmb.h"', 'int main(void) {']
+    for cname, st in pairs.items():
+        lines.append('printf("%s size %%zu\\n", sizeof(%s));' % (cname, cname))
+        for fname, _ in st._fields_:
+            lines.append('printf("%s %s %%zu\\n", offsetof(%s, %s));' % (cname, fname, cname, fname))
+    lines += ['return 0;', '}']
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    import subprocess
+    subprocess.check_call(["gcc", "-std=c99", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
+    out = subprocess.check_output([str(exe)]).decode().split("\n")
+    got = {tuple(l.split()[:2]): int(l.split()[2]) for l in out if l.strip()}
+    for cname, st in pairs.items():
+        assert got[(cname, "size")] == ctypes.sizeof(st), cname
+        for fname, _ in st._fields_:
+            assert got[(cname, fname)] == getattr(st, fname).offset, (cname, fname)
 
 
 def test_argument_validation_needs_no_gpu():
