@@ -10,10 +10,15 @@ point set.
             per-step CUDA events on the plan stream, L2 flushed between steps.
   e2e       the same through the host-buffer call fmmb_plan_execute (H2D of the charges and D2H of
             the results inside the timed region, pinned host memory).
-  roofline  the dominant kernel (M2L) against the FP64 FMA peak measured by a DFMA microbenchmark
-            in the same process (MEASURED_PEAKS.json carries HBM and bf16 only).
+  roofline  the longer of the two dominant kernels (P2P pair kernel / M2L GEMM) against the FP64 peak measured in
+            the same process (DFMA and DMMA micro-benchmarks; MEASURED_PEAKS.json carries HBM and bf16 only);
+            traffic = DRAM bytes per launch from the committed ncu capture (profiles/traffic_r01.json).
   cpu_baseline  the reference itself (oracle/_ref/ref_laplace, unmodified reference headers
             compiled with the reference's flags) timed on this host's cores.
+  gmres_c2, stresslet_c4   BASELINE configs 2 and 4 next to the reference (N = 1 only).
+N > 1 (torchrun, one rank per GPU, strong scaling): a step is one sharded matvec -- every rank feeds and keeps the
+tree-ordered slice of its own bodies (fmmb_plan_execute_sharded), multipoles and charge slices are exchanged through
+NVLink peer memory (--no-peer: NCCL all-gathers; --replicated-results: full vectors on every rank).
 --impl reference times only that CPU implementation.
 """
 import argparse
