@@ -376,12 +376,9 @@ void bem_execute(fmmb_plan* plan, const double* d_charges, double* d_results) {
   if (!plan->capturing) FMMB_CUDA(cudaEventRecord(ev[12], s));
   const int warps = pp <= 64 ? 4 : 1;
   const size_t sh = (size_t)warps * 32 * (pp | 1) * sizeof(double);
-  static bool attr = false;
-  if (!attr) {
-    FMMB_CUDA(cudaFuncSetAttribute(bem_p2m_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024));
-    FMMB_CUDA(cudaFuncSetAttribute(bem_p2m_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024));
-    attr = true;
-  }
+  // per call: function attributes belong to the current device
+  FMMB_CUDA(cudaFuncSetAttribute(bem_p2m_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024));
+  FMMB_CUDA(cudaFuncSetAttribute(bem_p2m_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024));
   for (int set = 0; set < 2; ++set) {
     if (!B->set_active[set] || plan->near_only) continue;   // near_only: plans for preconditioners, no far field
     if (set == 0)

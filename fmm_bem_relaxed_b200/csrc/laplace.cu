@@ -1117,11 +1117,8 @@ void laplace_execute(fmmb_plan* plan, const double* d_charges, double* d_results
   } else {
     const int p2m_warps = pp <= 64 ? 4 : 1;          // shared tile: warps x 32 bodies x P^2 doubles
     const size_t p2m_sh = (size_t)p2m_warps * 32 * (pp | 1) * sizeof(double);
-    static bool p2m_attr = false;
-    if (!p2m_attr) {
-      FMMB_CUDA(cudaFuncSetAttribute(p2m_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024));
-      p2m_attr = true;
-    }
+    // per call: function attributes belong to the current device
+    FMMB_CUDA(cudaFuncSetAttribute(p2m_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024));
     const int* p2m_list = p2m_owned ? T.own_leaves.p : T.leaves.p;
     const int p2m_n = p2m_owned ? T.n_own_leaves : T.nleaves;
     if (p2m_n)

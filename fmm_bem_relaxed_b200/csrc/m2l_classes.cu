@@ -416,15 +416,12 @@ template <int P, bool ACC>
 void launch_gemm_t(const TransBatch& B, int first, int count, const double* X, double* tmp, double* out,
                    cudaStream_t s) {
   size_t sh = (size_t)3 * kNB * GemmCfg<P>::LDB * sizeof(double);
-  static bool attr = false;
-  static int sms = 0;
-  if (!attr) {
-    FMMB_CUDA(cudaFuncSetAttribute(trans_gemm_kernel<P, ACC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh));
-    int dev = 0;
-    FMMB_CUDA(cudaGetDevice(&dev));
-    FMMB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    attr = true;
-  }
+  // per call, not once per process: function attributes and the SM count belong to the CURRENT device
+  // (a process may hold plans on several devices); both calls are host-side and cheap
+  int sms = 0, dev = 0;
+  FMMB_CUDA(cudaFuncSetAttribute(trans_gemm_kernel<P, ACC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh));
+  FMMB_CUDA(cudaGetDevice(&dev));
+  FMMB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   int grid = std::min(count, 2 * sms);
   trans_gemm_kernel<P, ACC><<<grid, 256, sh, s>>>(B.built_p * B.built_p, B.T.p, count, B.item_class.p + first,
                                                  B.item_start.p + first, B.item_count.p + first,

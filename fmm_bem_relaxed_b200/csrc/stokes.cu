@@ -384,12 +384,9 @@ void stokes_execute(fmmb_plan* plan, const double* d_charges, double* d_results)
   if (!plan->capturing) FMMB_CUDA(cudaEventRecord(ev[12], s));
   const int warps = pp <= 64 ? 4 : 1;
   const size_t sh = (size_t)warps * 32 * (pp | 1) * sizeof(double);
-  static bool attr = false;
-  if (!attr) {
-    FMMB_CUDA(cudaFuncSetAttribute(stokes_p2m_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024));
-    FMMB_CUDA(cudaFuncSetAttribute(stokes_p2m_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024));
-    attr = true;
-  }
+  // per call: function attributes belong to the current device
+  FMMB_CUDA(cudaFuncSetAttribute(stokes_p2m_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024));
+  FMMB_CUDA(cudaFuncSetAttribute(stokes_p2m_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024));
   // multi-GPU with a communicator: the upward pass is owned (own leaves, multipoles exchanged per set by
   // laplace_translations); otherwise it is replicated
   const bool p2m_owned = T.nranks > 1 && plan->comm && P <= 8 && plan->opts.m2l_mode != 1 && plan->m2m_own.n_items > 0;
