@@ -48,8 +48,8 @@ class StokesSpherical : public LaplaceSpherical {
     if (r2 < 1e-8) invR2 = 0;
     real invR3 = invR2 * std::sqrt(invR2);
     kernel_value_type r(0.);
-    for (int i = 0; i < 3; ++i)
-      for (int j = 0; j < 3; ++j) r(i, j) = invR3 * d[i] * d[j];
+    for (int i = 0; i < 3; ++i)       // symmetric: the lower-index component is multiplied first, as the reference does
+      for (int j = i + 1; j < 3; ++j) r(i, j) = r(j, i) = invR3 * d[i] * d[j];
     for (int i = 0; i < 3; ++i) r(i, i) = invR3 * (r2 + d[i] * d[i]);
     return r;
   }

@@ -59,3 +59,26 @@ def test_mirror_prints_what_the_reference_gmres_prints(ours, tmp_path):
     ref_it = int(re.search(r"after (\d+) iterations", b).group(1))
     assert ours_it < 30 and ref_it > 5 * ours_it
     assert a.splitlines()[:4] == b.splitlines()[:4]          # identical up to the first restart
+
+
+KERNELS = {1: "LaplaceSpherical", 2: "LaplaceSphericalBEM", 3: "YukawaCartesian", 4: "YukawaCartesianBEM",
+           5: "StokesSpherical (Stokeslet)"}
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(REF, "kernel", "LaplaceSpherical.hpp")),
+                    reason="reference sources are only present in the build container")
+@pytest.mark.parametrize("kernel", sorted(KERNELS))
+def test_host_kernel_classes_match_the_reference_bit_for_bit(kernel, tmp_path):
+    """K(t, s) of every host-side kernel class (hostcxx/*.hpp) on a fixed set of points / panels against the
+    reference's own kernel headers: every printed value identical.  For the BEM classes this covers the Gauss and
+    semi-analytical panel integrals of hostcxx/bem_math.hpp -- the same source the GPU near-field assembly compiles."""
+    src = os.path.join(ROOT, "tests", "host", "kernel_eval.cpp")
+    flags = ["g++", "-std=gnu++14", "-O1", "-DKERNEL=%d" % kernel]
+    ours, ref = str(tmp_path / "ours"), str(tmp_path / "ref")
+    subprocess.check_call(flags + ["-I", os.path.join(ROOT, "fmm_bem_relaxed_b200", "hostcxx"), src, "-o", ours])
+    subprocess.check_call(flags + ["-I", os.path.join(REF, "include"), "-I", os.path.join(REF, "kernel"),
+                                   "-I", os.path.join(REF, "examples", "BEM"), "-I", os.path.join(ROOT, "oracle", "boost_shim"),
+                                   "-include", os.path.join(ROOT, "oracle", "prelude.hpp"), src, "-o", ref])
+    a, b = run(ours), run(ref)
+    assert len(a.splitlines()) > 3000
+    assert a == b, KERNELS[kernel]
