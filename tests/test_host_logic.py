@@ -82,3 +82,22 @@ def test_host_kernel_classes_match_the_reference_bit_for_bit(kernel, tmp_path):
     a, b = run(ours), run(ref)
     assert len(a.splitlines()) > 3000
     assert a == b, KERNELS[kernel]
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(REF, "examples", "BEM", "Triangulation.hpp")),
+                    reason="reference sources are only present in the build container")
+@pytest.mark.parametrize("rec,k", [(3, 1), (4, 4), (5, 3)])
+def test_sphere_mesh_and_panel_geometry_match_the_reference(rec, k, tmp_path):
+    """Triangulation::UnitSphere + Panel(p0, p1, p2): vertices, panel order, centres, normals, areas and the K
+    quadrature points, bit for bit."""
+    src = os.path.join(ROOT, "tests", "host", "mesh_eval.cpp")
+    ours, ref = str(tmp_path / "ours"), str(tmp_path / "ref")
+    subprocess.check_call(["g++", "-std=gnu++14", "-O1", "-I", os.path.join(ROOT, "fmm_bem_relaxed_b200", "hostcxx"), src,
+                           "-o", ours])
+    subprocess.check_call(["g++", "-std=gnu++14", "-O1", "-I", os.path.join(REF, "include"), "-I", os.path.join(REF, "kernel"),
+                           "-I", os.path.join(REF, "examples", "BEM"), "-I", os.path.join(ROOT, "oracle", "boost_shim"),
+                           "-include", os.path.join(ROOT, "oracle", "prelude.hpp"), src, "-o", ref])
+    a = subprocess.check_output([ours, str(rec), str(k)], cwd=str(tmp_path)).decode()
+    b = subprocess.check_output([ref, str(rec), str(k)], cwd=str(tmp_path)).decode()   # writes test.vert / test.face there
+    assert int(a.splitlines()[1]) == 8 * 4 ** (rec - 1)       # line 0: the generator's own "initialised N triangles"
+    assert a == b
