@@ -30,13 +30,13 @@ class FmmbError(RuntimeError):
 
 class KernelDesc(ctypes.Structure):
     _fields_ = [("kind", ctypes.c_int32), ("p", ctypes.c_int32), ("kappa", ctypes.c_double),
-                ("quad_k", ctypes.c_int32), ("reserved", ctypes.c_int32)]
+                ("quad_k", ctypes.c_int32), ("quad_kfine", ctypes.c_int32)]
 
 
 class Options(ctypes.Structure):
     _fields_ = [("theta", ctypes.c_double), ("ncrit", ctypes.c_uint32), ("evaluator", ctypes.c_int32),
                 ("device", ctypes.c_int32), ("m2l_mode", ctypes.c_int32), ("rank", ctypes.c_int32),
-                ("nranks", ctypes.c_int32), ("near_only", ctypes.c_int32)]
+                ("nranks", ctypes.c_int32), ("near_only", ctypes.c_int32), ("kernel_flags", ctypes.c_int32)]
 
 
 class Sources(ctypes.Structure):

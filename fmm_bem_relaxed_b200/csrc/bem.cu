@@ -43,7 +43,7 @@ namespace {
 using namespace ops;
 
 __constant__ bem::Rule c_rule;   // K-point panel rule
-__constant__ bem::Rule c_fine;   // 16-point rule for the near-singular double layer
+__constant__ bem::Rule c_fine;   // the rule filed under 17 (16 points) for the near-singular double layer
 
 inline int nblk(int64_t n, int t) { return (int)((n + t - 1) / t); }
 
@@ -285,7 +285,7 @@ void bem_setup(fmmb_plan* plan, const double* verts_host, const int32_t* bc_host
   Tree& T = plan->tree;
   cudaStream_t s = plan->stream;
   if (!bem::rule_supported(quad_k))
-    throw StatusError{FMMB_ERR_UNSUPPORTED, "Gauss rules with 1, 3, 4 (or 7, aliased to 4 like the reference) points are built"};
+    throw StatusError{FMMB_ERR_UNSUPPORTED, "quad_k must be a key of the reference's Gauss table: 1, 3, 4, 7, 13, 17, 19, 25 or 79"};
   BemData* B = new BemData();
   plan->bem = B;
   B->K = quad_k == 7 ? 4 : quad_k;

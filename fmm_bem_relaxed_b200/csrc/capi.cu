@@ -67,15 +67,19 @@ int fmmb_plan_create(const fmmb_kernel_desc* kernel, const fmmb_sources* sources
   *out_plan = nullptr;
   const bool is_stokes = kernel->kind == FMMB_STOKES_SPHERICAL || kernel->kind == FMMB_STOKES_SPHERICAL_STRESSLET;
   const bool is_yukawa = kernel->kind == FMMB_YUKAWA_CARTESIAN || kernel->kind == FMMB_YUKAWA_CARTESIAN_BEM;
-  if (kernel->kind != FMMB_LAPLACE_SPHERICAL && kernel->kind != FMMB_LAPLACE_SPHERICAL_BEM && !is_stokes && !is_yukawa) {
+  const bool is_sbem = kernel->kind == FMMB_STOKES_SPHERICAL_BEM;
+  if (kernel->kind != FMMB_LAPLACE_SPHERICAL && kernel->kind != FMMB_LAPLACE_SPHERICAL_BEM && !is_stokes && !is_yukawa &&
+      !is_sbem) {
     set_error("built kernel kinds: FMMB_LAPLACE_SPHERICAL, FMMB_LAPLACE_SPHERICAL_BEM, FMMB_STOKES_SPHERICAL, "
-              "FMMB_STOKES_SPHERICAL_STRESSLET, FMMB_YUKAWA_CARTESIAN, FMMB_YUKAWA_CARTESIAN_BEM");
+              "FMMB_STOKES_SPHERICAL_STRESSLET, FMMB_YUKAWA_CARTESIAN, FMMB_YUKAWA_CARTESIAN_BEM, "
+              "FMMB_STOKES_SPHERICAL_BEM");
     return FMMB_ERR_UNSUPPORTED;
   }
   const bool is_bem = kernel->kind == FMMB_LAPLACE_SPHERICAL_BEM || kernel->kind == FMMB_YUKAWA_CARTESIAN_BEM;
-  if (is_bem && !sources->vertices) { set_error("BEM kernels need the panel vertices"); return FMMB_ERR_INVALID; }
+  const bool is_panel = is_bem || is_sbem;     // sources are triangular panels
+  if (is_panel && !sources->vertices) { set_error("BEM kernels need the panel vertices"); return FMMB_ERR_INVALID; }
   if (kernel->p < 1 || kernel->p > FMMB_MAX_P) { set_error("expansion order must be in 1..16"); return FMMB_ERR_INVALID; }
-  if (sources->n < 1 || (!sources->points && !(is_bem && sources->vertices))) {
+  if (sources->n < 1 || (!sources->points && !(is_panel && sources->vertices))) {
     set_error("need at least one source point");
     return FMMB_ERR_INVALID;
   }
@@ -118,8 +122,8 @@ int fmmb_plan_create(const fmmb_kernel_desc* kernel, const fmmb_sources* sources
     FMMB_CUDA(cudaStreamCreateWithPriority(&plan->stream, cudaStreamNonBlocking, prio_hi));
     FMMB_CUDA(cudaStreamCreateWithPriority(&plan->stream2, cudaStreamNonBlocking, prio_lo));
     for (auto& e : plan->ev) FMMB_CUDA(cudaEventCreate(&e));
-    plan->charge_dim = is_stokes ? (kernel->kind == FMMB_STOKES_SPHERICAL_STRESSLET ? 6 : 3) : 1;
-    plan->result_dim = is_bem ? 1 : (is_stokes ? 3 : 4);
+    plan->charge_dim = is_stokes ? (kernel->kind == FMMB_STOKES_SPHERICAL_STRESSLET ? 6 : 3) : (is_sbem ? 3 : 1);
+    plan->result_dim = is_bem ? 1 : (is_stokes || is_sbem ? 3 : 4);
     laplace_init_tables(plan);
     std::vector<double> centres;
     const double* pts = sources->points;
@@ -137,11 +141,12 @@ int fmmb_plan_create(const fmmb_kernel_desc* kernel, const fmmb_sources* sources
     plan->near_only = opts.near_only;
     if (opts.near_only == 2) restrict_p2p_to_self(plan);
     if (!opts.near_only) build_m2l_classes(plan);
-    if (is_bem) plan->p2p_item_mode = 0;   // one cached near-field block per chunk of <= 32 targets
+    if (is_panel) plan->p2p_item_mode = 0;   // one cached near-field block per chunk of <= 32 targets
     build_p2p_items(plan);
     if (is_bem) bem_setup(plan, sources->vertices, sources->bc, kernel->quad_k,
                           kernel->kind == FMMB_YUKAWA_CARTESIAN_BEM ? kernel->kappa : -1.0);
     if (is_stokes) stokes_setup(plan, kernel->kind == FMMB_STOKES_SPHERICAL_STRESSLET);
+    if (is_sbem) stokes_bem_setup(plan, sources->vertices, sources->bc, kernel->quad_k, kernel->quad_kfine, kernel->kappa);
     if (is_yukawa) yukawa_setup(plan, kernel->kappa);
   });
   if (rc != FMMB_OK) { fmmb_plan_destroy(plan); return rc; }
@@ -159,6 +164,7 @@ void fmmb_plan_destroy(fmmb_plan* plan) {
   comm_destroy(plan);
   bem_free(plan->bem);
   stokes_free(plan->stokes);
+  stokes_bem_free(plan->sbem);
   yukawa_free(plan->yukawa);
   gmres_free(plan->gmres_ws);
   for (auto& kv : plan->m2l_coeff) delete kv.second;
@@ -185,6 +191,7 @@ static void run_matvec(fmmb_plan* plan, const double* q, double* r) {
     if (plan->bem && plan->yukawa) yukawa_bem_execute(plan, q, r);
     else if (plan->bem) bem_execute(plan, q, r);
     else if (plan->stokes) stokes_execute(plan, q, r);
+    else if (plan->sbem) stokes_bem_execute(plan, q, r);
     else if (plan->yukawa) yukawa_execute(plan, q, r);
     else laplace_execute(plan, q, r);
   };
@@ -296,7 +303,7 @@ int fmmb_plan_execute(fmmb_plan* plan, const double* charges_host, double* resul
 int fmmb_plan_direct(fmmb_plan* plan, const double* charges_host, int64_t nt, const double* targets_host,
                      double* results_host) {
   if (!plan || !charges_host || !targets_host || !results_host || nt < 0) { set_error("bad argument"); return FMMB_ERR_INVALID; }
-  if (plan->bem) { set_error("fmmb_plan_direct is built for point kernels only"); return FMMB_ERR_UNSUPPORTED; }
+  if (plan->bem || plan->sbem) { set_error("fmmb_plan_direct is built for point kernels only"); return FMMB_ERR_UNSUPPORTED; }
   return guarded([&] {
     FMMB_CUDA(cudaSetDevice(plan->device));
     cudaStream_t s = plan->stream;
@@ -346,7 +353,7 @@ int fmmb_plan_set_option(fmmb_plan* plan, const char* name, int64_t value) {
   }
   if (!std::strcmp(name, "p2p_warps") || !std::strcmp(name, "p2p_items")) {
     const bool items = !std::strcmp(name, "p2p_items");
-    if (items && plan->bem) { set_error("BEM plans keep one near-field block per chunk"); return FMMB_ERR_UNSUPPORTED; }
+    if (items && (plan->bem || plan->sbem)) { set_error("BEM plans keep one near-field block per chunk"); return FMMB_ERR_UNSUPPORTED; }
     if (items ? (value != 0 && value != 1) : (value != 1 && value != 2 && value != 4)) {
       set_error("p2p_items: 0 or 1; p2p_warps: 1, 2 or 4");
       return FMMB_ERR_INVALID;
@@ -426,7 +433,7 @@ int fmmb_plan_get_info(fmmb_plan* plan, fmmb_plan_info* info) {
   info->n_m2l_pairs = T.n_lr; info->n_p2p_box_pairs = T.n_p2p; info->n_p2p_body_pairs = T.n_p2p_body_pairs;
   info->n_m2l_classes = plan->cls.n_classes; info->n_m2l_pairs_batched = plan->cls.n_pairs;
   info->own_body_begin = T.own_b0; info->own_body_end = T.own_b1;
-  info->n_near_entries = plan->bem ? bem_nnz(plan->bem) : 0;
+  info->n_near_entries = plan->bem ? bem_nnz(plan->bem) : (plan->sbem ? stokes_bem_nnz(plan->sbem) : 0);
   info->p = plan->p; info->charge_dim = plan->charge_dim; info->result_dim = plan->result_dim; info->device = plan->device;
   return FMMB_OK;
 }
@@ -470,7 +477,7 @@ int fmmb_plan_get_tree(fmmb_plan* plan, uint32_t* perm, uint32_t* codes, uint32_
 
 int fmmb_plan_get_expansions(fmmb_plan* plan, double* multipoles, double* locals) {
   if (!plan) { set_error("null plan"); return FMMB_ERR_INVALID; }
-  if (plan->stokes || plan->yukawa) {
+  if (plan->stokes || plan->yukawa || plan->sbem) {
     set_error("fmmb_plan_get_expansions returns LaplaceSpherical[BEM] expansions only");
     return FMMB_ERR_UNSUPPORTED;
   }

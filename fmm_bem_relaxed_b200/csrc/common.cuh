@@ -162,6 +162,7 @@ struct TransBatch {
 
 struct BemData;
 struct StokesData;
+struct StokesBemData;
 struct YukawaData;
 struct GmresWorkspace;
 
@@ -192,6 +193,7 @@ struct fmmb_plan {
   fmmb::DevBuf<double4> res_tree;    // multi-GPU: near + far in tree order, all-gathered over NCCL
   fmmb::BemData* bem = nullptr;      // LaplaceSphericalBEM plans only
   fmmb::StokesData* stokes = nullptr;  // StokesSpherical plans only
+  fmmb::StokesBemData* sbem = nullptr; // StokesSphericalBEM plans only
   fmmb::YukawaData* yukawa = nullptr;  // YukawaCartesian plans only
   fmmb::GmresWorkspace* gmres_ws = nullptr;  // fmmb_gmres scratch, kept between solves
   int charge_dim = 1, result_dim = 4;
@@ -297,6 +299,12 @@ void stokes_free(StokesData* d);
 bool stokes_is_stresslet(const StokesData* d);
 void stokes_direct_raw(bool stresslet, const double* d_spts, const double* d_q, int64_t ns, const double* d_tpts,
                        int64_t nt, double* d_out, cudaStream_t s);
+// stokes_bem.cu
+void stokes_bem_setup(fmmb_plan* plan, const double* verts_host, const int32_t* bc_host, int quad_k, int quad_kfine,
+                      double mu);
+void stokes_bem_execute(fmmb_plan* plan, const double* d_charges, double* d_results);
+void stokes_bem_free(StokesBemData* d);
+int64_t stokes_bem_nnz(const StokesBemData* d);
 // m2l_classes.cu
 void m2l_init_tables();
 void build_m2l_classes(fmmb_plan* plan);

@@ -1,0 +1,477 @@
+// csrc/stokes_bem.cu -- StokesSphericalBEM on the GPU: triangular panels, 3 x 3 block near field cached once per
+// plan, far field through two groups of four Laplace expansion sets.
+//
+// Replaces (reference kernel/StokesSphericalBEM.hpp):
+//   :60-96    Panel(p0, p1, p2): centre, normal, area                       -> sbem_setup_kernel (bem::make_panel)
+//   :377-390  operator() -> :257-375 eval_velocity_integral / :160-255 eval_traction_integral, evaluated for every
+//             near pair into a CSR matrix of Mat3 by include/executor/EvalP2P.hpp:47-97
+//                                                                          -> sbem_assemble_kernel (once per plan)
+//   include/Matvec.hpp:14-33 (Mat3 x Vec<3> CSR matvec) in EvalInteractionLazySparse.hpp:134-151
+//                                                                          -> sbem_near_kernel (per matvec)
+//   :392-466  P2M with K quadrature points per panel: VELOCITY panels feed group 0 with the Stokeslet sets
+//             f Y, (f.x) Y (f = Area w_i charge, x = quadrature point); TRACTION panels feed group 1 with the
+//             stresslet sets (w_s . grad)(rho^n Y), g = Area w_i charge, n = panel normal
+//                                                                          -> sbem_p2m_kernel<GROUP>
+//   :468-472, :494-506  M2M / M2L / L2L of each set                         -> laplace_translations() per set
+//   :508-527  L2P: r = StokesSpherical::L2P (kernel/StokesSpherical.hpp:318-401, scale 1) of the group the TARGET's
+//             boundary condition picks; result += r / (2 mu) (VELOCITY) or 0.5 r (TRACTION) -> sbem_l2p_kernel
+//
+// Near-field layout: block dense like csrc/bem.cu -- a work item is <= 32 targets of one leaf against the leaf's
+// whole source list; entry e (row-major in the 3 x 3 block) of (target lane, source j) sits at
+// val[base + (j * 9 + e) * cnt + lane], so the per-matvec kernel streams 72 bytes per pair with coalesced loads
+// (HBM bound).
+//
+// Reference quirks kept for parity: near-field entries as the reference computes them when
+// compiled (K-point rule for every pair) unless FMMB_FLAG_STOKES_BEM_AS_WRITTEN asks for the branches of its source
+// text, whose self term is the reference's reading of Fata's closed form (stokes_bem_math.hpp); the TRACTION far
+// field enters with +0.5 although the near field carries -3 x the same integral (the reference's own FMM and Direct
+// disagree for TRACTION targets; its driver only uses that plan for a right-hand side it then overwrites,
+// examples/StokesBEM.cpp:256-271).
+#include "common.cuh"
+#include "laplace_ops.cuh"
+#include "../hostcxx/stokes_bem_math.hpp"
+#include <algorithm>
+
+namespace fmmb {
+
+struct StokesBemData {
+  int K = 4, kfine = 19;
+  double mu = 1e-3;
+  bool as_written = false;                 // FMMB_FLAG_STOKES_BEM_AS_WRITTEN
+  bool group_active[2] = {false, false};   // some panel carries VELOCITY (0) / TRACTION (1)
+  DevBuf<bem::Panel> pan;          // tree order
+  DevBuf<int> bc;                  // tree order: 0 VELOCITY, 1 TRACTION
+  DevBuf<double> chg;              // tree order, 3 per panel
+  DevBuf<double> nf_val;           // cached near field, 9 doubles per pair, block layout (see above)
+  DevBuf<long long> nf_base;       // per work item: offset of its block in PAIRS
+  int64_t nnz = 0;                 // pairs
+  DevBuf<double> M4[4], L4[4];     // the four expansion sets of the group being evaluated
+  DevBuf<double> res_near, res_far;  // tree order, 3 per panel
+  int p_alloc = 0;
+};
+
+void stokes_bem_free(StokesBemData* d) { delete d; }
+int64_t stokes_bem_nnz(const StokesBemData* d) { return d->nnz; }
+
+namespace {
+
+using namespace ops;
+
+__constant__ bem::Rule c_srule;   // K-point panel rule
+__constant__ bem::Rule c_sfine;   // fine rule for panels closer than 2 sqrt(2 Area)
+
+inline int nblk(int64_t n, int t) { return (int)((n + t - 1) / t); }
+
+__global__ void sbem_setup_kernel(const double* __restrict__ verts, const int* __restrict__ bc,
+                                  const unsigned* __restrict__ perm, int64_t n, bem::Panel* __restrict__ pan,
+                                  int* __restrict__ bc_tree) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double* v = verts + 9 * (size_t)perm[i];
+  bem::Panel p;
+  bem::make_panel(v, v + 3, v + 6, p);
+  pan[i] = p;
+  bc_tree[i] = bc ? bc[perm[i]] : 0;
+}
+
+// per work item: pairs = targets x total source panels of the leaf's list
+__global__ void sbem_count_kernel(const int4* __restrict__ items, int nitems, const unsigned* __restrict__ bb,
+                                  const unsigned* __restrict__ be, const int* __restrict__ off,
+                                  const int* __restrict__ src, long long* __restrict__ cnt) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i > nitems) return;
+  long long c = 0;
+  if (i < nitems) {
+    const int4 it = items[i];
+    long long ns = 0;
+    for (int e = off[it.x]; e < off[it.x + 1]; ++e) ns += be[src[e]] - bb[src[e]];
+    c = ns * it.z;
+  }
+  cnt[i] = c;
+}
+
+constexpr int kSbemWarps = 4;
+
+// one warp per work item: lane = target, source panels staged through a warp-private tile
+__global__ void __launch_bounds__(32 * kSbemWarps)
+sbem_assemble_kernel(const int4* __restrict__ items, int nitems, const unsigned* __restrict__ bb,
+                     const unsigned* __restrict__ be, const int* __restrict__ off, const int* __restrict__ src,
+                     const bem::Panel* __restrict__ pan, const int* __restrict__ bc,
+                     const long long* __restrict__ base, double mu, bool as_written, double* __restrict__ val) {
+  __shared__ bem::Panel tiles[kSbemWarps][32];
+  const int wl = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int item = blockIdx.x * kSbemWarps + wl;
+  if (item >= nitems) return;
+  bem::Panel* tile = tiles[wl];
+  const int4 it = items[item];
+  const int cnt = it.z;
+  const bool act = lane < cnt;
+  double tc[3] = {0, 0, 0};
+  int tbc = 0;
+  if (act) {
+    const bem::Panel& t = pan[it.y + lane];
+    tc[0] = t.c[0]; tc[1] = t.c[1]; tc[2] = t.c[2];
+    tbc = bc[it.y + lane];
+  }
+  double* out = val + 9 * base[item];
+  long long j = 0;
+  for (int e = off[it.x]; e < off[it.x + 1]; ++e) {
+    const int sb = src[e];
+    const unsigned c0 = bb[sb], c1 = be[sb];
+    for (unsigned b0 = c0; b0 < c1; b0 += 32) {
+      const int ns = (int)min(32u, c1 - b0);
+      __syncwarp();
+      if (lane < ns) tile[lane] = pan[b0 + lane];
+      __syncwarp();
+      if (act)
+        for (int k = 0; k < ns; ++k) {
+          double m[9];
+          bem::stokes_kernel(tbc, tc, tile[k], c_srule, c_sfine, mu, as_written, m);
+#pragma unroll
+          for (int q = 0; q < 9; ++q) out[((j + k) * 9 + q) * cnt + lane] = m[q];
+        }
+      j += ns;
+    }
+  }
+}
+
+// results(targets of the item) = block * charges(sources); same traversal order as the assembly
+__global__ void __launch_bounds__(32 * kSbemWarps)
+sbem_near_kernel(const int4* __restrict__ items, int nitems, const unsigned* __restrict__ bb,
+                 const unsigned* __restrict__ be, const int* __restrict__ off, const int* __restrict__ src,
+                 const double* __restrict__ chg, const long long* __restrict__ base,
+                 const double* __restrict__ val, double* __restrict__ res) {
+  __shared__ double tiles[kSbemWarps][96];
+  const int wl = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int item = blockIdx.x * kSbemWarps + wl;
+  if (item >= nitems) return;
+  double* tile = tiles[wl];
+  const int4 it = items[item];
+  const int cnt = it.z;
+  const bool act = lane < cnt;
+  const double* in = val + 9 * base[item] + lane;
+  double u0 = 0, u1 = 0, u2 = 0;
+  long long j = 0;
+  for (int e = off[it.x]; e < off[it.x + 1]; ++e) {
+    const int sb = src[e];
+    const unsigned c0 = bb[sb], c1 = be[sb];
+    for (unsigned b0 = c0; b0 < c1; b0 += 32) {
+      const int ns = (int)min(32u, c1 - b0);
+      __syncwarp();
+      for (int k = lane; k < 3 * ns; k += 32) tile[k] = chg[3 * (size_t)b0 + k];   // contiguous: coalesced
+      __syncwarp();
+      if (act) {
+#pragma unroll 2
+        for (int k = 0; k < ns; ++k) {
+          const double* a = in + (j + k) * 9 * cnt;
+          const double f0 = tile[3 * k], f1 = tile[3 * k + 1], f2 = tile[3 * k + 2];
+          u0 = fma(a[0], f0, fma(a[(size_t)cnt], f1, fma(a[2 * (size_t)cnt], f2, u0)));
+          u1 = fma(a[3 * (size_t)cnt], f0, fma(a[4 * (size_t)cnt], f1, fma(a[5 * (size_t)cnt], f2, u1)));
+          u2 = fma(a[6 * (size_t)cnt], f0, fma(a[7 * (size_t)cnt], f1, fma(a[8 * (size_t)cnt], f2, u2)));
+        }
+      }
+      j += ns;
+    }
+  }
+  if (act) {
+    double* o = res + 3 * (size_t)(it.y + lane);
+    o[0] = u0; o[1] = u1; o[2] = u2;
+  }
+}
+
+// charges (original order, 3 per panel) into tree order
+__global__ void sbem_gather(const double* __restrict__ q, const unsigned* __restrict__ perm, int64_t n,
+                            double* __restrict__ chg) {
+  int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (t >= 3 * n) return;
+  const int64_t i = t / 3;
+  const int c = (int)(t - 3 * i);
+  chg[t] = q[3 * (size_t)perm[i] + c];
+}
+
+// ---- P2M: warp per (leaf, set); lane = (panel, quadrature point) writes its row, then lane = coefficient sums
+// the column.  GROUP 0: VELOCITY panels, Stokeslet sets; GROUP 1: TRACTION panels, stresslet sets.
+template <int GROUP>
+__global__ void __launch_bounds__(128)
+sbem_p2m_kernel(const int* __restrict__ leaves, int nleaves, const unsigned* __restrict__ bb,
+                const unsigned* __restrict__ be, const double4* __restrict__ center,
+                const bem::Panel* __restrict__ pan, const int* __restrict__ bc, const double* __restrict__ chg, int P,
+                double* __restrict__ M0, double* __restrict__ M1, double* __restrict__ M2, double* __restrict__ M3) {
+  extern __shared__ double sbem_sh[];
+  const int pp = P * P, ld = pp | 1;
+  const int wl = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int w = blockIdx.x * (blockDim.x >> 5) + wl;
+  const int set = blockIdx.y;
+  if (w >= nleaves) return;
+  double* tile = sbem_sh + (size_t)wl * 32 * ld;
+  const int b = leaves[w];
+  const double4 c = center[b];
+  const unsigned b0 = bb[b], b1 = be[b];
+  const int K = c_srule.n;
+  const int nent = (int)(b1 - b0) * K;
+  double acc[(FMMB_MAX_P * FMMB_MAX_P + 31) / 32];
+#pragma unroll
+  for (int i = 0; i < (FMMB_MAX_P * FMMB_MAX_P + 31) / 32; ++i) acc[i] = 0.0;
+  for (int base = 0; base < nent; base += 32) {
+    const int ent = base + lane;
+    const int cnt = min(32, nent - base);
+    __syncwarp();
+    if (ent < nent) {
+      const unsigned i = b0 + ent / K;
+      const int qi = ent % K;
+      double* row = tile + lane * ld;
+      if (bc[i] != GROUP) {
+        for (int r = 0; r < pp; ++r) row[r] = 0.0;
+      } else {
+        const bem::Panel& s = pan[i];
+        double q[3];
+        bem::quad_point(s, c_srule.pt[qi], q);
+        const double wa = s.area * c_srule.w[qi];
+        const double g0 = wa * chg[3 * (size_t)i], g1 = wa * chg[3 * (size_t)i + 1], g2 = wa * chg[3 * (size_t)i + 2];
+        const Sph sp = to_sph(q[0] - c.x, q[1] - c.y, q[2] - c.z);
+        if (GROUP == 0) {
+          const double mult = set == 0 ? g0 : (set == 1 ? g1 : (set == 2 ? g2 : g0 * q[0] + g1 * q[1] + g2 * q[2]));
+          regular_harmonics<false>(P, sp, -1.0, [&](int n, int m, double yr, double yi, double, double) {
+            row[n * n + n + m] = mult * yr;
+            if (m > 0) row[n * n + n - m] = mult * yi;
+          });
+        } else {
+          const double n0 = s.nrm[0], n1 = s.nrm[1], n2 = s.nrm[2];
+          // direction of the derivative for this set: w_s = g_s n + n_s g (s < 3), w_3 = (x.g) n + (n.x) g
+          double a, bq;
+          if (set == 0) { a = g0; bq = n0; }
+          else if (set == 1) { a = g1; bq = n1; }
+          else if (set == 2) { a = g2; bq = n2; }
+          else { a = q[0] * g0 + q[1] * g1 + q[2] * g2; bq = n0 * q[0] + n1 * q[1] + n2 * q[2]; }
+          const double w0 = a * n0 + bq * g0, w1 = a * n1 + bq * g1, w2 = a * n2 + bq * g2;
+          // spherical basis vectors over the metric: grad = e_r d/drho + e_a/rho d/dalpha + e_b/(rho sin) d/dbeta
+          const double ir = 1.0 / sp.r, iry = ir / sp.y;
+          const double wa_ = w0 * (sp.y * sp.cp) + w1 * (sp.y * sp.sp) + w2 * sp.x;
+          const double wb = (w0 * (sp.x * sp.cp) + w1 * (sp.x * sp.sp) - w2 * sp.y) * ir;
+          const double wc = (-w0 * sp.sp + w1 * sp.cp) * iry;
+          regular_harmonics<true>(P, sp, -1.0, [&](int n, int m, double yr, double yi, double tr, double ti) {
+            // brh = n/rho Y, bal = Ytheta, bbe = -i m Y = (m yi, -m yr)
+            const double fr = n * ir;
+            row[n * n + n + m] = wa_ * fr * yr + wb * tr + wc * (m * yi);
+            if (m > 0) row[n * n + n - m] = wa_ * fr * yi + wb * ti - wc * (m * yr);
+          });
+        }
+      }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int i2 = 0; i2 < (FMMB_MAX_P * FMMB_MAX_P + 31) / 32; ++i2) {
+      const int col = lane + 32 * i2;
+      if (col < pp) {
+        double sum = 0;
+        for (int k = 0; k < cnt; ++k) sum += tile[k * ld + col];
+        acc[i2] += sum;
+      }
+    }
+  }
+  double* Mb = (set == 0 ? M0 : (set == 1 ? M1 : (set == 2 ? M2 : M3))) + (size_t)b * xstride(P);
+#pragma unroll
+  for (int i2 = 0; i2 < (FMMB_MAX_P * FMMB_MAX_P + 31) / 32; ++i2) {
+    const int col = lane + 32 * i2;
+    if (col < pp) Mb[col] = acc[i2];
+  }
+}
+
+// ---- L2P: warp per leaf, lane per target panel (its centre), all four sets in one pass over the harmonics; only
+// targets whose boundary condition selects GROUP are written (res is zeroed before the first group)
+__global__ void __launch_bounds__(128)
+sbem_l2p_kernel(const int* __restrict__ leaves, int nleaves, const unsigned* __restrict__ bb,
+                const unsigned* __restrict__ be, const double4* __restrict__ center,
+                const unsigned char* __restrict__ has_local, const bem::Panel* __restrict__ pan,
+                const int* __restrict__ bc, int group, int P, const double* __restrict__ L0,
+                const double* __restrict__ L1, const double* __restrict__ L2, const double* __restrict__ L3,
+                double scale, double* __restrict__ res) {
+  extern __shared__ double2 sbem_ls[];
+  const int nc = P * (P + 1) / 2;
+  const int wl = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int w = blockIdx.x * (blockDim.x >> 5) + wl;
+  if (w >= nleaves) return;
+  const int b = leaves[w];
+  if (!has_local[b]) return;
+  const unsigned b0 = bb[b], b1 = be[b];
+  double2* Ls = sbem_ls + (size_t)wl * 4 * nc;
+  for (int i = lane; i < 4 * nc; i += 32) {
+    const int set = i / nc, e = i - set * nc;
+    int n, m;
+    unpack_nm(e, n, m);
+    const double* L = set == 0 ? L0 : (set == 1 ? L1 : (set == 2 ? L2 : L3));
+    Ls[i] = load_coef(L + (size_t)b * xstride(P), n, m);
+  }
+  __syncwarp();
+  const double4 c = center[b];
+  for (unsigned i = b0 + lane; i < b1; i += 32) {
+    if (bc[i] != group) continue;
+    const double px = pan[i].c[0], py = pan[i].c[1], pz = pan[i].c[2];
+    const Sph s = to_sph(px - c.x, py - c.y, pz - c.z);
+    const double inv_r = 1.0 / s.r;
+    double pot[4] = {0, 0, 0, 0}, ga[4] = {0, 0, 0, 0}, gb[4] = {0, 0, 0, 0}, gc[4] = {0, 0, 0, 0};
+    regular_harmonics<true>(P, s, 1.0, [&](int n, int m, double yr, double yi, double tr, double ti) {
+      const double w2 = m == 0 ? 1.0 : 2.0;
+      const int e = n * (n + 1) / 2 + m;
+#pragma unroll
+      for (int set = 0; set < 4; ++set) {
+        const double2 l = Ls[set * nc + e];
+        const double re = w2 * (l.x * yr - l.y * yi);     // Re(L Y)
+        pot[set] += re;
+        ga[set] += re * inv_r * n;
+        gb[set] += w2 * (l.x * tr - l.y * ti);            // Re(L Ytheta)
+        gc[set] -= w2 * (l.x * yi + l.y * yr) * m;        // Re(L Y i) m
+      }
+    });
+    const double inv_ry = inv_r / s.y;
+    const double xs_[3] = {px, py, pz};
+    double u[3] = {0, 0, 0};
+#pragma unroll
+    for (int set = 0; set < 4; ++set) {
+      const double cx = s.y * s.cp * ga[set] + s.x * s.cp * inv_r * gb[set] - s.sp * inv_ry * gc[set];
+      const double cy = s.y * s.sp * ga[set] + s.x * s.sp * inv_r * gb[set] + s.cp * inv_ry * gc[set];
+      const double cz = s.x * ga[set] - s.y * inv_r * gb[set];
+      const double f = set < 3 ? -xs_[set < 3 ? set : 0] : 1.0;
+      u[0] += f * cx; u[1] += f * cy; u[2] += f * cz;
+    }
+    res[3 * (size_t)i + 0] = scale * (pot[0] + u[0]);
+    res[3 * (size_t)i + 1] = scale * (pot[1] + u[1]);
+    res[3 * (size_t)i + 2] = scale * (pot[2] + u[2]);
+  }
+}
+
+void swap_buf(DevBuf<double>& a, DevBuf<double>& b) {
+  std::swap(a.p, b.p); std::swap(a.cap, b.cap); std::swap(a.n, b.n);
+}
+struct SetGuard {            // plan->M / plan->L temporarily ARE set k of the group being evaluated
+  fmmb_plan* plan; StokesBemData* d; int k;
+  SetGuard(fmmb_plan* pl, StokesBemData* dd, int kk) : plan(pl), d(dd), k(kk) { swap_buf(plan->M, d->M4[k]); swap_buf(plan->L, d->L4[k]); }
+  ~SetGuard() { swap_buf(plan->M, d->M4[k]); swap_buf(plan->L, d->L4[k]); }
+};
+
+}  // namespace
+
+// Plan-time: panel geometry in tree order, then the cached 3 x 3 block near field.
+void stokes_bem_setup(fmmb_plan* plan, const double* verts_host, const int32_t* bc_host, int quad_k, int quad_kfine,
+                      double mu) {
+  Tree& T = plan->tree;
+  cudaStream_t s = plan->stream;
+  if (quad_kfine <= 0) quad_kfine = 25;      // StokesSphericalBEM(p, k, mu) leaves K_fine = 25 (:136)
+  if (!bem::rule_supported(quad_k) || !bem::rule_supported(quad_kfine))
+    throw StatusError{FMMB_ERR_UNSUPPORTED, "quad_k / quad_kfine must be keys of the reference's Gauss table: 1, 3, 4, 7, 13, 17, 19, 25 or 79"};
+  if (!(mu > 0)) throw StatusError{FMMB_ERR_INVALID, "StokesSphericalBEM needs a positive viscosity (fmmb_kernel_desc.kappa)"};
+  StokesBemData* B = new StokesBemData();
+  plan->sbem = B;
+  B->K = quad_k; B->kfine = quad_kfine; B->mu = mu;
+  B->as_written = (plan->opts.kernel_flags & FMMB_FLAG_STOKES_BEM_AS_WRITTEN) != 0;
+  upload_laplace_tables();   // this translation unit's copy of the factorial tables
+  const bem::Rule rule = bem::make_rule(quad_k), fine = bem::make_rule(quad_kfine);
+  FMMB_CUDA(cudaMemcpyToSymbol(c_srule, &rule, sizeof rule));
+  FMMB_CUDA(cudaMemcpyToSymbol(c_sfine, &fine, sizeof fine));
+  const int64_t n = T.n;
+  DevBuf<double> verts;
+  DevBuf<int> bc;
+  verts.from_host(verts_host, 9 * (size_t)n, s);
+  for (int64_t i = 0; i < n; ++i) {
+    const int v = bc_host ? bc_host[i] : 0;
+    if (v != 0 && v != 1) throw StatusError{FMMB_ERR_INVALID, "bc entries must be 0 (VELOCITY) or 1 (TRACTION)"};
+    B->group_active[v] = true;
+  }
+  if (bc_host) bc.from_host(bc_host, n, s);
+  B->pan.resize(n); B->bc.resize(n); B->chg.resize(3 * (size_t)n);
+  sbem_setup_kernel<<<nblk(n, 128), 128, 0, s>>>(verts.p, bc_host ? bc.p : nullptr, T.perm.p, n, B->pan.p, B->bc.p);
+  FMMB_CUDA(cudaGetLastError());
+  const int ni = T.n_p2p_items;
+  DevBuf<long long> cnt;
+  cnt.resize(ni + 1);
+  sbem_count_kernel<<<nblk(ni + 1, 128), 128, 0, s>>>(T.p2p_items.p, ni, T.bbegin.p, T.bend.p, T.p2p_off.p,
+                                                     T.p2p_src.p, cnt.p);
+  FMMB_CUDA(cudaGetLastError());
+  std::vector<long long> h = cnt.to_host(s), off(ni + 1, 0);
+  for (int i = 0; i < ni; ++i) off[i + 1] = off[i] + h[i];
+  B->nnz = off[ni];
+  B->nf_base.from_host(off.data(), off.size(), s);
+  B->nf_val.resize(9 * (size_t)B->nnz);
+  if (ni)
+    sbem_assemble_kernel<<<nblk(ni, kSbemWarps), 32 * kSbemWarps, 0, s>>>(T.p2p_items.p, ni, T.bbegin.p, T.bend.p,
+                                                                         T.p2p_off.p, T.p2p_src.p, B->pan.p, B->bc.p,
+                                                                         B->nf_base.p, B->mu, B->as_written, B->nf_val.p);
+  FMMB_CUDA(cudaGetLastError());
+  FMMB_CUDA(cudaStreamSynchronize(s));
+}
+
+void stokes_bem_execute(fmmb_plan* plan, const double* d_charges, double* d_results) {
+  Tree& T = plan->tree;
+  StokesBemData* B = plan->sbem;
+  const int P = plan->p, nc = P * (P + 1) / 2, pp = P * P;
+  const int xs = xstride(P);
+  const int64_t n = T.n;
+  cudaStream_t s = plan->stream;
+  cudaEvent_t* ev = plan->ev;
+  for (int k = 0; k < 4; ++k) {
+    B->M4[k].resize((size_t)T.nboxes * xs);
+    B->L4[k].resize((size_t)T.nboxes * xs);
+    if (B->p_alloc != P) { B->M4[k].zero(s); B->L4[k].zero(s); }   // padding double of odd-sized expansions
+  }
+  B->p_alloc = P;
+  B->res_near.resize(3 * (size_t)n);
+  B->res_far.resize(3 * (size_t)n);
+  plan->launches = 0;
+
+  if (!plan->capturing) FMMB_CUDA(cudaEventRecord(ev[0], s));
+  sbem_gather<<<nblk(3 * n, 256), 256, 0, s>>>(d_charges, T.perm.p, n, B->chg.p);
+  ++plan->launches;
+  FMMB_CUDA(cudaEventRecord(ev[1], s));
+
+  // cached near field (one pass over 72 bytes per pair)
+  if (!plan->capturing) FMMB_CUDA(cudaEventRecord(ev[6], s));
+  const int ni = T.n_p2p_items;
+  if (ni) {
+    sbem_near_kernel<<<nblk(ni, kSbemWarps), 32 * kSbemWarps, 0, s>>>(T.p2p_items.p, ni, T.bbegin.p, T.bend.p,
+                                                                     T.p2p_off.p, T.p2p_src.p, B->chg.p, B->nf_base.p,
+                                                                     B->nf_val.p, B->res_near.p);
+    ++plan->launches;
+  }
+  FMMB_CUDA(cudaEventRecord(ev[7], s));
+  B->res_far.zero(s);
+  ++plan->launches;
+
+  // far field, one group of four sets at a time
+  if (!plan->capturing) FMMB_CUDA(cudaEventRecord(ev[12], s));
+  const int warps = pp <= 64 ? 4 : 1;
+  const size_t sh = (size_t)warps * 32 * (pp | 1) * sizeof(double);
+  // per call: function attributes belong to the current device
+  FMMB_CUDA(cudaFuncSetAttribute(sbem_p2m_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024));
+  FMMB_CUDA(cudaFuncSetAttribute(sbem_p2m_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024));
+  for (int group = 0; group < 2; ++group) {
+    if (!B->group_active[group] || plan->near_only) continue;   // near_only: plans for preconditioners
+    const dim3 pg(nblk(T.nleaves, warps), 4);
+    if (group == 0)
+      sbem_p2m_kernel<0><<<pg, 32 * warps, sh, s>>>(T.leaves.p, T.nleaves, T.bbegin.p, T.bend.p, T.center.p, B->pan.p,
+                                                    B->bc.p, B->chg.p, P, B->M4[0].p, B->M4[1].p, B->M4[2].p,
+                                                    B->M4[3].p);
+    else
+      sbem_p2m_kernel<1><<<pg, 32 * warps, sh, s>>>(T.leaves.p, T.nleaves, T.bbegin.p, T.bend.p, T.center.p, B->pan.p,
+                                                    B->bc.p, B->chg.p, P, B->M4[0].p, B->M4[1].p, B->M4[2].p,
+                                                    B->M4[3].p);
+    ++plan->launches;
+    for (int k = 0; k < 4; ++k) {
+      SetGuard g(plan, B, k);
+      laplace_translations(plan, s);
+    }
+    // VELOCITY: result += r / (2 mu);  TRACTION: result += 0.5 r  (:508-527)
+    const double scale = group == 0 ? 1. / 2 / B->mu : 0.5;
+    if (T.n_own_leaves)
+      sbem_l2p_kernel<<<nblk(T.n_own_leaves, 4), 128, (size_t)4 * 4 * nc * sizeof(double2), s>>>(
+          T.own_leaves.p, T.n_own_leaves, T.bbegin.p, T.bend.p, T.center.p, T.has_local.p, B->pan.p, B->bc.p, group, P,
+          B->L4[0].p, B->L4[1].p, B->L4[2].p, B->L4[3].p, scale, B->res_far.p);
+    ++plan->launches;
+  }
+  if (!plan->capturing) FMMB_CUDA(cudaEventRecord(ev[4], s));
+  finish_results(plan, B->res_near.p, B->res_far.p, 3, d_results, s);
+  if (!plan->capturing) FMMB_CUDA(cudaEventRecord(ev[5], s));
+  FMMB_CUDA(cudaGetLastError());
+  plan->timed = true;
+}
+
+}  // namespace fmmb

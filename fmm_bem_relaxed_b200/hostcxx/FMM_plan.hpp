@@ -37,7 +37,7 @@ class FMM_plan {
     std::vector<double> pts, verts;
     std::vector<int32_t> bc;
     Kernel::pack_sources(source, pts, verts, bc);
-    fmmb_kernel_desc kd = {Kernel::fmmb_kind, K.order(), K.kappa(), K.quad_k(), 0};
+    fmmb_kernel_desc kd = {Kernel::fmmb_kind, K.order(), K.kappa(), K.quad_k(), K.quad_kfine()};
     fmmb_sources src = {(int64_t)n_, pts.data(), verts.empty() ? nullptr : verts.data(),
                         bc.empty() ? nullptr : bc.data()};
     fmmb_options fo = {};
@@ -46,6 +46,7 @@ class FMM_plan {
     fo.evaluator = opts_.evaluator == FMMOptions::FMM ? FMMB_EVAL_FMM : FMMB_EVAL_TREECODE;
     fo.device = opts_.device;
     fo.near_only = opts_.block_diagonal ? 2 : (opts_.local_evaluation ? 1 : 0);   // plans for preconditioners
+    fo.kernel_flags = K.kernel_flags();
     if (fmmb_plan_create(&kd, &src, &fo, &plan_) != FMMB_OK) {
       std::cerr << "[E]: FMM_plan: " << fmmb_last_error() << "\n";
       plan_ = nullptr;

@@ -62,4 +62,6 @@ class LaplaceSpherical {
     for (size_t i = 0; i < src.size(); ++i) { pts[3 * i] = src[i][0]; pts[3 * i + 1] = src[i][1]; pts[3 * i + 2] = src[i][2]; }
   }
   int quad_k() const { return 0; }
+  int quad_kfine() const { return 0; }
+  int kernel_flags() const { return 0; }
 };

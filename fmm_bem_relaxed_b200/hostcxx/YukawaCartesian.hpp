@@ -43,6 +43,8 @@ class YukawaCartesian {
   int order() const { return P; }
   double kappa() const { return Kappa; }
   int quad_k() const { return 0; }
+  int quad_kfine() const { return 0; }
+  int kernel_flags() const { return 0; }
 
   /** Kernel evaluation K(t,s), same operation order as the reference (:148-159) */
   kernel_value_type operator()(const point_type& t, const point_type& s) const {

@@ -5,8 +5,8 @@
  * device (near-field assembly in csrc/bem.cu).
  *
  * Follows reference kernel/LaplaceSphericalBEM.hpp:61-97 (Panel), :159-264 (eval_G / eval_dGdn),
- * :273-297 (operator()), examples/BEM/SemiAnalytical.hpp:13-203 (Laplace branch) and the Gauss rules
- * 1, 3, 4 and "17" (16 points) of examples/BEM/GaussQuadrature.hpp:27-31,86-116.
+ * :273-297 (operator()), examples/BEM/SemiAnalytical.hpp:13-203 (Laplace branch) and the triangle Gauss rules
+ * of examples/BEM/GaussQuadrature.hpp:27-276 (every key of its table: 1, 3, 4, 7, 13, 17, 19, 25, 79).
  */
 #include <cmath>
 
@@ -25,33 +25,102 @@ struct Panel {
   double area;
 };
 
+constexpr int kMaxRulePoints = 79;
+
 struct Rule {
   int n;
-  double pt[16][3];
-  double w[16];
+  double pt[kMaxRulePoints][3];
+  double w[kMaxRulePoints];
 };
 
-/** Triangle Gauss rule with k points; k = 7 aliases the 4-point rule like the reference does. */
+namespace detail {
+/** Symmetric triangle rules are stored by orbit: 1 point (a, a, a); 3 points (p, q, q), (q, p, q), (q, q, p);
+ * 6 points (p, q, r), (p, r, q), (q, p, r), (q, r, p), (r, p, q), (r, q, p) -- the order in which the reference lists
+ * them (examples/BEM/GaussQuadrature.hpp:62-276), which fixes the summation order of every panel integral. */
+struct Orbit { int kind; double p, q, r, w; };
+
+inline void expand_orbits(const Orbit* o, int count, Rule& rule) {
+  int n = 0;
+  for (int i = 0; i < count; ++i) {
+    const double p = o[i].p, q = o[i].q, r = o[i].r;
+    if (o[i].kind == 1) {
+      const double t[1][3] = {{p, p, p}};
+      for (int k = 0; k < 3; ++k) rule.pt[n][k] = t[0][k];
+      rule.w[n++] = o[i].w;
+    } else if (o[i].kind == 3) {
+      const double t[3][3] = {{p, q, q}, {q, p, q}, {q, q, p}};
+      for (int j = 0; j < 3; ++j) { for (int k = 0; k < 3; ++k) rule.pt[n][k] = t[j][k]; rule.w[n++] = o[i].w; }
+    } else {
+      const double t[6][3] = {{p, q, r}, {p, r, q}, {q, p, r}, {q, r, p}, {r, p, q}, {r, q, p}};
+      for (int j = 0; j < 6; ++j) { for (int k = 0; k < 3; ++k) rule.pt[n][k] = t[j][k]; rule.w[n++] = o[i].w; }
+    }
+  }
+  rule.n = n;
+}
+}  // namespace detail
+
+/** Triangle Gauss rule filed under k in the reference's table (GaussQuadrature.hpp:41-276): k = 1, 3, 4, 13, 19, 25,
+ * 79 points; k = 7 aliases the 4-point rule and the rule filed under 17 has 16 points, both like the reference. */
 inline Rule make_rule(int k) {
+  using detail::Orbit;
   Rule r = {};
+  const double a = 1 / 3.;
   if (k == 1) {
     r.n = 1; r.pt[0][0] = r.pt[0][1] = r.pt[0][2] = 1. / 3; r.w[0] = 1.;
   } else if (k == 3) {
     const double p[3][3] = {{0.5, 0.5, 0.}, {0., 0.5, 0.5}, {0.5, 0., 0.5}};
     r.n = 3;
     for (int i = 0; i < 3; ++i) { for (int j = 0; j < 3; ++j) r.pt[i][j] = p[i][j]; r.w[i] = 1. / 3; }
+  } else if (k == 13) {
+    const Orbit o[] = {{1, a, 0, 0, -0.149570044467682},
+                       {3, 0.479308067841920, 0.260345966079040, 0, 0.175615257433208},
+                       {3, 0.869739794195568, 0.065130102902216, 0, 0.053347235608838},
+                       {6, 0.048690315425316, 0.312865496004874, 0.638444188569810, 0.077113760890257}};
+    detail::expand_orbits(o, 4, r);
   } else if (k == 17) {
-    const double a = 1 / 3., b1 = 0.081414823414554, b2 = 0.459292588292723, c1 = 0.658861384496480,
-                 c2 = 0.170569307751760, d1 = 0.898905543365938, d2 = 0.050547228317031,
-                 e1 = 0.008394777409958, e2 = 0.263112829634638, e3 = 0.728492392955404;
-    const double wa = 0.144315607677787, wb = 0.095091634267285, wc = 0.103217370534718,
-                 wd = 0.032458497623198, we = 0.027230314174435;
-    const double p[16][3] = {{a, a, a}, {b1, b2, b2}, {b2, b1, b2}, {b2, b2, b1}, {c1, c2, c2}, {c2, c1, c2},
-                             {c2, c2, c1}, {d1, d2, d2}, {d2, d1, d2}, {d2, d2, d1}, {e1, e2, e3}, {e1, e3, e2},
-                             {e2, e1, e3}, {e2, e3, e1}, {e3, e1, e2}, {e3, e2, e1}};
-    const double w[16] = {wa, wb, wb, wb, wc, wc, wc, wd, wd, wd, we, we, we, we, we, we};
-    r.n = 16;
-    for (int i = 0; i < 16; ++i) { for (int j = 0; j < 3; ++j) r.pt[i][j] = p[i][j]; r.w[i] = w[i]; }
+    const Orbit o[] = {{1, a, 0, 0, 0.144315607677787},
+                       {3, 0.081414823414554, 0.459292588292723, 0, 0.095091634267285},
+                       {3, 0.658861384496480, 0.170569307751760, 0, 0.103217370534718},
+                       {3, 0.898905543365938, 0.050547228317031, 0, 0.032458497623198},
+                       {6, 0.008394777409958, 0.263112829634638, 0.728492392955404, 0.027230314174435}};
+    detail::expand_orbits(o, 5, r);
+  } else if (k == 19) {
+    const Orbit o[] = {{1, a, 0, 0, 0.097135796282799},
+                       {3, 0.020634961602525, 0.489682519198738, 0, 0.031334700227139},
+                       {3, 0.125820817014127, 0.437089591492937, 0, 0.077827541004774},
+                       {3, 0.623592928761935, 0.188203535619033, 0, 0.079647738927210},
+                       {3, 0.910540973211095, 0.044729513394453, 0, 0.025577675658698},
+                       {6, 0.036838412054736, 0.221962989160766, 0.741198598784498, 0.043283539377289}};
+    detail::expand_orbits(o, 6, r);
+  } else if (k == 25) {
+    const Orbit o[] = {{1, a, 0, 0, 0.090817990382754},
+                       {3, 0.028844733232685, 0.485577633383657, 0, 0.036725957756467},
+                       {3, 0.781036849029926, 0.109481575485037, 0, 0.045321059435528},
+                       {6, 0.141707219414880, 0.307939838764121, 0.550352941820999, 0.072757916845420},
+                       {6, 0.025003534762686, 0.246672560639903, 0.728323904597411, 0.028327242531057},
+                       {6, 0.009540815400299, 0.066803251012200, 0.923655933587500, 0.009421666963733}};
+    detail::expand_orbits(o, 6, r);
+  } else if (k == 79) {
+    const Orbit o[] = {{1, a, 0, 0, 0.033057055541624},
+                       {3, -0.001900928704400, 0.500950464352200, 0, 0.000867019185663},
+                       {3, 0.023574084130543, 0.488212957934729, 0, 0.011660052716448},
+                       {3, 0.089726636099435, 0.455136681950283, 0, 0.022876936356421},
+                       {3, 0.196007481363421, 0.401996259318289, 0, 0.030448982673938},
+                       {3, 0.488214180481157, 0.255892909759421, 0, 0.030624891725355},
+                       {3, 0.647023488009788, 0.176488255995106, 0, 0.024368057676800},
+                       {3, 0.791658289326483, 0.104170855336758, 0, 0.015997432032024},
+                       {3, 0.893862072318140, 0.053068963840930, 0, 0.007698301815602},
+                       {3, 0.916762569607942, 0.041618715196029, 0, -0.000632060497488},
+                       {3, 0.976836157186356, 0.011581921406822, 0, 0.001751134301193},
+                       {6, 0.048741583664839, 0.344855770229001, 0.606402646106160, 0.016465839189576},
+                       {6, 0.006314115948605, 0.377843269594854, 0.615842614456541, 0.004839033540485},
+                       {6, 0.134316520547348, 0.306635479062357, 0.559048000390295, 0.025804906534650},
+                       {6, 0.013973893962392, 0.249419362774742, 0.736606743262866, 0.008471091054441},
+                       {6, 0.075549132909764, 0.212775724802802, 0.711675142287434, 0.018354914106280},
+                       {6, -0.008368153208227, 0.146965436053239, 0.861402717154987, 0.000704404677908},
+                       {6, 0.026686063258714, 0.137726978828923, 0.835586957912363, 0.010112684927462},
+                       {6, 0.010547719294141, 0.059696109149007, 0.929756171556853, 0.003573909385950}};
+    detail::expand_orbits(o, 19, r);
   } else {
     const double p[4][3] = {{1. / 3, 1. / 3, 1. / 3}, {.6, .2, .2}, {.2, .6, .2}, {.2, .2, .6}};
     const double w[4] = {-27. / 48, 25. / 48, 25. / 48, 25. / 48};
@@ -60,7 +129,10 @@ inline Rule make_rule(int k) {
   }
   return r;
 }
-inline bool rule_supported(int k) { return k == 1 || k == 3 || k == 4 || k == 7; }
+/** the keys of the reference's rule table (GaussQuadrature.hpp:41-276); any other k makes the reference exit */
+inline bool rule_supported(int k) {
+  return k == 1 || k == 3 || k == 4 || k == 7 || k == 13 || k == 17 || k == 19 || k == 25 || k == 79;
+}
 
 BEM_HD double norm3(const double* a) { return sqrt(a[0] * a[0] + a[1] * a[1] + a[2] * a[2]); }
 BEM_HD void cross3(const double* u, const double* v, double* o) {

@@ -55,16 +55,21 @@ typedef enum {
                                           1..10.  Near field and treecode are pinned to the reference; its FMM
                                           evaluator is broken for this kernel, so the far field is validated against
                                           Direct only */
-  FMMB_STOKES_SPHERICAL = 5            /* kernel/StokesSpherical.hpp default build (Stokeslet): charge 3 (f), result 3 */
+  FMMB_STOKES_SPHERICAL = 5,           /* kernel/StokesSpherical.hpp default build (Stokeslet): charge 3 (f), result 3 */
+  FMMB_STOKES_SPHERICAL_BEM = 6        /* kernel/StokesSphericalBEM.hpp: panels (bc 0 = VELOCITY, 1 = TRACTION), charge 3,
+                                          result 3; viscosity in fmmb_kernel_desc.kappa, quad_k and quad_kfine Gauss
+                                          rules (examples/StokesBEM.cpp:211-214) */
 } fmmb_kernel_kind;
 
 /* Mirrors the kernel constructor arguments: LaplaceSpherical(int p) etc. */
 typedef struct {
   int32_t kind;    /* fmmb_kernel_kind */
   int32_t p;       /* expansion order the kernel object was constructed with (1..FMMB_MAX_P) */
-  double kappa;    /* Yukawa screening parameter (unused for Laplace) */
-  int32_t quad_k;  /* BEM Gauss points per panel (unused for point kernels) */
-  int32_t reserved;
+  double kappa;    /* Yukawa screening parameter; StokesSphericalBEM: the viscosity Mu (unused for Laplace) */
+  int32_t quad_k;  /* BEM Gauss rule per panel: a key of the reference's table, 1, 3, 4, 7, 13, 17, 19, 25 or 79
+                      (examples/BEM/GaussQuadrature.hpp:41-276; unused for point kernels) */
+  int32_t quad_kfine; /* StokesSphericalBEM::set_Kfine: rule for panels closer than 2 sqrt(2 Area); 0 = the class
+                         default 25 (kernel/StokesSphericalBEM.hpp:136).  Other kinds: must be 0. */
 } fmmb_kernel_desc;
 
 #define FMMB_MAX_P 16 /* SolverOptions::max_p default, examples/BEM/SolverOptions.hpp:23 */
@@ -85,7 +90,15 @@ typedef struct {
                           near field of the traversal (reference include/executor/EvalLocal.hpp:12-72,
                           EvalLocalSparse.hpp); 2 = FMMOptions::block_diagonal, only leaf-with-itself blocks
                           (EvalDiagonalSparse.hpp:12-80).  LaplaceSpherical and the BEM kernel classes. */
+  int32_t kernel_flags; /* FMMB_FLAG_* bits, 0 = the reference's behaviour as compiled (occupies what was tail padding:
+                          size and offsets of the structure are unchanged) */
 } fmmb_options;
+
+/* FMMB_STOKES_SPHERICAL_BEM: evaluate the near-field entries as the reference's source text means them
+ * (self terms, fine rule for close panels) instead of as the unmodified reference computes them when compiled, where
+ * an expression template that outlives its operand makes every pair take the K-point rule
+ * (kernel/StokesSphericalBEM.hpp:162-163,262-263; fmm_bem_relaxed_b200/hostcxx/stokes_bem_math.hpp has the details). */
+#define FMMB_FLAG_STOKES_BEM_AS_WRITTEN 1
 
 /* Sources, host memory, borrowed for the duration of the call.
  *   points    3*n doubles, point-major (x0,y0,z0,x1,...): the positions the octree is built on.
@@ -94,7 +107,8 @@ typedef struct {
  *             (kernel/LaplaceSphericalBEM.hpp:99); NULL = computed from the vertices.
  *   vertices  BEM kernels only: 9*n doubles, (p0, p1, p2) per panel as passed to Panel(p0,p1,p2)
  *             (kernel/LaplaceSphericalBEM.hpp:61-97).
- *   bc        BEM kernels only: n entries, 0 = Panel::POTENTIAL, 1 = Panel::NORMAL_DERIV; NULL = all 0. */
+ *   bc        BEM kernels only: n entries, 0 = Panel::POTENTIAL (Stokes: VELOCITY), 1 = Panel::NORMAL_DERIV (Stokes:
+ *             TRACTION); NULL = all 0. */
 typedef struct {
   int64_t n;
   const double* points;
@@ -117,7 +131,7 @@ typedef struct {
   int64_t own_body_begin;  /* multi-GPU: tree-order body range whose results this rank computes */
   int64_t own_body_end;
   int32_t p;               /* current expansion order */
-  int32_t charge_dim;      /* doubles per charge (Laplace 1, Stokeslet 3, stresslet 6) */
+  int32_t charge_dim;      /* doubles per charge (Laplace 1, Stokeslet and StokesSphericalBEM 3, stresslet 6) */
   int32_t result_dim;      /* doubles per result (Laplace 4: potential, fx, fy, fz; BEM 1; Stokes 3) */
   int32_t device;
 } fmmb_plan_info;

@@ -142,7 +142,35 @@ def yukawa_bem_case(name, recursions, p, k, kappa, ncrit, bc):
         print(name, "treecode vs direct", meta["err_vs_direct"])
 
 
+def stokes_bem_case(name, exe, recursions, p, k, kfine, mu, ncrit, bc):
+    """StokesSphericalBEM through oracle/_ref/ref_stokes_bem_asis (the unmodified reference) or oracle/_ref/ref_stokes_bem
+    (the reference with the dangling `auto dist` of kernel/StokesSphericalBEM.hpp:162,262 materialised, oracle/Makefile):
+    FMM matvec with the sparse near field (examples/StokesBEM.cpp:126) and Direct::matvec, random Vec<3> charges."""
+    with tempfile.TemporaryDirectory() as tmp:
+        pre = os.path.join(tmp, "d")
+        cmd = [os.path.join(ROOT, "oracle", "_ref", exe), "-recursions", str(recursions), "-P", str(p), "-K", str(k),
+               "-kfine", str(kfine), "-mu", repr(mu), "-ncrit", str(ncrit), "-bc", str(bc), "-rand", "-direct", "-dump", pre]
+        out = subprocess.check_output(cmd, env=dict(os.environ, OMP_NUM_THREADS="1"), cwd=tmp).decode()
+        meta = json.loads([l for l in out.splitlines() if l.startswith("REF_JSON")][0][len("REF_JSON "):])
+        meta["as_written"] = 0 if exe.endswith("asis") else 1
+        np.savez_compressed(os.path.join(HERE, name + ".npz"), meta=json.dumps(meta),
+                            verts=np.fromfile(pre + ".verts.f64").reshape(-1, 3, 3),
+                            bc=np.fromfile(pre + ".bc.f64").astype(np.int32),
+                            charges=np.fromfile(pre + ".charges.f64").reshape(-1, 3),
+                            results=np.fromfile(pre + ".results.f64").reshape(-1, 3),
+                            direct=np.fromfile(pre + ".direct.f64").reshape(-1, 3))
+        print(name, "FMM vs direct", meta["err_vs_direct"])
+
+
 def main():
+    if "--stokes-bem" in sys.argv:
+        # StokesSphericalBEM: VELOCITY (the solve), TRACTION (the right-hand side) and mixed panels, as compiled and
+        # as written; 2 048 panels with ncrit 40 so that the far field is exercised (theta 0.5)
+        for bc in (0, 1, 2):
+            stokes_bem_case("stokes_bem_asis_2048_p6_bc%d" % bc, "ref_stokes_bem_asis", 5, 6, 4, 19, 1e-3, 40, bc)
+            stokes_bem_case("stokes_bem_2048_p6_bc%d" % bc, "ref_stokes_bem", 5, 6, 4, 19, 1e-3, 40, bc)
+        stokes_bem_case("stokes_bem_2048_p8_k3_kf25", "ref_stokes_bem", 5, 8, 3, 25, 0.7, 30, 2)
+        return
     if not os.path.exists(REF):
         sys.exit("oracle/_ref/ref_laplace missing: run `make -C oracle ref` in the build container")
     # 1. the reference's own test input (drand48 points then charges), small

@@ -58,6 +58,12 @@ def load():
         L.fmmo_panel_centers.argtypes = [ctypes.c_int, vp, vp]
         L.fmmo_bem_execute.argtypes = [vp, ctypes.c_int, ctypes.c_int, vp, vp, vp, vp, ctypes.c_int]
         L.fmmo_bem_direct.argtypes = [ctypes.c_int, ctypes.c_int, vp, vp, vp, vp, ctypes.c_int]
+        L.fmmo_stokes_bem_execute.argtypes = [vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_double, ctypes.c_int,
+                                              vp, vp, vp, vp, ctypes.c_int]
+        L.fmmo_stokes_bem_direct.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_double, ctypes.c_int,
+                                             vp, vp, vp, vp, ctypes.c_int]
+        L.fmmo_stokes_bem_entries.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_double, ctypes.c_int,
+                                              vp, vp, ctypes.c_int, vp, vp, vp]
         _lib = L
     return _lib
 
@@ -213,6 +219,44 @@ class YukawaBemOracle(BemOracle):
         out = np.zeros(self.n)
         self.L.fmmo_yukawa_bem_direct(self.n, K, self.kappa, _p(self.verts), _p(self.bc), _p(q), _p(out),
                                       threads or os.cpu_count() or 1)
+        return out
+
+
+class StokesBemOracle(BemOracle):
+    """Oracle tree on the panel centres + the restated StokesSphericalBEM matvec.  as_written: False = the entries the
+    unmodified reference computes when compiled (K-point rule for every pair), True = the branches of its source text
+    (self terms, fine rule); see oracle/fmm_oracle.cpp."""
+
+    def __init__(self, verts, bc, mu=1e-3, K=4, kfine=19, as_written=False, ncrit=64, theta=0.5):
+        super().__init__(verts, bc, ncrit, theta)
+        self.mu, self.K, self.kfine, self.as_written = float(mu), int(K), int(kfine), int(bool(as_written))
+
+    def execute(self, charges, P, threads=None):
+        q = np.ascontiguousarray(np.asarray(charges, dtype=np.float64).reshape(-1))
+        res = np.zeros((self.n, 3))
+        rc = self.L.fmmo_stokes_bem_execute(self.h, P, self.K, self.kfine, self.mu, self.as_written, _p(self.verts),
+                                            _p(self.bc), _p(q), _p(res), threads or os.cpu_count() or 1)
+        if rc != 0:
+            raise RuntimeError("oracle Stokes BEM execute failed: %d" % rc)
+        return res
+
+    def direct(self, charges, threads=None):
+        q = np.ascontiguousarray(np.asarray(charges, dtype=np.float64).reshape(-1))
+        out = np.zeros((self.n, 3))
+        rc = self.L.fmmo_stokes_bem_direct(self.n, self.K, self.kfine, self.mu, self.as_written, _p(self.verts),
+                                           _p(self.bc), _p(q), _p(out), threads or os.cpu_count() or 1)
+        if rc != 0:
+            raise RuntimeError("oracle Stokes BEM direct failed: %d" % rc)
+        return out
+
+    def entries(self, ti, si):
+        ti = np.ascontiguousarray(ti, np.int32)
+        si = np.ascontiguousarray(si, np.int32)
+        out = np.zeros((len(ti), 3, 3))
+        rc = self.L.fmmo_stokes_bem_entries(self.n, self.K, self.kfine, self.mu, self.as_written, _p(self.verts),
+                                            _p(self.bc), len(ti), _p(ti), _p(si), _p(out))
+        if rc != 0:
+            raise RuntimeError("oracle Stokes BEM entries failed: %d" % rc)
         return out
 
 
