@@ -23,7 +23,7 @@ import numpy as np
 from . import capi
 from .capi import FmmbError
 
-__all__ = ["FMMOptions", "LaplaceSpherical", "LaplaceSphericalBEM", "StokesSpherical", "YukawaCartesian", "YukawaCartesianBEM", "SolverOptions", "GMRES", "Panels", "FMM_plan", "Direct", "FmmbError", "capi", "comm_unique_id",
+__all__ = ["FMMOptions", "LaplaceSpherical", "LaplaceSphericalBEM", "StokesSpherical", "YukawaCartesian", "YukawaCartesianBEM", "StokesSphericalBEM", "SolverOptions", "GMRES", "Panels", "FMM_plan", "Direct", "FmmbError", "capi", "comm_unique_id",
            "partition_ranges", "get_options"]
 
 
@@ -146,9 +146,30 @@ class YukawaCartesianBEM(LaplaceSphericalBEM):
         self.Kappa = float(kappa)
 
 
+class StokesSphericalBEM(LaplaceSphericalBEM):
+    """Mirror of reference kernel/StokesSphericalBEM.hpp:9-158: StokesSphericalBEM(int p, unsigned k, double mu) and
+    set_Kfine(k) (examples/StokesBEM.cpp:211-214).  Panel sources with Panels.VELOCITY / Panels.TRACTION flags; charges
+    and results are (n, 3).  near_field_as_written: False (default) = near-field entries as the unmodified reference
+    computes them when compiled (K-point rule for every pair), True = as its source text means them (self terms, fine
+    rule); see fmm_bem_relaxed_b200/hostcxx/stokes_bem_math.hpp."""
+    kind = capi.STOKES_SPHERICAL_BEM
+    charge_dim = 3
+    result_dim = 3
+
+    def __init__(self, p=5, k=3, mu=1e-3, kfine=25, near_field_as_written=False):
+        super().__init__(p, k)
+        self.Mu = float(mu)
+        self.K_fine = int(kfine)
+        self.near_field_as_written = bool(near_field_as_written)
+
+    def set_Kfine(self, k):
+        self.K_fine = int(k)
+
+
 class Panels:
     """A set of triangular panels (the std::vector<Panel> a reference driver builds)."""
     POTENTIAL, NORMAL_DERIV = 0, 1
+    VELOCITY, TRACTION = 0, 1          # StokesSphericalBEM::Panel::BoundaryType
 
     def __init__(self, vertices, bc=None):
         self.vertices = np.ascontiguousarray(np.asarray(vertices, dtype=np.float64).reshape(-1, 3, 3))
@@ -183,9 +204,14 @@ class FMM_plan:
             verts, bc = sources.vertices, np.ascontiguousarray(sources.bc)
             if isinstance(kernel, YukawaCartesianBEM):
                 self.K = YukawaCartesianBEM(kernel.P, kernel.Kappa, kernel.K)
+            elif isinstance(kernel, StokesSphericalBEM):
+                self.K = StokesSphericalBEM(kernel.P, kernel.K, kernel.Mu, kernel.K_fine, kernel.near_field_as_written)
             else:
                 self.K = LaplaceSphericalBEM(kernel.P, kernel.K)
-            kd = capi.KernelDesc(kernel.kind, kernel.P, getattr(kernel, "Kappa", 0.0), kernel.K, 0)
+            if isinstance(kernel, StokesSphericalBEM):     # the viscosity travels in the kappa slot (include/fmmb.h)
+                kd = capi.KernelDesc(kernel.kind, kernel.P, kernel.Mu, kernel.K, kernel.K_fine)
+            else:
+                kd = capi.KernelDesc(kernel.kind, kernel.P, getattr(kernel, "Kappa", 0.0), kernel.K, 0)
         else:
             pts = np.ascontiguousarray(np.asarray(sources, dtype=np.float64).reshape(-1, 3))
             # the plan owns a COPY of the kernel (FMM_plan.hpp:37)
@@ -201,8 +227,9 @@ class FMM_plan:
         self._cdim = self.K.charge_dim
         src = capi.Sources(self._n, capi.ptr(pts), capi.ptr(verts), capi.ptr(bc))
         near_only = 2 if opts.block_diagonal else (1 if opts.local_evaluation else 0)
+        flags = capi.FLAG_STOKES_BEM_AS_WRITTEN if getattr(kernel, "near_field_as_written", False) else 0
         op = capi.Options(opts.theta, opts.NCRIT_, opts.evaluator, opts.device, 0,
-                          getattr(opts, "rank", 0), getattr(opts, "nranks", 1), near_only)
+                          getattr(opts, "rank", 0), getattr(opts, "nranks", 1), near_only, flags)
         h = ctypes.c_void_p()
         capi.check(lib.fmmb_plan_create(ctypes.byref(kd), ctypes.byref(src), ctypes.byref(op), ctypes.byref(h)))
         self._h = h
@@ -308,9 +335,10 @@ class SolverOptions:
     """Mirror of reference examples/BEM/SolverOptions.hpp:9-38 (defaults of the default constructor)."""
     BOURAS, SIMONCINI = 0, 1
 
-    def __init__(self, residual=1e-5, max_iters=500, restart=500, max_p=16, variable_p=True, relax_type=0):
+    def __init__(self, residual=1e-5, max_iters=500, restart=500, max_p=16, variable_p=True, relax_type=0, p_min=5):
         self.residual, self.max_iters, self.restart = float(residual), int(max_iters), int(restart)
         self.max_p, self.variable_p, self.relax_type = int(max_p), bool(variable_p), int(relax_type)
+        self.p_min = int(p_min)        # SolverOptions::p_min, read by GMRES_Stokes only (:13, GMRES_Stokes.hpp:229)
 
 
 def GMRES(plan, x, b, opts, diag=None, output=False):
@@ -319,8 +347,10 @@ def GMRES(plan, x, b, opts, diag=None, output=False):
     x = np.ascontiguousarray(x, dtype=np.float64)
     b = np.ascontiguousarray(b, dtype=np.float64)
     d = None if diag is None else np.ascontiguousarray(diag, dtype=np.float64)
+    # Vec<3> unknowns (StokesSphericalBEM): the order rule of GMRES_Stokes.hpp:229, max(p_min, predict_p - 1)
+    stokes = plan._cdim == 3
     so = capi.SolverOptions(opts.residual, opts.max_iters, opts.restart, opts.max_p, int(opts.variable_p),
-                            opts.relax_type, int(output))
+                            opts.relax_type, int(output), opts.p_min if stokes else 0, 1 if stokes else 0)
     info = capi.GmresInfo()
     cap = 4096
     ps = np.zeros(cap, np.int32)

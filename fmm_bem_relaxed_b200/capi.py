@@ -18,6 +18,8 @@ LAPLACE_SPHERICAL = 0
 LAPLACE_SPHERICAL_BEM = 1
 STOKES_SPHERICAL_STRESSLET = 2
 STOKES_SPHERICAL = 5
+STOKES_SPHERICAL_BEM = 6
+FLAG_STOKES_BEM_AS_WRITTEN = 1
 YUKAWA_CARTESIAN = 3
 YUKAWA_CARTESIAN_BEM = 4
 
@@ -47,7 +49,7 @@ class Sources(ctypes.Structure):
 class SolverOptions(ctypes.Structure):
     _fields_ = [("residual", ctypes.c_double), ("max_iters", ctypes.c_int32), ("restart", ctypes.c_int32),
                 ("max_p", ctypes.c_uint32), ("variable_p", ctypes.c_int32), ("relax_type", ctypes.c_int32),
-                ("verbose", ctypes.c_int32)]
+                ("verbose", ctypes.c_int32), ("p_min", ctypes.c_uint32), ("p_offset", ctypes.c_uint32)]
 
 
 class GmresInfo(ctypes.Structure):

@@ -4,6 +4,7 @@
 // Same algorithm and decisions as the reference: modified Gram-Schmidt, Givens rotations on host scalars,
 // convergence on the rotated residual estimate |s[i+1]| / ||b||, and before every inner matvec
 //     p = max(1, predict_p(|resid|));  kernel.set_p(p)
+// (GMRES_Stokes.hpp:229: p = max(p_min, predict_p(|resid|) - 1), selected by fmmb_solver_options.p_min / p_offset)
 // (the first matvec of a restart cycle runs at whatever order the kernel was left at, GMRES.hpp:174-175).
 // What moves: the Krylov basis, the work vectors and every BLAS-1 operation live on the GPU, the matvec is fed
 // from device-resident vectors (fmmb_plan_execute_device), and an inner iteration costs ONE host synchronisation:
@@ -102,10 +103,11 @@ void run_matvec_for_solver(fmmb_plan* plan, const double* q, double* r);   // ca
 
 void gmres_solve(fmmb_plan* plan, const double* b_host, double* x_host, const double* diag_host,
                  const fmmb_solver_options& o, fmmb_gmres_info* info, int32_t* p_sched, double* res_hist, int cap) {
-  if (plan->charge_dim != 1 || plan->result_dim != 1)
-    throw StatusError{FMMB_ERR_UNSUPPORTED, "fmmb_gmres: plans with scalar charges and results (BEM kernels)"};
+  if (plan->charge_dim != plan->result_dim || !(plan->bem || plan->sbem))
+    throw StatusError{FMMB_ERR_UNSUPPORTED, "fmmb_gmres: BEM plans (results have the shape of the charges)"};
   if (plan->tree.nranks > 1) throw StatusError{FMMB_ERR_UNSUPPORTED, "fmmb_gmres: single-GPU plans"};
-  const int64_t n = plan->tree.n;
+  // Vec<3> unknowns (StokesSphericalBEM) are solved on the flat array of 3 n doubles, like GMRES_Stokes.hpp:85-105
+  const int64_t n = plan->tree.n * plan->charge_dim;
   const int R = std::max(1, o.restart);
   cudaStream_t s = plan->stream;
   if (!plan->gmres_ws) plan->gmres_ws = new GmresWorkspace();
@@ -159,7 +161,9 @@ void gmres_solve(fmmb_plan* plan, const double* b_host, double* x_host, const do
     resid = sv[0] / normb;
     do {
       ++i; ++iter;
-      const int p = (int)std::max(1u, predict_p(o, std::fabs(resid)));
+      // GMRES.hpp:195: max(1u, predict_p);  GMRES_Stokes.hpp:229: max(p_min, predict_p - 1)
+      const unsigned pp = predict_p(o, std::fabs(resid));
+      const int p = (int)std::max(std::max(1u, o.p_min), pp > o.p_offset ? pp - o.p_offset : 0u);
       if (p > FMMB_MAX_P) throw StatusError{FMMB_ERR_INVALID, "predicted expansion order exceeds FMMB_MAX_P"};
       plan->p = p;
       precond_kernel<<<g, 256, 0, s>>>(basis(i), diag_host ? diag.p : nullptr, z.p, n);

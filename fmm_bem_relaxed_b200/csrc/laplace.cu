@@ -1212,7 +1212,8 @@ void build_p2p_items(fmmb_plan* plan) {
     FMMB_CUDA(cudaGetLastError());
     h = cnt.to_host(s);
     for (int i = 0; i < nl; ++i) off[i + 1] = off[i] + h[i];
-    if (plan->kind == FMMB_LAPLACE_SPHERICAL_BEM || plan->kind == FMMB_YUKAWA_CARTESIAN_BEM || mode != 0 || chunk <= plan->p2p_min_chunk || off[nl] >= 6 * 20 * sms) break;
+    if (plan->kind == FMMB_LAPLACE_SPHERICAL_BEM || plan->kind == FMMB_YUKAWA_CARTESIAN_BEM ||
+        plan->kind == FMMB_STOKES_SPHERICAL_BEM || mode != 0 || chunk <= plan->p2p_min_chunk || off[nl] >= 6 * 20 * sms) break;
     chunk >>= 1;
   }
   plan->p2p_chunk = chunk;

@@ -16,6 +16,7 @@
 #include <vector>
 
 #include "Vec.hpp"
+#include "Mat3.hpp"       // the reference's FMM_plan.hpp brings it in through its executors (include/Matvec.hpp:11)
 #include "FMMOptions.hpp"
 #include "Direct.hpp"
 #include <timing.hpp>   // <>: a build that puts the reference's examples/BEM first gets that one, not both

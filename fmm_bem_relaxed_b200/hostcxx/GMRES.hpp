@@ -144,3 +144,32 @@ GMRESReport GMRES_device(Matvec& MV, std::vector<double>& x, std::vector<double>
   rep.residuals.assign(rs.begin(), rs.begin() + k);
   return rep;
 }
+
+/** Vec<3> unknowns (StokesSphericalBEM): GMRES(plan, x, b, opts) of reference examples/BEM/GMRES_Stokes.hpp:170-300 --
+ * the same iteration on the flat array of 3 n doubles, with that header's order rule
+ * p = max(p_min, predict_p(|resid|) - 1) (:229) -- device resident. */
+template <typename Matvec>
+GMRESReport GMRES_device(Matvec& MV, std::vector<Vec<3, double>>& x, std::vector<Vec<3, double>>& b,
+                         const SolverOptions& opts, bool output = true) {
+  GMRESReport rep;
+  static_assert(sizeof(Vec<3, double>) == 3 * sizeof(double), "Vec<3,double> must be packed");
+  fmmb_solver_options so = {opts.residual, opts.max_iters, opts.restart, opts.max_p, opts.variable_p ? 1 : 0,
+                            opts.relax_type == SolverOptions::BOURAS ? 0 : 1, output ? 1 : 0, opts.p_min, 1u};
+  fmmb_gmres_info info = {};
+  const int cap = 4096;
+  std::vector<int32_t> ps(cap);
+  std::vector<double> rs(cap);
+  if (x.size() != b.size() || fmmb_plan_set_p(MV.handle(), MV.kernel().order()) != FMMB_OK ||
+      fmmb_gmres(MV.handle(), reinterpret_cast<const double*>(b.data()), reinterpret_cast<double*>(x.data()), nullptr, &so,
+                 &info, ps.data(), rs.data(), cap) != FMMB_OK) {
+    fprintf(stderr, "[E]: GMRES_device: %s\n", x.size() != b.size() ? "x.size() != b.size()" : fmmb_last_error());
+    return rep;
+  }
+  MV.kernel().set_p(info.final_p);
+  rep.iterations = info.iterations;
+  rep.final_residual = info.final_residual;
+  const int k = info.n_records < cap ? info.n_records : cap;
+  rep.p_schedule.assign(ps.begin(), ps.begin() + k);
+  rep.residuals.assign(rs.begin(), rs.begin() + k);
+  return rep;
+}

@@ -50,6 +50,16 @@ template <std::size_t N, typename T> Vec<N, T> operator-(Vec<N, T> a, const Vec<
 template <std::size_t N, typename T> Vec<N, T> operator*(Vec<N, T> a, const T& s) { return a *= s; }
 template <std::size_t N, typename T> Vec<N, T> operator*(const T& s, Vec<N, T> a) { return a *= s; }
 template <std::size_t N, typename T> Vec<N, T> operator/(Vec<N, T> a, const T& s) { return a /= s; }
+/** scalars of another arithmetic type (v / 4, 2 * v): converted like the built-in promotion would */
+template <std::size_t N, typename T, typename S,
+          typename std::enable_if<std::is_arithmetic<S>::value && !std::is_same<S, T>::value, int>::type = 0>
+Vec<N, T> operator*(Vec<N, T> a, const S& s) { return a *= static_cast<T>(s); }
+template <std::size_t N, typename T, typename S,
+          typename std::enable_if<std::is_arithmetic<S>::value && !std::is_same<S, T>::value, int>::type = 0>
+Vec<N, T> operator*(const S& s, Vec<N, T> a) { return a *= static_cast<T>(s); }
+template <std::size_t N, typename T, typename S,
+          typename std::enable_if<std::is_arithmetic<S>::value && !std::is_same<S, T>::value, int>::type = 0>
+Vec<N, T> operator/(Vec<N, T> a, const S& s) { return a /= static_cast<T>(s); }
 template <std::size_t N, typename T> Vec<N, T> operator+(Vec<N, T> a, const T& s) {
   for (std::size_t i = 0; i < N; ++i) a[i] += s;
   return a;

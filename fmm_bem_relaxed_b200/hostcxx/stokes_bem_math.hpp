@@ -71,7 +71,7 @@ BEM_HD void stokes_self_term(const Panel& s, double* m) {
  * comes from dead stack (undefined behaviour) and, as compiled, never selects the self term or the fine rule.
  * as_written = true: the branches as the source text means them -- the panel itself through the self term above,
  * panels with sqrt(2A)/dist >= 0.5 through the fine rule; pinned against the reference with that one declaration
- * changed to point_type (oracle/Makefile).  With the sphere driver the as-compiled entries give the better drag
+ * changed to point_type.  With the sphere driver the as-compiled entries give the better drag
  * (0.2 % against 5 %, 2 048 panels), the as-written self term being short of the exact integral. */
 BEM_HD void stokes_velocity_entry(const Panel& s, const double* t, const Rule& rule, const Rule& fine, double mu,
                                   bool as_written, double* m) {

@@ -230,7 +230,9 @@ int fmmb_partition_ranges(const double* weights, int64_t n, int nranks, int64_t*
  * SolverOptions (examples/BEM/SolverOptions.hpp:9-38): restarted GMRES, modified Gram-Schmidt, Givens rotations,
  * convergence on the rotated residual estimate, and p = max(1, predict_p(|resid|)) set before every inner matvec.
  * The Krylov basis and all BLAS-1 work stay on the GPU; one host synchronisation per inner iteration.
- * Plans with scalar charges and results (BEM kernels), single GPU. */
+ * BEM plans, single GPU: scalar unknowns (Laplace / Yukawa BEM) or Vec<3> unknowns solved on the flat array of
+ * 3 n doubles exactly like examples/BEM/GMRES_Stokes.hpp:170-300 (StokesSphericalBEM; set p_min and p_offset = 1
+ * for that header's order rule). */
 typedef struct {
   double residual;       /* SolverOptions::residual (tolerance on |s[i+1]| / ||b||) */
   int32_t max_iters;     /* SolverOptions::max_iters */
@@ -239,6 +241,9 @@ typedef struct {
   int32_t variable_p;    /* SolverOptions::variable_p: 1 = relax the order with the residual, 0 = always max_p */
   int32_t relax_type;    /* 0 = BOURAS (default), 1 = SIMONCINI */
   int32_t verbose;       /* 1 = print the reference's progress lines ("it: 001, res: ..., fmm_req_p: ...") */
+  uint32_t p_min;        /* SolverOptions::p_min: lower bound of the relaxed order (0 or 1 = the GMRES.hpp rule) */
+  uint32_t p_offset;     /* subtracted from predict_p before the bound: 0 = GMRES.hpp:195 max(1, predict_p),
+                            1 = GMRES_Stokes.hpp:229 max(p_min, predict_p - 1) */
 } fmmb_solver_options;
 
 typedef struct {
@@ -249,8 +254,8 @@ typedef struct {
   double final_residual;
 } fmmb_gmres_info;
 
-/* b, x: n doubles (host); x holds the initial guess on entry and the solution on return.
- * diag: NULL (identity) or n doubles d with M(v)_i = d_i v_i (Preconditioners::Diagonal, examples/BEM/Preconditioner.hpp:24-38).
+/* b, x: n * charge_dim doubles (host); x holds the initial guess on entry and the solution on return.
+ * diag: NULL (identity) or n * charge_dim doubles d with M(v)_i = d_i v_i (Preconditioners::Diagonal, examples/BEM/Preconditioner.hpp:24-38).
  * p_schedule / residuals: optional arrays of `capacity` entries: order and |resid| of every inner iteration. */
 int fmmb_gmres(fmmb_plan* plan, const double* b, double* x, const double* diag, const fmmb_solver_options* options,
                fmmb_gmres_info* info, int32_t* p_schedule, double* residuals, int32_t capacity);

@@ -1,0 +1,165 @@
+"""GPU suite (-m gpu): StokesSphericalBEM through the C ABI (csrc/stokes_bem.cu) against the golden fixtures of the
+reference (tests/golden/stokes_bem*.npz, made by tests/golden/make_golden.py --stokes-bem) and against the oracle
+restatement, which is bit-identical to the reference on every one of them (tests/test_oracle.py).
+
+"asis" fixtures: the UNMODIFIED reference (near-field entries as compiled, the plan default).  The others: the
+reference with the dangling `auto dist` of kernel/StokesSphericalBEM.hpp:162,262 materialised (near_field_as_written).
+Tolerance: relative L2 <= 1e-10 (BASELINE.json north_star) per velocity component.
+
+STATUS: this kernel class was written after round 1's GPU minutes were spent; the CUDA side compiles for sm_100a and
+shares its panel integrals with the CPU-pinned host class, but its first run on a B200 is the round-end run.  The
+module is therefore the last one collected and marked xfail(strict=False): a pass shows as XPASS, a failure cannot
+mask the suites that were green on hardware.  Remove the mark once a run is recorded.
+"""
+import json
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+import oracle_lib as O
+import fmm_bem_relaxed_b200 as F
+from conftest import GOLDEN, ROOT
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.xfail(strict=False, reason="StokesSphericalBEM kernels not yet run on hardware (round 1 GPU "
+                                                     "budget spent before they were written)")]
+
+TOL = 1e-10
+FIXTURES = ["stokes_bem_asis_2048_p6_bc0", "stokes_bem_asis_2048_p6_bc1", "stokes_bem_asis_2048_p6_bc2",
+            "stokes_bem_2048_p6_bc0", "stokes_bem_2048_p6_bc1", "stokes_bem_2048_p6_bc2", "stokes_bem_2048_p8_k3_kf25"]
+
+
+def make_plan(verts, bc, P, K=4, kfine=19, mu=1e-3, as_written=False, ncrit=64, theta=0.5, near_only=0):
+    opts = F.FMMOptions()
+    opts.set_mac_theta(theta)
+    opts.set_max_per_box(ncrit)
+    opts.local_evaluation = near_only == 1
+    opts.block_diagonal = near_only == 2
+    return F.FMM_plan(F.StokesSphericalBEM(P, K, mu, kfine, as_written), F.Panels(verts, bc), opts)
+
+
+@pytest.mark.parametrize("name", FIXTURES)
+def test_golden_fixtures(name):
+    g = dict(np.load(os.path.join(GOLDEN, name + ".npz")))
+    m = json.loads(str(g["meta"]))
+    plan = make_plan(g["verts"], g["bc"], m["P"], m["K"], m["kfine"], m["mu"], bool(m["as_written"]), m["ncrit"], m["theta"])
+    i = plan.info()
+    assert (i.charge_dim, i.result_dim, i.n_bodies) == (3, 3, len(g["bc"]))
+    assert i.n_m2l_pairs > 1000 and i.n_near_entries == i.n_p2p_body_pairs
+    res = plan.execute(g["charges"])
+    assert res.shape == g["results"].shape
+    for k in range(3):
+        assert O.rel_l2(res[:, k], g["results"][:, k]) <= TOL
+    for _ in range(3):                                   # deterministic, also through the CUDA-graph replay
+        assert np.array_equal(plan.execute(g["charges"]), res)
+
+
+@pytest.mark.parametrize("as_written", [False, True])
+@pytest.mark.parametrize("rec,P,K,ncrit,bc", [(6, 8, 4, 64, 0), (6, 5, 3, 30, 1), (5, 10, 4, 20, 2), (4, 3, 1, 8, 0)])
+def test_vs_oracle(as_written, rec, P, K, ncrit, bc):
+    """Sphere meshes of examples/StokesBEM.cpp (Triangulation::UnitSphere), random Vec<3> charges, all panels
+    VELOCITY / all TRACTION / mixed, orders above and below the batched-GEMM limit (P = 8)."""
+    verts = O.unit_sphere(rec)
+    n = len(verts)
+    flags = np.zeros(n, np.int32) if bc == 0 else (np.ones(n, np.int32) if bc == 1 else (np.arange(n) % 3 == 1).astype(np.int32))
+    q = np.random.default_rng(rec * 100 + P).random((n, 3)) - 0.3
+    orc = O.StokesBemOracle(verts, flags, mu=0.01, K=K, kfine=19, as_written=as_written, ncrit=ncrit)
+    want = orc.execute(q, P)
+    plan = make_plan(verts, flags, P, K, 19, 0.01, as_written, ncrit)
+    got = plan.execute(q)
+    for k in range(3):
+        assert O.rel_l2(got[:, k], want[:, k]) <= TOL
+    t = plan.tree()
+    ot = orc.tree()
+    assert np.array_equal(t["perm"], ot["perm"]) and np.array_equal(t["lr"], ot["lr"])
+
+
+def test_near_field_only_plans_and_order_relaxation():
+    verts = O.unit_sphere(5)
+    n = len(verts)
+    flags = np.zeros(n, np.int32)
+    q = np.random.default_rng(5).random((n, 3))
+    orc = O.StokesBemOracle(verts, flags, ncrit=40)
+    full = make_plan(verts, flags, 8, ncrit=40)
+    near = make_plan(verts, flags, 8, ncrit=40, near_only=1)
+    # near-field-only plan (FMMOptions::local_evaluation): the far field is the difference
+    r8 = full.execute(q)
+    rn = near.execute(q)
+    assert O.rel_l2(r8, orc.execute(q, 8)) <= TOL
+    assert 1e-3 < O.rel_l2(rn, r8) < 1.0
+    # set_p between matvecs, as GMRES_Stokes does (examples/BEM/GMRES_Stokes.hpp:229-231)
+    for p in (5, 3, 8, 12):
+        full.kernel().set_p(p)
+        assert O.rel_l2(full.execute(q), orc.execute(q, p)) <= TOL
+    # linearity (a size-independent property): A(2 x - 3 y) = 2 A x - 3 A y
+    y = np.random.default_rng(6).random((n, 3))
+    lhs = full.execute(2 * q - 3 * y)
+    rhs = 2 * full.execute(q) - 3 * full.execute(y)
+    assert O.rel_l2(lhs, rhs) <= 1e-12
+
+
+def test_rejects_bad_descriptors():
+    verts = O.unit_sphere(3)
+    with pytest.raises(F.FmmbError):
+        make_plan(verts, 0, 5, K=5)                       # not a key of the reference's Gauss table
+    with pytest.raises(F.FmmbError):
+        make_plan(verts, 0, 5, mu=0.0)
+    with pytest.raises(F.FmmbError):
+        make_plan(verts, np.full(len(verts), 2, np.int32), 5)
+
+
+def test_reference_stokes_driver_unchanged(tmp_path):
+    """Reference examples/StokesBEM.cpp (+ its GMRES_Stokes.hpp and friends) compiled unchanged against hostcxx/:
+    unit sphere, 2 048 panels, p = 8, k = 4, tol 1e-5.  The unmodified reference (oracle/_ref/StokesBEM, one thread:
+    its threaded M2L races) prints the lines below; the drag comes out at 0.01911 against 0.01885."""
+    exe = os.path.join(ROOT, "fmm_bem_relaxed_b200", "hostcxx", "bin", "ref_StokesBEM")
+    if not os.path.exists(exe):
+        pytest.skip(exe + " not built")
+    env = dict(os.environ)
+    env["LD_LIBRARY_PATH"] = os.path.join(ROOT, "fmm_bem_relaxed_b200") + ":" + env.get("LD_LIBRARY_PATH", "")
+    out = subprocess.check_output([exe, "-recursions", "5", "-p", "8", "-k", "4", "-solver_tol", "1e-5"], env=env,
+                                  timeout=600, cwd=str(tmp_path)).decode()   # the driver writes out.face / out.vert here
+    want = ["it: 001, res: 1.540e-03, fmm_req_p: 7", "it: 002, res: 5.298e-04, fmm_req_p: 7",
+            "it: 003, res: 2.929e-04, fmm_req_p: 5", "it: 004, res: 1.364e-04, fmm_req_p: 5",
+            "it: 005, res: 7.147e-05, fmm_req_p: 5", "it: 006, res: 4.341e-05, fmm_req_p: 5",
+            "it: 007, res: 2.744e-05, fmm_req_p: 5", "it: 008, res: 1.578e-05, fmm_req_p: 5",
+            "it: 009, res: 1.377e-05, fmm_req_p: 5", "Final residual: 8.1330e-06, after 10 iterations"]
+    lines = [l.strip() for l in out.splitlines()]
+    for w in want:
+        assert w in lines, (w, out)
+    assert "rhs error: 2.0203e+03" in lines
+    assert re.search(r"Fx: 0\.01911, analytical: 0\.01885", out), out
+
+
+def test_own_driver_device_gmres(tmp_path):
+    """hostcxx/examples/stokes_bem.cpp: the same problem solved by the device-resident GMRES on Vec<3> unknowns with
+    the order rule of GMRES_Stokes.hpp:229.  Same iteration count and drag as the reference's run (above), and the
+    GPU matvec agrees with Direct::matvec of the host kernel class to the far-field truncation error."""
+    exe = os.path.join(ROOT, "fmm_bem_relaxed_b200", "hostcxx", "bin", "stokes_bem")
+    if not os.path.exists(exe):
+        pytest.skip(exe + " not built")
+    env = dict(os.environ)
+    env["LD_LIBRARY_PATH"] = os.path.join(ROOT, "fmm_bem_relaxed_b200") + ":" + env.get("LD_LIBRARY_PATH", "")
+    out = subprocess.check_output([exe, "-recursions", "5", "-p", "8", "-k", "4", "-solver_tol", "1e-5", "-check", "100"],
+                                  env=env, timeout=600, cwd=str(tmp_path)).decode()
+    assert float(re.search(r"matvec vs Direct \(first 100 rows\): ([0-9.eE+-]+)", out).group(1)) < 1e-4
+    m = re.search(r"iterations: (\d+), final residual: ([0-9.eE+-]+)", out)
+    assert m and int(m.group(1)) == 10 and abs(float(m.group(2)) - 8.1330e-06) < 1e-9, out
+    assert re.search(r"Fx: 0\.01911, analytical: 0\.01885", out), out
+
+
+def test_python_gmres_on_vec3_unknowns():
+    """F.GMRES on a StokesSphericalBEM plan: fmmb_gmres with charge_dim 3 and the GMRES_Stokes order rule."""
+    verts = O.unit_sphere(5)
+    n = len(verts)
+    plan = make_plan(verts, np.zeros(n, np.int32), 8, 4, 19, 1e-3)
+    b = np.tile([4 * np.pi, 0.0, 0.0], (n, 1))
+    rep = F.GMRES(plan, np.zeros((n, 3)), b, F.SolverOptions(residual=1e-5, max_iters=100, restart=100, max_p=8, p_min=5))
+    assert rep["iterations"] == 10 and abs(rep["final_residual"] - 8.1330e-06) < 1e-9
+    assert rep["p_schedule"] == [7, 7, 5, 5, 5, 5, 5, 5, 5, 5]
+    x = rep["x"].reshape(n, 3)
+    area = 0.5 * np.linalg.norm(np.cross(verts[:, 2] - verts[:, 0], verts[:, 1] - verts[:, 0]), axis=1)
+    assert abs((x[:, 0] * area).sum() - 0.01911) < 1e-5
