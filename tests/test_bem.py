@@ -75,6 +75,21 @@ def run_bin(exe, *args):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("name", ["laplace_bem_2048_p6_k4_bc0", "laplace_bem_2048_p6_k4_bc1"])
+def test_golden_fixtures_of_the_reference(name):
+    """FMM matvec of the unmodified reference class (oracle/_ref/ref_bem, tests/golden/make_golden.py --laplace-bem)."""
+    import json
+    from conftest import GOLDEN
+    g = dict(np.load(os.path.join(GOLDEN, name + ".npz")))
+    m = json.loads(str(g["meta"]))
+    opts = F.FMMOptions()
+    opts.set_max_per_box(m["ncrit"])
+    opts.set_mac_theta(m["theta"])
+    plan = F.FMM_plan(F.LaplaceSphericalBEM(m["P"], m["K"]), F.Panels(g["verts"], m["bc"]), opts)
+    assert O.rel_l2(plan.execute(g["charges"]), g["results"]) <= 1e-10
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("rec,P,K", [(4, 8, 4), (5, 8, 4), (5, 5, 3), (6, 6, 1), (7, 8, 4)])
 def test_bem_matvec_vs_oracle(rec, P, K):
     v = O.unit_sphere(rec)

@@ -256,3 +256,19 @@ def test_stokes_bem_self_terms_and_modes():
         assert np.allclose(blk, np.swapaxes(blk, 1, 2))
         assert (np.linalg.eigvalsh(blk) > 0).all()
     assert np.abs(written[~trac] / compiled[~trac] - 1)[:, [0, 1, 2], [0, 1, 2]].min() > 0.05
+
+
+# ---- LaplaceSphericalBEM (BASELINE config 2's kernel class): FMM matvec with the sparse near field and Direct::matvec
+# ---- of the unmodified reference (oracle/_ref/ref_bem), bit for bit, for the 4-point rule and the higher rules of
+# ---- the reference's table ----------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["laplace_bem_2048_p6_k4_bc0", "laplace_bem_2048_p6_k4_bc1", "laplace_bem_2048_p6_k13_bc0",
+                                  "laplace_bem_2048_p6_k13_bc1", "laplace_bem_2048_p8_k25_bc0"])
+def test_laplace_bem_restatement_matches_reference_bitwise(name):
+    g = dict(np.load(os.path.join(GOLDEN, name + ".npz")))
+    m = _meta(g)
+    orc = O.BemOracle(g["verts"], m["bc"], ncrit=m["ncrit"], theta=m["theta"])
+    assert len(orc.tree()["lr"]) > 1000
+    assert np.array_equal(orc.execute(g["charges"], m["P"], m["K"], threads=1), g["results"])
+    assert np.array_equal(orc.execute(g["charges"], m["P"], m["K"], threads=4), g["results"])
+    assert np.array_equal(orc.direct(g["charges"], m["K"]), g["direct"])
+    assert O.rel_l2(g["results"], g["direct"]) < 5e-4

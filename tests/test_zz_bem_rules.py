@@ -1,0 +1,48 @@
+"""GPU suite (-m gpu): the higher triangle Gauss rules of the reference's table (examples/BEM/GaussQuadrature.hpp:62-276,
+keys 13, 19, 25, 79) as panel rules of LaplaceSphericalBEM, against the golden fixtures of the unmodified reference
+(tests/golden/laplace_bem_2048_*_k13_*.npz, *_k25_*.npz) and the oracle restatement (bit-identical to them,
+tests/test_oracle.py).  The rule tables themselves are pinned on the CPU (tests/test_host_logic.py, kernel 7).
+
+STATUS: like tests/test_zz_stokes_bem.py -- added after round 1's GPU minutes were spent, so collected late and marked
+xfail(strict=False) until a hardware run is recorded.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import oracle_lib as O
+import fmm_bem_relaxed_b200 as F
+from conftest import GOLDEN
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.xfail(strict=False, reason="Gauss rules above 4 points not yet run on hardware (round 1 GPU "
+                                                     "budget spent before they were added)")]
+
+
+@pytest.mark.parametrize("name", ["laplace_bem_2048_p6_k13_bc0", "laplace_bem_2048_p6_k13_bc1", "laplace_bem_2048_p8_k25_bc0"])
+def test_golden_fixtures_of_the_reference(name):
+    g = dict(np.load(os.path.join(GOLDEN, name + ".npz")))
+    m = json.loads(str(g["meta"]))
+    opts = F.FMMOptions()
+    opts.set_max_per_box(m["ncrit"])
+    opts.set_mac_theta(m["theta"])
+    plan = F.FMM_plan(F.LaplaceSphericalBEM(m["P"], m["K"]), F.Panels(g["verts"], m["bc"]), opts)
+    assert O.rel_l2(plan.execute(g["charges"]), g["results"]) <= 1e-10
+
+
+@pytest.mark.parametrize("K", [13, 19, 25])
+def test_vs_oracle(K):
+    v = O.unit_sphere(5)
+    q = np.random.default_rng(K).random(len(v)) - 0.3
+    bc = (np.arange(len(v)) % 2).astype(np.int32)
+    opts = F.FMMOptions()
+    opts.set_max_per_box(30)
+    plan = F.FMM_plan(F.LaplaceSphericalBEM(7, K), F.Panels(v, bc), opts)
+    assert O.rel_l2(plan.execute(q), O.BemOracle(v, bc, ncrit=30).execute(q, 7, K)) <= 1e-10
+
+
+def test_key_5_is_rejected():
+    with pytest.raises(F.FmmbError):
+        F.FMM_plan(F.LaplaceSphericalBEM(5, 5), F.Panels(O.unit_sphere(3)))
