@@ -1,0 +1,70 @@
+// tests/emu/cuda_emu.hpp -- TEST INFRASTRUCTURE ONLY.
+// Lock-step CPU emulation of a CUDA launch, enough to execute the warp-synchronous kernels of
+// fmm_bem_relaxed_b200/csrc/stokes.cu and stokes_bem.cu UNCHANGED on a machine without a GPU: one std::thread per CUDA
+// thread of a block, blocks one after the other, __syncwarp / __syncthreads as std::barrier, static __shared__ arrays
+// as function-local statics (one block runs at a time), the dynamic shared segment as one global buffer, __constant__
+// arrays as ordinary globals (cudaMemcpyToSymbol = memcpy).  No warp shuffles, no PTX: kernels that need them are
+// compiled but must not be launched here.
+// This is a checker for kernel LOGIC (indexing, staging, the arithmetic of every lane); it says nothing about
+// performance and does not replace a run on the device.
+#pragma once
+#define __global__
+#define __device__
+#define __host__
+#define __constant__
+#define __forceinline__ inline
+#define __launch_bounds__(...)
+#include <cuda_runtime.h>
+#include <barrier>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <memory>
+#include <thread>
+#include <vector>
+#include <algorithm>
+
+#define cudaMemcpyToSymbol(dst, src, n) (std::memcpy((void*)(dst), (src), (n)), cudaSuccess)
+
+namespace emu {
+struct Idx { unsigned x = 0, y = 0, z = 0; };
+inline thread_local Idx threadIdx_, blockIdx_, blockDim_, gridDim_;
+inline thread_local std::barrier<>* warp_bar = nullptr;
+inline thread_local std::barrier<>* block_bar = nullptr;
+alignas(16) inline unsigned char dyn_shared[232448];
+
+template <class F>
+void launch(dim3 grid, dim3 block, F&& body) {
+  if (block.x % 32 != 0 || block.y != 1 || block.z != 1) { fprintf(stderr, "emu: block must be a multiple of 32 x 1 x 1\n"); exit(3); }
+  const unsigned nw = block.x / 32;
+  for (unsigned by = 0; by < grid.y; ++by)
+    for (unsigned bx = 0; bx < grid.x; ++bx) {
+      std::vector<std::unique_ptr<std::barrier<>>> wb;
+      for (unsigned w = 0; w < nw; ++w) wb.emplace_back(new std::barrier<>(32));
+      std::barrier<> bb(block.x);
+      std::vector<std::thread> th;
+      for (unsigned t = 0; t < block.x; ++t)
+        th.emplace_back([&, t] {
+          threadIdx_ = {t, 0, 0}; blockIdx_ = {bx, by, 0}; blockDim_ = {block.x, 1, 1}; gridDim_ = {grid.x, grid.y, 1};
+          warp_bar = wb[t / 32].get(); block_bar = &bb;
+          body();
+          // a CUDA thread that has exited no longer takes part in barriers
+          warp_bar->arrive_and_drop(); block_bar->arrive_and_drop();
+        });
+      for (auto& t : th) t.join();
+    }
+}
+}  // namespace emu
+
+#define threadIdx emu::threadIdx_
+#define blockIdx emu::blockIdx_
+#define blockDim emu::blockDim_
+#define gridDim emu::gridDim_
+inline void __syncwarp() { emu::warp_bar->arrive_and_wait(); }
+inline void __syncthreads() { emu::block_bar->arrive_and_wait(); }
+inline double __ddiv_rn(double a, double b) { return a / b; }
+inline double __shfl_sync(unsigned, double, int) { fprintf(stderr, "emu: warp shuffles are not emulated\n"); abort(); }
+inline double __shfl_xor_sync(unsigned, double, int) { fprintf(stderr, "emu: warp shuffles are not emulated\n"); abort(); }
+using std::min;
+using std::max;

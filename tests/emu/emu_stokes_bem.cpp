@@ -1,0 +1,206 @@
+// tests/emu/emu_stokes_bem.cpp -- TEST INFRASTRUCTURE ONLY (built and run by tests/test_cuda_emulation.py, CPU).
+// Executes the StokesSphericalBEM kernels of fmm_bem_relaxed_b200/csrc/stokes_bem.cu -- the shipped source lines, cut
+// out by tests/emu/extract_kernels.py -- under the lock-step emulation of tests/emu/cuda_emu.hpp:
+//   near  <file>   sbem_setup_kernel, sbem_count_kernel, sbem_assemble_kernel, sbem_gather, sbem_near_kernel on a tree
+//                  and near-field lists written by the test (from the oracle); prints nothing, writes the near-field
+//                  result in ORIGINAL order to <file>.out
+//   far            sbem_p2m_kernel<0|1> against stokes_p2m_kernel<false|true> of csrc/stokes.cu (hardware-verified
+//                  this round) fed with one point source per (panel, quadrature point), and sbem_l2p_kernel against
+//                  stokes_l2p_kernel at the panel centres; prints the largest relative differences
+#include "cuda_emu.hpp"
+#include "../../fmm_bem_relaxed_b200/csrc/common.cuh"
+#include "../../fmm_bem_relaxed_b200/csrc/laplace_ops.cuh"
+#include "../../fmm_bem_relaxed_b200/hostcxx/stokes_bem_math.hpp"
+#include <random>
+
+#define asm(...) ((void)0)   // the PTX rsqrt of the Stokes pair kernel (compiled, never launched here)
+namespace fmmb {
+namespace emu_stokes {
+#include "stokes_kernels.inc"
+}
+namespace emu_sbem {
+#include "sbem_kernels.inc"
+}
+}  // namespace fmmb
+#undef asm
+
+using namespace fmmb;
+
+static std::vector<char> slurp(const char* path) {
+  FILE* f = fopen(path, "rb");
+  if (!f) { perror(path); exit(2); }
+  fseek(f, 0, SEEK_END);
+  long n = ftell(f);
+  fseek(f, 0, SEEK_SET);
+  std::vector<char> b(n);
+  if (fread(b.data(), 1, n, f) != (size_t)n) { fprintf(stderr, "short read\n"); exit(2); }
+  fclose(f);
+  return b;
+}
+template <class T> static const T* take(const char*& p, size_t n) { const T* r = (const T*)p; p += n * sizeof(T); return r; }
+static int nblocks(long n, int t) { return (int)((n + t - 1) / t); }
+
+// ---- near field --------------------------------------------------------------------------------------------------
+// file layout (little endian): int64 n, nb, ni, ne; int32 K, kfine, as_written, pad; double mu;
+// verts[9n] f64, bc[n] i32, perm[n] u32, bb[nb] u32, be[nb] u32, off[nb+1] i32, src[ne] i32, items[4 ni] i32, q[3n] f64
+static int run_near(const char* path) {
+  std::vector<char> buf = slurp(path);
+  const char* p = buf.data();
+  const long long* hd = take<long long>(p, 4);
+  const long n = hd[0], nb = hd[1], ni = hd[2], ne = hd[3];
+  const int* ip = take<int>(p, 4);
+  const int K = ip[0], kfine = ip[1], as_written = ip[2];
+  const double mu = *take<double>(p, 1);
+  const double* verts = take<double>(p, 9 * n);
+  const int* bc = take<int>(p, n);
+  const unsigned* perm = take<unsigned>(p, n);
+  const unsigned* bb = take<unsigned>(p, nb);
+  const unsigned* be = take<unsigned>(p, nb);
+  const int* off = take<int>(p, nb + 1);
+  const int* src = take<int>(p, ne);
+  const int4* items = (const int4*)take<int>(p, 4 * ni);
+  const double* q = take<double>(p, 3 * n);
+
+  using namespace emu_sbem;
+  c_srule = bem::make_rule(K);
+  c_sfine = bem::make_rule(kfine);
+  std::vector<bem::Panel> pan(n);
+  std::vector<int> bct(n);
+  emu::launch(dim3(nblocks(n, 128)), dim3(128), [&] { sbem_setup_kernel(verts, bc, perm, n, pan.data(), bct.data()); });
+  std::vector<long long> cnt(ni + 1), base(ni + 1, 0);
+  emu::launch(dim3(nblocks(ni + 1, 128)), dim3(128), [&] { sbem_count_kernel(items, (int)ni, bb, be, off, src, cnt.data()); });
+  for (long i = 0; i < ni; ++i) base[i + 1] = base[i] + cnt[i];
+  std::vector<double> val(9 * (size_t)base[ni], -7.0), chg(3 * n), res(3 * n, -7.0);
+  emu::launch(dim3(nblocks(ni, kSbemWarps)), dim3(32 * kSbemWarps), [&] {
+    sbem_assemble_kernel(items, (int)ni, bb, be, off, src, pan.data(), bct.data(), base.data(), mu, as_written != 0, val.data());
+  });
+  emu::launch(dim3(nblocks(3 * n, 256)), dim3(256), [&] { sbem_gather(q, perm, n, chg.data()); });
+  emu::launch(dim3(nblocks(ni, kSbemWarps)), dim3(32 * kSbemWarps), [&] {
+    sbem_near_kernel(items, (int)ni, bb, be, off, src, chg.data(), base.data(), val.data(), res.data());
+  });
+  std::vector<double> out(3 * n);
+  for (long i = 0; i < n; ++i) for (int c = 0; c < 3; ++c) out[3 * (size_t)perm[i] + c] = res[3 * i + c];
+  std::string o = std::string(path) + ".out";
+  FILE* f = fopen(o.c_str(), "wb");
+  fwrite(out.data(), 8, out.size(), f);
+  fclose(f);
+  printf("near: n %ld items %ld pairs %lld\n", n, ni, base[ni]);
+  return 0;
+}
+
+// ---- far field ---------------------------------------------------------------------------------------------------
+static double rel_diff(const std::vector<double>& a, const std::vector<double>& b) {
+  double e = 0, s = 0;
+  for (size_t i = 0; i < a.size(); ++i) { e = std::max(e, std::fabs(a[i] - b[i])); s = std::max(s, std::fabs(b[i])); }
+  return e / s;
+}
+
+static int run_far() {
+  upload_laplace_tables();
+  std::mt19937_64 rng(7);
+  std::uniform_real_distribution<double> U(0., 1.);
+  // three "leaves" of 37, 1 and 64 small panels inside unit-ish boxes; box 1 has no local expansion
+  const int nleaf = 3, sizes[nleaf] = {37, 1, 64};
+  std::vector<unsigned> bb(nleaf), be(nleaf);
+  std::vector<double4> center(nleaf);
+  std::vector<int> leaves = {0, 1, 2};
+  std::vector<unsigned char> has_local = {1, 0, 1};
+  int n = 0;
+  for (int b = 0; b < nleaf; ++b) { bb[b] = n; n += sizes[b]; be[b] = n; center[b] = make_double4(0.5 + b, 0.5, 0.25 * b, 1.0); }
+  std::vector<bem::Panel> pan(n);
+  std::vector<int> bc(n);
+  std::vector<double> chg(3 * n);
+  for (int b = 0; b < nleaf; ++b)
+    for (unsigned i = bb[b]; i < be[b]; ++i) {
+      double c[3] = {center[b].x - 0.45 + 0.9 * U(rng), center[b].y - 0.45 + 0.9 * U(rng), center[b].z - 0.45 + 0.9 * U(rng)};
+      double v[9];
+      for (int k = 0; k < 9; ++k) v[k] = c[k % 3] + 0.04 * (U(rng) - 0.5);
+      bem::make_panel(v, v + 3, v + 6, pan[i]);
+      bc[i] = (i % 3 == 1) ? 1 : 0;
+      for (int k = 0; k < 3; ++k) chg[3 * i + k] = U(rng) - 0.3;
+    }
+  double worst_p2m = 0, worst_l2p = 0, max_m = 0, max_u = 0;
+  const int keys[] = {1, 4, 13};
+  for (int P : {3, 8, 11})
+    for (int key : keys) {
+      const bem::Rule rule = bem::make_rule(key);
+      emu_sbem::c_srule = rule;
+      const int K = rule.n, xs = ops::xstride(P), pp = P * P;
+      const int warps = pp <= 64 ? 4 : 1;
+      for (int group = 0; group < 2; ++group) {
+        // the kernel under test
+        std::vector<double> M[4], R[4];
+        for (int s = 0; s < 4; ++s) { M[s].assign((size_t)nleaf * xs, 0.0); R[s].assign((size_t)nleaf * xs, 0.0); }
+        emu::launch(dim3(nblocks(nleaf, warps), 4), dim3(32 * warps), [&] {
+          if (group == 0) emu_sbem::sbem_p2m_kernel<0>(leaves.data(), nleaf, bb.data(), be.data(), center.data(), pan.data(),
+                                                       bc.data(), chg.data(), P, M[0].data(), M[1].data(), M[2].data(), M[3].data());
+          else emu_sbem::sbem_p2m_kernel<1>(leaves.data(), nleaf, bb.data(), be.data(), center.data(), pan.data(), bc.data(),
+                                            chg.data(), P, M[0].data(), M[1].data(), M[2].data(), M[3].data());
+        });
+        // comparator: the point-source kernel of csrc/stokes.cu on one body per (panel of this group, quadrature point)
+        const int REC = group == 0 ? 6 : 9;
+        std::vector<double> srcrec;
+        std::vector<unsigned> vb(nleaf), ve(nleaf);
+        unsigned m = 0;
+        for (int b = 0; b < nleaf; ++b) {
+          vb[b] = m;
+          for (unsigned i = bb[b]; i < be[b]; ++i) {
+            if (bc[i] != group) continue;
+            for (int k = 0; k < K; ++k) {
+              double qp[3];
+              bem::quad_point(pan[i], rule.pt[k], qp);
+              const double wa = pan[i].area * rule.w[k];
+              for (int c = 0; c < 3; ++c) srcrec.push_back(qp[c]);
+              for (int c = 0; c < 3; ++c) srcrec.push_back(wa * chg[3 * i + c]);
+              if (group == 1) for (int c = 0; c < 3; ++c) srcrec.push_back(pan[i].nrm[c]);
+              ++m;
+            }
+          }
+          ve[b] = m;
+        }
+        emu::launch(dim3(nblocks(nleaf, warps), 4), dim3(32 * warps), [&] {
+          if (group == 0) emu_stokes::stokes_p2m_kernel<false>(leaves.data(), nleaf, vb.data(), ve.data(), center.data(),
+                                                               srcrec.data(), P, R[0].data(), R[1].data(), R[2].data(), R[3].data());
+          else emu_stokes::stokes_p2m_kernel<true>(leaves.data(), nleaf, vb.data(), ve.data(), center.data(), srcrec.data(), P,
+                                                   R[0].data(), R[1].data(), R[2].data(), R[3].data());
+        });
+        for (int s = 0; s < 4; ++s) {
+          worst_p2m = std::max(worst_p2m, rel_diff(M[s], R[s]));
+          for (double x : M[s]) max_m = std::max(max_m, std::fabs(x));
+        }
+        (void)REC;
+      }
+      // L2P: random local expansions; the BEM kernel writes only the targets of its group, scaled
+      std::vector<double> L[4];
+      for (int s = 0; s < 4; ++s) { L[s].resize((size_t)nleaf * xs); for (auto& x : L[s]) x = U(rng) - 0.5; }
+      std::vector<double4> body(n);
+      for (int i = 0; i < n; ++i) body[i] = make_double4(pan[i].c[0], pan[i].c[1], pan[i].c[2], 0.0);
+      const int nc = P * (P + 1) / 2;
+      if ((size_t)4 * 4 * nc * sizeof(double2) > sizeof emu::dyn_shared) return 4;
+      for (int group = 0; group < 2; ++group) {
+        const double scale = group == 0 ? 1. / 2 / 0.037 : 0.5;
+        std::vector<double> got(3 * n, 0.0), want(3 * n, -1.0);
+        emu::launch(dim3(nblocks(nleaf, 4)), dim3(128), [&] {
+          emu_sbem::sbem_l2p_kernel(leaves.data(), nleaf, bb.data(), be.data(), center.data(), has_local.data(), pan.data(),
+                                    bc.data(), group, P, L[0].data(), L[1].data(), L[2].data(), L[3].data(), scale, got.data());
+        });
+        emu::launch(dim3(nblocks(nleaf, 4)), dim3(128), [&] {
+          emu_stokes::stokes_l2p_kernel(leaves.data(), nleaf, bb.data(), be.data(), center.data(), has_local.data(), body.data(),
+                                        P, L[0].data(), L[1].data(), L[2].data(), L[3].data(), scale, want.data());
+        });
+        for (int i = 0; i < n; ++i)
+          if (bc[i] != group) for (int c = 0; c < 3; ++c) want[3 * i + c] = 0.0;     // untouched by the BEM kernel
+        worst_l2p = std::max(worst_l2p, rel_diff(got, want));
+        for (double x : got) max_u = std::max(max_u, std::fabs(x));
+      }
+    }
+  printf("far: p2m %.3e l2p %.3e max_multipole %.3e max_velocity %.3e\n", worst_p2m, worst_l2p, max_m, max_u);
+  return 0;
+}
+
+int main(int argc, char** argv) {
+  if (argc >= 3 && !strcmp(argv[1], "near")) return run_near(argv[2]);
+  if (argc >= 2 && !strcmp(argv[1], "far")) return run_far();
+  fprintf(stderr, "usage: emu_stokes_bem near <file> | far\n");
+  return 2;
+}

@@ -1,0 +1,81 @@
+"""CPU suite: the StokesSphericalBEM CUDA kernels (fmm_bem_relaxed_b200/csrc/stokes_bem.cu) executed WITHOUT a GPU.
+
+tests/emu/extract_kernels.py cuts the kernels out of the shipped .cu files and tests/emu/cuda_emu.hpp runs them in lock
+step (one std::thread per CUDA thread, __syncwarp as a barrier, shared memory as statics): the indexing, staging and
+per-lane arithmetic that will run on the B200 are these very source lines.  Checked here:
+  * near field -- sbem_setup / count / assemble / gather / near kernels on a 512-panel sphere whose interaction lists
+    are all near field (so the oracle's FMM matvec IS the near field), all boundary-condition mixes, both near-field
+    modes: 1e-13 against the oracle restatement, which is bit-identical to the reference;
+  * far field -- sbem_p2m_kernel<0|1> against the point-source kernels of csrc/stokes.cu (green on hardware this round)
+    fed with one source per (panel, quadrature point), sbem_l2p_kernel against stokes_l2p_kernel: 1e-13.
+This verifies kernel logic, not performance, and does not replace the first run on the device (tests/test_zz_stokes_bem.py).
+"""
+import os
+import re
+import struct
+import subprocess
+
+import numpy as np
+import pytest
+
+import oracle_lib as O
+from conftest import ROOT
+
+EMU = os.path.join(ROOT, "tests", "emu")
+CSRC = os.path.join(ROOT, "fmm_bem_relaxed_b200", "csrc")
+CUDA_INC = "/usr/local/cuda/include"
+
+pytestmark = pytest.mark.skipif(not os.path.exists(os.path.join(CUDA_INC, "cuda_runtime.h")),
+                                reason="CUDA headers not installed")
+
+
+@pytest.fixture(scope="module")
+def emu(tmp_path_factory):
+    d = tmp_path_factory.mktemp("emu")
+    for src, dst in (("stokes.cu", "stokes_kernels.inc"), ("stokes_bem.cu", "sbem_kernels.inc")):
+        subprocess.check_call(["python", os.path.join(EMU, "extract_kernels.py"), os.path.join(CSRC, src), str(d / dst)])
+    exe = str(d / "emu_stokes_bem")
+    subprocess.check_call(["g++", "-std=c++20", "-O1", "-pthread", "-I", CUDA_INC, "-I", str(d), "-I", EMU,
+                           os.path.join(EMU, "emu_stokes_bem.cpp"), "-o", exe, "-L/usr/local/cuda/lib64", "-lcudart"])
+    return exe
+
+
+def test_far_field_kernels_match_the_point_source_kernels(emu):
+    out = subprocess.check_output([emu, "far"], timeout=600).decode()
+    m = re.search(r"far: p2m ([0-9.eE+-]+) l2p ([0-9.eE+-]+) max_multipole ([0-9.eE+-]+) max_velocity ([0-9.eE+-]+)", out)
+    assert m, out
+    p2m, l2p, mm, mu = (float(x) for x in m.groups())
+    assert mm > 1e-4 and mu > 1e-2                      # the comparison is not between zeros
+    assert p2m <= 1e-13 and l2p <= 1e-13
+
+
+@pytest.mark.parametrize("bcmix,as_written,K", [(0, False, 4), (1, False, 4), (2, False, 3), (0, True, 4), (1, True, 4),
+                                               (2, True, 1)])
+def test_near_field_kernels_match_the_oracle(emu, tmp_path, bcmix, as_written, K):
+    verts = O.unit_sphere(4)                            # 512 panels, ncrit 64, theta 0.5: every list entry is near field
+    n = len(verts)
+    bc = np.zeros(n, np.int32) if bcmix == 0 else (np.ones(n, np.int32) if bcmix == 1 else (np.arange(n) % 3 == 1).astype(np.int32))
+    mu, kfine = 0.02, 19
+    orc = O.StokesBemOracle(verts, bc, mu=mu, K=K, kfine=kfine, as_written=as_written)
+    t = orc.tree()
+    assert len(t["lr"]) == 0 and t["p2p_off"][-1] >= 64
+    q = np.random.default_rng(11 + bcmix).random((n, 3)) - 0.4
+    want = orc.execute(q, 5, threads=1)
+    boxes = t["boxes"]
+    bb, be, leaf = boxes[:, 4].astype(np.uint32), boxes[:, 5].astype(np.uint32), boxes[:, 7]
+    items = []
+    for b in np.nonzero(leaf)[0]:                       # csrc/laplace.cu: chunks of <= 32 targets in leaf order
+        for first in range(int(bb[b]), int(be[b]), 32):
+            items.append((int(b), first, min(32, int(be[b]) - first), 0))
+    items = np.array(items, np.int32)
+    path = tmp_path / "near.bin"
+    with open(path, "wb") as f:
+        f.write(struct.pack("<4q4id", n, len(boxes), len(items), len(t["p2p_idx"]), K, kfine, int(as_written), 0, mu))
+        for a in (np.ascontiguousarray(verts, np.float64), bc, t["perm"].astype(np.uint32), bb, be,
+                  t["p2p_off"].astype(np.int32), t["p2p_idx"].astype(np.int32), items, np.ascontiguousarray(q, np.float64)):
+            f.write(np.ascontiguousarray(a).tobytes())
+    out = subprocess.check_output([emu, "near", str(path)], timeout=900).decode()
+    assert "near: n %d" % n in out
+    got = np.fromfile(str(path) + ".out").reshape(n, 3)
+    for k in range(3):
+        assert O.rel_l2(got[:, k], want[:, k]) <= 1e-13
