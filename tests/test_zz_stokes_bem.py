@@ -163,3 +163,32 @@ def test_python_gmres_on_vec3_unknowns():
     x = rep["x"].reshape(n, 3)
     area = 0.5 * np.linalg.norm(np.cross(verts[:, 2] - verts[:, 0], verts[:, 1] - verts[:, 0]), axis=1)
     assert abs((x[:, 0] * area).sum() - 0.01911) < 1e-5
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_partitioned_plans_tile_the_single_gpu_result(world):
+    """Target-leaf sharding on one device without a communicator: each rank writes its own slice."""
+    verts = O.unit_sphere(6)
+    n = len(verts)
+    bc = (np.arange(n) % 3 == 1).astype(np.int32)
+    q = np.random.default_rng(world).random((n, 3))
+    full = make_plan(verts, bc, 6, ncrit=40).execute(q)
+    merged = np.zeros_like(full)
+    for r in range(world):
+        opts = F.FMMOptions()
+        opts.set_max_per_box(40)
+        opts.rank, opts.nranks = r, world
+        merged += F.FMM_plan(F.StokesSphericalBEM(6, 4, 1e-3, 19), F.Panels(verts, bc), opts).execute(q)
+    assert O.rel_l2(merged, full) <= 1e-13
+
+
+@pytest.mark.parametrize("rec,ncrit", [(1, 64), (2, 64), (2, 4), (3, 1)])
+def test_tiny_meshes(rec, ncrit):
+    """8 panels in a single leaf (the root), 32 panels, one panel per leaf: no far field or a degenerate tree."""
+    verts = O.unit_sphere(rec)
+    n = len(verts)
+    q = np.random.default_rng(rec).random((n, 3)) - 0.5
+    for bc in (0, 1):
+        orc = O.StokesBemOracle(verts, bc, K=3, kfine=13, ncrit=ncrit)
+        got = make_plan(verts, bc, 4, K=3, kfine=13, ncrit=ncrit).execute(q)
+        assert O.rel_l2(got, orc.execute(q, 4)) <= TOL
