@@ -7,6 +7,7 @@
 //   include/Matvec.hpp:14-33 CSR matvec in EvalInteractionLazySparse.hpp:134-151 -> bem_near_kernel (per matvec)
 //   :307-352 P2M with K quadrature points per panel, two expansion sets     -> bem_p2m_kernel<SET>
 //   :448-476 L2P (scalar result, set and sign picked by the target's BC)     -> bem_l2p_kernel<SET>
+//   :394-422 vector M2P (treecode evaluator, `LaplaceBEM -eval TREE`)        -> bem_m2p_kernel<SET>
 //   M2M / M2L / L2L of each set (:362-383,432-437) are the Laplace translations -> laplace_translations()
 //
 // Near field layout.  All targets of a leaf share one source list (the P2P list of the leaf), so the
@@ -272,6 +273,57 @@ bem_l2p_kernel(const int* __restrict__ leaves, int nleaves, const unsigned* __re
   }
 }
 
+// M2P (treecode, `LaplaceBEM -eval TREE`): warp per leaf, lane per target panel; every source box accepted for the
+// leaf or one of its ancestors is evaluated at the panel centres (vector M2P, LaplaceSphericalBEM.hpp:394-422):
+// only panels whose BC selects this set are touched, set 0 adds, set 1 subtracts.  Accumulates into res (zeroed by
+// the caller), sources in list order per box, ancestors bottom-up -- a fixed order, no atomics.
+template <int SET>
+__global__ void __launch_bounds__(128)
+bem_m2p_kernel(const int* __restrict__ leaves, int nleaves, const unsigned* __restrict__ bb,
+               const unsigned* __restrict__ be, const unsigned* __restrict__ parent, const int* __restrict__ off,
+               const int* __restrict__ src, const double4* __restrict__ center, const bem::Panel* __restrict__ pan,
+               const int* __restrict__ bc, int P, const double* __restrict__ M, double* __restrict__ res) {
+  extern __shared__ double2 bem_ms[];
+  const int nc = P * (P + 1) / 2;
+  const int wl = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int w = blockIdx.x * (blockDim.x >> 5) + wl;
+  if (w >= nleaves) return;
+  double2* Ms = bem_ms + wl * nc;
+  const int leaf = leaves[w];
+  const unsigned b0 = bb[leaf], b1 = be[leaf];
+  for (unsigned base = b0; base < b1; base += 32) {
+    const unsigned i = base + lane;
+    const bool act = i < b1 && bc[i] == SET;
+    double px = 0, py = 0, pz = 0;
+    if (act) { px = pan[i].c[0]; py = pan[i].c[1]; pz = pan[i].c[2]; }
+    double acc = 0;
+    for (int a = leaf;; a = (int)parent[a]) {
+      for (int e = off[a]; e < off[a + 1]; ++e) {
+        const int sb = src[e];
+        __syncwarp();
+        for (int k = lane; k < nc; k += 32) {
+          int n, m;
+          unpack_nm(k, n, m);
+          Ms[k] = load_coef(M + (size_t)sb * xstride(P), n, m);
+        }
+        __syncwarp();
+        if (act) {
+          const double4 c = center[sb];
+          const Sph s = to_sph(px - c.x, py - c.y, pz - c.z);
+          double v = 0;
+          regular_harmonics<false, true>(P, s, 1.0, [&](int n, int m, double yr, double yi, double, double) {
+            const double2 c2 = Ms[n * (n + 1) / 2 + m];
+            v += (m == 0 ? 1.0 : 2.0) * (c2.x * yr - c2.y * yi);   // Re(M Y)
+          });
+          acc += v;
+        }
+      }
+      if (a == 0) break;
+    }
+    if (act) res[i] += SET == 0 ? acc : -acc;
+  }
+}
+
 __global__ void bem_gather_charges(const double* __restrict__ q, const unsigned* __restrict__ perm, int64_t n,
                                    double4* __restrict__ body) {
   int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
@@ -390,7 +442,20 @@ void bem_execute(fmmb_plan* plan, const double* d_charges, double* d_results) {
                                                                       T.center.p, T.body.p, B->pan.p, B->bc.p, P,
                                                                       plan->M.p);
     ++plan->launches;
-    laplace_translations(plan, s);
+    laplace_translations(plan, s);          // treecode: stops after the upward pass
+    if (plan->opts.evaluator == FMMB_EVAL_TREECODE) {
+      if (!T.n_own_leaves) continue;
+      if (set == 0)
+        bem_m2p_kernel<0><<<nblk(T.n_own_leaves, 4), 128, 4 * nc * sizeof(double2), s>>>(
+            T.own_leaves.p, T.n_own_leaves, T.bbegin.p, T.bend.p, T.parent.p, T.m2l_off.p, T.m2l_src.p, T.center.p,
+            B->pan.p, B->bc.p, P, plan->M.p, B->res_far.p);
+      else
+        bem_m2p_kernel<1><<<nblk(T.n_own_leaves, 4), 128, 4 * nc * sizeof(double2), s>>>(
+            T.own_leaves.p, T.n_own_leaves, T.bbegin.p, T.bend.p, T.parent.p, T.m2l_off.p, T.m2l_src.p, T.center.p,
+            B->pan.p, B->bc.p, P, plan->M.p, B->res_far.p);
+      ++plan->launches;
+      continue;
+    }
     if (set == 0)
       bem_l2p_kernel<0><<<nblk(T.n_own_leaves, 4), 128, 4 * nc * sizeof(double2), s>>>(
           T.own_leaves.p, T.n_own_leaves, T.bbegin.p, T.bend.p, T.center.p, T.has_local.p, B->pan.p, B->bc.p, P,

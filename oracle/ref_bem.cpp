@@ -4,7 +4,8 @@
 // 9 doubles per panel; FMM_plan<LaplaceSphericalBEM>(K, panels, opts) with opts.sparse_local as
 // examples/LaplaceBEM.cpp:81 sets it; one plan.execute(charges).  Dumps panels, charges and results.
 // Build: oracle/Makefile (g++ -fno-access-control, oracle/boost_shim).
-//   ref_bem -recursions 4 -P 8 -K 4 -ncrit 64 -theta 0.5 -bc 0 [-rand] [-sparse 1] [-direct] [-in file -n N] -dump prefix
+//   ref_bem -recursions 4 -P 8 -K 4 -ncrit 64 -theta 0.5 -bc 0 [-rand] [-sparse 1] [-tree] [-direct] [-in file -n N] -dump prefix
+// -tree: FMMOptions::TREECODE (what `LaplaceBEM -eval TREE` selects): M2P instead of M2L / L2L / L2P
 #include <cmath>
 #include <cstring>
 #include <cstdio>
@@ -84,9 +85,9 @@ int main(int argc, char** argv) {
     else if (!strcmp(argv[i], "-in")) in_file = argv[++i];
     else if (!strcmp(argv[i], "-n")) n_in = atoi(argv[++i]);
     else if (!strcmp(argv[i], "-dump")) dump_prefix = argv[++i];
+    else if (!strcmp(argv[i], "-tree")) tree = 1;
 #ifdef YUKAWA_BEM
     else if (!strcmp(argv[i], "-kappa")) g_kappa = atof(argv[++i]);
-    else if (!strcmp(argv[i], "-tree")) tree = 1;
 #endif
     else { fprintf(stderr, "unknown arg %s\n", argv[i]); return 2; }
   }

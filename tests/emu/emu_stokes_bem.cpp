@@ -7,6 +7,8 @@
 //   far            sbem_p2m_kernel<0|1> against stokes_p2m_kernel<false|true> of csrc/stokes.cu (hardware-verified
 //                  this round) fed with one point source per (panel, quadrature point), and sbem_l2p_kernel against
 //                  stokes_l2p_kernel at the panel centres; prints the largest relative differences
+//   m2p            bem_m2p_kernel<0|1> (treecode of LaplaceSphericalBEM, csrc/bem.cu) against m2p_kernel of
+//                  csrc/laplace.cu (hardware-verified) on a toy tree with random multipoles
 #include "cuda_emu.hpp"
 #include "../../fmm_bem_relaxed_b200/csrc/common.cuh"
 #include "../../fmm_bem_relaxed_b200/csrc/laplace_ops.cuh"
@@ -20,6 +22,11 @@ namespace emu_stokes {
 }
 namespace emu_sbem {
 #include "sbem_kernels.inc"
+}
+namespace emu_m2p {            // treecode: the point kernel of csrc/laplace.cu and the panel kernel of csrc/bem.cu
+using namespace ops;
+#include "lap_m2p.inc"
+#include "bem_m2p.inc"
 }
 }  // namespace fmmb
 #undef asm
@@ -198,9 +205,63 @@ static int run_far() {
   return 0;
 }
 
+// ---- treecode: bem_m2p_kernel<SET> (csrc/bem.cu) against m2p_kernel (csrc/laplace.cu, hardware-verified) ----------
+// a three-level toy tree: root 0, children 1..2 (box 2 is a leaf), leaves 3..4 under box 1; interaction lists of random
+// source boxes for every box; random multipoles.  The panel kernel must add (set 0) or subtract (set 1) the potential
+// component of the point kernel at the centres of the panels of its set, and leave the others alone.
+static int run_m2p() {
+  upload_laplace_tables();
+  std::mt19937_64 rng(13);
+  std::uniform_real_distribution<double> U(0., 1.);
+  const int nb = 5;
+  std::vector<unsigned> parent = {0, 0, 0, 1, 1}, bb = {0, 0, 70, 0, 33}, be = {103, 70, 103, 33, 70};
+  std::vector<int> leaves = {2, 3, 4};
+  std::vector<int> off = {0, 0, 2, 5, 6, 9}, src = {2, 4, 1, 3, 4, 2, 2, 1, 3};   // far boxes (any box with a multipole)
+  std::vector<double4> center(nb);
+  for (int b = 0; b < nb; ++b) center[b] = make_double4(3.0 * b, -2.0 + b, 1.5 * b, 1.0);
+  const int n = 103;
+  std::vector<bem::Panel> pan(n);
+  std::vector<int> bc(n);
+  std::vector<double4> body(n);
+  for (int i = 0; i < n; ++i) {
+    double c[3] = {20 + U(rng), 20 + U(rng), 20 + U(rng)}, v[9];     // far from every source box
+    for (int k = 0; k < 9; ++k) v[k] = c[k % 3] + 0.04 * (U(rng) - 0.5);
+    bem::make_panel(v, v + 3, v + 6, pan[i]);
+    bc[i] = i % 2;
+    body[i] = make_double4(pan[i].c[0], pan[i].c[1], pan[i].c[2], 0.0);
+  }
+  double worst = 0, biggest = 0;
+  for (int P : {2, 8, 13}) {
+    const int xs = ops::xstride(P), nc = P * (P + 1) / 2;
+    std::vector<double> M((size_t)nb * xs);
+    for (auto& x : M) x = U(rng) - 0.5;
+    std::vector<double4> ref(n, make_double4(0, 0, 0, 0));
+    emu::launch(dim3(nblocks(3, 4)), dim3(128), [&] {
+      emu_m2p::m2p_kernel(leaves.data(), 3, bb.data(), be.data(), parent.data(), off.data(), src.data(), center.data(),
+                          body.data(), P, M.data(), ref.data());
+    });
+    for (int set = 0; set < 2; ++set) {
+      std::vector<double> got(n, 0.25), want(n, 0.25);
+      emu::launch(dim3(nblocks(3, 4)), dim3(128), [&] {
+        if (set == 0) emu_m2p::bem_m2p_kernel<0>(leaves.data(), 3, bb.data(), be.data(), parent.data(), off.data(), src.data(),
+                                                 center.data(), pan.data(), bc.data(), P, M.data(), got.data());
+        else emu_m2p::bem_m2p_kernel<1>(leaves.data(), 3, bb.data(), be.data(), parent.data(), off.data(), src.data(),
+                                        center.data(), pan.data(), bc.data(), P, M.data(), got.data());
+      });
+      for (int i = 0; i < n; ++i) if (bc[i] == set) want[i] += set == 0 ? ref[i].x : -ref[i].x;
+      for (int i = 0; i < n; ++i) biggest = std::max(biggest, std::fabs(ref[i].x));
+      worst = std::max(worst, rel_diff(got, want));
+    }
+    (void)nc;
+  }
+  printf("m2p: %.3e max_potential %.3e\n", worst, biggest);
+  return 0;
+}
+
 int main(int argc, char** argv) {
+  if (argc >= 2 && !strcmp(argv[1], "m2p")) return run_m2p();
   if (argc >= 3 && !strcmp(argv[1], "near")) return run_near(argv[2]);
   if (argc >= 2 && !strcmp(argv[1], "far")) return run_far();
-  fprintf(stderr, "usage: emu_stokes_bem near <file> | far\n");
+  fprintf(stderr, "usage: emu_stokes_bem near <file> | far | m2p\n");
   return 2;
 }

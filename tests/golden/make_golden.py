@@ -162,15 +162,16 @@ def stokes_bem_case(name, exe, recursions, p, k, kfine, mu, ncrit, bc):
         print(name, "FMM vs direct", meta["err_vs_direct"])
 
 
-def laplace_bem_case(name, recursions, p, k, ncrit, bc):
+def laplace_bem_case(name, recursions, p, k, ncrit, bc, tree=False):
     """LaplaceSphericalBEM through oracle/_ref/ref_bem (the unmodified reference class): FMM matvec with the sparse near
     field (examples/LaplaceBEM.cpp:81) and Direct::matvec, random charges."""
     with tempfile.TemporaryDirectory() as tmp:
         pre = os.path.join(tmp, "d")
         cmd = [os.path.join(ROOT, "oracle", "_ref", "ref_bem"), "-recursions", str(recursions), "-P", str(p), "-K", str(k),
-               "-ncrit", str(ncrit), "-bc", str(bc), "-rand", "-direct", "-dump", pre]
+               "-ncrit", str(ncrit), "-bc", str(bc), "-rand", "-direct", "-dump", pre] + (["-tree"] if tree else [])
         out = subprocess.check_output(cmd, env=dict(os.environ, OMP_NUM_THREADS="1"), cwd=tmp).decode()
         meta = json.loads([l for l in out.splitlines() if l.startswith("REF_JSON")][0][len("REF_JSON "):])
+        meta["treecode"] = int(tree)
         np.savez_compressed(os.path.join(HERE, name + ".npz"), meta=json.dumps(meta),
                             verts=np.fromfile(pre + ".verts.f64").reshape(-1, 3, 3), charges=np.fromfile(pre + ".charges.f64"),
                             results=np.fromfile(pre + ".results.f64"), direct=np.fromfile(pre + ".direct.f64"))
@@ -178,6 +179,11 @@ def laplace_bem_case(name, recursions, p, k, ncrit, bc):
 
 
 def main():
+    if "--laplace-bem-tree" in sys.argv:
+        # `LaplaceBEM -eval TREE`: FMMOptions::TREECODE with the sparse near field
+        for bc in (0, 1):
+            laplace_bem_case("laplace_bem_tree_2048_p6_k4_bc%d" % bc, 5, 6, 4, 40, bc, tree=True)
+        return
     if "--laplace-bem" in sys.argv:
         # LaplaceSphericalBEM: both boundary conditions, the 4-point rule of BASELINE config 2 and the 13- and 25-point
         # rules of the reference's table; 2 048 panels with ncrit 40 so that the far field is exercised

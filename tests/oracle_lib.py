@@ -56,7 +56,7 @@ def load():
         L.fmmo_yukawa_bem_direct.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_double, vp, vp, vp, vp, ctypes.c_int]
         L.fmmo_unit_sphere.argtypes = [ctypes.c_int, vp]
         L.fmmo_panel_centers.argtypes = [ctypes.c_int, vp, vp]
-        L.fmmo_bem_execute.argtypes = [vp, ctypes.c_int, ctypes.c_int, vp, vp, vp, vp, ctypes.c_int]
+        L.fmmo_bem_execute.argtypes = [vp, ctypes.c_int, ctypes.c_int, vp, vp, vp, vp, ctypes.c_int, ctypes.c_int]
         L.fmmo_bem_direct.argtypes = [ctypes.c_int, ctypes.c_int, vp, vp, vp, vp, ctypes.c_int]
         L.fmmo_stokes_bem_execute.argtypes = [vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_double, ctypes.c_int,
                                               vp, vp, vp, vp, ctypes.c_int]
@@ -181,11 +181,11 @@ class BemOracle(Oracle):
         self.bc = np.ascontiguousarray(np.broadcast_to(bc, (n,)), np.int32)
         super().__init__(panel_centers(self.verts), ncrit, theta)
 
-    def execute(self, charges, P, K=4, threads=None):
+    def execute(self, charges, P, K=4, threads=None, treecode=False):
         q = np.ascontiguousarray(np.asarray(charges, dtype=np.float64).reshape(-1))
         res = np.zeros(self.n)
         rc = self.L.fmmo_bem_execute(self.h, P, K, _p(self.verts), _p(self.bc), _p(q), _p(res),
-                                     threads or os.cpu_count() or 1)
+                                     2 if treecode else 0, threads or os.cpu_count() or 1)
         if rc != 0:
             raise RuntimeError("oracle BEM execute failed: %d" % rc)
         return res

@@ -8,6 +8,7 @@ per-lane arithmetic that will run on the B200 are these very source lines.  Chec
     modes: 1e-13 against the oracle restatement, which is bit-identical to the reference;
   * far field -- sbem_p2m_kernel<0|1> against the point-source kernels of csrc/stokes.cu (green on hardware this round)
     fed with one source per (panel, quadrature point), sbem_l2p_kernel against stokes_l2p_kernel: 1e-13.
+  * treecode -- bem_m2p_kernel<0|1> of csrc/bem.cu against m2p_kernel of csrc/laplace.cu (green on hardware).
 This verifies kernel logic, not performance, and does not replace the first run on the device (tests/test_zz_stokes_bem.py).
 """
 import os
@@ -32,8 +33,9 @@ pytestmark = pytest.mark.skipif(not os.path.exists(os.path.join(CUDA_INC, "cuda_
 @pytest.fixture(scope="module")
 def emu(tmp_path_factory):
     d = tmp_path_factory.mktemp("emu")
-    for src, dst in (("stokes.cu", "stokes_kernels.inc"), ("stokes_bem.cu", "sbem_kernels.inc")):
-        subprocess.check_call(["python", os.path.join(EMU, "extract_kernels.py"), os.path.join(CSRC, src), str(d / dst)])
+    for src, dst, names in (("stokes.cu", "stokes_kernels.inc", []), ("stokes_bem.cu", "sbem_kernels.inc", []),
+                            ("laplace.cu", "lap_m2p.inc", ["m2p_kernel"]), ("bem.cu", "bem_m2p.inc", ["bem_m2p_kernel"])):
+        subprocess.check_call(["python", os.path.join(EMU, "extract_kernels.py"), os.path.join(CSRC, src), str(d / dst)] + names)
     exe = str(d / "emu_stokes_bem")
     subprocess.check_call(["g++", "-std=c++20", "-O1", "-pthread", "-I", CUDA_INC, "-I", str(d), "-I", EMU,
                            os.path.join(EMU, "emu_stokes_bem.cpp"), "-o", exe, "-L/usr/local/cuda/lib64", "-lcudart"])
@@ -47,6 +49,15 @@ def test_far_field_kernels_match_the_point_source_kernels(emu):
     p2m, l2p, mm, mu = (float(x) for x in m.groups())
     assert mm > 1e-4 and mu > 1e-2                      # the comparison is not between zeros
     assert p2m <= 1e-13 and l2p <= 1e-13
+
+
+def test_bem_treecode_kernel_matches_the_point_treecode_kernel(emu):
+    """bem_m2p_kernel<0|1> (`LaplaceBEM -eval TREE`, csrc/bem.cu) against m2p_kernel of csrc/laplace.cu, which is green on
+    hardware against the reference's treecode: same potential at the panel centres, sign and set by the target's BC."""
+    out = subprocess.check_output([emu, "m2p"], timeout=600).decode()
+    m = re.search(r"m2p: ([0-9.eE+-]+) max_potential ([0-9.eE+-]+)", out)
+    assert m, out
+    assert float(m.group(2)) > 1e-3 and float(m.group(1)) <= 1e-13
 
 
 @pytest.mark.parametrize("bcmix,as_written,K", [(0, False, 4), (1, False, 4), (2, False, 3), (0, True, 4), (1, True, 4),

@@ -272,3 +272,16 @@ def test_laplace_bem_restatement_matches_reference_bitwise(name):
     assert np.array_equal(orc.execute(g["charges"], m["P"], m["K"], threads=4), g["results"])
     assert np.array_equal(orc.direct(g["charges"], m["K"]), g["direct"])
     assert O.rel_l2(g["results"], g["direct"]) < 5e-4
+
+
+@pytest.mark.parametrize("bc", [0, 1])
+def test_laplace_bem_treecode_restatement_matches_reference_bitwise(bc):
+    """`LaplaceBEM -eval TREE`: FMMOptions::TREECODE with the sparse near field (oracle/_ref/ref_bem -tree)."""
+    g = dict(np.load(os.path.join(GOLDEN, "laplace_bem_tree_2048_p6_k4_bc%d.npz" % bc)))
+    m = _meta(g)
+    assert m["treecode"] == 1
+    orc = O.BemOracle(g["verts"], bc, ncrit=m["ncrit"], theta=m["theta"])
+    res = orc.execute(g["charges"], m["P"], m["K"], threads=1, treecode=True)
+    assert np.array_equal(res, g["results"])
+    assert O.rel_l2(res, g["direct"]) < 2e-4
+    assert not np.array_equal(res, orc.execute(g["charges"], m["P"], m["K"], threads=1))     # not the FMM path

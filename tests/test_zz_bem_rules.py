@@ -3,6 +3,9 @@ keys 13, 19, 25, 79) as panel rules of LaplaceSphericalBEM, against the golden f
 (tests/golden/laplace_bem_2048_*_k13_*.npz, *_k25_*.npz) and the oracle restatement (bit-identical to them,
 tests/test_oracle.py).  The rule tables themselves are pinned on the CPU (tests/test_host_logic.py, kernel 7).
 
+Also here: the treecode evaluator of LaplaceSphericalBEM (`LaplaceBEM -eval TREE`, bem_m2p_kernel in csrc/bem.cu) against
+the golden fixtures of `ref_bem -tree` and the oracle (bit-identical to them).
+
 STATUS: like tests/test_zz_stokes_bem.py -- added after round 1's GPU minutes were spent, so collected late and marked
 xfail(strict=False) until a hardware run is recorded.
 """
@@ -41,6 +44,34 @@ def test_vs_oracle(K):
     opts.set_max_per_box(30)
     plan = F.FMM_plan(F.LaplaceSphericalBEM(7, K), F.Panels(v, bc), opts)
     assert O.rel_l2(plan.execute(q), O.BemOracle(v, bc, ncrit=30).execute(q, 7, K)) <= 1e-10
+
+
+@pytest.mark.parametrize("bc", [0, 1])
+def test_treecode_golden_fixtures(bc):
+    g = dict(np.load(os.path.join(GOLDEN, "laplace_bem_tree_2048_p6_k4_bc%d.npz" % bc)))
+    m = json.loads(str(g["meta"]))
+    opts = F.FMMOptions()
+    opts.set_max_per_box(m["ncrit"])
+    opts.set_mac_theta(m["theta"])
+    opts.evaluator = F.FMMOptions.TREECODE
+    plan = F.FMM_plan(F.LaplaceSphericalBEM(m["P"], m["K"]), F.Panels(g["verts"], bc), opts)
+    res = plan.execute(g["charges"])
+    assert O.rel_l2(res, g["results"]) <= 1e-10
+    assert np.array_equal(plan.execute(g["charges"]), res)
+
+
+def test_treecode_mixed_boundary_conditions_and_orders():
+    v = O.unit_sphere(6)
+    bc = (np.arange(len(v)) % 2).astype(np.int32)
+    q = np.random.default_rng(8).random(len(v)) - 0.3
+    orc = O.BemOracle(v, bc, ncrit=50)
+    opts = F.FMMOptions()
+    opts.set_max_per_box(50)
+    opts.evaluator = F.FMMOptions.TREECODE
+    plan = F.FMM_plan(F.LaplaceSphericalBEM(8, 4), F.Panels(v, bc), opts)
+    for p in (8, 3, 12):
+        plan.kernel().set_p(p)
+        assert O.rel_l2(plan.execute(q), orc.execute(q, p, 4, treecode=True)) <= 1e-10
 
 
 def test_key_5_is_rejected():
