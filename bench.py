@@ -212,7 +212,7 @@ def bench_stokes_bem():
         if not os.path.exists(exe):
             return None
         with tempfile.TemporaryDirectory() as tmp:     # the drivers write out.face / out.vert / test.vert into cwd
-            out = subprocess.check_output([exe] + args, env=env, cwd=tmp, timeout=900, stderr=subprocess.STDOUT).decode()
+            out = subprocess.check_output([exe] + args, env=env, cwd=tmp, timeout=120, stderr=subprocess.STDOUT).decode()
         it = re.search(r"after (\d+) iterations|iterations: (\d+)", out)
         fx = re.search(r"Fx: ([0-9.eE+-]+), analytical: ([0-9.eE+-]+)", out)
         return {"solve_s": float(re.search(r"solve : ([0-9.eE+-]+)s", out).group(1)),
