@@ -97,8 +97,9 @@ int fmmb_plan_create(const fmmb_kernel_desc* kernel, const fmmb_sources* sources
   if (opts.ncrit < 1) { set_error("ncrit must be at least 1"); return FMMB_ERR_INVALID; }
   if (opts.evaluator != FMMB_EVAL_FMM && opts.evaluator != FMMB_EVAL_TREECODE) { set_error("unknown evaluator"); return FMMB_ERR_INVALID; }
   if (opts.evaluator == FMMB_EVAL_TREECODE && kernel->kind != FMMB_LAPLACE_SPHERICAL &&
-      kernel->kind != FMMB_LAPLACE_SPHERICAL_BEM) {
-    set_error("the treecode evaluator (M2P) is built for FMMB_LAPLACE_SPHERICAL and FMMB_LAPLACE_SPHERICAL_BEM plans");
+      kernel->kind != FMMB_LAPLACE_SPHERICAL_BEM && kernel->kind != FMMB_YUKAWA_CARTESIAN_BEM) {
+    set_error("the treecode evaluator (M2P) is built for FMMB_LAPLACE_SPHERICAL, FMMB_LAPLACE_SPHERICAL_BEM and "
+              "FMMB_YUKAWA_CARTESIAN_BEM plans");
     return FMMB_ERR_UNSUPPORTED;
   }
   int ndev = 0;

@@ -241,6 +241,69 @@ yk_table_kernel(int P, double kappa, const double4* __restrict__ vec, double* __
   for (int t = threadIdx.x; t < nt; t += blockDim.x) table[(size_t)blockIdx.x * nt + t] = a[t];
 }
 
+// ---- M2P (treecode evaluator of YukawaCartesianBEM, reference kernel/YukawaCartesianBEM.hpp:298-327): warp per
+// leaf, lane per target panel.  For every source box accepted for the leaf or one of its ancestors the Taylor
+// table a'_n of exp(-kappa R)/R at (panel centre - box centre) is built in the lane's private arrays by the
+// recurrence of yk_coeff_table above (order by order: entries of order s need orders s-1 and s-2), then
+// phi += sum_n a'_n M_n.  Only panels whose BC selects this set are touched; set 0 adds, set 1 subtracts.  The
+// reference's FMM evaluator is broken for this kernel class while its treecode agrees with Direct, so this
+// is the far-field path of BASELINE config 3 that is pinned to the reference.
+template <int SET>
+__global__ void __launch_bounds__(128)
+yk_bem_m2p_kernel(const int* __restrict__ leaves, int nleaves, const unsigned* __restrict__ bb,
+                  const unsigned* __restrict__ be, const unsigned* __restrict__ parent, const int* __restrict__ off,
+                  const int* __restrict__ src, const double4* __restrict__ center, const bem::Panel* __restrict__ pan,
+                  const int* __restrict__ bc, int P, double kappa, const double* __restrict__ M,
+                  double* __restrict__ res) {
+  const int nt = yk_terms(P);
+  const int wl = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int w = blockIdx.x * (blockDim.x >> 5) + wl;
+  if (w >= nleaves) return;
+  const int leaf = leaves[w];
+  double a[kYkMaxT], b[kYkMaxT];
+  for (unsigned i = bb[leaf] + lane; i < be[leaf]; i += 32) {
+    if (bc[i] != SET) continue;
+    const double px = pan[i].c[0], py = pan[i].c[1], pz = pan[i].c[2];
+    double acc = 0;
+    for (int anc = leaf;; anc = (int)parent[anc]) {
+      for (int e = off[anc]; e < off[anc + 1]; ++e) {
+        const int sb = src[e];
+        const double4 c = center[sb];
+        const double xv[3] = {px - c.x, py - c.y, pz - c.z};
+        const double R2 = xv[0] * xv[0] + xv[1] * xv[1] + xv[2] * xv[2], R = sqrt(R2), R2_1 = 1.0 / R2;
+        b[0] = exp(-kappa * R);
+        a[0] = b[0] / R;
+        for (int s = 1; s <= P; ++s)
+          for (int i0 = 0; i0 <= s; ++i0)
+            for (int j0 = 0; j0 <= s - i0; ++j0) {
+              const int n[3] = {i0, j0, s - i0 - j0};
+              const int t = yk_idx(P, n[0], n[1], n[2]);
+              double xa = 0, xb = 0, a2 = 0, b2 = 0;
+#pragma unroll
+              for (int d = 0; d < 3; ++d) {
+                if (n[d] >= 1) {
+                  const int q = yk_idx(P, n[0] - (d == 0), n[1] - (d == 1), n[2] - (d == 2));
+                  xa += xv[d] * a[q]; xb += xv[d] * b[q];
+                }
+                if (n[d] >= 2) {
+                  const int q = yk_idx(P, n[0] - 2 * (d == 0), n[1] - 2 * (d == 1), n[2] - 2 * (d == 2));
+                  a2 += a[q]; b2 += b[q];
+                }
+              }
+              b[t] = -kappa / s * (xa + a2);
+              a[t] = R2_1 / s * (-kappa * (xb + b2) - (2 * s - 1) * xa - (s - 1) * a2);
+            }
+        const double* Ms = M + (size_t)sb * nt;
+        double v = 0;
+        for (int t = 0; t < nt; ++t) v += a[t] * Ms[t] * (c_yfact[c_yI[P][t]] * c_yfact[c_yJ[P][t]] * c_yfact[c_yK[P][t]]);
+        acc += v;
+      }
+      if (anc == 0) break;
+    }
+    res[i] += SET == 0 ? acc : -acc;
+  }
+}
+
 __global__ void yk_slot_class_kernel(int n_items, const int* __restrict__ item_class, const int* __restrict__ item_start,
                                      const int* __restrict__ item_count, const int* __restrict__ sorted_slot,
                                      int* __restrict__ slot_class) {
@@ -568,6 +631,10 @@ void yk_translations(fmmb_plan* plan, YukawaData* d, int P, const double* table,
     ++plan->launches;
   }
   if (!plan->capturing) FMMB_CUDA(cudaEventRecord(ev[2], s));
+  if (plan->opts.evaluator == FMMB_EVAL_TREECODE) {       // treecode: multipoles only, M2P does the rest
+    if (!plan->capturing) FMMB_CUDA(cudaEventRecord(ev[3], s));
+    return;
+  }
   yk_m2l_kernel<<<nb, 128, 0, s>>>(nb, T.m2l_off.p, T.m2l_src.p, table ? d->slot_class.p : nullptr, table, T.center.p, P,
                                   d->kappa, d->M.p, d->L.p);
   ++plan->launches;
@@ -678,7 +745,8 @@ void yukawa_bem_execute(fmmb_plan* plan, const double* d_charges, double* d_resu
   d->M.resize((size_t)T.nboxes * nt);
   d->L.resize((size_t)T.nboxes * nt);
   plan->launches = 0;
-  const double* table = plan->near_only ? nullptr : yk_class_tables(plan, d, P, s);
+  const double* table = (plan->near_only || plan->opts.evaluator == FMMB_EVAL_TREECODE) ? nullptr
+                                                                                        : yk_class_tables(plan, d, P, s);
   if (!plan->capturing) FMMB_CUDA(cudaEventRecord(ev[0], s));
   FMMB_CUDA(cudaEventRecord(ev[1], s));
   if (!plan->capturing) FMMB_CUDA(cudaEventRecord(ev[6], s));
@@ -698,7 +766,17 @@ void yukawa_bem_execute(fmmb_plan* plan, const double* d_charges, double* d_resu
                                                                   T.body.p, bem_panels(B), bem_bc(B), rule, P, d->M.p);
     ++plan->launches;
     yk_translations(plan, d, P, table, s);
-    if (T.n_own_leaves) {
+    if (T.n_own_leaves && plan->opts.evaluator == FMMB_EVAL_TREECODE) {
+      if (set == 0)
+        yk_bem_m2p_kernel<0><<<nblk(T.n_own_leaves, 4), 128, 0, s>>>(
+            T.own_leaves.p, T.n_own_leaves, T.bbegin.p, T.bend.p, T.parent.p, T.m2l_off.p, T.m2l_src.p, T.center.p,
+            bem_panels(B), bem_bc(B), P, d->kappa, d->M.p, bem_res_far(B));
+      else
+        yk_bem_m2p_kernel<1><<<nblk(T.n_own_leaves, 4), 128, 0, s>>>(
+            T.own_leaves.p, T.n_own_leaves, T.bbegin.p, T.bend.p, T.parent.p, T.m2l_off.p, T.m2l_src.p, T.center.p,
+            bem_panels(B), bem_bc(B), P, d->kappa, d->M.p, bem_res_far(B));
+      ++plan->launches;
+    } else if (T.n_own_leaves) {
       if (set == 0)
         yk_bem_l2p_kernel<0><<<nblk(T.n_own_leaves, 4), 128, sh_l2p, s>>>(T.own_leaves.p, T.n_own_leaves, T.bbegin.p, T.bend.p,
                                                                          T.center.p, T.has_local.p, bem_panels(B), bem_bc(B),

@@ -26,6 +26,7 @@
 #include <algorithm>
 
 #define cudaMemcpyToSymbol(dst, src, n) (std::memcpy((void*)(dst), (src), (n)), cudaSuccess)
+#define cudaGetDevice(p) (*(p) = 0, cudaSuccess)
 
 namespace emu {
 struct Idx { unsigned x = 0, y = 0, z = 0; };

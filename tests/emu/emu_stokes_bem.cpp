@@ -9,6 +9,8 @@
 //                  stokes_l2p_kernel at the panel centres; prints the largest relative differences
 //   m2p            bem_m2p_kernel<0|1> (treecode of LaplaceSphericalBEM, csrc/bem.cu) against m2p_kernel of
 //                  csrc/laplace.cu (hardware-verified) on a toy tree with random multipoles
+//   ykm2p          yk_bem_m2p_kernel<0|1> (treecode of YukawaCartesianBEM, csrc/yukawa.cu) against yk_table_kernel
+//                  (the table builder of the hardware-verified M2L) + a host dot product
 #include "cuda_emu.hpp"
 #include "../../fmm_bem_relaxed_b200/csrc/common.cuh"
 #include "../../fmm_bem_relaxed_b200/csrc/laplace_ops.cuh"
@@ -27,6 +29,11 @@ namespace emu_m2p {            // treecode: the point kernel of csrc/laplace.cu 
 using namespace ops;
 #include "lap_m2p.inc"
 #include "bem_m2p.inc"
+}
+namespace emu_yk {             // YukawaCartesian[BEM] kernels of csrc/yukawa.cu
+const bem::Panel* bem_panels(const BemData* b);
+const int* bem_bc(const BemData* b);
+#include "yukawa_kernels.inc"
 }
 }  // namespace fmmb
 #undef asm
@@ -258,10 +265,77 @@ static int run_m2p() {
   return 0;
 }
 
+// ---- Yukawa BEM treecode: yk_bem_m2p_kernel<SET> (lane-private Taylor tables) against yk_table_kernel (the block-
+// cooperative table builder behind the hardware-verified M2L) + a host dot product with the multipoles --------------
+static int run_ykm2p() {
+  using namespace emu_yk;
+  upload_tables();
+  std::mt19937_64 rng(21);
+  std::uniform_real_distribution<double> U(0., 1.);
+  const int nb = 5;
+  std::vector<unsigned> parent = {0, 0, 0, 1, 1}, bb = {0, 0, 40, 0, 17}, be = {57, 40, 57, 17, 40};
+  std::vector<int> leaves = {2, 3, 4};
+  std::vector<int> off = {0, 0, 2, 5, 6, 9}, src = {2, 4, 1, 3, 4, 2, 2, 1, 3};
+  std::vector<double4> center(nb);
+  for (int b = 0; b < nb; ++b) center[b] = make_double4(0.7 * b, -1.0 + 0.5 * b, 0.4 * b, 1.0);
+  const int n = 57;
+  std::vector<bem::Panel> pan(n);
+  std::vector<int> bc(n);
+  for (int i = 0; i < n; ++i) {
+    double c[3] = {6 + U(rng), 5 + U(rng), 4 + U(rng)}, v[9];
+    for (int k = 0; k < 9; ++k) v[k] = c[k % 3] + 0.04 * (U(rng) - 0.5);
+    bem::make_panel(v, v + 3, v + 6, pan[i]);
+    bc[i] = i % 2;
+  }
+  auto leaf_of = [&](int i) { for (int l : leaves) if ((unsigned)i >= bb[l] && (unsigned)i < be[l]) return l; return -1; };
+  double worst = 0, biggest = 0;
+  const double kappa = 0.35;
+  for (int P : {1, 4, 8, 10}) {
+    const int nt = yk_terms(P);
+    std::vector<double> M((size_t)nb * nt);
+    for (auto& x : M) x = U(rng) - 0.5;
+    // expected: one table per (target, accepted box)
+    std::vector<double4> vec;
+    std::vector<int> pair_t, pair_b;
+    for (int i = 0; i < n; ++i)
+      for (int a = leaf_of(i);; a = (int)parent[a]) {
+        for (int e = off[a]; e < off[a + 1]; ++e) {
+          const double4 c = center[src[e]];
+          vec.push_back(make_double4(pan[i].c[0] - c.x, pan[i].c[1] - c.y, pan[i].c[2] - c.z, 0));
+          pair_t.push_back(i); pair_b.push_back(src[e]);
+        }
+        if (a == 0) break;
+      }
+    std::vector<double> table(vec.size() * (size_t)nt);
+    emu::launch(dim3((unsigned)vec.size()), dim3(128), [&] { yk_table_kernel(P, kappa, vec.data(), table.data()); });
+    std::vector<double> phi(n, 0.0);
+    for (size_t k = 0; k < vec.size(); ++k) {
+      double v = 0;
+      for (int t = 0; t < nt; ++t) v += table[k * nt + t] * M[(size_t)pair_b[k] * nt + t];
+      phi[pair_t[k]] += v;
+    }
+    for (int set = 0; set < 2; ++set) {
+      std::vector<double> got(n, 0.125), want(n, 0.125);
+      emu::launch(dim3(nblocks(3, 4)), dim3(128), [&] {
+        if (set == 0) yk_bem_m2p_kernel<0>(leaves.data(), 3, bb.data(), be.data(), parent.data(), off.data(), src.data(),
+                                           center.data(), pan.data(), bc.data(), P, kappa, M.data(), got.data());
+        else yk_bem_m2p_kernel<1>(leaves.data(), 3, bb.data(), be.data(), parent.data(), off.data(), src.data(), center.data(),
+                                  pan.data(), bc.data(), P, kappa, M.data(), got.data());
+      });
+      for (int i = 0; i < n; ++i) if (bc[i] == set) want[i] += set == 0 ? phi[i] : -phi[i];
+      for (int i = 0; i < n; ++i) { got[i] -= 0.125; want[i] -= 0.125; biggest = std::max(biggest, std::fabs(want[i])); }
+      worst = std::max(worst, rel_diff(got, want));
+    }
+  }
+  printf("ykm2p: %.3e max_potential %.3e\n", worst, biggest);
+  return 0;
+}
+
 int main(int argc, char** argv) {
+  if (argc >= 2 && !strcmp(argv[1], "ykm2p")) return run_ykm2p();
   if (argc >= 2 && !strcmp(argv[1], "m2p")) return run_m2p();
   if (argc >= 3 && !strcmp(argv[1], "near")) return run_near(argv[2]);
   if (argc >= 2 && !strcmp(argv[1], "far")) return run_far();
-  fprintf(stderr, "usage: emu_stokes_bem near <file> | far | m2p\n");
+  fprintf(stderr, "usage: emu_stokes_bem near <file> | far | m2p | ykm2p\n");
   return 2;
 }

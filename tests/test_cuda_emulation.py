@@ -8,7 +8,8 @@ per-lane arithmetic that will run on the B200 are these very source lines.  Chec
     modes: 1e-13 against the oracle restatement, which is bit-identical to the reference;
   * far field -- sbem_p2m_kernel<0|1> against the point-source kernels of csrc/stokes.cu (green on hardware this round)
     fed with one source per (panel, quadrature point), sbem_l2p_kernel against stokes_l2p_kernel: 1e-13.
-  * treecode -- bem_m2p_kernel<0|1> of csrc/bem.cu against m2p_kernel of csrc/laplace.cu (green on hardware).
+  * treecode -- bem_m2p_kernel<0|1> of csrc/bem.cu against m2p_kernel of csrc/laplace.cu (green on hardware);
+    yk_bem_m2p_kernel<0|1> of csrc/yukawa.cu against yk_table_kernel (green on hardware) + a host dot product.
 This verifies kernel logic, not performance, and does not replace the first run on the device (tests/test_zz_stokes_bem.py).
 """
 import os
@@ -36,6 +37,8 @@ def emu(tmp_path_factory):
     for src, dst, names in (("stokes.cu", "stokes_kernels.inc", []), ("stokes_bem.cu", "sbem_kernels.inc", []),
                             ("laplace.cu", "lap_m2p.inc", ["m2p_kernel"]), ("bem.cu", "bem_m2p.inc", ["bem_m2p_kernel"])):
         subprocess.check_call(["python", os.path.join(EMU, "extract_kernels.py"), os.path.join(CSRC, src), str(d / dst)] + names)
+    subprocess.check_call(["python", os.path.join(EMU, "extract_kernels.py"), os.path.join(CSRC, "yukawa.cu"),
+                           str(d / "yukawa_kernels.inc"), "--until", "const double* yk_class_tables("])
     exe = str(d / "emu_stokes_bem")
     subprocess.check_call(["g++", "-std=c++20", "-O1", "-pthread", "-I", CUDA_INC, "-I", str(d), "-I", EMU,
                            os.path.join(EMU, "emu_stokes_bem.cpp"), "-o", exe, "-L/usr/local/cuda/lib64", "-lcudart"])
@@ -58,6 +61,16 @@ def test_bem_treecode_kernel_matches_the_point_treecode_kernel(emu):
     m = re.search(r"m2p: ([0-9.eE+-]+) max_potential ([0-9.eE+-]+)", out)
     assert m, out
     assert float(m.group(2)) > 1e-3 and float(m.group(1)) <= 1e-13
+
+
+def test_yukawa_bem_treecode_kernel_matches_the_table_builder(emu):
+    """yk_bem_m2p_kernel<0|1> (treecode of YukawaCartesianBEM, csrc/yukawa.cu: Taylor tables in lane-private arrays)
+    against yk_table_kernel -- the block-cooperative builder behind the M2L that is green on hardware -- and a host
+    dot product with the multipoles, orders 1, 4, 8, 10."""
+    out = subprocess.check_output([emu, "ykm2p"], timeout=900).decode()
+    m = re.search(r"ykm2p: ([0-9.eE+-]+) max_potential ([0-9.eE+-]+)", out)
+    assert m, out
+    assert float(m.group(2)) > 1e-4 and float(m.group(1)) <= 1e-12
 
 
 @pytest.mark.parametrize("bcmix,as_written,K", [(0, False, 4), (1, False, 4), (2, False, 3), (0, True, 4), (1, True, 4),

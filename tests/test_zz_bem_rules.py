@@ -3,7 +3,7 @@ keys 13, 19, 25, 79) as panel rules of LaplaceSphericalBEM, against the golden f
 (tests/golden/laplace_bem_2048_*_k13_*.npz, *_k25_*.npz) and the oracle restatement (bit-identical to them,
 tests/test_oracle.py).  The rule tables themselves are pinned on the CPU (tests/test_host_logic.py, kernel 7).
 
-Also here: the treecode evaluator of LaplaceSphericalBEM (`LaplaceBEM -eval TREE`, bem_m2p_kernel in csrc/bem.cu) against
+Also here: the treecode evaluator of YukawaCartesianBEM (yk_bem_m2p_kernel in csrc/yukawa.cu) and of LaplaceSphericalBEM (`LaplaceBEM -eval TREE`, bem_m2p_kernel in csrc/bem.cu) against
 the golden fixtures of `ref_bem -tree` and the oracle (bit-identical to them).
 
 STATUS: like tests/test_zz_stokes_bem.py -- added after round 1's GPU minutes were spent, so collected late and marked
@@ -72,6 +72,25 @@ def test_treecode_mixed_boundary_conditions_and_orders():
     for p in (8, 3, 12):
         plan.kernel().set_p(p)
         assert O.rel_l2(plan.execute(q), orc.execute(q, p, 4, treecode=True)) <= 1e-10
+
+
+@pytest.mark.parametrize("bc", [0, 1])
+def test_yukawa_bem_treecode_golden_fixtures(bc):
+    """BASELINE config 3's kernel class through the evaluator of the reference that works for it: the treecode
+    (tests/golden/yukawa_bem_tree_2048_p6_bc*.npz from oracle/_ref/ref_yukawa_bem -tree; the reference's FMM evaluator
+    returns garbage for this class).  This pins the GPU far field of YukawaCartesianBEM to the reference."""
+    g = dict(np.load(os.path.join(GOLDEN, "yukawa_bem_tree_2048_p6_bc%d.npz" % bc)))
+    opts = F.FMMOptions()
+    opts.set_max_per_box(32)
+    opts.evaluator = F.FMMOptions.TREECODE
+    plan = F.FMM_plan(F.YukawaCartesianBEM(6, 1.0, 4), F.Panels(g["verts"], bc), opts)
+    res = plan.execute(g["charges"])
+    assert O.rel_l2(res, g["results"]) <= 1e-10
+    assert O.rel_l2(res, g["direct"]) < (1e-4 if bc == 0 else 1e-3)
+    # and the FMM evaluator of the engine approximates the same sum
+    opts.evaluator = F.FMMOptions.FMM
+    fmm = F.FMM_plan(F.YukawaCartesianBEM(6, 1.0, 4), F.Panels(g["verts"], bc), opts).execute(g["charges"])
+    assert O.rel_l2(fmm, res) < (2e-4 if bc == 0 else 2e-3)
 
 
 def test_key_5_is_rejected():
