@@ -17,9 +17,10 @@
 //             boundary condition picks; result += r / (2 mu) (VELOCITY) or 0.5 r (TRACTION) -> sbem_l2p_kernel
 //
 // Near-field layout: block dense like csrc/bem.cu -- a work item is <= 32 targets of one leaf against the leaf's
-// whole source list; entry e (row-major in the 3 x 3 block) of (target lane, source j) sits at
-// val[base + (j * 9 + e) * cnt + lane], so the per-matvec kernel streams 72 bytes per pair with coalesced loads
-// (HBM bound).
+// whole source list.  Both layers give SYMMETRIC 3 x 3 blocks (r^2 I + d d' and d d' scaled, the self terms too), so
+// only the upper triangle is kept: entry e of (xx, xy, xz, yy, yz, zz) of (target lane, source j) sits at
+// val[6 base + (j * 6 + e) * cnt + lane]; the per-matvec kernel streams 48 bytes per pair with coalesced loads
+// (HBM bound: 48 B for 18 flop) instead of the 72 B of the reference's Mat3 CSR plus its indices.
 //
 // Reference quirks kept for parity: near-field entries as the reference computes them when
 // compiled (K-point rule for every pair) unless FMMB_FLAG_STOKES_BEM_AS_WRITTEN asks for the branches of its source
@@ -42,7 +43,7 @@ struct StokesBemData {
   DevBuf<bem::Panel> pan;          // tree order
   DevBuf<int> bc;                  // tree order: 0 VELOCITY, 1 TRACTION
   DevBuf<double> chg;              // tree order, 3 per panel
-  DevBuf<double> nf_val;           // cached near field, 9 doubles per pair, block layout (see above)
+  DevBuf<double> nf_val;           // cached near field, 6 doubles per pair (upper triangle), block layout (see above)
   DevBuf<long long> nf_base;       // per work item: offset of its block in PAIRS
   int64_t nnz = 0;                 // pairs
   DevBuf<double> M4[4], L4[4];     // the four expansion sets of the group being evaluated
@@ -91,6 +92,7 @@ __global__ void sbem_count_kernel(const int4* __restrict__ items, int nitems, co
 }
 
 constexpr int kSbemWarps = 4;
+constexpr int kSbemEntries = 6;   // stored entries per 3 x 3 block: xx, xy, xz, yy, yz, zz
 
 // one warp per work item: lane = target, source panels staged through a warp-private tile
 __global__ void __launch_bounds__(32 * kSbemWarps)
@@ -113,7 +115,7 @@ sbem_assemble_kernel(const int4* __restrict__ items, int nitems, const unsigned*
     tc[0] = t.c[0]; tc[1] = t.c[1]; tc[2] = t.c[2];
     tbc = bc[it.y + lane];
   }
-  double* out = val + 9 * base[item];
+  double* out = val + kSbemEntries * base[item];
   long long j = 0;
   for (int e = off[it.x]; e < off[it.x + 1]; ++e) {
     const int sb = src[e];
@@ -127,8 +129,9 @@ sbem_assemble_kernel(const int4* __restrict__ items, int nitems, const unsigned*
         for (int k = 0; k < ns; ++k) {
           double m[9];
           bem::stokes_kernel(tbc, tc, tile[k], c_srule, c_sfine, mu, as_written, m);
+          const double up[kSbemEntries] = {m[0], m[1], m[2], m[4], m[5], m[8]};     // m[3] = m[1], m[6] = m[2], m[7] = m[5]
 #pragma unroll
-          for (int q = 0; q < 9; ++q) out[((j + k) * 9 + q) * cnt + lane] = m[q];
+          for (int q = 0; q < kSbemEntries; ++q) out[((j + k) * kSbemEntries + q) * cnt + lane] = up[q];
         }
       j += ns;
     }
@@ -149,7 +152,7 @@ sbem_near_kernel(const int4* __restrict__ items, int nitems, const unsigned* __r
   const int4 it = items[item];
   const int cnt = it.z;
   const bool act = lane < cnt;
-  const double* in = val + 9 * base[item] + lane;
+  const double* in = val + kSbemEntries * base[item] + lane;
   double u0 = 0, u1 = 0, u2 = 0;
   long long j = 0;
   for (int e = off[it.x]; e < off[it.x + 1]; ++e) {
@@ -163,11 +166,13 @@ sbem_near_kernel(const int4* __restrict__ items, int nitems, const unsigned* __r
       if (act) {
 #pragma unroll 2
         for (int k = 0; k < ns; ++k) {
-          const double* a = in + (j + k) * 9 * cnt;
+          const double* a = in + (j + k) * kSbemEntries * cnt;
           const double f0 = tile[3 * k], f1 = tile[3 * k + 1], f2 = tile[3 * k + 2];
-          u0 = fma(a[0], f0, fma(a[(size_t)cnt], f1, fma(a[2 * (size_t)cnt], f2, u0)));
-          u1 = fma(a[3 * (size_t)cnt], f0, fma(a[4 * (size_t)cnt], f1, fma(a[5 * (size_t)cnt], f2, u1)));
-          u2 = fma(a[6 * (size_t)cnt], f0, fma(a[7 * (size_t)cnt], f1, fma(a[8 * (size_t)cnt], f2, u2)));
+          const double xx = a[0], xy = a[(size_t)cnt], xz = a[2 * (size_t)cnt], yy = a[3 * (size_t)cnt],
+                       yz = a[4 * (size_t)cnt], zz = a[5 * (size_t)cnt];
+          u0 = fma(xx, f0, fma(xy, f1, fma(xz, f2, u0)));
+          u1 = fma(xy, f0, fma(yy, f1, fma(yz, f2, u1)));
+          u2 = fma(xz, f0, fma(yz, f1, fma(zz, f2, u2)));
         }
       }
       j += ns;
@@ -391,7 +396,7 @@ void stokes_bem_setup(fmmb_plan* plan, const double* verts_host, const int32_t* 
   for (int i = 0; i < ni; ++i) off[i + 1] = off[i] + h[i];
   B->nnz = off[ni];
   B->nf_base.from_host(off.data(), off.size(), s);
-  B->nf_val.resize(9 * (size_t)B->nnz);
+  B->nf_val.resize(kSbemEntries * (size_t)B->nnz);
   if (ni)
     sbem_assemble_kernel<<<nblk(ni, kSbemWarps), 32 * kSbemWarps, 0, s>>>(T.p2p_items.p, ni, T.bbegin.p, T.bend.p,
                                                                          T.p2p_off.p, T.p2p_src.p, B->pan.p, B->bc.p,
@@ -423,7 +428,7 @@ void stokes_bem_execute(fmmb_plan* plan, const double* d_charges, double* d_resu
   ++plan->launches;
   FMMB_CUDA(cudaEventRecord(ev[1], s));
 
-  // cached near field (one pass over 72 bytes per pair)
+  // cached near field (one pass over 48 bytes per pair)
   if (!plan->capturing) FMMB_CUDA(cudaEventRecord(ev[6], s));
   const int ni = T.n_p2p_items;
   if (ni) {

@@ -19,7 +19,7 @@ grep -E "iterations|Fx|solve|setup|matvec vs" gpurun_out/stokes_bem_drivers.log 
 ( cd gpurun_out && timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv \
     --log-file launches_stokes_bem.csv ../fmm_bem_relaxed_b200/hostcxx/bin/stokes_bem -recursions 7 -p 8 -k 4 -solver_tol 1e-5 \
     > ncu_stokes_bem.log 2>&1 )
-# 4. one full capture of the per-matvec near-field kernel (HBM bound: 72 B per pair)
+# 4. one full capture of the per-matvec near-field kernel (HBM bound: 48 B per pair)
 ( cd gpurun_out && timeout 600 ncu --set full --clock-control none --import-source on -k regex:sbem_near_kernel -c 1 \
     -o prof_sbem_near ../fmm_bem_relaxed_b200/hostcxx/bin/stokes_bem -recursions 7 -p 8 -k 4 -solver_tol 1e-5 \
     > ncu_sbem_near.log 2>&1 )

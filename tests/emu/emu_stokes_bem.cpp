@@ -84,7 +84,7 @@ static int run_near(const char* path) {
   std::vector<long long> cnt(ni + 1), base(ni + 1, 0);
   emu::launch(dim3(nblocks(ni + 1, 128)), dim3(128), [&] { sbem_count_kernel(items, (int)ni, bb, be, off, src, cnt.data()); });
   for (long i = 0; i < ni; ++i) base[i + 1] = base[i] + cnt[i];
-  std::vector<double> val(9 * (size_t)base[ni], -7.0), chg(3 * n), res(3 * n, -7.0);
+  std::vector<double> val(kSbemEntries * (size_t)base[ni], -7.0), chg(3 * n), res(3 * n, -7.0);
   emu::launch(dim3(nblocks(ni, kSbemWarps)), dim3(32 * kSbemWarps), [&] {
     sbem_assemble_kernel(items, (int)ni, bb, be, off, src, pan.data(), bct.data(), base.data(), mu, as_written != 0, val.data());
   });
