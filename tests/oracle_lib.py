@@ -292,3 +292,25 @@ def yukawa_direct(spts, q, tpts, kappa, threads=None):
 
 def rel_l2(a, b):
     return float(np.linalg.norm(np.asarray(a) - np.asarray(b)) / np.linalg.norm(np.asarray(b)))
+
+
+def coverage_counts(tree, n):
+    """UnitKernel idea of the reference's tests/correctness.cpp (:58-78) on a set of lists: for every leaf, the number of
+    sources it sees through its near-field list plus the far-field lists of itself and all its ancestors.  A correct
+    traversal counts every source exactly once, i.e. returns n for every leaf ("Wrong counts: 0")."""
+    boxes = tree["boxes"].astype(np.int64)
+    nb = len(boxes)
+    count = boxes[:, 5] - boxes[:, 4]
+    lr = tree["lr"].astype(np.int64)
+    far = np.bincount(lr[:, 1], weights=count[lr[:, 0]], minlength=nb).astype(np.int64) if len(lr) else np.zeros(nb, np.int64)
+    parent = boxes[:, 1]
+    level = boxes[:, 6]
+    for l in range(1, int(level.max()) + 1):           # parents precede children: accumulate level by level
+        idx = np.nonzero(level == l)[0]
+        far[idx] += far[parent[idx]]
+    off = tree["p2p_off"].astype(np.int64)
+    tgt = np.repeat(np.arange(nb), np.diff(off))
+    near = np.bincount(tgt, weights=count[tree["p2p_idx"].astype(np.int64)], minlength=nb).astype(np.int64)
+    leaves = np.nonzero(boxes[:, 7])[0]
+    assert count[leaves].sum() == n
+    return near[leaves] + far[leaves]

@@ -285,3 +285,18 @@ def test_laplace_bem_treecode_restatement_matches_reference_bitwise(bc):
     assert np.array_equal(res, g["results"])
     assert O.rel_l2(res, g["direct"]) < 2e-4
     assert not np.array_equal(res, orc.execute(g["charges"], m["P"], m["K"], threads=1))     # not the FMM path
+
+
+@pytest.mark.parametrize("n,ncrit,theta", [(5000, 16, 0.5), (20000, 64, 0.5), (3000, 8, 0.8)])
+def test_every_source_is_counted_exactly_once(n, ncrit, theta):
+    """The reference's tests/correctness.cpp (UnitKernel; N = 5 000, ncrit = 16: "Wrong counts: 0") as a property of the
+    lists: near-field list + far-field lists of a leaf and its ancestors cover all n sources exactly once."""
+    pts, _ = O.drand48_inputs(n)
+    t = O.Oracle(pts, ncrit, theta).tree()
+    c = O.coverage_counts(t, n)
+    assert len(c) > 10 and (c == n).all()
+    # strongly adaptive cloud
+    rng = np.random.default_rng(n)
+    p2 = rng.random((n, 3))
+    p2[n // 2:] = 0.3 + 0.04 * rng.random((n - n // 2, 3))
+    assert (O.coverage_counts(O.Oracle(p2, ncrit, theta).tree(), n) == n).all()

@@ -43,3 +43,14 @@ def test_c5_counts_accuracy_and_checksums():
     assert np.array_equal(plan.execute(q), res)
     lhs = plan.execute(-2.5 * q)
     assert O.rel_l2(lhs, -2.5 * res) <= 1e-13
+
+
+@pytest.mark.parametrize("n", [1_000_000, 10_000_000])
+def test_device_lists_count_every_source_exactly_once(n):
+    """The reference's tests/correctness.cpp (UnitKernel, "Wrong counts: 0") as a property of the DEVICE-built lists at
+    the metric size and at the C5 size: near-field list + far-field lists of a leaf and its ancestors cover all n
+    sources exactly once (host arithmetic on fmmb_plan_get_tree)."""
+    pts, _ = O.drand48_inputs(n)
+    plan = F.FMM_plan(F.LaplaceSpherical(8), pts)
+    c = O.coverage_counts(plan.tree(), n)
+    assert len(c) == plan.info().n_leaves and (c == n).all()
