@@ -11,6 +11,7 @@
 //   :190-196, :293-307  M2M / M2L / L2L on each of the 4 sets               -> laplace_translations() per set
 //   :318-401  L2P: u_s += c (phi_s - x_s d_k phi_k ... ) i.e. per set s the potential (s < 3) and the Cartesian
 //             gradient times -x_s (s < 3) or 1 (s = 3); c = 1 (Stokeslet) or 1/6 (stresslet) -> stokes_l2p_kernel
+//   :207-291  M2P (treecode evaluator): the same on the singular harmonics                -> stokes_m2p_kernel
 // x is the ABSOLUTE body position (not relative to the box centre), exactly as in the reference.
 //
 // The stresslet path corresponds to the reference compiled with -DSTRESSLET and the two compile fixes listed in
@@ -195,6 +196,81 @@ stokes_l2p_kernel(const int* __restrict__ leaves, int nleaves, const unsigned* _
     res[3 * (size_t)i + 0] = scale * (pot[0] + u[0]);
     res[3 * (size_t)i + 1] = scale * (pot[1] + u[1]);
     res[3 * (size_t)i + 2] = scale * (pot[2] + u[2]);
+  }
+}
+
+// ---- M2P (treecode, FMMOptions::TREECODE; StokesSpherical.hpp:207-291): warp per leaf, lane per body; every source
+// box accepted for the leaf or one of its ancestors is evaluated at the bodies -- the L2P arithmetic on the singular
+// harmonics (radial factor -(n+1)/r), converted to Cartesian per source box.  Fixed order, no atomics.
+__global__ void __launch_bounds__(128)
+stokes_m2p_kernel(const int* __restrict__ leaves, int nleaves, const unsigned* __restrict__ bb,
+                  const unsigned* __restrict__ be, const unsigned* __restrict__ parent, const int* __restrict__ off,
+                  const int* __restrict__ srcbox, const double4* __restrict__ center, const double4* __restrict__ body,
+                  int P, const double* __restrict__ M0, const double* __restrict__ M1, const double* __restrict__ M2,
+                  const double* __restrict__ M3, double scale, double* __restrict__ res) {
+  extern __shared__ double2 stk_ms[];
+  const int nc = P * (P + 1) / 2;
+  const int wl = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int w = blockIdx.x * (blockDim.x >> 5) + wl;
+  if (w >= nleaves) return;
+  double2* Ms = stk_ms + (size_t)wl * 4 * nc;
+  const int leaf = leaves[w];
+  const unsigned b0 = bb[leaf], b1 = be[leaf];
+  for (unsigned base = b0; base < b1; base += 32) {
+    const unsigned i = base + lane;
+    const bool act = i < b1;
+    const double4 p = act ? body[i] : make_double4(0, 0, 0, 0);
+    const double xs_[3] = {p.x, p.y, p.z};
+    double u[3] = {0, 0, 0};
+    for (int a = leaf;; a = (int)parent[a]) {
+      for (int e = off[a]; e < off[a + 1]; ++e) {
+        const int sb = srcbox[e];
+        __syncwarp();
+        for (int k = lane; k < 4 * nc; k += 32) {
+          const int set = k / nc, c = k - set * nc;
+          int n, m;
+          unpack_nm(c, n, m);
+          const double* M = set == 0 ? M0 : (set == 1 ? M1 : (set == 2 ? M2 : M3));
+          Ms[k] = load_coef(M + (size_t)sb * xstride(P), n, m);
+        }
+        __syncwarp();
+        if (act) {
+          const double4 c = center[sb];
+          const Sph s = to_sph(p.x - c.x, p.y - c.y, p.z - c.z);
+          const double inv_r = 1.0 / s.r;
+          double pot[4] = {0, 0, 0, 0}, ga[4] = {0, 0, 0, 0}, gb[4] = {0, 0, 0, 0}, gc[4] = {0, 0, 0, 0};
+          regular_harmonics<true, true>(P, s, 1.0, [&](int n, int m, double yr, double yi, double tr, double ti) {
+            const double w2 = m == 0 ? 1.0 : 2.0;
+            const int q = n * (n + 1) / 2 + m;
+#pragma unroll
+            for (int set = 0; set < 4; ++set) {
+              const double2 l = Ms[set * nc + q];
+              const double re = w2 * (l.x * yr - l.y * yi);     // Re(M Y)
+              pot[set] += re;
+              ga[set] -= re * inv_r * (n + 1);
+              gb[set] += w2 * (l.x * tr - l.y * ti);            // Re(M Ytheta)
+              gc[set] -= w2 * (l.x * yi + l.y * yr) * m;        // Re(M Y i) m
+            }
+          });
+          const double inv_ry = inv_r / s.y;
+#pragma unroll
+          for (int set = 0; set < 4; ++set) {
+            const double cx = s.y * s.cp * ga[set] + s.x * s.cp * inv_r * gb[set] - s.sp * inv_ry * gc[set];
+            const double cy = s.y * s.sp * ga[set] + s.x * s.sp * inv_r * gb[set] + s.cp * inv_ry * gc[set];
+            const double cz = s.x * ga[set] - s.y * inv_r * gb[set];
+            const double f = set < 3 ? -xs_[set < 3 ? set : 0] : 1.0;
+            u[0] += f * cx; u[1] += f * cy; u[2] += f * cz;
+          }
+          u[0] += pot[0]; u[1] += pot[1]; u[2] += pot[2];
+        }
+      }
+      if (a == 0) break;
+    }
+    if (act) {
+      res[3 * (size_t)i + 0] = scale * u[0];
+      res[3 * (size_t)i + 1] = scale * u[1];
+      res[3 * (size_t)i + 2] = scale * u[2];
+    }
   }
 }
 
@@ -405,7 +481,11 @@ void stokes_execute(fmmb_plan* plan, const double* d_charges, double* d_results)
     SetGuard g(plan, d, k);
     laplace_translations(plan, s);
   }
-  if (T.n_own_leaves)
+  if (T.n_own_leaves && plan->opts.evaluator == FMMB_EVAL_TREECODE)      // the translations stopped after the upward pass
+    stokes_m2p_kernel<<<nblk(T.n_own_leaves, 4), 128, (size_t)4 * 4 * nc * sizeof(double2), s>>>(
+        T.own_leaves.p, T.n_own_leaves, T.bbegin.p, T.bend.p, T.parent.p, T.m2l_off.p, T.m2l_src.p, T.center.p, T.body.p, P,
+        d->M4[0].p, d->M4[1].p, d->M4[2].p, d->M4[3].p, d->stresslet ? 1.0 / 6 : 1.0, d->res_far.p);
+  else if (T.n_own_leaves)
   stokes_l2p_kernel<<<nblk(T.n_own_leaves, 4), 128, (size_t)4 * 4 * nc * sizeof(double2), s>>>(
       T.own_leaves.p, T.n_own_leaves, T.bbegin.p, T.bend.p, T.center.p, T.has_local.p, T.body.p, P, d->L4[0].p,
       d->L4[1].p, d->L4[2].p, d->L4[3].p, d->stresslet ? 1.0 / 6 : 1.0, d->res_far.p);

@@ -15,6 +15,7 @@
 //   :468-472, :494-506  M2M / M2L / L2L of each set                         -> laplace_translations() per set
 //   :508-527  L2P: r = StokesSpherical::L2P (kernel/StokesSpherical.hpp:318-401, scale 1) of the group the TARGET's
 //             boundary condition picks; result += r / (2 mu) (VELOCITY) or 0.5 r (TRACTION) -> sbem_l2p_kernel
+//   :474-492  M2P (treecode evaluator, `StokesBEM -eval TREE`), same scaling                -> sbem_m2p_kernel
 //
 // Near-field layout: block dense like csrc/bem.cu -- a work item is <= 32 targets of one leaf against the leaf's
 // whole source list.  Both layers give SYMMETRIC 3 x 3 blocks (r^2 I + d d' and d d' scaled, the self terms too), so
@@ -345,6 +346,83 @@ sbem_l2p_kernel(const int* __restrict__ leaves, int nleaves, const unsigned* __r
   }
 }
 
+// ---- M2P (treecode, `StokesBEM -eval TREE`; :474-492 over StokesSpherical.hpp:207-291): warp per leaf, lane per
+// target panel; every source box accepted for the leaf or one of its ancestors is evaluated at the centres of the
+// panels whose boundary condition selects GROUP -- the L2P arithmetic on the singular harmonics (radial factor
+// -(n+1)/r), converted to Cartesian per source box.  res is zeroed before the first group.
+__global__ void __launch_bounds__(128)
+sbem_m2p_kernel(const int* __restrict__ leaves, int nleaves, const unsigned* __restrict__ bb,
+                const unsigned* __restrict__ be, const unsigned* __restrict__ parent, const int* __restrict__ off,
+                const int* __restrict__ srcbox, const double4* __restrict__ center, const bem::Panel* __restrict__ pan,
+                const int* __restrict__ bc, int group, int P, const double* __restrict__ M0,
+                const double* __restrict__ M1, const double* __restrict__ M2, const double* __restrict__ M3,
+                double scale, double* __restrict__ res) {
+  extern __shared__ double2 sbem_ms[];
+  const int nc = P * (P + 1) / 2;
+  const int wl = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int w = blockIdx.x * (blockDim.x >> 5) + wl;
+  if (w >= nleaves) return;
+  double2* Ms = sbem_ms + (size_t)wl * 4 * nc;
+  const int leaf = leaves[w];
+  const unsigned b0 = bb[leaf], b1 = be[leaf];
+  for (unsigned base = b0; base < b1; base += 32) {
+    const unsigned i = base + lane;
+    const bool act = i < b1 && bc[i] == group;
+    double xs_[3] = {0, 0, 0};
+    if (act) { xs_[0] = pan[i].c[0]; xs_[1] = pan[i].c[1]; xs_[2] = pan[i].c[2]; }
+    double u[3] = {0, 0, 0};
+    for (int a = leaf;; a = (int)parent[a]) {
+      for (int e = off[a]; e < off[a + 1]; ++e) {
+        const int sb = srcbox[e];
+        __syncwarp();
+        for (int k = lane; k < 4 * nc; k += 32) {
+          const int set = k / nc, c = k - set * nc;
+          int n, m;
+          unpack_nm(c, n, m);
+          const double* M = set == 0 ? M0 : (set == 1 ? M1 : (set == 2 ? M2 : M3));
+          Ms[k] = load_coef(M + (size_t)sb * xstride(P), n, m);
+        }
+        __syncwarp();
+        if (act) {
+          const double4 c = center[sb];
+          const Sph s = to_sph(xs_[0] - c.x, xs_[1] - c.y, xs_[2] - c.z);
+          const double inv_r = 1.0 / s.r;
+          double pot[4] = {0, 0, 0, 0}, ga[4] = {0, 0, 0, 0}, gb[4] = {0, 0, 0, 0}, gc[4] = {0, 0, 0, 0};
+          regular_harmonics<true, true>(P, s, 1.0, [&](int n, int m, double yr, double yi, double tr, double ti) {
+            const double w2 = m == 0 ? 1.0 : 2.0;
+            const int q = n * (n + 1) / 2 + m;
+#pragma unroll
+            for (int set = 0; set < 4; ++set) {
+              const double2 l = Ms[set * nc + q];
+              const double re = w2 * (l.x * yr - l.y * yi);     // Re(M Y)
+              pot[set] += re;
+              ga[set] -= re * inv_r * (n + 1);
+              gb[set] += w2 * (l.x * tr - l.y * ti);            // Re(M Ytheta)
+              gc[set] -= w2 * (l.x * yi + l.y * yr) * m;        // Re(M Y i) m
+            }
+          });
+          const double inv_ry = inv_r / s.y;
+#pragma unroll
+          for (int set = 0; set < 4; ++set) {
+            const double cx = s.y * s.cp * ga[set] + s.x * s.cp * inv_r * gb[set] - s.sp * inv_ry * gc[set];
+            const double cy = s.y * s.sp * ga[set] + s.x * s.sp * inv_r * gb[set] + s.cp * inv_ry * gc[set];
+            const double cz = s.x * ga[set] - s.y * inv_r * gb[set];
+            const double f = set < 3 ? -xs_[set < 3 ? set : 0] : 1.0;
+            u[0] += f * cx; u[1] += f * cy; u[2] += f * cz;
+          }
+          u[0] += pot[0]; u[1] += pot[1]; u[2] += pot[2];
+        }
+      }
+      if (a == 0) break;
+    }
+    if (act) {
+      res[3 * (size_t)i + 0] = scale * u[0];
+      res[3 * (size_t)i + 1] = scale * u[1];
+      res[3 * (size_t)i + 2] = scale * u[2];
+    }
+  }
+}
+
 void swap_buf(DevBuf<double>& a, DevBuf<double>& b) {
   std::swap(a.p, b.p); std::swap(a.cap, b.cap); std::swap(a.n, b.n);
 }
@@ -466,7 +544,11 @@ void stokes_bem_execute(fmmb_plan* plan, const double* d_charges, double* d_resu
     }
     // VELOCITY: result += r / (2 mu);  TRACTION: result += 0.5 r  (:508-527)
     const double scale = group == 0 ? 1. / 2 / B->mu : 0.5;
-    if (T.n_own_leaves)
+    if (T.n_own_leaves && plan->opts.evaluator == FMMB_EVAL_TREECODE)    // the translations stopped after the upward pass
+      sbem_m2p_kernel<<<nblk(T.n_own_leaves, 4), 128, (size_t)4 * 4 * nc * sizeof(double2), s>>>(
+          T.own_leaves.p, T.n_own_leaves, T.bbegin.p, T.bend.p, T.parent.p, T.m2l_off.p, T.m2l_src.p, T.center.p, B->pan.p,
+          B->bc.p, group, P, B->M4[0].p, B->M4[1].p, B->M4[2].p, B->M4[3].p, scale, B->res_far.p);
+    else if (T.n_own_leaves)
       sbem_l2p_kernel<<<nblk(T.n_own_leaves, 4), 128, (size_t)4 * 4 * nc * sizeof(double2), s>>>(
           T.own_leaves.p, T.n_own_leaves, T.bbegin.p, T.bend.p, T.center.p, T.has_local.p, B->pan.p, B->bc.p, group, P,
           B->L4[0].p, B->L4[1].p, B->L4[2].p, B->L4[3].p, scale, B->res_far.p);

@@ -44,7 +44,7 @@ static void dump(const std::string& path, const std::vector<T>& v) {
 }
 
 int main(int argc, char** argv) {
-  int N = 10000, P = 8, ndirect = 0, reps = 1;
+  int N = 10000, P = 8, ndirect = 0, reps = 1, tree = 0;
   unsigned ncrit = 64;
   double theta = 0.5;
   std::string dump_prefix, in_file;
@@ -57,6 +57,7 @@ int main(int argc, char** argv) {
     else if (!strcmp(argv[i], "-reps")) reps = atoi(argv[++i]);
     else if (!strcmp(argv[i], "-in")) in_file = argv[++i];
     else if (!strcmp(argv[i], "-dump")) dump_prefix = argv[++i];
+    else if (!strcmp(argv[i], "-tree")) tree = 1;
     else { fprintf(stderr, "unknown arg %s\n", argv[i]); return 2; }
   }
   std::vector<point_type> points(N);
@@ -83,6 +84,7 @@ int main(int argc, char** argv) {
   FMMOptions opts;
   opts.set_mac_theta(theta);
   opts.set_max_per_box(ncrit);
+  if (tree) opts.evaluator = FMMOptions::TREECODE;     // -tree: M2P instead of M2L / L2L / L2P
   double t0 = get_time();
   FMM_plan<kernel_type> plan(K, points, opts);
   double t_plan = get_time() - t0;

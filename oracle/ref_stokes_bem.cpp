@@ -7,7 +7,7 @@
 // plan.execute(charges).  Dumps panels, boundary conditions, charges, results and optionally Direct::matvec.
 // Build: oracle/Makefile (g++ -fno-access-control, oracle/boost_shim).
 //   ref_stokes_bem -recursions 4 -P 8 -K 4 -kfine 19 -mu 1e-3 -ncrit 64 -theta 0.5 -bc 0 [-rand] [-sparse 1]
-//                  [-direct] [-in file -n N] -dump prefix
+//                  [-tree] [-direct] [-in file -n N] -dump prefix
 // -selftest: prints K(t, t) (the Fata analytical self term of the single layer, examples/BEM/FataAnalytical.hpp:
 //   414-713 through eval_velocity_integral, kernel/StokesSphericalBEM.hpp:264-275) for the first 64 panels.
 #include <cmath>
@@ -47,7 +47,7 @@ static std::vector<double> flat(const std::vector<result_type>& v) {
 }
 
 int main(int argc, char** argv) {
-  int recursions = 4, P = 8, K = 4, kfine = 19, bc = 0, rnd = 0, sparse = 1, direct = 0, n_in = 0, reps = 1, selftest = 0;
+  int recursions = 4, P = 8, K = 4, kfine = 19, bc = 0, rnd = 0, sparse = 1, direct = 0, n_in = 0, reps = 1, selftest = 0, tree = 0;
   unsigned ncrit = 64;
   double theta = 0.5, mu = 1e-3;
   std::string dump_prefix, in_file;
@@ -64,6 +64,7 @@ int main(int argc, char** argv) {
     else if (!strcmp(argv[i], "-sparse")) sparse = atoi(argv[++i]);
     else if (!strcmp(argv[i], "-direct")) direct = 1;
     else if (!strcmp(argv[i], "-selftest")) selftest = 1;
+    else if (!strcmp(argv[i], "-tree")) tree = 1;
     else if (!strcmp(argv[i], "-reps")) reps = atoi(argv[++i]);
     else if (!strcmp(argv[i], "-in")) in_file = argv[++i];
     else if (!strcmp(argv[i], "-n")) n_in = atoi(argv[++i]);
@@ -104,6 +105,7 @@ int main(int argc, char** argv) {
   opts.set_mac_theta(theta);
   opts.set_max_per_box(ncrit);
   opts.sparse_local = sparse != 0;
+  if (tree) opts.evaluator = FMMOptions::TREECODE;     // -tree (`StokesBEM -eval TREE`): M2P instead of M2L / L2L / L2P
   double t0 = get_time();
   FMM_plan<kernel_type> plan(Kn, panels, opts);
   double t_plan = get_time() - t0;

@@ -9,6 +9,8 @@
 //                  stokes_l2p_kernel at the panel centres; prints the largest relative differences
 //   m2p            bem_m2p_kernel<0|1> (treecode of LaplaceSphericalBEM, csrc/bem.cu) against m2p_kernel of
 //                  csrc/laplace.cu (hardware-verified) on a toy tree with random multipoles
+//   stokes_m2p     stokes_m2p_kernel (csrc/stokes.cu) and sbem_m2p_kernel (csrc/stokes_bem.cu), the treecode evaluators of
+//                  the Stokes classes, against four runs of m2p_kernel combined on the host
 //   ykm2p          yk_bem_m2p_kernel<0|1> (treecode of YukawaCartesianBEM, csrc/yukawa.cu) against yk_table_kernel
 //                  (the table builder of the hardware-verified M2L) + a host dot product
 #include "cuda_emu.hpp"
@@ -265,6 +267,79 @@ static int run_m2p() {
   return 0;
 }
 
+// ---- Stokes treecode: stokes_m2p_kernel (csrc/stokes.cu) and sbem_m2p_kernel (csrc/stokes_bem.cu) against four runs
+// of the Laplace point treecode kernel m2p_kernel (csrc/laplace.cu, hardware-verified) -- one per expansion set, its
+// potential and Cartesian gradient combined on the host as StokesSpherical.hpp:207-291 prescribes:
+//   u_k = scale ( pot_k + sum_{s<3} (-x_s) grad_s[k] + grad_3[k] )
+static int run_stokes_m2p() {
+  upload_laplace_tables();
+  std::mt19937_64 rng(17);
+  std::uniform_real_distribution<double> U(0., 1.);
+  const int nb = 5;
+  std::vector<unsigned> parent = {0, 0, 0, 1, 1}, bb = {0, 0, 70, 0, 33}, be = {103, 70, 103, 33, 70};
+  std::vector<int> leaves = {2, 3, 4};
+  std::vector<int> off = {0, 0, 2, 5, 6, 9}, src = {2, 4, 1, 3, 4, 2, 2, 1, 3};
+  std::vector<double4> center(nb);
+  for (int b = 0; b < nb; ++b) center[b] = make_double4(3.0 * b, -2.0 + b, 1.5 * b, 1.0);
+  const int n = 103;
+  std::vector<bem::Panel> pan(n);
+  std::vector<int> bc(n);
+  std::vector<double4> body(n);
+  for (int i = 0; i < n; ++i) {
+    double c[3] = {20 + U(rng), 20 + U(rng), 20 + U(rng)}, v[9];
+    for (int k = 0; k < 9; ++k) v[k] = c[k % 3] + 0.04 * (U(rng) - 0.5);
+    bem::make_panel(v, v + 3, v + 6, pan[i]);
+    bc[i] = (i % 3 == 1) ? 1 : 0;
+    body[i] = make_double4(pan[i].c[0], pan[i].c[1], pan[i].c[2], 0.0);
+  }
+  double worst_pt = 0, worst_bem = 0, biggest = 0;
+  for (int P : {2, 8, 13}) {
+    const int xs = ops::xstride(P), nc = P * (P + 1) / 2;
+    std::vector<double> M[4];
+    std::vector<double4> lap[4];
+    for (int s4 = 0; s4 < 4; ++s4) {
+      M[s4].resize((size_t)nb * xs);
+      for (auto& x : M[s4]) x = U(rng) - 0.5;
+      lap[s4].assign(n, make_double4(0, 0, 0, 0));
+      emu::launch(dim3(nblocks(3, 4)), dim3(128), [&] {
+        emu_m2p::m2p_kernel(leaves.data(), 3, bb.data(), be.data(), parent.data(), off.data(), src.data(), center.data(),
+                            body.data(), P, M[s4].data(), lap[s4].data());
+      });
+    }
+    const double scale = 1. / 6;
+    std::vector<double> want(3 * n);
+    for (int i = 0; i < n; ++i) {
+      const double x[3] = {body[i].x, body[i].y, body[i].z};
+      const double g[4][3] = {{lap[0][i].y, lap[0][i].z, lap[0][i].w}, {lap[1][i].y, lap[1][i].z, lap[1][i].w},
+                              {lap[2][i].y, lap[2][i].z, lap[2][i].w}, {lap[3][i].y, lap[3][i].z, lap[3][i].w}};
+      const double pot[3] = {lap[0][i].x, lap[1][i].x, lap[2][i].x};
+      for (int k = 0; k < 3; ++k)
+        want[3 * i + k] = scale * (pot[k] - x[0] * g[0][k] - x[1] * g[1][k] - x[2] * g[2][k] + g[3][k]);
+    }
+    for (double x : want) biggest = std::max(biggest, std::fabs(x));
+    if ((size_t)4 * 4 * nc * sizeof(double2) > sizeof emu::dyn_shared) return 4;
+    std::vector<double> got(3 * n, -3.0);
+    emu::launch(dim3(nblocks(3, 4)), dim3(128), [&] {
+      emu_stokes::stokes_m2p_kernel(leaves.data(), 3, bb.data(), be.data(), parent.data(), off.data(), src.data(),
+                                    center.data(), body.data(), P, M[0].data(), M[1].data(), M[2].data(), M[3].data(), scale,
+                                    got.data());
+    });
+    worst_pt = std::max(worst_pt, rel_diff(got, want));
+    for (int group = 0; group < 2; ++group) {
+      std::vector<double> gb(3 * n, 0.0), wb(3 * n, 0.0);
+      emu::launch(dim3(nblocks(3, 4)), dim3(128), [&] {
+        emu_sbem::sbem_m2p_kernel(leaves.data(), 3, bb.data(), be.data(), parent.data(), off.data(), src.data(), center.data(),
+                                  pan.data(), bc.data(), group, P, M[0].data(), M[1].data(), M[2].data(), M[3].data(), scale,
+                                  gb.data());
+      });
+      for (int i = 0; i < n; ++i) if (bc[i] == group) for (int k = 0; k < 3; ++k) wb[3 * i + k] = want[3 * i + k];
+      worst_bem = std::max(worst_bem, rel_diff(gb, wb));
+    }
+  }
+  printf("stokes_m2p: point %.3e bem %.3e max_velocity %.3e\n", worst_pt, worst_bem, biggest);
+  return 0;
+}
+
 // ---- Yukawa BEM treecode: yk_bem_m2p_kernel<SET> (lane-private Taylor tables) against yk_table_kernel (the block-
 // cooperative table builder behind the hardware-verified M2L) + a host dot product with the multipoles --------------
 static int run_ykm2p() {
@@ -333,9 +408,10 @@ static int run_ykm2p() {
 
 int main(int argc, char** argv) {
   if (argc >= 2 && !strcmp(argv[1], "ykm2p")) return run_ykm2p();
+  if (argc >= 2 && !strcmp(argv[1], "stokes_m2p")) return run_stokes_m2p();
   if (argc >= 2 && !strcmp(argv[1], "m2p")) return run_m2p();
   if (argc >= 3 && !strcmp(argv[1], "near")) return run_near(argv[2]);
   if (argc >= 2 && !strcmp(argv[1], "far")) return run_far();
-  fprintf(stderr, "usage: emu_stokes_bem near <file> | far | m2p | ykm2p\n");
+  fprintf(stderr, "usage: emu_stokes_bem near <file> | far | m2p | ykm2p | stokes_m2p\n");
   return 2;
 }

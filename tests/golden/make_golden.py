@@ -83,12 +83,14 @@ def treecode_case(name, n, p, ncrit, theta, points=None, charges=None):
         print(name, meta["pot"], "err vs direct", meta["err_pot"], meta["err_force"])
 
 
-def stokes_case(name, stresslet, n, p, ncrit, theta, points=None, charges=None, direct=300):
+def stokes_case(name, stresslet, n, p, ncrit, theta, points=None, charges=None, direct=300, tree=False):
     """StokesSpherical through oracle/_ref/ref_stokeslet (unmodified reference) or ref_stresslet (the
     reference with the two compile patches of SURVEY.md section 8(c)); stores inputs, results, checksums."""
     exe = os.path.join(ROOT, "oracle", "_ref", "ref_stresslet" if stresslet else "ref_stokeslet")
     with tempfile.TemporaryDirectory() as tmp:
         cmd = [exe, "-N", str(n), "-P", str(p), "-ncrit", str(ncrit), "-theta", repr(theta), "-direct", str(direct)]
+        if tree:
+            cmd.append("-tree")
         if points is not None:
             infile = os.path.join(tmp, "in.f64")
             np.concatenate([points.ravel(), charges.ravel()]).tofile(infile)
@@ -142,17 +144,19 @@ def yukawa_bem_case(name, recursions, p, k, kappa, ncrit, bc):
         print(name, "treecode vs direct", meta["err_vs_direct"])
 
 
-def stokes_bem_case(name, exe, recursions, p, k, kfine, mu, ncrit, bc):
+def stokes_bem_case(name, exe, recursions, p, k, kfine, mu, ncrit, bc, tree=False):
     """StokesSphericalBEM through oracle/_ref/ref_stokes_bem_asis (the unmodified reference) or oracle/_ref/ref_stokes_bem
     (the reference with the dangling `auto dist` of kernel/StokesSphericalBEM.hpp:162,262 materialised, oracle/Makefile):
     FMM matvec with the sparse near field (examples/StokesBEM.cpp:126) and Direct::matvec, random Vec<3> charges."""
     with tempfile.TemporaryDirectory() as tmp:
         pre = os.path.join(tmp, "d")
         cmd = [os.path.join(ROOT, "oracle", "_ref", exe), "-recursions", str(recursions), "-P", str(p), "-K", str(k),
-               "-kfine", str(kfine), "-mu", repr(mu), "-ncrit", str(ncrit), "-bc", str(bc), "-rand", "-direct", "-dump", pre]
+               "-kfine", str(kfine), "-mu", repr(mu), "-ncrit", str(ncrit), "-bc", str(bc), "-rand", "-direct", "-dump", pre] + \
+              (["-tree"] if tree else [])
         out = subprocess.check_output(cmd, env=dict(os.environ, OMP_NUM_THREADS="1"), cwd=tmp).decode()
         meta = json.loads([l for l in out.splitlines() if l.startswith("REF_JSON")][0][len("REF_JSON "):])
         meta["as_written"] = 0 if exe.endswith("asis") else 1
+        meta["treecode"] = int(tree)
         np.savez_compressed(os.path.join(HERE, name + ".npz"), meta=json.dumps(meta),
                             verts=np.fromfile(pre + ".verts.f64").reshape(-1, 3, 3),
                             bc=np.fromfile(pre + ".bc.f64").astype(np.int32),
@@ -179,6 +183,14 @@ def laplace_bem_case(name, recursions, p, k, ncrit, bc, tree=False):
 
 
 def main():
+    if "--stokes-tree" in sys.argv:
+        # FMMOptions::TREECODE for the Stokes classes: Stokeslet (unmodified reference), stresslet (patched),
+        # StokesSphericalBEM as compiled (`StokesBEM -eval TREE`)
+        stokes_case("stokeslet_tree_n3000_p5", False, 3000, 5, 32, 0.5, tree=True)
+        stokes_case("stresslet_tree_n3000_p6", True, 3000, 6, 32, 0.5, tree=True)
+        for bc in (0, 2):
+            stokes_bem_case("stokes_bem_tree_asis_2048_p6_bc%d" % bc, "ref_stokes_bem_asis", 5, 6, 4, 19, 1e-3, 40, bc, tree=True)
+        return
     if "--laplace-bem-tree" in sys.argv:
         # `LaplaceBEM -eval TREE`: FMMOptions::TREECODE with the sparse near field
         for bc in (0, 1):

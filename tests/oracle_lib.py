@@ -47,7 +47,7 @@ def load():
         L.fmmo_get_expansions.argtypes = [vp, vp, vp]
         L.fmmo_laplace_direct.argtypes = [ctypes.c_int, vp, vp, ctypes.c_int, vp, vp, ctypes.c_int]
         L.fmmo_drand48_inputs.argtypes = [ctypes.c_int, vp, vp]
-        L.fmmo_stokes_execute.argtypes = [vp, ctypes.c_int, ctypes.c_int, vp, vp, ctypes.c_int]
+        L.fmmo_stokes_execute.argtypes = [vp, ctypes.c_int, ctypes.c_int, vp, vp, ctypes.c_int, ctypes.c_int]
         L.fmmo_stokes_direct.argtypes = [ctypes.c_int, vp, ctypes.c_int, vp, ctypes.c_int, vp, vp, ctypes.c_int]
         L.fmmo_yukawa_execute.argtypes = [vp, ctypes.c_int, ctypes.c_double, vp, vp, ctypes.c_int]
         L.fmmo_yukawa_direct.argtypes = [ctypes.c_int, vp, ctypes.c_double, vp, ctypes.c_int, vp, vp, ctypes.c_int]
@@ -59,7 +59,7 @@ def load():
         L.fmmo_bem_execute.argtypes = [vp, ctypes.c_int, ctypes.c_int, vp, vp, vp, vp, ctypes.c_int, ctypes.c_int]
         L.fmmo_bem_direct.argtypes = [ctypes.c_int, ctypes.c_int, vp, vp, vp, vp, ctypes.c_int]
         L.fmmo_stokes_bem_execute.argtypes = [vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_double, ctypes.c_int,
-                                              vp, vp, vp, vp, ctypes.c_int]
+                                              vp, vp, vp, vp, ctypes.c_int, ctypes.c_int]
         L.fmmo_stokes_bem_direct.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_double, ctypes.c_int,
                                              vp, vp, vp, vp, ctypes.c_int]
         L.fmmo_stokes_bem_entries.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_double, ctypes.c_int,
@@ -129,12 +129,13 @@ class Oracle:
         self.P = P
         return res
 
-    def stokes_execute(self, charges, P, stresslet, threads=None):
+    def stokes_execute(self, charges, P, stresslet, threads=None, treecode=False):
         """StokesSpherical matvec: charges (n, 3) Stokeslet or (n, 6) stresslet (g, n); results (n, 3)."""
         cd = 6 if stresslet else 3
         q = np.ascontiguousarray(np.asarray(charges, dtype=np.float64).reshape(-1, cd))
         res = np.zeros((self.n, 3))
-        rc = self.L.fmmo_stokes_execute(self.h, P, int(bool(stresslet)), _p(q), _p(res), threads or os.cpu_count() or 1)
+        rc = self.L.fmmo_stokes_execute(self.h, P, int(bool(stresslet)), _p(q), _p(res), 2 if treecode else 0,
+                                        threads or os.cpu_count() or 1)
         if rc != 0:
             raise RuntimeError("oracle stokes execute failed: %d" % rc)
         return res
@@ -231,11 +232,12 @@ class StokesBemOracle(BemOracle):
         super().__init__(verts, bc, ncrit, theta)
         self.mu, self.K, self.kfine, self.as_written = float(mu), int(K), int(kfine), int(bool(as_written))
 
-    def execute(self, charges, P, threads=None):
+    def execute(self, charges, P, threads=None, treecode=False):
         q = np.ascontiguousarray(np.asarray(charges, dtype=np.float64).reshape(-1))
         res = np.zeros((self.n, 3))
         rc = self.L.fmmo_stokes_bem_execute(self.h, P, self.K, self.kfine, self.mu, self.as_written, _p(self.verts),
-                                            _p(self.bc), _p(q), _p(res), threads or os.cpu_count() or 1)
+                                            _p(self.bc), _p(q), _p(res), 2 if treecode else 0,
+                                            threads or os.cpu_count() or 1)
         if rc != 0:
             raise RuntimeError("oracle Stokes BEM execute failed: %d" % rc)
         return res

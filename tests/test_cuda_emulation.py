@@ -9,7 +9,8 @@ per-lane arithmetic that will run on the B200 are these very source lines.  Chec
   * far field -- sbem_p2m_kernel<0|1> against the point-source kernels of csrc/stokes.cu (green on hardware this round)
     fed with one source per (panel, quadrature point), sbem_l2p_kernel against stokes_l2p_kernel: 1e-13.
   * treecode -- bem_m2p_kernel<0|1> of csrc/bem.cu against m2p_kernel of csrc/laplace.cu (green on hardware);
-    yk_bem_m2p_kernel<0|1> of csrc/yukawa.cu against yk_table_kernel (green on hardware) + a host dot product.
+    yk_bem_m2p_kernel<0|1> of csrc/yukawa.cu against yk_table_kernel (green on hardware) + a host dot product;
+    stokes_m2p_kernel / sbem_m2p_kernel against four runs of m2p_kernel combined on the host.
 This verifies kernel logic, not performance, and does not replace the first run on the device (tests/test_zz_stokes_bem.py).
 """
 import os
@@ -61,6 +62,16 @@ def test_bem_treecode_kernel_matches_the_point_treecode_kernel(emu):
     m = re.search(r"m2p: ([0-9.eE+-]+) max_potential ([0-9.eE+-]+)", out)
     assert m, out
     assert float(m.group(2)) > 1e-3 and float(m.group(1)) <= 1e-13
+
+
+def test_stokes_treecode_kernels_match_the_point_treecode_kernel(emu):
+    """stokes_m2p_kernel (StokesSpherical, csrc/stokes.cu) and sbem_m2p_kernel (StokesSphericalBEM, csrc/stokes_bem.cu)
+    against four runs of m2p_kernel of csrc/laplace.cu (green on hardware), one per expansion set, combined on the host
+    as StokesSpherical.hpp:207-291 prescribes."""
+    out = subprocess.check_output([emu, "stokes_m2p"], timeout=900).decode()
+    m = re.search(r"stokes_m2p: point ([0-9.eE+-]+) bem ([0-9.eE+-]+) max_velocity ([0-9.eE+-]+)", out)
+    assert m, out
+    assert float(m.group(3)) > 1e-3 and float(m.group(1)) <= 1e-12 and float(m.group(2)) <= 1e-12
 
 
 def test_yukawa_bem_treecode_kernel_matches_the_table_builder(emu):

@@ -300,3 +300,24 @@ def test_every_source_is_counted_exactly_once(n, ncrit, theta):
     p2 = rng.random((n, 3))
     p2[n // 2:] = 0.3 + 0.04 * rng.random((n - n // 2, 3))
     assert (O.coverage_counts(O.Oracle(p2, ncrit, theta).tree(), n) == n).all()
+
+
+# ---- treecode evaluator of the Stokes classes (FMMOptions::TREECODE, `-eval TREE`), bit for bit -----------------------
+@pytest.mark.parametrize("name,stresslet", [("stokeslet_tree_n3000_p5", False), ("stresslet_tree_n3000_p6", True)])
+def test_stokes_treecode_restatement_matches_reference_bitwise(name, stresslet):
+    g = dict(np.load(os.path.join(GOLDEN, name + ".npz")))
+    m = _meta(g)
+    orc = O.Oracle(g["points"], m["ncrit"], m["theta"])
+    res = orc.stokes_execute(g["charges"], m["P"], stresslet, threads=1, treecode=True)
+    assert np.array_equal(res, g["results"])
+    assert not np.array_equal(res, orc.stokes_execute(g["charges"], m["P"], stresslet, threads=1))
+
+
+@pytest.mark.parametrize("bc", [0, 2])
+def test_stokes_bem_treecode_restatement_matches_reference_bitwise(bc):
+    g = dict(np.load(os.path.join(GOLDEN, "stokes_bem_tree_asis_2048_p6_bc%d.npz" % bc)))
+    m = _meta(g)
+    assert m["treecode"] == 1 and m["as_written"] == 0
+    orc = O.StokesBemOracle(g["verts"], g["bc"], mu=m["mu"], K=m["K"], kfine=m["kfine"], as_written=False, ncrit=m["ncrit"],
+                            theta=m["theta"])
+    assert np.array_equal(orc.execute(g["charges"], m["P"], threads=1, treecode=True), g["results"])

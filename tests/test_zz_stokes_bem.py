@@ -192,3 +192,36 @@ def test_tiny_meshes(rec, ncrit):
         orc = O.StokesBemOracle(verts, bc, K=3, kfine=13, ncrit=ncrit)
         got = make_plan(verts, bc, 4, K=3, kfine=13, ncrit=ncrit).execute(q)
         assert O.rel_l2(got, orc.execute(q, 4)) <= TOL
+
+
+# ---- treecode evaluator (`-eval TREE`) of the Stokes classes: stokes_m2p_kernel, sbem_m2p_kernel -------------------
+@pytest.mark.parametrize("bc", [0, 2])
+def test_treecode_golden_fixtures(bc):
+    g = dict(np.load(os.path.join(GOLDEN, "stokes_bem_tree_asis_2048_p6_bc%d.npz" % bc)))
+    m = json.loads(str(g["meta"]))
+    opts = F.FMMOptions()
+    opts.set_max_per_box(m["ncrit"])
+    opts.evaluator = F.FMMOptions.TREECODE
+    plan = F.FMM_plan(F.StokesSphericalBEM(m["P"], m["K"], m["mu"], m["kfine"]), F.Panels(g["verts"], g["bc"]), opts)
+    res = plan.execute(g["charges"])
+    for k in range(3):
+        assert O.rel_l2(res[:, k], g["results"][:, k]) <= TOL
+
+
+@pytest.mark.parametrize("name,stresslet", [("stokeslet_tree_n3000_p5", False), ("stresslet_tree_n3000_p6", True)])
+def test_point_kernel_treecode_golden_fixtures(name, stresslet):
+    """StokesSpherical (Stokeslet / stresslet) with FMMOptions::TREECODE against ref_stokeslet / ref_stresslet -tree."""
+    g = dict(np.load(os.path.join(GOLDEN, name + ".npz")))
+    m = json.loads(str(g["meta"]))
+    opts = F.FMMOptions()
+    opts.set_max_per_box(m["ncrit"])
+    opts.set_mac_theta(m["theta"])
+    opts.evaluator = F.FMMOptions.TREECODE
+    plan = F.FMM_plan(F.StokesSpherical(m["P"], stresslet), g["points"], opts)
+    res = plan.execute(g["charges"])
+    for k in range(3):
+        assert O.rel_l2(res[:, k], g["results"][:, k]) <= TOL
+    orc = O.Oracle(g["points"], m["ncrit"], m["theta"])
+    for p in (3, 9):                                   # order changes, also above the batched-translation limit
+        plan.kernel().set_p(p)
+        assert O.rel_l2(plan.execute(g["charges"]), orc.stokes_execute(g["charges"], p, stresslet, treecode=True)) <= TOL
