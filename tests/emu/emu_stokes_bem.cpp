@@ -11,6 +11,8 @@
 //                  csrc/laplace.cu (hardware-verified) on a toy tree with random multipoles
 //   stokes_m2p     stokes_m2p_kernel (csrc/stokes.cu) and sbem_m2p_kernel (csrc/stokes_bem.cu), the treecode evaluators of
 //                  the Stokes classes, against four runs of m2p_kernel combined on the host
+//   bem_rules      bem_p2m_kernel<0|1> (csrc/bem.cu) with the 13-, 19-, 25- and 79-point rules against the sum of its
+//                  own one-point-rule runs (the K = 1 path is hardware-verified)
 //   ykm2p          yk_bem_m2p_kernel<0|1> (treecode of YukawaCartesianBEM, csrc/yukawa.cu) against yk_table_kernel
 //                  (the table builder of the hardware-verified M2L) + a host dot product
 #include "cuda_emu.hpp"
@@ -31,6 +33,9 @@ namespace emu_m2p {            // treecode: the point kernel of csrc/laplace.cu 
 using namespace ops;
 #include "lap_m2p.inc"
 #include "bem_m2p.inc"
+}
+namespace emu_bem {            // LaplaceSphericalBEM kernels of csrc/bem.cu
+#include "bem_kernels.inc"
 }
 namespace emu_yk {             // YukawaCartesian[BEM] kernels of csrc/yukawa.cu
 const bem::Panel* bem_panels(const BemData* b);
@@ -267,6 +272,64 @@ static int run_m2p() {
   return 0;
 }
 
+// ---- Gauss rules above 4 points in the LaplaceSphericalBEM P2M: bem_p2m_kernel<SET> with the K-point rule against the
+// sum of K runs of the same kernel with the one-point rules (pt_k, w_k) -- the one-point path is the K = 1 rule that is
+// green on hardware; what is new with K = 13, 19, 25, 79 is the (panel, quadrature point) -> lane mapping.
+static int run_bem_rules() {
+  upload_laplace_tables();
+  std::mt19937_64 rng(29);
+  std::uniform_real_distribution<double> U(0., 1.);
+  const int nleaf = 2, sizes[nleaf] = {41, 7};
+  std::vector<unsigned> bb(nleaf), be(nleaf);
+  std::vector<double4> center(nleaf);
+  std::vector<int> leaves = {0, 1};
+  int n = 0;
+  for (int b = 0; b < nleaf; ++b) { bb[b] = n; n += sizes[b]; be[b] = n; center[b] = make_double4(0.5 + b, 0.5, 0.25 * b, 1.0); }
+  std::vector<bem::Panel> pan(n);
+  std::vector<int> bc(n);
+  std::vector<double4> body(n);
+  for (int b = 0; b < nleaf; ++b)
+    for (unsigned i = bb[b]; i < be[b]; ++i) {
+      double c[3] = {center[b].x - 0.45 + 0.9 * U(rng), center[b].y - 0.45 + 0.9 * U(rng), center[b].z - 0.45 + 0.9 * U(rng)}, v[9];
+      for (int k = 0; k < 9; ++k) v[k] = c[k % 3] + 0.04 * (U(rng) - 0.5);
+      bem::make_panel(v, v + 3, v + 6, pan[i]);
+      bc[i] = i % 2;
+      body[i] = make_double4(pan[i].c[0], pan[i].c[1], pan[i].c[2], U(rng) - 0.3);     // .w = charge
+    }
+  double worst = 0, biggest = 0;
+  for (int P : {4, 8})
+    for (int key : {13, 19, 25, 79}) {
+      const bem::Rule rule = bem::make_rule(key);
+      const int xs = ops::xstride(P), pp = P * P, warps = pp <= 64 ? 4 : 1;
+      for (int set = 0; set < 2; ++set) {
+        auto run = [&](const bem::Rule& r, std::vector<double>& M) {
+          emu_bem::c_rule = r;
+          M.assign((size_t)nleaf * xs, 0.0);
+          emu::launch(dim3(nblocks(nleaf, warps)), dim3(32 * warps), [&] {
+            if (set == 0) emu_bem::bem_p2m_kernel<0>(leaves.data(), nleaf, bb.data(), be.data(), center.data(), body.data(),
+                                                     pan.data(), bc.data(), P, M.data());
+            else emu_bem::bem_p2m_kernel<1>(leaves.data(), nleaf, bb.data(), be.data(), center.data(), body.data(), pan.data(),
+                                            bc.data(), P, M.data());
+          });
+        };
+        std::vector<double> got, part, want((size_t)nleaf * xs, 0.0);
+        run(rule, got);
+        for (int k = 0; k < rule.n; ++k) {
+          bem::Rule one = {};
+          one.n = 1;
+          for (int c = 0; c < 3; ++c) one.pt[0][c] = rule.pt[k][c];
+          one.w[0] = rule.w[k];
+          run(one, part);
+          for (size_t t = 0; t < want.size(); ++t) want[t] += part[t];
+        }
+        for (double x : want) biggest = std::max(biggest, std::fabs(x));
+        worst = std::max(worst, rel_diff(got, want));
+      }
+    }
+  printf("bem_rules: %.3e max_multipole %.3e\n", worst, biggest);
+  return 0;
+}
+
 // ---- Stokes treecode: stokes_m2p_kernel (csrc/stokes.cu) and sbem_m2p_kernel (csrc/stokes_bem.cu) against four runs
 // of the Laplace point treecode kernel m2p_kernel (csrc/laplace.cu, hardware-verified) -- one per expansion set, its
 // potential and Cartesian gradient combined on the host as StokesSpherical.hpp:207-291 prescribes:
@@ -408,10 +471,11 @@ static int run_ykm2p() {
 
 int main(int argc, char** argv) {
   if (argc >= 2 && !strcmp(argv[1], "ykm2p")) return run_ykm2p();
+  if (argc >= 2 && !strcmp(argv[1], "bem_rules")) return run_bem_rules();
   if (argc >= 2 && !strcmp(argv[1], "stokes_m2p")) return run_stokes_m2p();
   if (argc >= 2 && !strcmp(argv[1], "m2p")) return run_m2p();
   if (argc >= 3 && !strcmp(argv[1], "near")) return run_near(argv[2]);
   if (argc >= 2 && !strcmp(argv[1], "far")) return run_far();
-  fprintf(stderr, "usage: emu_stokes_bem near <file> | far | m2p | ykm2p | stokes_m2p\n");
+  fprintf(stderr, "usage: emu_stokes_bem near <file> | far | m2p | ykm2p | stokes_m2p | bem_rules\n");
   return 2;
 }

@@ -36,7 +36,8 @@ pytestmark = pytest.mark.skipif(not os.path.exists(os.path.join(CUDA_INC, "cuda_
 def emu(tmp_path_factory):
     d = tmp_path_factory.mktemp("emu")
     for src, dst, names in (("stokes.cu", "stokes_kernels.inc", []), ("stokes_bem.cu", "sbem_kernels.inc", []),
-                            ("laplace.cu", "lap_m2p.inc", ["m2p_kernel"]), ("bem.cu", "bem_m2p.inc", ["bem_m2p_kernel"])):
+                            ("laplace.cu", "lap_m2p.inc", ["m2p_kernel"]), ("bem.cu", "bem_m2p.inc", ["bem_m2p_kernel"]),
+                            ("bem.cu", "bem_kernels.inc", [])):
         subprocess.check_call(["python", os.path.join(EMU, "extract_kernels.py"), os.path.join(CSRC, src), str(d / dst)] + names)
     subprocess.check_call(["python", os.path.join(EMU, "extract_kernels.py"), os.path.join(CSRC, "yukawa.cu"),
                            str(d / "yukawa_kernels.inc"), "--until", "const double* yk_class_tables("])
@@ -62,6 +63,15 @@ def test_bem_treecode_kernel_matches_the_point_treecode_kernel(emu):
     m = re.search(r"m2p: ([0-9.eE+-]+) max_potential ([0-9.eE+-]+)", out)
     assert m, out
     assert float(m.group(2)) > 1e-3 and float(m.group(1)) <= 1e-13
+
+
+def test_bem_p2m_with_the_higher_gauss_rules(emu):
+    """bem_p2m_kernel<0|1> with the 13-, 19-, 25- and 79-point rules of the reference's table equals the sum of its own
+    runs with the one-point rules (pt_k, w_k): the (panel, quadrature point) -> lane mapping for K > 4."""
+    out = subprocess.check_output([emu, "bem_rules"], timeout=900).decode()
+    m = re.search(r"bem_rules: ([0-9.eE+-]+) max_multipole ([0-9.eE+-]+)", out)
+    assert m, out
+    assert float(m.group(2)) > 1e-4 and float(m.group(1)) <= 1e-12
 
 
 def test_stokes_treecode_kernels_match_the_point_treecode_kernel(emu):
