@@ -153,9 +153,9 @@ sbem_near_kernel(const int4* __restrict__ items, int nitems, const unsigned* __r
   const int4 it = items[item];
   const int cnt = it.z;
   const bool act = lane < cnt;
-  const double* in = val + kSbemEntries * base[item] + lane;
+  const double* a = val + kSbemEntries * base[item] + lane;      // walks the block: one pair = 6 rows of cnt doubles
+  const size_t cs = (size_t)cnt;
   double u0 = 0, u1 = 0, u2 = 0;
-  long long j = 0;
   for (int e = off[it.x]; e < off[it.x + 1]; ++e) {
     const int sb = src[e];
     const unsigned c0 = bb[sb], c1 = be[sb];
@@ -167,16 +167,14 @@ sbem_near_kernel(const int4* __restrict__ items, int nitems, const unsigned* __r
       if (act) {
 #pragma unroll 2
         for (int k = 0; k < ns; ++k) {
-          const double* a = in + (j + k) * kSbemEntries * cnt;
           const double f0 = tile[3 * k], f1 = tile[3 * k + 1], f2 = tile[3 * k + 2];
-          const double xx = a[0], xy = a[(size_t)cnt], xz = a[2 * (size_t)cnt], yy = a[3 * (size_t)cnt],
-                       yz = a[4 * (size_t)cnt], zz = a[5 * (size_t)cnt];
+          const double xx = a[0], xy = a[cs], xz = a[2 * cs], yy = a[3 * cs], yz = a[4 * cs], zz = a[5 * cs];
+          a += kSbemEntries * cs;
           u0 = fma(xx, f0, fma(xy, f1, fma(xz, f2, u0)));
           u1 = fma(xy, f0, fma(yy, f1, fma(yz, f2, u1)));
           u2 = fma(xz, f0, fma(yz, f1, fma(zz, f2, u2)));
         }
       }
-      j += ns;
     }
   }
   if (act) {
