@@ -456,7 +456,11 @@ def bench_ours(args, rank, world, local_rank):
     except Exception:
         pass
     roofline = {
-        "kernel": dominant, "bound": "fp64", "achieved": dk["achieved"], "peak": fp64_peak, "unit": "TFLOP/s",
+        # "tensor": the contract's name for a compute roofline.  Here that is the FP64 pipe: DFMA and the FP64 tensor
+        # instruction DMMA.8x8x4 share ONE pipe on sm_100a (scripts/micro/dual_pipe.cu), and the peak is the measured
+        # DMMA rate, the higher of the two -- for the DFMA-bound near-field kernel as well as for the DMMA GEMM.
+        "kernel": dominant, "bound": "tensor", "bound_detail": "fp64 pipe (DFMA / DMMA.8x8x4)",
+        "achieved": dk["achieved"], "peak": fp64_peak, "unit": "TFLOP/s",
         "frac": dk["achieved"] / fp64_peak, "traffic": traffic,
         "peak_source": "measured in this process by fmmb_measure_fp64_peak: DFMA %.1f, DMMA.8x8x4 %.1f TFLOP/s "
                        "(MEASURED_PEAKS.json has no FP64 entry)" % (pk_fma.value, pk_mma.value),
