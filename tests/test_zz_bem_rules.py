@@ -19,7 +19,7 @@ import oracle_lib as O
 import fmm_bem_relaxed_b200 as F
 from conftest import GOLDEN
 
-pytestmark = [pytest.mark.gpu,
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(900),
               pytest.mark.xfail(strict=False, reason="Gauss rules above 4 points not yet run on hardware (round 1 GPU "
                                                      "budget spent before they were added)")]
 

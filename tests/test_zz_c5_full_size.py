@@ -15,7 +15,7 @@ import pytest
 import oracle_lib as O
 import fmm_bem_relaxed_b200 as F
 
-pytestmark = [pytest.mark.gpu,
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(900),
               pytest.mark.xfail(strict=False, reason="N = 10M not yet run on hardware (round 1 GPU budget spent)")]
 
 

@@ -23,7 +23,7 @@ import oracle_lib as O
 import fmm_bem_relaxed_b200 as F
 from conftest import GOLDEN, ROOT
 
-pytestmark = [pytest.mark.gpu,
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(900),
               pytest.mark.xfail(strict=False, reason="StokesSphericalBEM kernels not yet run on hardware (round 1 GPU "
                                                      "budget spent before they were written)")]
 
