@@ -384,6 +384,13 @@ class Direct:
     @staticmethod
     def matvec(plan, charges, targets):
         q = np.ascontiguousarray(np.asarray(charges, dtype=np.float64).reshape(-1))
+        if isinstance(targets, Panels):                 # BEM kernel classes: K(target panel, source panel)
+            nt = len(targets)
+            out = np.empty((nt, plan._rdim) if plan._rdim > 1 else (nt,))
+            bc = np.ascontiguousarray(targets.bc, np.int32)
+            capi.check(plan._lib.fmmb_plan_direct_panels(plan._h, capi.ptr(q), nt, capi.ptr(targets.vertices), capi.ptr(bc),
+                                                         capi.ptr(out)))
+            return out
         t = np.ascontiguousarray(np.asarray(targets, dtype=np.float64).reshape(-1, 3))
         out = np.empty((t.shape[0], plan._rdim))
         capi.check(plan._lib.fmmb_plan_direct(plan._h, capi.ptr(q), t.shape[0], capi.ptr(t), capi.ptr(out)))

@@ -72,7 +72,7 @@ class PlanInfo(ctypes.Structure):
 EXPORTS = [
     "fmmb_plan_create", "fmmb_plan_set_p", "fmmb_plan_execute", "fmmb_plan_execute_device",
     "fmmb_plan_execute_sharded", "fmmb_gmres", "fmmb_plan_peer_export", "fmmb_plan_peer_init",
-    "fmmb_plan_direct", "fmmb_plan_set_option", "fmmb_plan_sync", "fmmb_comm_unique_id", "fmmb_plan_comm_init",
+    "fmmb_plan_direct", "fmmb_plan_direct_panels", "fmmb_plan_set_option", "fmmb_plan_sync", "fmmb_comm_unique_id", "fmmb_plan_comm_init",
     "fmmb_partition_ranges", "fmmb_plan_stream", "fmmb_plan_get_info", "fmmb_plan_get_tree",
     "fmmb_plan_get_expansions", "fmmb_plan_phase_times", "fmmb_plan_destroy", "fmmb_last_error",
     "fmmb_version", "fmmb_measure_fp64_peak",
@@ -101,6 +101,7 @@ def load():
     lib.fmmb_plan_peer_export.argtypes = [vp, dp]
     lib.fmmb_plan_peer_init.argtypes = [vp, dp]
     lib.fmmb_plan_direct.argtypes = [vp, dp, i64, dp, dp]
+    lib.fmmb_plan_direct_panels.argtypes = [vp, dp, i64, dp, dp, dp]
     lib.fmmb_plan_sync.argtypes = [vp]
     lib.fmmb_comm_unique_id.argtypes = [dp]
     lib.fmmb_plan_comm_init.argtypes = [vp, dp]

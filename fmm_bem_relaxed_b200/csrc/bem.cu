@@ -324,6 +324,35 @@ bem_m2p_kernel(const int* __restrict__ leaves, int nleaves, const unsigned* __re
   }
 }
 
+// Direct::matvec with the panel kernel (include/Direct.hpp:99-125 over operator(), :273-297): block per target panel,
+// threads stride over ALL source panels of the plan, block-wide sum in a fixed tree order.
+__global__ void __launch_bounds__(128)
+bem_direct_kernel(const bem::Panel* __restrict__ pan, const double* __restrict__ chg, int64_t ns,
+                  const double* __restrict__ tverts, const int* __restrict__ tbc, double kappa,
+                  double* __restrict__ out) {
+  __shared__ double part[128];
+  const int64_t t = blockIdx.x;
+  const double* v = tverts + 9 * (size_t)t;
+  const double tc[3] = {((v[0] + v[3]) + v[6]) / 3, ((v[1] + v[4]) + v[7]) / 3, ((v[2] + v[5]) + v[8]) / 3};
+  const int bc = tbc ? tbc[t] : 0;
+  double acc = 0;
+  for (int64_t j = threadIdx.x; j < ns; j += blockDim.x)
+    acc += (kappa < 0 ? bem::kernel(bc, tc, pan[j], c_rule, c_fine) : bem::kernel_yk(bc, tc, pan[j], c_rule, kappa)) * chg[j];
+  part[threadIdx.x] = acc;
+  __syncthreads();
+  for (int w = 64; w > 0; w >>= 1) {
+    if ((int)threadIdx.x < w) part[threadIdx.x] += part[threadIdx.x + w];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[t] = part[0];
+}
+
+__global__ void bem_gather_plain(const double* __restrict__ q, const unsigned* __restrict__ perm, int64_t n,
+                                 double* __restrict__ chg) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < n) chg[i] = q[perm[i]];
+}
+
 __global__ void bem_gather_charges(const double* __restrict__ q, const unsigned* __restrict__ perm, int64_t n,
                                    double4* __restrict__ body) {
   int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
@@ -402,6 +431,19 @@ bool bem_set_active(const BemData* b, int set) { return b->set_active[set]; }
 double* bem_res_near(BemData* b) { return b->res_near.p; }
 double* bem_res_far(BemData* b) { return b->res_far.p; }
 int bem_rule_points(const BemData* b) { return b->K; }
+
+// fmmb_plan_direct_panels for LaplaceSphericalBEM / YukawaCartesianBEM plans (device pointers; charges original order)
+void bem_direct(fmmb_plan* plan, const double* d_charges, int64_t nt, const double* d_tverts, const int* d_tbc,
+                double* d_out, cudaStream_t s) {
+  Tree& T = plan->tree;
+  BemData* B = plan->bem;
+  DevBuf<double> chg;
+  chg.resize(T.n);
+  bem_gather_plain<<<nblk(T.n, 256), 256, 0, s>>>(d_charges, T.perm.p, T.n, chg.p);
+  if (nt) bem_direct_kernel<<<(unsigned)nt, 128, 0, s>>>(B->pan.p, chg.p, T.n, d_tverts, d_tbc, B->kappa, d_out);
+  FMMB_CUDA(cudaGetLastError());
+  FMMB_CUDA(cudaStreamSynchronize(s));      // chg is released on return
+}
 
 void bem_execute(fmmb_plan* plan, const double* d_charges, double* d_results) {
   Tree& T = plan->tree;

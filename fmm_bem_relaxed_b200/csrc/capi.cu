@@ -322,6 +322,29 @@ int fmmb_plan_direct(fmmb_plan* plan, const double* charges_host, int64_t nt, co
   });
 }
 
+int fmmb_plan_direct_panels(fmmb_plan* plan, const double* charges_host, int64_t nt, const double* target_vertices_host,
+                            const int32_t* target_bc_host, double* results_host) {
+  if (!plan || !charges_host || !target_vertices_host || !results_host || nt < 0) { set_error("bad argument"); return FMMB_ERR_INVALID; }
+  if (!plan->bem && !plan->sbem) { set_error("fmmb_plan_direct_panels is for the BEM kernel kinds (fmmb_plan_direct: point kernels)"); return FMMB_ERR_UNSUPPORTED; }
+  for (int64_t i = 0; target_bc_host && i < nt; ++i)
+    if (target_bc_host[i] != 0 && target_bc_host[i] != 1) { set_error("bc entries must be 0 or 1"); return FMMB_ERR_INVALID; }
+  return guarded([&] {
+    FMMB_CUDA(cudaSetDevice(plan->device));
+    cudaStream_t s = plan->stream;
+    DevBuf<double> q, t, out;
+    DevBuf<int> bc;
+    const size_t rd = plan->result_dim;
+    q.from_host(charges_host, (size_t)plan->charge_dim * plan->tree.n, s);
+    t.from_host(target_vertices_host, 9 * (size_t)nt, s);
+    if (target_bc_host) bc.from_host(target_bc_host, (size_t)nt, s);
+    out.resize(rd * (size_t)nt);
+    if (plan->sbem) stokes_bem_direct(plan, q.p, nt, t.p, target_bc_host ? bc.p : nullptr, out.p, s);
+    else bem_direct(plan, q.p, nt, t.p, target_bc_host ? bc.p : nullptr, out.p, s);
+    if (nt) FMMB_CUDA(cudaMemcpyAsync(results_host, out.p, rd * (size_t)nt * sizeof(double), cudaMemcpyDeviceToHost, s));
+    FMMB_CUDA(cudaStreamSynchronize(s));
+  });
+}
+
 int fmmb_plan_set_option(fmmb_plan* plan, const char* name, int64_t value) {
   if (!plan || !name) { set_error("null argument"); return FMMB_ERR_INVALID; }
   if (!std::strcmp(name, "overlap_p2p")) { plan->overlap_p2p = value != 0; return FMMB_OK; }

@@ -277,6 +277,8 @@ int bem_rule_points(const BemData* b);
 void yukawa_bem_execute(fmmb_plan* plan, const double* d_charges, double* d_results);
 void bem_execute(fmmb_plan* plan, const double* d_charges, double* d_results);
 void bem_free(BemData* b);
+void bem_direct(fmmb_plan* plan, const double* d_charges, int64_t nt, const double* d_tverts, const int* d_tbc,
+                double* d_out, cudaStream_t s);
 int64_t bem_nnz(const BemData* b);
 void laplace_direct_raw(const double* d_spts, const double* d_q, int64_t ns, const double* d_tpts, int64_t nt,
                         double* d_out, cudaStream_t s);
@@ -304,6 +306,8 @@ void stokes_bem_setup(fmmb_plan* plan, const double* verts_host, const int32_t* 
                       double mu);
 void stokes_bem_execute(fmmb_plan* plan, const double* d_charges, double* d_results);
 void stokes_bem_free(StokesBemData* d);
+void stokes_bem_direct(fmmb_plan* plan, const double* d_charges, int64_t nt, const double* d_tverts, const int* d_tbc,
+                       double* d_out, cudaStream_t s);
 int64_t stokes_bem_nnz(const StokesBemData* d);
 // m2l_classes.cu
 void m2l_init_tables();

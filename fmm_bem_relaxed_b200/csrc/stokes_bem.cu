@@ -421,6 +421,36 @@ sbem_m2p_kernel(const int* __restrict__ leaves, int nleaves, const unsigned* __r
   }
 }
 
+// Direct::matvec with the panel kernel (include/Direct.hpp:99-125 over operator(), :377-390): block per target panel,
+// threads stride over ALL source panels of the plan, block-wide sums in a fixed tree order.
+__global__ void __launch_bounds__(128)
+sbem_direct_kernel(const bem::Panel* __restrict__ pan, const double* __restrict__ chg, int64_t ns,
+                   const double* __restrict__ tverts, const int* __restrict__ tbc, double mu, bool as_written,
+                   double* __restrict__ out) {
+  __shared__ double part[3][128];
+  const int64_t t = blockIdx.x;
+  const double* v = tverts + 9 * (size_t)t;
+  const double tc[3] = {((v[0] + v[3]) + v[6]) / 3, ((v[1] + v[4]) + v[7]) / 3, ((v[2] + v[5]) + v[8]) / 3};
+  const int bc = tbc ? tbc[t] : 0;
+  double u0 = 0, u1 = 0, u2 = 0;
+  for (int64_t j = threadIdx.x; j < ns; j += blockDim.x) {
+    double m[9];
+    bem::stokes_kernel(bc, tc, pan[j], c_srule, c_sfine, mu, as_written, m);
+    const double f0 = chg[3 * j], f1 = chg[3 * j + 1], f2 = chg[3 * j + 2];
+    u0 += m[0] * f0 + m[1] * f1 + m[2] * f2;
+    u1 += m[3] * f0 + m[4] * f1 + m[5] * f2;
+    u2 += m[6] * f0 + m[7] * f1 + m[8] * f2;
+  }
+  part[0][threadIdx.x] = u0; part[1][threadIdx.x] = u1; part[2][threadIdx.x] = u2;
+  __syncthreads();
+  for (int w = 64; w > 0; w >>= 1) {
+    if ((int)threadIdx.x < w)
+      for (int c = 0; c < 3; ++c) part[c][threadIdx.x] += part[c][threadIdx.x + w];
+    __syncthreads();
+  }
+  if (threadIdx.x < 3) out[3 * (size_t)t + threadIdx.x] = part[threadIdx.x][0];
+}
+
 void swap_buf(DevBuf<double>& a, DevBuf<double>& b) {
   std::swap(a.p, b.p); std::swap(a.cap, b.cap); std::swap(a.n, b.n);
 }
@@ -479,6 +509,19 @@ void stokes_bem_setup(fmmb_plan* plan, const double* verts_host, const int32_t* 
                                                                          B->nf_base.p, B->mu, B->as_written, B->nf_val.p);
   FMMB_CUDA(cudaGetLastError());
   FMMB_CUDA(cudaStreamSynchronize(s));
+}
+
+// fmmb_plan_direct_panels for StokesSphericalBEM plans (device pointers; charges original order, 3 per panel)
+void stokes_bem_direct(fmmb_plan* plan, const double* d_charges, int64_t nt, const double* d_tverts, const int* d_tbc,
+                       double* d_out, cudaStream_t s) {
+  Tree& T = plan->tree;
+  StokesBemData* B = plan->sbem;
+  DevBuf<double> chg;
+  chg.resize(3 * (size_t)T.n);
+  sbem_gather<<<nblk(3 * T.n, 256), 256, 0, s>>>(d_charges, T.perm.p, T.n, chg.p);
+  if (nt) sbem_direct_kernel<<<(unsigned)nt, 128, 0, s>>>(B->pan.p, chg.p, T.n, d_tverts, d_tbc, B->mu, B->as_written, d_out);
+  FMMB_CUDA(cudaGetLastError());
+  FMMB_CUDA(cudaStreamSynchronize(s));      // chg is released on return
 }
 
 void stokes_bem_execute(fmmb_plan* plan, const double* d_charges, double* d_results) {

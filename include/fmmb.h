@@ -181,6 +181,15 @@ int fmmb_plan_execute_sharded(fmmb_plan* plan, const double* charges_own_dev, do
 int fmmb_plan_direct(fmmb_plan* plan, const double* charges_host, int64_t nt,
                      const double* targets_host, double* results_host);
 
+/* The same for the panel kernels (LaplaceSphericalBEM, YukawaCartesianBEM, StokesSphericalBEM): results[i] = sum over ALL
+ * source panels j of the plan of K(t_i, s_j) q_j with K = the kernel class's operator()(target, source)
+ * (kernel/LaplaceSphericalBEM.hpp:273-297, YukawaCartesianBEM.hpp:213-230, StokesSphericalBEM.hpp:377-390) -- what
+ * examples/StokesBEM.cpp:377-380 and the accuracy checks of the BEM drivers call Direct::matvec for.
+ * target_vertices: 9*nt doubles, (p0, p1, p2) per target panel (the kernels evaluate at its centre); target_bc: nt
+ * entries like fmmb_sources.bc, NULL = all 0; results: nt*result_dim doubles (host). */
+int fmmb_plan_direct_panels(fmmb_plan* plan, const double* charges_host, int64_t nt, const double* target_vertices_host,
+                            const int32_t* target_bc_host, double* results_host);
+
 /* Engine knobs that have no counterpart in the reference (all default to the fast setting):
  *   "overlap_p2p"  1 = near field runs on a second stream concurrently with the far field (default),
  *                  0 = every kernel on one stream, so per-kernel CUDA-event times are undisturbed

@@ -4,6 +4,8 @@
 //   near  <file>   sbem_setup_kernel, sbem_count_kernel, sbem_assemble_kernel, sbem_gather, sbem_near_kernel on a tree
 //                  and near-field lists written by the test (from the oracle); prints nothing, writes the near-field
 //                  result in ORIGINAL order to <file>.out
+//   direct <file>  sbem_direct_kernel / bem_direct_kernel (fmmb_plan_direct_panels) on panels and targets written by the
+//                  test; writes the sums to <file>.out
 //   far            sbem_p2m_kernel<0|1> against stokes_p2m_kernel<false|true> of csrc/stokes.cu (hardware-verified
 //                  this round) fed with one point source per (panel, quadrature point), and sbem_l2p_kernel against
 //                  stokes_l2p_kernel at the panel centres; prints the largest relative differences
@@ -106,6 +108,46 @@ static int run_near(const char* path) {
   fwrite(out.data(), 8, out.size(), f);
   fclose(f);
   printf("near: n %ld items %ld pairs %lld\n", n, ni, base[ni]);
+  return 0;
+}
+
+// ---- Direct::matvec kernels: sbem_direct_kernel (csrc/stokes_bem.cu) and bem_direct_kernel (csrc/bem.cu) ----------
+// file layout: int64 n, nt; int32 K, kfine, as_written, kind (0 Stokes BEM, 1 Laplace BEM, 2 Yukawa BEM); double mu_or_kappa;
+// verts[9n] f64 (tree order = file order), q[cd n] f64, tverts[9 nt] f64, tbc[nt] i32.  Writes <file>.out (rd nt doubles).
+static int run_direct(const char* path) {
+  std::vector<char> buf = slurp(path);
+  const char* p = buf.data();
+  const long long* hd = take<long long>(p, 2);
+  const long n = hd[0], nt = hd[1];
+  const int* ip = take<int>(p, 4);
+  const int K = ip[0], kfine = ip[1], as_written = ip[2], kind = ip[3];
+  const double par = *take<double>(p, 1);
+  const double* verts = take<double>(p, 9 * n);
+  const int cd = kind == 0 ? 3 : 1;
+  const double* q = take<double>(p, cd * n);
+  const double* tverts = take<double>(p, 9 * nt);
+  const int* tbc = take<int>(p, nt);
+  std::vector<bem::Panel> pan(n);
+  for (long i = 0; i < n; ++i) bem::make_panel(verts + 9 * i, verts + 9 * i + 3, verts + 9 * i + 6, pan[i]);
+  std::vector<double> out(cd * nt, -5.0);
+  if (kind == 0) {
+    emu_sbem::c_srule = bem::make_rule(K);
+    emu_sbem::c_sfine = bem::make_rule(kfine);
+    emu::launch(dim3((unsigned)nt), dim3(128), [&] {
+      emu_sbem::sbem_direct_kernel(pan.data(), q, n, tverts, tbc, par, as_written != 0, out.data());
+    });
+  } else {
+    emu_bem::c_rule = bem::make_rule(K == 7 ? 4 : K);
+    emu_bem::c_fine = bem::make_rule(17);
+    emu::launch(dim3((unsigned)nt), dim3(128), [&] {
+      emu_bem::bem_direct_kernel(pan.data(), q, n, tverts, tbc, kind == 2 ? par : -1.0, out.data());
+    });
+  }
+  std::string o = std::string(path) + ".out";
+  FILE* f = fopen(o.c_str(), "wb");
+  fwrite(out.data(), 8, out.size(), f);
+  fclose(f);
+  printf("direct: n %ld nt %ld kind %d\n", n, nt, kind);
   return 0;
 }
 
@@ -475,7 +517,8 @@ int main(int argc, char** argv) {
   if (argc >= 2 && !strcmp(argv[1], "stokes_m2p")) return run_stokes_m2p();
   if (argc >= 2 && !strcmp(argv[1], "m2p")) return run_m2p();
   if (argc >= 3 && !strcmp(argv[1], "near")) return run_near(argv[2]);
+  if (argc >= 3 && !strcmp(argv[1], "direct")) return run_direct(argv[2]);
   if (argc >= 2 && !strcmp(argv[1], "far")) return run_far();
-  fprintf(stderr, "usage: emu_stokes_bem near <file> | far | m2p | ykm2p | stokes_m2p | bem_rules\n");
+  fprintf(stderr, "usage: emu_stokes_bem near <file> | direct <file> | far | m2p | ykm2p | stokes_m2p | bem_rules\n");
   return 2;
 }

@@ -11,6 +11,7 @@ per-lane arithmetic that will run on the B200 are these very source lines.  Chec
   * treecode -- bem_m2p_kernel<0|1> of csrc/bem.cu against m2p_kernel of csrc/laplace.cu (green on hardware);
     yk_bem_m2p_kernel<0|1> of csrc/yukawa.cu against yk_table_kernel (green on hardware) + a host dot product;
     stokes_m2p_kernel / sbem_m2p_kernel against four runs of m2p_kernel combined on the host.
+  * Direct::matvec kernels of fmmb_plan_direct_panels against the oracle's direct sums.
 This verifies kernel logic, not performance, and does not replace the first run on the device (tests/test_zz_stokes_bem.py).
 """
 import os
@@ -124,3 +125,34 @@ def test_near_field_kernels_match_the_oracle(emu, tmp_path, bcmix, as_written, K
     got = np.fromfile(str(path) + ".out").reshape(n, 3)
     for k in range(3):
         assert O.rel_l2(got[:, k], want[:, k]) <= 1e-13
+
+
+@pytest.mark.parametrize("kind,as_written", [(0, False), (0, True), (1, False), (2, False)])
+def test_direct_matvec_kernels_match_the_oracle(emu, tmp_path, kind, as_written):
+    """sbem_direct_kernel / bem_direct_kernel (fmmb_plan_direct_panels: Direct::matvec with the panel kernels) against
+    the oracle's direct sums, which are bit-identical to the reference's Direct::matvec."""
+    verts = O.unit_sphere(3)                             # 128 source panels
+    n = len(verts)
+    bc = (np.arange(n) % 3 == 1).astype(np.int32)
+    sel = np.arange(0, n, 5)
+    rng = np.random.default_rng(3 + kind)
+    par = 0.02 if kind == 0 else 0.7
+    if kind == 0:
+        q = rng.random((n, 3)) - 0.4
+        want = O.StokesBemOracle(verts, bc, mu=par, K=4, kfine=19, as_written=as_written).direct(q)[sel]
+    elif kind == 1:
+        q = rng.random(n) - 0.4
+        want = O.BemOracle(verts, bc).direct(q, 4)[sel]
+    else:
+        q = rng.random(n) - 0.4
+        want = O.YukawaBemOracle(verts, bc, par).direct(q, 4)[sel]
+    path = tmp_path / "direct.bin"
+    with open(path, "wb") as f:
+        f.write(struct.pack("<2q4id", n, len(sel), 4, 19, int(as_written), kind, par))
+        for a in (np.ascontiguousarray(verts, np.float64), np.ascontiguousarray(q, np.float64),
+                  np.ascontiguousarray(verts[sel], np.float64), np.ascontiguousarray(bc[sel], np.int32)):
+            f.write(a.tobytes())
+    out = subprocess.check_output([emu, "direct", str(path)], timeout=900).decode()
+    assert "direct: n %d" % n in out
+    got = np.fromfile(str(path) + ".out").reshape(want.shape)
+    assert O.rel_l2(got, want) <= 1e-13

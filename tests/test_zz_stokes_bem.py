@@ -194,6 +194,30 @@ def test_tiny_meshes(rec, ncrit):
         assert O.rel_l2(got, orc.execute(q, 4)) <= TOL
 
 
+def test_direct_matvec_on_the_gpu_for_the_panel_kernels():
+    """fmmb_plan_direct_panels (Direct::matvec with operator()(target panel, source panel)) against the oracle's direct
+    sums, which are bit-identical to the reference's: StokesSphericalBEM in both near-field modes, LaplaceSphericalBEM,
+    YukawaCartesianBEM; targets = a slice of the panels with mixed boundary conditions."""
+    verts = O.unit_sphere(5)
+    n = len(verts)
+    bc = (np.arange(n) % 3 == 1).astype(np.int32)
+    rng = np.random.default_rng(9)
+    sel = np.arange(0, n, 7)
+    tg = F.Panels(verts[sel], bc[sel])
+    q3 = rng.random((n, 3)) - 0.4
+    for as_written in (False, True):
+        plan = make_plan(verts, bc, 5, as_written=as_written)
+        want = O.StokesBemOracle(verts, bc, as_written=as_written).direct(q3)[sel]
+        assert O.rel_l2(F.Direct.matvec(plan, q3, tg), want) <= 1e-12
+    q = rng.random(n) - 0.4
+    plan = F.FMM_plan(F.LaplaceSphericalBEM(5, 4), F.Panels(verts, bc))
+    assert O.rel_l2(F.Direct.matvec(plan, q, tg), O.BemOracle(verts, bc).direct(q, 4)[sel]) <= 1e-12
+    plan = F.FMM_plan(F.YukawaCartesianBEM(5, 0.7, 4), F.Panels(verts, bc))
+    assert O.rel_l2(F.Direct.matvec(plan, q, tg), O.YukawaBemOracle(verts, bc, 0.7).direct(q, 4)[sel]) <= 1e-12
+    with pytest.raises(F.FmmbError):
+        F.Direct.matvec(F.FMM_plan(F.LaplaceSpherical(4), rng.random((100, 3))), rng.random(100), tg)
+
+
 # ---- treecode evaluator (`-eval TREE`) of the Stokes classes: stokes_m2p_kernel, sbem_m2p_kernel -------------------
 @pytest.mark.parametrize("bc", [0, 2])
 def test_treecode_golden_fixtures(bc):
