@@ -1,12 +1,14 @@
 #!/bin/bash
-# First hardware run of the StokesSphericalBEM kernels and the higher Gauss rules (written after round 1's GPU minutes
-# were spent; DESIGN.md sections 0 and 5.7).  One gpurun call, about 6 minutes of box time:
-#   gpurun --timeout 900 -- 'bash scripts/gpu_first_run_stokes_bem.sh'
+# First hardware run of everything written after round 1's GPU minutes were spent (DESIGN.md sections 0 and 5.7):
+# StokesSphericalBEM, the Gauss rules above 4 points, the treecode evaluators of the BEM and Stokes classes,
+# fmmb_plan_direct_panels, config C5 at N = 10M.  One gpurun call, about 8 minutes of box time:
+#   gpurun --timeout 1200 -- 'bash scripts/gpu_first_run_new_kernels.sh'
 # Everything it writes lands in gpurun_out/; copy what should be judged into profiles/.
 set -x
 mkdir -p gpurun_out
 # 1. the guarded suites, without the xfail mask (--runxfail turns xfail marks off: failures show as failures)
-timeout 600 python -m pytest tests/test_zz_stokes_bem.py tests/test_zz_bem_rules.py -q --runxfail -x 2>&1 | tail -30 > gpurun_out/zz_first_run.log
+timeout 900 python -m pytest tests/test_zz_stokes_bem.py tests/test_zz_bem_rules.py tests/test_zz_c5_full_size.py -q --runxfail \
+    2>&1 | tail -60 > gpurun_out/zz_first_run.log
 tail -5 gpurun_out/zz_first_run.log
 # 2. the drivers: ours (device GMRES), the reference's unchanged driver over the GPU plan, larger sphere
 export LD_LIBRARY_PATH=$PWD/fmm_bem_relaxed_b200:$LD_LIBRARY_PATH
