@@ -96,10 +96,6 @@ int fmmb_plan_create(const fmmb_kernel_desc* kernel, const fmmb_sources* sources
   }
   if (opts.ncrit < 1) { set_error("ncrit must be at least 1"); return FMMB_ERR_INVALID; }
   if (opts.evaluator != FMMB_EVAL_FMM && opts.evaluator != FMMB_EVAL_TREECODE) { set_error("unknown evaluator"); return FMMB_ERR_INVALID; }
-  if (opts.evaluator == FMMB_EVAL_TREECODE && kernel->kind == FMMB_YUKAWA_CARTESIAN) {
-    set_error("the treecode evaluator (M2P) is not built for FMMB_YUKAWA_CARTESIAN plans (every other kind has it)");
-    return FMMB_ERR_UNSUPPORTED;
-  }
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
     cudaGetLastError();

@@ -304,6 +304,69 @@ yk_bem_m2p_kernel(const int* __restrict__ leaves, int nleaves, const unsigned* _
   }
 }
 
+// ---- M2P of the point kernel (treecode, reference kernel/YukawaCartesian.hpp:221-240): warp per leaf, lane per body.
+// Same lane-private table as above; the gradient uses ax_m = (m_x + 1) a_{m + e_x} for |m| < P and nothing for
+// |m| = P, which is what getCoeff's `ax[Im1x] = a[I] * i` lines leave in ax / ay / az (:388-672).
+__global__ void __launch_bounds__(128)
+yk_m2p_kernel(const int* __restrict__ leaves, int nleaves, const unsigned* __restrict__ bb,
+              const unsigned* __restrict__ be, const unsigned* __restrict__ parent, const int* __restrict__ off,
+              const int* __restrict__ src, const double4* __restrict__ center, const double4* __restrict__ body, int P,
+              double kappa, const double* __restrict__ M, double4* __restrict__ res) {
+  const int nt = yk_terms(P);
+  const int wl = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int w = blockIdx.x * (blockDim.x >> 5) + wl;
+  if (w >= nleaves) return;
+  const int leaf = leaves[w];
+  double a[kYkMaxT], b[kYkMaxT];
+  for (unsigned i = bb[leaf] + lane; i < be[leaf]; i += 32) {
+    const double4 p = body[i];
+    double pot = 0, gx = 0, gy = 0, gz = 0;
+    for (int anc = leaf;; anc = (int)parent[anc]) {
+      for (int e = off[anc]; e < off[anc + 1]; ++e) {
+        const int sb = src[e];
+        const double4 c = center[sb];
+        const double xv[3] = {p.x - c.x, p.y - c.y, p.z - c.z};
+        const double R2 = xv[0] * xv[0] + xv[1] * xv[1] + xv[2] * xv[2], R = sqrt(R2), R2_1 = 1.0 / R2;
+        b[0] = exp(-kappa * R);
+        a[0] = b[0] / R;
+        for (int s = 1; s <= P; ++s)
+          for (int i0 = 0; i0 <= s; ++i0)
+            for (int j0 = 0; j0 <= s - i0; ++j0) {
+              const int n[3] = {i0, j0, s - i0 - j0};
+              const int t = yk_idx(P, n[0], n[1], n[2]);
+              double xa = 0, xb = 0, a2 = 0, b2 = 0;
+#pragma unroll
+              for (int d = 0; d < 3; ++d) {
+                if (n[d] >= 1) {
+                  const int q = yk_idx(P, n[0] - (d == 0), n[1] - (d == 1), n[2] - (d == 2));
+                  xa += xv[d] * a[q]; xb += xv[d] * b[q];
+                }
+                if (n[d] >= 2) {
+                  const int q = yk_idx(P, n[0] - 2 * (d == 0), n[1] - 2 * (d == 1), n[2] - 2 * (d == 2));
+                  a2 += a[q]; b2 += b[q];
+                }
+              }
+              b[t] = -kappa / s * (xa + a2);
+              a[t] = R2_1 / s * (-kappa * (xb + b2) - (2 * s - 1) * xa - (s - 1) * a2);
+            }
+        const double* Ms = M + (size_t)sb * nt;
+        for (int t = 0; t < nt; ++t) {
+          const int ii = c_yI[P][t], jj = c_yJ[P][t], kk = c_yK[P][t];
+          const double mf = Ms[t] * (c_yfact[ii] * c_yfact[jj] * c_yfact[kk]);
+          pot += a[t] * mf;
+          if (ii + jj + kk < P) {
+            gx += a[yk_idx(P, ii + 1, jj, kk)] * (ii + 1) * mf;
+            gy += a[yk_idx(P, ii, jj + 1, kk)] * (jj + 1) * mf;
+            gz += a[yk_idx(P, ii, jj, kk + 1)] * (kk + 1) * mf;
+          }
+        }
+      }
+      if (anc == 0) break;
+    }
+    res[i] = make_double4(pot, gx, gy, gz);
+  }
+}
+
 __global__ void yk_slot_class_kernel(int n_items, const int* __restrict__ item_class, const int* __restrict__ item_start,
                                      const int* __restrict__ item_count, const int* __restrict__ sorted_slot,
                                      int* __restrict__ slot_class) {
@@ -684,7 +747,7 @@ void yukawa_execute(fmmb_plan* plan, const double* d_charges, double* d_results)
   double4* near = reinterpret_cast<double4*>(d->res_near.p);
   double4* far = reinterpret_cast<double4*>(d->res_far.p);
   plan->launches = 0;
-  const double* table = yk_class_tables(plan, d, P, s);
+  const double* table = plan->opts.evaluator == FMMB_EVAL_TREECODE ? nullptr : yk_class_tables(plan, d, P, s);
 
   if (!plan->capturing) FMMB_CUDA(cudaEventRecord(ev[0], s));
   yk_gather<<<nblk(n, 256), 256, 0, s>>>(d_charges, T.perm.p, n, T.body.p);
@@ -708,8 +771,14 @@ void yukawa_execute(fmmb_plan* plan, const double* d_charges, double* d_results)
                                                      P, d->M.p);
     ++plan->launches;
   }
-  yk_translations(plan, d, P, table, s);
-  {
+  yk_translations(plan, d, P, table, s);      // treecode: stops after the upward pass
+  if (plan->opts.evaluator == FMMB_EVAL_TREECODE) {
+    if (T.n_own_leaves)
+      yk_m2p_kernel<<<nblk(T.n_own_leaves, 4), 128, 0, s>>>(T.own_leaves.p, T.n_own_leaves, T.bbegin.p, T.bend.p, T.parent.p,
+                                                           T.m2l_off.p, T.m2l_src.p, T.center.p, T.body.p, P, d->kappa,
+                                                           d->M.p, far);
+    ++plan->launches;
+  } else {
     const size_t sh = (size_t)4 * (nt + 32 * 3 * (P + 1)) * sizeof(double);
     if (T.n_own_leaves)
     yk_l2p_kernel<<<nblk(T.n_own_leaves, 4), 128, sh, s>>>(T.own_leaves.p, T.n_own_leaves, T.bbegin.p, T.bend.p,

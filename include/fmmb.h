@@ -81,8 +81,8 @@ typedef struct {
   double theta;        /* FMMOptions::set_mac_theta, default 0.5 */
   uint32_t ncrit;      /* FMMOptions::set_max_per_box, default 64 */
   int32_t evaluator;   /* fmmb_evaluator; FMMB_EVAL_TREECODE (-eval TREE: M2P instead of M2L/L2L/L2P) is built for every
-                          kind except FMMB_YUKAWA_CARTESIAN (for FMMB_YUKAWA_CARTESIAN_BEM it is the far-field path
-                          pinned to the reference, whose FMM evaluator is broken for that kernel class) */
+                          kind (for FMMB_YUKAWA_CARTESIAN_BEM it is the far-field path pinned to the reference, whose
+                          FMM evaluator is broken for that kernel class) */
   int32_t device;      /* CUDA device ordinal, -1 = current device */
   int32_t m2l_mode;    /* 0 = auto, 1 = per-pair kernel only, 2 = prefer batched translation classes */
   int32_t rank;        /* multi-GPU: this process's rank (0 when nranks <= 1) */

@@ -468,7 +468,7 @@ static int run_ykm2p() {
     bc[i] = i % 2;
   }
   auto leaf_of = [&](int i) { for (int l : leaves) if ((unsigned)i >= bb[l] && (unsigned)i < be[l]) return l; return -1; };
-  double worst = 0, biggest = 0;
+  double worst = 0, biggest = 0, worst_pt = 0;
   const double kappa = 0.35;
   for (int P : {1, 4, 8, 10}) {
     const int nt = yk_terms(P);
@@ -494,6 +494,33 @@ static int run_ykm2p() {
       for (int t = 0; t < nt; ++t) v += table[k * nt + t] * M[(size_t)pair_b[k] * nt + t];
       phi[pair_t[k]] += v;
     }
+    // the point kernel: potential and gradient (ax_m f_m = a'_{m + e_x} for |m| < P)
+    {
+      std::vector<double> w4(4 * n, 0.0);
+      for (size_t k = 0; k < vec.size(); ++k) {
+        const double* tab = &table[k * nt];
+        const double* Mb = &M[(size_t)pair_b[k] * nt];
+        double* r = &w4[4 * pair_t[k]];
+        for (int t = 0; t < nt; ++t) {
+          const int ii = c_yI[P][t], jj = c_yJ[P][t], kk = c_yK[P][t];
+          r[0] += tab[t] * Mb[t];
+          if (ii + jj + kk < P) {
+            r[1] += tab[yk_idx(P, ii + 1, jj, kk)] * Mb[t];
+            r[2] += tab[yk_idx(P, ii, jj + 1, kk)] * Mb[t];
+            r[3] += tab[yk_idx(P, ii, jj, kk + 1)] * Mb[t];
+          }
+        }
+      }
+      std::vector<double4> body(n), g4(n, make_double4(-9, -9, -9, -9));
+      for (int i = 0; i < n; ++i) body[i] = make_double4(pan[i].c[0], pan[i].c[1], pan[i].c[2], 1.0);
+      emu::launch(dim3(nblocks(3, 4)), dim3(128), [&] {
+        yk_m2p_kernel(leaves.data(), 3, bb.data(), be.data(), parent.data(), off.data(), src.data(), center.data(), body.data(),
+                      P, kappa, M.data(), g4.data());
+      });
+      std::vector<double> got4(4 * n);
+      for (int i = 0; i < n; ++i) { got4[4 * i] = g4[i].x; got4[4 * i + 1] = g4[i].y; got4[4 * i + 2] = g4[i].z; got4[4 * i + 3] = g4[i].w; }
+      worst_pt = std::max(worst_pt, rel_diff(got4, w4));
+    }
     for (int set = 0; set < 2; ++set) {
       std::vector<double> got(n, 0.125), want(n, 0.125);
       emu::launch(dim3(nblocks(3, 4)), dim3(128), [&] {
@@ -507,7 +534,7 @@ static int run_ykm2p() {
       worst = std::max(worst, rel_diff(got, want));
     }
   }
-  printf("ykm2p: %.3e max_potential %.3e\n", worst, biggest);
+  printf("ykm2p: %.3e max_potential %.3e point %.3e\n", worst, biggest, worst_pt);
   return 0;
 }
 

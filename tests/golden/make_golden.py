@@ -106,13 +106,13 @@ def stokes_case(name, stresslet, n, p, ncrit, theta, points=None, charges=None, 
         print(name, meta["sum"], "err vs direct", meta["err_vs_direct"])
 
 
-def yukawa_case(name, n, p, kappa, ncrit, theta, points=None, charges=None, direct=300):
+def yukawa_case(name, n, p, kappa, ncrit, theta, points=None, charges=None, direct=300, tree=False):
     """YukawaCartesian through oracle/_ref/ref_yukawa: the unmodified reference class behind the arity adapter of
     oracle/ref_yukawa.cpp."""
     exe = os.path.join(ROOT, "oracle", "_ref", "ref_yukawa")
     with tempfile.TemporaryDirectory() as tmp:
         cmd = [exe, "-N", str(n), "-P", str(p), "-kappa", repr(kappa), "-ncrit", str(ncrit), "-theta", repr(theta),
-               "-direct", str(direct)]
+               "-direct", str(direct)] + (["-tree"] if tree else [])
         if points is not None:
             infile = os.path.join(tmp, "in.f64")
             np.concatenate([points.ravel(), charges.ravel()]).tofile(infile)
@@ -183,6 +183,9 @@ def laplace_bem_case(name, recursions, p, k, ncrit, bc, tree=False):
 
 
 def main():
+    if "--yukawa-tree" in sys.argv:
+        yukawa_case("yukawa_tree_n3000_p5", 3000, 5, 0.125, 32, 0.5, tree=True)
+        return
     if "--stokes-tree" in sys.argv:
         # FMMOptions::TREECODE for the Stokes classes: Stokeslet (unmodified reference), stresslet (patched),
         # StokesSphericalBEM as compiled (`StokesBEM -eval TREE`)

@@ -49,7 +49,7 @@ def load():
         L.fmmo_drand48_inputs.argtypes = [ctypes.c_int, vp, vp]
         L.fmmo_stokes_execute.argtypes = [vp, ctypes.c_int, ctypes.c_int, vp, vp, ctypes.c_int, ctypes.c_int]
         L.fmmo_stokes_direct.argtypes = [ctypes.c_int, vp, ctypes.c_int, vp, ctypes.c_int, vp, vp, ctypes.c_int]
-        L.fmmo_yukawa_execute.argtypes = [vp, ctypes.c_int, ctypes.c_double, vp, vp, ctypes.c_int]
+        L.fmmo_yukawa_execute.argtypes = [vp, ctypes.c_int, ctypes.c_double, vp, vp, ctypes.c_int, ctypes.c_int]
         L.fmmo_yukawa_direct.argtypes = [ctypes.c_int, vp, ctypes.c_double, vp, ctypes.c_int, vp, vp, ctypes.c_int]
         L.fmmo_yukawa_bem_execute.argtypes = [vp, ctypes.c_int, ctypes.c_int, ctypes.c_double, vp, vp, vp, vp,
                                               ctypes.c_int, ctypes.c_int]
@@ -140,11 +140,12 @@ class Oracle:
             raise RuntimeError("oracle stokes execute failed: %d" % rc)
         return res
 
-    def yukawa_execute(self, charges, P, kappa, threads=None):
+    def yukawa_execute(self, charges, P, kappa, threads=None, treecode=False):
         """YukawaCartesian matvec: results (n, 4) = potential and the three force-like components."""
         q = np.ascontiguousarray(np.asarray(charges, dtype=np.float64).reshape(-1))
         res = np.zeros((self.n, 4))
-        rc = self.L.fmmo_yukawa_execute(self.h, P, float(kappa), _p(q), _p(res), threads or os.cpu_count() or 1)
+        rc = self.L.fmmo_yukawa_execute(self.h, P, float(kappa), _p(q), _p(res), 2 if treecode else 0,
+                                        threads or os.cpu_count() or 1)
         if rc != 0:
             raise RuntimeError("oracle yukawa execute failed: %d" % rc)
         return res

@@ -90,9 +90,10 @@ def test_yukawa_bem_treecode_kernel_matches_the_table_builder(emu):
     against yk_table_kernel -- the block-cooperative builder behind the M2L that is green on hardware -- and a host
     dot product with the multipoles, orders 1, 4, 8, 10."""
     out = subprocess.check_output([emu, "ykm2p"], timeout=900).decode()
-    m = re.search(r"ykm2p: ([0-9.eE+-]+) max_potential ([0-9.eE+-]+)", out)
+    m = re.search(r"ykm2p: ([0-9.eE+-]+) max_potential ([0-9.eE+-]+) point ([0-9.eE+-]+)", out)
     assert m, out
     assert float(m.group(2)) > 1e-4 and float(m.group(1)) <= 1e-12
+    assert float(m.group(3)) <= 1e-12          # yk_m2p_kernel (point kernel): potential and gradient
 
 
 @pytest.mark.parametrize("bcmix,as_written,K", [(0, False, 4), (1, False, 4), (2, False, 3), (0, True, 4), (1, True, 4),

@@ -321,3 +321,17 @@ def test_stokes_bem_treecode_restatement_matches_reference_bitwise(bc):
     orc = O.StokesBemOracle(g["verts"], g["bc"], mu=m["mu"], K=m["K"], kfine=m["kfine"], as_written=False, ncrit=m["ncrit"],
                             theta=m["theta"])
     assert np.array_equal(orc.execute(g["charges"], m["P"], threads=1, treecode=True), g["results"])
+
+
+def test_yukawa_treecode_restatement_matches_reference():
+    """YukawaCartesian with FMMOptions::TREECODE (oracle/_ref/ref_yukawa -tree, the unmodified class behind the arity
+    adapter): potential and gradient to 1e-15 (the restated getCoeff is one recurrence, not the reference's hand-unrolled
+    cases, so the last bit differs -- like the FMM path of this kernel)."""
+    g = dict(np.load(os.path.join(GOLDEN, "yukawa_tree_n3000_p5.npz")))
+    m = _meta(g)
+    assert m["treecode"] == 1
+    orc = O.Oracle(g["points"], m["ncrit"], m["theta"])
+    res = orc.yukawa_execute(g["charges"], m["P"], m["kappa"], threads=1, treecode=True)
+    for k in range(4):
+        assert O.rel_l2(res[:, k], g["results"][:, k]) <= 1e-15
+    assert 1e-6 < O.rel_l2(res[:, 0], orc.yukawa_execute(g["charges"], m["P"], m["kappa"], threads=1)[:, 0]) < 1e-3

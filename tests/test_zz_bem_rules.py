@@ -3,7 +3,7 @@ keys 13, 19, 25, 79) as panel rules of LaplaceSphericalBEM, against the golden f
 (tests/golden/laplace_bem_2048_*_k13_*.npz, *_k25_*.npz) and the oracle restatement (bit-identical to them,
 tests/test_oracle.py).  The rule tables themselves are pinned on the CPU (tests/test_host_logic.py, kernel 7).
 
-Also here: the treecode evaluator of YukawaCartesianBEM (yk_bem_m2p_kernel in csrc/yukawa.cu) and of LaplaceSphericalBEM (`LaplaceBEM -eval TREE`, bem_m2p_kernel in csrc/bem.cu) against
+Also here: the treecode evaluator of YukawaCartesian[BEM] (yk_m2p_kernel, yk_bem_m2p_kernel in csrc/yukawa.cu) and of LaplaceSphericalBEM (`LaplaceBEM -eval TREE`, bem_m2p_kernel in csrc/bem.cu) against
 the golden fixtures of `ref_bem -tree` and the oracle (bit-identical to them).
 
 STATUS: like tests/test_zz_stokes_bem.py -- added after round 1's GPU minutes were spent, so collected late and marked
@@ -91,6 +91,23 @@ def test_yukawa_bem_treecode_golden_fixtures(bc):
     opts.evaluator = F.FMMOptions.FMM
     fmm = F.FMM_plan(F.YukawaCartesianBEM(6, 1.0, 4), F.Panels(g["verts"], bc), opts).execute(g["charges"])
     assert O.rel_l2(fmm, res) < (2e-4 if bc == 0 else 2e-3)
+
+
+def test_yukawa_point_kernel_treecode_golden_fixture():
+    """YukawaCartesian with FMMOptions::TREECODE (yk_m2p_kernel) against ref_yukawa -tree: potential and gradient."""
+    g = dict(np.load(os.path.join(GOLDEN, "yukawa_tree_n3000_p5.npz")))
+    m = json.loads(str(g["meta"]))
+    opts = F.FMMOptions()
+    opts.set_max_per_box(m["ncrit"])
+    opts.set_mac_theta(m["theta"])
+    opts.evaluator = F.FMMOptions.TREECODE
+    plan = F.FMM_plan(F.YukawaCartesian(m["P"], m["kappa"]), g["points"], opts)
+    res = plan.execute(g["charges"])
+    for k in range(4):
+        assert O.rel_l2(res[:, k], g["results"][:, k]) <= 1e-10
+    orc = O.Oracle(g["points"], m["ncrit"], m["theta"])
+    plan.kernel().set_p(8)
+    assert O.rel_l2(plan.execute(g["charges"]), orc.yukawa_execute(g["charges"], 8, m["kappa"], treecode=True)) <= 1e-10
 
 
 def test_key_5_is_rejected():
