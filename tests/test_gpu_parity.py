@@ -215,9 +215,7 @@ def test_treecode_vs_oracle_and_fmm():
     # treecode and FMM approximate the same sum: they agree to the truncation error of the expansions
     fmm = make_plan(pts, P).execute(q)
     assert O.rel_l2(res[:, 0], fmm[:, 0]) < 1e-4
-    # other kernel classes do not have the treecode path yet
-    with pytest.raises(F.FmmbError):
-        F.FMM_plan(F.StokesSpherical(4), pts, opts)
+    # (the other kernel classes have the treecode path too: tests/test_zz_*.py)
 
 
 def _near_field_numpy(t, pts, q, self_only):
