@@ -71,8 +71,11 @@ BEM_HD void stokes_self_term(const Panel& s, double* m) {
  * comes from dead stack (undefined behaviour) and, as compiled, never selects the self term or the fine rule.
  * as_written = true: the branches as the source text means them -- the panel itself through the self term above,
  * panels with sqrt(2A)/dist >= 0.5 through the fine rule; pinned against the reference with that one declaration
- * changed to point_type.  With the sphere driver the as-compiled entries give the better drag
- * (0.2 % against 5 %, 2 048 panels), the as-written self term being short of the exact integral. */
+ * changed to point_type.  What the dead stack holds depends on the translation unit and its
+ * optimisation level: the reference's drivers built by the oracle recipe behave as described (bit-identical matvecs on
+ * every fixture), other programs around the same header need not.  On the unit sphere (2 048 panels, tol 1e-5) the
+ * as-compiled entries converge in 10 iterations to a drag 0.8 % low, the as-written ones in 22 iterations to a drag
+ * 0.4 % high. */
 BEM_HD void stokes_velocity_entry(const Panel& s, const double* t, const Rule& rule, const Rule& fine, double mu,
                                   bool as_written, double* m) {
   const double dc[3] = {t[0] - s.c[0], t[1] - s.c[1], t[2] - s.c[2]};

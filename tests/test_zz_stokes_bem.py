@@ -114,7 +114,7 @@ def test_rejects_bad_descriptors():
 def test_reference_stokes_driver_unchanged(tmp_path):
     """Reference examples/StokesBEM.cpp (+ its GMRES_Stokes.hpp and friends) compiled unchanged against hostcxx/:
     unit sphere, 2 048 panels, p = 8, k = 4, tol 1e-5.  The unmodified reference (oracle/_ref/StokesBEM, one thread:
-    its threaded M2L races) prints the lines below; the drag comes out at 0.01911 against 0.01885."""
+    its threaded M2L races) prints the lines below."""
     exe = os.path.join(ROOT, "fmm_bem_relaxed_b200", "hostcxx", "bin", "ref_StokesBEM")
     if not os.path.exists(exe):
         pytest.skip(exe + " not built")
@@ -122,21 +122,27 @@ def test_reference_stokes_driver_unchanged(tmp_path):
     env["LD_LIBRARY_PATH"] = os.path.join(ROOT, "fmm_bem_relaxed_b200") + ":" + env.get("LD_LIBRARY_PATH", "")
     out = subprocess.check_output([exe, "-recursions", "5", "-p", "8", "-k", "4", "-solver_tol", "1e-5"], env=env,
                                   timeout=600, cwd=str(tmp_path)).decode()   # the driver writes out.face / out.vert here
-    want = ["it: 001, res: 1.540e-03, fmm_req_p: 7", "it: 002, res: 5.298e-04, fmm_req_p: 7",
-            "it: 003, res: 2.929e-04, fmm_req_p: 5", "it: 004, res: 1.364e-04, fmm_req_p: 5",
-            "it: 005, res: 7.147e-05, fmm_req_p: 5", "it: 006, res: 4.341e-05, fmm_req_p: 5",
-            "it: 007, res: 2.744e-05, fmm_req_p: 5", "it: 008, res: 1.578e-05, fmm_req_p: 5",
-            "it: 009, res: 1.377e-05, fmm_req_p: 5", "Final residual: 8.1330e-06, after 10 iterations"]
-    lines = [l.strip() for l in out.splitlines()]
-    for w in want:
-        assert w in lines, (w, out)
-    assert "rhs error: 2.0203e+03" in lines
-    assert re.search(r"Fx: 0\.01911, analytical: 0\.01885", out), out
+    # lines of the unmodified reference (a Python replica of GMRES_Stokes.hpp over the oracle matvec prints the same on
+    # the CPU); residuals compared to 2e-3: the rotated residual estimate feels the rounding of the matvec in its 4th digit
+    want = [(1, 1.540e-03, 7), (2, 5.298e-04, 7), (3, 2.929e-04, 5), (4, 1.364e-04, 5), (5, 7.147e-05, 5),
+            (6, 4.341e-05, 5), (7, 2.744e-05, 5), (8, 1.578e-05, 5), (9, 1.377e-05, 5)]
+    got = [(int(a), float(b), int(c)) for a, b, c in re.findall(r"it: (\d+), res: ([0-9.eE+-]+), fmm_req_p: (\d+)", out)]
+    assert len(got) == len(want), out
+    for (i, r, p), (wi, wr, wp) in zip(got, want):
+        assert (i, p) == (wi, wp) and abs(r - wr) <= 2e-3 * wr, (got, out)
+    m = re.search(r"Final residual: ([0-9.eE+-]+), after (\d+) iterations", out)
+    assert m and int(m.group(2)) == 10 and abs(float(m.group(1)) - 8.1330e-06) <= 2e-3 * 8.1330e-06, out
+    m = re.search(r"rhs error: ([0-9.eE+-]+)", out)
+    assert m and abs(float(m.group(1)) - 2.0203e+03) <= 1e-3 * 2.0203e+03, out
+    # the driver prints x[0][0] times the total area (its loop never advances its index, examples/StokesBEM.cpp:341-352)
+    m = re.search(r"Fx: ([0-9.]+), analytical: 0\.01885", out)
+    assert m and abs(float(m.group(1)) - 0.01911) <= 2e-5, out
 
 
 def test_own_driver_device_gmres(tmp_path):
     """hostcxx/examples/stokes_bem.cpp: the same problem solved by the device-resident GMRES on Vec<3> unknowns with
-    the order rule of GMRES_Stokes.hpp:229.  Same iteration count and drag as the reference's run (above), and the
+    the order rule of GMRES_Stokes.hpp:229.  Same iteration count as the reference's run (above), the drag of the
+    solution the reference writes to out.charge (0.018695; the 0.01911 it prints is x[0][0] times the area), and the
     GPU matvec agrees with Direct::matvec of the host kernel class to the far-field truncation error."""
     exe = os.path.join(ROOT, "fmm_bem_relaxed_b200", "hostcxx", "bin", "stokes_bem")
     if not os.path.exists(exe):
@@ -147,8 +153,9 @@ def test_own_driver_device_gmres(tmp_path):
                                   env=env, timeout=600, cwd=str(tmp_path)).decode()
     assert float(re.search(r"matvec vs Direct \(first 100 rows\): ([0-9.eE+-]+)", out).group(1)) < 1e-4
     m = re.search(r"iterations: (\d+), final residual: ([0-9.eE+-]+)", out)
-    assert m and int(m.group(1)) == 10 and abs(float(m.group(2)) - 8.1330e-06) < 1e-9, out
-    assert re.search(r"Fx: 0\.01911, analytical: 0\.01885", out), out
+    assert m and int(m.group(1)) == 10 and abs(float(m.group(2)) - 8.1330e-06) < 2e-8, out
+    m = re.search(r"Fx: ([0-9.]+), analytical: 0\.01885", out)     # the true drag of that solution: 0.018695 (0.8 % low)
+    assert m and abs(float(m.group(1)) - 0.01870) <= 2e-5, out
 
 
 def test_python_gmres_on_vec3_unknowns():
@@ -158,11 +165,11 @@ def test_python_gmres_on_vec3_unknowns():
     plan = make_plan(verts, np.zeros(n, np.int32), 8, 4, 19, 1e-3)
     b = np.tile([4 * np.pi, 0.0, 0.0], (n, 1))
     rep = F.GMRES(plan, np.zeros((n, 3)), b, F.SolverOptions(residual=1e-5, max_iters=100, restart=100, max_p=8, p_min=5))
-    assert rep["iterations"] == 10 and abs(rep["final_residual"] - 8.1330e-06) < 1e-9
+    assert rep["iterations"] == 10 and abs(rep["final_residual"] - 8.1330e-06) < 2e-8
     assert rep["p_schedule"] == [7, 7, 5, 5, 5, 5, 5, 5, 5, 5]
     x = rep["x"].reshape(n, 3)
     area = 0.5 * np.linalg.norm(np.cross(verts[:, 2] - verts[:, 0], verts[:, 1] - verts[:, 0]), axis=1)
-    assert abs((x[:, 0] * area).sum() - 0.01911) < 1e-5
+    assert abs((x[:, 0] * area).sum() - 0.018695) < 1e-5
 
 
 @pytest.mark.parametrize("world", [2, 3])
