@@ -32,8 +32,8 @@ def test_c5_counts_accuracy_and_checksums():
     exact = F.Direct.matvec(plan, q, pts[:100])
     e_pot = O.rel_l2(res[:100, 0], exact[:, 0])
     e_force = O.rel_l2(res[:100, 1:], exact[:, 1:])
-    assert abs(e_pot - 1.083326e-06) < 0.02 * 1.083326e-06
-    assert abs(e_force - 3.772107e-05) < 0.02 * 3.772107e-05
+    assert abs(e_pot - 1.083326e-06) < 0.05 * 1.083326e-06
+    assert abs(e_force - 3.772107e-05) < 0.05 * 3.772107e-05
     pot = res[:, 0].sum()
     fxw = (res[:, 1] * (np.arange(n) % 7 + 1)).sum()
     assert abs(pot - 94107688197563.641) <= 1e-6 * 94107688197563.641
