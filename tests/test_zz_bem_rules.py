@@ -110,6 +110,30 @@ def test_yukawa_point_kernel_treecode_golden_fixture():
     assert O.rel_l2(plan.execute(g["charges"]), orc.yukawa_execute(g["charges"], 8, m["kappa"], treecode=True)) <= 1e-10
 
 
+def test_reference_laplacebem_driver_with_the_treecode_evaluator(tmp_path):
+    """bin/ref_LaplaceBEM (the reference's examples/LaplaceBEM.cpp compiled unchanged) with `-eval TREE`: the lines the
+    unmodified reference prints on one thread (oracle/_ref/LaplaceBEM -recursions 5 -p 8 -k 4 -solver_tol 1e-6 -eval TREE)."""
+    import re
+    import subprocess
+    from conftest import ROOT
+    exe = os.path.join(ROOT, "fmm_bem_relaxed_b200", "hostcxx", "bin", "ref_LaplaceBEM")
+    if not os.path.exists(exe):
+        pytest.skip(exe + " not built")
+    env = dict(os.environ)
+    env["LD_LIBRARY_PATH"] = os.path.join(ROOT, "fmm_bem_relaxed_b200") + ":" + env.get("LD_LIBRARY_PATH", "")
+    out = subprocess.check_output([exe, "-recursions", "5", "-p", "8", "-k", "4", "-solver_tol", "1e-6", "-eval", "TREE"],
+                                  env=env, timeout=600, cwd=str(tmp_path)).decode()
+    want = [(1, 2.030e-04, 8), (2, 9.140e-05, 8), (3, 4.232e-05, 7), (4, 1.847e-05, 6), (5, 8.457e-06, 5), (6, 3.965e-06, 4),
+            (7, 2.880e-06, 2), (8, 1.142e-06, 2)]
+    got = [(int(a), float(b), int(c)) for a, b, c in re.findall(r"it: (\d+), res: ([0-9.eE+-]+), fmm_req_p: (\d+)", out)]
+    assert len(got) == len(want), out
+    for (i, r, p), (wi, wr, wp) in zip(got, want):
+        assert (i, p) == (wi, wp) and abs(r - wr) <= 2e-3 * wr, (got, out)
+    m = re.search(r"Final residual: ([0-9.eE+-]+), after (\d+) iterations", out)
+    assert m and int(m.group(2)) == 9 and abs(float(m.group(1)) - 3.5761e-07) <= 5e-3 * 3.5761e-07, out
+    assert "relative error: 5.302e-03" in out
+
+
 def test_key_5_is_rejected():
     with pytest.raises(F.FmmbError):
         F.FMM_plan(F.LaplaceSphericalBEM(5, 5), F.Panels(O.unit_sphere(3)))
