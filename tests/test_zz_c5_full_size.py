@@ -3,8 +3,9 @@ theta = 0.5, ncrit = 64 -- through size-independent properties (the oracle canno
   * the device-built tree and lists have exactly the counts the reference's own Octree + MAC produce (SURVEY.md 8:
     299 673 boxes, 262 214 leaves, 7 721 718 near box pairs, 11 243 004 342 near body pairs, 33 183 336 M2L pairs);
   * the first 100 targets against the brute-force sum on the GPU reproduce the reference's printed errors
-    (1.083e-06 potential, 3.772e-05 force, SURVEY 8c);
-  * checksums against the reference's run (8 racy threads, so "indicative": 1e-6);
+    (1.083326e-06 potential, 3.772107e-05 force);
+  * checksums and the first result against the unmodified reference run on ONE thread (11 minutes in the build
+    container, tests/golden/checksums.json key c5_n10000000_p8; the 8-thread figures of SURVEY 8c are racy);
   * linearity and determinism.
 STATUS: first run at this size -- the kernels are the hardware-verified ones, the size is new -- so collected late and
 marked xfail(strict=False) until a run is recorded (python bench.py --n 10000000 times the same configuration).
@@ -32,14 +33,14 @@ def test_c5_counts_accuracy_and_checksums():
     exact = F.Direct.matvec(plan, q, pts[:100])
     e_pot = O.rel_l2(res[:100, 0], exact[:, 0])
     e_force = O.rel_l2(res[:100, 1:], exact[:, 1:])
-    assert abs(e_pot - 1.083326e-06) < 0.05 * 1.083326e-06
-    assert abs(e_force - 3.772107e-05) < 0.05 * 3.772107e-05
+    assert abs(e_pot - 1.083326e-06) < 1e-3 * 1.083326e-06
+    assert abs(e_force - 3.772107e-05) < 1e-3 * 3.772107e-05
     pot = res[:, 0].sum()
     fxw = (res[:, 1] * (np.arange(n) % 7 + 1)).sum()
-    assert abs(pot - 94107688197563.641) <= 1e-6 * 94107688197563.641
-    assert abs(fxw - (-6256844396.2503462)) <= 1e-4 * 6256844396.2503462      # a sum with heavy cancellation
+    assert abs(pot - 94107688197567.375) <= 1e-10 * 94107688197567.375
+    assert abs(fxw - (-6256841743.8522444)) <= 1e-8 * 6256841743.8522444      # a sum with heavy cancellation
     ref0 = np.array([6149948.1913637547, 4475840.7864965731, 5602940.2385787647, 5669542.2231329549])
-    assert np.allclose(res[0], ref0, rtol=1e-7)                      # 8-thread reference run: racy M2L, indicative
+    assert np.allclose(res[0], ref0, rtol=1e-10)
     assert np.array_equal(plan.execute(q), res)
     lhs = plan.execute(-2.5 * q)
     assert O.rel_l2(lhs, -2.5 * res) <= 1e-13
