@@ -335,3 +335,19 @@ def test_yukawa_treecode_restatement_matches_reference():
     for k in range(4):
         assert O.rel_l2(res[:, k], g["results"][:, k]) <= 1e-15
     assert 1e-6 < O.rel_l2(res[:, 0], orc.yukawa_execute(g["charges"], m["P"], m["kappa"], threads=1)[:, 0]) < 1e-3
+
+
+def test_full_size_known_answers_of_the_bem_classes():
+    """Sizes of BASELINE configs 2 / 3 (32 768 panels): the restatements against the unmodified reference on one thread.
+    StokesSphericalBEM FMM matvec: checksums printed by oracle/_ref/ref_stokes_bem_asis -recursions 7 -P 8 -K 4 -rand;
+    YukawaCartesianBEM treecode: tests/golden/yukawa_bem_tree_c3_32768_p8_bc0.npz from ref_yukawa_bem -tree."""
+    verts = O.unit_sphere(7)
+    n = len(verts)
+    q, _ = O.drand48_inputs(n)
+    res = O.StokesBemOracle(verts, 0, mu=1e-3, K=4, kfine=19, ncrit=64).execute(q, 8)
+    assert abs(res.sum() - 412026328.28298724) <= 1e-13 * 412026328.28298724
+    assert abs((res[:, 0] * (np.arange(n) % 7 + 1)).sum() - 550770297.18691444) <= 1e-13 * 550770297.18691444
+    assert np.array_equal(res[0], [4176.1890163885519, 4164.5741064921531, 4158.9512682252498])
+    g = dict(np.load(os.path.join(GOLDEN, "yukawa_bem_tree_c3_32768_p8_bc0.npz")))
+    got = O.YukawaBemOracle(verts, 0, 1.0, ncrit=64).execute(g["charges"], 8, 4, treecode=True)
+    assert O.rel_l2(got, g["results"]) <= 1e-15

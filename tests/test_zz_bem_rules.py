@@ -93,6 +93,21 @@ def test_yukawa_bem_treecode_golden_fixtures(bc):
     assert O.rel_l2(fmm, res) < (2e-4 if bc == 0 else 2e-3)
 
 
+def test_yukawa_bem_treecode_at_the_size_of_config_c3():
+    """BASELINE config 3 at full size (32 768 panels, kappa = 1, p = 8, k = 4) through the evaluator of the reference that
+    works for this kernel class: tests/golden/yukawa_bem_tree_c3_32768_p8_bc0.npz holds the charges and the results of
+    oracle/_ref/ref_yukawa_bem -recursions 7 -P 8 -K 4 -kappa 1 -tree (one thread, 14 s)."""
+    g = dict(np.load(os.path.join(GOLDEN, "yukawa_bem_tree_c3_32768_p8_bc0.npz")))
+    m = json.loads(str(g["meta"]))
+    verts = O.unit_sphere(m["recursions"])
+    opts = F.FMMOptions()
+    opts.evaluator = F.FMMOptions.TREECODE
+    plan = F.FMM_plan(F.YukawaCartesianBEM(m["P"], m["kappa"], m["K"]), F.Panels(verts, 0), opts)
+    res = plan.execute(g["charges"])
+    assert O.rel_l2(res, g["results"]) <= 1e-10
+    assert abs(res.sum() - m["sum"]) <= 1e-11 * m["sum"]
+
+
 def test_yukawa_point_kernel_treecode_golden_fixture():
     """YukawaCartesian with FMMOptions::TREECODE (yk_m2p_kernel) against ref_yukawa -tree: potential and gradient."""
     g = dict(np.load(os.path.join(GOLDEN, "yukawa_tree_n3000_p5.npz")))

@@ -256,3 +256,22 @@ def test_point_kernel_treecode_golden_fixtures(name, stresslet):
     for p in (3, 9):                                   # order changes, also above the batched-translation limit
         plan.kernel().set_p(p)
         assert O.rel_l2(plan.execute(g["charges"]), orc.stokes_execute(g["charges"], p, stresslet, treecode=True)) <= TOL
+
+
+def test_full_size_sphere_32768_panels_known_answer():
+    """The size of BASELINE config 2 (32 768 panels, p = 8, k = 4, ncrit 64) for the Stokes kernel class: checksums and
+    the first result of the UNMODIFIED reference on one thread (oracle/_ref/ref_stokes_bem_asis -recursions 7 -P 8 -K 4
+    -rand: sum 412026328.28298724, wsum 550770297.18691444; charges = its drand48 sequence), plus the oracle."""
+    verts = O.unit_sphere(7)
+    n = len(verts)
+    q, _ = O.drand48_inputs(n)                           # (drand48(), drand48(), drand48()) per panel, like the driver
+    plan = make_plan(verts, 0, 8)
+    i = plan.info()
+    assert (i.n_bodies, i.n_m2l_pairs, i.n_p2p_body_pairs) == (32768, 41516, 17077856)      # SURVEY 8, config C2's tree
+    res = plan.execute(q)
+    assert abs(res.sum() - 412026328.28298724) <= 1e-11 * 412026328.28298724
+    assert abs((res[:, 0] * (np.arange(n) % 7 + 1)).sum() - 550770297.18691444) <= 1e-11 * 550770297.18691444
+    assert np.allclose(res[0], [4176.1890163885519, 4164.5741064921531, 4158.9512682252498], rtol=1e-11)
+    want = O.StokesBemOracle(verts, 0, ncrit=64).execute(q, 8)
+    for k in range(3):
+        assert O.rel_l2(res[:, k], want[:, k]) <= TOL
