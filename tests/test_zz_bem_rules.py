@@ -108,6 +108,24 @@ def test_yukawa_bem_treecode_at_the_size_of_config_c3():
     assert abs(res.sum() - m["sum"]) <= 1e-11 * m["sum"]
 
 
+def test_yukawa_bem_driver_with_the_treecode_evaluator(tmp_path):
+    """hostcxx/examples/yukawa_bem.cpp with `-eval TREE` (get_options -> FMMOptions::TREECODE -> fmmb_options.evaluator):
+    the GPU matvec against Direct::matvec of the host kernel class, and a relaxed device-resident GMRES solve."""
+    import re
+    import subprocess
+    from conftest import ROOT
+    exe = os.path.join(ROOT, "fmm_bem_relaxed_b200", "hostcxx", "bin", "yukawa_bem")
+    if not os.path.exists(exe):
+        pytest.skip(exe + " not built")
+    env = dict(os.environ)
+    env["LD_LIBRARY_PATH"] = os.path.join(ROOT, "fmm_bem_relaxed_b200") + ":" + env.get("LD_LIBRARY_PATH", "")
+    out = subprocess.check_output([exe, "-recursions", "6", "-p", "8", "-k", "4", "-kappa", "1", "-solver_tol", "1e-6", "-check",
+                                   "200", "-eval", "TREE"], env=env, timeout=600, cwd=str(tmp_path)).decode()
+    assert float(re.search(r"matvec vs Direct \(first 200 rows\): ([0-9.eE+-]+)", out).group(1)) < 1e-4
+    m = re.search(r"iterations: (\d+), final residual: ([0-9.eE+-]+), relative error of the solution: ([0-9.eE+-]+)", out)
+    assert m and int(m.group(1)) < 60 and float(m.group(2)) < 1e-6 and float(m.group(3)) < 5e-3, out
+
+
 def test_yukawa_point_kernel_treecode_golden_fixture():
     """YukawaCartesian with FMMOptions::TREECODE (yk_m2p_kernel) against ref_yukawa -tree: potential and gradient."""
     g = dict(np.load(os.path.join(GOLDEN, "yukawa_tree_n3000_p5.npz")))
