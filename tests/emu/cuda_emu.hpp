@@ -25,7 +25,8 @@
 #include <vector>
 #include <algorithm>
 
-#define cudaMemcpyToSymbol(dst, src, n) (std::memcpy((void*)(dst), (src), (n)), cudaSuccess)
+namespace emu { template <class T> void* symbol(T& x) { return (void*)&x; } }     // arrays and objects alike
+#define cudaMemcpyToSymbol(dst, src, n) (std::memcpy(emu::symbol(dst), (src), (n)), cudaSuccess)
 #define cudaGetDevice(p) (*(p) = 0, cudaSuccess)
 
 namespace emu {
@@ -34,6 +35,9 @@ inline thread_local Idx threadIdx_, blockIdx_, blockDim_, gridDim_;
 inline thread_local std::barrier<>* warp_bar = nullptr;
 inline thread_local std::barrier<>* block_bar = nullptr;
 alignas(16) inline unsigned char dyn_shared[232448];
+
+inline size_t dyn_shared_limit = sizeof dyn_shared;     // bytes the current launch asked for (guard bytes follow)
+inline long launches = 0, guard_failures = 0;
 
 template <class F>
 void launch(dim3 grid, dim3 block, F&& body) {
@@ -56,7 +60,38 @@ void launch(dim3 grid, dim3 block, F&& body) {
       for (auto& t : th) t.join();
     }
 }
+
+// A launch as the host code writes it, kernel<<<grid, block, shmem, stream>>>(args): the dynamic shared segment is
+// exactly `shmem` bytes, followed by guard bytes that a kernel indexing past its request would overwrite.
+template <class F>
+void launch_cfg_impl(dim3 grid, dim3 block, size_t shmem, F&& body) {
+  ++launches;
+  if (grid.x == 0 || grid.y == 0 || block.x == 0 || block.x > 1024 || shmem + 64 > sizeof dyn_shared || shmem > 232448 - 1024) {
+    fprintf(stderr, "emu: invalid launch configuration grid (%u, %u) block %u shared %zu\n", grid.x, grid.y, block.x, shmem);
+    exit(5);
+  }
+  std::memset(dyn_shared + shmem, 0xA5, 64);
+  launch(grid, block, body);
+  for (int i = 0; i < 64; ++i)
+    if (dyn_shared[shmem + i] != 0xA5) { ++guard_failures; break; }
+}
+inline dim3 to_dim3(dim3 d) { return d; }
+template <class T> dim3 to_dim3(T v) { return dim3((unsigned)v); }
+template <class G, class B, class F>
+void launch_cfg(G grid, B block, size_t shmem, F&& body) { launch_cfg_impl(to_dim3(grid), to_dim3(block), shmem, body); }
 }  // namespace emu
+
+// ---- the few runtime calls the host side of a csrc/*.cu file makes, on host memory (after the CUDA headers: these
+// ---- function-like macros replace the calls, not the declarations)
+#define cudaMalloc(pp, bytes) (*(pp) = std::malloc(bytes), cudaSuccess)
+#define cudaFree(p) (std::free(p), cudaSuccess)
+#define cudaMemcpyAsync(dst, src, bytes, kind, stream) (std::memcpy((dst), (src), (bytes)), cudaSuccess)
+#define cudaMemsetAsync(dst, v, bytes, stream) (std::memset((dst), (v), (bytes)), cudaSuccess)
+#define cudaStreamSynchronize(s) (cudaSuccess)
+#define cudaEventRecord(e, s) (cudaSuccess)
+#define cudaStreamWaitEvent(s, e, f) (cudaSuccess)
+#define cudaGetLastError() (cudaSuccess)
+#define cudaFuncSetAttribute(f, a, v) (cudaSuccess)
 
 #define threadIdx emu::threadIdx_
 #define blockIdx emu::blockIdx_

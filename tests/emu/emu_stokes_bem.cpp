@@ -4,6 +4,8 @@
 //   near  <file>   sbem_setup_kernel, sbem_count_kernel, sbem_assemble_kernel, sbem_gather, sbem_near_kernel on a tree
 //                  and near-field lists written by the test (from the oracle); prints nothing, writes the near-field
 //                  result in ORIGINAL order to <file>.out
+//   pipeline <file>  stokes_bem_setup + stokes_bem_execute, the HOST functions of csrc/stokes_bem.cu as written (launch
+//                  configurations checked, translations stubbed: the test mesh has no far-field pairs); writes <file>.out
 //   direct <file>  sbem_direct_kernel / bem_direct_kernel (fmmb_plan_direct_panels) on panels and targets written by the
 //                  test; writes the sums to <file>.out
 //   far            sbem_p2m_kernel<0|1> against stokes_p2m_kernel<false|true> of csrc/stokes.cu (hardware-verified
@@ -28,9 +30,11 @@ namespace fmmb {
 namespace emu_stokes {
 #include "stokes_kernels.inc"
 }
-namespace emu_sbem {
-#include "sbem_kernels.inc"
-}
+// csrc/stokes_bem.cu whole, kernels AND host functions (launches rewritten to emu::launch_cfg), at fmmb scope so that
+// fmmb_plan::sbem points at its StokesBemData
+#include "sbem_whole.inc"
+namespace emu_sbem = ::fmmb;
+namespace emu_whole = ::fmmb;
 namespace emu_m2p {            // treecode: the point kernel of csrc/laplace.cu and the panel kernel of csrc/bem.cu
 using namespace ops;
 #include "lap_m2p.inc"
@@ -108,6 +112,85 @@ static int run_near(const char* path) {
   fwrite(out.data(), 8, out.size(), f);
   fclose(f);
   printf("near: n %ld items %ld pairs %lld\n", n, ni, base[ni]);
+  return 0;
+}
+
+// ---- host sequencing and launch configurations of csrc/stokes_bem.cu: stokes_bem_setup + stokes_bem_execute run as
+// written (DevBuf on host memory, every launch with its own grid / block / dynamic shared size, guard bytes behind the
+// shared segment) on a tree written by the test.  The test mesh has no far-field pairs, so the translations -- the one
+// thing not emulated -- are a stub; the far-field kernels still launch with their real configurations.
+namespace fmmb {
+static int g_translation_calls = 0;
+void laplace_translations(fmmb_plan*, cudaStream_t) { ++g_translation_calls; }
+void finish_results(fmmb_plan* plan, const double* near, const double* far, int rd, double* d_results, cudaStream_t) {
+  Tree& T = plan->tree;                                   // csrc/comm.cu: gen_combine_scatter on one rank
+  for (int64_t i = T.own_b0; i < T.own_b1; ++i)
+    for (int c = 0; c < rd; ++c) d_results[(size_t)T.perm.p[i] * rd + c] = near[i * rd + c] + far[i * rd + c];
+}
+}  // namespace fmmb
+
+// same file layout as `near`, followed by geom[4 nb] f64 (box centre x, y, z, side), parent[nb] u32, leaf[nb] u8 padded
+// to 4-byte entries (i32), P (i32), treecode (i32)
+static int run_pipeline(const char* path) {
+  std::vector<char> buf = slurp(path);
+  const char* p = buf.data();
+  const long long* hd = take<long long>(p, 4);
+  const long n = hd[0], nb = hd[1], ni = hd[2], ne = hd[3];
+  const int* ip = take<int>(p, 4);
+  const int K = ip[0], kfine = ip[1], as_written = ip[2];
+  const double mu = *take<double>(p, 1);
+  const double* verts = take<double>(p, 9 * n);
+  const int* bc = take<int>(p, n);
+  const unsigned* perm = take<unsigned>(p, n);
+  const unsigned* bb = take<unsigned>(p, nb);
+  const unsigned* be = take<unsigned>(p, nb);
+  const int* off = take<int>(p, nb + 1);
+  const int* src = take<int>(p, ne);
+  const int4* items = (const int4*)take<int>(p, 4 * ni);
+  const double* q = take<double>(p, 3 * n);
+  const double* geom = take<double>(p, 4 * nb);
+  const unsigned* parent = take<unsigned>(p, nb);
+  const int* leaf = take<int>(p, nb);
+  const int P = *take<int>(p, 1), treecode = *take<int>(p, 1);
+
+  upload_laplace_tables();
+  fmmb_plan plan;
+  plan.kind = FMMB_STOKES_SPHERICAL_BEM;
+  plan.p = P;
+  std::memset(&plan.opts, 0, sizeof plan.opts);
+  plan.opts.kernel_flags = as_written ? FMMB_FLAG_STOKES_BEM_AS_WRITTEN : 0;
+  plan.opts.evaluator = treecode ? FMMB_EVAL_TREECODE : FMMB_EVAL_FMM;
+  plan.charge_dim = plan.result_dim = 3;
+  Tree& T = plan.tree;
+  T.n = n; T.nboxes = (int)nb; T.own_b0 = 0; T.own_b1 = n;
+  T.perm.from_host(perm, n, nullptr);
+  T.bbegin.from_host(bb, nb, nullptr); T.bend.from_host(be, nb, nullptr);
+  T.parent.from_host(parent, nb, nullptr);
+  T.p2p_off.from_host(off, nb + 1, nullptr); T.p2p_src.from_host(src, ne, nullptr);
+  T.p2p_items.from_host(items, ni, nullptr); T.n_p2p_items = (int)ni;
+  std::vector<double4> cen(nb);
+  std::vector<int> leaves;
+  for (long b = 0; b < nb; ++b) { cen[b] = make_double4(geom[4 * b], geom[4 * b + 1], geom[4 * b + 2], geom[4 * b + 3]); if (leaf[b]) leaves.push_back((int)b); }
+  T.center.from_host(cen.data(), nb, nullptr);
+  T.leaves.from_host(leaves.data(), leaves.size(), nullptr); T.nleaves = (int)leaves.size();
+  T.own_leaves.from_host(leaves.data(), leaves.size(), nullptr); T.n_own_leaves = (int)leaves.size();
+  std::vector<unsigned char> hl(nb, 0);
+  T.has_local.from_host(hl.data(), nb, nullptr);
+  std::vector<int> zoff(nb + 1, 0);
+  T.m2l_off.from_host(zoff.data(), nb + 1, nullptr); T.m2l_src.resize(1);
+
+  emu_whole::stokes_bem_setup(&plan, verts, bc, K, kfine, mu);
+  std::vector<double> out(3 * n, -11.0), out2(3 * n, -12.0);
+  emu_whole::stokes_bem_execute(&plan, q, out.data());
+  emu_whole::stokes_bem_execute(&plan, q, out2.data());            // second call: no reallocation, same result
+  const bool same = out == out2;
+  std::string o = std::string(path) + ".out";
+  FILE* f = fopen(o.c_str(), "wb");
+  fwrite(out.data(), 8, out.size(), f);
+  fclose(f);
+  printf("pipeline: n %ld launches %ld (reported %d) translation_calls %d guard_failures %ld repeatable %d nnz %lld\n", n, emu::launches,
+         plan.launches, g_translation_calls, emu::guard_failures, (int)same, (long long)emu_whole::stokes_bem_nnz(plan.sbem));
+  emu_whole::stokes_bem_free(plan.sbem);
   return 0;
 }
 
@@ -545,7 +628,8 @@ int main(int argc, char** argv) {
   if (argc >= 2 && !strcmp(argv[1], "m2p")) return run_m2p();
   if (argc >= 3 && !strcmp(argv[1], "near")) return run_near(argv[2]);
   if (argc >= 3 && !strcmp(argv[1], "direct")) return run_direct(argv[2]);
+  if (argc >= 3 && !strcmp(argv[1], "pipeline")) return run_pipeline(argv[2]);
   if (argc >= 2 && !strcmp(argv[1], "far")) return run_far();
-  fprintf(stderr, "usage: emu_stokes_bem near <file> | direct <file> | far | m2p | ykm2p | stokes_m2p | bem_rules\n");
+  fprintf(stderr, "usage: emu_stokes_bem near <file> | direct <file> | pipeline <file> | far | m2p | ykm2p | stokes_m2p | bem_rules\n");
   return 2;
 }

@@ -11,7 +11,9 @@ per-lane arithmetic that will run on the B200 are these very source lines.  Chec
   * treecode -- bem_m2p_kernel<0|1> of csrc/bem.cu against m2p_kernel of csrc/laplace.cu (green on hardware);
     yk_bem_m2p_kernel<0|1> of csrc/yukawa.cu against yk_table_kernel (green on hardware) + a host dot product;
     stokes_m2p_kernel / sbem_m2p_kernel against four runs of m2p_kernel combined on the host.
-  * Direct::matvec kernels of fmmb_plan_direct_panels against the oracle's direct sums.
+  * Direct::matvec kernels of fmmb_plan_direct_panels against the oracle's direct sums;
+  * host sequencing -- stokes_bem_setup + stokes_bem_execute as written, each launch with its own configuration and
+    guard bytes behind the dynamic shared segment, on host memory (cudaMalloc / cudaMemcpyAsync ... as macros).
 This verifies kernel logic, not performance, and does not replace the first run on the device (tests/test_zz_stokes_bem.py).
 """
 import os
@@ -36,7 +38,9 @@ pytestmark = pytest.mark.skipif(not os.path.exists(os.path.join(CUDA_INC, "cuda_
 @pytest.fixture(scope="module")
 def emu(tmp_path_factory):
     d = tmp_path_factory.mktemp("emu")
-    for src, dst, names in (("stokes.cu", "stokes_kernels.inc", []), ("stokes_bem.cu", "sbem_kernels.inc", []),
+    subprocess.check_call(["python", os.path.join(EMU, "extract_kernels.py"), os.path.join(CSRC, "stokes_bem.cu"),
+                           str(d / "sbem_whole.inc"), "--whole"])
+    for src, dst, names in (("stokes.cu", "stokes_kernels.inc", []),
                             ("laplace.cu", "lap_m2p.inc", ["m2p_kernel"]), ("bem.cu", "bem_m2p.inc", ["bem_m2p_kernel"]),
                             ("bem.cu", "bem_kernels.inc", [])):
         subprocess.check_call(["python", os.path.join(EMU, "extract_kernels.py"), os.path.join(CSRC, src), str(d / dst)] + names)
@@ -157,3 +161,45 @@ def test_direct_matvec_kernels_match_the_oracle(emu, tmp_path, kind, as_written)
     assert "direct: n %d" % n in out
     got = np.fromfile(str(path) + ".out").reshape(want.shape)
     assert O.rel_l2(got, want) <= 1e-13
+
+
+@pytest.mark.parametrize("bcmix,as_written,treecode,P", [(0, False, False, 8), (2, True, False, 5), (1, False, True, 11), (2, False, True, 3)])
+def test_host_sequencing_and_launch_configurations_of_the_stokes_bem_plan(emu, tmp_path, bcmix, as_written, treecode, P):
+    """stokes_bem_setup + stokes_bem_execute of csrc/stokes_bem.cu -- the HOST functions as written, every launch with its
+    own grid, block and dynamic shared size (guard bytes behind the shared segment) -- on the 512-panel sphere, whose
+    lists have no far-field pairs (the translations, the one thing not emulated, are a stub): results against the oracle,
+    FMM and treecode evaluators, orders on both sides of the 4-warp / 1-warp P2M configuration switch."""
+    verts = O.unit_sphere(4)
+    n = len(verts)
+    bc = np.zeros(n, np.int32) if bcmix == 0 else (np.ones(n, np.int32) if bcmix == 1 else (np.arange(n) % 3 == 1).astype(np.int32))
+    mu, kfine, K = 0.02, 19, 4
+    orc = O.StokesBemOracle(verts, bc, mu=mu, K=K, kfine=kfine, as_written=as_written)
+    t = orc.tree()
+    assert len(t["lr"]) == 0
+    q = np.random.default_rng(5 + bcmix).random((n, 3)) - 0.4
+    want = orc.execute(q, P, threads=1, treecode=treecode)
+    boxes = t["boxes"]
+    bb, be, leaf = boxes[:, 4].astype(np.uint32), boxes[:, 5].astype(np.uint32), boxes[:, 7]
+    items = []
+    for b in np.nonzero(leaf)[0]:
+        for first in range(int(bb[b]), int(be[b]), 32):
+            items.append((int(b), first, min(32, int(be[b]) - first), 0))
+    items = np.array(items, np.int32)
+    path = tmp_path / "pipe.bin"
+    with open(path, "wb") as f:
+        f.write(struct.pack("<4q4id", n, len(boxes), len(items), len(t["p2p_idx"]), K, kfine, int(as_written), 0, mu))
+        for a in (np.ascontiguousarray(verts, np.float64), bc, t["perm"].astype(np.uint32), bb, be,
+                  t["p2p_off"].astype(np.int32), t["p2p_idx"].astype(np.int32), items, np.ascontiguousarray(q, np.float64),
+                  np.ascontiguousarray(t["geom"], np.float64), boxes[:, 1].astype(np.uint32), leaf.astype(np.int32),
+                  np.array([P, int(treecode)], np.int32)):
+            f.write(np.ascontiguousarray(a).tobytes())
+    out = subprocess.check_output([emu, "pipeline", str(path)], timeout=900).decode()
+    m = re.search(r"pipeline: n (\d+) launches (\d+) \(reported (\d+)\) translation_calls (\d+) guard_failures (\d+) repeatable (\d+) nnz (\d+)", out)
+    assert m, out
+    groups = len(set(bc.tolist()))
+    assert int(m.group(1)) == n and int(m.group(5)) == 0 and int(m.group(6)) == 1
+    assert int(m.group(4)) == 2 * 4 * groups                       # two matvecs x four sets per active group
+    assert int(m.group(7)) == int(t["p2p_off"][-1] and sum((be[b] - bb[b]) * sum(be[s] - bb[s] for s in t["p2p_idx"][t["p2p_off"][b]:t["p2p_off"][b + 1]]) for b in np.nonzero(leaf)[0]))
+    got = np.fromfile(str(path) + ".out").reshape(n, 3)
+    for k in range(3):
+        assert O.rel_l2(got[:, k], want[:, k]) <= 1e-13
