@@ -46,9 +46,12 @@ def emu(tmp_path_factory):
         subprocess.check_call(["python", os.path.join(EMU, "extract_kernels.py"), os.path.join(CSRC, src), str(d / dst)] + names)
     subprocess.check_call(["python", os.path.join(EMU, "extract_kernels.py"), os.path.join(CSRC, "yukawa.cu"),
                            str(d / "yukawa_kernels.inc"), "--until", "const double* yk_class_tables("])
+    subprocess.check_call(["python", os.path.join(EMU, "extract_kernels.py"), os.path.join(CSRC, "bem.cu"),
+                           str(d / "bem_whole.inc"), "--whole"])
     exe = str(d / "emu_stokes_bem")
-    subprocess.check_call(["g++", "-std=c++20", "-O1", "-pthread", "-I", CUDA_INC, "-I", str(d), "-I", EMU,
-                           os.path.join(EMU, "emu_stokes_bem.cpp"), "-o", exe, "-L/usr/local/cuda/lib64", "-lcudart"])
+    for src, out in (("emu_stokes_bem.cpp", exe), ("emu_bem_pipeline.cpp", str(d / "emu_bem_pipeline"))):
+        subprocess.check_call(["g++", "-std=c++20", "-O1", "-pthread", "-I", CUDA_INC, "-I", str(d), "-I", EMU,
+                               os.path.join(EMU, src), "-o", out, "-L/usr/local/cuda/lib64", "-lcudart"])
     return exe
 
 
@@ -203,3 +206,41 @@ def test_host_sequencing_and_launch_configurations_of_the_stokes_bem_plan(emu, t
     got = np.fromfile(str(path) + ".out").reshape(n, 3)
     for k in range(3):
         assert O.rel_l2(got[:, k], want[:, k]) <= 1e-13
+
+
+@pytest.mark.parametrize("K,treecode,P", [(4, False, 8), (13, False, 6), (25, True, 9), (4, True, 5), (79, False, 3)])
+def test_host_sequencing_of_the_laplace_bem_plan_with_high_rules_and_treecode(emu, tmp_path, K, treecode, P):
+    """bem_setup + bem_execute of csrc/bem.cu as written (same emulation as above) on the 512-panel sphere with mixed
+    boundary conditions: the Gauss rules above 4 points in setup / assembly / P2M and the treecode branch
+    (bem_m2p_kernel) with their launch configurations; K = 4 without treecode is the hardware-verified path, as a
+    control.  Results against the oracle (K = 79 is not in the oracle: finite values and repeatability only)."""
+    verts = O.unit_sphere(4)
+    n = len(verts)
+    bc = (np.arange(n) % 2).astype(np.int32)
+    orc = O.BemOracle(verts, bc)
+    t = orc.tree()
+    assert len(t["lr"]) == 0
+    q = np.random.default_rng(K).random(n) - 0.4
+    boxes = t["boxes"]
+    bb, be, leaf = boxes[:, 4].astype(np.uint32), boxes[:, 5].astype(np.uint32), boxes[:, 7]
+    items = []
+    for b in np.nonzero(leaf)[0]:
+        for first in range(int(bb[b]), int(be[b]), 32):
+            items.append((int(b), first, min(32, int(be[b]) - first), 0))
+    items = np.array(items, np.int32)
+    path = tmp_path / "bem.bin"
+    with open(path, "wb") as f:
+        f.write(struct.pack("<4q4i", n, len(boxes), len(items), len(t["p2p_idx"]), K, P, int(treecode), 0))
+        for a in (np.ascontiguousarray(verts, np.float64), bc, t["perm"].astype(np.uint32), bb, be,
+                  t["p2p_off"].astype(np.int32), t["p2p_idx"].astype(np.int32), items, np.ascontiguousarray(q, np.float64),
+                  np.ascontiguousarray(t["geom"], np.float64), boxes[:, 1].astype(np.uint32), leaf.astype(np.int32)):
+            f.write(np.ascontiguousarray(a).tobytes())
+    exe = os.path.join(os.path.dirname(emu), "emu_bem_pipeline")
+    out = subprocess.check_output([exe, str(path)], timeout=900).decode()
+    m = re.search(r"bem pipeline: n (\d+) launches (\d+) translation_calls (\d+) guard_failures (\d+) repeatable (\d+)", out)
+    assert m, out
+    assert int(m.group(1)) == n and int(m.group(4)) == 0 and int(m.group(5)) == 1 and int(m.group(3)) == 2 * 2
+    got = np.fromfile(str(path) + ".out")
+    assert np.isfinite(got).all()
+    if K != 79:
+        assert O.rel_l2(got, orc.execute(q, P, K, threads=1, treecode=treecode)) <= 1e-13
