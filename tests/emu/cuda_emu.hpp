@@ -102,5 +102,7 @@ inline void __syncthreads() { emu::block_bar->arrive_and_wait(); }
 inline double __ddiv_rn(double a, double b) { return a / b; }
 inline double __shfl_sync(unsigned, double, int) { fprintf(stderr, "emu: warp shuffles are not emulated\n"); abort(); }
 inline double __shfl_xor_sync(unsigned, double, int) { fprintf(stderr, "emu: warp shuffles are not emulated\n"); abort(); }
+inline unsigned atomicAdd(unsigned* p, unsigned v) { unsigned o = *p; *p += v; return o; }   // blocks run one at a time and
+inline void __threadfence() {}                                                               // one thread per block calls it
 using std::min;
 using std::max;

@@ -6,6 +6,8 @@
 //                  result in ORIGINAL order to <file>.out
 //   pipeline <file>  stokes_bem_setup + stokes_bem_execute, the HOST functions of csrc/stokes_bem.cu as written (launch
 //                  configurations checked, translations stubbed: the test mesh has no far-field pairs); writes <file>.out
+//   gmres <file>   gmres_solve of csrc/gmres.cu as written (fmmb_gmres on Vec<3> unknowns) over the emulated
+//                  stokes_bem_execute: the sphere problem of examples/StokesBEM.cpp; writes the solution to <file>.out
 //   direct <file>  sbem_direct_kernel / bem_direct_kernel (fmmb_plan_direct_panels) on panels and targets written by the
 //                  test; writes the sums to <file>.out
 //   far            sbem_p2m_kernel<0|1> against stokes_p2m_kernel<false|true> of csrc/stokes.cu (hardware-verified
@@ -35,6 +37,10 @@ namespace emu_stokes {
 #include "sbem_whole.inc"
 namespace emu_sbem = ::fmmb;
 namespace emu_whole = ::fmmb;
+// csrc/gmres.cu whole (its anonymous-namespace helper nblk renamed: stokes_bem.cu has one of that name at this scope)
+#define nblk gm_nblk
+#include "gmres_whole.inc"
+#undef nblk
 namespace emu_m2p {            // treecode: the point kernel of csrc/laplace.cu and the panel kernel of csrc/bem.cu
 using namespace ops;
 #include "lap_m2p.inc"
@@ -122,6 +128,7 @@ static int run_near(const char* path) {
 namespace fmmb {
 static int g_translation_calls = 0;
 void laplace_translations(fmmb_plan*, cudaStream_t) { ++g_translation_calls; }
+void run_matvec_for_solver(fmmb_plan* plan, const double* q, double* r) { stokes_bem_execute(plan, q, r); }   // capi.cu
 void finish_results(fmmb_plan* plan, const double* near, const double* far, int rd, double* d_results, cudaStream_t) {
   Tree& T = plan->tree;                                   // csrc/comm.cu: gen_combine_scatter on one rank
   for (int64_t i = T.own_b0; i < T.own_b1; ++i)
@@ -131,7 +138,7 @@ void finish_results(fmmb_plan* plan, const double* near, const double* far, int 
 
 // same file layout as `near`, followed by geom[4 nb] f64 (box centre x, y, z, side), parent[nb] u32, leaf[nb] u8 padded
 // to 4-byte entries (i32), P (i32), treecode (i32)
-static int run_pipeline(const char* path) {
+static int run_pipeline(const char* path, bool solve = false) {
   std::vector<char> buf = slurp(path);
   const char* p = buf.data();
   const long long* hd = take<long long>(p, 4);
@@ -180,6 +187,30 @@ static int run_pipeline(const char* path) {
   T.m2l_off.from_host(zoff.data(), nb + 1, nullptr); T.m2l_src.resize(1);
 
   emu_whole::stokes_bem_setup(&plan, verts, bc, K, kfine, mu);
+  if (solve) {
+    // fmmb_gmres on Vec<3> unknowns (csrc/gmres.cu as written): the sphere problem of examples/StokesBEM.cpp,
+    // b = (4 pi, 0, 0) per panel, x0 = 0, order rule of GMRES_Stokes.hpp:229
+    plan.bem = nullptr;
+    std::vector<double> b(3 * n), x(3 * n, 0.0), hist(256);
+    for (long i = 0; i < n; ++i) { b[3 * i] = 4 * M_PI; b[3 * i + 1] = b[3 * i + 2] = 0.0; }
+    fmmb_solver_options so = {1e-5, 100, 100, 8u, 1, 0, 0, 5u, 1u};
+    fmmb_gmres_info info = {};
+    std::vector<int32_t> ps(256);
+    gmres_solve(&plan, b.data(), x.data(), nullptr, so, &info, ps.data(), hist.data(), 256);
+    std::string o = std::string(path) + ".out";
+    FILE* f = fopen(o.c_str(), "wb");
+    fwrite(x.data(), 8, x.size(), f);
+    fclose(f);
+    printf("gmres: iterations %d final_residual %.6e final_p %d guard_failures %ld schedule", info.iterations, info.final_residual,
+           info.final_p, emu::guard_failures);
+    for (int k = 0; k < info.n_records && k < 256; ++k) printf(" %d", ps[k]);
+    printf("\nresiduals");
+    for (int k = 0; k < info.n_records && k < 256; ++k) printf(" %.6e", hist[k]);
+    printf("\n");
+    gmres_free(plan.gmres_ws);
+    emu_whole::stokes_bem_free(plan.sbem);
+    return 0;
+  }
   std::vector<double> out(3 * n, -11.0), out2(3 * n, -12.0);
   emu_whole::stokes_bem_execute(&plan, q, out.data());
   emu_whole::stokes_bem_execute(&plan, q, out2.data());            // second call: no reallocation, same result
@@ -629,7 +660,8 @@ int main(int argc, char** argv) {
   if (argc >= 3 && !strcmp(argv[1], "near")) return run_near(argv[2]);
   if (argc >= 3 && !strcmp(argv[1], "direct")) return run_direct(argv[2]);
   if (argc >= 3 && !strcmp(argv[1], "pipeline")) return run_pipeline(argv[2]);
+  if (argc >= 3 && !strcmp(argv[1], "gmres")) return run_pipeline(argv[2], true);
   if (argc >= 2 && !strcmp(argv[1], "far")) return run_far();
-  fprintf(stderr, "usage: emu_stokes_bem near <file> | direct <file> | pipeline <file> | far | m2p | ykm2p | stokes_m2p | bem_rules\n");
+  fprintf(stderr, "usage: emu_stokes_bem near <file> | direct <file> | pipeline <file> | gmres <file> | far | m2p | ykm2p | stokes_m2p | bem_rules\n");
   return 2;
 }

@@ -40,6 +40,8 @@ def emu(tmp_path_factory):
     d = tmp_path_factory.mktemp("emu")
     subprocess.check_call(["python", os.path.join(EMU, "extract_kernels.py"), os.path.join(CSRC, "stokes_bem.cu"),
                            str(d / "sbem_whole.inc"), "--whole"])
+    subprocess.check_call(["python", os.path.join(EMU, "extract_kernels.py"), os.path.join(CSRC, "gmres.cu"),
+                           str(d / "gmres_whole.inc"), "--whole"])
     for src, dst, names in (("stokes.cu", "stokes_kernels.inc", []),
                             ("laplace.cu", "lap_m2p.inc", ["m2p_kernel"]), ("bem.cu", "bem_m2p.inc", ["bem_m2p_kernel"]),
                             ("bem.cu", "bem_kernels.inc", [])):
@@ -244,3 +246,48 @@ def test_host_sequencing_of_the_laplace_bem_plan_with_high_rules_and_treecode(em
     assert np.isfinite(got).all()
     if K != 79:
         assert O.rel_l2(got, orc.execute(q, P, K, threads=1, treecode=treecode)) <= 1e-13
+
+
+def test_device_gmres_on_vec3_unknowns_matches_the_replica_of_gmres_stokes(emu, tmp_path):
+    """gmres_solve of csrc/gmres.cu as written -- fmmb_gmres with charge_dim 3, the order rule of GMRES_Stokes.hpp:229,
+    Krylov basis, dot / axpy kernels and their launches -- over the emulated stokes_bem_execute, on the sphere problem of
+    examples/StokesBEM.cpp with 512 panels; against the Python replica of the reference's GMRES_Stokes.hpp over the
+    oracle matvec (tests/test_stokes_solve_replica.py): same iteration count, same order schedule, same residual
+    history, same solution."""
+    from test_stokes_solve_replica import gmres_stokes
+    verts = O.unit_sphere(4)
+    n = len(verts)
+    bc = np.zeros(n, np.int32)
+    mu, kfine, K, P = 1e-3, 19, 4, 8
+    orc = O.StokesBemOracle(verts, bc, mu=mu, K=K, kfine=kfine, as_written=False)
+    t = orc.tree()
+    assert len(t["lr"]) == 0
+    b = np.tile([4 * np.pi, 0.0, 0.0], (n, 1)).reshape(-1)
+    x, it, res, lines = gmres_stokes(lambda v, p: orc.execute(v.reshape(-1, 3), p).reshape(-1), b, 1e-5, 8, 5)
+    boxes = t["boxes"]
+    bb, be, leaf = boxes[:, 4].astype(np.uint32), boxes[:, 5].astype(np.uint32), boxes[:, 7]
+    items = []
+    for bx in np.nonzero(leaf)[0]:
+        for first in range(int(bb[bx]), int(be[bx]), 32):
+            items.append((int(bx), first, min(32, int(be[bx]) - first), 0))
+    items = np.array(items, np.int32)
+    path = tmp_path / "gmres.bin"
+    with open(path, "wb") as f:
+        f.write(struct.pack("<4q4id", n, len(boxes), len(items), len(t["p2p_idx"]), K, kfine, 0, 0, mu))
+        for a in (np.ascontiguousarray(verts, np.float64), bc, t["perm"].astype(np.uint32), bb, be,
+                  t["p2p_off"].astype(np.int32), t["p2p_idx"].astype(np.int32), items, np.zeros(3 * n),
+                  np.ascontiguousarray(t["geom"], np.float64), boxes[:, 1].astype(np.uint32), leaf.astype(np.int32),
+                  np.array([P, 0], np.int32)):
+            f.write(np.ascontiguousarray(a).tobytes())
+    out = subprocess.check_output([emu, "gmres", str(path)], timeout=1800).decode()
+    m = re.search(r"gmres: iterations (\d+) final_residual ([0-9.eE+-]+) final_p (\d+) guard_failures (\d+) schedule((?: \d+)+)", out)
+    assert m, out
+    sched = [int(v) for v in m.group(5).split()]
+    hist = [float(v) for v in re.search(r"residuals((?: [0-9.eE+-]+)+)", out).group(1).split()]
+    assert int(m.group(1)) == it and int(m.group(4)) == 0
+    assert sched[:len(lines)] == [p for _, _, p in lines] and len(sched) == it
+    for h, (_, r, _) in zip(hist, lines):
+        assert abs(h - r) <= 1e-6 * r
+    assert abs(float(m.group(2)) - res) <= 1e-6 * res
+    got = np.fromfile(str(path) + ".out")
+    assert O.rel_l2(got, x) <= 1e-9
