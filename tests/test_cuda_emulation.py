@@ -44,6 +44,7 @@ def emu(tmp_path_factory):
                            str(d / "gmres_whole.inc"), "--whole"])
     for src, dst, names in (("stokes.cu", "stokes_kernels.inc", []),
                             ("laplace.cu", "lap_m2p.inc", ["m2p_kernel"]), ("bem.cu", "bem_m2p.inc", ["bem_m2p_kernel"]),
+                            ("laplace.cu", "lap_trans.inc", ["m2m_kernel", "m2l_coeff_kernel", "m2l_pair_kernel", "l2l_kernel"]),
                             ("bem.cu", "bem_kernels.inc", [])):
         subprocess.check_call(["python", os.path.join(EMU, "extract_kernels.py"), os.path.join(CSRC, src), str(d / dst)] + names)
     subprocess.check_call(["python", os.path.join(EMU, "extract_kernels.py"), os.path.join(CSRC, "yukawa.cu"),
@@ -291,3 +292,66 @@ def test_device_gmres_on_vec3_unknowns_matches_the_replica_of_gmres_stokes(emu, 
     assert abs(float(m.group(2)) - res) <= 1e-6 * res
     got = np.fromfile(str(path) + ".out")
     assert O.rel_l2(got, x) <= 1e-9
+
+
+def _write_pipeline_file(path, verts, bc, t, q, K, kfine, as_written, mu, P, treecode, far):
+    """File of `emu_stokes_bem pipeline`: tree and near-field lists, optionally the far-field structures."""
+    n = len(verts)
+    boxes = t["boxes"]
+    bb, be, leaf = boxes[:, 4].astype(np.uint32), boxes[:, 5].astype(np.uint32), boxes[:, 7]
+    items = []
+    for b in np.nonzero(leaf)[0]:
+        for first in range(int(bb[b]), int(be[b]), 32):
+            items.append((int(b), first, min(32, int(be[b]) - first), 0))
+    items = np.array(items, np.int32)
+    with open(path, "wb") as f:
+        f.write(struct.pack("<4q4id", n, len(boxes), len(items), len(t["p2p_idx"]), K, kfine, int(as_written), 0, mu))
+        for a in (np.ascontiguousarray(verts, np.float64), bc, t["perm"].astype(np.uint32), bb, be,
+                  t["p2p_off"].astype(np.int32), t["p2p_idx"].astype(np.int32), items, np.ascontiguousarray(q, np.float64),
+                  np.ascontiguousarray(t["geom"], np.float64), boxes[:, 1].astype(np.uint32), leaf.astype(np.int32),
+                  np.array([P, int(treecode)], np.int32)):
+            f.write(np.ascontiguousarray(a).tobytes())
+        if far:
+            nb = len(boxes)
+            lr = t["lr"].astype(np.int64)
+            order = np.argsort(lr[:, 1], kind="stable")                 # target-major, list order inside a target
+            m2l_off = np.zeros(nb + 1, np.int32)
+            np.add.at(m2l_off, lr[:, 1] + 1, 1)
+            m2l_off = np.cumsum(m2l_off).astype(np.int32)
+            has_local = np.zeros(nb, np.int32)
+            has_local[lr[:, 1]] = 1
+            level = boxes[:, 6].astype(np.int64)
+            nlevels = int(level.max()) + 1
+            for b in range(1, nb):                                       # parents precede children
+                if has_local[boxes[b, 1]]:
+                    has_local[b] = 1
+            level_off = np.searchsorted(level, np.arange(nlevels + 1)).astype(np.int32)
+            f.write(struct.pack("<q2i", len(lr), nlevels, 0))
+            for a in (boxes[:, 0].astype(np.uint32), boxes[:, 2].astype(np.uint32), boxes[:, 3].astype(np.uint32), level_off,
+                      m2l_off, lr[order, 0].astype(np.int32), has_local):
+                f.write(np.ascontiguousarray(a).tobytes())
+
+
+@pytest.mark.parametrize("name,treecode", [("stokes_bem_2048_p6_bc2", False), ("stokes_bem_tree_asis_2048_p6_bc2", True)])
+def test_whole_stokes_bem_matvec_with_far_field_against_the_reference_fixtures(emu, tmp_path, name, treecode):
+    """The complete StokesSphericalBEM matvec of csrc/stokes_bem.cu on the CPU: host functions as written, all their
+    kernels, and for the translations the per-pair kernels of csrc/laplace.cu (M2M sweep, M2L per target box, L2L sweep:
+    the path behind P > 8 / m2l_mode 1, with laplace_translations' launch configurations; the class-batched DMMA path is
+    PTX and is not emulated).  2 048 panels with a real far field, against the golden fixtures of the reference."""
+    import json
+    from conftest import GOLDEN
+    g = dict(np.load(os.path.join(GOLDEN, name + ".npz")))
+    m = json.loads(str(g["meta"]))
+    orc = O.StokesBemOracle(g["verts"], g["bc"], mu=m["mu"], K=m["K"], kfine=m["kfine"], as_written=m["as_written"],
+                            ncrit=m["ncrit"], theta=m["theta"])
+    t = orc.tree()
+    assert len(t["lr"]) > 1000
+    path = tmp_path / "whole.bin"
+    _write_pipeline_file(path, g["verts"], g["bc"].astype(np.int32), t, g["charges"], m["K"], m["kfine"], m["as_written"],
+                         m["mu"], m["P"], treecode, far=True)
+    out = subprocess.check_output([emu, "pipeline", str(path)], timeout=3000).decode()
+    mm = re.search(r"guard_failures (\d+) repeatable (\d+)", out)
+    assert mm and int(mm.group(1)) == 0, out
+    got = np.fromfile(str(path) + ".out").reshape(-1, 3)
+    for k in range(3):
+        assert O.rel_l2(got[:, k], g["results"][:, k]) <= 1e-10
