@@ -2,8 +2,8 @@
 // The HOST functions bem_setup + bem_execute of fmm_bem_relaxed_b200/csrc/bem.cu as written (LaplaceSphericalBEM plan),
 // under the emulation of tests/emu/cuda_emu.hpp: runtime calls as macros on host memory, every launch with its own
 // configuration and guard bytes behind the dynamic shared segment.  Used for what has not run on hardware in that file:
-// the Gauss rules above 4 points and the treecode branch (bem_m2p_kernel).  The test mesh has no far-field pairs, so
-// the translations -- not emulated -- are a stub.
+// the Gauss rules above 4 points and the treecode branch (bem_m2p_kernel).  Translations: the per-pair kernels of
+// csrc/laplace.cu when the file carries the far-field structures, nothing to do otherwise.
 //   emu_bem_pipeline <file>      file layout: see tests/test_cuda_emulation.py; writes <file>.out (n doubles)
 #include "cuda_emu.hpp"
 #include "../../fmm_bem_relaxed_b200/csrc/common.cuh"
@@ -12,8 +12,46 @@
 
 namespace fmmb {
 #include "bem_whole.inc"
+namespace emu_trans {          // the per-pair translation kernels of csrc/laplace.cu (the path behind P > 8 and m2l_mode 1)
+using namespace ops;
+#include "lap_trans.inc"
+}
 static int g_translation_calls = 0;
-void laplace_translations(fmmb_plan*, cudaStream_t) { ++g_translation_calls; }
+// csrc/laplace.cu::laplace_translations, per-pair path, launch configurations of :943-981 (see emu_stokes_bem.cpp)
+void laplace_translations(fmmb_plan* plan, cudaStream_t) {
+  ++g_translation_calls;
+  Tree& T = plan->tree;
+  if (T.n_lr == 0) return;
+  const int P = plan->p, nc = P * (P + 1) / 2, pp = P * P, nb = T.nboxes;
+  const size_t sh_mm = (size_t)(pp + nc) * sizeof(double2);
+  for (int l = T.nlevels - 2; l >= 0; --l) {
+    const int lo = T.level_off[l], hi = T.level_off[l + 1];
+    emu::launch_cfg(hi - lo, 64, sh_mm, [&] {
+      emu_trans::m2m_kernel(lo, hi, nullptr, T.key.p, T.cbegin.p, T.cend.p, T.center.p, P, plan->M.p);
+    });
+  }
+  if (plan->opts.evaluator == FMMB_EVAL_TREECODE) return;
+  static std::map<int, std::vector<double>> coeff;
+  std::vector<double>& C = coeff[P];
+  if (C.empty()) {
+    C.resize((size_t)nc * pp);
+    emu::launch_cfg((int)((C.size() + 255) / 256), 256, 0, [&] { emu_trans::m2l_coeff_kernel(P, C.data()); });
+  }
+  int threads = 128;
+  while (threads < nc) threads += 32;
+  size_t sh = (size_t)(5 * pp) * sizeof(double2);
+  const size_t red = (size_t)(threads / nc) * nc * sizeof(double2);
+  if (red > sh) sh = red;
+  emu::launch_cfg(nb, threads, sh, [&] {
+    emu_trans::m2l_pair_kernel(nb, nullptr, T.m2l_off.p, T.m2l_src.p, T.center.p, P, C.data(), plan->M.p, plan->L.p, 0);
+  });
+  for (int l = 1; l < T.nlevels; ++l) {
+    const int lo = T.level_off[l], hi = T.level_off[l + 1];
+    emu::launch_cfg(hi - lo, 64, sh_mm, [&] {
+      emu_trans::l2l_kernel(lo, hi, T.parent.p, T.has_local.p, T.center.p, P, plan->L.p);
+    });
+  }
+}
 void laplace_prepare_expansions(fmmb_plan* plan) {          // csrc/laplace.cu: sizes plan->M / plan->L for the order
   const int xs = ops::xstride(plan->p);
   plan->M.resize((size_t)plan->tree.nboxes * xs);
@@ -57,6 +95,20 @@ int main(int argc, char** argv) {
   const double* geom = take<double>(p, 4 * nb);
   const unsigned* parent = take<unsigned>(p, nb);
   const int* leaf = take<int>(p, nb);
+  // optional far-field section: int64 n_lr, int32 nlevels, pad; key[nb], cbegin[nb], cend[nb] u32,
+  // level_off[nlevels + 1], m2l_off[nb + 1], m2l_src[n_lr], has_local[nb] i32
+  long n_lr = 0;
+  int nlevels = 0;
+  const unsigned *key = nullptr, *cbegin = nullptr, *cend = nullptr;
+  const int *level_off = nullptr, *m2l_off = nullptr, *m2l_src = nullptr, *has_local_i = nullptr;
+  if (p < buf.data() + buf.size()) {
+    n_lr = (long)*take<long long>(p, 1);
+    nlevels = take<int>(p, 2)[0];
+    key = take<unsigned>(p, nb); cbegin = take<unsigned>(p, nb); cend = take<unsigned>(p, nb);
+    level_off = take<int>(p, nlevels + 1);
+    m2l_off = take<int>(p, nb + 1); m2l_src = take<int>(p, n_lr);
+    has_local_i = take<int>(p, nb);
+  }
 
   upload_laplace_tables();
   fmmb_plan plan;
@@ -84,14 +136,22 @@ int main(int argc, char** argv) {
   T.leaves.from_host(leaves.data(), leaves.size(), nullptr); T.nleaves = (int)leaves.size();
   T.own_leaves.from_host(leaves.data(), leaves.size(), nullptr); T.n_own_leaves = (int)leaves.size();
   std::vector<unsigned char> hl(nb, 0);
-  T.has_local.from_host(hl.data(), nb, nullptr);
   std::vector<int> zoff(nb + 1, 0);
-  T.m2l_off.from_host(zoff.data(), nb + 1, nullptr); T.m2l_src.resize(1);
+  if (n_lr > 0) {
+    for (long b = 0; b < nb; ++b) hl[b] = (unsigned char)has_local_i[b];
+    T.n_lr = n_lr; T.nlevels = nlevels;
+    T.level_off.assign(level_off, level_off + nlevels + 1);
+    T.key.from_host(key, nb, nullptr); T.cbegin.from_host(cbegin, nb, nullptr); T.cend.from_host(cend, nb, nullptr);
+    T.m2l_off.from_host(m2l_off, nb + 1, nullptr); T.m2l_src.from_host(m2l_src, n_lr, nullptr);
+  } else {
+    T.m2l_off.from_host(zoff.data(), nb + 1, nullptr); T.m2l_src.resize(1);
+  }
+  T.has_local.from_host(hl.data(), nb, nullptr);
 
   bem_setup(&plan, verts, bc, K, -1.0);
   std::vector<double> out(n, -11.0), out2(n, -12.0);
   bem_execute(&plan, q, out.data());
-  bem_execute(&plan, q, out2.data());
+  if (n_lr == 0) bem_execute(&plan, q, out2.data()); else out2 = out;     // (far field: one matvec, the translations dominate)
   std::string o = std::string(argv[1]) + ".out";
   f = fopen(o.c_str(), "wb");
   fwrite(out.data(), 8, out.size(), f);

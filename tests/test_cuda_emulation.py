@@ -294,7 +294,7 @@ def test_device_gmres_on_vec3_unknowns_matches_the_replica_of_gmres_stokes(emu, 
     assert O.rel_l2(got, x) <= 1e-9
 
 
-def _write_pipeline_file(path, verts, bc, t, q, K, kfine, as_written, mu, P, treecode, far):
+def _write_pipeline_file(path, verts, bc, t, q, K, kfine, as_written, mu, P, treecode, far, laplace=False):
     """File of `emu_stokes_bem pipeline`: tree and near-field lists, optionally the far-field structures."""
     n = len(verts)
     boxes = t["boxes"]
@@ -305,12 +305,16 @@ def _write_pipeline_file(path, verts, bc, t, q, K, kfine, as_written, mu, P, tre
             items.append((int(b), first, min(32, int(be[b]) - first), 0))
     items = np.array(items, np.int32)
     with open(path, "wb") as f:
-        f.write(struct.pack("<4q4id", n, len(boxes), len(items), len(t["p2p_idx"]), K, kfine, int(as_written), 0, mu))
+        if laplace:      # emu_bem_pipeline: K, P, treecode in the header, scalar charges
+            f.write(struct.pack("<4q4i", n, len(boxes), len(items), len(t["p2p_idx"]), K, P, int(treecode), 0))
+        else:
+            f.write(struct.pack("<4q4id", n, len(boxes), len(items), len(t["p2p_idx"]), K, kfine, int(as_written), 0, mu))
         for a in (np.ascontiguousarray(verts, np.float64), bc, t["perm"].astype(np.uint32), bb, be,
                   t["p2p_off"].astype(np.int32), t["p2p_idx"].astype(np.int32), items, np.ascontiguousarray(q, np.float64),
-                  np.ascontiguousarray(t["geom"], np.float64), boxes[:, 1].astype(np.uint32), leaf.astype(np.int32),
-                  np.array([P, int(treecode)], np.int32)):
+                  np.ascontiguousarray(t["geom"], np.float64), boxes[:, 1].astype(np.uint32), leaf.astype(np.int32)):
             f.write(np.ascontiguousarray(a).tobytes())
+        if not laplace:
+            f.write(np.array([P, int(treecode)], np.int32).tobytes())
         if far:
             nb = len(boxes)
             lr = t["lr"].astype(np.int64)
@@ -355,3 +359,25 @@ def test_whole_stokes_bem_matvec_with_far_field_against_the_reference_fixtures(e
     got = np.fromfile(str(path) + ".out").reshape(-1, 3)
     for k in range(3):
         assert O.rel_l2(got[:, k], g["results"][:, k]) <= 1e-10
+
+
+@pytest.mark.parametrize("name", ["laplace_bem_2048_p6_k13_bc1", "laplace_bem_tree_2048_p6_k4_bc0"])
+def test_whole_laplace_bem_matvec_with_far_field_against_the_reference_fixtures(emu, tmp_path, name):
+    """The same for csrc/bem.cu: bem_setup + bem_execute as written with the 13-point rule (FMM) and with the treecode
+    branch, per-pair translation kernels of csrc/laplace.cu, 2 048 panels, against the golden fixtures of the reference."""
+    import json
+    from conftest import GOLDEN
+    g = dict(np.load(os.path.join(GOLDEN, name + ".npz")))
+    m = json.loads(str(g["meta"]))
+    n = len(g["verts"])
+    bc = np.full(n, m["bc"], np.int32)
+    t = O.BemOracle(g["verts"], bc, ncrit=m["ncrit"], theta=m["theta"]).tree()
+    assert len(t["lr"]) > 1000
+    path = tmp_path / "whole_bem.bin"
+    _write_pipeline_file(path, g["verts"], bc, t, g["charges"], m["K"], 0, 0, 0.0, m["P"], bool(m.get("treecode", 0)), far=True,
+                         laplace=True)
+    out = subprocess.check_output([os.path.join(os.path.dirname(emu), "emu_bem_pipeline"), str(path)], timeout=3000).decode()
+    mm = re.search(r"guard_failures (\d+)", out)
+    assert mm and int(mm.group(1)) == 0, out
+    got = np.fromfile(str(path) + ".out")
+    assert O.rel_l2(got, g["results"]) <= 1e-10
