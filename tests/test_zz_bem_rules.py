@@ -6,8 +6,7 @@ tests/test_oracle.py).  The rule tables themselves are pinned on the CPU (tests/
 Also here: the treecode evaluator of YukawaCartesian[BEM] (yk_m2p_kernel, yk_bem_m2p_kernel in csrc/yukawa.cu) and of LaplaceSphericalBEM (`LaplaceBEM -eval TREE`, bem_m2p_kernel in csrc/bem.cu) against
 the golden fixtures of `ref_bem -tree` and the oracle (bit-identical to them).
 
-STATUS: like tests/test_zz_stokes_bem.py -- added after round 1's GPU minutes were spent, so collected late and marked
-xfail(strict=False) until a hardware run is recorded.
+STATUS: green on hardware since the round-1 driver run (GPUTEST_r01.json); no xfail mask.
 """
 import json
 import os
@@ -19,9 +18,7 @@ import oracle_lib as O
 import fmm_bem_relaxed_b200 as F
 from conftest import GOLDEN
 
-pytestmark = [pytest.mark.gpu, pytest.mark.timeout(900),
-              pytest.mark.xfail(strict=False, reason="Gauss rules above 4 points not yet run on hardware (round 1 GPU "
-                                                     "budget spent before they were added)")]
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(900)]
 
 
 @pytest.mark.parametrize("name", ["laplace_bem_2048_p6_k13_bc0", "laplace_bem_2048_p6_k13_bc1", "laplace_bem_2048_p8_k25_bc0"])

@@ -7,8 +7,7 @@ theta = 0.5, ncrit = 64 -- through size-independent properties (the oracle canno
   * checksums and the first result against the unmodified reference run on ONE thread (11 minutes in the build
     container, tests/golden/checksums.json key c5_n10000000_p8; the 8-thread figures of SURVEY 8c are racy);
   * linearity and determinism.
-STATUS: first run at this size -- the kernels are the hardware-verified ones, the size is new -- so collected late and
-marked xfail(strict=False) until a run is recorded (python bench.py --n 10000000 times the same configuration).
+STATUS: green on hardware since the round-1 driver run (GPUTEST_r01.json); no xfail mask.
 """
 import numpy as np
 import pytest
@@ -16,8 +15,7 @@ import pytest
 import oracle_lib as O
 import fmm_bem_relaxed_b200 as F
 
-pytestmark = [pytest.mark.gpu, pytest.mark.timeout(900),
-              pytest.mark.xfail(strict=False, reason="N = 10M not yet run on hardware (round 1 GPU budget spent)")]
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(900)]
 
 
 def test_c5_counts_accuracy_and_checksums():

@@ -6,10 +6,8 @@ restatement, which is bit-identical to the reference on every one of them (tests
 reference with the dangling `auto dist` of kernel/StokesSphericalBEM.hpp:162,262 materialised (near_field_as_written).
 Tolerance: relative L2 <= 1e-10 (BASELINE.json north_star) per velocity component.
 
-STATUS: this kernel class was written after round 1's GPU minutes were spent; the CUDA side compiles for sm_100a and
-shares its panel integrals with the CPU-pinned host class, but its first run on a B200 is the round-end run.  The
-module is therefore the last one collected and marked xfail(strict=False): a pass shows as XPASS, a failure cannot
-mask the suites that were green on hardware.  Remove the mark once a run is recorded.
+STATUS: green on hardware since the round-1 driver run (GPUTEST_r01.json); the xfail mask of round 1 is gone, a
+failure here fails the suite.
 """
 import json
 import os
@@ -23,9 +21,7 @@ import oracle_lib as O
 import fmm_bem_relaxed_b200 as F
 from conftest import GOLDEN, ROOT
 
-pytestmark = [pytest.mark.gpu, pytest.mark.timeout(900),
-              pytest.mark.xfail(strict=False, reason="StokesSphericalBEM kernels not yet run on hardware (round 1 GPU "
-                                                     "budget spent before they were written)")]
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(900)]
 
 TOL = 1e-10
 FIXTURES = ["stokes_bem_asis_2048_p6_bc0", "stokes_bem_asis_2048_p6_bc1", "stokes_bem_asis_2048_p6_bc2",
