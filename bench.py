@@ -39,9 +39,12 @@ UNIT = "matvec/s"
 
 
 def workload(args):
+    """The `config` object: identical in both arms (the driver compares them)."""
     return {"workload": "LaplaceSpherical FMM matvec, N=%d uniform cube (drand48), P=%d, theta=%g, ncrit=%d"
                         % (args.n, args.p, args.theta, args.ncrit),
-            "N": args.n, "P": args.p, "theta": args.theta, "ncrit": args.ncrit}
+            "N": args.n, "P": args.p, "theta": args.theta, "ncrit": args.ncrit,
+            "l2": "GPU arm: 256 MiB memset between steps, outside the per-step event pairs; the working set of a "
+                  "step (0.3 GB) exceeds the 126 MB L2 as well"}
 
 
 def ref_binary():
@@ -277,10 +280,87 @@ def bench_reference(args, rank, world):
     print(json.dumps(line))
 
 
+def bench_c5(args, rank, world, local_rank, dist, barrier):
+    """BASELINE config 5 (reference tests/scaling.cpp:14-74 at N = 10M, P = 8, theta = 0.5, ncrit = 64) sharded over
+    the ranks of this run: device-resident sharded matvec, per-step CUDA events, max over ranks.  Rank 0 returns the
+    key; a failure is reported in it, not raised."""
+    import numpy as np
+    import torch
+    import fmm_bem_relaxed_b200 as F
+    try:
+        n, P = 10_000_000, 8
+        pts, q = F.drand48_inputs(n)
+        opts = F.FMMOptions()
+        opts.set_mac_theta(0.5)
+        opts.set_max_per_box(64)
+        opts.device = local_rank
+        opts.rank, opts.nranks = rank, world
+        opts.m2l_mode = args.m2l_mode
+        t0 = time.perf_counter()
+        plan = F.FMM_plan(F.LaplaceSpherical(P), pts, opts)
+        plan_s = time.perf_counter() - t0
+        if world > 1:
+            idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
+            if rank == 0:
+                idt.copy_(torch.frombuffer(bytearray(F.comm_unique_id()), dtype=torch.uint8))
+            dist.broadcast(idt, 0)
+            plan.comm_init(bytes(idt.cpu().numpy().tobytes()))
+            if not args.no_peer:
+                mine = torch.frombuffer(bytearray(plan.peer_export()), dtype=torch.uint8).cuda()
+                blobs = [torch.zeros(128, dtype=torch.uint8, device="cuda") for _ in range(world)]
+                dist.all_gather(blobs, mine)
+                plan.peer_init(b"".join(bytes(t.cpu().numpy().tobytes()) for t in blobs))
+        info = plan.info()
+        perm = plan.tree()["perm"].astype(np.int64)
+        b0, b1 = info.own_body_begin, info.own_body_end
+        d_q = torch.from_numpy(np.ascontiguousarray(q[perm[b0:b1]])).cuda()
+        d_r = torch.empty((b1 - b0, 4), dtype=torch.float64, device="cuda")
+        stream = torch.cuda.ExternalStream(plan.stream(), device=torch.device("cuda", local_rank))
+        steps = 5
+        for _ in range(3):
+            plan.execute_sharded(d_q.data_ptr(), d_r.data_ptr())
+        barrier()
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        for a, b in ev:
+            with torch.cuda.stream(stream):
+                a.record(stream)
+                plan.execute_sharded(d_q.data_ptr(), d_r.data_ptr())
+                b.record(stream)
+        barrier()
+        ms = sum(a.elapsed_time(b) for a, b in ev) / steps
+        # known answer of the unmodified reference on one thread (tests/golden/checksums.json c5_n10000000_p8):
+        # the potential checksum over ALL bodies is the sum of the per-rank slice sums
+        pot = torch.tensor([float(d_r[:, 0].sum().item())], dtype=torch.float64, device="cuda")
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dist.all_reduce(pot, op=dist.ReduceOp.SUM)
+        plan.close()
+        del d_q, d_r
+        torch.cuda.empty_cache()
+        if rank != 0:
+            return None
+        ref_pot = None
+        try:
+            ref_pot = json.load(open(os.path.join(ROOT, "tests", "golden", "checksums.json")))["c5_n10000000_p8"]["pot"]
+        except Exception:
+            pass
+        ms = float(t.item())
+        return {"workload": "LaplaceSpherical FMM matvec, N=10000000 uniform cube (drand48), P=8, theta=0.5, ncrit=64",
+                "n_gpus": world, "ms_per_matvec": ms, "matvecs_per_s": 1e3 / ms, "steps": steps, "warmup": 3,
+                "plan_build_s": plan_s, "boxes": info.n_boxes, "m2l_pairs": info.n_m2l_pairs,
+                "p2p_body_pairs": info.n_p2p_body_pairs, "pot_checksum": float(pot.item()),
+                "pot_checksum_reference_1_thread": ref_pot,
+                "pot_checksum_rel_err": abs(float(pot.item()) - ref_pot) / abs(ref_pot) if ref_pot else None,
+                "timing": "device-resident sharded call, per-step CUDA events, max over ranks; inputs (0.5 GB per "
+                          "step) exceed L2"}
+    except Exception as e:  # noqa: BLE001 -- an extra must not take the headline measurement down
+        return {"error": "%s: %s" % (type(e).__name__, str(e)[-400:])} if rank == 0 else None
+
+
 def bench_ours(args, rank, world, local_rank):
     import numpy as np
     import torch
-    import oracle_lib as O          # inputs (drand48 restatement) and the cpu_baseline leg only
     import fmm_bem_relaxed_b200 as F
 
     if not torch.cuda.is_available():
@@ -291,12 +371,16 @@ def bench_ours(args, rank, world, local_rank):
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
-    pts, q = O.drand48_inputs(args.n)
+    pts, q = F.drand48_inputs(args.n)      # the reference drivers' input (tests/scaling.cpp:29-38), numpy restatement
     opts = F.FMMOptions()
     opts.set_mac_theta(args.theta)
     opts.set_max_per_box(args.ncrit)
     opts.device = local_rank
     opts.rank, opts.nranks = rank, world
+    opts.m2l_mode = args.m2l_mode
+    far_engine = {0: "auto (class-major DMMA GEMM + column reduction for P <= 8, fused output-stationary sweep above)",
+                  1: "per-pair kernels", 2: "class-major DMMA GEMM + column reduction",
+                  3: "fused output-stationary sweep"}[args.m2l_mode]
     t0 = time.perf_counter()
     plan = F.FMM_plan(F.LaplaceSpherical(args.p), pts, opts)
     plan_s = time.perf_counter() - t0
@@ -385,14 +469,24 @@ def bench_ours(args, rank, world, local_rank):
     ms_per_step = ms / args.steps
     value = 1e3 / ms_per_step
 
-    # end to end through the public host-buffer API (pinned host memory)
-    hq = torch.from_numpy(q).pin_memory()
-    hres = torch.empty((n, 4), dtype=torch.float64).pin_memory()
-    hq_np, hres_np = hq.numpy(), hres.numpy()
+    # end to end through the public host-buffer API (pinned host memory).  N = 1: fmmb_plan_execute, full vectors in
+    # the caller's order.  N > 1: fmmb_plan_execute_sharded_host -- every rank copies the charges of ITS bodies up and
+    # the results of ITS bodies down (results stay sharded by target), 1/N of the bytes per rank.
     lib = F.capi.load()
+    if sharded:
+        hq_own = torch.from_numpy(np.ascontiguousarray(q[perm[b0:b1]])).pin_memory()
+        hres_own = torch.empty((b1 - b0, 4), dtype=torch.float64).pin_memory()
+        hq_np, hres_np = hq_own.numpy(), hres_own.numpy()
 
-    def step_host():
-        F.capi.check(lib.fmmb_plan_execute(plan._h, F.capi.ptr(hq_np), F.capi.ptr(hres_np)))
+        def step_host():
+            F.capi.check(lib.fmmb_plan_execute_sharded_host(plan._h, F.capi.ptr(hq_np), F.capi.ptr(hres_np)))
+    else:
+        hq = torch.from_numpy(q).pin_memory()
+        hres = torch.empty((n, 4), dtype=torch.float64).pin_memory()
+        hq_np, hres_np = hq.numpy(), hres.numpy()
+
+        def step_host():
+            F.capi.check(lib.fmmb_plan_execute(plan._h, F.capi.ptr(hq_np), F.capi.ptr(hres_np)))
 
     for _ in range(max(1, min(args.warmup, 3))):
         step_host()
@@ -406,6 +500,9 @@ def bench_ours(args, rank, world, local_rank):
     if dist is not None:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_s = float(te.item())
+
+    # BASELINE config 5 beside the metric config: LaplaceSpherical, N = 10M, P = 8, sharded over the same ranks
+    c5 = bench_c5(args, rank, world, local_rank, dist, barrier) if args.c5 else None
 
     if rank != 0:
         if dist is not None:
@@ -449,7 +546,7 @@ def bench_ours(args, rank, world, local_rank):
     # (profiles/traffic_r01.json, written by scripts/summarize_profiles.py from the .ncu-rep files)
     traffic = None
     try:
-        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic_r01.json")))
+        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic_r02.json")))
         key = "p2p" if dominant.startswith("p2p") else "m2l_gemm"
         if world == 1 and args.n == 1000000 and P == 8 and key in tj:
             traffic = tj[key]["dram_bytes_read"] + tj[key]["dram_bytes_write"]
@@ -503,20 +600,22 @@ def bench_ours(args, rank, world, local_rank):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": dict(workload(args), l2="256 MiB memset between steps, outside the per-step event pairs",
-                       parallelism="1 GPU" if world == 1 else
-                       ("target leaves in %d Morton-contiguous ranges of equal estimated work; per step: NCCL "
-                        "all-gather of the charge slices, owned upward pass, multipoles %s; "
-                        "results stay sharded by target (fmmb_plan_execute_sharded)"
-                        % (world, "all-gathered over NCCL" if args.no_peer else
-                           "pushed into the peers' arrays over NVLink (P2P stores + flag vectors)")) if sharded else
-                       ("target leaves in %d Morton-contiguous ranges of equal estimated work; charges replicated, "
-                        "owned upward pass + NCCL all-gather of multipoles, NCCL all-gather of the result slices"
-                        % world),
-                       plan_build_s=plan_s, boxes=info.n_boxes, m2l_pairs=info.n_m2l_pairs,
-                       p2p_body_pairs=info.n_p2p_body_pairs),
+        "config": workload(args),
+        "details": dict(parallelism="1 GPU" if world == 1 else
+                        ("target leaves in %d Morton-contiguous ranges of equal estimated work; per step: owned upward "
+                         "pass, multipoles and charge slices %s; results stay sharded by target "
+                         "(fmmb_plan_execute_sharded; e2e: fmmb_plan_execute_sharded_host)"
+                         % (world, "all-gathered over NCCL" if args.no_peer else
+                            "stored into the peers' arrays over NVLink (P2P stores + flag vectors, no NCCL in the step)"))
+                        if sharded else
+                        ("target leaves in %d Morton-contiguous ranges of equal estimated work; charges replicated, "
+                         "owned upward pass + multipole exchange, NCCL all-gather of the result slices" % world),
+                        plan_build_s=plan_s, boxes=info.n_boxes, m2l_pairs=info.n_m2l_pairs,
+                        p2p_body_pairs=info.n_p2p_body_pairs, far_field_engine=far_engine),
+        # bytes per step summed over the ranks (every rank moves the slice of its own bodies)
         "e2e": {"value": 1.0 / e2e_s, "unit": UNIT, "h2d_bytes_per_step": 8 * n, "d2h_bytes_per_step": 32 * n,
-                "ms_per_step": e2e_s * 1e3},
+                "ms_per_step": e2e_s * 1e3,
+                "call": "fmmb_plan_execute_sharded_host" if sharded else "fmmb_plan_execute"},
         "gpu_launches": launches,
         "roofline": roofline, "phases": others, "clocks": clocks,
     }
@@ -528,6 +627,8 @@ def bench_ours(args, rank, world, local_rank):
         line["stresslet_c4"] = stokes
     if sbem is not None:
         line["stokes_bem"] = sbem
+    if c5 is not None:
+        line["c5_scaling"] = c5
     print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()
@@ -544,6 +645,9 @@ def main():
     ap.add_argument("--theta", type=float, default=0.5)
     ap.add_argument("--ncrit", type=int, default=64)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-c5", dest="c5", action="store_false",
+                    help="skip the N = 10M (BASELINE config 5) extra")
+    ap.add_argument("--m2l-mode", type=int, default=0, help="far-field engine (fmmb_options.m2l_mode)")
     ap.add_argument("--no-peer", action="store_true",
                     help="N > 1: exchange the multipoles with an NCCL all-gather instead of peer-memory stores")
     ap.add_argument("--replicated-results", action="store_true",

@@ -24,7 +24,7 @@ from . import capi
 from .capi import FmmbError
 
 __all__ = ["FMMOptions", "LaplaceSpherical", "LaplaceSphericalBEM", "StokesSpherical", "YukawaCartesian", "YukawaCartesianBEM", "StokesSphericalBEM", "SolverOptions", "GMRES", "Panels", "FMM_plan", "Direct", "FmmbError", "capi", "comm_unique_id",
-           "partition_ranges", "get_options"]
+           "partition_ranges", "get_options", "drand48_inputs"]
 
 
 class FMMOptions:
@@ -50,6 +50,36 @@ class FMMOptions:
 
     def max_per_box(self):
         return self.NCRIT_
+
+
+def drand48_inputs(n):
+    """The reference drivers' synthetic input (tests/scaling.cpp:29-38, serialrun.cpp): n points in the unit cube, then n
+    charges, from glibc drand48() in its default state -- X' = (0x5DEECE66D X + 0xB) mod 2^48 from X0 = 0, value
+    X'/2^48; g++ evaluates the three coordinate draws of a point right to left, so the first draw lands in z.
+    Vectorised: the first block of the sequence is stepped, every later block is the block before it pushed through
+    the block-sized jump X -> A X + C (mod 2^48; 64-bit wrap-around products keep the low 48 bits exact)."""
+    a, c, mask = 0x5DEECE66D, 0xB, (1 << 48) - 1
+    total = 4 * int(n)
+    B = min(total, 1 << 16)
+    first = np.empty(B, dtype=np.uint64)
+    x = 0
+    for i in range(B):
+        x = (a * x + c) & mask
+        first[i] = x
+    A, C = 1, 0                                # B-fold composition of X -> a X + c
+    for _ in range(B):
+        A, C = (a * A) & mask, (a * C + c) & mask
+    out = np.empty(total, dtype=np.uint64)
+    out[:B] = first
+    m = np.uint64(mask)
+    pos = B
+    while pos < total:
+        k = min(B, total - pos)
+        out[pos:pos + k] = (out[pos - B:pos - B + k] * np.uint64(A) + np.uint64(C)) & m
+        pos += k
+    v = out.astype(np.float64) / 281474976710656.0
+    pts = np.ascontiguousarray(v[:3 * n].reshape(n, 3)[:, ::-1])
+    return pts, np.ascontiguousarray(v[3 * n:])
 
 
 def get_options(argv):
@@ -228,7 +258,7 @@ class FMM_plan:
         src = capi.Sources(self._n, capi.ptr(pts), capi.ptr(verts), capi.ptr(bc))
         near_only = 2 if opts.block_diagonal else (1 if opts.local_evaluation else 0)
         flags = capi.FLAG_STOKES_BEM_AS_WRITTEN if getattr(kernel, "near_field_as_written", False) else 0
-        op = capi.Options(opts.theta, opts.NCRIT_, opts.evaluator, opts.device, 0,
+        op = capi.Options(opts.theta, opts.NCRIT_, opts.evaluator, opts.device, int(getattr(opts, "m2l_mode", 0)),
                           getattr(opts, "rank", 0), getattr(opts, "nranks", 1), near_only, flags)
         h = ctypes.c_void_p()
         capi.check(lib.fmmb_plan_create(ctypes.byref(kd), ctypes.byref(src), ctypes.byref(op), ctypes.byref(h)))
@@ -269,6 +299,19 @@ class FMM_plan:
         """Sharded matvec: this rank's charge / result slices (device pointers, tree order, owned range)."""
         capi.check(self._lib.fmmb_plan_execute_sharded(self._h, ctypes.c_void_p(charges_own_ptr),
                                                        ctypes.c_void_p(results_own_ptr)))
+
+    def execute_sharded_host(self, charges_own, results_own=None):
+        """Sharded matvec with HOST buffers: charges of this rank's bodies (tree order, owned range) in, results of
+        this rank's bodies out.  Pass pinned numpy views to keep the copies asynchronous to the host."""
+        i = self.info()
+        own = i.own_body_end - i.own_body_begin
+        q = np.ascontiguousarray(np.asarray(charges_own, dtype=np.float64).reshape(-1))
+        if q.shape[0] != own * self._cdim:
+            raise ValueError("charges_own.size() != owned bodies * charge_dim")
+        if results_own is None:
+            results_own = np.empty((own, self._rdim) if self._rdim > 1 else (own,), dtype=np.float64)
+        capi.check(self._lib.fmmb_plan_execute_sharded_host(self._h, capi.ptr(q), capi.ptr(results_own)))
+        return results_own
 
     def comm_init(self, unique_id):
         """Join the NCCL communicator of a partitioned plan (unique_id: 128 bytes from comm_unique_id)."""

@@ -71,7 +71,7 @@ class PlanInfo(ctypes.Structure):
 # every symbol include/fmmb.h declares
 EXPORTS = [
     "fmmb_plan_create", "fmmb_plan_set_p", "fmmb_plan_execute", "fmmb_plan_execute_device",
-    "fmmb_plan_execute_sharded", "fmmb_gmres", "fmmb_plan_peer_export", "fmmb_plan_peer_init",
+    "fmmb_plan_execute_sharded", "fmmb_plan_execute_sharded_host", "fmmb_gmres", "fmmb_plan_peer_export", "fmmb_plan_peer_init",
     "fmmb_plan_direct", "fmmb_plan_direct_panels", "fmmb_plan_set_option", "fmmb_plan_sync", "fmmb_comm_unique_id", "fmmb_plan_comm_init",
     "fmmb_partition_ranges", "fmmb_plan_stream", "fmmb_plan_get_info", "fmmb_plan_get_tree",
     "fmmb_plan_get_expansions", "fmmb_plan_phase_times", "fmmb_plan_destroy", "fmmb_last_error",
@@ -97,6 +97,7 @@ def load():
     lib.fmmb_plan_execute.argtypes = [vp, dp, dp]
     lib.fmmb_plan_execute_device.argtypes = [vp, dp, dp]
     lib.fmmb_plan_execute_sharded.argtypes = [vp, dp, dp]
+    lib.fmmb_plan_execute_sharded_host.argtypes = [vp, dp, dp]
     lib.fmmb_gmres.argtypes = [vp, dp, dp, dp, ctypes.POINTER(SolverOptions), ctypes.POINTER(GmresInfo), dp, dp, i32]
     lib.fmmb_plan_peer_export.argtypes = [vp, dp]
     lib.fmmb_plan_peer_init.argtypes = [vp, dp]

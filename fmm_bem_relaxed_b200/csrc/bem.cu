@@ -415,7 +415,7 @@ void bem_begin(fmmb_plan* plan, const double* d_charges, cudaStream_t s) {
   BemData* B = plan->bem;
   const int64_t n = T.n;
   B->res_near.resize(n); B->res_far.resize(n);
-  bem_gather_charges<<<nblk(n, 256), 256, 0, s>>>(d_charges, T.perm.p, n, T.body.p);
+  bem_gather_charges<<<nblk(n, 256), 256, 0, s>>>(exec_charges(plan, d_charges), exec_perm(plan), n, T.body.p);
   const int ni = T.n_p2p_items;
   if (ni)
     bem_near_kernel<<<nblk(ni, kBemWarps), 32 * kBemWarps, 0, s>>>(T.p2p_items.p, ni, T.bbegin.p, T.bend.p,
@@ -456,7 +456,7 @@ void bem_execute(fmmb_plan* plan, const double* d_charges, double* d_results) {
   B->res_near.resize(n); B->res_far.resize(n);
   plan->launches = 0;
   if (!plan->capturing) FMMB_CUDA(cudaEventRecord(ev[0], s));
-  bem_gather_charges<<<nblk(n, 256), 256, 0, s>>>(d_charges, T.perm.p, n, T.body.p);
+  bem_gather_charges<<<nblk(n, 256), 256, 0, s>>>(exec_charges(plan, d_charges), exec_perm(plan), n, T.body.p);
   FMMB_CUDA(cudaEventRecord(ev[1], s));
   if (!plan->capturing) FMMB_CUDA(cudaEventRecord(ev[6], s));
   const int ni = T.n_p2p_items;
@@ -498,6 +498,7 @@ void bem_execute(fmmb_plan* plan, const double* d_charges, double* d_results) {
       ++plan->launches;
       continue;
     }
+    if (!T.n_own_leaves) continue;         // a rank may own no leaf at all (more ranks than leaves)
     if (set == 0)
       bem_l2p_kernel<0><<<nblk(T.n_own_leaves, 4), 128, 4 * nc * sizeof(double2), s>>>(
           T.own_leaves.p, T.n_own_leaves, T.bbegin.p, T.bend.p, T.center.p, T.has_local.p, B->pan.p, B->bc.p, P,

@@ -3,6 +3,7 @@
 // thread-local message (the reference prints and exit()s instead: include/executor/P2M.hpp:13-17).
 #include "common.cuh"
 #include <cstring>
+#include <algorithm>
 #include <new>
 
 namespace fmmb {
@@ -121,6 +122,7 @@ int fmmb_plan_create(const fmmb_kernel_desc* kernel, const fmmb_sources* sources
     plan->charge_dim = is_stokes ? (kernel->kind == FMMB_STOKES_SPHERICAL_STRESSLET ? 6 : 3) : (is_sbem ? 3 : 1);
     plan->result_dim = is_bem ? 1 : (is_stokes || is_sbem ? 3 : 4);
     laplace_init_tables(plan);
+    blocked_init_tables();
     std::vector<double> centres;
     const double* pts = sources->points;
     if (!pts) {
@@ -136,7 +138,12 @@ int fmmb_plan_create(const fmmb_kernel_desc* kernel, const fmmb_sources* sources
     build_tree(plan, pts, sources->n);
     plan->near_only = opts.near_only;
     if (opts.near_only == 2) restrict_p2p_to_self(plan);
-    if (!opts.near_only) build_m2l_classes(plan);
+    if (!opts.near_only) {
+      // YukawaCartesian[BEM] runs its own translation kernels on the class tables of m2l_classes.cu; the Laplace
+      // family runs the engine fmmb_options.m2l_mode selects (laplace_build_far)
+      if (is_yukawa) { build_m2l_classes(plan); plan->far_built_classes = true; }
+      else laplace_build_far(plan);
+    }
     if (is_panel) plan->p2p_item_mode = 0;   // one cached near-field block per chunk of <= 32 targets
     build_p2p_items(plan);
     if (is_bem) bem_setup(plan, sources->vertices, sources->bc, kernel->quad_k,
@@ -174,6 +181,11 @@ int fmmb_plan_set_p(fmmb_plan* plan, int p) {
   if (!plan) { set_error("null plan"); return FMMB_ERR_INVALID; }
   if (p < 1 || p > FMMB_MAX_P) { set_error("expansion order must be in 1..16"); return FMMB_ERR_INVALID; }
   if (plan->yukawa && p > 10) { set_error("YukawaCartesian is built for orders 1..10"); return FMMB_ERR_UNSUPPORTED; }
+  if (plan->peer_alloc && p > 8) {
+    // the exported multipole block holds 64 doubles per box with the flag vectors and the charge vector behind it
+    set_error("plans with a peer-memory exchange run orders 1..8 (the exported multipole block is sized for P = 8)");
+    return FMMB_ERR_UNSUPPORTED;
+  }
   plan->p = p;
   return FMMB_OK;
 }
@@ -182,8 +194,22 @@ namespace fmmb {
 // One matvec on the plan stream.  The second time a (order, charges, results) combination is seen the
 // kernel sequence -- including the second stream and the NCCL collectives -- is captured into a CUDA
 // graph; from then on a matvec is a single graph launch (no per-kernel launch gaps).
+static void drop_graphs(fmmb_plan* plan) {
+  for (auto& kv : plan->graphs) cudaGraphExecDestroy(kv.second);
+  plan->graphs.clear();
+  plan->graph_seen.clear();
+  plan->graphs_valid_at = plan->realloc_count;
+}
+
 static void run_matvec(fmmb_plan* plan, const double* q, double* r) {
+  struct CountScope {                       // DevBuf frees during this call are charged to this plan
+    unsigned long long* prev;
+    explicit CountScope(fmmb_plan* p) : prev(g_realloc_counter) { g_realloc_counter = &p->realloc_count; }
+    ~CountScope() { g_realloc_counter = prev; }
+  } scope(plan);
   auto direct = [&] {
+    // sharded call of a class that gathers its charges through a permutation: assemble the tree-ordered vector first
+    if (plan->call_sharded && plan->kind != FMMB_LAPLACE_SPHERICAL) plan->sharded_q = sharded_assemble_charges(plan, q, plan->stream);
     if (plan->bem && plan->yukawa) yukawa_bem_execute(plan, q, r);
     else if (plan->bem) bem_execute(plan, q, r);
     else if (plan->stokes) stokes_execute(plan, q, r);
@@ -192,6 +218,12 @@ static void run_matvec(fmmb_plan* plan, const double* q, double* r) {
     else laplace_execute(plan, q, r);
   };
   if (!plan->use_graph || !plan->overlap_p2p) { direct(); return; }
+  // a buffer that a cached graph points into was freed since the capture (a larger order came by): the graphs of
+  // every order are stale.  They are rebuilt on the next two calls of their key.
+  if (plan->graphs_valid_at != plan->realloc_count) {
+    FMMB_CUDA(cudaStreamSynchronize(plan->stream));
+    drop_graphs(plan);
+  }
   fmmb_plan::GraphKey key{plan->p, q, r, plan->call_sharded ? 1 : 0};
   cudaStream_t s = plan->stream;
   auto it = plan->graphs.find(key);
@@ -205,6 +237,12 @@ static void run_matvec(fmmb_plan* plan, const double* q, double* r) {
       e = cudaStreamEndCapture(s, &g);
     }
     plan->capturing = false;
+    if (plan->graphs_valid_at != plan->realloc_count) {   // the captured launches already point at freed memory
+      if (g) cudaGraphDestroy(g);
+      drop_graphs(plan);
+      direct();
+      return;
+    }
     cudaGraphExec_t ex = nullptr;
     if (e == cudaSuccess && g) e = cudaGraphInstantiate(&ex, g, 0);
     if (g) cudaGraphDestroy(g);
@@ -253,10 +291,6 @@ int fmmb_plan_execute_device(fmmb_plan* plan, const double* charges_dev, double*
 
 int fmmb_plan_execute_sharded(fmmb_plan* plan, const double* charges_own_dev, double* results_own_dev) {
   if (!plan || !charges_own_dev || !results_own_dev) { set_error("null argument"); return FMMB_ERR_INVALID; }
-  if (plan->kind != FMMB_LAPLACE_SPHERICAL) {
-    set_error("fmmb_plan_execute_sharded is built for FMMB_LAPLACE_SPHERICAL plans");
-    return FMMB_ERR_UNSUPPORTED;
-  }
   if (plan->tree.nranks > 1 && !plan->comm && !plan->peer_ready) {
     set_error("call fmmb_plan_comm_init or fmmb_plan_peer_init first");
     return FMMB_ERR_INVALID;
@@ -266,6 +300,36 @@ int fmmb_plan_execute_sharded(fmmb_plan* plan, const double* charges_own_dev, do
     plan->call_sharded = true;
     try { run_matvec(plan, charges_own_dev, results_own_dev); } catch (...) { plan->call_sharded = false; throw; }
     plan->call_sharded = false;
+  });
+}
+
+int fmmb_plan_execute_sharded_host(fmmb_plan* plan, const double* charges_own_host, double* results_own_host) {
+  if (!plan || !charges_own_host || !results_own_host) { set_error("null argument"); return FMMB_ERR_INVALID; }
+  if (plan->tree.nranks > 1 && !plan->comm && !plan->peer_ready) {
+    set_error("call fmmb_plan_comm_init or fmmb_plan_peer_init first");
+    return FMMB_ERR_INVALID;
+  }
+  return guarded([&] {
+    FMMB_CUDA(cudaSetDevice(plan->device));
+    const size_t own = (size_t)(plan->tree.own_b1 - plan->tree.own_b0), cd = plan->charge_dim, rd = plan->result_dim;
+    cudaStream_t s = plan->stream;
+    // staging sized once for the slice (a rank may own nothing: keep the pointers valid)
+    if (plan->own_q.n < std::max<size_t>(1, cd * own)) plan->own_q.resize(std::max<size_t>(1, cd * own));
+    if (plan->own_r.n < std::max<size_t>(1, rd * own)) plan->own_r.resize(std::max<size_t>(1, rd * own));
+    FMMB_CUDA(cudaEventRecord(plan->ev[8], s));
+    if (own) FMMB_CUDA(cudaMemcpyAsync(plan->own_q.p, charges_own_host, cd * own * sizeof(double), cudaMemcpyHostToDevice, s));
+    FMMB_CUDA(cudaEventRecord(plan->ev[9], s));
+    plan->call_sharded = true;
+    try { run_matvec(plan, plan->own_q.p, plan->own_r.p); } catch (...) { plan->call_sharded = false; throw; }
+    plan->call_sharded = false;
+    FMMB_CUDA(cudaEventRecord(plan->ev[10], s));
+    if (own) FMMB_CUDA(cudaMemcpyAsync(results_own_host, plan->own_r.p, rd * own * sizeof(double), cudaMemcpyDeviceToHost, s));
+    FMMB_CUDA(cudaEventRecord(plan->ev[11], s));
+    FMMB_CUDA(cudaStreamSynchronize(s));
+    update_phase_times(plan);
+    float t = 0;
+    FMMB_CUDA(cudaEventElapsedTime(&t, plan->ev[8], plan->ev[9])); plan->phase_ms[FMMB_T_H2D] = t;
+    FMMB_CUDA(cudaEventElapsedTime(&t, plan->ev[10], plan->ev[11])); plan->phase_ms[FMMB_T_D2H] = t;
   });
 }
 
@@ -348,10 +412,10 @@ int fmmb_plan_set_option(fmmb_plan* plan, const char* name, int64_t value) {
     return guarded([&] {
       FMMB_CUDA(cudaSetDevice(plan->device));
       FMMB_CUDA(cudaStreamSynchronize(plan->stream));
-      for (auto& kv : plan->graphs) cudaGraphExecDestroy(kv.second);   // graphs captured with the other path are stale
-      plan->graphs.clear();
-      plan->graph_seen.clear();
+      drop_graphs(plan);   // graphs captured with the other path are stale
+      if (value < 0 || value > 3) throw StatusError{FMMB_ERR_INVALID, "m2l_mode: 0 (auto), 1 (per pair), 2 (class-major GEMM), 3 (blocked)"};
       plan->opts.m2l_mode = (int32_t)value;
+      if (!plan->yukawa) laplace_build_far(plan);
     });
   }
   if (!std::strcmp(name, "use_graph")) { plan->use_graph = value != 0; return FMMB_OK; }
@@ -364,9 +428,7 @@ int fmmb_plan_set_option(fmmb_plan* plan, const char* name, int64_t value) {
     return guarded([&] {
       FMMB_CUDA(cudaSetDevice(plan->device));
       FMMB_CUDA(cudaStreamSynchronize(plan->stream));
-      for (auto& kv : plan->graphs) cudaGraphExecDestroy(kv.second);
-      plan->graphs.clear();
-      plan->graph_seen.clear();
+      drop_graphs(plan);
       if (kern) plan->p2p_kernel = (int)value; else plan->p2p_unroll = (int)value;
     });
   }
@@ -380,9 +442,7 @@ int fmmb_plan_set_option(fmmb_plan* plan, const char* name, int64_t value) {
     return guarded([&] {
       FMMB_CUDA(cudaSetDevice(plan->device));
       FMMB_CUDA(cudaStreamSynchronize(plan->stream));
-      for (auto& kv : plan->graphs) cudaGraphExecDestroy(kv.second);   // captured launches are stale
-      plan->graphs.clear();
-      plan->graph_seen.clear();
+      drop_graphs(plan);   // captured launches are stale
       if (items) { plan->p2p_item_mode = (int)value; build_p2p_items(plan); }
       else plan->p2p_warps = (int)value;
     });
@@ -400,6 +460,8 @@ int fmmb_plan_comm_init(fmmb_plan* plan, const unsigned char id[128]) {
   if (!plan || !id) { set_error("null argument"); return FMMB_ERR_INVALID; }
   return guarded([&] {
     FMMB_CUDA(cudaSetDevice(plan->device));
+    FMMB_CUDA(cudaStreamSynchronize(plan->stream));
+    drop_graphs(plan);   // graphs captured before the communicator existed took the single-rank path
     comm_init(plan, id);
   });
 }
@@ -409,9 +471,7 @@ int fmmb_plan_peer_export(fmmb_plan* plan, unsigned char blob[128]) {
   return guarded([&] {
     FMMB_CUDA(cudaSetDevice(plan->device));
     FMMB_CUDA(cudaStreamSynchronize(plan->stream));
-    for (auto& kv : plan->graphs) cudaGraphExecDestroy(kv.second);   // the multipole array moves: captured launches are stale
-    plan->graphs.clear();
-    plan->graph_seen.clear();
+    drop_graphs(plan);   // the multipole array moves: captured launches are stale
     peer_export(plan, blob);
   });
 }
@@ -420,9 +480,7 @@ int fmmb_plan_peer_init(fmmb_plan* plan, const unsigned char* blobs) {
   if (!plan || !blobs) { set_error("null argument"); return FMMB_ERR_INVALID; }
   return guarded([&] {
     FMMB_CUDA(cudaSetDevice(plan->device));
-    for (auto& kv : plan->graphs) cudaGraphExecDestroy(kv.second);
-    plan->graphs.clear();
-    plan->graph_seen.clear();
+    drop_graphs(plan);
     peer_init(plan, blobs);
   });
 }
@@ -450,7 +508,8 @@ int fmmb_plan_get_info(fmmb_plan* plan, fmmb_plan_info* info) {
   const Tree& T = plan->tree;
   info->n_bodies = T.n; info->n_boxes = T.nboxes; info->n_leaves = T.nleaves; info->n_levels = T.nlevels;
   info->n_m2l_pairs = T.n_lr; info->n_p2p_box_pairs = T.n_p2p; info->n_p2p_body_pairs = T.n_p2p_body_pairs;
-  info->n_m2l_classes = plan->cls.n_classes; info->n_m2l_pairs_batched = plan->cls.n_pairs;
+  if (plan->far_built_classes) { info->n_m2l_classes = plan->cls.n_classes; info->n_m2l_pairs_batched = plan->cls.n_pairs; }
+  else if (plan->far_built_blocked) { info->n_m2l_classes = plan->b_m2l.n_classes; info->n_m2l_pairs_batched = plan->b_m2l.n_pairs; }
   info->own_body_begin = T.own_b0; info->own_body_end = T.own_b1;
   info->n_near_entries = plan->bem ? bem_nnz(plan->bem) : (plan->sbem ? stokes_bem_nnz(plan->sbem) : 0);
   info->p = plan->p; info->charge_dim = plan->charge_dim; info->result_dim = plan->result_dim; info->device = plan->device;

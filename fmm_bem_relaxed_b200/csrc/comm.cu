@@ -93,6 +93,22 @@ void allgather_results(fmmb_plan* plan, cudaStream_t s) {
 
 // ---- generic result epilogue (BEM: 1, Stokes: 3, Yukawa: 4 doubles per body) ----------------------------------
 namespace {
+__global__ void gen_combine_slice(const double* __restrict__ near, const double* __restrict__ far, int64_t i0, int64_t i1,
+                                  int rd, double* __restrict__ out) {
+  int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (t < (i1 - i0) * rd) out[t] = near[i0 * rd + t] + far[i0 * rd + t];
+}
+__global__ void iota_kernel(unsigned* __restrict__ a, int64_t n) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < n) a[i] = (unsigned)i;
+}
+__global__ void place_charge_slices(const double* __restrict__ stage, const long long* __restrict__ cuts, long long chunk,
+                                    int cd, double* __restrict__ qtree) {
+  const int q = blockIdx.y;
+  const long long b0 = cuts[q] * cd, len = (cuts[q + 1] - cuts[q]) * cd;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < len; i += (long long)gridDim.x * blockDim.x)
+    qtree[b0 + i] = stage[(size_t)q * chunk * cd + i];
+}
 __global__ void gen_combine_scatter(const double* __restrict__ near, const double* __restrict__ far,
                                     const unsigned* __restrict__ perm, int64_t i0, int64_t i1, int rd,
                                     double* __restrict__ out) {
@@ -130,6 +146,14 @@ void finish_results(fmmb_plan* plan, const double* near, const double* far, int 
   Tree& T = plan->tree;
   const int64_t n = T.n;
   auto nb = [](int64_t c, int t) { return (int)((c + t - 1) / t); };
+  if (plan->call_sharded) {
+    // results stay sharded by target: this rank's slice in tree order, no collective, no permutation
+    if (T.own_b1 > T.own_b0)
+      gen_combine_slice<<<nb((T.own_b1 - T.own_b0) * rd, 256), 256, 0, s>>>(near, far, T.own_b0, T.own_b1, rd, d_results);
+    ++plan->launches;
+    FMMB_CUDA(cudaGetLastError());
+    return;
+  }
   if (!(T.nranks > 1 && plan->comm)) {
     if (T.own_b1 > T.own_b0)
       gen_combine_scatter<<<nb((T.own_b1 - T.own_b0) * rd, 256), 256, 0, s>>>(near, far, T.perm.p, T.own_b0, T.own_b1,
@@ -152,6 +176,37 @@ void finish_results(fmmb_plan* plan, const double* near, const double* far, int 
   gen_scatter<<<nb(n * rd, 256), 256, 0, s>>>(plan->gen_tree.p, T.perm.p, n, rd, d_results);
   plan->launches += 3;
   FMMB_CUDA(cudaGetLastError());
+}
+
+// Sharded call of the kernel classes that gather their charges through a permutation (BEM, Stokes, Yukawa): the
+// per-rank charge slices (tree order, cd doubles per body) become one tree-ordered vector on every rank -- a padded
+// ncclAllGather -- and the class's own gather kernel then runs with the identity permutation (exec_perm below).
+const double* sharded_assemble_charges(fmmb_plan* plan, const double* d_own, cudaStream_t s) {
+  Tree& T = plan->tree;
+  const int cd = plan->charge_dim;
+  auto nb = [](int64_t c, int t) { return (int)((c + t - 1) / t); };
+  if (T.iota.n != (size_t)T.n) {
+    if (plan->capturing) throw StatusError{FMMB_ERR_INVALID, "first sharded call inside a graph capture"};
+    T.iota.resize(T.n);
+    iota_kernel<<<nb(T.n, 256), 256, 0, s>>>(T.iota.p, T.n);
+  }
+  if (T.nranks == 1) return d_own;                          // the slice is the whole tree-ordered vector
+  if (!plan->comm) throw StatusError{FMMB_ERR_INVALID, "call fmmb_plan_comm_init first"};
+  ncclComm_t c = (ncclComm_t)plan->comm;
+  long long chunk = 0;
+  for (int q = 0; q < T.nranks; ++q) chunk = std::max<long long>(chunk, T.body_cuts[q + 1] - T.body_cuts[q]);
+  plan->chg_stage.resize((size_t)chunk * T.nranks * cd);
+  plan->chg_send.resize((size_t)chunk * cd);
+  plan->q_tree.resize((size_t)T.n * cd);
+  ensure_cuts(plan, s);
+  const long long own = T.own_b1 - T.own_b0;
+  if (own) FMMB_CUDA(cudaMemcpyAsync(plan->chg_send.p, d_own, own * cd * sizeof(double), cudaMemcpyDeviceToDevice, s));
+  FMMB_NCCL(ncclAllGather(plan->chg_send.p, plan->chg_stage.p, (size_t)chunk * cd, ncclDouble, c, s));
+  dim3 grid(64, T.nranks);
+  place_charge_slices<<<grid, 256, 0, s>>>(plan->chg_stage.p, plan->cuts_dev.p, chunk, cd, plan->q_tree.p);
+  FMMB_CUDA(cudaGetLastError());
+  plan->launches += 2;
+  return plan->q_tree.p;
 }
 
 namespace {
@@ -321,7 +376,7 @@ void peer_export(fmmb_plan* plan, unsigned char* blob) {
   if (plan->kind != FMMB_LAPLACE_SPHERICAL) throw StatusError{FMMB_ERR_UNSUPPORTED, "peer exchange: LaplaceSpherical plans"};
   cudaStream_t s = plan->stream;
   // one allocation for good: multipoles at the largest batched order (P = 8: 64 doubles per box) + the flag tail
-  const size_t md = (size_t)T.nboxes * 64;
+  const size_t md = (size_t)(T.nboxes + 1) * 64;
   if (!plan->peer_alloc) {
     FMMB_CUDA(cudaStreamSynchronize(s));
     plan->M.release();
@@ -347,7 +402,7 @@ void peer_init(fmmb_plan* plan, const unsigned char* blobs) {
   Tree& T = plan->tree;
   if (!plan->peer_alloc) throw StatusError{FMMB_ERR_INVALID, "call fmmb_plan_peer_export first"};
   if (plan->peer_ready) return;
-  const size_t md = (size_t)T.nboxes * 64;
+  const size_t md = (size_t)(T.nboxes + 1) * 64;
   std::vector<double*> pm(T.nranks);
   std::vector<unsigned long long*> pf(T.nranks);
   for (int q = 0; q < T.nranks; ++q) {
@@ -379,7 +434,7 @@ void exchange_multipoles_peer(fmmb_plan* plan, cudaStream_t s) {
   Tree& T = plan->tree;
   const int P = plan->p, xs = (P * P + 1) & ~1;
   const int mine = T.xchg_off[T.rank + 1] - T.xchg_off[T.rank];
-  unsigned long long* local_flags = (unsigned long long*)(plan->M.p + (size_t)T.nboxes * 64);
+  unsigned long long* local_flags = (unsigned long long*)(plan->M.p + (size_t)(T.nboxes + 1) * 64);
   unsigned long long* st = plan->peer_state.p;
   peer_push_kernel<<<std::max(mine, 1), 64, 0, s>>>(T.xchg_list.p + T.xchg_off[T.rank], mine, xs, plan->M.p, plan->peer_M.p,
                                                    plan->peer_flags.p, T.nranks, T.rank, local_flags, st,
@@ -392,7 +447,7 @@ void exchange_multipoles_peer(fmmb_plan* plan, cudaStream_t s) {
 // sharded call: d_own = the charges of this rank's bodies (tree order) -> body[].w on every rank
 void peer_exchange_charges(fmmb_plan* plan, const double* d_own, cudaStream_t s) {
   Tree& T = plan->tree;
-  const size_t md = (size_t)T.nboxes * 64;
+  const size_t md = (size_t)(T.nboxes + 1) * 64;
   unsigned long long* local_flags = (unsigned long long*)(plan->M.p + md);
   unsigned long long* st = plan->peer_state.p;
   const long long own = T.own_b1 - T.own_b0;

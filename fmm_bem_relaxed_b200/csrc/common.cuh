@@ -33,6 +33,12 @@ struct StatusError {
   std::string msg;
 };
 
+// Captured CUDA graphs hold raw device pointers.  Every DevBuf that FREES an allocation while a plan's matvec is
+// being issued bumps that plan's counter (run_matvec points this thread-local at it); a changed counter tells
+// run_matvec that graphs captured earlier may replay freed pointers, and they are dropped.
+inline thread_local unsigned long long* g_realloc_counter = nullptr;
+inline void note_realloc() { if (g_realloc_counter) ++*g_realloc_counter; }
+
 // Plain device buffer.  resize() discards contents; grow() preserves them.
 template <typename T>
 struct DevBuf {
@@ -44,12 +50,12 @@ struct DevBuf {
   DevBuf& operator=(const DevBuf&) = delete;
   ~DevBuf() { release(); }
   void release() {
-    if (p) cudaFree(p);
+    if (p) { cudaFree(p); note_realloc(); }
     p = nullptr; cap = n = 0;
   }
   void resize(size_t count) {
     if (count > cap) {
-      if (p) cudaFree(p);
+      if (p) { cudaFree(p); note_realloc(); }
       p = nullptr;
       FMMB_CUDA(cudaMalloc((void**)&p, (count ? count : 1) * sizeof(T)));
       cap = count ? count : 1;
@@ -62,7 +68,7 @@ struct DevBuf {
       T* q = nullptr;
       FMMB_CUDA(cudaMalloc((void**)&q, ncap * sizeof(T)));
       if (p && n) FMMB_CUDA(cudaMemcpyAsync(q, p, n * sizeof(T), cudaMemcpyDeviceToDevice, s));
-      if (p) { FMMB_CUDA(cudaStreamSynchronize(s)); cudaFree(p); }
+      if (p) { FMMB_CUDA(cudaStreamSynchronize(s)); cudaFree(p); note_realloc(); }
       p = q; cap = ncap;
     }
     n = count;
@@ -93,6 +99,7 @@ struct Tree {
 
   DevBuf<double> pts_orig;           // the caller's points, original order (3n)
   DevBuf<unsigned> perm;             // tree index -> original index
+  DevBuf<unsigned> iota;             // identity permutation (sharded calls: charges arrive in tree order)
   DevBuf<unsigned> code;             // Morton code, tree order
   DevBuf<double4> body;              // tree order: x, y, z, (charge slot written per matvec)
   // box table (SoA)
@@ -109,6 +116,8 @@ struct Tree {
   // owned upward pass (used once a communicator exists): a box is "inside" a rank when all its bodies
   // belong to that rank; boxes that straddle a cut are recomputed by every rank after the exchange
   DevBuf<unsigned char> up_inside;   // inside MY range
+  std::vector<int> box_owner;        // host: rank whose range holds the whole box, -1 = straddles a cut (all ranks agree)
+  bool owned_upward = false;         // some rank owns a parent box: every rank runs the owned upward pass + exchange
   // straddling (non-leaf) boxes and, for each, its maximal descendants that lie inside one rank:
   // M[straddler] = sum of direct (multi-level) M2M translations of those descendants
   DevBuf<int> strad_box, strad_off, strad_desc, strad_pair_box;
@@ -160,6 +169,40 @@ struct TransBatch {
   DevBuf<double> tmp;                // phase-1 output columns, [slot][p^2]
 };
 
+// One family of box-to-box translations evaluated output-stationary (trans_blocked.cu): targets of a level in
+// blocks of <= 128 columns, per block the list of (class, active column tiles) items.
+struct BlkBatch {
+  int kind = 0;                      // 0 = M2L, 1 = M2M, 2 = L2L
+  int n_blocks = 0, n_items = 0, sms = 148;
+  int64_t n_pairs = 0, n_tiles = 0, n_classes = 0;
+  DevBuf<int2> items;                // x = class | (tile mask << 16), y = first tile of the item
+  DevBuf<int> tile_src;              // 8 source boxes per active tile (nboxes = the all-zero expansion)
+  DevBuf<int> blk_item_off;          // n_blocks + 1
+  DevBuf<int> blk_cols;              // n_blocks x 128: target box of a column, -1 = none
+  DevBuf<int> blk_order;             // all blocks, heaviest first
+  std::vector<int> level_blk_off;    // blocks whose targets are at level l: [l], [l + 1])
+  DevBuf<double4> class_vec;         // translation vector of a class (target centre - source centre)
+  std::map<int, DevBuf<double>*> T;  // per order: fragment-major translation matrices
+  DevBuf<double> scratch;            // split launches: partial accumulators
+  DevBuf<unsigned> counters;
+  BlkBatch() {}
+  BlkBatch(const BlkBatch&) = delete;
+  BlkBatch& operator=(const BlkBatch&) = delete;
+  ~BlkBatch() { for (auto& kv : T) delete kv.second; }
+};
+
+// One launch of trans_blocked.cu: work units of up to three batches in dependent phases.
+struct Sweep {
+  bool built = false;
+  int n_units = 0, n_phases = 0, n_partials = 0;
+  BlkBatch* batch[3] = {nullptr, nullptr, nullptr};
+  int mode[3] = {0, 1, 2};           // per batch slot: 0 = M -> M, 1 = M -> L, 2 = L += L
+  DevBuf<int4> units;
+  DevBuf<int> phase_total;
+  DevBuf<unsigned> phase_cnt, split_cnt;
+  DevBuf<double> scratch;
+};
+
 struct BemData;
 struct StokesData;
 struct StokesBemData;
@@ -186,6 +229,10 @@ struct fmmb_plan {
   fmmb::LaplaceTables tab;
   fmmb::TransBatch cls, m2m, l2l;    // batched M2L / M2M / L2L
   fmmb::TransBatch m2m_own;          // multi-GPU: M2M restricted to parents inside this rank's range
+  // output-stationary translations (trans_blocked.cu): M2L; M2M of all / of the owned parents / of the parents
+  // that straddle a partition cut; L2L
+  fmmb::BlkBatch b_m2l, b_m2m, b_m2m_own, b_m2m_strad, b_l2l;
+  fmmb::Sweep sweeps[5];             // plan_sweep(): all / up / own / rest / strad
   std::map<int, fmmb::DevBuf<double>*> m2l_coeff;  // per-order real M2L coefficient tables
   fmmb::DevBuf<double> M, L;         // box-major, real layout (laplace_ops.cuh), stride xstride(p)
   fmmb::DevBuf<double> charges;      // original order staging
@@ -203,6 +250,8 @@ struct fmmb_plan {
   fmmb::DevBuf<double> gen_tree, gen_stage;  // finish_results(): tree-ordered results and the all-gather staging
   fmmb::DevBuf<long long> cuts_dev;
   fmmb::DevBuf<double> chg_stage, chg_send;  // sharded call: padded all-gather of the charge slices
+  fmmb::DevBuf<double> q_tree;               // sharded call of the gather-by-permutation classes: all charges, tree order
+  const double* sharded_q = nullptr;         // ... the vector their gather kernels read during the current call
   long long chg_chunk = 0;
   // multipole exchange through peer memory (comm.cu): the M allocation is exported once and never reallocated
   bool peer_alloc = false, peer_ready = false;
@@ -215,6 +264,7 @@ struct fmmb_plan {
   bool cuts_ready = false;
   bool xchg_off_ready = false;
   fmmb::DevBuf<double> results;      // original order staging, 4n
+  fmmb::DevBuf<double> own_q, own_r; // fmmb_plan_execute_sharded_host: device staging of this rank's slices
   double phase_ms[FMMB_T_COUNT] = {0};
   bool timed = false;
   bool m2l_gemm_timed = false;
@@ -225,6 +275,7 @@ struct fmmb_plan {
   int p2p_kernel = 2;                // 1 = merged source runs with prefetch (p2p_run_kernel), 0 = per source leaf
   int p2p_unroll = 4;
   int near_only = 0;                 // fmmb_options.near_only
+  bool far_built_classes = false, far_built_blocked = false;   // which far-field structures exist (laplace_build_far)
   int p2p_chunk = 32, p2p_min_chunk = 8;  // targets per near-field work item (chosen at plan time)
   // CUDA graphs: one captured matvec per (order, charge pointer, result pointer)
   bool use_graph = true;
@@ -240,6 +291,8 @@ struct fmmb_plan {
   };
   std::map<GraphKey, cudaGraphExec_t> graphs;
   std::map<GraphKey, int> graph_seen;
+  unsigned long long realloc_count = 0;   // device buffers freed while this plan's matvecs were issued (common.cuh)
+  unsigned long long graphs_valid_at = 0; // value of realloc_count the cached graphs were captured under
   int launches = 0;                  // kernel launches of the last execute
 };
 
@@ -254,6 +307,13 @@ void comm_destroy(fmmb_plan* plan);
 void allgather_results(fmmb_plan* plan, cudaStream_t s);
 void finish_results(fmmb_plan* plan, const double* near, const double* far, int rd, double* d_results, cudaStream_t s);
 void allgather_charges(fmmb_plan* plan, const double* d_own, cudaStream_t s);
+const double* sharded_assemble_charges(fmmb_plan* plan, const double* d_own, cudaStream_t s);
+// what a kernel class's charge-gather kernel reads: the caller's vector through the tree permutation, or -- in a
+// sharded call -- the assembled tree-ordered vector through the identity
+inline const unsigned* exec_perm(const fmmb_plan* plan) { return plan->call_sharded ? plan->tree.iota.p : plan->tree.perm.p; }
+inline const double* exec_charges(const fmmb_plan* plan, const double* d_charges) {
+  return plan->call_sharded ? plan->sharded_q : d_charges;
+}
 void exchange_multipoles(fmmb_plan* plan, cudaStream_t s);
 void peer_export(fmmb_plan* plan, unsigned char* blob);
 void peer_init(fmmb_plan* plan, const unsigned char* blobs);
@@ -266,6 +326,8 @@ void laplace_init_tables(fmmb_plan* plan);
 void laplace_execute(fmmb_plan* plan, const double* d_charges, double* d_results);
 void build_p2p_items(fmmb_plan* plan);
 void laplace_translations(fmmb_plan* plan, cudaStream_t s);
+void laplace_build_far(fmmb_plan* plan);
+bool laplace_owned_upward(const fmmb_plan* plan);
 void laplace_prepare_expansions(fmmb_plan* plan);
 // bem.cu
 void bem_setup(fmmb_plan* plan, const double* verts_host, const int32_t* bc_host, int quad_k, double kappa = -1.0);
@@ -309,6 +371,12 @@ void stokes_bem_free(StokesBemData* d);
 void stokes_bem_direct(fmmb_plan* plan, const double* d_charges, int64_t nt, const double* d_tverts, const int* d_tbc,
                        double* d_out, cudaStream_t s);
 int64_t stokes_bem_nnz(const StokesBemData* d);
+// trans_blocked.cu
+void blocked_init_tables();
+void build_blk_batch(fmmb_plan* plan, BlkBatch& B, int kind, const int* d_tgt, const int* d_src, int64_t n);
+Sweep& plan_sweep(fmmb_plan* plan, int which);
+void run_sweep(fmmb_plan* plan, Sweep& S, cudaStream_t s);
+void build_blocked_batches(fmmb_plan* plan);
 // m2l_classes.cu
 void m2l_init_tables();
 void build_m2l_classes(fmmb_plan* plan);

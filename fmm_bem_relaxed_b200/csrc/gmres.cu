@@ -139,6 +139,16 @@ void gmres_solve(fmmb_plan* plan, const double* b_host, double* x_host, const do
   dot_to(b.p, b.p, scal.p + R);
   fetch(scal.p + R, &normb2, 1);
   const double normb = std::sqrt(normb2);
+  if (!(normb > 0)) {
+    // b = 0 (or not finite): the reference divides by |b| and iterates on NaN residuals; the solution of A x = 0
+    // by GMRES from any start is x = 0, which is what a caller gets here, with zero iterations
+    if (normb == 0) {
+      std::memset(x_host, 0, (size_t)n * sizeof(double));
+      if (info) { info->iterations = 0; info->n_records = 0; info->final_residual = 0.0; info->final_p = plan->p; }
+      return;
+    }
+    throw StatusError{FMMB_ERR_INVALID, "fmmb_gmres: the right-hand side is not finite"};
+  }
 
   std::vector<std::vector<double>> H;
   std::vector<double> sv(R + 1), cs(R), sn(R), col(R + 2);

@@ -914,36 +914,97 @@ static const double* m2l_coeffs(fmmb_plan* plan, int P) {
   return buf->p;
 }
 
+// Which far-field engine runs.  fmmb_options.m2l_mode: 1 = the per-pair kernels above; 2 = the class-major GEMM +
+// column reduction of m2l_classes.cu (orders <= 8; per-pair kernels above that); 3 = the output-stationary fused sweep
+// of trans_blocked.cu (all orders); 0 (auto) = whichever is faster on a B200: measured at N = 1M, P = 8 the
+// class-major engine runs the far field in 1.72 ms (4.5 GB of DRAM traffic through its 2 GB column scratch), the
+// fused sweep in 1.87 ms (0.14 GB, no scratch, one launch), so auto takes 2 for orders <= 8 and 3 for orders 9..16,
+// where the class-major GEMM does not exist.
+static int far_engine(const fmmb_plan* plan) {
+  const int m = plan->opts.m2l_mode;
+  if (m == 1) return 1;
+  if (m == 3) return 3;
+  if (m == 2) return plan->p <= 8 ? 2 : 1;
+  return plan->p <= 8 ? 2 : 3;
+}
+
+void laplace_build_far(fmmb_plan* plan) {
+  if (plan->near_only) return;
+  const int e = far_engine(plan);
+  if (e == 2 && !plan->far_built_classes) { build_m2l_classes(plan); plan->far_built_classes = true; }
+  if (e == 3 && !plan->far_built_blocked) { build_blocked_batches(plan); plan->far_built_blocked = true; }
+}
+
+// the few boxes that straddle a partition cut, from their maximal single-rank descendants (per-pair engines)
+static void straddlers_direct(fmmb_plan* plan, cudaStream_t s) {
+  Tree& T = plan->tree;
+  const int P = plan->p, nc = P * (P + 1) / 2, pp = P * P;
+  if (!T.n_strad_pairs) return;
+  const size_t sh_mm = (size_t)(pp + nc) * sizeof(double2);
+  T.strad_tmp.resize((size_t)T.n_strad_pairs * xstride(P));
+  m2m_direct_kernel<<<T.n_strad_pairs, 64, sh_mm, s>>>(T.strad_pair_box.p, T.strad_box.p, T.strad_desc.p, T.center.p,
+                                                      P, plan->M.p, T.strad_tmp.p);
+  strad_reduce_kernel<<<T.n_strad, 64, 0, s>>>(T.strad_box.p, T.strad_off.p, P, T.strad_tmp.p, plan->M.p);
+  plan->launches += 2;
+}
+
 // M2M sweep -> M2L -> L2L sweep on plan->M / plan->L at the current order (expects the leaf multipoles
 // in plan->M; leaves the complete local expansions in plan->L).  Records ev[2] / ev[3] around M2L.
 void laplace_translations(fmmb_plan* plan, cudaStream_t s) {
   Tree& T = plan->tree;
   const int P = plan->p, nc = P * (P + 1) / 2, pp = P * P;
   const int nb = T.nboxes;
-  const double* C = m2l_coeffs(plan, P);
   cudaEvent_t* ev = plan->ev;
-  size_t sh_mm = (size_t)(pp + nc) * sizeof(double2);
-  const bool owned_up = T.nranks > 1 && (plan->comm || plan->peer_ready) && P <= 8 && plan->opts.m2l_mode != 1 &&
-                        plan->m2m_own.n_items > 0;
-  if (owned_up) {
-    // multi-GPU: M2M inside the owned subtrees, exchange, then the few boxes that straddle a cut
-    m2m_batched(plan, s, /*owned_only=*/true);
+  const size_t sh_mm = (size_t)(pp + nc) * sizeof(double2);
+  const int engine = far_engine(plan);
+  if (!plan->capturing) laplace_build_far(plan);
+  // multi-GPU: upward pass inside the owned subtrees, exchange, then the boxes that straddle a cut.  The gate is
+  // the same on every rank (Tree::owned_upward): a collective follows.
+  const bool owned_up = laplace_owned_upward(plan);
+  auto exchange = [&] {
     if (plan->hook_after_owned_m2m) plan->hook_after_owned_m2m();   // laplace_execute: start the near field now
     if (plan->peer_ready && plan->kind == FMMB_LAPLACE_SPHERICAL) exchange_multipoles_peer(plan, s);
     else exchange_multipoles(plan, s);
-    if (T.n_strad_pairs) {
-      T.strad_tmp.resize((size_t)T.n_strad_pairs * xstride(P));
-      m2m_direct_kernel<<<T.n_strad_pairs, 64, sh_mm, s>>>(T.strad_pair_box.p, T.strad_box.p, T.strad_desc.p, T.center.p,
-                                                          P, plan->M.p, T.strad_tmp.p);
-      strad_reduce_kernel<<<T.n_strad, 64, 0, s>>>(T.strad_box.p, T.strad_off.p, P, T.strad_tmp.p, plan->M.p);
-      plan->launches += 2;
+  };
+
+  // ---- engine 3: the whole far field is one launch (two around the exchange on a multi-GPU plan); the phases
+  // inside it are ordered by device-side counters (trans_blocked.cu)
+  if (engine == 3) {
+    const bool tree_only = plan->opts.evaluator == FMMB_EVAL_TREECODE;
+    // every target box is written exactly once by the block that owns it; boxes without M2L pairs stay zero
+    if (!tree_only) FMMB_CUDA(cudaMemsetAsync(plan->L.p, 0, (size_t)nb * xstride(P) * sizeof(double), s));
+    if (!plan->capturing) FMMB_CUDA(cudaEventRecord(plan->ev[13], s));
+    if (owned_up) {
+      run_sweep(plan, plan_sweep(plan, 2), s);
+      exchange();
+      run_sweep(plan, plan_sweep(plan, tree_only ? 4 : 3), s);
+    } else {
+      run_sweep(plan, plan_sweep(plan, tree_only ? 1 : 0), s);
     }
+    if (!plan->capturing) {
+      FMMB_CUDA(cudaEventRecord(plan->ev[14], s));
+      FMMB_CUDA(cudaEventRecord(ev[2], s));
+      FMMB_CUDA(cudaEventRecord(ev[3], s));
+    }
+    plan->m2l_gemm_timed = true;
+    return;
   }
-  const bool up_batched = owned_up || m2m_batched(plan, s);
-  for (int l = T.nlevels - 2; l >= 0 && !up_batched; --l) {
-    int lo = T.level_off[l], hi = T.level_off[l + 1];
-    m2m_kernel<<<hi - lo, 64, sh_mm, s>>>(lo, hi, nullptr, T.key.p, T.cbegin.p, T.cend.p, T.center.p, P, plan->M.p);
-    ++plan->launches;
+  // ---- upward sweep
+  {
+    bool up_done = false;
+    if (owned_up) {
+      m2m_batched(plan, s, /*owned_only=*/true);
+      exchange();
+      straddlers_direct(plan, s);
+      up_done = true;
+    } else if (engine == 2) {
+      up_done = m2m_batched(plan, s);
+    }
+    for (int l = T.nlevels - 2; l >= 0 && !up_done; --l) {
+      int lo = T.level_off[l], hi = T.level_off[l + 1];
+      m2m_kernel<<<hi - lo, 64, sh_mm, s>>>(lo, hi, nullptr, T.key.p, T.cbegin.p, T.cend.p, T.center.p, P, plan->M.p);
+      ++plan->launches;
+    }
   }
   if (!plan->capturing) FMMB_CUDA(cudaEventRecord(ev[2], s));
   if (plan->opts.evaluator == FMMB_EVAL_TREECODE) {        // treecode: multipoles only, M2P does the rest
@@ -951,14 +1012,15 @@ void laplace_translations(fmmb_plan* plan, cudaStream_t s) {
     return;
   }
 
-  // far field translations: batched translation classes, then the per-pair kernel for the rest
+  // ---- far field translations
   {
+    const double* C = m2l_coeffs(plan, P);
     int threads = 128;
     while (threads < nc) threads += 32;
     size_t sh = (size_t)(5 * pp) * sizeof(double2);
     size_t red = (size_t)(threads / nc) * nc * sizeof(double2);
     if (red > sh) sh = red;
-    bool batched = plan->opts.m2l_mode != 1 && m2l_batched(plan, s);
+    bool batched = engine == 2 && m2l_batched(plan, s);
     if (!batched) {
       m2l_pair_kernel<<<nb, threads, sh, s>>>(nb, nullptr, T.m2l_off.p, T.m2l_src.p, T.center.p, P, C, plan->M.p,
                                              plan->L.p, 0);
@@ -972,26 +1034,38 @@ void laplace_translations(fmmb_plan* plan, cudaStream_t s) {
   }
   if (!plan->capturing) FMMB_CUDA(cudaEventRecord(ev[3], s));
 
-  // downward sweep
-  const bool down_batched = l2l_batched(plan, s);
-  for (int l = 1; l < T.nlevels && !down_batched; ++l) {
-    int lo = T.level_off[l], hi = T.level_off[l + 1];
-    l2l_kernel<<<hi - lo, 64, sh_mm, s>>>(lo, hi, T.parent.p, T.has_local.p, T.center.p, P, plan->L.p);
-    ++plan->launches;
+  // ---- downward sweep
+  {
+    const bool down_batched = engine == 2 && l2l_batched(plan, s);
+    for (int l = 1; l < T.nlevels && !down_batched; ++l) {
+      int lo = T.level_off[l], hi = T.level_off[l + 1];
+      l2l_kernel<<<hi - lo, 64, sh_mm, s>>>(lo, hi, T.parent.p, T.has_local.p, T.center.p, P, plan->L.p);
+      ++plan->launches;
+    }
   }
+}
+
+// The owned upward pass (P2M and M2M inside the rank's subtrees, multipole exchange, straddling boxes) runs when the
+// plan is one of several ranks with an exchange path and some rank owns a parent box -- facts every rank agrees on.
+bool laplace_owned_upward(const fmmb_plan* plan) {
+  const Tree& T = plan->tree;
+  const int engine = far_engine(plan);
+  return T.nranks > 1 && (plan->comm || plan->peer_ready) && T.owned_upward && engine != 1 && (engine == 3 || plan->p <= 8);
 }
 
 // Sizes the expansion buffers for the current order (real layout, see laplace_ops.cuh).
 void laplace_prepare_expansions(fmmb_plan* plan) {
   const int P = plan->p, pp = P * P;
   const int xs = (pp + 1) & ~1;
-  plan->M.resize((size_t)plan->tree.nboxes * xs);
-  plan->L.resize((size_t)plan->tree.nboxes * xs);
+  // one more expansion than boxes: row nboxes stays all zero (the source of absent pairs in trans_blocked.cu)
+  plan->M.resize((size_t)(plan->tree.nboxes + 1) * xs);
+  plan->L.resize((size_t)(plan->tree.nboxes + 1) * xs);
   if (plan->p_alloc != P) {
     // the padding double of odd-sized expansions is read (times zero) by the GEMM: keep it finite.
     // An exported (peer) multipole array was zeroed once and is never cleared again: a faster peer may already be
     // writing the next matvec's rows into it.
     if (!plan->peer_alloc) plan->M.zero(plan->stream);
+    else FMMB_CUDA(cudaMemsetAsync(plan->M.p + (size_t)plan->tree.nboxes * xs, 0, (size_t)xs * sizeof(double), plan->stream));
     plan->L.zero(plan->stream);
     plan->p_alloc = P;
   }
@@ -1103,8 +1177,7 @@ void laplace_execute(fmmb_plan* plan, const double* d_charges, double* d_results
   // One GPU: it starts right away and fills the gaps of the latency-bound upward chain.  Sharded with an owned
   // upward pass: it starts once the owned M2M sweep is enqueued (hook below), so that the short dependent kernels
   // before the multipole exchange are not queued behind its blocks and it overlaps the exchange instead.
-  const bool p2m_owned = T.nranks > 1 && (plan->comm || plan->peer_ready) && P <= 8 && plan->opts.m2l_mode != 1 &&
-                         plan->m2m_own.n_items > 0;
+  const bool p2m_owned = laplace_owned_upward(plan);
   const bool defer_p2p = p2m_owned && s2 != s && !plan->near_only;
   if (!defer_p2p) launch_near_field(plan, s, s2);
 

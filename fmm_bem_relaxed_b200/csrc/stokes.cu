@@ -428,8 +428,8 @@ void stokes_execute(fmmb_plan* plan, const double* d_charges, double* d_results)
   cudaStream_t s = plan->stream, s2 = plan->overlap_p2p ? plan->stream2 : plan->stream;
   cudaEvent_t* ev = plan->ev;
   for (int k = 0; k < 4; ++k) {
-    d->M4[k].resize((size_t)T.nboxes * xs);
-    d->L4[k].resize((size_t)T.nboxes * xs);
+    d->M4[k].resize((size_t)(T.nboxes + 1) * xs);      // + the all-zero expansion of trans_blocked.cu
+    d->L4[k].resize((size_t)(T.nboxes + 1) * xs);
     if (d->p_alloc != P) { d->M4[k].zero(s); d->L4[k].zero(s); }   // padding double of odd-sized expansions
   }
   d->p_alloc = P;
@@ -438,7 +438,7 @@ void stokes_execute(fmmb_plan* plan, const double* d_charges, double* d_results)
   plan->launches = 0;
 
   if (!plan->capturing) FMMB_CUDA(cudaEventRecord(ev[0], s));
-  stokes_gather<<<nblk(n * d->cd, 256), 256, 0, s>>>(d_charges, T.perm.p, n, d->cd, d->rec, d->src.p);
+  stokes_gather<<<nblk(n * d->cd, 256), 256, 0, s>>>(exec_charges(plan, d_charges), exec_perm(plan), n, d->cd, d->rec, d->src.p);
   ++plan->launches;
   FMMB_CUDA(cudaEventRecord(ev[1], s));
 
@@ -465,7 +465,7 @@ void stokes_execute(fmmb_plan* plan, const double* d_charges, double* d_results)
   FMMB_CUDA(cudaFuncSetAttribute(stokes_p2m_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024));
   // multi-GPU with a communicator: the upward pass is owned (own leaves, multipoles exchanged per set by
   // laplace_translations); otherwise it is replicated
-  const bool p2m_owned = T.nranks > 1 && plan->comm && P <= 8 && plan->opts.m2l_mode != 1 && plan->m2m_own.n_items > 0;
+  const bool p2m_owned = laplace_owned_upward(plan);
   const int* p2m_list = p2m_owned ? T.own_leaves.p : T.leaves.p;
   const int p2m_n = p2m_owned ? T.n_own_leaves : T.nleaves;
   const dim3 pg(nblk(p2m_n, warps), 4);

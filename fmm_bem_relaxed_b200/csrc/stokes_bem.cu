@@ -533,8 +533,8 @@ void stokes_bem_execute(fmmb_plan* plan, const double* d_charges, double* d_resu
   cudaStream_t s = plan->stream;
   cudaEvent_t* ev = plan->ev;
   for (int k = 0; k < 4; ++k) {
-    B->M4[k].resize((size_t)T.nboxes * xs);
-    B->L4[k].resize((size_t)T.nboxes * xs);
+    B->M4[k].resize((size_t)(T.nboxes + 1) * xs);      // + the all-zero expansion of trans_blocked.cu
+    B->L4[k].resize((size_t)(T.nboxes + 1) * xs);
     if (B->p_alloc != P) { B->M4[k].zero(s); B->L4[k].zero(s); }   // padding double of odd-sized expansions
   }
   B->p_alloc = P;
@@ -543,7 +543,7 @@ void stokes_bem_execute(fmmb_plan* plan, const double* d_charges, double* d_resu
   plan->launches = 0;
 
   if (!plan->capturing) FMMB_CUDA(cudaEventRecord(ev[0], s));
-  sbem_gather<<<nblk(3 * n, 256), 256, 0, s>>>(d_charges, T.perm.p, n, B->chg.p);
+  sbem_gather<<<nblk(3 * n, 256), 256, 0, s>>>(exec_charges(plan, d_charges), exec_perm(plan), n, B->chg.p);
   ++plan->launches;
   FMMB_CUDA(cudaEventRecord(ev[1], s));
 

@@ -455,6 +455,11 @@ static void partition_tree(fmmb_plan* plan) {
     }
     T.up_inside.from_host(inside_me.data(), inside_me.size(), s);
     std::vector<unsigned> key = T.key.to_host(s);
+    // the gate of the owned upward pass must come out the same on every rank (a collective follows it): it is
+    // computed from the owners of ALL boxes, not from what this rank happens to hold
+    T.box_owner = owner;
+    T.owned_upward = false;
+    for (int b = 0; b < nb; ++b) if (owner[b] >= 0 && !(key[b] >> 31)) { T.owned_upward = true; break; }
     // straddlers and their maximal single-rank descendants (children of straddlers that are not straddlers)
     std::vector<int> sb, soff(1, 0), sdesc, spair;
     for (int b = 0; b < nb; ++b) {

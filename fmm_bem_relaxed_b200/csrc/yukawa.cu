@@ -750,7 +750,7 @@ void yukawa_execute(fmmb_plan* plan, const double* d_charges, double* d_results)
   const double* table = plan->opts.evaluator == FMMB_EVAL_TREECODE ? nullptr : yk_class_tables(plan, d, P, s);
 
   if (!plan->capturing) FMMB_CUDA(cudaEventRecord(ev[0], s));
-  yk_gather<<<nblk(n, 256), 256, 0, s>>>(d_charges, T.perm.p, n, T.body.p);
+  yk_gather<<<nblk(n, 256), 256, 0, s>>>(exec_charges(plan, d_charges), exec_perm(plan), n, T.body.p);
   ++plan->launches;
   FMMB_CUDA(cudaEventRecord(ev[1], s));
 

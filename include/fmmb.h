@@ -84,7 +84,8 @@ typedef struct {
                           kind (for FMMB_YUKAWA_CARTESIAN_BEM it is the far-field path pinned to the reference, whose
                           FMM evaluator is broken for that kernel class) */
   int32_t device;      /* CUDA device ordinal, -1 = current device */
-  int32_t m2l_mode;    /* 0 = auto, 1 = per-pair kernel only, 2 = prefer batched translation classes */
+  int32_t m2l_mode;    /* far-field engine: 0 = auto (2 for orders <= 8, 3 above), 1 = per-pair kernels, 2 = class-major
+                          DMMA GEMM + column reduction (orders <= 8), 3 = output-stationary fused sweep (all orders) */
   int32_t rank;        /* multi-GPU: this process's rank (0 when nranks <= 1) */
   int32_t nranks;      /* multi-GPU: number of ranks sharing the matvec; 0 or 1 = single GPU */
   int32_t near_only;   /* plans for preconditioners: 0 = full matvec; 1 = FMMOptions::local_evaluation, only the
@@ -170,9 +171,18 @@ int fmmb_plan_execute_device(fmmb_plan* plan, const double* charges_dev, double*
  * arrays in TREE order covering the plan's owned range [own_body_begin, own_body_end) of fmmb_plan_info
  * (tree index -> original index: perm of fmmb_plan_get_tree).  The one data exchange besides the multipoles is
  * an NCCL all-gather of the charge slices (8 bytes per body); no result collective, no permutation.
- * Works on a single-GPU plan too (the slice is then the whole tree-ordered vector).  LaplaceSpherical plans.
+ * Works on a single-GPU plan too (the slice is then the whole tree-ordered vector).  Every kernel kind:
+ * own_count * charge_dim doubles in, own_count * result_dim doubles out (LaplaceSpherical can exchange the slices
+ * through peer memory, fmmb_plan_peer_init; the other kinds need fmmb_plan_comm_init).
  * Asynchronous on the plan's stream. */
 int fmmb_plan_execute_sharded(fmmb_plan* plan, const double* charges_own_dev, double* results_own_dev);
+
+/* The same call with HOST buffers (what a host-side distributed solver holds: the reference's GMRES keeps
+ * std::vector's, examples/BEM/GMRES.hpp:142-252): copies this rank's charge slice to the device, runs the sharded
+ * matvec, copies this rank's result slice back and blocks until it is written.  Per rank and matvec that is
+ * own_count * charge_dim * 8 bytes up and own_count * result_dim * 8 bytes down -- 1/nranks of what
+ * fmmb_plan_execute moves.  Pinned host memory makes the copies asynchronous to the host. */
+int fmmb_plan_execute_sharded_host(fmmb_plan* plan, const double* charges_own_host, double* results_own_host);
 
 /* Brute force reference sum on the GPU for accuracy checks:
  * Direct::matvec(K, sources, charges, targets, results), reference include/Direct.hpp:273-288.

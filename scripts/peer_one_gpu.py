@@ -1,6 +1,8 @@
-"""Two ranks (two processes) on ONE GPU: the sharded matvec with peer-memory exchange only (no NCCL; the processes
+"""Two ranks (two processes), one GPU each: the sharded matvec with peer-memory exchange only (no NCCL; the processes
 swap the 128-byte IPC blobs over gloo).  Exercises fmmb_plan_peer_export / peer_init / execute_sharded and the flag
-protocol on a single-GPU box.  usage: python scripts/peer_one_gpu.py [N] [P]   (spawns the two ranks itself)"""
+protocol.  Needs two GPUs: kernels of two processes that wait on one another through flags must not share a device
+(nothing guarantees that they run at the same time; B200_PROFILING.md records Xid 109 for exactly that), so with one
+visible device the script refuses to run.  usage: python scripts/peer_one_gpu.py [N] [P]   (spawns the ranks itself)"""
 import os
 import sys
 
@@ -18,15 +20,16 @@ def worker(rank, world, port, n, P, ret):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
-    torch.cuda.set_device(0)
+    dev = rank
+    torch.cuda.set_device(dev)
     pts, q = O.drand48_inputs(n)
     single = F.FMMOptions()
-    single.device = 0
+    single.device = dev
     ref_plan = F.FMM_plan(F.LaplaceSpherical(P), pts, single)
     ref = ref_plan.execute(q)
     perm = ref_plan.tree()["perm"].astype(np.int64)
     opts = F.FMMOptions()
-    opts.device = 0
+    opts.device = dev
     opts.rank, opts.nranks = rank, world
     plan = F.FMM_plan(F.LaplaceSpherical(P), pts, opts)
     blobs = [None] * world
@@ -57,7 +60,11 @@ def worker(rank, world, port, n, P, ret):
 
 
 if __name__ == "__main__":
+    import torch
     import torch.multiprocessing as mp
+    if torch.cuda.device_count() < 2:
+        print("PEER_ONE_GPU needs two devices (spin-waiting kernels of two processes must not share a GPU)")
+        sys.exit(3)
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 40000
     P = int(sys.argv[2]) if len(sys.argv) > 2 else 6
     mgr = mp.Manager()

@@ -267,3 +267,58 @@ def test_near_field_only_plans_for_preconditioners():
     assert np.isfinite(diag.execute(qq)).all()
     with pytest.raises(F.FmmbError):
         F.FMM_plan(F.StokesSpherical(4), pts, opts)
+
+
+def _plan_mode(points, P, mode, ncrit=64, theta=0.5):
+    opts = F.FMMOptions()
+    opts.set_mac_theta(theta)
+    opts.set_max_per_box(ncrit)
+    opts.m2l_mode = mode
+    return F.FMM_plan(F.LaplaceSpherical(P), points, opts)
+
+
+@pytest.mark.parametrize("which", ["golden_drand48", "golden_two_scale"])
+@pytest.mark.parametrize("mode", [1, 2, 3])
+def test_every_far_field_engine_reproduces_the_reference_expansions(which, mode, request):
+    """m2l_mode 1 (per-pair kernels), 2 (class-major DMMA GEMM + column reduction) and 3 (output-stationary fused
+    sweep, csrc/trans_blocked.cu) against the multipole / local expansions and results the reference itself dumped
+    (uniform and strongly adaptive fixture)."""
+    g = request.getfixturevalue(which)
+    m = json.loads(str(g["meta"]))
+    plan = _plan_mode(g["points"], m["P"], mode, m["ncrit"], m["theta"])
+    res = plan.execute(g["charges"])
+    assert_parity(res, g["results"])
+    M, L = plan.expansions()
+    used = np.abs(g["M"]).sum(axis=(1, 2)) > 0
+    assert O.rel_l2(M[used], g["M"][used]) <= TOL
+    assert O.rel_l2(L, g["L"]) <= TOL
+    assert np.array_equal(plan.execute(g["charges"]), res)       # fixed summation order in every engine
+
+
+@pytest.mark.parametrize("P", [1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 12, 13, 16])
+def test_fused_sweep_engine_all_orders_vs_oracle(P):
+    """The blocked engine at every order 1..16 (orders 9..16: k-chunks of 64, row blocks of 64) on an adaptive
+    cloud, against the oracle; auto mode (class-major GEMM up to 8, fused sweep above) must agree too."""
+    rng = np.random.default_rng(P)
+    n = 6000
+    pts = rng.random((n, 3))
+    pts[n // 2:] = 0.6 + 0.1 * rng.random((n - n // 2, 3))        # dense sub-cube: leaves on several levels
+    q = rng.random(n) - 0.4
+    ref = O.Oracle(pts, 32, 0.5).execute(q, P, mode=0)
+    res = _plan_mode(pts, P, 3, 32).execute(q)
+    assert_parity(res, ref)
+    assert_parity(_plan_mode(pts, P, 0, 32).execute(q), ref)
+
+
+def test_order_changes_do_not_replay_stale_graphs():
+    """graphs are cached per (order, pointers); growing the order reallocates the expansion buffers
+    the cached graphs point into.  p = 5, 5, 5 (graph captured and replayed), 12 (buffers grow, other engine), 5
+    (must NOT replay the stale graph), 12, 12, 12 (captured at the new order), 5 -- every result against the oracle."""
+    n = 20000
+    pts, q = O.drand48_inputs(n)
+    orc = O.Oracle(pts, 64, 0.5)
+    ref = {p: orc.execute(q, p, mode=0) for p in (5, 12)}
+    plan = make_plan(pts, 5)
+    for p in (5, 5, 5, 12, 5, 5, 12, 12, 12, 5, 5):
+        plan.kernel().set_p(p)
+        assert_parity(plan.execute(q), ref[p])

@@ -143,6 +143,39 @@ def _tile_check(make_kernel, sources, charges, world, tol=1e-13):
 
 
 @pytest.mark.gpu
+def test_sharded_host_call_and_sharded_calls_of_every_kernel_kind():
+    """fmmb_plan_execute_sharded[_host] on single-GPU plans of every kernel kind: the slice is the whole vector in
+    tree order, so the result must be the ordinary matvec, permuted (bit for bit: same kernels, same sums)."""
+    import torch
+    n = 20000
+    pts, q = O.drand48_inputs(n)
+    rng = np.random.default_rng(5)
+    verts = O.unit_sphere(5)
+    g = np.hstack([rng.random((n, 3)), np.tile([0.0, 1.0, 0.0], (n, 1))])
+    cases = [(lambda: F.LaplaceSpherical(6), pts, q),
+             (lambda: F.StokesSpherical(5, False), pts, rng.random((n, 3))),
+             (lambda: F.StokesSpherical(5, True), pts, g),
+             (lambda: F.YukawaCartesian(5, 0.5), pts, q),
+             (lambda: F.LaplaceSphericalBEM(6, 4), F.Panels(verts), rng.random(len(verts))),
+             (lambda: F.YukawaCartesianBEM(5, 1.0, 4), F.Panels(verts), rng.random(len(verts))),
+             (lambda: F.StokesSphericalBEM(5), F.Panels(verts), rng.random((len(verts), 3)))]
+    for mk, src, chg in cases:
+        plan = F.FMM_plan(mk(), src)
+        full = plan.execute(chg)
+        perm = plan.tree()["perm"].astype(np.int64)
+        chg2 = np.asarray(chg, dtype=np.float64).reshape(len(perm), -1)
+        own_q = np.ascontiguousarray(chg2[perm])
+        for _ in range(3):                            # third call replays the captured graph
+            out = plan.execute_sharded_host(own_q)
+            assert np.array_equal(out.reshape(len(perm), -1), full.reshape(len(perm), -1)[perm]), type(plan.K).__name__
+        d_q = torch.from_numpy(own_q).cuda()
+        d_r = torch.zeros(out.shape, dtype=torch.float64, device="cuda")
+        plan.execute_sharded(d_q.data_ptr(), d_r.data_ptr())
+        plan.sync()
+        assert np.array_equal(d_r.cpu().numpy(), out)
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("world", [2, 3])
 def test_partitioned_plans_other_kernels(world):
     n = 20000
@@ -158,11 +191,15 @@ def test_partitioned_plans_other_kernels(world):
 
 
 @pytest.mark.gpu
-def test_two_ranks_on_one_gpu_peer_memory_exchange():
-    """Two processes on ONE device: sharded matvec with the peer-memory exchange only (IPC-exported multipole /
+def test_two_ranks_peer_memory_exchange():
+    """Two processes, one device each: sharded matvec with the peer-memory exchange only (IPC-exported multipole /
     charge arrays, P2P stores, system-scope flag vectors; no NCCL).  scripts/peer_one_gpu.py spawns the ranks and
-    compares every rank's slice with the single-GPU result (including an order change and the graph replay)."""
+    compares every rank's slice with the single-GPU result (including an order change and the graph replay).
+    Skipped on a one-GPU box: kernels of two processes that spin on each other's flags must not share a device."""
     import subprocess
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs (run under gpurun --gpus 2)")
     out = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "peer_one_gpu.py"), "30000", "6"],
                          capture_output=True, text=True, timeout=240)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
