@@ -421,8 +421,8 @@ int fmmb_plan_set_option(fmmb_plan* plan, const char* name, int64_t value) {
   if (!std::strcmp(name, "use_graph")) { plan->use_graph = value != 0; return FMMB_OK; }
   if (!std::strcmp(name, "p2p_kernel") || !std::strcmp(name, "p2p_unroll")) {
     const bool kern = !std::strcmp(name, "p2p_kernel");
-    if (kern ? (value < 0 || value > 2) : (value != 4 && value != 8)) {
-      set_error("p2p_kernel: 0, 1 or 2; p2p_unroll: 4 or 8");
+    if (kern ? (value < 0 || value > 3) : (value != 4 && value != 8)) {
+      set_error("p2p_kernel: 0, 1, 2 or 3; p2p_unroll: 4 or 8");
       return FMMB_ERR_INVALID;
     }
     return guarded([&] {
@@ -430,6 +430,14 @@ int fmmb_plan_set_option(fmmb_plan* plan, const char* name, int64_t value) {
       FMMB_CUDA(cudaStreamSynchronize(plan->stream));
       drop_graphs(plan);
       if (kern) plan->p2p_kernel = (int)value; else plan->p2p_unroll = (int)value;
+    });
+  }
+  if (!std::strcmp(name, "p2p_newton")) {
+    return guarded([&] {
+      FMMB_CUDA(cudaSetDevice(plan->device));
+      FMMB_CUDA(cudaStreamSynchronize(plan->stream));
+      drop_graphs(plan);
+      plan->p2p_newton = value != 0;
     });
   }
   if (!std::strcmp(name, "p2p_warps") || !std::strcmp(name, "p2p_items")) {

@@ -274,6 +274,7 @@ struct fmmb_plan {
   int p2p_warps = 1;                 // warps per block of the near-field pair kernels
   int p2p_kernel = 2;                // 1 = merged source runs with prefetch (p2p_run_kernel), 0 = per source leaf
   int p2p_unroll = 4;
+  int p2p_newton = 0;                // 1 = Newton-only inverse root in the near-field pair kernel (p2p_kernel 3)
   int near_only = 0;                 // fmmb_options.near_only
   bool far_built_classes = false, far_built_blocked = false;   // which far-field structures exist (laplace_build_far)
   int p2p_chunk = 32, p2p_min_chunk = 8;  // targets per near-field work item (chosen at plan time)

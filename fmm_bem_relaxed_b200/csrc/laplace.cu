@@ -790,6 +790,194 @@ p2p_pair2_kernel(const int4* __restrict__ items, const int4* __restrict__ items_
   }
 }
 
+// ---- P2P, source tiles staged by TMA -----------------------------------------------------------------------------
+// The same work decomposition and pair loop as p2p_pair2_kernel; what changes is how a 32-source tile reaches
+// shared memory.  The merged source runs are contiguous stretches of the tree-ordered body array, so a tile is one
+// to three 1-D bulk copies (cp.async.bulk.shared::cluster.global, SASS UBLKCP) issued by one lane, completion
+// counted in bytes on an mbarrier: no LDG -> register -> STS round trip (the 10 M shared-store bank conflicts and
+// the 8 staging registers per lane of p2p_pair2_kernel), and the next tile is in flight while this one is consumed.
+// NEWTON: one Newton step on the MUFU.RSQ64H seed instead of the cubic step -- 16 instead of 18 FP64 instructions
+// per pair; the inverse root is then accurate to 3/8 e^2 <= 1.3e-12 relative (measured max |e| = 1.86e-6 over
+// 2.7e8 arguments, scripts/micro/probe_r2.cu), inside the 1e-10 parity tolerance but not at round-off.
+__device__ __forceinline__ void p2p_mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count));
+}
+__device__ __forceinline__ void p2p_mbar_expect_tx(uint64_t* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)),
+               "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void p2p_mbar_wait(uint64_t* bar, unsigned parity) {
+  asm volatile(
+      "{\n .reg .pred p;\n WAIT_%=:\n mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n @p bra DONE_%=;\n"
+      " bra WAIT_%=;\n DONE_%=:\n}\n" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void p2p_bulk_g2s(void* dst, const void* src, unsigned bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   (unsigned)__cvta_generic_to_shared(dst)), "l"(src), "r"(bytes),
+               "r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
+}
+
+template <bool MASKED, bool NEWTON>
+__device__ __forceinline__ void p2p_pair_n(const double tx, const double ty, const double tz, const double4 sq,
+                                           double& pot, double& fx, double& fy, double& fz) {
+  const double dx = sq.x - tx, dy = sq.y - ty, dz = sq.z - tz;
+  const double r2 = dx * dx + dy * dy + dz * dz;
+  double y0;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y0) : "d"(r2));
+  const double e = fma(-(r2 * y0), y0, 1.0);
+  double inv;
+  if (NEWTON) {
+    // y0 / 2 by an exponent decrement on the integer pipe (y0 is a normal number for every r2 in range)
+    const double h = __hiloint2double(__double2hiint(y0) - 0x00100000, __double2loint(y0));
+    inv = fma(h, e, y0);
+  } else {
+    inv = fma(y0 * e, fma(0.375, e, 0.5), y0);
+  }
+  if (MASKED) { if (__double_as_longlong(r2) < __double_as_longlong(1e-8)) inv = 0.0; }
+  const double qi = sq.w * inv;
+  const double qi3 = qi * (inv * inv);
+  pot += qi;
+  fx = fma(dx, qi3, fx); fy = fma(dy, qi3, fy); fz = fma(dz, qi3, fz);
+}
+
+template <int UNROLL, bool NEWTON>
+__global__ void __launch_bounds__(32)
+p2p_tma_kernel(const int4* __restrict__ items, const int4* __restrict__ items_ext, int nitems,
+               const int2* __restrict__ runs, const double4* __restrict__ body, double4 dummy,
+               double4* __restrict__ res) {
+  __shared__ __align__(128) double4 tile[2][32];
+  __shared__ __align__(8) uint64_t bar[2];
+  const int lane = threadIdx.x;
+  const int item = blockIdx.x;
+  if (item >= nitems) return;
+  if (lane == 0) { p2p_mbar_init(&bar[0], 1); p2p_mbar_init(&bar[1], 1); }
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  __syncwarp();
+  const int4 it = items[item];
+  const int r = it.z;                      // targets in this chunk (<= 32)
+  const int G = (r + 1) >> 1;              // lanes per replica, two targets each
+  const int S = 32 / G;                    // replicas: each takes every S-th source
+  const int g = lane % G, sp = lane / G;
+  const bool act = sp < S;
+  const bool even_split = (32 % S) == 0;
+  const int steps = 32 / S;
+  const bool hasb = g + G < r;
+  const double4 ta = body[it.y + g];
+  const double4 tb = hasb ? body[it.y + g + G] : ta;
+  double pa = 0, ax = 0, ay = 0, az = 0, pb = 0, bx = 0, by = 0, bz = 0;
+  const int4 ix = items_ext[item];         // x, y: run range; z: own bodies begin; w: (own count << 1) | close flag
+  const int self0 = ix.z, self1 = ix.z + (ix.w >> 1);
+  const bool all_masked = (ix.w & 1) != 0;
+  int j = ix.x;
+  const int j1 = ix.y;
+  // length of the virtual source stream (sum of the run lengths): lanes add up the runs
+  int total = 0;
+  for (int k = j + lane; k < j1; k += 32) { const int2 rr = runs[k]; total += rr.y - rr.x; }
+  total = __reduce_add_sync(0xffffffffu, total);
+  const int ntiles = (total + 31) >> 5;
+  int p = 0, pend = 0;
+  int2 rnext = make_int2(0, 0);
+  if (j < j1) { p = it.w; pend = runs[j].y; }    // it.w = begin of the first run
+  if (j + 1 < j1) rnext = runs[j + 1];
+  // tile t -> stage t & 1: one to three bulk copies (pieces of consecutive runs), issued by lane 0; every lane
+  // advances the cursor and learns whether the tile can hold a pair with R2 < 1e-8
+  auto issue = [&](int t) -> bool {
+    const int s = t & 1;
+    const int cnt = min(32, total - 32 * t);
+    bool masked = all_masked;
+    if (lane == 0) p2p_mbar_expect_tx(&bar[s], (unsigned)cnt * 32u);
+    int filled = 0;
+    while (filled < cnt) {
+      const int take = min(cnt - filled, pend - p);
+      if (lane == 0) p2p_bulk_g2s(&tile[s][filled], body + p, (unsigned)take * 32u, &bar[s]);
+      masked = masked || (p < self1 && p + take > self0);
+      p += take; filled += take;
+      if (p == pend) {
+        ++j;
+        p = rnext.x; pend = rnext.y;
+        if (j + 1 < j1) rnext = runs[j + 1];
+      }
+    }
+    if (lane >= cnt) tile[s][lane] = dummy;      // last tile: zero-charge sources far outside the domain
+    return masked;
+  };
+  bool mask_cur = false, mask_nxt = false;
+  if (ntiles > 0) mask_cur = issue(0);
+  for (int t = 0; t < ntiles; ++t) {
+    if (t + 1 < ntiles) mask_nxt = issue(t + 1);           // in flight while tile t is consumed
+    p2p_mbar_wait(&bar[t & 1], (unsigned)(t >> 1) & 1u);
+    __syncwarp();                                          // the dummy stores of the last tile
+    const double4* tl = tile[t & 1];
+    const bool masked = mask_cur;
+    if (act) {
+      if (S == 2) {                        // full chunks (17..32 targets): compile-time trip count
+        const double4* ts = tl + sp;
+        if (masked) {
+#pragma unroll UNROLL
+          for (int kk = 0; kk < 16; ++kk) {
+            const double4 s = ts[2 * kk];
+            p2p_pair_n<true, NEWTON>(ta.x, ta.y, ta.z, s, pa, ax, ay, az);
+            p2p_pair_n<true, NEWTON>(tb.x, tb.y, tb.z, s, pb, bx, by, bz);
+          }
+        } else {
+#pragma unroll UNROLL
+          for (int kk = 0; kk < 16; ++kk) {
+            const double4 s = ts[2 * kk];
+            p2p_pair_n<false, NEWTON>(ta.x, ta.y, ta.z, s, pa, ax, ay, az);
+            p2p_pair_n<false, NEWTON>(tb.x, tb.y, tb.z, s, pb, bx, by, bz);
+          }
+        }
+      } else if (even_split) {             // S divides 32: every replica takes exactly 32 / S sources of the tile
+        const double4* ts = tl + sp;
+        if (masked) {
+#pragma unroll UNROLL
+          for (int kk = 0; kk < steps; ++kk) {
+            const double4 s = ts[kk * S];
+            p2p_pair_n<true, NEWTON>(ta.x, ta.y, ta.z, s, pa, ax, ay, az);
+            p2p_pair_n<true, NEWTON>(tb.x, tb.y, tb.z, s, pb, bx, by, bz);
+          }
+        } else {
+#pragma unroll UNROLL
+          for (int kk = 0; kk < steps; ++kk) {
+            const double4 s = ts[kk * S];
+            p2p_pair_n<false, NEWTON>(ta.x, ta.y, ta.z, s, pa, ax, ay, az);
+            p2p_pair_n<false, NEWTON>(tb.x, tb.y, tb.z, s, pb, bx, by, bz);
+          }
+        }
+      } else if (masked) {
+#pragma unroll 2
+        for (int k = sp; k < 32; k += S) {
+          const double4 s = tl[k];
+          p2p_pair_n<true, NEWTON>(ta.x, ta.y, ta.z, s, pa, ax, ay, az);
+          p2p_pair_n<true, NEWTON>(tb.x, tb.y, tb.z, s, pb, bx, by, bz);
+        }
+      } else {
+#pragma unroll 2
+        for (int k = sp; k < 32; k += S) {
+          const double4 s = tl[k];
+          p2p_pair_n<false, NEWTON>(ta.x, ta.y, ta.z, s, pa, ax, ay, az);
+          p2p_pair_n<false, NEWTON>(tb.x, tb.y, tb.z, s, pb, bx, by, bz);
+        }
+      }
+    }
+    mask_cur = mask_nxt;
+    __syncwarp();                                          // everyone is done with the stage before it is refilled
+  }
+  // replicas sp = 1..S-1 hold partial sums of the same targets as replica 0
+  for (int q = 1; q < S; ++q) {
+    const int from = (lane + q * G) & 31;
+    const double a0 = __shfl_sync(0xffffffffu, pa, from), a1 = __shfl_sync(0xffffffffu, ax, from),
+                 a2 = __shfl_sync(0xffffffffu, ay, from), a3 = __shfl_sync(0xffffffffu, az, from),
+                 b0 = __shfl_sync(0xffffffffu, pb, from), b1 = __shfl_sync(0xffffffffu, bx, from),
+                 b2 = __shfl_sync(0xffffffffu, by, from), b3 = __shfl_sync(0xffffffffu, bz, from);
+    if (lane < G) { pa += a0; ax += a1; ay += a2; az += a3; pb += b0; bx += b1; by += b2; bz += b3; }
+  }
+  if (lane < G) {
+    res[it.y + g] = make_double4(pa, ax, ay, az);
+    if (hasb) res[it.y + g + G] = make_double4(pb, bx, by, bz);
+  }
+}
+
 // ---- results back to the caller's order ----------------------------------------------------------
 __global__ void scatter_results(const double4* __restrict__ near, const double4* __restrict__ far,
                                 const unsigned* __restrict__ perm, int64_t i0, int64_t i1,
@@ -1089,7 +1277,14 @@ static void launch_near_field(fmmb_plan* plan, cudaStream_t s, cudaStream_t s2) 
   p2p_kernel<W><<<nblk(ni, W), 32 * W, 0, s2>>>(T.p2p_items.p, ni, T.bbegin.p, T.bend.p, T.p2p_off.p, T.p2p_src.p, \
                                                 T.body.p, plan->res_near.p)
   if (ni > 0) {
-    if (plan->p2p_kernel == 2) {                    // default: two targets per lane, merged runs, prefetch
+    if (plan->p2p_kernel == 3) {                    // two targets per lane, merged runs, tiles staged by TMA
+      if (plan->p2p_newton)
+        p2p_tma_kernel<4, true><<<ni, 32, 0, s2>>>(T.p2p_items.p, T.p2p_items_ext.p, ni, T.p2p_runs.p, T.body.p, dummy,
+                                                   plan->res_near.p);
+      else
+        p2p_tma_kernel<4, false><<<ni, 32, 0, s2>>>(T.p2p_items.p, T.p2p_items_ext.p, ni, T.p2p_runs.p, T.body.p, dummy,
+                                                    plan->res_near.p);
+    } else if (plan->p2p_kernel == 2) {             // two targets per lane, merged runs, register prefetch
       if (u == 8)
         p2p_pair2_kernel<8><<<ni, 32, 0, s2>>>(T.p2p_items.p, T.p2p_items_ext.p, ni, T.p2p_runs.p, T.body.p, dummy,
                                                plan->res_near.p);

@@ -420,7 +420,7 @@ trans_sweep_kernel(const SweepArgs a) {
   // the expansions this unit reads are written by the previous phase of the same launch
   if (phase > 0) {
     if (tid == 0) {
-      const unsigned need = (unsigned)a.phase_total[phase - 1];
+      const unsigned need = (unsigned)a.phase_total[phase - 1] * C::RBLK;   // every row block of every block signals
       while (ld_acquire_gpu(a.phase_cnt + phase - 1) < need) __nanosleep(40);
       asm volatile("fence.proxy.async;" ::: "memory");
     }
