@@ -432,6 +432,15 @@ int fmmb_plan_set_option(fmmb_plan* plan, const char* name, int64_t value) {
       if (kern) plan->p2p_kernel = (int)value; else plan->p2p_unroll = (int)value;
     });
   }
+  if (!std::strcmp(name, "p2p_wps")) {
+    if (value < 0 || value > 32) { set_error("p2p_wps: 0 (plain grid) .. 32 persistent near-field warps per SM"); return FMMB_ERR_INVALID; }
+    return guarded([&] {
+      FMMB_CUDA(cudaSetDevice(plan->device));
+      FMMB_CUDA(cudaStreamSynchronize(plan->stream));
+      drop_graphs(plan);
+      plan->p2p_wps = (int)value;
+    });
+  }
   if (!std::strcmp(name, "p2p_newton")) {
     return guarded([&] {
       FMMB_CUDA(cudaSetDevice(plan->device));

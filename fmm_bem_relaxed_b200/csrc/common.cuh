@@ -274,6 +274,11 @@ struct fmmb_plan {
   int p2p_warps = 1;                 // warps per block of the near-field pair kernels
   int p2p_kernel = 2;                // 1 = merged source runs with prefetch (p2p_run_kernel), 0 = per source leaf
   int p2p_unroll = 4;
+  int p2p_wps = 0;                   // > 0: persistent near-field blocks, that many one-warp blocks per SM (0 = plain grid).
+                                     // Measured at N = 1M, P = 8: 8 per SM hides the whole far field under the near
+                                     // field (3.31 ms) but the near field itself is then latency-bound per warp, so the
+                                     // matvec is no faster than the plain grid (3.32 ms); fewer or more are slower.
+  fmmb::DevBuf<unsigned> p2p_counter;
   int p2p_newton = 0;                // 1 = Newton-only inverse root in the near-field pair kernel (p2p_kernel 3)
   int near_only = 0;                 // fmmb_options.near_only
   bool far_built_classes = false, far_built_blocked = false;   // which far-field structures exist (laplace_build_far)

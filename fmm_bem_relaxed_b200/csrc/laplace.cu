@@ -663,14 +663,25 @@ __global__ void p2p_items_ext_kernel(int4* __restrict__ items, int n, const unsi
   ext[i] = make_int4(j0, j1, (int)bb[b], (int)((be[b] - bb[b]) << 1) | (close_flag[b] ? 1 : 0));
 }
 
-template <int UNROLL>
+// PERSIST (option "p2p_wps"): the grid is a fixed number of one-warp blocks per SM that pull items from a counter.
+// The near field then occupies a fixed share of every SM for its whole duration and the far-field kernels of the
+// other stream find room beside it (a grid of 44 000 one-warp blocks refills every slot a finished block frees, so
+// the large CTAs of the DMMA GEMM never accumulate the registers they need until the near field is done).  Measured:
+// the far field does hide under the near field, but at 8 warps per SM the pair loop is latency-bound per warp and
+// the matvec is not faster than with the plain grid -- kept as an option, not the default.
+template <int UNROLL, bool PERSIST>
 __global__ void __launch_bounds__(32)
 p2p_pair2_kernel(const int4* __restrict__ items, const int4* __restrict__ items_ext, int nitems,
                  const int2* __restrict__ runs, const double4* __restrict__ body, double4 dummy,
-                 double4* __restrict__ res) {
+                 double4* __restrict__ res, unsigned* __restrict__ counter) {
   __shared__ double4 tile[32];
   const int lane = threadIdx.x;
-  const int item = blockIdx.x;
+  for (;;) {
+  int item = blockIdx.x;
+  if (PERSIST) {
+    if (lane == 0) item = (int)atomicAdd(counter, 1u);
+    item = __shfl_sync(0xffffffffu, item, 0);
+  }
   if (item >= nitems) return;
   const int4 it = items[item];
   const int r = it.z;                      // targets in this chunk (<= 32)
@@ -787,6 +798,9 @@ p2p_pair2_kernel(const int4* __restrict__ items, const int4* __restrict__ items_
   if (lane < G) {
     res[it.y + g] = make_double4(pa, ax, ay, az);
     if (hasb) res[it.y + g + G] = make_double4(pb, bx, by, bz);
+  }
+  if (!PERSIST) return;
+  __syncwarp();                                              // the tile is reused by the next item
   }
 }
 
@@ -1284,13 +1298,27 @@ static void launch_near_field(fmmb_plan* plan, cudaStream_t s, cudaStream_t s2) 
       else
         p2p_tma_kernel<4, false><<<ni, 32, 0, s2>>>(T.p2p_items.p, T.p2p_items_ext.p, ni, T.p2p_runs.p, T.body.p, dummy,
                                                     plan->res_near.p);
+    } else if (plan->p2p_kernel == 2 && plan->p2p_wps > 0 && s2 != s) {
+      // default when the near field runs beside the far field: p2p_wps persistent one-warp blocks per SM
+      int sms = 148;
+      FMMB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, plan->device));
+      const int wps = plan->p2p_wps;
+      const int grid = std::min(ni, sms * wps);
+      // no residency cap beyond the grid size: the launch finds the GPU (nearly) empty, and the block scheduler
+      // deals a grid of sms x wps small blocks evenly over the SMs.  (Capping the residency with a dynamic shared
+      // memory request was tried: it takes the shared memory the far-field kernels need.)
+      const size_t cap = 0;
+      plan->p2p_counter.resize(1);
+      FMMB_CUDA(cudaMemsetAsync(plan->p2p_counter.p, 0, sizeof(unsigned), s2));
+      p2p_pair2_kernel<4, true><<<grid, 32, cap, s2>>>(T.p2p_items.p, T.p2p_items_ext.p, ni, T.p2p_runs.p, T.body.p, dummy,
+                                                       plan->res_near.p, plan->p2p_counter.p);
     } else if (plan->p2p_kernel == 2) {             // two targets per lane, merged runs, register prefetch
       if (u == 8)
-        p2p_pair2_kernel<8><<<ni, 32, 0, s2>>>(T.p2p_items.p, T.p2p_items_ext.p, ni, T.p2p_runs.p, T.body.p, dummy,
-                                               plan->res_near.p);
+        p2p_pair2_kernel<8, false><<<ni, 32, 0, s2>>>(T.p2p_items.p, T.p2p_items_ext.p, ni, T.p2p_runs.p, T.body.p, dummy,
+                                                      plan->res_near.p, nullptr);
       else
-        p2p_pair2_kernel<4><<<ni, 32, 0, s2>>>(T.p2p_items.p, T.p2p_items_ext.p, ni, T.p2p_runs.p, T.body.p, dummy,
-                                               plan->res_near.p);
+        p2p_pair2_kernel<4, false><<<ni, 32, 0, s2>>>(T.p2p_items.p, T.p2p_items_ext.p, ni, T.p2p_runs.p, T.body.p, dummy,
+                                                      plan->res_near.p, nullptr);
     } else if (plan->p2p_kernel == 1) {             // one target per lane over merged runs
       if (w == 1 && u == 4) FMMB_P2P_RUN(1, 4);
       else if (w == 1) FMMB_P2P_RUN(1, 8);
