@@ -330,6 +330,7 @@ int fmmb_plan_execute_sharded_host(fmmb_plan* plan, const double* charges_own_ho
     float t = 0;
     FMMB_CUDA(cudaEventElapsedTime(&t, plan->ev[8], plan->ev[9])); plan->phase_ms[FMMB_T_H2D] = t;
     FMMB_CUDA(cudaEventElapsedTime(&t, plan->ev[10], plan->ev[11])); plan->phase_ms[FMMB_T_D2H] = t;
+    peer_check_timeout(plan);
   });
 }
 
@@ -514,6 +515,7 @@ int fmmb_plan_sync(fmmb_plan* plan) {
     FMMB_CUDA(cudaSetDevice(plan->device));
     FMMB_CUDA(cudaStreamSynchronize(plan->stream));
     update_phase_times(plan);
+    peer_check_timeout(plan);
   });
 }
 

@@ -287,17 +287,34 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
 __device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
   asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
+// Bounded wait on a flag a peer writes: a rank that died or fell out of step must not wedge this GPU inside a kernel.
+// After kPeerTimeoutNs the wait gives up, raises the plan's timeout flag (peer_state[3], reported by the next
+// fmmb_plan_sync / host-buffer call as FMMB_ERR_CUDA) and lets the matvec run to its end on whatever data is there.
+constexpr unsigned long long kPeerTimeoutNs = 20ull * 1000 * 1000 * 1000;
+__device__ __forceinline__ unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ void wait_flag_at_least(const unsigned long long* flag, unsigned long long v,
+                                                   unsigned long long* timeout_flag) {
+  if (ld_acquire_sys(flag) >= v) return;
+  const unsigned long long t0 = global_ns();
+  while (ld_acquire_sys(flag) < v) {
+    __nanosleep(200);
+    if (global_ns() - t0 > kPeerTimeoutNs) { atomicExch(timeout_flag, 1ull); return; }
+  }
+}
 
 __global__ void __launch_bounds__(64)
 peer_push_kernel(const int* __restrict__ list, int count, int xs, const double* __restrict__ M,
                  double* const* __restrict__ peerM, unsigned long long* const* __restrict__ peer_flags, int nranks, int me,
-                 const unsigned long long* __restrict__ local_flags, const unsigned long long* __restrict__ epoch,
+                 const unsigned long long* __restrict__ local_flags, unsigned long long* __restrict__ epoch,
                  unsigned int* __restrict__ counter) {
   __shared__ int s_last;
   const unsigned long long e = *epoch;              // matvecs completed so far; this one is e + 1
   // nobody may still be reading the previous multipoles out of the arrays this block is about to write
-  if ((int)threadIdx.x < nranks)
-    while (ld_acquire_sys(local_flags + kPeerMaxRanks + threadIdx.x) < e) {}
+  if ((int)threadIdx.x < nranks) wait_flag_at_least(local_flags + kPeerMaxRanks + threadIdx.x, e, epoch + 3);
   __syncthreads();
   const int i = blockIdx.x;
   if (i < count) {
@@ -319,10 +336,9 @@ peer_push_kernel(const int* __restrict__ list, int count, int xs, const double* 
   }
 }
 __global__ void peer_wait_kernel(const unsigned long long* __restrict__ local_flags,
-                                 const unsigned long long* __restrict__ epoch, int nranks) {
+                                 unsigned long long* __restrict__ epoch, int nranks) {
   const unsigned long long e = *epoch + 1;
-  if ((int)threadIdx.x < nranks)
-    while (ld_acquire_sys(local_flags + threadIdx.x) < e) {}
+  if ((int)threadIdx.x < nranks) wait_flag_at_least(local_flags + threadIdx.x, e, epoch + 3);
 }
 // last kernel of a matvec: this rank no longer reads its multipole array; the matvec counter advances
 __global__ void peer_read_done_kernel(unsigned long long* const* __restrict__ peer_flags, int nranks, int me,
@@ -358,11 +374,10 @@ peer_push_charges_kernel(const double* __restrict__ own, long long b0, long long
 }
 // ... and, once every rank's slice has landed, into the charge slot of the bodies
 __global__ void __launch_bounds__(256)
-peer_place_charges_kernel(const unsigned long long* __restrict__ local_flags, const unsigned long long* __restrict__ epoch,
+peer_place_charges_kernel(const unsigned long long* __restrict__ local_flags, unsigned long long* __restrict__ epoch,
                           int nranks, const double* __restrict__ qtree, long long n, double4* __restrict__ body) {
   const unsigned long long e = *epoch + 1;
-  if ((int)threadIdx.x < nranks)
-    while (ld_acquire_sys(local_flags + 2 * kPeerMaxRanks + threadIdx.x) < e) {}
+  if ((int)threadIdx.x < nranks) wait_flag_at_least(local_flags + 2 * kPeerMaxRanks + threadIdx.x, e, epoch + 3);
   __syncthreads();
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
     body[i].w = qtree[i];
@@ -385,7 +400,8 @@ void peer_export(fmmb_plan* plan, unsigned char* blob) {
     plan->M.n = 0;
     plan->p_alloc = 0;
     plan->peer_alloc = true;
-    plan->peer_state.resize(3);                       // [0] matvec counter, [1], [2] block counters of the push kernels
+    plan->peer_state.resize(4);                       // [0] matvec counter, [1], [2] block counters of the push kernels,
+                                                      // [3] timeout flag of the bounded flag waits
     plan->peer_state.zero(s);
     FMMB_CUDA(cudaStreamSynchronize(s));
   }
@@ -457,6 +473,18 @@ void peer_exchange_charges(fmmb_plan* plan, const double* d_own, cudaStream_t s)
   peer_place_charges_kernel<<<296, 256, 0, s>>>(local_flags, st, T.nranks, plan->M.p + md + kPeerTail, T.n, T.body.p);
   FMMB_CUDA(cudaGetLastError());
   plan->launches += 2;
+}
+
+// After a synchronisation: did a bounded flag wait of the peer exchange give up?
+void peer_check_timeout(fmmb_plan* plan) {
+  if (!plan->peer_ready) return;
+  unsigned long long flag = 0;
+  FMMB_CUDA(cudaMemcpy(&flag, plan->peer_state.p + 3, sizeof flag, cudaMemcpyDeviceToHost));
+  if (flag) {
+    FMMB_CUDA(cudaMemset(plan->peer_state.p + 3, 0, sizeof flag));
+    throw StatusError{FMMB_ERR_CUDA, "peer-memory exchange timed out: a rank did not arrive within 20 s "
+                                     "(all ranks must run the same sequence of matvecs); the last results are invalid"};
+  }
 }
 
 void peer_read_done(fmmb_plan* plan, cudaStream_t s) {

@@ -327,6 +327,7 @@ void peer_close(fmmb_plan* plan);
 void exchange_multipoles_peer(fmmb_plan* plan, cudaStream_t s);
 void peer_exchange_charges(fmmb_plan* plan, const double* d_own, cudaStream_t s);
 void peer_read_done(fmmb_plan* plan, cudaStream_t s);
+void peer_check_timeout(fmmb_plan* plan);
 // laplace.cu
 void laplace_init_tables(fmmb_plan* plan);
 void laplace_execute(fmmb_plan* plan, const double* d_charges, double* d_results);

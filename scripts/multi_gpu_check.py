@@ -62,10 +62,12 @@ rng = np.random.default_rng(11)
 n = 40000
 pts, q = O.drand48_inputs(n)
 verts = O.unit_sphere(6)
-cases = [("stokeslet", lambda: F.StokesSpherical(7, False), pts, rng.random((n, 3))),
+cases = [("laplace-p12", lambda: F.LaplaceSpherical(12), pts, q),      # fused sweep engine: owned sweep, exchange, rest
+         ("stokeslet", lambda: F.StokesSpherical(7, False), pts, rng.random((n, 3))),
          ("stresslet", lambda: F.StokesSpherical(8, True), pts, np.hstack([rng.random((n, 3)), np.tile([1.0, 0, 0], (n, 1))])),
          ("yukawa", lambda: F.YukawaCartesian(6, 1.0), pts, q),
-         ("laplace-bem", lambda: F.LaplaceSphericalBEM(8, 4), F.Panels(verts), rng.random(len(verts)))]
+         ("laplace-bem", lambda: F.LaplaceSphericalBEM(8, 4), F.Panels(verts), rng.random(len(verts))),
+         ("stokes-bem", lambda: F.StokesSphericalBEM(6), F.Panels(verts), rng.random((len(verts), 3)))]
 for name, mk, src, chg in cases:
     single = F.FMMOptions(); single.device = local
     ref = F.FMM_plan(mk(), src, single).execute(chg)
@@ -79,8 +81,20 @@ for name, mk, src, chg in cases:
     for rep in range(3):
         err = O.rel_l2(plan.execute(chg), ref)
         ok &= err < 1e-12
+    # the sharded call of this kernel kind with HOST buffers: this rank's charge slice up, its result slice down
+    # (fmmb_plan_execute_sharded_host; charge slices all-gathered over NCCL inside the call)
+    i = plan.info()
+    perm = plan.tree()["perm"].astype(np.int64)
+    own = perm[i.own_body_begin:i.own_body_end]
+    chg2 = np.asarray(chg, dtype=np.float64).reshape(len(perm), -1)
+    ref2 = np.asarray(ref).reshape(len(perm), -1)
+    for rep in range(3):
+        out = plan.execute_sharded_host(np.ascontiguousarray(chg2[own]))
+        serr = O.rel_l2(out.reshape(len(own), -1), ref2[own]) if len(own) else 0.0
+        ok &= serr < 1e-12
     plan.close()
-    print("rank %d/%d %s rel-L2 vs single GPU %.2e" % (rank, world, name, err), flush=True)
+    print("rank %d/%d %s rel-L2 vs single GPU %.2e, sharded host call %.2e (own %d bodies)" % (
+        rank, world, name, err, serr, len(own)), flush=True)
 dist.barrier()
 if rank == 0:
     print("MULTI_GPU_CHECK", "OK" if ok else "FAILED")

@@ -204,3 +204,39 @@ def test_two_ranks_peer_memory_exchange():
                          capture_output=True, text=True, timeout=240)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
     assert "PEER_ONE_GPU" in out.stdout
+
+
+def _torchrun(script, nproc, *args, timeout=900):
+    import subprocess
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(nproc),
+           "--master-addr", "127.0.0.1", "--master-port", str(29700 + os.getpid() % 200),
+           os.path.join(ROOT, "scripts", script)] + [str(a) for a in args]
+    return subprocess.run(cmd, capture_output=True, text=True, timeout=timeout)
+
+
+@pytest.mark.gpu
+@pytest.mark.timeout(1200)
+@pytest.mark.parametrize("world", [2, 8])
+def test_c5_n10m_sharded_over_ranks(world):
+    """BASELINE config 5 on several GPUs (judge-added row J1): N = 10M sharded over `world` ranks through the
+    peer-memory exchange and the sharded host call; slices against the single-GPU plan, global checksums against the
+    one-thread run of the unmodified reference (scripts/multi_gpu_c5.py).  Needs `world` GPUs."""
+    import torch
+    if torch.cuda.device_count() < world:
+        pytest.skip("needs %d GPUs (gpurun --gpus %d)" % (world, world))
+    out = _torchrun("multi_gpu_c5.py", world)
+    assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
+    assert "MULTI_GPU_C5 OK" in out.stdout
+
+
+@pytest.mark.gpu
+@pytest.mark.timeout(1200)
+def test_every_kernel_kind_sharded_over_two_ranks():
+    """All kernel kinds over NCCL and peer memory on 2 GPUs: replicated call, sharded host call, order changes, the
+    fused sweep engine at P = 12 (scripts/multi_gpu_check.py).  Needs 2 GPUs."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
+    out = _torchrun("multi_gpu_check.py", 2)
+    assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
+    assert "MULTI_GPU_CHECK OK" in out.stdout
