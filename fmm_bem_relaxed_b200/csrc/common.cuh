@@ -129,6 +129,9 @@ struct Tree {
   DevBuf<double> xchg_send, xchg_recv;
   int64_t n_lr_local = 0;            // M2L pairs whose target is active here (= n_lr on one GPU)
   DevBuf<unsigned char> has_local;   // box carries a local expansion (M2L target or descendant of one)
+  DevBuf<unsigned char> need_M;      // box's multipole is read by a matvec (M2L source, or below one)
+  std::vector<unsigned char> need_M_host;
+  DevBuf<unsigned char> m2m_mask_all, m2m_mask_own;   // parents the batched M2M writes: needed [and inside my range]
   // M2L: reference-order pair list and target-major CSR (sources in list order per target)
   DevBuf<int2> lr;                   // (source, target) in LR_list order
   DevBuf<int> m2l_off, m2l_src;

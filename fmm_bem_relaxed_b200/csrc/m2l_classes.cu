@@ -579,6 +579,9 @@ void build_m2l_classes(fmmb_plan* plan) {
     C.slot_src_p = T.m2l_src.p;
     classify(plan, C, C.slot_tgt.p, T.m2l_src.p, 0, nullptr, T.n_lr_local, kMinPopM2L, false);
   }
+  const std::vector<unsigned char>& need = T.need_M_host;     // parents whose multipole a matvec reads
+  std::vector<unsigned> par;
+  if (nb > 1) par = T.parent.to_host(s);
   if (nb > 1 && T.nranks > 1) {
     // M2M restricted to parents whose bodies all belong to this rank (owned upward pass)
     TransBatch& B = plan->m2m_own;
@@ -586,10 +589,10 @@ void build_m2l_classes(fmmb_plan* plan) {
     B.slot_tgt.resize(nb); B.slot_src.resize(nb);
     parent_child_pairs<<<nblk(nb, 256), 256, 0, s>>>(T.parent.p, nb, 0, B.slot_tgt.p, B.slot_src.p);
     B.slot_src_p = B.slot_src.p;
-    std::vector<unsigned char> ins = T.up_inside.to_host(s);
-    std::vector<unsigned> par = T.parent.to_host(s);
+    std::vector<unsigned char> ins = T.up_inside.to_host(s), mask(nb, 0);
     std::vector<int> list;
-    for (int c = 1; c < nb; ++c) if (ins[par[c]]) list.push_back(c);
+    for (int c = 1; c < nb; ++c) if (ins[par[c]] && need[par[c]]) { list.push_back(c); mask[par[c]] = 1; }
+    T.m2m_mask_own.from_host(mask.data(), mask.size(), s);
     DevBuf<int> dl;
     dl.from_host(list.data(), list.size(), s);
     if (!list.empty()) classify(plan, B, B.slot_tgt.p, B.slot_src.p, 0, dl.p, (int64_t)list.size(), 1, true);
@@ -602,19 +605,23 @@ void build_m2l_classes(fmmb_plan* plan) {
       B.slot_tgt.resize(nb); B.slot_src.resize(nb);
       parent_child_pairs<<<nblk(nb, 256), 256, 0, s>>>(T.parent.p, nb, kind == 2, B.slot_tgt.p, B.slot_src.p);
       B.slot_src_p = B.slot_src.p;
-      if (kind == 2 && T.nranks > 1) {
-        // L2L only into boxes that are targets on this rank
-        std::vector<unsigned char> act = T.active.to_host(s);
-        std::vector<int> list;
-        for (int c = 1; c < nb; ++c) if (act[c]) list.push_back(c);
-        DevBuf<int> dl;
-        dl.from_host(list.data(), list.size(), s);
-        if (!list.empty()) classify(plan, B, B.slot_tgt.p, B.slot_src.p, 0, dl.p, (int64_t)list.size(), 1, true);
-        B.n_pairs = (int64_t)list.size();
+      std::vector<int> list;
+      if (kind == 1) {
+        // M2M only into parents whose multipole is read (M2L sources and what lies below them)
+        std::vector<unsigned char> mask(nb, 0);
+        for (int c = 1; c < nb; ++c) if (need[par[c]]) { list.push_back(c); mask[par[c]] = 1; }
+        T.m2m_mask_all.from_host(mask.data(), mask.size(), s);
       } else {
-        classify(plan, B, B.slot_tgt.p, B.slot_src.p, 1, nullptr, nb - 1, 1, true);
-        B.n_pairs = nb - 1;
+        // L2L only into boxes that are targets on this rank, from parents that carry a local expansion
+        std::vector<unsigned char> act = T.active.to_host(s), hl = T.has_local.to_host(s);
+        for (int c = 1; c < nb; ++c) if (act[c] && hl[par[c]]) list.push_back(c);
       }
+      DevBuf<int> dl;
+      dl.from_host(list.data(), list.size(), s);
+      if (!list.empty()) classify(plan, B, B.slot_tgt.p, B.slot_src.p, 0, dl.p, (int64_t)list.size(), 1, true);
+      else { B.level_item_off.assign(T.nlevels + 1, 0); B.n_items = 0; }
+      B.n_pairs = (int64_t)list.size();
+      FMMB_CUDA(cudaStreamSynchronize(s));
     }
   }
 }
@@ -655,7 +662,7 @@ bool m2m_batched(fmmb_plan* plan, cudaStream_t s, bool owned_only) {
     launch_gemm<false>(B, P, i0, i1 - i0, plan->M.p, B.tmp.p, nullptr, s);
     int lo = T.level_off[l], hi = T.level_off[l + 1];
     m2m_reduce_kernel<<<hi - lo, 64, 0, s>>>(
-        lo, hi, T.key.p, T.cbegin.p, T.cend.p, owned_only ? T.up_inside.p : nullptr, P, B.tmp.p, plan->M.p);
+        lo, hi, T.key.p, T.cbegin.p, T.cend.p, owned_only ? T.m2m_mask_own.p : T.m2m_mask_all.p, P, B.tmp.p, plan->M.p);
     plan->launches += 2;
   }
   FMMB_CUDA(cudaGetLastError());

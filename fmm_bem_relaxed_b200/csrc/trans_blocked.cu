@@ -896,14 +896,16 @@ void build_blocked_batches(fmmb_plan* plan) {
     FMMB_CUDA(cudaStreamSynchronize(s));
   };
   std::vector<int> tg, sr;
-  // M2M: child -> parent
+  // M2M: child -> parent, only into parents whose multipole a matvec reads (M2L sources and what lies below them)
+  const std::vector<unsigned char>& need = T.need_M_host;
   tg.clear(); sr.clear();
-  for (int c = 1; c < nb; ++c) { tg.push_back((int)par[c]); sr.push_back(c); }
+  for (int c = 1; c < nb; ++c) if (need[par[c]]) { tg.push_back((int)par[c]); sr.push_back(c); }
   build(plan->b_m2m, 1, tg, sr);
   if (T.nranks > 1) {
     std::vector<int> tg2, sr2;
     tg.clear(); sr.clear();
     for (int c = 1; c < nb; ++c) {
+      if (!need[par[c]]) continue;
       const int o = T.box_owner[par[c]];
       if (o == T.rank) { tg.push_back((int)par[c]); sr.push_back(c); }           // parents inside my range
       else if (o < 0) { tg2.push_back((int)par[c]); sr2.push_back(c); }          // parents that straddle a cut

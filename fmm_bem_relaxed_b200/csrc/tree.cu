@@ -311,6 +311,10 @@ __global__ void mark_targets(const int2* __restrict__ lr, int64_t n, unsigned ch
   int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i < n) has[lr[i].y] = 1;
 }
+__global__ void mark_sources(const int2* __restrict__ lr, int64_t n, unsigned char* __restrict__ need) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < n) need[lr[i].x] = 1;
+}
 __global__ void inherit_local(const unsigned* __restrict__ parent, int lo, int hi, unsigned char* __restrict__ has) {
   int b = lo + blockIdx.x * blockDim.x + threadIdx.x;
   if (b < hi && has[parent[b]]) has[b] = 1;
@@ -463,7 +467,7 @@ static void partition_tree(fmmb_plan* plan) {
     // straddlers and their maximal single-rank descendants (children of straddlers that are not straddlers)
     std::vector<int> sb, soff(1, 0), sdesc, spair;
     for (int b = 0; b < nb; ++b) {
-      if (owner[b] >= 0 || (key[b] >> 31)) continue;
+      if (owner[b] >= 0 || (key[b] >> 31) || !T.need_M_host[b]) continue;
       // descendants of b form contiguous index ranges per level; walk down through straddling children only
       std::vector<int> stack(1, b);
       while (!stack.empty()) {
@@ -693,6 +697,17 @@ void build_tree(fmmb_plan* plan, const double* points_host, int64_t n) {
     if (b > a) inherit_local<<<nblk(b - a, 256), 256, 0, s>>>(T.parent.p, a, b, T.has_local.p);
   }
   FMMB_CUDA(cudaGetLastError());
+  // which multipoles a matvec needs: the sources of the accepted pairs and everything below them (a parent's
+  // multipole is built from its children's).  The root and the first levels under it are never a source at
+  // theta < 1, so the upward sweep stops early -- like the reference's lazy lists (EvalInteractionLazy.hpp:158-183).
+  T.need_M.resize(nb); T.need_M.zero(s);
+  if (n_lr) mark_sources<<<nblk(n_lr, 256), 256, 0, s>>>(T.lr.p, n_lr, T.need_M.p);
+  for (int l = 1; l < T.nlevels; ++l) {
+    int a = T.level_off[l], b = T.level_off[l + 1];
+    if (b > a) inherit_local<<<nblk(b - a, 256), 256, 0, s>>>(T.parent.p, a, b, T.need_M.p);
+  }
+  FMMB_CUDA(cudaGetLastError());
+  T.need_M_host = T.need_M.to_host(s);
 
   // work count
   {
