@@ -111,6 +111,7 @@ int fmmb_plan_create(const fmmb_kernel_desc* kernel, const fmmb_sources* sources
     plan->opts = opts;
     plan->kind = kernel->kind;
     if (const char* g = std::getenv("FMMB_USE_GRAPH")) plan->use_graph = std::atoi(g) != 0;   // same as set_option
+    if (const char* g = std::getenv("FMMB_M2L_MODE")) plan->opts.m2l_mode = std::atoi(g);     // experiments: drivers that build their own FMMOptions
     plan->p = kernel->p;
     // the far-field chain (many short dependent kernels and the collectives) outranks the near-field kernel
     // that runs beside it: its blocks take the SM slots first whenever both have work
@@ -135,9 +136,10 @@ int fmmb_plan_create(const fmmb_kernel_desc* kernel, const fmmb_sources* sources
         }
       pts = centres.data();
     }
-    build_tree(plan, pts, sources->n);
+    { NvtxRange r("fmmb: octree + dual traversal"); build_tree(plan, pts, sources->n); }
     plan->near_only = opts.near_only;
     if (opts.near_only == 2) restrict_p2p_to_self(plan);
+    NvtxRange r_far("fmmb: translation classes / near-field items / kernel setup");
     if (!opts.near_only) {
       // YukawaCartesian[BEM] runs its own translation kernels on the class tables of m2l_classes.cu; the Laplace
       // family runs the engine fmmb_options.m2l_mode selects (laplace_build_far)
@@ -207,6 +209,7 @@ static void run_matvec(fmmb_plan* plan, const double* q, double* r) {
     explicit CountScope(fmmb_plan* p) : prev(g_realloc_counter) { g_realloc_counter = &p->realloc_count; }
     ~CountScope() { g_realloc_counter = prev; }
   } scope(plan);
+  NvtxRange r_mv(plan->call_sharded ? "fmmb: sharded matvec" : "fmmb: matvec");
   auto direct = [&] {
     // sharded call of a class that gathers its charges through a permutation: assemble the tree-ordered vector first
     if (plan->call_sharded && plan->kind != FMMB_LAPLACE_SPHERICAL) plan->sharded_q = sharded_assemble_charges(plan, q, plan->stream);

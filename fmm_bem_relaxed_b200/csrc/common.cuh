@@ -9,6 +9,7 @@
 #include <vector>
 #include <map>
 #include <functional>
+#include <nvtx3/nvToolsExt.h>
 #include "../../include/fmmb.h"
 
 namespace fmmb {
@@ -27,6 +28,14 @@ struct CudaError {
     cudaError_t e_ = (call);                                                   \
     if (e_ != cudaSuccess) throw ::fmmb::CudaError{e_, #call, __FILE__, __LINE__}; \
   } while (0)
+
+// NVTX range for the host-side span of a plan-time step or of a matvec's launch sequence (timeline tools)
+struct NvtxRange {
+  explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+  NvtxRange(const NvtxRange&) = delete;
+  NvtxRange& operator=(const NvtxRange&) = delete;
+};
 
 struct StatusError {
   int status;

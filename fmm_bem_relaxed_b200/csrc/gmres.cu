@@ -170,6 +170,7 @@ void gmres_solve(fmmb_plan* plan, const double* b_host, double* x_host, const do
     i = -1;
     resid = sv[0] / normb;
     do {
+      NvtxRange r_it("fmmb_gmres: iteration (predict_p, matvec, Gram-Schmidt, Givens)");
       ++i; ++iter;
       // GMRES.hpp:195: max(1u, predict_p);  GMRES_Stokes.hpp:229: max(p_min, predict_p - 1)
       const unsigned pp = predict_p(o, std::fabs(resid));

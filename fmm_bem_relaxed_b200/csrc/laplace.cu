@@ -1378,6 +1378,7 @@ void laplace_execute(fmmb_plan* plan, const double* d_charges, double* d_results
   plan->launches = 0;
 
   // ---- charges into the tree-ordered bodies
+  NvtxRange r_exec("fmmb: LaplaceSpherical launches (gather, P2P, P2M, translations, L2P, scatter)");
   if (!plan->capturing) FMMB_CUDA(cudaEventRecord(ev[0], s));
   if (plan->call_sharded) {
     // charges = this rank's slice in tree order, no permutation

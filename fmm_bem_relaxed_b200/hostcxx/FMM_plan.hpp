@@ -14,6 +14,7 @@
 #include <cstdio>
 #include <iostream>
 #include <vector>
+#include <cstdlib>
 
 #include "Vec.hpp"
 #include "Mat3.hpp"       // the reference's FMM_plan.hpp brings it in through its executors (include/Matvec.hpp:11)
@@ -79,6 +80,20 @@ class FMM_plan {
       std::cerr << "[E]: FMM_plan::execute: "
                 << (charges.size() != n_ ? "charges.size() != sources.size()" : fmmb_last_error()) << "\n";
       return std::vector<result_type>(0);
+    }
+    // the reference prints its two dominant phases after every execute (include/executor/EvalInteractionLazy.hpp:152);
+    // here that line is opt-in (FMMB_PRINT_PHASES=1) and carries device times -- both phases when the matvec ran
+    // as plain launches, the whole matvec when it was one CUDA-graph replay
+    static const bool print_phases = std::getenv("FMMB_PRINT_PHASES") != nullptr;
+    if (print_phases) {
+      double ms[FMMB_T_COUNT] = {0};
+      fmmb_plan_info info;
+      if (fmmb_plan_phase_times(plan_, ms, FMMB_T_COUNT) == FMMB_OK && fmmb_plan_get_info(plan_, &info) == FMMB_OK) {
+        if (ms[FMMB_T_P2P] > 0 || ms[FMMB_T_M2L] > 0)
+          printf("P2P: %.4gs, M2L (%d): %.4gs\n", ms[FMMB_T_P2P] * 1e-3, (int)info.n_m2l_pairs, ms[FMMB_T_M2L] * 1e-3);
+        else
+          printf("matvec (CUDA graph): %.4gs, M2L pairs %d\n", ms[FMMB_T_TOTAL] * 1e-3, (int)info.n_m2l_pairs);
+      }
     }
     return results;
   }
