@@ -640,7 +640,8 @@ def main():
     ap.add_argument("--steps", type=int, default=None)
     ap.add_argument("--warmup", type=int, default=None)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--n", type=int, default=1000000)
+    ap.add_argument("--n", "--npoints", dest="n", type=int, default=1000000,
+                    help="bodies (under torchrun use --npoints: its own parser claims the prefix --n)")
     ap.add_argument("--p", type=int, default=8)
     ap.add_argument("--theta", type=float, default=0.5)
     ap.add_argument("--ncrit", type=int, default=64)

@@ -669,8 +669,8 @@ __global__ void p2p_items_ext_kernel(int4* __restrict__ items, int n, const unsi
 // the large CTAs of the DMMA GEMM never accumulate the registers they need until the near field is done).  Measured:
 // the far field does hide under the near field, but at 8 warps per SM the pair loop is latency-bound per warp and
 // the matvec is not faster than with the plain grid -- kept as an option, not the default.
-template <int UNROLL, bool PERSIST>
-__global__ void __launch_bounds__(32)
+template <int UNROLL, bool PERSIST, int MINB = 1>
+__global__ void __launch_bounds__(32, MINB)
 p2p_pair2_kernel(const int4* __restrict__ items, const int4* __restrict__ items_ext, int nitems,
                  const int2* __restrict__ runs, const double4* __restrict__ body, double4 dummy,
                  double4* __restrict__ res, unsigned* __restrict__ counter) {
@@ -1312,6 +1312,14 @@ static void launch_near_field(fmmb_plan* plan, cudaStream_t s, cudaStream_t s2) 
       FMMB_CUDA(cudaMemsetAsync(plan->p2p_counter.p, 0, sizeof(unsigned), s2));
       p2p_pair2_kernel<4, true><<<grid, 32, cap, s2>>>(T.p2p_items.p, T.p2p_items_ext.p, ni, T.p2p_runs.p, T.body.p, dummy,
                                                        plan->res_near.p, plan->p2p_counter.p);
+    } else if (plan->p2p_kernel == 2 && plan->p2p_occ > 20) {   // the same kernel compiled for more resident warps
+#define FMMB_P2P_OCC(B)                                                                                              \
+      p2p_pair2_kernel<4, false, B><<<ni, 32, 0, s2>>>(T.p2p_items.p, T.p2p_items_ext.p, ni, T.p2p_runs.p, T.body.p, \
+                                                       dummy, plan->res_near.p, nullptr)
+      if (plan->p2p_occ >= 32) FMMB_P2P_OCC(32);
+      else if (plan->p2p_occ >= 28) FMMB_P2P_OCC(28);
+      else FMMB_P2P_OCC(24);
+#undef FMMB_P2P_OCC
     } else if (plan->p2p_kernel == 2) {             // two targets per lane, merged runs, register prefetch
       if (u == 8)
         p2p_pair2_kernel<8, false><<<ni, 32, 0, s2>>>(T.p2p_items.p, T.p2p_items_ext.p, ni, T.p2p_runs.p, T.body.p, dummy,

@@ -440,44 +440,60 @@ trans_sweep_kernel(const SweepArgs a) {
     if (rows_live) {
       const unsigned mask = (unsigned)d0.x >> 16;
       const double* st = stage + (size_t)(v & 1) * C::STAGE;
-      // the warp's 8 rows of T_c: fragment-major, 16 bytes per lane and k-step pair
-      double2 A2[KB2];
+      // The warp's 8 rows of T_c (fragment-major, 16 bytes per lane and k-step pair) are taken in two halves of the k
+      // range: half the fragment registers, which leaves room to run the source-fragment loads from shared memory one
+      // k-step pair ahead of the DMMAs that use them.  Column tiles are dealt round-robin to the NCG warp columns (the
+      // tiles of a class spread over all of them) and taken two at a time with their k loops interleaved: independent
+      // accumulator chains hide the 26-cycle latency of a dependent DMMA.
+      constexpr int QH = KB2 > 4 ? (KB2 + 1) / 2 : KB2;      // k-step pairs per half
       const double2* As = reinterpret_cast<const double2*>(st + kCols * LDB) + rt * KB2 * 32 + lane;
-#pragma unroll
-      for (int q = 0; q < KB2; ++q) A2[q] = As[q * 32];
       const double* Bw = st + (size_t)lr * LDB + lk;
-      // Column tiles are dealt round-robin to the NCG warp columns (the tiles of a class spread over all of them)
-      // and taken two at a time with their k loops interleaved: independent accumulator chains hide the 26-cycle
-      // latency of a dependent DMMA.
-      auto one = [&](double (&c)[2], const double* Bs) {
-#pragma unroll
-        for (int q = 0; q < KB2; ++q) {
-          dmma8x8x4(c[0], c[1], A2[q].x, Bs[8 * q]);
-          if (2 * q + 1 < KB) dmma8x8x4(c[0], c[1], A2[q].y, Bs[8 * q + 4]);
-        }
-      };
-      auto two = [&](double (&c)[2], const double* Bs, double (&e)[2], const double* Es) {
-#pragma unroll
-        for (int q = 0; q < KB2; ++q) {
-          dmma8x8x4(c[0], c[1], A2[q].x, Bs[8 * q]);
-          dmma8x8x4(e[0], e[1], A2[q].x, Es[8 * q]);
-          if (2 * q + 1 < KB) {
-            dmma8x8x4(c[0], c[1], A2[q].y, Bs[8 * q + 4]);
-            dmma8x8x4(e[0], e[1], A2[q].y, Es[8 * q + 4]);
-          }
-        }
-      };
       auto bcol = [&](int ct) { return Bw + (size_t)__popc(mask & ((1u << ct) - 1u)) * 8 * LDB; };
-      if (TPW == 1) {
-        if ((mask >> cg) & 1u) one(acc[0], bcol(cg));
-      } else {
 #pragma unroll
-        for (int t = 0; t < TPW; t += 2) {
-          const int c0 = t * C::NCG + cg, c1 = (t + 1) * C::NCG + cg;
-          const bool h0 = (mask >> c0) & 1u, h1 = (mask >> c1) & 1u;
-          if (h0 && h1) two(acc[t], bcol(c0), acc[t + 1], bcol(c1));
-          else if (h0) one(acc[t], bcol(c0));
-          else if (h1) one(acc[t + 1], bcol(c1));
+      for (int q0 = 0; q0 < KB2; q0 += QH) {
+        double2 A2[QH];
+#pragma unroll
+        for (int q = 0; q < QH; ++q) A2[q] = q0 + q < KB2 ? As[(q0 + q) * 32] : make_double2(0.0, 0.0);
+        auto one = [&](double (&c)[2], const double* Bs) {
+          double bx = Bs[8 * q0], by = Bs[8 * q0 + 4];
+#pragma unroll
+          for (int q = 0; q < QH; ++q) {
+            if (q0 + q >= KB2) break;
+            const double cx = bx, cy = by;
+            if (q + 1 < QH && q0 + q + 1 < KB2) { bx = Bs[8 * (q0 + q + 1)]; by = Bs[8 * (q0 + q + 1) + 4]; }
+            dmma8x8x4(c[0], c[1], A2[q].x, cx);
+            if (2 * (q0 + q) + 1 < KB) dmma8x8x4(c[0], c[1], A2[q].y, cy);
+          }
+        };
+        auto two = [&](double (&c)[2], const double* Bs, double (&e)[2], const double* Es) {
+          double bx = Bs[8 * q0], by = Bs[8 * q0 + 4], ex = Es[8 * q0], ey = Es[8 * q0 + 4];
+#pragma unroll
+          for (int q = 0; q < QH; ++q) {
+            if (q0 + q >= KB2) break;
+            const double cx = bx, cy = by, dx = ex, dy = ey;
+            if (q + 1 < QH && q0 + q + 1 < KB2) {
+              bx = Bs[8 * (q0 + q + 1)]; by = Bs[8 * (q0 + q + 1) + 4];
+              ex = Es[8 * (q0 + q + 1)]; ey = Es[8 * (q0 + q + 1) + 4];
+            }
+            dmma8x8x4(c[0], c[1], A2[q].x, cx);
+            dmma8x8x4(e[0], e[1], A2[q].x, dx);
+            if (2 * (q0 + q) + 1 < KB) {
+              dmma8x8x4(c[0], c[1], A2[q].y, cy);
+              dmma8x8x4(e[0], e[1], A2[q].y, dy);
+            }
+          }
+        };
+        if (TPW == 1) {
+          if ((mask >> cg) & 1u) one(acc[0], bcol(cg));
+        } else {
+#pragma unroll
+          for (int t = 0; t < TPW; t += 2) {
+            const int c0 = t * C::NCG + cg, c1 = (t + 1) * C::NCG + cg;
+            const bool h0 = (mask >> c0) & 1u, h1 = (mask >> c1) & 1u;
+            if (h0 && h1) two(acc[t], bcol(c0), acc[t + 1], bcol(c1));
+            else if (h0) one(acc[t], bcol(c0));
+            else if (h1) one(acc[t + 1], bcol(c1));
+          }
         }
       }
     }

@@ -58,16 +58,23 @@ def launches(tag):
     os.system("cp %s %s" % (path, os.path.join(OUT, "launches_%s.csv" % tag)))
 
 
+def longest(H, rows):
+    i = H.index("gpu__time_duration.sum")
+    return max((r for r in rows if len(r) > i), key=lambda r: float(r[i].replace(",", "")))
+
+
 def report(rep, tag):
     path = os.path.join(GP, rep + ".ncu-rep")
     if not os.path.exists(path):
         return
     raw = subprocess.check_output(["ncu", "-i", path, "--page", "raw", "--csv"]).decode()
     rows = list(csv.reader(io.StringIO(raw)))
-    H, U, V = rows[0], rows[1], rows[2]
+    H, U = rows[0], rows[1]
+    V = longest(H, rows[2:])             # several launches captured: summarise the longest one
     with open(os.path.join(OUT, rep + ".md"), "w") as f:
         f.write("# %s\n\n`ncu --set full --clock-control none --import-source on`, one launch of the kernel inside "
-                "`python bench.py --steps 1 --warmup 3 --no-cpu-baseline` (N=1M, P=8).\n\n" % rep)
+                "`python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-c5` (N=1M, P=8); when the capture holds several "
+                "launches of the kernel, the longest one.\n\n" % rep)
         name = V[H.index("Kernel Name")]
         f.write("kernel: `%s`\n\n| metric | unit | value |\n|---|---|---:|\n" % name)
         for k in KEYS:
@@ -76,8 +83,8 @@ def report(rep, tag):
                 f.write("| %s | %s | %s |\n" % (k, U[i], V[i]))
 
 
-def traffic(reps):
-    """profiles/traffic_r01.json: DRAM bytes per launch of the top kernels (read by bench.py for roofline.traffic)."""
+def traffic(reps, tag):
+    """profiles/traffic_rNN.json: DRAM bytes per launch of the top kernels (read by bench.py for roofline.traffic)."""
     import json
     out = {}
     for key, rep in reps.items():
@@ -86,7 +93,8 @@ def traffic(reps):
             continue
         raw = subprocess.check_output(["ncu", "-i", path, "--page", "raw", "--csv"]).decode()
         rows = list(csv.reader(io.StringIO(raw)))
-        H, U, V = rows[0], rows[1], rows[2]
+        H, U = rows[0], rows[1]
+        V = longest(H, rows[2:])
         scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
 
         def val(name):
@@ -98,7 +106,7 @@ def traffic(reps):
                     {"ms": 1.0, "us": 1e-3, "ns": 1e-6}.get(U[H.index("gpu__time_duration.sum")].replace("second", "s")
                                                           .replace("msecond", "ms"), 1.0)}
     if out:
-        json.dump(out, open(os.path.join(OUT, "traffic_r01.json"), "w"), indent=1)
+        json.dump(out, open(os.path.join(OUT, "traffic_%s.json" % tag.split("_")[0]), "w"), indent=1)
 
 
 if __name__ == "__main__":
@@ -108,4 +116,4 @@ if __name__ == "__main__":
     reps = [a for a in sys.argv[2:] if "=" not in a]
     for rep in reps:
         report(rep, tag)
-    traffic(dict(a.split("=", 1) for a in sys.argv[2:] if "=" in a))
+    traffic(dict(a.split("=", 1) for a in sys.argv[2:] if "=" in a), tag)
