@@ -328,6 +328,7 @@ int fmmb_plan_execute_sharded_host(fmmb_plan* plan, const double* charges_own_ho
     FMMB_CUDA(cudaEventRecord(plan->ev[10], s));
     if (own) FMMB_CUDA(cudaMemcpyAsync(results_own_host, plan->own_r.p, rd * own * sizeof(double), cudaMemcpyDeviceToHost, s));
     FMMB_CUDA(cudaEventRecord(plan->ev[11], s));
+    peer_flag_fetch(plan, s);
     FMMB_CUDA(cudaStreamSynchronize(s));
     update_phase_times(plan);
     float t = 0;
@@ -524,6 +525,7 @@ int fmmb_plan_sync(fmmb_plan* plan) {
   if (!plan) { set_error("null plan"); return FMMB_ERR_INVALID; }
   return guarded([&] {
     FMMB_CUDA(cudaSetDevice(plan->device));
+    peer_flag_fetch(plan, plan->stream);
     FMMB_CUDA(cudaStreamSynchronize(plan->stream));
     update_phase_times(plan);
     peer_check_timeout(plan);

@@ -441,6 +441,7 @@ void peer_init(fmmb_plan* plan, const unsigned char* blobs) {
 }
 
 void peer_close(fmmb_plan* plan) {
+  if (plan->peer_flag_host) { cudaFreeHost(plan->peer_flag_host); plan->peer_flag_host = nullptr; }
   for (void* p : plan->peer_opened) cudaIpcCloseMemHandle(p);
   plan->peer_opened.clear();
   plan->peer_ready = false;
@@ -475,16 +476,23 @@ void peer_exchange_charges(fmmb_plan* plan, const double* d_own, cudaStream_t s)
   plan->launches += 2;
 }
 
-// After a synchronisation: did a bounded flag wait of the peer exchange give up?
-void peer_check_timeout(fmmb_plan* plan) {
+// Did a bounded flag wait of the peer exchange give up?  The flag travels to a pinned host word behind the matvec
+// (peer_flag_fetch, asynchronous, 8 bytes) and is looked at after the caller's synchronisation (peer_check_timeout):
+// no extra blocking copy on the host-buffer call path.
+void peer_flag_fetch(fmmb_plan* plan, cudaStream_t s) {
   if (!plan->peer_ready) return;
-  unsigned long long flag = 0;
-  FMMB_CUDA(cudaMemcpy(&flag, plan->peer_state.p + 3, sizeof flag, cudaMemcpyDeviceToHost));
-  if (flag) {
-    FMMB_CUDA(cudaMemset(plan->peer_state.p + 3, 0, sizeof flag));
-    throw StatusError{FMMB_ERR_CUDA, "peer-memory exchange timed out: a rank did not arrive within 20 s "
-                                     "(all ranks must run the same sequence of matvecs); the last results are invalid"};
+  if (!plan->peer_flag_host) {
+    FMMB_CUDA(cudaHostAlloc((void**)&plan->peer_flag_host, sizeof(unsigned long long), cudaHostAllocDefault));
+    *plan->peer_flag_host = 0;
   }
+  FMMB_CUDA(cudaMemcpyAsync(plan->peer_flag_host, plan->peer_state.p + 3, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+}
+void peer_check_timeout(fmmb_plan* plan) {
+  if (!plan->peer_ready || !plan->peer_flag_host || !*plan->peer_flag_host) return;
+  *plan->peer_flag_host = 0;
+  FMMB_CUDA(cudaMemset(plan->peer_state.p + 3, 0, sizeof(unsigned long long)));
+  throw StatusError{FMMB_ERR_CUDA, "peer-memory exchange timed out: a rank did not arrive within 20 s "
+                                   "(all ranks must run the same sequence of matvecs); the last results are invalid"};
 }
 
 void peer_read_done(fmmb_plan* plan, cudaStream_t s) {

@@ -271,6 +271,7 @@ struct fmmb_plan {
   fmmb::DevBuf<unsigned long long*> peer_flags;       // per rank: its flag tail
   fmmb::DevBuf<unsigned long long> peer_state;        // [0] matvec counter, [1] push-kernel block counter
   std::vector<void*> peer_opened;
+  unsigned long long* peer_flag_host = nullptr;       // pinned: timeout flag of the bounded flag waits, fetched per call
   std::function<void()> hook_after_owned_m2m;  // set by laplace_execute around laplace_translations
   bool call_sharded = false;         // the current call is fmmb_plan_execute_sharded
   bool cuts_ready = false;
@@ -342,6 +343,7 @@ void peer_close(fmmb_plan* plan);
 void exchange_multipoles_peer(fmmb_plan* plan, cudaStream_t s);
 void peer_exchange_charges(fmmb_plan* plan, const double* d_own, cudaStream_t s);
 void peer_read_done(fmmb_plan* plan, cudaStream_t s);
+void peer_flag_fetch(fmmb_plan* plan, cudaStream_t s);
 void peer_check_timeout(fmmb_plan* plan);
 // laplace.cu
 void laplace_init_tables(fmmb_plan* plan);

@@ -23,6 +23,15 @@
 //  * small phases (multi-GPU shards, top levels, BEM meshes) split the item list of a block over 2..8 CTAs; the
 //    partial accumulators meet in a small scratch array and the last CTA to arrive adds them in split order.
 //  * orders 9..16: the contraction is cut into k-chunks of 64 and the rows into blocks of 64.
+//
+// Where the time goes (B200, N = 1M, P = 8, the M2L phase of the sweep, 1.77 ms): with the DMMAs removed the phase
+// takes 0.96 ms, with the operand copies removed 1.44 ms, with both removed 0.33 ms (the per-item loop: barrier,
+// descriptors).  The math alone (1.1 ms) is at the DMMA pipe's rate for the 16.8 % padded tile count; the copies move
+// 5.5 GB out of L2 (3.2 GB of T slices, 2.3 GB of source expansions) at the 8.9 TB/s this access shape measures
+// (scripts/micro/probe_r2.cu) and overlap the math poorly at a prefetch distance of one item, because half of the
+// items are the two-tile items of the classes with three odd offset components.  The class-major engine of
+// m2l_classes.cu keeps T_c in registers across ~190 items and pays with a column scratch instead; at orders <= 8 it
+// is the faster of the two on a uniform tree (1.58 ms) and the default there.
 #include "common.cuh"
 #include "laplace_ops.cuh"
 #include <cub/cub.cuh>
