@@ -185,7 +185,7 @@ struct TransBatch {
 // blocks of <= 128 columns, per block the list of (class, active column tiles) items.
 struct BlkBatch {
   int kind = 0;                      // 0 = M2L, 1 = M2M, 2 = L2L
-  int n_blocks = 0, n_items = 0, sms = 148;
+  int n_blocks = 0, n_items = 0;
   int64_t n_pairs = 0, n_tiles = 0, n_classes = 0;
   DevBuf<int2> items;                // x = class | (tile mask << 16), y = first tile of the item
   DevBuf<int> tile_src;              // 8 source boxes per active tile (nboxes = the all-zero expansion)
@@ -195,8 +195,6 @@ struct BlkBatch {
   std::vector<int> level_blk_off;    // blocks whose targets are at level l: [l], [l + 1])
   DevBuf<double4> class_vec;         // translation vector of a class (target centre - source centre)
   std::map<int, DevBuf<double>*> T;  // per order: fragment-major translation matrices
-  DevBuf<double> scratch;            // split launches: partial accumulators
-  DevBuf<unsigned> counters;
   BlkBatch() {}
   BlkBatch(const BlkBatch&) = delete;
   BlkBatch& operator=(const BlkBatch&) = delete;

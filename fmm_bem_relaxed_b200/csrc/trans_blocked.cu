@@ -609,6 +609,8 @@ const double* ensure_T(fmmb_plan* plan, BlkBatch& B, int P, cudaStream_t s) {
 }  // namespace
 
 
+static void check_blk_batch(fmmb_plan* plan, const BlkBatch& B, const int* d_tgt, const int* d_src, int64_t n);
+
 // Plan time: pairs (tgt[e], src[e]), e < n (device arrays) -> classes, blocks, items.  kind: 0 M2L, 1 M2M, 2 L2L.
 void build_blk_batch(fmmb_plan* plan, BlkBatch& B, int kind, const int* d_tgt, const int* d_src, int64_t n) {
   Tree& T = plan->tree;
@@ -732,13 +734,61 @@ void build_blk_batch(fmmb_plan* plan, BlkBatch& B, int kind, const int* d_tgt, c
     FMMB_CUDA(cub::DeviceRadixSort::SortPairsDescending(t, bytes, w0.p, w1.p, id0.p, B.blk_order.p, nblocks, 0, 32, s));
     FMMB_CUDA(cudaStreamSynchronize(s));
   }
-  // scratch for split launches: at most 2 x SMs CTAs take part in one
-  int sms = 148;
-  FMMB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, plan->device));
-  B.sms = sms;
-  B.counters.resize((size_t)4 * sms * 4);
-  B.counters.zero(s);
   FMMB_CUDA(cudaStreamSynchronize(s));
+  static const bool self_check = std::getenv("FMMB_SELF_CHECK") != nullptr;
+  if (self_check) check_blk_batch(plan, B, d_tgt, d_src, n);
+}
+
+// Host-side audit of a batch (FMMB_SELF_CHECK=1; compute-sanitizer is not available on every pool): every index the
+// sweep kernel will dereference is inside its array, every pair of the input appears exactly once, masks and tile
+// offsets are consistent.  Throws FMMB_ERR_INVALID with the first violation.
+static void check_blk_batch(fmmb_plan* plan, const BlkBatch& B, const int* d_tgt, const int* d_src, int64_t n) {
+  cudaStream_t s = plan->stream;
+  const int nb = plan->tree.nboxes;
+  auto fail = [&](const std::string& m) { throw StatusError{FMMB_ERR_INVALID, "blocked batch self-check: " + m}; };
+  std::vector<int2> items = B.items.to_host(s);
+  std::vector<int> tsrc = B.tile_src.to_host(s), off = B.blk_item_off.to_host(s), cols = B.blk_cols.to_host(s),
+                   order = B.blk_order.to_host(s);
+  std::vector<int> tg(n), sr(n);
+  FMMB_CUDA(cudaMemcpy(tg.data(), d_tgt, n * sizeof(int), cudaMemcpyDeviceToHost));
+  FMMB_CUDA(cudaMemcpy(sr.data(), d_src, n * sizeof(int), cudaMemcpyDeviceToHost));
+  if ((int)off.size() != B.n_blocks + 1 || off[0] != 0 || off[B.n_blocks] != B.n_items) fail("block item offsets");
+  if ((int64_t)tsrc.size() != B.n_tiles * 8 || (int)items.size() != B.n_items) fail("array sizes");
+  std::vector<char> seen_blk(B.n_blocks, 0);
+  for (int b : order) { if (b < 0 || b >= B.n_blocks || seen_blk[b]) fail("launch order is not a permutation"); seen_blk[b] = 1; }
+  std::vector<long long> pair_key;
+  pair_key.reserve(n);
+  int64_t tile = 0;
+  for (int b = 0; b < B.n_blocks; ++b) {
+    if (off[b + 1] <= off[b]) fail("empty block");
+    for (int c = 0; c < kCols; ++c) { const int t = cols[(size_t)b * kCols + c]; if (t < -1 || t >= nb) fail("column target out of range"); }
+    for (int i = off[b]; i < off[b + 1]; ++i) {
+      const unsigned mask = (unsigned)items[i].x >> 16;
+      const int cls = items[i].x & 0xffff;
+      if (cls >= B.n_classes || !mask) fail("item class / empty mask");
+      if (items[i].y != tile) fail("tile offsets are not consecutive");
+      int j = 0;
+      for (int ct = 0; ct < 16; ++ct) {
+        if (!((mask >> ct) & 1u)) continue;
+        for (int k = 0; k < 8; ++k) {
+          const int src = tsrc[(size_t)(tile + j) * 8 + k], t = cols[(size_t)b * kCols + ct * 8 + k];
+          if (src < 0 || src > nb) fail("source box out of range");
+          if (src < nb) {
+            if (t < 0) fail("pair into an empty column");
+            pair_key.push_back(((long long)t << 32) | (unsigned)src);
+          }
+        }
+        ++j;
+      }
+      tile += j;
+    }
+  }
+  if (tile != B.n_tiles) fail("tile count");
+  std::vector<long long> want(n);
+  for (int64_t e = 0; e < n; ++e) want[e] = ((long long)tg[e] << 32) | (unsigned)sr[e];
+  std::sort(want.begin(), want.end());
+  std::sort(pair_key.begin(), pair_key.end());
+  if (want != pair_key) fail("the items do not hold exactly the input pairs");
 }
 
 // Plan time: the unit list of a sweep.  phases: (batch slot, first block, block count, heavy-first order) in

@@ -322,3 +322,24 @@ def test_order_changes_do_not_replay_stale_graphs():
     for p in (5, 5, 5, 12, 5, 5, 12, 12, 12, 5, 5):
         plan.kernel().set_p(p)
         assert_parity(plan.execute(q), ref[p])
+
+
+def test_blocked_batches_pass_their_host_side_audit(monkeypatch):
+    """compute-sanitizer is closed on this GPU pool, so the plan-time structures of the fused sweep engine carry their
+    own audit (FMMB_SELF_CHECK=1, csrc/trans_blocked.cu::check_blk_batch): every index the kernel dereferences is in
+    range, launch orders are permutations, and the items hold exactly the input pairs -- on a uniform and on a strongly
+    adaptive tree, single-rank and as one of three ranks."""
+    monkeypatch.setenv("FMMB_SELF_CHECK", "1")
+    rng = np.random.default_rng(9)
+    n = 30000
+    uni = rng.random((n, 3))
+    ada = rng.random((n, 3))
+    ada[n // 3:] = 0.2 + 0.02 * rng.random((n - n // 3, 3))
+    for pts in (uni, ada):
+        for rank, nranks in ((0, 1), (1, 3)):
+            opts = F.FMMOptions()
+            opts.m2l_mode = 3
+            opts.rank, opts.nranks = rank, nranks
+            plan = F.FMM_plan(F.LaplaceSpherical(4), pts, opts)      # build_blk_batch audits M2L, M2M, L2L (+ own / strad)
+            plan.execute(rng.random(n))
+            plan.close()
