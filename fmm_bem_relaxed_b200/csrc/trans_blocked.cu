@@ -735,8 +735,7 @@ void build_blk_batch(fmmb_plan* plan, BlkBatch& B, int kind, const int* d_tgt, c
     FMMB_CUDA(cudaStreamSynchronize(s));
   }
   FMMB_CUDA(cudaStreamSynchronize(s));
-  static const bool self_check = std::getenv("FMMB_SELF_CHECK") != nullptr;
-  if (self_check) check_blk_batch(plan, B, d_tgt, d_src, n);
+  if (std::getenv("FMMB_SELF_CHECK")) check_blk_batch(plan, B, d_tgt, d_src, n);   // read per call: tests toggle it
 }
 
 // Host-side audit of a batch (FMMB_SELF_CHECK=1; compute-sanitizer is not available on every pool): every index the

@@ -209,7 +209,12 @@ int fmmb_plan_direct_panels(fmmb_plan* plan, const double* charges_host, int64_t
  *   "m2l_mode"     see fmmb_options.m2l_mode.
  *   "p2p_items"    near-field work decomposition of point kernels: 0 = chunks of <= 32 targets in leaf order
  *                  (default); 1 = chunks of 32 targets plus power-of-two pieces of the remainder, longest first.
- *   "p2p_kernel"   0 = one tile per source leaf (default); 1 = merged source runs, fixed 32-source tiles, prefetch.
+ *   "p2p_kernel"   0 = one tile per source leaf; 1 = merged source runs, fixed 32-source tiles, prefetch; 2 = the same
+ *                  with two targets per lane (default); 3 = 2 with the source tiles staged by 1-D TMA bulk copies.
+ *   "p2p_occ"      resident warps per SM the default pair kernel is compiled for: 20, 24, 28 (default) or 32.
+ *   "p2p_newton"   1 = Newton-only inverse root in p2p_kernel 3 (16 instead of 18 FP64 instructions per pair; the
+ *                  near field is then accurate to ~1e-13 instead of round-off).  Default 0.
+ *   "p2p_wps"      > 0: persistent near-field blocks, that many one-warp blocks per SM (default 0 = plain grid).
  *   "p2p_unroll"   pair-loop unroll of p2p_kernel 1: 4 (default) or 8.
  *   "p2p_warps"    warps per block of the near-field pair kernel: 1 (default), 2 or 4.
  *   (measured on B200 at N = 1M: all combinations within 4 %; see profiles/README.md) */
