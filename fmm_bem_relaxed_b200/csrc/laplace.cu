@@ -86,6 +86,72 @@ p2m_kernel(const int* __restrict__ leaves, int nleaves, const unsigned* __restri
   }
 }
 
+// ---- P2M with a narrow transposition tile ---------------------------------------------------------------------------
+// p2m_kernel holds all P^2 values of 32 bodies in shared memory (16.6 KB per warp at P = 8: 12 warps per SM, FP64
+// pipe 26 % busy, issue-latency bound).  Here the columns of the harmonics table are flushed in chunks of <= kP2MCols
+// values as the m-major recurrence produces them: 6.4 KB per warp, more than twice the resident warps.  Same sums in
+// the same order (bodies ascending per coefficient), so the multipoles are bit-identical to p2m_kernel's.
+constexpr int kP2MCols = 24;
+__global__ void __launch_bounds__(128)
+p2m_cols_kernel(const int* __restrict__ leaves, int nleaves, const unsigned* __restrict__ bb,
+                const unsigned* __restrict__ be, const double4* __restrict__ center,
+                const double4* __restrict__ body, int P, double* __restrict__ M) {
+  constexpr int ld = kP2MCols | 1;
+  __shared__ double tiles[4][32 * ld];
+  __shared__ int colidx[4][kP2MCols];
+  const int pp = P * P;
+  const int wl = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int w = blockIdx.x * (blockDim.x >> 5) + wl;
+  if (w >= nleaves) return;
+  double* tile = tiles[wl];
+  int* cidx = colidx[wl];
+  const int b = leaves[w];
+  const double4 c = center[b];
+  const unsigned b0 = bb[b], b1 = be[b];
+  double* Mb = M + (size_t)b * xstride(P);
+  bool first = true;
+  for (unsigned base = b0; base < b1; base += 32) {
+    const unsigned i = base + lane;
+    const int cnt = (int)min(32u, b1 - base);
+    const bool live = i < b1;
+    const double4 p = live ? body[i] : make_double4(c.x + 0.125, c.y + 0.25, c.z + 0.5, 0.0);   // idle lanes: any regular point
+    const double q = p.w;
+    const Sph s = to_sph(p.x - c.x, p.y - c.y, p.z - c.z);
+    double* row = tile + lane * ld;
+    int pos = 0;                                    // values of the current chunk written so far (warp-uniform)
+    auto flush = [&]() {
+      __syncwarp();
+      if (lane < pos) {
+        double sum = 0;
+        for (int k = 0; k < cnt; ++k) sum += tile[k * ld + lane];
+        double* o = Mb + cidx[lane];
+        *o = first ? sum : *o + sum;
+      }
+      __syncwarp();
+      pos = 0;
+    };
+    regular_harmonics<false>(
+        P, s, -1.0,
+        [&](int n, int m, double yr, double yi, double, double) {
+          row[pos] = q * yr;
+          if (lane == 0) cidx[pos] = n * n + n + m;
+          ++pos;
+          if (m > 0) {
+            row[pos] = q * yi;
+            if (lane == 0) cidx[pos] = n * n + n - m;
+            ++pos;
+          }
+        },
+        [&](int m) {
+          // room for the next column (2 (P - m - 1) values)?  otherwise flush what the tile holds
+          const int next = m + 1 < P ? 2 * (P - m - 1) : kP2MCols + 1;
+          if (pos + next > kP2MCols) flush();
+        });
+    first = false;
+  }
+  if (lane == 0 && xstride(P) > pp) Mb[pp] = 0.0;   // padding double of odd-sized expansions
+}
+
 // ---- M2M: block per parent box of one level; children accumulate in index order ----------------
 __global__ void __launch_bounds__(64)
 m2m_kernel(int lo, int hi, const int* __restrict__ box_list, const unsigned* __restrict__ key,
@@ -1310,8 +1376,9 @@ static void launch_near_field(fmmb_plan* plan, cudaStream_t s, cudaStream_t s2) 
       const size_t cap = 0;
       plan->p2p_counter.resize(1);
       FMMB_CUDA(cudaMemsetAsync(plan->p2p_counter.p, 0, sizeof(unsigned), s2));
-      p2p_pair2_kernel<4, true><<<grid, 32, cap, s2>>>(T.p2p_items.p, T.p2p_items_ext.p, ni, T.p2p_runs.p, T.body.p, dummy,
-                                                       plan->res_near.p, plan->p2p_counter.p);
+      // the 72-register build: 14 resident blocks leave half of the register file to the far-field kernels
+      p2p_pair2_kernel<4, true, 28><<<grid, 32, cap, s2>>>(T.p2p_items.p, T.p2p_items_ext.p, ni, T.p2p_runs.p, T.body.p,
+                                                           dummy, plan->res_near.p, plan->p2p_counter.p);
     } else if (plan->p2p_kernel == 2 && plan->p2p_occ > 20) {   // the same kernel compiled for more resident warps
 #define FMMB_P2P_OCC(B)                                                                                              \
       p2p_pair2_kernel<4, false, B><<<ni, 32, 0, s2>>>(T.p2p_items.p, T.p2p_items_ext.p, ni, T.p2p_runs.p, T.body.p, \
@@ -1426,7 +1493,11 @@ void laplace_execute(fmmb_plan* plan, const double* d_charges, double* d_results
     FMMB_CUDA(cudaFuncSetAttribute(p2m_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024));
     const int* p2m_list = p2m_owned ? T.own_leaves.p : T.leaves.p;
     const int p2m_n = p2m_owned ? T.n_own_leaves : T.nleaves;
-    if (p2m_n)
+    // narrow-tile kernel whenever the widest column (m = 1: 2 (P - 1) values; m = 0: P values) fits its tile
+    if (p2m_n && plan->p2m_kernel == 1 && 2 * (P - 1) <= kP2MCols && P <= kP2MCols)
+      p2m_cols_kernel<<<nblk(p2m_n, 4), 128, 0, s>>>(p2m_list, p2m_n, T.bbegin.p, T.bend.p, T.center.p, T.body.p, P,
+                                                     plan->M.p);
+    else if (p2m_n)
       p2m_kernel<<<nblk(p2m_n, p2m_warps), 32 * p2m_warps, p2m_sh, s>>>(p2m_list, p2m_n, T.bbegin.p, T.bend.p, T.center.p,
                                                                        T.body.p, P, plan->M.p);
     ++plan->launches;

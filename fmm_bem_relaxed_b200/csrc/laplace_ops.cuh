@@ -29,8 +29,11 @@ __device__ __forceinline__ Sph to_sph(double dx, double dy, double dz) {
 // All rho^n Y_n^m, 0 <= m <= n < P, visited m-major exactly like evalMultipole (:455-488).
 // f(n, m, Yre, Yim, Ytre, Ytim); sign = +1 for e^{+i m phi}, -1 for e^{-i m phi}.
 // SINGULAR: rho^{-n-1} Y_n^m instead (evalLocal :491-524, used by M2P for n < P).
-template <bool THETA, bool SINGULAR = false, typename F>
-__device__ __forceinline__ void regular_harmonics(int P, const Sph& s, double sign, F&& f) {
+struct NoColumnHook { __device__ __forceinline__ void operator()(int) const {} };
+
+// g(m) is called after the last term of column m (all n for that m): P2M flushes its transposition tile there.
+template <bool THETA, bool SINGULAR = false, typename F, typename G = NoColumnHook>
+__device__ __forceinline__ void regular_harmonics(int P, const Sph& s, double sign, F&& f, G&& g = G()) {
   const double step = SINGULAR ? 1.0 / s.r : s.r;
   double fact = 1, pn = 1, rhom = SINGULAR ? step : 1.0;
   double er = 1, ei = 0;
@@ -58,6 +61,7 @@ __device__ __forceinline__ void regular_harmonics(int P, const Sph& s, double si
       f(n, m, a * er, a * ei, at * er, at * ei);
       rhon *= step;
     }
+    g(m);
     pn = -pn * fact * s.y;
     fact += 2;
     double t = er * cp - ei * sp;
