@@ -120,6 +120,7 @@ struct Tree {
   int64_t own_b0 = 0, own_b1 = 0;
   std::vector<int64_t> body_cuts;    // nranks + 1 body offsets, identical on every rank
   DevBuf<int> own_leaves;            // leaf boxes inside the owned range, ascending
+  DevBuf<int> own_leaves_body;       // the same leaves in body order (consecutive leaves, consecutive body ranges)
   int n_own_leaves = 0;
   DevBuf<unsigned char> active;      // box intersects the owned range (is a target on this rank)
   // owned upward pass (used once a communicator exists): a box is "inside" a rank when all its bodies
@@ -293,6 +294,7 @@ struct fmmb_plan {
   int p2p_occ = 28;                  // resident one-warp blocks per SM the pair kernel is compiled for: 20 (96 registers,
                                      // no spill), 24, 28 (72 registers, 12 bytes of spill: fastest, 1.29 vs 1.35 ms at
                                      // N = 1M) or 32; same bits in every variant
+  int l2p_kernel = 1;                // 1 = four leaves per warp in body order (l2p_packed_kernel), 0 = one leaf per warp
   int p2m_kernel = 1;                // 1 = narrow transposition tile (p2m_cols_kernel), 0 = full tile (p2m_kernel)
   int p2p_newton = 0;                // 1 = Newton-only inverse root in the near-field pair kernel (p2p_kernel 3)
   int near_only = 0;                 // fmmb_options.near_only

@@ -383,6 +383,72 @@ l2p_kernel(const int* __restrict__ leaves, int nleaves, const unsigned* __restri
   }
 }
 
+// ---- L2P, leaves packed four to a warp -------------------------------------------------------------------------------
+// l2p_kernel gives a warp one leaf: with ~30 bodies per leaf and leaves of up to 64 bodies the second pass over a leaf
+// is mostly empty (22 of 32 lanes on average, ncu).  Here a warp takes kL2PLeaves consecutive leaves IN BODY ORDER --
+// their bodies are one contiguous stretch of the tree-ordered array -- stages all their local expansions and walks the
+// stretch 32 bodies at a time; a lane picks the expansion of the leaf its body lies in.  Same arithmetic per body.
+constexpr int kL2PLeaves = 4;
+__global__ void __launch_bounds__(128)
+l2p_packed_kernel(const int* __restrict__ leaves, int nleaves, const unsigned* __restrict__ bb,
+                  const unsigned* __restrict__ be, const double4* __restrict__ center,
+                  const unsigned char* __restrict__ has_local, const double4* __restrict__ body, int P,
+                  const double* __restrict__ L, double4* __restrict__ res) {
+  extern __shared__ double2 sh[];
+  __shared__ double4 s_cen[4][kL2PLeaves];
+  __shared__ unsigned s_end[4][kL2PLeaves];
+  __shared__ unsigned char s_has[4][kL2PLeaves];
+  const int nc = P * (P + 1) / 2;
+  const int wl = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int w = blockIdx.x * (blockDim.x >> 5) + wl;
+  const int l0 = w * kL2PLeaves;
+  if (l0 >= nleaves) return;
+  const int nl = min(kL2PLeaves, nleaves - l0);
+  double2* Ls = sh + (size_t)wl * kL2PLeaves * nc;
+  if (lane < kL2PLeaves) {
+    const int b = leaves[l0 + min(lane, nl - 1)];
+    s_cen[wl][lane] = center[b];
+    s_end[wl][lane] = lane < nl ? be[b] : 0xffffffffu;
+    s_has[wl][lane] = has_local[b];
+  }
+  for (int j = 0; j < nl; ++j) {
+    const int b = leaves[l0 + j];
+    if (!has_local[b]) continue;
+    for (int i = lane; i < nc; i += 32) {
+      int n, m;
+      unpack_nm(i, n, m);
+      Ls[j * nc + i] = load_coef(L + (size_t)b * xstride(P), n, m);
+    }
+  }
+  __syncwarp();
+  const unsigned begin = bb[leaves[l0]], end = be[leaves[l0 + nl - 1]];
+  const unsigned e0 = s_end[wl][0], e1 = s_end[wl][1], e2 = s_end[wl][2];
+  for (unsigned i = begin + lane; i < end; i += 32) {
+    const int j = (i >= e0) + (i >= e1) + (i >= e2);
+    if (!s_has[wl][j]) { res[i] = make_double4(0, 0, 0, 0); continue; }
+    const double4 c = s_cen[wl][j];
+    const double2* Lj = Ls + j * nc;
+    const double4 p = body[i];
+    const Sph s = to_sph(p.x - c.x, p.y - c.y, p.z - c.z);
+    double pot = 0, s0 = 0, s1 = 0, s2 = 0;
+    const double inv_r = 1.0 / s.r;
+    regular_harmonics<true>(P, s, 1.0, [&](int n, int m, double yr, double yi, double tr, double ti) {
+      const double2 l = Lj[n * (n + 1) / 2 + m];
+      const double w2 = m == 0 ? 1.0 : 2.0;
+      const double re = l.x * yr - l.y * yi;             // Re(L Y)
+      pot += w2 * re;
+      s0 += w2 * re * inv_r * n;
+      s1 += w2 * (l.x * tr - l.y * ti);            // Re(L Ytheta)
+      s2 -= w2 * (l.x * yi + l.y * yr) * m;        // Re(L Y i) m = -Im(L Y) m
+    });
+    const double inv_ry = inv_r / s.y;
+    const double fx = s.y * s.cp * s0 + s.x * s.cp * inv_r * s1 - s.sp * inv_ry * s2;
+    const double fy = s.y * s.sp * s0 + s.x * s.sp * inv_r * s1 + s.cp * inv_ry * s2;
+    const double fz = s.x * s0 - s.y * inv_r * s1;
+    res[i] = make_double4(pot, fx, fy, fz);
+  }
+}
+
 // ---- M2P (treecode, FMMOptions::TREECODE): warp per leaf, lane per body ---------------------------------------
 // Every accepted pair (source box, target box) of the traversal evaluates the source multipole at the bodies of
 // the target box (LaplaceSpherical.hpp:340-368 through EvalInteractionLazy.hpp:271-282).  A body receives from
@@ -1493,8 +1559,9 @@ void laplace_execute(fmmb_plan* plan, const double* d_charges, double* d_results
     FMMB_CUDA(cudaFuncSetAttribute(p2m_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024));
     const int* p2m_list = p2m_owned ? T.own_leaves.p : T.leaves.p;
     const int p2m_n = p2m_owned ? T.n_own_leaves : T.nleaves;
-    // narrow-tile kernel whenever the widest column (m = 1: 2 (P - 1) values; m = 0: P values) fits its tile
-    if (p2m_n && plan->p2m_kernel == 1 && 2 * (P - 1) <= kP2MCols && P <= kP2MCols)
+    // narrow-tile kernel for the orders where the full tile limits the occupancy (P >= 7: measured 0.222 -> 0.195 ms
+    // of upward phase at N = 1M, P = 8; at P = 5 the full tile is already small and the extra flushes cost 15 us)
+    if (p2m_n && plan->p2m_kernel == 1 && P >= 7 && 2 * (P - 1) <= kP2MCols)
       p2m_cols_kernel<<<nblk(p2m_n, 4), 128, 0, s>>>(p2m_list, p2m_n, T.bbegin.p, T.bend.p, T.center.p, T.body.p, P,
                                                      plan->M.p);
     else if (p2m_n)
@@ -1515,6 +1582,11 @@ void laplace_execute(fmmb_plan* plan, const double* d_charges, double* d_results
         m2p_kernel<<<nblk(T.n_own_leaves, 4), 128, 4 * nc * sizeof(double2), s>>>(
             T.own_leaves.p, T.n_own_leaves, T.bbegin.p, T.bend.p, T.parent.p, T.m2l_off.p, T.m2l_src.p, T.center.p,
             T.body.p, P, plan->M.p, plan->res_far.p);
+    } else if (T.n_own_leaves && plan->l2p_kernel == 1 && T.own_leaves_body.n == (size_t)T.n_own_leaves) {
+      const int nw = (T.n_own_leaves + kL2PLeaves - 1) / kL2PLeaves;
+      l2p_packed_kernel<<<nblk(nw, 4), 128, (size_t)4 * kL2PLeaves * nc * sizeof(double2), s>>>(
+          T.own_leaves_body.p, T.n_own_leaves, T.bbegin.p, T.bend.p, T.center.p, T.has_local.p, T.body.p, P, plan->L.p,
+          plan->res_far.p);
     } else if (T.n_own_leaves) {
       l2p_kernel<<<nblk(T.n_own_leaves, 4), 128, 4 * nc * sizeof(double2), s>>>(
           T.own_leaves.p, T.n_own_leaves, T.bbegin.p, T.bend.p, T.center.p, T.has_local.p, T.body.p, P, plan->L.p,
@@ -1571,6 +1643,14 @@ void build_p2p_items(fmmb_plan* plan) {
     p2p_close_kernel<<<nblk(T.nleaves, 4), 128, 0, s>>>(T.leaves.p, T.nleaves, T.bbegin.p, T.bend.p, T.p2p_off.p,
                                                        T.p2p_src.p, T.body.p, T.p2p_close.p);
     FMMB_CUDA(cudaGetLastError());
+    FMMB_CUDA(cudaStreamSynchronize(s));
+  }
+  if (T.own_leaves_body.n != (size_t)T.n_own_leaves && T.n_own_leaves > 0) {
+    // the rank's leaves in BODY order (consecutive entries own consecutive body ranges): l2p_packed_kernel
+    std::vector<int> lv = T.own_leaves.to_host(s);
+    std::vector<unsigned> hb = T.bbegin.to_host(s);
+    std::sort(lv.begin(), lv.end(), [&](int a, int b) { return hb[a] < hb[b]; });
+    T.own_leaves_body.from_host(lv.data(), lv.size(), s);
     FMMB_CUDA(cudaStreamSynchronize(s));
   }
   DevBuf<int> cnt;
