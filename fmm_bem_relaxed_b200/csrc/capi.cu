@@ -221,6 +221,12 @@ static void run_matvec(fmmb_plan* plan, const double* q, double* r) {
     else laplace_execute(plan, q, r);
   };
   if (!plan->use_graph || !plan->overlap_p2p) { direct(); return; }
+  // The expansion arrays are laid out for ONE order at a time (row stride, the all-zero row behind the last box);
+  // moving them to this call's order is host-driven work that a cached graph does not contain, so it happens here,
+  // ahead of a replay as much as ahead of plain launches (Yukawa keeps per-order strides of its own and no zero row)
+  if (plan->stokes) stokes_prepare_expansions(plan);
+  else if (plan->sbem) stokes_bem_prepare_expansions(plan);
+  else if (!plan->yukawa) laplace_prepare_expansions(plan);
   // a buffer that a cached graph points into was freed since the capture (a larger order came by): the graphs of
   // every order are stale.  They are rebuilt on the next two calls of their key.
   if (plan->graphs_valid_at != plan->realloc_count) {

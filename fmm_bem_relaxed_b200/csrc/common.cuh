@@ -354,6 +354,8 @@ void laplace_translations(fmmb_plan* plan, cudaStream_t s);
 void laplace_build_far(fmmb_plan* plan);
 bool laplace_owned_upward(const fmmb_plan* plan);
 void laplace_prepare_expansions(fmmb_plan* plan);
+void stokes_prepare_expansions(fmmb_plan* plan);
+void stokes_bem_prepare_expansions(fmmb_plan* plan);
 // bem.cu
 void bem_setup(fmmb_plan* plan, const double* verts_host, const int32_t* bc_host, int quad_k, double kappa = -1.0);
 void bem_begin(fmmb_plan* plan, const double* d_charges, cudaStream_t s);

@@ -419,6 +419,20 @@ void stokes_setup(fmmb_plan* plan, bool stresslet) {
   FMMB_CUDA(cudaStreamSynchronize(plan->stream));
 }
 
+// The four expansion sets at the plan's current order.  A change of order moves every row (and the all-zero row
+// nboxes that trans_blocked.cu reads for absent pairs), so the arrays are cleared then; run_matvec calls this before
+// it replays a cached graph as well -- a graph holds the launches of a matvec, not this clearing.
+void stokes_prepare_expansions(fmmb_plan* plan) {
+  StokesData* d = plan->stokes;
+  const int P = plan->p, xs = xstride(P);
+  for (int k = 0; k < 4; ++k) {
+    d->M4[k].resize((size_t)(plan->tree.nboxes + 1) * xs);
+    d->L4[k].resize((size_t)(plan->tree.nboxes + 1) * xs);
+    if (d->p_alloc != P) { d->M4[k].zero(plan->stream); d->L4[k].zero(plan->stream); }
+  }
+  d->p_alloc = P;
+}
+
 void stokes_execute(fmmb_plan* plan, const double* d_charges, double* d_results) {
   Tree& T = plan->tree;
   StokesData* d = plan->stokes;
@@ -427,12 +441,7 @@ void stokes_execute(fmmb_plan* plan, const double* d_charges, double* d_results)
   const int64_t n = T.n;
   cudaStream_t s = plan->stream, s2 = plan->overlap_p2p ? plan->stream2 : plan->stream;
   cudaEvent_t* ev = plan->ev;
-  for (int k = 0; k < 4; ++k) {
-    d->M4[k].resize((size_t)(T.nboxes + 1) * xs);      // + the all-zero expansion of trans_blocked.cu
-    d->L4[k].resize((size_t)(T.nboxes + 1) * xs);
-    if (d->p_alloc != P) { d->M4[k].zero(s); d->L4[k].zero(s); }   // padding double of odd-sized expansions
-  }
-  d->p_alloc = P;
+  stokes_prepare_expansions(plan);
   d->res_near.resize(3 * (size_t)n);
   d->res_far.resize(3 * (size_t)n);
   plan->launches = 0;

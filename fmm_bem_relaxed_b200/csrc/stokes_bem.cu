@@ -524,6 +524,18 @@ void stokes_bem_direct(fmmb_plan* plan, const double* d_charges, int64_t nt, con
   FMMB_CUDA(cudaStreamSynchronize(s));      // chg is released on return
 }
 
+// see stokes_prepare_expansions (stokes.cu)
+void stokes_bem_prepare_expansions(fmmb_plan* plan) {
+  StokesBemData* B = plan->sbem;
+  const int P = plan->p, xs = xstride(P);
+  for (int k = 0; k < 4; ++k) {
+    B->M4[k].resize((size_t)(plan->tree.nboxes + 1) * xs);
+    B->L4[k].resize((size_t)(plan->tree.nboxes + 1) * xs);
+    if (B->p_alloc != P) { B->M4[k].zero(plan->stream); B->L4[k].zero(plan->stream); }
+  }
+  B->p_alloc = P;
+}
+
 void stokes_bem_execute(fmmb_plan* plan, const double* d_charges, double* d_results) {
   Tree& T = plan->tree;
   StokesBemData* B = plan->sbem;
@@ -532,12 +544,7 @@ void stokes_bem_execute(fmmb_plan* plan, const double* d_charges, double* d_resu
   const int64_t n = T.n;
   cudaStream_t s = plan->stream;
   cudaEvent_t* ev = plan->ev;
-  for (int k = 0; k < 4; ++k) {
-    B->M4[k].resize((size_t)(T.nboxes + 1) * xs);      // + the all-zero expansion of trans_blocked.cu
-    B->L4[k].resize((size_t)(T.nboxes + 1) * xs);
-    if (B->p_alloc != P) { B->M4[k].zero(s); B->L4[k].zero(s); }   // padding double of odd-sized expansions
-  }
-  B->p_alloc = P;
+  stokes_bem_prepare_expansions(plan);
   B->res_near.resize(3 * (size_t)n);
   B->res_far.resize(3 * (size_t)n);
   plan->launches = 0;

@@ -324,6 +324,24 @@ def test_order_changes_do_not_replay_stale_graphs():
         assert_parity(plan.execute(q), ref[p])
 
 
+@pytest.mark.parametrize("mode,orders", [(3, (6, 6, 6, 8, 8, 8, 6, 6, 4, 4, 4, 8, 6)),
+                                         (0, (12, 12, 12, 16, 16, 16, 12, 12, 5, 5, 5, 12, 16))])
+def test_replayed_graphs_see_the_expansion_layout_of_their_order(mode, orders):
+    """The expansion arrays hold one order's layout at a time (row stride P^2, plus the all-zero row the fused sweep
+    reads for absent pairs), and re-laying them out is host-driven work outside the captured launches.  A relaxed
+    GMRES revisits orders, so a graph captured at order a is replayed after order b has overwritten the place of a's
+    zero row (found with config C2 under m2l_mode 3: the second solve of a plan took 26 iterations instead of 16).
+    Third and later calls of an order are replays; every result against the oracle."""
+    n = 8000
+    pts, q = O.drand48_inputs(n)
+    orc = O.Oracle(pts, 64, 0.5)
+    ref = {p: orc.execute(q, p, mode=0) for p in set(orders)}
+    plan = _plan_mode(pts, orders[0], mode, 64)
+    for p in orders:
+        plan.kernel().set_p(p)
+        assert_parity(plan.execute(q), ref[p])
+
+
 def test_blocked_batches_pass_their_host_side_audit(monkeypatch):
     """compute-sanitizer is closed on this GPU pool, so the plan-time structures of the fused sweep engine carry their
     own audit (FMMB_SELF_CHECK=1, csrc/trans_blocked.cu::check_blk_batch): every index the kernel dereferences is in
