@@ -157,6 +157,82 @@ bem_near_kernel(const int4* __restrict__ items, int nitems, const unsigned* __re
   if (act) res[it.y + lane] = a0 + a1;
 }
 
+// The same product with kNearSplit warps per work item (round 2).  One warp per item leaves ~11 warps per SM, each
+// with two loads in flight: 139 MB of config C2's cached entries took 221 us (0.6 TB/s).  Here the source leaves of
+// the item's list are dealt round-robin to the warps of a block (entry offsets from a warp scan of the leaf sizes),
+// every lane keeps eight independent loads in flight, and the warps' partial sums are added in warp order through
+// shared memory (fixed order: same bits on every run).
+constexpr int kNearSplit = 8;
+
+__global__ void __launch_bounds__(32 * kNearSplit)
+bem_near_split_kernel(const int4* __restrict__ items, int nitems, const unsigned* __restrict__ bb,
+                      const unsigned* __restrict__ be, const int* __restrict__ off, const int* __restrict__ src,
+                      const double4* __restrict__ body, const long long* __restrict__ base,
+                      const double* __restrict__ val, double* __restrict__ res) {
+  __shared__ double part[kNearSplit][32];
+  const int wl = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int item = blockIdx.x;
+  const int4 it = items[item];
+  const int cnt = it.z;
+  const bool act = lane < cnt;
+  const double* in = val + base[item] + (act ? lane : 0);
+  double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+  const int e0 = off[it.x], e1 = off[it.x + 1];
+  long long jbase = 0;
+  for (int ec = e0; ec < e1; ec += 32) {
+    // lane l: source leaf ec + l of the list -- first body, size, offset of its rows in the block
+    unsigned c0 = 0, ns_l = 0;
+    if (ec + lane < e1) {
+      const int sb = src[ec + lane];
+      c0 = bb[sb];
+      ns_l = be[sb] - c0;
+    }
+    unsigned incl = ns_l;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const unsigned t = __shfl_up_sync(0xffffffffu, incl, d);
+      if (lane >= d) incl += t;
+    }
+    const int nent = min(32, e1 - ec);
+    for (int l = wl; l < nent; l += kNearSplit) {
+      const unsigned b0 = __shfl_sync(0xffffffffu, c0, l);
+      const int ns = (int)__shfl_sync(0xffffffffu, ns_l, l);
+      const long long j0 = jbase + (long long)(__shfl_sync(0xffffffffu, incl, l) - (unsigned)ns);
+      for (int t0 = 0; t0 < ns; t0 += 32) {
+        const int nt = min(32, ns - t0);
+        const double q = lane < nt ? body[b0 + t0 + lane].w : 0.0;
+        const double* row = in + (j0 + t0) * cnt;
+        int k = 0;
+        for (; k + 8 <= nt; k += 8) {
+          double v[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) v[u] = act ? __ldg(row + (size_t)(k + u) * cnt) : 0.0;
+#pragma unroll
+          for (int u = 0; u < 8; u += 4) {
+            a0 = fma(v[u], __shfl_sync(0xffffffffu, q, k + u), a0);
+            a1 = fma(v[u + 1], __shfl_sync(0xffffffffu, q, k + u + 1), a1);
+            a2 = fma(v[u + 2], __shfl_sync(0xffffffffu, q, k + u + 2), a2);
+            a3 = fma(v[u + 3], __shfl_sync(0xffffffffu, q, k + u + 3), a3);
+          }
+        }
+        for (; k < nt; ++k) {
+          const double v = act ? __ldg(row + (size_t)k * cnt) : 0.0;
+          a0 = fma(v, __shfl_sync(0xffffffffu, q, k), a0);
+        }
+      }
+    }
+    jbase += __shfl_sync(0xffffffffu, incl, 31);
+  }
+  part[wl][lane] = (a0 + a1) + (a2 + a3);
+  __syncthreads();
+  if (wl == 0 && act) {
+    double t = part[0][lane];
+#pragma unroll
+    for (int w = 1; w < kNearSplit; ++w) t += part[w][lane];
+    res[it.y + lane] = t;
+  }
+}
+
 // P2M: warp per leaf; lane = (panel, quadrature point); rows go through a shared tile, then lane = coefficient
 template <int SET>
 __global__ void __launch_bounds__(128)
@@ -408,6 +484,19 @@ void bem_setup(fmmb_plan* plan, const double* verts_host, const int32_t* bc_host
   FMMB_CUDA(cudaStreamSynchronize(s));
 }
 
+static void launch_bem_near(fmmb_plan* plan, cudaStream_t s) {
+  Tree& T = plan->tree;
+  BemData* B = plan->bem;
+  const int ni = T.n_p2p_items;
+  if (plan->bem_near_kernel)
+    bem_near_split_kernel<<<ni, 32 * kNearSplit, 0, s>>>(T.p2p_items.p, ni, T.bbegin.p, T.bend.p, T.p2p_off.p,
+                                                        T.p2p_src.p, T.body.p, B->nf_base.p, B->nf_val.p, B->res_near.p);
+  else
+    bem_near_kernel<<<nblk(ni, kBemWarps), 32 * kBemWarps, 0, s>>>(T.p2p_items.p, ni, T.bbegin.p, T.bend.p, T.p2p_off.p,
+                                                                  T.p2p_src.p, T.body.p, B->nf_base.p, B->nf_val.p,
+                                                                  B->res_near.p);
+}
+
 // pieces of the BEM matvec shared with YukawaCartesianBEM (csrc/yukawa.cu): charges into tree order + cached near
 // field, and access to the panel data
 void bem_begin(fmmb_plan* plan, const double* d_charges, cudaStream_t s) {
@@ -418,9 +507,7 @@ void bem_begin(fmmb_plan* plan, const double* d_charges, cudaStream_t s) {
   bem_gather_charges<<<nblk(n, 256), 256, 0, s>>>(exec_charges(plan, d_charges), exec_perm(plan), n, T.body.p);
   const int ni = T.n_p2p_items;
   if (ni)
-    bem_near_kernel<<<nblk(ni, kBemWarps), 32 * kBemWarps, 0, s>>>(T.p2p_items.p, ni, T.bbegin.p, T.bend.p,
-                                                                  T.p2p_off.p, T.p2p_src.p, T.body.p,
-                                                                  B->nf_base.p, B->nf_val.p, B->res_near.p);
+    launch_bem_near(plan, s);
   B->res_far.zero(s);
   plan->launches += 3;
   FMMB_CUDA(cudaGetLastError());
@@ -461,9 +548,7 @@ void bem_execute(fmmb_plan* plan, const double* d_charges, double* d_results) {
   if (!plan->capturing) FMMB_CUDA(cudaEventRecord(ev[6], s));
   const int ni = T.n_p2p_items;
   if (ni)
-    bem_near_kernel<<<nblk(ni, kBemWarps), 32 * kBemWarps, 0, s>>>(T.p2p_items.p, ni, T.bbegin.p, T.bend.p,
-                                                                  T.p2p_off.p, T.p2p_src.p, T.body.p,
-                                                                  B->nf_base.p, B->nf_val.p, B->res_near.p);
+    launch_bem_near(plan, s);
   FMMB_CUDA(cudaEventRecord(ev[7], s));
   B->res_far.zero(s);
   plan->launches += 3;

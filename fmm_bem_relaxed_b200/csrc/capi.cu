@@ -452,13 +452,14 @@ int fmmb_plan_set_option(fmmb_plan* plan, const char* name, int64_t value) {
       plan->p2p_wps = (int)value;
     });
   }
-  if (!std::strcmp(name, "p2m_kernel") || !std::strcmp(name, "l2p_kernel")) {
-    const bool p2m = !std::strcmp(name, "p2m_kernel");
+  if (!std::strcmp(name, "p2m_kernel") || !std::strcmp(name, "l2p_kernel") || !std::strcmp(name, "bem_near_kernel")) {
+    int* which = !std::strcmp(name, "p2m_kernel") ? &plan->p2m_kernel
+                 : (!std::strcmp(name, "l2p_kernel") ? &plan->l2p_kernel : &plan->bem_near_kernel);
     return guarded([&] {
       FMMB_CUDA(cudaSetDevice(plan->device));
       FMMB_CUDA(cudaStreamSynchronize(plan->stream));
       drop_graphs(plan);
-      (p2m ? plan->p2m_kernel : plan->l2p_kernel) = value != 0;
+      *which = value != 0;
     });
   }
   if (!std::strcmp(name, "p2p_occ")) {

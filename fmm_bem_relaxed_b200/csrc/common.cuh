@@ -294,6 +294,7 @@ struct fmmb_plan {
   int p2p_occ = 28;                  // resident one-warp blocks per SM the pair kernel is compiled for: 20 (96 registers,
                                      // no spill), 24, 28 (72 registers, 12 bytes of spill: fastest, 1.29 vs 1.35 ms at
                                      // N = 1M) or 32; same bits in every variant
+  int bem_near_kernel = 1;           // cached BEM near field: 1 = eight warps per work item (bem_near_split_kernel), 0 = one
   int l2p_kernel = 1;                // 1 = four leaves per warp in body order (l2p_packed_kernel), 0 = one leaf per warp
   int p2m_kernel = 1;                // 1 = narrow transposition tile (p2m_cols_kernel), 0 = full tile (p2m_kernel)
   int p2p_newton = 0;                // 1 = Newton-only inverse root in the near-field pair kernel (p2p_kernel 3)

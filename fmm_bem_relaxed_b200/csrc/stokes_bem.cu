@@ -183,6 +183,94 @@ sbem_near_kernel(const int4* __restrict__ items, int nitems, const unsigned* __r
   }
 }
 
+// The same product with kSbemSplit warps per work item (round 2; see bem_near_split_kernel in csrc/bem.cu): the
+// source leaves of the list are dealt round-robin to the warps, entry offsets come from a warp scan of the leaf
+// sizes, four pairs (24 loads) are in flight per lane, partial sums are added in warp order (same bits every run).
+constexpr int kSbemSplit = 8;
+
+__global__ void __launch_bounds__(32 * kSbemSplit)
+sbem_near_split_kernel(const int4* __restrict__ items, int nitems, const unsigned* __restrict__ bb,
+                       const unsigned* __restrict__ be, const int* __restrict__ off, const int* __restrict__ src,
+                       const double* __restrict__ chg, const long long* __restrict__ base,
+                       const double* __restrict__ val, double* __restrict__ res) {
+  __shared__ double part[kSbemSplit][3][32];
+  const int wl = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int item = blockIdx.x;
+  const int4 it = items[item];
+  const int cnt = it.z;
+  const bool act = lane < cnt;
+  const double* in = val + kSbemEntries * base[item] + (act ? lane : 0);
+  const size_t cs = (size_t)cnt;
+  double u0 = 0, u1 = 0, u2 = 0;
+  const int e0 = off[it.x], e1 = off[it.x + 1];
+  long long jbase = 0;
+  for (int ec = e0; ec < e1; ec += 32) {
+    unsigned c0 = 0, ns_l = 0;
+    if (ec + lane < e1) {
+      const int sb = src[ec + lane];
+      c0 = bb[sb];
+      ns_l = be[sb] - c0;
+    }
+    unsigned incl = ns_l;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const unsigned t = __shfl_up_sync(0xffffffffu, incl, d);
+      if (lane >= d) incl += t;
+    }
+    const int nent = min(32, e1 - ec);
+    for (int l = wl; l < nent; l += kSbemSplit) {
+      const unsigned b0 = __shfl_sync(0xffffffffu, c0, l);
+      const int ns = (int)__shfl_sync(0xffffffffu, ns_l, l);
+      const long long j0 = jbase + (long long)(__shfl_sync(0xffffffffu, incl, l) - (unsigned)ns);
+      for (int t0 = 0; t0 < ns; t0 += 32) {
+        const int nt = min(32, ns - t0);
+        // lane k holds the three charge components of source t0 + k
+        double f0 = 0, f1 = 0, f2 = 0;
+        if (lane < nt) {
+          const double* c = chg + 3 * (size_t)(b0 + t0 + lane);
+          f0 = c[0]; f1 = c[1]; f2 = c[2];
+        }
+        const double* a = in + (size_t)(j0 + t0) * kSbemEntries * cs;
+        int k = 0;
+        for (; k + 4 <= nt; k += 4) {
+          double m[4][kSbemEntries];
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+#pragma unroll
+            for (int q = 0; q < kSbemEntries; ++q) m[u][q] = act ? __ldg(a + ((size_t)(k + u) * kSbemEntries + q) * cs) : 0.0;
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const double g0 = __shfl_sync(0xffffffffu, f0, k + u), g1 = __shfl_sync(0xffffffffu, f1, k + u),
+                         g2 = __shfl_sync(0xffffffffu, f2, k + u);
+            u0 = fma(m[u][0], g0, fma(m[u][1], g1, fma(m[u][2], g2, u0)));
+            u1 = fma(m[u][1], g0, fma(m[u][3], g1, fma(m[u][4], g2, u1)));
+            u2 = fma(m[u][2], g0, fma(m[u][4], g1, fma(m[u][5], g2, u2)));
+          }
+        }
+        for (; k < nt; ++k) {
+          double m[kSbemEntries];
+#pragma unroll
+          for (int q = 0; q < kSbemEntries; ++q) m[q] = act ? __ldg(a + ((size_t)k * kSbemEntries + q) * cs) : 0.0;
+          const double g0 = __shfl_sync(0xffffffffu, f0, k), g1 = __shfl_sync(0xffffffffu, f1, k),
+                       g2 = __shfl_sync(0xffffffffu, f2, k);
+          u0 = fma(m[0], g0, fma(m[1], g1, fma(m[2], g2, u0)));
+          u1 = fma(m[1], g0, fma(m[3], g1, fma(m[4], g2, u1)));
+          u2 = fma(m[2], g0, fma(m[4], g1, fma(m[5], g2, u2)));
+        }
+      }
+    }
+    jbase += __shfl_sync(0xffffffffu, incl, 31);
+  }
+  part[wl][0][lane] = u0; part[wl][1][lane] = u1; part[wl][2][lane] = u2;
+  __syncthreads();
+  if (wl < 3 && act) {                       // warp c sums component c
+    double t = part[0][wl][lane];
+#pragma unroll
+    for (int w = 1; w < kSbemSplit; ++w) t += part[w][wl][lane];
+    res[3 * (size_t)(it.y + lane) + wl] = t;
+  }
+}
+
 // charges (original order, 3 per panel) into tree order
 __global__ void sbem_gather(const double* __restrict__ q, const unsigned* __restrict__ perm, int64_t n,
                             double* __restrict__ chg) {
@@ -558,9 +646,13 @@ void stokes_bem_execute(fmmb_plan* plan, const double* d_charges, double* d_resu
   if (!plan->capturing) FMMB_CUDA(cudaEventRecord(ev[6], s));
   const int ni = T.n_p2p_items;
   if (ni) {
-    sbem_near_kernel<<<nblk(ni, kSbemWarps), 32 * kSbemWarps, 0, s>>>(T.p2p_items.p, ni, T.bbegin.p, T.bend.p,
-                                                                     T.p2p_off.p, T.p2p_src.p, B->chg.p, B->nf_base.p,
-                                                                     B->nf_val.p, B->res_near.p);
+    if (plan->bem_near_kernel)
+      sbem_near_split_kernel<<<ni, 32 * kSbemSplit, 0, s>>>(T.p2p_items.p, ni, T.bbegin.p, T.bend.p, T.p2p_off.p,
+                                                           T.p2p_src.p, B->chg.p, B->nf_base.p, B->nf_val.p, B->res_near.p);
+    else
+      sbem_near_kernel<<<nblk(ni, kSbemWarps), 32 * kSbemWarps, 0, s>>>(T.p2p_items.p, ni, T.bbegin.p, T.bend.p,
+                                                                       T.p2p_off.p, T.p2p_src.p, B->chg.p, B->nf_base.p,
+                                                                       B->nf_val.p, B->res_near.p);
     ++plan->launches;
   }
   FMMB_CUDA(cudaEventRecord(ev[7], s));

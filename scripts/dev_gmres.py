@@ -16,6 +16,8 @@ t0 = time.perf_counter()
 plan = F.FMM_plan(F.LaplaceSphericalBEM(8, 4), F.Panels(v, 0))
 t1 = time.perf_counter()
 b = F.FMM_plan(F.LaplaceSphericalBEM(8, 4), F.Panels(v, 1)).execute(np.ones(n))
+if "BEM_NEAR" in os.environ:
+    plan.set_option("bem_near_kernel", int(os.environ["BEM_NEAR"]))
 print("panels %d  plan build %.4fs" % (n, t1 - t0), flush=True)
 so = F.SolverOptions(residual=1e-6, max_iters=200, restart=200, max_p=8)
 for k in range(solves):
