@@ -41,6 +41,7 @@ class FMMOptions:
         self.NCRIT_ = 64
         self.printTree = False
         self.device = -1
+        self.cold_plan = False        # extension: FMMB_FLAG_COLD_PLAN (no warm start at construction)
 
     def set_mac_theta(self, theta):
         self.theta = float(theta)
@@ -258,6 +259,8 @@ class FMM_plan:
         src = capi.Sources(self._n, capi.ptr(pts), capi.ptr(verts), capi.ptr(bc))
         near_only = 2 if opts.block_diagonal else (1 if opts.local_evaluation else 0)
         flags = capi.FLAG_STOKES_BEM_AS_WRITTEN if getattr(kernel, "near_field_as_written", False) else 0
+        if getattr(opts, "cold_plan", False):
+            flags |= capi.FLAG_COLD_PLAN
         op = capi.Options(opts.theta, opts.NCRIT_, opts.evaluator, opts.device, int(getattr(opts, "m2l_mode", 0)),
                           getattr(opts, "rank", 0), getattr(opts, "nranks", 1), near_only, flags)
         h = ctypes.c_void_p()

@@ -20,6 +20,7 @@ STOKES_SPHERICAL_STRESSLET = 2
 STOKES_SPHERICAL = 5
 STOKES_SPHERICAL_BEM = 6
 FLAG_STOKES_BEM_AS_WRITTEN = 1
+FLAG_COLD_PLAN = 2       # fmmb.h: skip the warm start of fmmb_plan_create
 YUKAWA_CARTESIAN = 3
 YUKAWA_CARTESIAN_BEM = 4
 
@@ -75,7 +76,7 @@ EXPORTS = [
     "fmmb_plan_direct", "fmmb_plan_direct_panels", "fmmb_plan_set_option", "fmmb_plan_sync", "fmmb_comm_unique_id", "fmmb_plan_comm_init",
     "fmmb_partition_ranges", "fmmb_plan_stream", "fmmb_plan_get_info", "fmmb_plan_get_tree",
     "fmmb_plan_get_expansions", "fmmb_plan_phase_times", "fmmb_plan_destroy", "fmmb_last_error",
-    "fmmb_version", "fmmb_measure_fp64_peak",
+    "fmmb_version", "fmmb_measure_fp64_peak", "fmmb_init",
 ]
 
 _lib = None
@@ -118,6 +119,7 @@ def load():
     lib.fmmb_plan_destroy.restype = None
     lib.fmmb_last_error.restype = ctypes.c_char_p
     lib.fmmb_version.restype = ctypes.c_char_p
+    lib.fmmb_init.argtypes = [i32]
     lib.fmmb_measure_fp64_peak.argtypes = [i32, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]
     _lib = lib
     return lib

@@ -545,11 +545,14 @@ void bem_execute(fmmb_plan* plan, const double* d_charges, double* d_results) {
   if (!plan->capturing) FMMB_CUDA(cudaEventRecord(ev[0], s));
   bem_gather_charges<<<nblk(n, 256), 256, 0, s>>>(exec_charges(plan, d_charges), exec_perm(plan), n, T.body.p);
   FMMB_CUDA(cudaEventRecord(ev[1], s));
-  if (!plan->capturing) FMMB_CUDA(cudaEventRecord(ev[6], s));
+  // cached near field on the second stream, beside the far-field chain of short dependent kernels (round 2)
+  cudaStream_t s2 = plan->overlap_p2p ? plan->stream2 : s;
+  if (s2 != s) FMMB_CUDA(cudaStreamWaitEvent(s2, ev[1], 0));
+  if (!plan->capturing) FMMB_CUDA(cudaEventRecord(ev[6], s2));
   const int ni = T.n_p2p_items;
   if (ni)
-    launch_bem_near(plan, s);
-  FMMB_CUDA(cudaEventRecord(ev[7], s));
+    launch_bem_near(plan, s2);
+  FMMB_CUDA(cudaEventRecord(ev[7], s2));
   B->res_far.zero(s);
   plan->launches += 3;
   if (!plan->capturing) FMMB_CUDA(cudaEventRecord(ev[12], s));
@@ -595,6 +598,7 @@ void bem_execute(fmmb_plan* plan, const double* d_charges, double* d_results) {
     ++plan->launches;
   }
   if (!plan->capturing) FMMB_CUDA(cudaEventRecord(ev[4], s));
+  if (s2 != s) FMMB_CUDA(cudaStreamWaitEvent(s, ev[7], 0));
   finish_results(plan, B->res_near.p, B->res_far.p, 1, d_results, s);
   if (!plan->capturing) FMMB_CUDA(cudaEventRecord(ev[5], s));
   FMMB_CUDA(cudaGetLastError());

@@ -2,6 +2,7 @@
 // No torch, no C++ types across the boundary; every failure becomes a negative status plus a
 // thread-local message (the reference prints and exit()s instead: include/executor/P2M.hpp:13-17).
 #include "common.cuh"
+#include <chrono>
 #include <cstring>
 #include <algorithm>
 #include <new>
@@ -61,6 +62,8 @@ extern "C" {
 
 const char* fmmb_last_error(void) { return g_last_error.c_str(); }
 const char* fmmb_version(void) { return "fmmb200 0.1 sm_100a"; }
+
+static void warm_start(fmmb_plan* plan);   // after run_matvec
 
 int fmmb_plan_create(const fmmb_kernel_desc* kernel, const fmmb_sources* sources, const fmmb_options* options,
                      fmmb_plan** out_plan) {
@@ -136,7 +139,20 @@ int fmmb_plan_create(const fmmb_kernel_desc* kernel, const fmmb_sources* sources
         }
       pts = centres.data();
     }
+    // FMMB_PRINT_SETUP=1: host time of each construction step (stream synchronised) on stderr
+    const bool print_setup = std::getenv("FMMB_PRINT_SETUP") != nullptr;
+    auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    double t_step = now();
+    auto step_done = [&](const char* what) {
+      if (!print_setup) return;
+      cudaStreamSynchronize(plan->stream);
+      const double t = now();
+      fprintf(stderr, "fmmb setup: %-46s %9.3f ms\n", what, (t - t_step) * 1e3);
+      t_step = t;
+    };
+    step_done("streams, events, constant tables (+ CUDA context)");
     { NvtxRange r("fmmb: octree + dual traversal"); build_tree(plan, pts, sources->n); }
+    step_done("octree + dual traversal");
     plan->near_only = opts.near_only;
     if (opts.near_only == 2) restrict_p2p_to_self(plan);
     NvtxRange r_far("fmmb: translation classes / near-field items / kernel setup");
@@ -146,13 +162,20 @@ int fmmb_plan_create(const fmmb_kernel_desc* kernel, const fmmb_sources* sources
       if (is_yukawa) { build_m2l_classes(plan); plan->far_built_classes = true; }
       else laplace_build_far(plan);
     }
+    step_done("far-field structures (classes / blocks)");
     if (is_panel) plan->p2p_item_mode = 0;   // one cached near-field block per chunk of <= 32 targets
     build_p2p_items(plan);
+    step_done("near-field work items");
     if (is_bem) bem_setup(plan, sources->vertices, sources->bc, kernel->quad_k,
                           kernel->kind == FMMB_YUKAWA_CARTESIAN_BEM ? kernel->kappa : -1.0);
     if (is_stokes) stokes_setup(plan, kernel->kind == FMMB_STOKES_SPHERICAL_STRESSLET);
     if (is_sbem) stokes_bem_setup(plan, sources->vertices, sources->bc, kernel->quad_k, kernel->quad_kfine, kernel->kappa);
     if (is_yukawa) yukawa_setup(plan, kernel->kappa);
+    step_done("kernel class setup (panels, cached near field)");
+    if (!(opts.kernel_flags & FMMB_FLAG_COLD_PLAN) && plan->tree.nranks <= 1) {
+      warm_start(plan);
+      step_done("warm start (buffers, tables, launch graphs)");
+    }
   });
   if (rc != FMMB_OK) { fmmb_plan_destroy(plan); return rc; }
   *out_plan = plan;
@@ -276,6 +299,38 @@ namespace fmmb {
 void run_matvec_for_solver(fmmb_plan* plan, const double* q, double* r) { run_matvec(plan, q, r); }
 }
 }
+
+}  // extern "C"
+
+// Everything a first matvec would otherwise do on the caller's clock happens at construction: expansion and scratch
+// buffers, the translation tables of the order, the host staging buffers.  A panel plan is the operator of a relaxed
+// Krylov solve that walks down through the orders (GMRES.hpp:195-196), so for those every order 1..P is prepared on
+// the solver's work vectors and its launch graph captured; the solve then starts on replays.  Single-GPU plans only
+// (a sharded plan cannot run before its communicator exists).  FMMB_FLAG_COLD_PLAN skips all of it.
+static void warm_start(fmmb_plan* plan) {
+  const size_t n = (size_t)plan->tree.n;
+  cudaStream_t s = plan->stream;
+  plan->charges.resize(plan->charge_dim * n);
+  plan->results.resize(plan->result_dim * n);
+  plan->charges.zero(s);
+  fmmb::run_matvec_for_solver(plan, plan->charges.p, plan->results.p);
+  if ((plan->bem || plan->sbem) && !plan->near_only && plan->charge_dim == plan->result_dim) {
+    double *z = nullptr, *w = nullptr;
+    gmres_reserve(plan, &z, &w);
+    const int P = plan->p;
+    for (int p = P; p >= 1; --p) {
+      plan->p = p;
+      fmmb::run_matvec_for_solver(plan, z, w);      // buffers and tables of the order
+      fmmb::run_matvec_for_solver(plan, z, w);      // captured
+    }
+    plan->p = P;
+  }
+  FMMB_CUDA(cudaStreamSynchronize(s));
+  plan->timed = false;
+  plan->graph_timed = false;
+}
+
+extern "C" {
 
 int fmmb_gmres(fmmb_plan* plan, const double* b, double* x, const double* diag, const fmmb_solver_options* options,
                fmmb_gmres_info* info, int32_t* p_schedule, double* residuals, int32_t capacity) {
@@ -636,6 +691,24 @@ int fmmb_plan_phase_times(fmmb_plan* plan, double* ms, int count) {
   if (!plan || !ms) { set_error("null argument"); return FMMB_ERR_INVALID; }
   for (int i = 0; i < count && i < FMMB_T_COUNT; ++i) ms[i] = plan->phase_ms[i];
   return FMMB_OK;
+}
+
+int fmmb_init(int32_t device) {
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    set_error("no CUDA device: this engine has no CPU path");
+    return FMMB_ERR_NO_DEVICE;
+  }
+  return guarded([&] {
+    if (device >= 0) FMMB_CUDA(cudaSetDevice(device));
+    FMMB_CUDA(cudaFree(nullptr));          // context
+    fmmb_plan tmp;                         // constant tables: the first use of the module loads it
+    FMMB_CUDA(cudaGetDevice(&tmp.device));
+    laplace_init_tables(&tmp);
+    blocked_init_tables();
+    FMMB_CUDA(cudaDeviceSynchronize());
+  });
 }
 
 int fmmb_measure_fp64_peak(int device, double* tflops_dfma, double* tflops_dmma) {

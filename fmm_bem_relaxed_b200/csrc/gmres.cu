@@ -57,6 +57,48 @@ dot_kernel(const double* __restrict__ a, const double* __restrict__ b, int64_t n
     *counter = 0;
   }
 }
+// One modified Gram-Schmidt step in one launch: w -= (*coef) v_prev (skipped for v_prev == nullptr), then
+// out = <w, v_next> (v_next == nullptr: <w, w>).  Element for element the arithmetic of axpy_dev_kernel followed by
+// dot_kernel (same grid, same strides, same order of the partial sums), so the Hessenberg entries keep their bits.
+__global__ void __launch_bounds__(256)
+axpy_dot_kernel(const double* __restrict__ vprev, const double* __restrict__ coef, double* __restrict__ w,
+                const double* __restrict__ vnext, int64_t n, double* __restrict__ partial,
+                unsigned int* __restrict__ counter, double* __restrict__ out) {
+  __shared__ double sh[256];
+  __shared__ int last;
+  const double alpha = vprev ? -1.0 * *coef : 0.0;
+  double s = 0;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    double wi = w[i];
+    if (vprev) { wi = fma(alpha, vprev[i], wi); w[i] = wi; }
+    s += wi * (vnext ? vnext[i] : wi);
+  }
+  sh[threadIdx.x] = s;
+  __syncthreads();
+  for (int k = 128; k > 0; k >>= 1) {
+    if ((int)threadIdx.x < k) sh[threadIdx.x] += sh[threadIdx.x + k];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    partial[blockIdx.x] = sh[0];
+    __threadfence();
+    last = atomicAdd(counter, 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (last && threadIdx.x == 0) {
+    __threadfence();
+    double t = 0;
+    for (unsigned k = 0; k < gridDim.x; ++k) t += ((volatile double*)partial)[k];
+    *out = t;
+    *counter = 0;
+  }
+}
+// out = w / sqrt(*coef)
+__global__ void scale_into_kernel(const double* __restrict__ w, double* __restrict__ out, int64_t n,
+                                  const double* __restrict__ coef) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < n) out[i] = w[i] * (1.0 / sqrt(*coef));
+}
 // y += alpha x with alpha = sign * (*coef) read from device memory (sqrt / reciprocal variants for the norms)
 // mode 0: alpha = sign * coef;  1: y = y * (sign / sqrt(coef)) (x unused)
 __global__ void axpy_dev_kernel(const double* __restrict__ x, double* __restrict__ y, int64_t n,
@@ -100,6 +142,31 @@ inline void make_rotation(double dx, double dy, double& cs, double& sn) {
 }  // namespace
 
 void run_matvec_for_solver(fmmb_plan* plan, const double* q, double* r);   // capi.cu
+
+// Solver workspace of a plan ahead of its first solve (warm start of panel plans, capi.cu): the vectors a solve
+// feeds the matvec from (z) and reads it into (w) keep their addresses, so the launch graphs captured on them at
+// construction are the ones the solve replays.
+void gmres_reserve(fmmb_plan* plan, double** z_out, double** w_out) {
+  const int64_t n = plan->tree.n * plan->charge_dim;
+  if (!plan->gmres_ws) plan->gmres_ws = new GmresWorkspace();
+  GmresWorkspace& ws = *plan->gmres_ws;
+  ws.x.resize(n); ws.b.resize(n); ws.w.resize(n); ws.z.resize(n); ws.diag.resize(n);
+  ws.scal.resize(256 + 4);
+  ws.partial.resize(kDotBlocks);
+  ws.counter.resize(1);
+  if (ws.basis.n < (size_t)n * 24) ws.basis.resize((size_t)n * 24);
+  ws.z.zero(plan->stream);
+  // the solver's kernels are loaded with the module's first use of each: do that now
+  cudaFuncAttributes fa;
+  FMMB_CUDA(cudaFuncGetAttributes(&fa, dot_kernel));
+  FMMB_CUDA(cudaFuncGetAttributes(&fa, axpy_dot_kernel));
+  FMMB_CUDA(cudaFuncGetAttributes(&fa, scale_into_kernel));
+  FMMB_CUDA(cudaFuncGetAttributes(&fa, axpy_dev_kernel));
+  FMMB_CUDA(cudaFuncGetAttributes(&fa, axpy_kernel));
+  FMMB_CUDA(cudaFuncGetAttributes(&fa, precond_kernel));
+  *z_out = ws.z.p;
+  *w_out = ws.w.p;
+}
 
 void gmres_solve(fmmb_plan* plan, const double* b_host, double* x_host, const double* diag_host,
                  const fmmb_solver_options& o, fmmb_gmres_info* info, int32_t* p_sched, double* res_hist, int cap) {
@@ -179,18 +246,15 @@ void gmres_solve(fmmb_plan* plan, const double* b_host, double* x_host, const do
       plan->p = p;
       precond_kernel<<<g, 256, 0, s>>>(basis(i), diag_host ? diag.p : nullptr, z.p, n);
       run_matvec_for_solver(plan, z.p, w.p);
-      // modified Gram-Schmidt: coefficient k is produced and consumed on the device
-      for (int k = 0; k <= i; ++k) {
-        dot_to(w.p, basis(k), scal.p + k);
-        axpy_dev_kernel<<<g, 256, 0, s>>>(basis(k), w.p, n, scal.p + k, -1.0, 0);
-      }
-      dot_to(w.p, w.p, scal.p + R);
-      double* vnext = basis(i + 1);
-      FMMB_CUDA(cudaMemcpyAsync(vnext, w.p, n * sizeof(double), cudaMemcpyDeviceToDevice, s));
-      axpy_dev_kernel<<<g, 256, 0, s>>>(nullptr, vnext, n, scal.p + R, 1.0, 1);
+      // modified Gram-Schmidt: coefficient k is produced and consumed on the device; launch k subtracts the
+      // projection on V[k-1] and takes the product with V[k], the last one leaves |w|^2 behind the coefficients
+      double* vnext = basis(i + 1);             // (may grow the basis: before any pointer into it is used)
+      for (int k = 0; k <= i + 1; ++k)
+        axpy_dot_kernel<<<kDotBlocks, 256, 0, s>>>(k ? basis(k - 1) : nullptr, k ? scal.p + k - 1 : nullptr, w.p,
+                                                  k <= i ? basis(k) : nullptr, n, partial.p, counter.p, scal.p + k);
+      scale_into_kernel<<<g, 256, 0, s>>>(w.p, vnext, n, scal.p + i + 1);
       // the one synchronisation of the iteration: the new Hessenberg column
-      FMMB_CUDA(cudaMemcpyAsync(col.data(), scal.p, (i + 1) * sizeof(double), cudaMemcpyDeviceToHost, s));
-      FMMB_CUDA(cudaMemcpyAsync(col.data() + i + 1, scal.p + R, sizeof(double), cudaMemcpyDeviceToHost, s));
+      FMMB_CUDA(cudaMemcpyAsync(col.data(), scal.p, (i + 2) * sizeof(double), cudaMemcpyDeviceToHost, s));
       FMMB_CUDA(cudaStreamSynchronize(s));
       H.push_back(std::vector<double>(col.begin(), col.begin() + i + 2));
       H[i][i + 1] = std::sqrt(H[i][i + 1]);

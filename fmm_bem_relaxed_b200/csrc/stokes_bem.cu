@@ -642,20 +642,23 @@ void stokes_bem_execute(fmmb_plan* plan, const double* d_charges, double* d_resu
   ++plan->launches;
   FMMB_CUDA(cudaEventRecord(ev[1], s));
 
-  // cached near field (one pass over 48 bytes per pair)
-  if (!plan->capturing) FMMB_CUDA(cudaEventRecord(ev[6], s));
+  // cached near field (one pass over 48 bytes per pair) on the second stream, beside the far-field chain of short
+  // dependent kernels (round 2; joined before the results are combined)
+  cudaStream_t s2 = plan->overlap_p2p ? plan->stream2 : s;
+  if (s2 != s) FMMB_CUDA(cudaStreamWaitEvent(s2, ev[1], 0));
+  if (!plan->capturing) FMMB_CUDA(cudaEventRecord(ev[6], s2));
   const int ni = T.n_p2p_items;
   if (ni) {
     if (plan->bem_near_kernel)
-      sbem_near_split_kernel<<<ni, 32 * kSbemSplit, 0, s>>>(T.p2p_items.p, ni, T.bbegin.p, T.bend.p, T.p2p_off.p,
-                                                           T.p2p_src.p, B->chg.p, B->nf_base.p, B->nf_val.p, B->res_near.p);
+      sbem_near_split_kernel<<<ni, 32 * kSbemSplit, 0, s2>>>(T.p2p_items.p, ni, T.bbegin.p, T.bend.p, T.p2p_off.p,
+                                                            T.p2p_src.p, B->chg.p, B->nf_base.p, B->nf_val.p, B->res_near.p);
     else
-      sbem_near_kernel<<<nblk(ni, kSbemWarps), 32 * kSbemWarps, 0, s>>>(T.p2p_items.p, ni, T.bbegin.p, T.bend.p,
-                                                                       T.p2p_off.p, T.p2p_src.p, B->chg.p, B->nf_base.p,
-                                                                       B->nf_val.p, B->res_near.p);
+      sbem_near_kernel<<<nblk(ni, kSbemWarps), 32 * kSbemWarps, 0, s2>>>(T.p2p_items.p, ni, T.bbegin.p, T.bend.p,
+                                                                        T.p2p_off.p, T.p2p_src.p, B->chg.p, B->nf_base.p,
+                                                                        B->nf_val.p, B->res_near.p);
     ++plan->launches;
   }
-  FMMB_CUDA(cudaEventRecord(ev[7], s));
+  FMMB_CUDA(cudaEventRecord(ev[7], s2));
   B->res_far.zero(s);
   ++plan->launches;
 
@@ -695,6 +698,7 @@ void stokes_bem_execute(fmmb_plan* plan, const double* d_charges, double* d_resu
     ++plan->launches;
   }
   if (!plan->capturing) FMMB_CUDA(cudaEventRecord(ev[4], s));
+  if (s2 != s) FMMB_CUDA(cudaStreamWaitEvent(s, ev[7], 0));
   finish_results(plan, B->res_near.p, B->res_far.p, 3, d_results, s);
   if (!plan->capturing) FMMB_CUDA(cudaEventRecord(ev[5], s));
   FMMB_CUDA(cudaGetLastError());

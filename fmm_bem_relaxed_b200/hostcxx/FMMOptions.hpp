@@ -35,10 +35,11 @@ class FMMOptions {
   unsigned NCRIT_;
   bool printTree;
   int device;  // extension: CUDA device ordinal, -1 = current
+  bool cold_plan;  // extension: FMMB_FLAG_COLD_PLAN -- no warm start at construction (include/fmmb.h)
 
   FMMOptions()
       : lazy_evaluation(true), local_evaluation(false), sparse_local(false), block_diagonal(false),
-        evaluator(FMM), MAC_(DefaultMAC(0.5)), NCRIT_(64), printTree(false), device(-1) {}
+        evaluator(FMM), MAC_(DefaultMAC(0.5)), NCRIT_(64), printTree(false), device(-1), cold_plan(false) {}
 
   void set_mac_theta(double theta) { MAC_ = DefaultMAC(theta); }
   DefaultMAC MAC() { return MAC_; }

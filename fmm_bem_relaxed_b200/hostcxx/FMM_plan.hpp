@@ -48,7 +48,7 @@ class FMM_plan {
     fo.evaluator = opts_.evaluator == FMMOptions::FMM ? FMMB_EVAL_FMM : FMMB_EVAL_TREECODE;
     fo.device = opts_.device;
     fo.near_only = opts_.block_diagonal ? 2 : (opts_.local_evaluation ? 1 : 0);   // plans for preconditioners
-    fo.kernel_flags = K.kernel_flags();
+    fo.kernel_flags = K.kernel_flags() | (opts_.cold_plan ? FMMB_FLAG_COLD_PLAN : 0);
     if (fmmb_plan_create(&kd, &src, &fo, &plan_) != FMMB_OK) {
       std::cerr << "[E]: FMM_plan: " << fmmb_last_error() << "\n";
       plan_ = nullptr;

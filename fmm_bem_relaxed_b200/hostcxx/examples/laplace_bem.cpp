@@ -49,10 +49,18 @@ int main(int argc, char** argv) {
   if (second_kind) for (auto& it : panels) it.switch_BC();
   std::vector<charge_type> charges(panels.size(), 1.);
 
+  // Timing regions as in the reference's driver (examples/LaplaceBEM.cpp:209-235): the main plan is built before its
+  // clock starts, "setup" is the right-hand side (a temporary plan with flipped boundary conditions + one matvec),
+  // "solve" the Krylov solve.  Reported next to them: the CUDA context + module load of the process, and the main plan.
   double tic = get_time();
+  fmmb_init(opts.device);
+  double context_time = get_time() - tic;
+  tic = get_time();
   FMM_plan<kernel_type> plan(K, panels, opts);
+  double plan_time = get_time() - tic;
   std::vector<charge_type> x(panels.size(), 0.);
   std::vector<result_type> b;
+  tic = get_time();
   {
     for (auto& it : panels) it.switch_BC();
     FMM_plan<kernel_type> rhs_plan(K, panels, opts);
@@ -91,7 +99,8 @@ int main(int argc, char** argv) {
   solve_time = std::min(solve_time, get_time() - tic);
   }
 
-  printf("\nTIMING:\n\tsetup : %.4es\n\tsolve : %.4es\n", setup_time, solve_time);
+  printf("\nTIMING:\n\tcontext : %.4es\n\tplan : %.4es\n\tsetup : %.4es\n\tsolve : %.4es\n", context_time, plan_time,
+         setup_time, solve_time);
 
   double e = 0., e2 = 0.;
   for (auto xi : x) { e += (xi - 1.) * (xi - 1.); e2 += 1.; }

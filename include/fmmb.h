@@ -101,6 +101,12 @@ typedef struct {
  * an expression template that outlives its operand makes every pair take the K-point rule
  * (kernel/StokesSphericalBEM.hpp:162-163,262-263; fmm_bem_relaxed_b200/hostcxx/stokes_bem_math.hpp has the details). */
 #define FMMB_FLAG_STOKES_BEM_AS_WRITTEN 1
+/* Every kind: skip the warm start of fmmb_plan_create.  By default construction also does what a first matvec would
+ * otherwise do on the caller's clock -- expansion / scratch / staging buffers, the translation tables of the order,
+ * one matvec on zero charges -- and, for the panel kernel classes (the operators of the relaxed solvers, which walk
+ * down through the orders: reference examples/BEM/GMRES.hpp:195-196), prepares every order 1..p on the solver's
+ * work vectors with its launch graph captured.  Single-GPU plans only; sharded plans are always cold. */
+#define FMMB_FLAG_COLD_PLAN 2
 
 /* Sources, host memory, borrowed for the duration of the call.
  *   points    3*n doubles, point-major (x0,y0,z0,x1,...): the positions the octree is built on.
@@ -312,6 +318,11 @@ int fmmb_plan_phase_times(fmmb_plan* plan, double* ms, int count);
 void fmmb_plan_destroy(fmmb_plan* plan);
 
 const char* fmmb_last_error(void);
+
+/* Optional: create the CUDA context of `device` (-1 = current) and load this library's module now, so that a caller
+ * can keep that process-level cost (0.2 - 1 s on a fresh process) out of what it times as plan construction; the
+ * first fmmb_plan_create does the same implicitly.  FMMB_ERR_NO_DEVICE without a GPU. */
+int fmmb_init(int32_t device);
 
 /* Library build info: "fmmb200 <version> sm_100a". */
 const char* fmmb_version(void);

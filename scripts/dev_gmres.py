@@ -19,6 +19,18 @@ b = F.FMM_plan(F.LaplaceSphericalBEM(8, 4), F.Panels(v, 1)).execute(np.ones(n))
 if "BEM_NEAR" in os.environ:
     plan.set_option("bem_near_kernel", int(os.environ["BEM_NEAR"]))
 print("panels %d  plan build %.4fs" % (n, t1 - t0), flush=True)
+if os.environ.get("FIRST_USE"):
+    fresh = F.FMM_plan(F.LaplaceSphericalBEM(8, 4), F.Panels(v, 0))
+    xx = np.ones(n)
+    for p in (8, 6, 5, 4, 3, 2, 1):
+        fresh.kernel().set_p(p)
+        ts = []
+        for _ in range(4):
+            t0 = time.perf_counter()
+            fresh.execute(xx)
+            ts.append((time.perf_counter() - t0) * 1e3)
+        print("first use p=%d: call 1 %.3f ms (tables, buffers)  call 2 %.3f (capture)  call 3 %.3f  call 4 %.3f" % (p, *ts), flush=True)
+    fresh.close()
 so = F.SolverOptions(residual=1e-6, max_iters=200, restart=200, max_p=8)
 for k in range(solves):
     plan.kernel().set_p(8)

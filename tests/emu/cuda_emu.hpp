@@ -92,6 +92,7 @@ void launch_cfg(G grid, B block, size_t shmem, F&& body) { launch_cfg_impl(to_di
 #define cudaStreamWaitEvent(s, e, f) (cudaSuccess)
 #define cudaGetLastError() (cudaSuccess)
 #define cudaFuncSetAttribute(f, a, v) (cudaSuccess)
+#define cudaFuncGetAttributes(a, f) (cudaSuccess)
 
 #define threadIdx emu::threadIdx_
 #define blockIdx emu::blockIdx_
@@ -102,6 +103,9 @@ inline void __syncthreads() { emu::block_bar->arrive_and_wait(); }
 inline double __ddiv_rn(double a, double b) { return a / b; }
 inline double __shfl_sync(unsigned, double, int) { fprintf(stderr, "emu: warp shuffles are not emulated\n"); abort(); }
 inline double __shfl_xor_sync(unsigned, double, int) { fprintf(stderr, "emu: warp shuffles are not emulated\n"); abort(); }
+inline unsigned __shfl_sync(unsigned, unsigned, int) { fprintf(stderr, "emu: warp shuffles are not emulated\n"); abort(); }
+inline unsigned __shfl_up_sync(unsigned, unsigned, int) { fprintf(stderr, "emu: warp shuffles are not emulated\n"); abort(); }
+template <class T> inline T __ldg(const T* p) { return *p; }
 inline unsigned atomicAdd(unsigned* p, unsigned v) { unsigned o = *p; *p += v; return o; }   // blocks run one at a time and
 inline void __threadfence() {}                                                               // one thread per block calls it
 using std::min;

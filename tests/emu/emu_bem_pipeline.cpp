@@ -112,6 +112,7 @@ int main(int argc, char** argv) {
 
   upload_laplace_tables();
   fmmb_plan plan;
+  plan.bem_near_kernel = 0;   // the one-warp-per-item kernel: the split kernel's warp shuffles are not emulated
   plan.kind = FMMB_LAPLACE_SPHERICAL_BEM;
   plan.p = P;
   std::memset(&plan.opts, 0, sizeof plan.opts);

@@ -216,6 +216,7 @@ static int run_pipeline(const char* path, bool solve = false) {
 
   upload_laplace_tables();
   fmmb_plan plan;
+  plan.bem_near_kernel = 0;   // the one-warp-per-item kernel: the split kernel's warp shuffles are not emulated
   plan.kind = FMMB_STOKES_SPHERICAL_BEM;
   plan.p = P;
   std::memset(&plan.opts, 0, sizeof plan.opts);
