@@ -23,7 +23,7 @@ import numpy as np
 from . import capi
 from .capi import FmmbError
 
-__all__ = ["FMMOptions", "LaplaceSpherical", "LaplaceSphericalBEM", "StokesSpherical", "YukawaCartesian", "YukawaCartesianBEM", "StokesSphericalBEM", "SolverOptions", "GMRES", "Panels", "FMM_plan", "Direct", "FmmbError", "capi", "comm_unique_id",
+__all__ = ["FMMOptions", "LaplaceSpherical", "LaplaceSphericalBEM", "StokesSpherical", "YukawaCartesian", "YukawaCartesianBEM", "StokesSphericalBEM", "SolverOptions", "GMRES", "FGMRES", "Panels", "FMM_plan", "Direct", "FmmbError", "capi", "comm_unique_id",
            "partition_ranges", "get_options", "drand48_inputs"]
 
 
@@ -405,6 +405,29 @@ def GMRES(plan, x, b, opts, diag=None, output=False):
                                     capi.ptr(ps), capi.ptr(rs), cap))
     k = min(cap, info.n_records)
     plan.K.P = info.final_p           # like the reference, the kernel is left at the last relaxed order
+    return {"x": x, "iterations": info.iterations, "final_residual": info.final_residual,
+            "p_schedule": ps[:k].tolist(), "residuals": rs[:k].tolist()}
+
+
+def FGMRES(plan, x, b, opts, pc_plan=None, output=False):
+    """FGMRES(plan, x, b, solver_options[, M]) of reference examples/BEM/GMRES_Stokes.hpp:297-431, device resident
+    (fmmb_fgmres): flexible GMRES, order rule max(5, predict_p) (:375).  pc_plan: None (identity) or a near-field-only
+    plan over the same panels (FMMOptions.local_evaluation -> Preconditioners::LocalInnerSolver, .block_diagonal ->
+    Preconditioners::BlockDiagonal); the inner solves use those classes' options (LocalPC_Stokes.hpp:53-57)."""
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    b = np.ascontiguousarray(b, dtype=np.float64)
+    so = capi.SolverOptions(opts.residual, opts.max_iters, opts.restart, opts.max_p, int(opts.variable_p),
+                            opts.relax_type, int(output), 5, 0)
+    inner = capi.SolverOptions(1e-1, 1, 50, opts.max_p, 0, 0, 0, 0, 0)
+    info = capi.GmresInfo()
+    cap = 4096
+    ps = np.zeros(cap, np.int32)
+    rs = np.zeros(cap)
+    capi.check(plan._lib.fmmb_fgmres(plan._h, pc_plan._h if pc_plan is not None else None,
+                                     ctypes.byref(inner) if pc_plan is not None else None, capi.ptr(b), capi.ptr(x),
+                                     ctypes.byref(so), ctypes.byref(info), capi.ptr(ps), capi.ptr(rs), cap))
+    k = min(cap, info.n_records)
+    plan.K.P = info.final_p
     return {"x": x, "iterations": info.iterations, "final_residual": info.final_residual,
             "p_schedule": ps[:k].tolist(), "residuals": rs[:k].tolist()}
 

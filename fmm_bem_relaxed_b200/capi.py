@@ -76,7 +76,7 @@ EXPORTS = [
     "fmmb_plan_direct", "fmmb_plan_direct_panels", "fmmb_plan_set_option", "fmmb_plan_sync", "fmmb_comm_unique_id", "fmmb_plan_comm_init",
     "fmmb_partition_ranges", "fmmb_plan_stream", "fmmb_plan_get_info", "fmmb_plan_get_tree",
     "fmmb_plan_get_expansions", "fmmb_plan_phase_times", "fmmb_plan_destroy", "fmmb_last_error",
-    "fmmb_version", "fmmb_measure_fp64_peak", "fmmb_init",
+    "fmmb_version", "fmmb_measure_fp64_peak", "fmmb_init", "fmmb_fgmres",
 ]
 
 _lib = None
@@ -100,6 +100,8 @@ def load():
     lib.fmmb_plan_execute_sharded.argtypes = [vp, dp, dp]
     lib.fmmb_plan_execute_sharded_host.argtypes = [vp, dp, dp]
     lib.fmmb_gmres.argtypes = [vp, dp, dp, dp, ctypes.POINTER(SolverOptions), ctypes.POINTER(GmresInfo), dp, dp, i32]
+    lib.fmmb_fgmres.argtypes = [vp, vp, ctypes.POINTER(SolverOptions), dp, dp, ctypes.POINTER(SolverOptions),
+                                ctypes.POINTER(GmresInfo), dp, dp, i32]
     lib.fmmb_plan_peer_export.argtypes = [vp, dp]
     lib.fmmb_plan_peer_init.argtypes = [vp, dp]
     lib.fmmb_plan_direct.argtypes = [vp, dp, i64, dp, dp]

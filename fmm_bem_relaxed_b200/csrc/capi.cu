@@ -345,6 +345,23 @@ int fmmb_gmres(fmmb_plan* plan, const double* b, double* x, const double* diag, 
   });
 }
 
+int fmmb_fgmres(fmmb_plan* plan, fmmb_plan* pc_plan, const fmmb_solver_options* pc_options, const double* b, double* x,
+                const fmmb_solver_options* options, fmmb_gmres_info* info, int32_t* p_schedule, double* residuals,
+                int32_t capacity) {
+  if (!plan || !b || !x || !options) { set_error("null argument"); return FMMB_ERR_INVALID; }
+  for (const fmmb_solver_options* o : {options, pc_plan ? pc_options : options}) {
+    if (!o) { set_error("a preconditioner plan needs its solver options"); return FMMB_ERR_INVALID; }
+    if (o->max_p < 1 || o->max_p > FMMB_MAX_P || !(o->residual > 0) || o->restart < 1) {
+      set_error("solver options: residual > 0, restart >= 1, 1 <= max_p <= 16");
+      return FMMB_ERR_INVALID;
+    }
+  }
+  return guarded([&] {
+    FMMB_CUDA(cudaSetDevice(plan->device));
+    fgmres_solve(plan, pc_plan, pc_options, b, x, *options, info, p_schedule, residuals, capacity < 0 ? 0 : capacity);
+  });
+}
+
 int fmmb_plan_execute_device(fmmb_plan* plan, const double* charges_dev, double* results_dev) {
   if (!plan || !charges_dev || !results_dev) { set_error("null argument"); return FMMB_ERR_INVALID; }
   return guarded([&] {

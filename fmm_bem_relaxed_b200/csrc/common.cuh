@@ -382,6 +382,9 @@ void yukawa_direct_raw(double kappa, const double* d_spts, const double* d_q, in
                        int64_t nt, double* d_out, cudaStream_t s);
 // gmres.cu
 void gmres_free(GmresWorkspace* w);
+void fgmres_solve(fmmb_plan* plan, fmmb_plan* pc_plan, const fmmb_solver_options* pc_opts, const double* b_host,
+                  double* x_host, const fmmb_solver_options& o, fmmb_gmres_info* info, int32_t* p_sched,
+                  double* res_hist, int cap);
 void gmres_reserve(fmmb_plan* plan, double** z, double** w);   // solver workspace at plan construction (warm start)
 void gmres_solve(fmmb_plan* plan, const double* b_host, double* x_host, const double* diag_host,
                  const fmmb_solver_options& o, fmmb_gmres_info* info, int32_t* p_sched, double* res_hist, int cap);

@@ -19,7 +19,7 @@ namespace fmmb {
 // Solver workspace, kept on the plan between solves (a cudaMalloc / cudaFree pair per Krylov vector would cost more
 // than the BLAS-1 work of a whole solve at BEM sizes).
 struct GmresWorkspace {
-  DevBuf<double> x, b, w, z, diag, scal, partial, basis;   // basis: vectors back to back, grown geometrically
+  DevBuf<double> x, b, w, z, diag, scal, partial, basis, zbasis;   // (z)basis: vectors back to back, grown geometrically
   DevBuf<unsigned int> counter;
 };
 void gmres_free(GmresWorkspace* w) { delete w; }
@@ -27,6 +27,38 @@ void gmres_free(GmresWorkspace* w) { delete w; }
 namespace {
 
 constexpr int kDotBlocks = 32;
+
+// Thread sums -> block sum (tree in shared memory) -> partial[block]; the last block to arrive adds the partials in
+// index order (the result does not depend on which block is last).  The partials are fetched by as many threads in
+// parallel and summed from shared memory: one thread reading them one after the other from L2 cost ~10 us per dot
+// product, most of what a Gram-Schmidt step took at BEM sizes.
+__device__ __forceinline__ void block_dot_finish(double s, double* sh, int* last, double* __restrict__ partial,
+                                                 unsigned int* __restrict__ counter, double* __restrict__ out) {
+  sh[threadIdx.x] = s;
+  __syncthreads();
+  for (int w = 128; w > 0; w >>= 1) {
+    if ((int)threadIdx.x < w) sh[threadIdx.x] += sh[threadIdx.x + w];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    partial[blockIdx.x] = sh[0];
+    __threadfence();
+    *last = atomicAdd(counter, 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (*last) {                                   // block-uniform
+    if (threadIdx.x == 0) __threadfence();
+    __syncthreads();
+    if (threadIdx.x < gridDim.x) sh[threadIdx.x] = ((volatile double*)partial)[threadIdx.x];   // gridDim.x <= 256
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double t = 0;
+      for (unsigned k = 0; k < gridDim.x; ++k) t += sh[k];
+      *out = t;
+      *counter = 0;
+    }
+  }
+}
 
 // out[slot] = sum a[i] b[i]: block partial sums, the last block to finish adds them in index order
 // (deterministic: the result does not depend on which block is last)
@@ -37,25 +69,7 @@ dot_kernel(const double* __restrict__ a, const double* __restrict__ b, int64_t n
   __shared__ int last;
   double s = 0;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) s += a[i] * b[i];
-  sh[threadIdx.x] = s;
-  __syncthreads();
-  for (int w = 128; w > 0; w >>= 1) {
-    if ((int)threadIdx.x < w) sh[threadIdx.x] += sh[threadIdx.x + w];
-    __syncthreads();
-  }
-  if (threadIdx.x == 0) {
-    partial[blockIdx.x] = sh[0];
-    __threadfence();
-    last = atomicAdd(counter, 1u) == gridDim.x - 1;
-  }
-  __syncthreads();
-  if (last && threadIdx.x == 0) {
-    __threadfence();
-    double t = 0;
-    for (unsigned k = 0; k < gridDim.x; ++k) t += ((volatile double*)partial)[k];
-    *out = t;
-    *counter = 0;
-  }
+  block_dot_finish(s, sh, &last, partial, counter, out);
 }
 // One modified Gram-Schmidt step in one launch: w -= (*coef) v_prev (skipped for v_prev == nullptr), then
 // out = <w, v_next> (v_next == nullptr: <w, w>).  Element for element the arithmetic of axpy_dev_kernel followed by
@@ -73,25 +87,7 @@ axpy_dot_kernel(const double* __restrict__ vprev, const double* __restrict__ coe
     if (vprev) { wi = fma(alpha, vprev[i], wi); w[i] = wi; }
     s += wi * (vnext ? vnext[i] : wi);
   }
-  sh[threadIdx.x] = s;
-  __syncthreads();
-  for (int k = 128; k > 0; k >>= 1) {
-    if ((int)threadIdx.x < k) sh[threadIdx.x] += sh[threadIdx.x + k];
-    __syncthreads();
-  }
-  if (threadIdx.x == 0) {
-    partial[blockIdx.x] = sh[0];
-    __threadfence();
-    last = atomicAdd(counter, 1u) == gridDim.x - 1;
-  }
-  __syncthreads();
-  if (last && threadIdx.x == 0) {
-    __threadfence();
-    double t = 0;
-    for (unsigned k = 0; k < gridDim.x; ++k) t += ((volatile double*)partial)[k];
-    *out = t;
-    *counter = 0;
-  }
+  block_dot_finish(s, sh, &last, partial, counter, out);
 }
 // out = w / sqrt(*coef)
 __global__ void scale_into_kernel(const double* __restrict__ w, double* __restrict__ out, int64_t n,
@@ -168,24 +164,32 @@ void gmres_reserve(fmmb_plan* plan, double** z_out, double** w_out) {
   *w_out = ws.w.p;
 }
 
-void gmres_solve(fmmb_plan* plan, const double* b_host, double* x_host, const double* diag_host,
-                 const fmmb_solver_options& o, fmmb_gmres_info* info, int32_t* p_sched, double* res_hist, int cap) {
-  if (plan->charge_dim != plan->result_dim || !(plan->bem || plan->sbem))
-    throw StatusError{FMMB_ERR_UNSUPPORTED, "fmmb_gmres: BEM plans (results have the shape of the charges)"};
-  if (plan->tree.nranks > 1) throw StatusError{FMMB_ERR_UNSUPPORTED, "fmmb_gmres: single-GPU plans"};
-  // Vec<3> unknowns (StokesSphericalBEM) are solved on the flat array of 3 n doubles, like GMRES_Stokes.hpp:85-105
+// An inner near-field solve as preconditioner (Preconditioners::LocalInnerSolver / BlockDiagonal: examples/BEM/
+// LocalPC.hpp:26-59, LocalPC_Stokes.hpp:27-62, BlockDiagonalPC.hpp:16-60): z = GMRES(pc plan, rhs v, x0 = 0, opts).
+struct InnerPC {
+  fmmb_plan* plan;
+  fmmb_solver_options opts;
+};
+
+static GmresWorkspace& workspace(fmmb_plan* plan) {
+  if (!plan->gmres_ws) plan->gmres_ws = new GmresWorkspace();
+  return *plan->gmres_ws;
+}
+
+// The solver on device vectors x (initial guess in, solution out) and b of n doubles.  diag: device vector or nullptr.
+// flexible: the preconditioned vectors Z[j] are kept and the solution is updated from them (FGMRES of
+// GMRES_Stokes.hpp:319-431); otherwise the update applies the preconditioner to V[j] again (GMRES.hpp:234-239).
+static void gmres_core(fmmb_plan* plan, double* x, const double* b, const double* diag, const fmmb_solver_options& o,
+                       bool flexible, const InnerPC* pc, fmmb_gmres_info* info, int32_t* p_sched, double* res_hist,
+                       int cap) {
   const int64_t n = plan->tree.n * plan->charge_dim;
   const int R = std::max(1, o.restart);
   cudaStream_t s = plan->stream;
-  if (!plan->gmres_ws) plan->gmres_ws = new GmresWorkspace();
-  GmresWorkspace& ws = *plan->gmres_ws;
-  DevBuf<double>&x = ws.x, &b = ws.b, &w = ws.w, &z = ws.z, &diag = ws.diag, &scal = ws.scal, &partial = ws.partial;
+  GmresWorkspace& ws = workspace(plan);
+  DevBuf<double>&w = ws.w, &z = ws.z, &scal = ws.scal, &partial = ws.partial;
   DevBuf<unsigned int>& counter = ws.counter;
-  x.from_host(x_host, n, s);
-  b.from_host(b_host, n, s);
-  if (diag_host) diag.from_host(diag_host, n, s);
   w.resize(n); z.resize(n);
-  scal.resize(R + 4);                     // [0..R): Gram-Schmidt column, [R]: norm^2, [R+1]: scratch
+  scal.resize(R + 4);                     // [0..R]: Gram-Schmidt column + |w|^2, [R+1]: norms of b and of the residual
   partial.resize(kDotBlocks);
   counter.resize(1);
   counter.zero(s);
@@ -193,6 +197,10 @@ void gmres_solve(fmmb_plan* plan, const double* b_host, double* x_host, const do
   auto basis = [&](int k) -> double* {
     if (ws.basis.n < (size_t)n * (k + 1)) ws.basis.grow(std::max((size_t)n * (k + 1), 2 * ws.basis.n), s);   // keeps the vectors
     return ws.basis.p + (size_t)n * k;
+  };
+  auto zbasis = [&](int k) -> double* {
+    if (ws.zbasis.n < (size_t)n * (k + 1)) ws.zbasis.grow(std::max((size_t)n * (k + 1), std::max((size_t)n * 8, 2 * ws.zbasis.n)), s);
+    return ws.zbasis.p + (size_t)n * k;
   };
   const int g = nblk(n, 256);
   auto dot_to = [&](const double* a, const double* c, double* out) {
@@ -202,15 +210,32 @@ void gmres_solve(fmmb_plan* plan, const double* b_host, double* x_host, const do
     FMMB_CUDA(cudaMemcpyAsync(host, dev, count * sizeof(double), cudaMemcpyDeviceToHost, s));
     FMMB_CUDA(cudaStreamSynchronize(s));
   };
+  // zout = M(v)
+  auto apply_M = [&](const double* v, double* zout) {
+    if (pc) {
+      fmmb_plan* ip = pc->plan;
+      GmresWorkspace& iw = workspace(ip);
+      iw.x.resize(n); iw.b.resize(n);
+      FMMB_CUDA(cudaStreamSynchronize(s));                       // v is complete; the inner solve runs on its plan's stream
+      FMMB_CUDA(cudaMemcpyAsync(iw.b.p, v, n * sizeof(double), cudaMemcpyDeviceToDevice, ip->stream));
+      FMMB_CUDA(cudaMemsetAsync(iw.x.p, 0, n * sizeof(double), ip->stream));
+      gmres_core(ip, iw.x.p, iw.b.p, nullptr, pc->opts, false, nullptr, nullptr, nullptr, nullptr, 0);
+      FMMB_CUDA(cudaStreamSynchronize(ip->stream));
+      FMMB_CUDA(cudaMemcpyAsync(zout, iw.x.p, n * sizeof(double), cudaMemcpyDeviceToDevice, s));
+    } else {
+      precond_kernel<<<g, 256, 0, s>>>(v, diag, zout, n);
+    }
+  };
   double normb2 = 0;
-  dot_to(b.p, b.p, scal.p + R);
-  fetch(scal.p + R, &normb2, 1);
+  dot_to(b, b, scal.p + R + 1);
+  fetch(scal.p + R + 1, &normb2, 1);
   const double normb = std::sqrt(normb2);
   if (!(normb > 0)) {
     // b = 0 (or not finite): the reference divides by |b| and iterates on NaN residuals; the solution of A x = 0
     // by GMRES from any start is x = 0, which is what a caller gets here, with zero iterations
     if (normb == 0) {
-      std::memset(x_host, 0, (size_t)n * sizeof(double));
+      FMMB_CUDA(cudaMemsetAsync(x, 0, (size_t)n * sizeof(double), s));
+      FMMB_CUDA(cudaStreamSynchronize(s));
       if (info) { info->iterations = 0; info->n_records = 0; info->final_residual = 0.0; info->final_p = plan->p; }
       return;
     }
@@ -223,14 +248,14 @@ void gmres_solve(fmmb_plan* plan, const double* b_host, double* x_host, const do
   int i = -1, iter = 0, rec = 0;
   do {
     // w = A x - b at the order the kernel currently has; V[0] = -w / |w|
-    run_matvec_for_solver(plan, x.p, w.p);
-    axpy_kernel<<<g, 256, 0, s>>>(b.p, w.p, n, -1.0);
-    dot_to(w.p, w.p, scal.p + R);
+    run_matvec_for_solver(plan, x, w.p);
+    axpy_kernel<<<g, 256, 0, s>>>(b, w.p, n, -1.0);
+    dot_to(w.p, w.p, scal.p + R + 1);
     double beta2 = 0;
-    fetch(scal.p + R, &beta2, 1);
+    fetch(scal.p + R + 1, &beta2, 1);
     const double beta = std::sqrt(beta2);
     FMMB_CUDA(cudaMemcpyAsync(basis(0), w.p, n * sizeof(double), cudaMemcpyDeviceToDevice, s));
-    axpy_dev_kernel<<<g, 256, 0, s>>>(nullptr, basis(0), n, scal.p + R, -1.0, 1);
+    axpy_dev_kernel<<<g, 256, 0, s>>>(nullptr, basis(0), n, scal.p + R + 1, -1.0, 1);
     H.clear();
     std::fill(sv.begin(), sv.end(), 0.0);
     sv[0] = beta;
@@ -239,16 +264,17 @@ void gmres_solve(fmmb_plan* plan, const double* b_host, double* x_host, const do
     do {
       NvtxRange r_it("fmmb_gmres: iteration (predict_p, matvec, Gram-Schmidt, Givens)");
       ++i; ++iter;
-      // GMRES.hpp:195: max(1u, predict_p);  GMRES_Stokes.hpp:229: max(p_min, predict_p - 1)
+      // GMRES.hpp:195: max(1u, predict_p);  GMRES_Stokes.hpp:229: max(p_min, predict_p - 1);  :375 (FGMRES): max(5u, predict_p)
       const unsigned pp = predict_p(o, std::fabs(resid));
       const int p = (int)std::max(std::max(1u, o.p_min), pp > o.p_offset ? pp - o.p_offset : 0u);
       if (p > FMMB_MAX_P) throw StatusError{FMMB_ERR_INVALID, "predicted expansion order exceeds FMMB_MAX_P"};
       plan->p = p;
-      precond_kernel<<<g, 256, 0, s>>>(basis(i), diag_host ? diag.p : nullptr, z.p, n);
+      double* vnext = basis(i + 1);             // (may grow the basis: before any pointer into it is used)
+      apply_M(basis(i), z.p);
+      if (flexible) FMMB_CUDA(cudaMemcpyAsync(zbasis(i), z.p, n * sizeof(double), cudaMemcpyDeviceToDevice, s));
       run_matvec_for_solver(plan, z.p, w.p);
       // modified Gram-Schmidt: coefficient k is produced and consumed on the device; launch k subtracts the
       // projection on V[k-1] and takes the product with V[k], the last one leaves |w|^2 behind the coefficients
-      double* vnext = basis(i + 1);             // (may grow the basis: before any pointer into it is used)
       for (int k = 0; k <= i + 1; ++k)
         axpy_dot_kernel<<<kDotBlocks, 256, 0, s>>>(k ? basis(k - 1) : nullptr, k ? scal.p + k - 1 : nullptr, w.p,
                                                   k <= i ? basis(k) : nullptr, n, partial.p, counter.p, scal.p + k);
@@ -277,14 +303,17 @@ void gmres_solve(fmmb_plan* plan, const double* b_host, double* x_host, const do
       for (int k = j - 1; k >= 0; --k) sv[k] -= H[j][k] * sv[j];
     }
     for (int j = 0; j <= i; ++j) {
-      precond_kernel<<<g, 256, 0, s>>>(basis(j), diag_host ? diag.p : nullptr, z.p, n);
-      axpy_kernel<<<g, 256, 0, s>>>(z.p, x.p, n, sv[j]);
+      if (flexible) {
+        axpy_kernel<<<g, 256, 0, s>>>(zbasis(j), x, n, sv[j]);
+      } else {
+        apply_M(basis(j), z.p);
+        axpy_kernel<<<g, 256, 0, s>>>(z.p, x, n, sv[j]);
+      }
     }
     if (o.verbose && iter % 10 == 0) printf("it: %04d, residual: %.3e\n", iter, std::fabs(resid));
   } while (std::fabs(resid) > o.residual && iter < o.max_iters);
   if (o.verbose) printf("Final residual: %.4e, after %d iterations\n", std::fabs(resid), iter);
   FMMB_CUDA(cudaGetLastError());
-  FMMB_CUDA(cudaMemcpyAsync(x_host, x.p, n * sizeof(double), cudaMemcpyDeviceToHost, s));
   FMMB_CUDA(cudaStreamSynchronize(s));
   if (info) {
     info->iterations = iter;
@@ -292,6 +321,53 @@ void gmres_solve(fmmb_plan* plan, const double* b_host, double* x_host, const do
     info->final_residual = std::fabs(resid);
     info->final_p = plan->p;
   }
+}
+
+static void check_solver_plan(fmmb_plan* plan) {
+  if (plan->charge_dim != plan->result_dim || !(plan->bem || plan->sbem))
+    throw StatusError{FMMB_ERR_UNSUPPORTED, "fmmb_gmres: BEM plans (results have the shape of the charges)"};
+  if (plan->tree.nranks > 1) throw StatusError{FMMB_ERR_UNSUPPORTED, "fmmb_gmres: single-GPU plans"};
+}
+
+// fmmb_gmres: host vectors in and out.  Vec<3> unknowns (StokesSphericalBEM) are solved on the flat array of 3 n
+// doubles, like GMRES_Stokes.hpp:85-105.
+void gmres_solve(fmmb_plan* plan, const double* b_host, double* x_host, const double* diag_host,
+                 const fmmb_solver_options& o, fmmb_gmres_info* info, int32_t* p_sched, double* res_hist, int cap) {
+  check_solver_plan(plan);
+  const int64_t n = plan->tree.n * plan->charge_dim;
+  cudaStream_t s = plan->stream;
+  GmresWorkspace& ws = workspace(plan);
+  ws.x.from_host(x_host, n, s);
+  ws.b.from_host(b_host, n, s);
+  if (diag_host) ws.diag.from_host(diag_host, n, s);
+  gmres_core(plan, ws.x.p, ws.b.p, diag_host ? ws.diag.p : nullptr, o, false, nullptr, info, p_sched, res_hist, cap);
+  FMMB_CUDA(cudaMemcpyAsync(x_host, ws.x.p, n * sizeof(double), cudaMemcpyDeviceToHost, s));
+  FMMB_CUDA(cudaStreamSynchronize(s));
+}
+
+// fmmb_fgmres: flexible GMRES; pc_plan == nullptr: identity preconditioner, else an inner solve on pc_plan (a
+// near-field-only plan over the same panels) per outer iteration.
+void fgmres_solve(fmmb_plan* plan, fmmb_plan* pc_plan, const fmmb_solver_options* pc_opts, const double* b_host,
+                  double* x_host, const fmmb_solver_options& o, fmmb_gmres_info* info, int32_t* p_sched,
+                  double* res_hist, int cap) {
+  check_solver_plan(plan);
+  const int64_t n = plan->tree.n * plan->charge_dim;
+  InnerPC pc{pc_plan, fmmb_solver_options{}};
+  if (pc_plan) {
+    check_solver_plan(pc_plan);
+    if (pc_plan == plan || pc_plan->tree.n * pc_plan->charge_dim != n || pc_plan->device != plan->device)
+      throw StatusError{FMMB_ERR_INVALID, "fmmb_fgmres: the preconditioner plan must be another plan over the same panels on the same device"};
+    if (!pc_opts) throw StatusError{FMMB_ERR_INVALID, "fmmb_fgmres: a preconditioner plan needs its solver options"};
+    pc.opts = *pc_opts;
+    pc.opts.verbose = 0;
+  }
+  cudaStream_t s = plan->stream;
+  GmresWorkspace& ws = workspace(plan);
+  ws.x.from_host(x_host, n, s);
+  ws.b.from_host(b_host, n, s);
+  gmres_core(plan, ws.x.p, ws.b.p, nullptr, o, true, pc_plan ? &pc : nullptr, info, p_sched, res_hist, cap);
+  FMMB_CUDA(cudaMemcpyAsync(x_host, ws.x.p, n * sizeof(double), cudaMemcpyDeviceToHost, s));
+  FMMB_CUDA(cudaStreamSynchronize(s));
 }
 
 }  // namespace fmmb

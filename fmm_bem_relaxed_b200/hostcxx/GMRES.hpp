@@ -173,3 +173,35 @@ GMRESReport GMRES_device(Matvec& MV, std::vector<Vec<3, double>>& x, std::vector
   rep.residuals.assign(rs.begin(), rs.begin() + k);
   return rep;
 }
+
+/** FGMRES(plan, x, b, opts[, M]) of reference examples/BEM/GMRES_Stokes.hpp:297-431 on Vec<3> unknowns, device resident
+ * (fmmb_fgmres): flexible GMRES with that function's order rule p = max(5, predict_p(|resid|)) (:375).  `pc`: nullptr for
+ * the identity, or the near-field-only plan a Preconditioners::LocalInnerSolver / BlockDiagonal would own
+ * (FMMOptions::local_evaluation / block_diagonal); the inner solves then run with those classes' options
+ * (LocalPC_Stokes.hpp:53-57: residual 1e-1, max_iters 1, fixed order, restart 50), on the device as well. */
+template <typename Matvec>
+GMRESReport FGMRES_device(Matvec& MV, std::vector<Vec<3, double>>& x, std::vector<Vec<3, double>>& b,
+                          const SolverOptions& opts, Matvec* pc = nullptr, bool output = true) {
+  GMRESReport rep;
+  static_assert(sizeof(Vec<3, double>) == 3 * sizeof(double), "Vec<3,double> must be packed");
+  fmmb_solver_options so = {opts.residual, opts.max_iters, opts.restart, opts.max_p, opts.variable_p ? 1 : 0,
+                            opts.relax_type == SolverOptions::BOURAS ? 0 : 1, output ? 1 : 0, 5u, 0u};
+  fmmb_solver_options in = {1e-1, 1, 50, opts.max_p, 0, 0, 0, 0u, 0u};
+  fmmb_gmres_info info = {};
+  const int cap = 4096;
+  std::vector<int32_t> ps(cap);
+  std::vector<double> rs(cap);
+  if (x.size() != b.size() || fmmb_plan_set_p(MV.handle(), MV.kernel().order()) != FMMB_OK ||
+      fmmb_fgmres(MV.handle(), pc ? pc->handle() : nullptr, pc ? &in : nullptr, reinterpret_cast<const double*>(b.data()),
+                  reinterpret_cast<double*>(x.data()), &so, &info, ps.data(), rs.data(), cap) != FMMB_OK) {
+    fprintf(stderr, "[E]: FGMRES_device: %s\n", x.size() != b.size() ? "x.size() != b.size()" : fmmb_last_error());
+    return rep;
+  }
+  MV.kernel().set_p(info.final_p);
+  rep.iterations = info.iterations;
+  rep.final_residual = info.final_residual;
+  const int k = info.n_records < cap ? info.n_records : cap;
+  rep.p_schedule.assign(ps.begin(), ps.begin() + k);
+  rep.residuals.assign(rs.begin(), rs.begin() + k);
+  return rep;
+}

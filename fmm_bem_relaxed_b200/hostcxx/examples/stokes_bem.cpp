@@ -2,6 +2,8 @@
 // solved with the device-resident relaxed GMRES (fmmb_gmres through GMRES_device; the reference's own driver and its
 // GMRES_Stokes.hpp compile unchanged against these headers as bin/ref_StokesBEM).
 //   stokes_bem -recursions 5 -p 8 -k 4 -kfine 19 -mu 1e-3 -pmin 5 -solver_tol 1e-5 [-fixed_p] [-as_written] [-check N]
+//              [-fgmres [-local | -diagonal]]   the reference driver's flexible GMRES and its two inner-solve
+//              preconditioners (examples/StokesBEM.cpp:309-323), device resident (fmmb_fgmres)
 // First-kind equation for the traction t on the sphere moving with u = (1, 0, 0):  A t = b, b = (4 pi, 0, 0) on every
 // panel (the reference overwrites its computed right-hand side with exactly this, :262-266), x0 = 0; the drag
 // sum_j t_j[0] Area_j is compared with Stokes' law 6 pi mu.
@@ -12,13 +14,14 @@
 #include <GMRES.hpp>
 
 #include <algorithm>
+#include <memory>
 #include <cmath>
 #include <cstring>
 
 int main(int argc, char** argv) {
   int recursions = 5, p = 8, k = 4, kfine = 19, check = 0;
   double mu = 1e-3;
-  bool as_written = false;
+  bool as_written = false, fgmres = false, pc_local = false, pc_diagonal = false;
   FMMOptions opts = get_options(argc, argv);
   opts.sparse_local = true;
   SolverOptions so;
@@ -33,7 +36,11 @@ int main(int argc, char** argv) {
     else if (!strcmp(argv[i], "-fixed_p")) so.variable_p = false;
     else if (!strcmp(argv[i], "-as_written")) as_written = true;
     else if (!strcmp(argv[i], "-check")) check = atoi(argv[++i]);
+    else if (!strcmp(argv[i], "-fgmres")) fgmres = true;
+    else if (!strcmp(argv[i], "-local")) pc_local = true;
+    else if (!strcmp(argv[i], "-diagonal")) pc_diagonal = true;
   }
+  if (pc_local || pc_diagonal) fgmres = true;     // the reference's driver: -local / -diagonal select FGMRES (StokesBEM.cpp:170-186)
   so.max_p = p;
   so.max_iters = so.restart = 100;
   typedef StokesSphericalBEM kernel_type;
@@ -73,7 +80,26 @@ int main(int argc, char** argv) {
   std::vector<charge_type> x(n, charge_type(0., 0., 0.));
   tic = get_time();
   plan.kernel().set_p(p);
-  GMRESReport rep = GMRES_device(plan, x, b, so);
+  GMRESReport rep;
+  if (fgmres) {
+    // like the reference's driver, the preconditioner's plan is built inside the timed solve (StokesBEM.cpp:305-329)
+    std::unique_ptr<FMM_plan<kernel_type>> pc;
+    if (pc_local || pc_diagonal) {
+      FMMOptions po;                       // LocalPC_Stokes.hpp:8-18 / BlockDiagonalPC_Stokes.hpp local_options()
+      po.lazy_evaluation = false;
+      po.set_mac_theta(0.5);
+      po.sparse_local = true;
+      po.local_evaluation = pc_local && !pc_diagonal;
+      po.block_diagonal = pc_diagonal;
+      po.device = opts.device;
+      pc.reset(new FMM_plan<kernel_type>(K, panels, po));
+      if (!pc->handle()) return 1;
+    }
+    printf("Solver: FGMRES, Preconditioner: %s\n", pc_diagonal ? "Block-Diagonal" : (pc_local ? "Local Solve" : "Identity"));
+    rep = FGMRES_device(plan, x, b, so, pc.get());
+  } else {
+    rep = GMRES_device(plan, x, b, so);
+  }
   double solve = get_time() - tic;
   double fx = 0, fy = 0, fz = 0;
   for (size_t i = 0; i < n; ++i) { fx += x[i][0] * panels[i].Area; fy += x[i][1] * panels[i].Area; fz += x[i][2] * panels[i].Area; }

@@ -291,6 +291,17 @@ typedef struct {
 int fmmb_gmres(fmmb_plan* plan, const double* b, double* x, const double* diag, const fmmb_solver_options* options,
                fmmb_gmres_info* info, int32_t* p_schedule, double* residuals, int32_t capacity);
 
+/* Flexible GMRES, device resident (reference examples/BEM/GMRES_Stokes.hpp:319-431 FGMRES, driven by
+ * examples/StokesBEM.cpp:309-323): the preconditioned vectors Z[j] are kept and the solution is updated from them.
+ * pc_plan: NULL = identity, or a near-field-only plan over the same panels on the same device
+ * (fmmb_options.near_only 1 = Preconditioners::LocalInnerSolver, LocalPC_Stokes.hpp:27-62; 2 =
+ * Preconditioners::BlockDiagonal, BlockDiagonalPC_Stokes.hpp): every outer iteration solves pc_plan z = v from z = 0 by
+ * GMRES with pc_options (the reference's: residual 1e-1, max_iters 1, variable_p 0, restart 50), also on the device.
+ * The order rule of the outer iteration comes from options (FGMRES of GMRES_Stokes.hpp:375: p_min 5, p_offset 0). */
+int fmmb_fgmres(fmmb_plan* plan, fmmb_plan* pc_plan, const fmmb_solver_options* pc_options, const double* b, double* x,
+                const fmmb_solver_options* options, fmmb_gmres_info* info, int32_t* p_schedule, double* residuals,
+                int32_t capacity);
+
 int fmmb_plan_sync(fmmb_plan* plan);
 void* fmmb_plan_stream(fmmb_plan* plan); /* cudaStream_t */
 

@@ -307,6 +307,46 @@ def test_preconditioned_solves_match_the_reference(tmp_path):
         assert m and abs(float(m.group(1)) - rec["fx"]) <= 2e-5, (rec["args"], out[-800:])
 
 
+def test_device_resident_fgmres_and_inner_solves_match_the_reference(tmp_path):
+    """The same solves with everything on the GPU (fmmb_fgmres through hostcxx/examples/stokes_bem.cpp): flexible GMRES
+    with the order rule of GMRES_Stokes.hpp:375, and the two inner-solve preconditioners as GMRES solves on the
+    near-field-only plan, nested on the device.  Against the lines the reference prints on one CPU thread: same
+    iteration count, same order in every iteration, residuals to 2e-3."""
+    gold = json.load(open(os.path.join(GOLDEN, "precond_lines.json")))
+    for rec in gold["stokes"]:
+        out = _driver_lines("stokes_bem", rec["args"], tmp_path)
+        assert rec["solver_line"] in out, (rec["args"], out[-800:])
+        got = [(int(a), float(b), int(c)) for a, b, c in re.findall(r"it: (\d+), res: ([0-9.eE+-]+), fmm_req_p: (\d+)", out)]
+        want = [tuple(w) for w in rec["iterations"]]
+        assert len(got) == len(want), (rec["args"], got, want)
+        for (i, r, p), (wi, wr, wp) in zip(got, want):
+            assert (i, p) == (wi, wp) and abs(r - wr) <= 2e-3 * wr, (rec["args"], got, want)
+        m = re.search(r"Final residual: ([0-9.eE+-]+), after (\d+) iterations", out)
+        assert m and int(m.group(2)) == rec["n_iterations"], (rec["args"], out[-800:])
+        assert abs(float(m.group(1)) - rec["final_residual"]) <= 5e-3 * rec["final_residual"], (rec["args"], out[-800:])
+
+
+def test_python_fgmres_with_a_local_inner_solve():
+    """F.FGMRES (fmmb_fgmres through ctypes) with a local_evaluation plan as preconditioner converges to the solution
+    F.GMRES finds, and the identity-preconditioned call takes the iterations the golden -fgmres line records."""
+    verts = O.unit_sphere(4)
+    n = len(verts)
+    plan = make_plan(verts, 0, 8)
+    b = np.tile([4 * np.pi, 0.0, 0.0], (n, 1))
+    so = F.SolverOptions(residual=1e-5, max_iters=100, restart=100, max_p=8)
+    ref = F.GMRES(plan, np.zeros((n, 3)), b, so)
+    plan.kernel().set_p(8)
+    ident = F.FGMRES(plan, np.zeros((n, 3)), b, so)
+    gold = json.load(open(os.path.join(GOLDEN, "precond_lines.json")))["stokes"][0]
+    assert ident["iterations"] == gold["n_iterations"]
+    assert ident["p_schedule"][:len(gold["iterations"])] == [w[2] for w in gold["iterations"]]
+    pc = make_plan(verts, 0, 8, near_only=1)
+    plan.kernel().set_p(8)
+    loc = F.FGMRES(plan, np.zeros((n, 3)), b, so, pc_plan=pc)
+    assert loc["final_residual"] < 1e-5 and loc["iterations"] <= ident["iterations"]
+    assert O.rel_l2(loc["x"], ref["x"]) < 1e-3 and O.rel_l2(ident["x"], ref["x"]) < 1e-3
+
+
 def test_shipped_laplacebem_driver_compiles_its_preconditioned_branches_out(tmp_path):
     """examples/LaplaceBEM.cpp:285-317: the FGMRES / local-solve branches sit behind `#if 1 ... #else`, so the shipped
     driver solves NOTHING with -local or -fgmres (relative error 1).  The same source over the GPU plan does the same;
