@@ -223,11 +223,12 @@ def bench_stokes_bem():
     import tempfile
     args = ["-recursions", "6", "-p", "8", "-k", "4", "-solver_tol", "1e-5"]
 
-    def run(exe, env):
+    def run(exe, env, extra=()):
         if not os.path.exists(exe):
             return None
         with tempfile.TemporaryDirectory() as tmp:     # the drivers write out.face / out.vert / test.vert into cwd
-            out = subprocess.check_output([exe] + args, env=env, cwd=tmp, timeout=120, stderr=subprocess.STDOUT).decode()
+            out = subprocess.check_output([exe] + args + list(extra), env=env, cwd=tmp, timeout=120,
+                                          stderr=subprocess.STDOUT).decode()
         it = re.search(r"after (\d+) iterations|iterations: (\d+)", out)
         fx = re.search(r"Fx: ([0-9.eE+-]+), analytical: ([0-9.eE+-]+)", out)
         r = {"solve_s": float(re.search(r"solve : ([0-9.eE+-]+)s", out).group(1)),
@@ -257,6 +258,18 @@ def bench_stokes_bem():
         if ref is not None:
             out["reference"] = dict(ref, cores=threads, kind="reference",
                                     note="multi-threaded reference M2L has a data race (SURVEY F5): iteration count may differ")
+        # the reference's preconditioned solve (-local: FGMRES + an inner GMRES on a near-field-only plan per iteration,
+        # examples/StokesBEM.cpp:317-320); in every arm the preconditioner's plan is built inside the timed solve
+        pc = {}
+        for key, exe, e in (("device_resident_fgmres", os.path.join(bindir, "stokes_bem"), env),
+                            ("reference_driver_on_gpu_plan", os.path.join(bindir, "ref_StokesBEM"), env),
+                            ("reference", os.path.join(ROOT, "oracle", "_ref", "StokesBEM"),
+                             dict(os.environ, OMP_NUM_THREADS=str(threads)))):
+            r = run(exe, e, ("-local",))
+            if r is not None:
+                pc[key] = {k: r[k] for k in ("solve_s", "iterations", "drag_fx")}
+        if pc:
+            out["fgmres_local_preconditioner"] = pc
         return out
     except Exception as e:  # noqa: BLE001 -- an extra must not take the headline measurement down
         return {"error": "%s: %s" % (type(e).__name__, str(e)[-400:])}
