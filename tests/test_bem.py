@@ -105,6 +105,36 @@ def test_bem_matvec_vs_oracle(rec, P, K):
         assert plan.info().n_near_entries == plan.info().n_p2p_body_pairs
 
 
+def _two_scale_mesh():
+    """A sphere with a 20x smaller one just outside its surface: leaves of the coarse mesh see long lists of small
+    neighbour leaves (hundreds: the chunked list walk of the split near-field kernels).  With ncrit = 8 the tree is 8
+    levels deep, inside the 10 levels of the reference's 30-bit Morton codes."""
+    big = O.unit_sphere(4)
+    small = 0.05 * O.unit_sphere(5) + np.array([1.075, 0.0, 0.0])
+    return np.concatenate([big, small])
+
+
+@pytest.mark.gpu
+def test_cached_near_field_with_long_source_lists():
+    """bem_near_split_kernel (eight warps per work item, source leaves dealt round-robin, offsets from a warp scan)
+    against the one-warp-per-item kernel it replaced and against the oracle, on a two-scale mesh with ncrit = 8 where
+    target leaves have hundreds of source leaves; deterministic across calls."""
+    v = _two_scale_mesh()
+    n = len(v)
+    q = np.random.default_rng(11).random(n) - 0.4
+    opts = F.FMMOptions()
+    opts.set_max_per_box(8)
+    for bc in (0, 1):
+        plan = F.FMM_plan(F.LaplaceSphericalBEM(6, 4), F.Panels(v, bc), opts)
+        off = plan.tree()["p2p_off"]
+        assert np.diff(off).max() > 100
+        res = plan.execute(q)
+        assert np.array_equal(plan.execute(q), res) and np.array_equal(plan.execute(q), res)
+        plan.set_option("bem_near_kernel", 0)
+        assert O.rel_l2(res, plan.execute(q)) <= 1e-13
+        assert O.rel_l2(res, O.BemOracle(v, bc, ncrit=8).execute(q, 6, 4)) <= TOL
+
+
 @pytest.mark.gpu
 def test_bem_mixed_boundary_conditions_and_relaxation():
     v = O.unit_sphere(5)
