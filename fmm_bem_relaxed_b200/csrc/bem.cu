@@ -158,17 +158,21 @@ bem_near_kernel(const int4* __restrict__ items, int nitems, const unsigned* __re
 }
 
 // The same product with kNearSplit warps per work item (round 2).  One warp per item leaves ~11 warps per SM, each
-// with two loads in flight: 139 MB of config C2's cached entries took 221 us (0.6 TB/s).  Here the source leaves of
-// the item's list are dealt round-robin to the warps of a block (entry offsets from a warp scan of the leaf sizes),
-// every lane keeps eight independent loads in flight, and the warps' partial sums are added in warp order through
-// shared memory (fixed order: same bits on every run).
+// with two loads in flight: 139 MB of config C2's cached entries took 221 us (0.6 TB/s).  Here a block of eight
+// warps takes the item.  The list is walked 32 source leaves at a time (row offsets from a warp scan of the leaf
+// sizes); the charges of such a chunk are staged in shared memory and its rows are split EVENLY over the warps
+// (dealing whole leaves left the warps 2 or 3 leaves each: ncu showed 6.4 barrier stalls per issue), every lane
+// keeps eight independent loads in flight, and the warps' partial sums are added in warp order (fixed order: same
+// bits on every run).  A chunk with more rows than the staging buffer (huge ncrit) deals its leaves to the warps.
 constexpr int kNearSplit = 8;
+constexpr int kNearRows = 2048;
 
-__global__ void __launch_bounds__(32 * kNearSplit)
+__global__ void __launch_bounds__(32 * kNearSplit, 4)
 bem_near_split_kernel(const int4* __restrict__ items, int nitems, const unsigned* __restrict__ bb,
                       const unsigned* __restrict__ be, const int* __restrict__ off, const int* __restrict__ src,
                       const double4* __restrict__ body, const long long* __restrict__ base,
                       const double* __restrict__ val, double* __restrict__ res) {
+  __shared__ double qs[kNearRows];
   __shared__ double part[kNearSplit][32];
   const int wl = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int item = blockIdx.x;
@@ -194,34 +198,53 @@ bem_near_split_kernel(const int4* __restrict__ items, int nitems, const unsigned
       if (lane >= d) incl += t;
     }
     const int nent = min(32, e1 - ec);
-    for (int l = wl; l < nent; l += kNearSplit) {
-      const unsigned b0 = __shfl_sync(0xffffffffu, c0, l);
-      const int ns = (int)__shfl_sync(0xffffffffu, ns_l, l);
-      const long long j0 = jbase + (long long)(__shfl_sync(0xffffffffu, incl, l) - (unsigned)ns);
-      for (int t0 = 0; t0 < ns; t0 += 32) {
-        const int nt = min(32, ns - t0);
-        const double q = lane < nt ? body[b0 + t0 + lane].w : 0.0;
-        const double* row = in + (j0 + t0) * cnt;
-        int k = 0;
-        for (; k + 8 <= nt; k += 8) {
+    const unsigned total = __shfl_sync(0xffffffffu, incl, 31);
+    if (total <= (unsigned)kNearRows) {
+      // stage the chunk's charges (leaves dealt to the warps), then an even share of its rows per warp
+      for (int l = wl; l < nent; l += kNearSplit) {
+        const unsigned b0 = __shfl_sync(0xffffffffu, c0, l);
+        const unsigned ns = __shfl_sync(0xffffffffu, ns_l, l);
+        const unsigned r0 = __shfl_sync(0xffffffffu, incl, l) - ns;
+        for (unsigned t = lane; t < ns; t += 32) qs[r0 + t] = body[b0 + t].w;
+      }
+      __syncthreads();
+      const int ra = (int)((unsigned long long)total * wl / kNearSplit);
+      const int rb = (int)((unsigned long long)total * (wl + 1) / kNearSplit);
+      const double* row = in + (jbase + ra) * cnt;
+      int k = ra;
+      if (act) {
+        for (; k + 8 <= rb; k += 8, row += (size_t)8 * cnt) {
           double v[8];
 #pragma unroll
-          for (int u = 0; u < 8; ++u) v[u] = act ? __ldg(row + (size_t)(k + u) * cnt) : 0.0;
+          for (int u = 0; u < 8; ++u) v[u] = __ldg(row + (size_t)u * cnt);
 #pragma unroll
           for (int u = 0; u < 8; u += 4) {
-            a0 = fma(v[u], __shfl_sync(0xffffffffu, q, k + u), a0);
-            a1 = fma(v[u + 1], __shfl_sync(0xffffffffu, q, k + u + 1), a1);
-            a2 = fma(v[u + 2], __shfl_sync(0xffffffffu, q, k + u + 2), a2);
-            a3 = fma(v[u + 3], __shfl_sync(0xffffffffu, q, k + u + 3), a3);
+            a0 = fma(v[u], qs[k + u], a0);
+            a1 = fma(v[u + 1], qs[k + u + 1], a1);
+            a2 = fma(v[u + 2], qs[k + u + 2], a2);
+            a3 = fma(v[u + 3], qs[k + u + 3], a3);
           }
         }
-        for (; k < nt; ++k) {
-          const double v = act ? __ldg(row + (size_t)k * cnt) : 0.0;
-          a0 = fma(v, __shfl_sync(0xffffffffu, q, k), a0);
+        for (; k < rb; ++k, row += cnt) a0 = fma(__ldg(row), qs[k], a0);
+      }
+      __syncthreads();                       // qs is overwritten by the next chunk
+    } else {
+      for (int l = wl; l < nent; l += kNearSplit) {
+        const unsigned b0 = __shfl_sync(0xffffffffu, c0, l);
+        const int ns = (int)__shfl_sync(0xffffffffu, ns_l, l);
+        const long long j0 = jbase + (long long)(__shfl_sync(0xffffffffu, incl, l) - (unsigned)ns);
+        for (int t0 = 0; t0 < ns; t0 += 32) {
+          const int nt = min(32, ns - t0);
+          const double q = lane < nt ? body[b0 + t0 + lane].w : 0.0;
+          const double* row = in + (j0 + t0) * cnt;
+          for (int k = 0; k < nt; ++k) {
+            const double v = act ? __ldg(row + (size_t)k * cnt) : 0.0;
+            a0 = fma(v, __shfl_sync(0xffffffffu, q, k), a0);
+          }
         }
       }
     }
-    jbase += __shfl_sync(0xffffffffu, incl, 31);
+    jbase += total;
   }
   part[wl][lane] = (a0 + a1) + (a2 + a3);
   __syncthreads();

@@ -184,15 +184,29 @@ sbem_near_kernel(const int4* __restrict__ items, int nitems, const unsigned* __r
 }
 
 // The same product with kSbemSplit warps per work item (round 2; see bem_near_split_kernel in csrc/bem.cu): the
-// source leaves of the list are dealt round-robin to the warps, entry offsets come from a warp scan of the leaf
-// sizes, four pairs (24 loads) are in flight per lane, partial sums are added in warp order (same bits every run).
+// list is walked 32 source leaves at a time, row offsets from a warp scan of the leaf sizes; the charges of a chunk
+// are staged in shared memory and its pairs split evenly over the warps, four pairs (24 loads) in flight per lane;
+// partial sums are added in warp order (same bits every run).  A chunk with more pairs than the staging buffer deals
+// its leaves to the warps instead.
 constexpr int kSbemSplit = 8;
+constexpr int kSbemRows = 1024;
 
-__global__ void __launch_bounds__(32 * kSbemSplit)
+__device__ __forceinline__ void sbem_pair(const double* __restrict__ a, size_t cs, double g0, double g1, double g2,
+                                          double& u0, double& u1, double& u2) {
+  double m[kSbemEntries];
+#pragma unroll
+  for (int q = 0; q < kSbemEntries; ++q) m[q] = __ldg(a + q * cs);
+  u0 = fma(m[0], g0, fma(m[1], g1, fma(m[2], g2, u0)));
+  u1 = fma(m[1], g0, fma(m[3], g1, fma(m[4], g2, u1)));
+  u2 = fma(m[2], g0, fma(m[4], g1, fma(m[5], g2, u2)));
+}
+
+__global__ void __launch_bounds__(32 * kSbemSplit, 2)
 sbem_near_split_kernel(const int4* __restrict__ items, int nitems, const unsigned* __restrict__ bb,
                        const unsigned* __restrict__ be, const int* __restrict__ off, const int* __restrict__ src,
                        const double* __restrict__ chg, const long long* __restrict__ base,
                        const double* __restrict__ val, double* __restrict__ res) {
+  __shared__ double qs[3 * kSbemRows];
   __shared__ double part[kSbemSplit][3][32];
   const int wl = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int item = blockIdx.x;
@@ -218,48 +232,59 @@ sbem_near_split_kernel(const int4* __restrict__ items, int nitems, const unsigne
       if (lane >= d) incl += t;
     }
     const int nent = min(32, e1 - ec);
-    for (int l = wl; l < nent; l += kSbemSplit) {
-      const unsigned b0 = __shfl_sync(0xffffffffu, c0, l);
-      const int ns = (int)__shfl_sync(0xffffffffu, ns_l, l);
-      const long long j0 = jbase + (long long)(__shfl_sync(0xffffffffu, incl, l) - (unsigned)ns);
-      for (int t0 = 0; t0 < ns; t0 += 32) {
-        const int nt = min(32, ns - t0);
-        // lane k holds the three charge components of source t0 + k
-        double f0 = 0, f1 = 0, f2 = 0;
-        if (lane < nt) {
-          const double* c = chg + 3 * (size_t)(b0 + t0 + lane);
-          f0 = c[0]; f1 = c[1]; f2 = c[2];
-        }
-        const double* a = in + (size_t)(j0 + t0) * kSbemEntries * cs;
-        int k = 0;
-        for (; k + 4 <= nt; k += 4) {
+    const unsigned total = __shfl_sync(0xffffffffu, incl, 31);
+    if (total <= (unsigned)kSbemRows) {
+      for (int l = wl; l < nent; l += kSbemSplit) {
+        const unsigned b0 = __shfl_sync(0xffffffffu, c0, l);
+        const unsigned ns = __shfl_sync(0xffffffffu, ns_l, l);
+        const unsigned r0 = __shfl_sync(0xffffffffu, incl, l) - ns;
+        for (unsigned t = lane; t < 3 * ns; t += 32) qs[3 * r0 + t] = chg[3 * (size_t)b0 + t];   // contiguous
+      }
+      __syncthreads();
+      const int ra = (int)((unsigned long long)total * wl / kSbemSplit);
+      const int rb = (int)((unsigned long long)total * (wl + 1) / kSbemSplit);
+      if (act) {
+        const double* a = in + (size_t)(jbase + ra) * kSbemEntries * cs;
+        int k = ra;
+        for (; k + 4 <= rb; k += 4, a += 4 * kSbemEntries * cs) {
           double m[4][kSbemEntries];
 #pragma unroll
           for (int u = 0; u < 4; ++u)
 #pragma unroll
-            for (int q = 0; q < kSbemEntries; ++q) m[u][q] = act ? __ldg(a + ((size_t)(k + u) * kSbemEntries + q) * cs) : 0.0;
+            for (int q = 0; q < kSbemEntries; ++q) m[u][q] = __ldg(a + ((size_t)u * kSbemEntries + q) * cs);
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
-            const double g0 = __shfl_sync(0xffffffffu, f0, k + u), g1 = __shfl_sync(0xffffffffu, f1, k + u),
-                         g2 = __shfl_sync(0xffffffffu, f2, k + u);
+            const double g0 = qs[3 * (k + u)], g1 = qs[3 * (k + u) + 1], g2 = qs[3 * (k + u) + 2];
             u0 = fma(m[u][0], g0, fma(m[u][1], g1, fma(m[u][2], g2, u0)));
             u1 = fma(m[u][1], g0, fma(m[u][3], g1, fma(m[u][4], g2, u1)));
             u2 = fma(m[u][2], g0, fma(m[u][4], g1, fma(m[u][5], g2, u2)));
           }
         }
-        for (; k < nt; ++k) {
-          double m[kSbemEntries];
-#pragma unroll
-          for (int q = 0; q < kSbemEntries; ++q) m[q] = act ? __ldg(a + ((size_t)k * kSbemEntries + q) * cs) : 0.0;
-          const double g0 = __shfl_sync(0xffffffffu, f0, k), g1 = __shfl_sync(0xffffffffu, f1, k),
-                       g2 = __shfl_sync(0xffffffffu, f2, k);
-          u0 = fma(m[0], g0, fma(m[1], g1, fma(m[2], g2, u0)));
-          u1 = fma(m[1], g0, fma(m[3], g1, fma(m[4], g2, u1)));
-          u2 = fma(m[2], g0, fma(m[4], g1, fma(m[5], g2, u2)));
+        for (; k < rb; ++k, a += kSbemEntries * cs) sbem_pair(a, cs, qs[3 * k], qs[3 * k + 1], qs[3 * k + 2], u0, u1, u2);
+      }
+      __syncthreads();                       // qs is overwritten by the next chunk
+    } else {
+      for (int l = wl; l < nent; l += kSbemSplit) {
+        const unsigned b0 = __shfl_sync(0xffffffffu, c0, l);
+        const int ns = (int)__shfl_sync(0xffffffffu, ns_l, l);
+        const long long j0 = jbase + (long long)(__shfl_sync(0xffffffffu, incl, l) - (unsigned)ns);
+        for (int t0 = 0; t0 < ns; t0 += 32) {
+          const int nt = min(32, ns - t0);
+          double f0 = 0, f1 = 0, f2 = 0;       // lane k holds the three charge components of source t0 + k
+          if (lane < nt) {
+            const double* c = chg + 3 * (size_t)(b0 + t0 + lane);
+            f0 = c[0]; f1 = c[1]; f2 = c[2];
+          }
+          const double* a = in + (size_t)(j0 + t0) * kSbemEntries * cs;
+          for (int k = 0; k < nt; ++k, a += kSbemEntries * cs) {
+            const double g0 = __shfl_sync(0xffffffffu, f0, k), g1 = __shfl_sync(0xffffffffu, f1, k),
+                         g2 = __shfl_sync(0xffffffffu, f2, k);
+            if (act) sbem_pair(a, cs, g0, g1, g2, u0, u1, u2);
+          }
         }
       }
     }
-    jbase += __shfl_sync(0xffffffffu, incl, 31);
+    jbase += total;
   }
   part[wl][0][lane] = u0; part[wl][1][lane] = u1; part[wl][2][lane] = u2;
   __syncthreads();

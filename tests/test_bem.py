@@ -114,25 +114,38 @@ def _two_scale_mesh():
     return np.concatenate([big, small])
 
 
+def _largest_first_chunk_rows(tree):
+    """Rows (source panels) in the first 32 source boxes of a target box's near-field list, maximised over the boxes."""
+    off, idx, boxes = tree["p2p_off"], tree["p2p_idx"], tree["boxes"]
+    size = (boxes[:, 5] - boxes[:, 4]).astype(np.int64)
+    return max(int(size[idx[off[b]:min(off[b] + 32, off[b + 1])]].sum()) for b in range(len(off) - 1))
+
+
 @pytest.mark.gpu
-def test_cached_near_field_with_long_source_lists():
-    """bem_near_split_kernel (eight warps per work item, source leaves dealt round-robin, offsets from a warp scan)
-    against the one-warp-per-item kernel it replaced and against the oracle, on a two-scale mesh with ncrit = 8 where
-    target leaves have hundreds of source leaves; deterministic across calls."""
-    v = _two_scale_mesh()
+@pytest.mark.parametrize("case", ["long lists", "large leaves"])
+def test_cached_near_field_with_long_source_lists(case):
+    """bem_near_split_kernel (eight warps per work item; the list is walked 32 source leaves at a time, a chunk's
+    charges staged in shared memory and its rows split evenly over the warps) against the one-warp-per-item kernel it
+    replaced and against the oracle.  "long lists": two-scale mesh, ncrit = 8, target leaves with hundreds of source
+    leaves (several chunks).  "large leaves": ncrit = 250, chunks with more rows than the staging buffer (2 048), which
+    take the per-leaf path.  Deterministic across calls."""
+    v, ncrit = (_two_scale_mesh(), 8) if case == "long lists" else (O.unit_sphere(6), 250)
     n = len(v)
     q = np.random.default_rng(11).random(n) - 0.4
     opts = F.FMMOptions()
-    opts.set_max_per_box(8)
+    opts.set_max_per_box(ncrit)
     for bc in (0, 1):
         plan = F.FMM_plan(F.LaplaceSphericalBEM(6, 4), F.Panels(v, bc), opts)
-        off = plan.tree()["p2p_off"]
-        assert np.diff(off).max() > 100
+        t = plan.tree()
+        if case == "long lists":
+            assert np.diff(t["p2p_off"]).max() > 100
+        else:
+            assert _largest_first_chunk_rows(t) > 2048
         res = plan.execute(q)
         assert np.array_equal(plan.execute(q), res) and np.array_equal(plan.execute(q), res)
         plan.set_option("bem_near_kernel", 0)
         assert O.rel_l2(res, plan.execute(q)) <= 1e-13
-        assert O.rel_l2(res, O.BemOracle(v, bc, ncrit=8).execute(q, 6, 4)) <= TOL
+        assert O.rel_l2(res, O.BemOracle(v, bc, ncrit=ncrit).execute(q, 6, 4)) <= TOL
 
 
 @pytest.mark.gpu

@@ -73,19 +73,25 @@ def test_vs_oracle(as_written, rec, P, K, ncrit, bc):
     assert np.array_equal(t["perm"], ot["perm"]) and np.array_equal(t["lr"], ot["lr"])
 
 
-def test_cached_near_field_with_long_source_lists():
-    """sbem_near_split_kernel against the one-warp-per-item kernel and the oracle on a two-scale mesh (a sphere with a
-    20x smaller one just outside it, ncrit = 8): target leaves with hundreds of source leaves."""
-    verts = np.concatenate([O.unit_sphere(4), 0.05 * O.unit_sphere(5) + np.array([1.075, 0.0, 0.0])])
+@pytest.mark.parametrize("case", ["long lists", "large leaves"])
+def test_cached_near_field_with_long_source_lists(case):
+    """sbem_near_split_kernel against the one-warp-per-item kernel and the oracle.  "long lists": a sphere with a 20x
+    smaller one just outside it, ncrit = 8 -- target leaves with hundreds of source leaves (several 32-leaf chunks);
+    "large leaves": ncrit = 250 -- chunks with more pairs than the staging buffer (1 024), which take the per-leaf path."""
+    if case == "long lists":
+        verts, ncrit = np.concatenate([O.unit_sphere(4), 0.05 * O.unit_sphere(5) + np.array([1.075, 0.0, 0.0])]), 8
+    else:
+        verts, ncrit = O.unit_sphere(6), 250
     n = len(verts)
     q = np.random.default_rng(12).random((n, 3)) - 0.4
-    plan = make_plan(verts, 0, 6, ncrit=8)
-    assert np.diff(plan.tree()["p2p_off"]).max() > 100
+    plan = make_plan(verts, 0, 6, ncrit=ncrit)
+    if case == "long lists":
+        assert np.diff(plan.tree()["p2p_off"]).max() > 100
     res = plan.execute(q)
     assert np.array_equal(plan.execute(q), res)
     plan.set_option("bem_near_kernel", 0)
     assert O.rel_l2(res, plan.execute(q)) <= 1e-13
-    want = O.StokesBemOracle(verts, 0, ncrit=8).execute(q, 6)
+    want = O.StokesBemOracle(verts, 0, ncrit=ncrit).execute(q, 6)
     for k in range(3):
         assert O.rel_l2(res[:, k], want[:, k]) <= TOL
 
