@@ -91,7 +91,7 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.lines.append(line.strip())
 
-    def stop(self):
+    def stop(self, first=0):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -101,7 +101,7 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for l in self.lines:
+        for l in self.lines[first:]:
             f = [x.strip() for x in l.split(",")]
             if len(f) < 8:
                 continue
@@ -456,12 +456,16 @@ def bench_ours(args, rank, world, local_rank):
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(args.warmup):
-        step_device()
-    barrier()
+    # nvidia-smi needs ~0.1 s to start and then reports every 0.1 s, the timed region of the default run lasts less
+    # than that: the sampler starts ahead of the warm-up, and the same steps keep running (untimed) after the timed
+    # region until samples under this load have arrived; `clocks` is computed from the samples since the region began
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+    for _ in range(args.warmup):
+        step_device()
+    barrier()
+    first_sample = len(sampler.lines)
     starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     ends = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     phase_acc = {}
@@ -474,7 +478,21 @@ def bench_ours(args, rank, world, local_rank):
             ends[i].record(stream)
     barrier()
     ms = sum(s.elapsed_time(e) for s, e in zip(starts, ends))
-    clocks = sampler.stop() if rank == 0 else None
+    in_region = len(sampler.lines) - first_sample
+    tmax = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    # every rank runs the same number of extra steps (the sharded step exchanges data between the ranks): 0.5 s of load
+    extra = int(min(400, max(0, 500.0 / max(float(tmax.item()) / args.steps, 1e-3))))
+    for _ in range(extra):
+        with torch.cuda.stream(stream):
+            flush.zero_()
+        step_device()
+    barrier()
+    clocks = sampler.stop(first_sample) if rank == 0 else None
+    if clocks is not None:
+        clocks["samples_inside_timed_region"] = in_region
+        clocks["sampling"] = "nvidia-smi every 0.1 s from the start of the timed region through %d more untimed steps of the same load" % extra
     # per-kernel times for the roofline: a few extra steps with every kernel on ONE stream, so the
     # CUDA events around M2L / P2P are not disturbed by the concurrent near-field stream
     plan.set_option("overlap_p2p", 0)
