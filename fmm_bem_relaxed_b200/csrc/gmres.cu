@@ -21,6 +21,10 @@ namespace fmmb {
 struct GmresWorkspace {
   DevBuf<double> x, b, w, z, diag, scal, partial, basis, zbasis;   // (z)basis: vectors back to back, grown geometrically
   DevBuf<unsigned int> counter;
+  DevBuf<double> part2;               // mgs_sweep_kernel: two rows of partial sums
+  DevBuf<unsigned int> bar;           // its grid-barrier counter (never reset) and the value the host knows it has
+  unsigned int bar_count = 0;
+  bool mgs_cooperative = true;        // cleared when a cooperative launch is refused
 };
 void gmres_free(GmresWorkspace* w) { delete w; }
 
@@ -89,6 +93,72 @@ axpy_dot_kernel(const double* __restrict__ vprev, const double* __restrict__ coe
   }
   block_dot_finish(s, sh, &last, partial, counter, out);
 }
+// The whole modified Gram-Schmidt sweep of one iteration in ONE launch (cooperative: all kDotBlocks blocks are
+// resident): step k subtracts the projection on V[k-1] and takes the product with V[k] (k = nvec: |w|^2), the blocks
+// meet at a grid barrier, every block adds the partial sums in index order, and at the end V[nvec] = w / |w|.  Same
+// strides, same partial sums, same order as the chain of axpy_dot_kernel launches it replaces (same bits); what goes
+// away is a launch + drain per step (~4.5 us against a ~1.5 us barrier).
+//   bar:  arrival counter, never reset; the host passes the value it has before this launch (bar_base)
+//   part: two rows of kDotBlocks partial sums, used alternately (a block that is one barrier ahead writes the other row)
+// A barrier that does not complete within kGridBarrierTimeoutClocks writes NaN coefficients (the host turns that into an
+// error) instead of spinning forever.
+constexpr long long kGridBarrierTimeoutClocks = 6000000000ll;    // ~3 s of SM clock
+
+__global__ void __launch_bounds__(256)
+mgs_sweep_kernel(double* __restrict__ w, const double* __restrict__ basis, int nvec, int64_t n,
+                 double* __restrict__ vnext, double* __restrict__ part, unsigned int* __restrict__ bar,
+                 unsigned int bar_base, double* __restrict__ scal) {
+  __shared__ double sh[256];
+  __shared__ double h_sh;
+  __shared__ int dead;
+  if (threadIdx.x == 0) dead = 0;
+  const int64_t i0 = blockIdx.x * (int64_t)blockDim.x + threadIdx.x, stride = (int64_t)gridDim.x * blockDim.x;
+  double h_prev = 0.0;
+  for (int k = 0; k <= nvec; ++k) {
+    const double* vp = k ? basis + (size_t)n * (k - 1) : nullptr;
+    const double* vn = k < nvec ? basis + (size_t)n * k : nullptr;
+    const double alpha = -1.0 * h_prev;
+    double s = 0;
+    for (int64_t i = i0; i < n; i += stride) {
+      double wi = w[i];
+      if (vp) { wi = fma(alpha, vp[i], wi); w[i] = wi; }
+      s += wi * (vn ? vn[i] : wi);
+    }
+    sh[threadIdx.x] = s;
+    __syncthreads();
+    for (int t = 128; t > 0; t >>= 1) {
+      if ((int)threadIdx.x < t) sh[threadIdx.x] += sh[threadIdx.x + t];
+      __syncthreads();
+    }
+    double* row = part + (size_t)(k & 1) * gridDim.x;
+    if (threadIdx.x == 0) {
+      row[blockIdx.x] = sh[0];
+      __threadfence();
+      atomicAdd(bar, 1u);
+      const unsigned int target = bar_base + (unsigned)(k + 1) * gridDim.x;
+      const long long t0 = clock64();
+      while ((int)(*(volatile unsigned int*)bar - target) < 0) {
+        if (clock64() - t0 > kGridBarrierTimeoutClocks) { dead = 1; break; }
+      }
+      __threadfence();
+    }
+    __syncthreads();
+    if (threadIdx.x < gridDim.x) sh[threadIdx.x] = ((volatile double*)row)[threadIdx.x];   // gridDim.x <= 256
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double t = 0;
+      for (unsigned b = 0; b < gridDim.x; ++b) t += sh[b];
+      if (dead) t = __longlong_as_double(0x7ff8000000000000ll);
+      h_sh = t;
+      if (blockIdx.x == 0) scal[k] = t;
+    }
+    __syncthreads();
+    h_prev = h_sh;
+  }
+  const double inv = 1.0 / sqrt(h_prev);
+  for (int64_t i = i0; i < n; i += stride) vnext[i] = w[i] * inv;
+}
+
 // out = w / sqrt(*coef)
 __global__ void scale_into_kernel(const double* __restrict__ w, double* __restrict__ out, int64_t n,
                                   const double* __restrict__ coef) {
@@ -156,6 +226,9 @@ void gmres_reserve(fmmb_plan* plan, double** z_out, double** w_out) {
   cudaFuncAttributes fa;
   FMMB_CUDA(cudaFuncGetAttributes(&fa, dot_kernel));
   FMMB_CUDA(cudaFuncGetAttributes(&fa, axpy_dot_kernel));
+  FMMB_CUDA(cudaFuncGetAttributes(&fa, mgs_sweep_kernel));
+  if (ws.bar.n < 1) { ws.bar.resize(1); ws.bar.zero(plan->stream); ws.bar_count = 0; }
+  ws.part2.resize(2 * kDotBlocks);
   FMMB_CUDA(cudaFuncGetAttributes(&fa, scale_into_kernel));
   FMMB_CUDA(cudaFuncGetAttributes(&fa, axpy_dev_kernel));
   FMMB_CUDA(cudaFuncGetAttributes(&fa, axpy_kernel));
@@ -193,6 +266,8 @@ static void gmres_core(fmmb_plan* plan, double* x, const double* b, const double
   partial.resize(kDotBlocks);
   counter.resize(1);
   counter.zero(s);
+  if (ws.bar.n < 1) { ws.bar.resize(1); ws.bar.zero(s); ws.bar_count = 0; }
+  ws.part2.resize(2 * kDotBlocks);
   if (ws.basis.n < (size_t)n * 24) ws.basis.resize((size_t)n * 24);
   auto basis = [&](int k) -> double* {
     if (ws.basis.n < (size_t)n * (k + 1)) ws.basis.grow(std::max((size_t)n * (k + 1), 2 * ws.basis.n), s);   // keeps the vectors
@@ -275,13 +350,31 @@ static void gmres_core(fmmb_plan* plan, double* x, const double* b, const double
       run_matvec_for_solver(plan, z.p, w.p);
       // modified Gram-Schmidt: coefficient k is produced and consumed on the device; launch k subtracts the
       // projection on V[k-1] and takes the product with V[k], the last one leaves |w|^2 behind the coefficients
-      for (int k = 0; k <= i + 1; ++k)
-        axpy_dot_kernel<<<kDotBlocks, 256, 0, s>>>(k ? basis(k - 1) : nullptr, k ? scal.p + k - 1 : nullptr, w.p,
-                                                  k <= i ? basis(k) : nullptr, n, partial.p, counter.p, scal.p + k);
-      scale_into_kernel<<<g, 256, 0, s>>>(w.p, vnext, n, scal.p + i + 1);
+      bool swept = false;
+      if (ws.mgs_cooperative) {
+        double* w_p = w.p; const double* basis_p = ws.basis.p; int nvec = i + 1; int64_t nn = n;
+        double* part_p = ws.part2.p; unsigned int* bar_p = ws.bar.p; unsigned int base = ws.bar_count; double* scal_p = scal.p;
+        void* args[] = {&w_p, &basis_p, &nvec, &nn, &vnext, &part_p, &bar_p, &base, &scal_p};
+        const cudaError_t e = cudaLaunchCooperativeKernel((const void*)mgs_sweep_kernel, dim3(kDotBlocks), dim3(256), args, 0, s);
+        if (e == cudaSuccess) {
+          ws.bar_count += (unsigned)(nvec + 1) * kDotBlocks;
+          swept = true;
+        } else {
+          cudaGetLastError();                   // no cooperative launches here: the chain of launches below
+          ws.mgs_cooperative = false;
+        }
+      }
+      if (!swept) {
+        for (int k = 0; k <= i + 1; ++k)
+          axpy_dot_kernel<<<kDotBlocks, 256, 0, s>>>(k ? basis(k - 1) : nullptr, k ? scal.p + k - 1 : nullptr, w.p,
+                                                    k <= i ? basis(k) : nullptr, n, partial.p, counter.p, scal.p + k);
+        scale_into_kernel<<<g, 256, 0, s>>>(w.p, vnext, n, scal.p + i + 1);
+      }
       // the one synchronisation of the iteration: the new Hessenberg column
       FMMB_CUDA(cudaMemcpyAsync(col.data(), scal.p, (i + 2) * sizeof(double), cudaMemcpyDeviceToHost, s));
       FMMB_CUDA(cudaStreamSynchronize(s));
+      for (int k = 0; k < i + 2; ++k)
+        if (std::isnan(col[k])) throw StatusError{FMMB_ERR_CUDA, "fmmb_gmres: Gram-Schmidt coefficients are not numbers (grid barrier timed out, or the operator returned NaN)"};
       H.push_back(std::vector<double>(col.begin(), col.begin() + i + 2));
       H[i][i + 1] = std::sqrt(H[i][i + 1]);
       for (int k = 0; k < i; ++k) apply_rotation(H[i][k], H[i][k + 1], cs[k], sn[k]);

@@ -93,6 +93,7 @@ void launch_cfg(G grid, B block, size_t shmem, F&& body) { launch_cfg_impl(to_di
 #define cudaGetLastError() (cudaSuccess)
 #define cudaFuncSetAttribute(f, a, v) (cudaSuccess)
 #define cudaFuncGetAttributes(a, f) (cudaSuccess)
+#define cudaLaunchCooperativeKernel(f, g, b, a, sh, s) (cudaErrorNotSupported)   // grid barriers are not emulated
 
 #define threadIdx emu::threadIdx_
 #define blockIdx emu::blockIdx_
@@ -106,6 +107,8 @@ inline double __shfl_xor_sync(unsigned, double, int) { fprintf(stderr, "emu: war
 inline unsigned __shfl_sync(unsigned, unsigned, int) { fprintf(stderr, "emu: warp shuffles are not emulated\n"); abort(); }
 inline unsigned __shfl_up_sync(unsigned, unsigned, int) { fprintf(stderr, "emu: warp shuffles are not emulated\n"); abort(); }
 template <class T> inline T __ldg(const T* p) { return *p; }
+inline long long clock64() { return 0; }
+inline double __longlong_as_double(long long v) { double d; std::memcpy(&d, &v, sizeof d); return d; }
 inline unsigned atomicAdd(unsigned* p, unsigned v) { unsigned o = *p; *p += v; return o; }   // blocks run one at a time and
 inline void __threadfence() {}                                                               // one thread per block calls it
 using std::min;
