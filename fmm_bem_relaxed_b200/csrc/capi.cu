@@ -46,6 +46,10 @@ static void update_phase_times(fmmb_plan* plan) {
     if (cudaEventElapsedTime(&t, plan->ev[a], plan->ev[b]) != cudaSuccess) { cudaGetLastError(); return 0.0; }
     return (double)t;
   };
+  if (std::getenv("FMMB_PRINT_TIMELINE"))   // where the phases lie on the clock of the matvec (plain launches only)
+    std::fprintf(stderr, "timeline (ms after the first launch): far field %.3f | upward done %.3f | M2L GEMM %.3f .. %.3f | "
+                 "M2L done %.3f | downward done %.3f | near field %.3f .. %.3f | results %.3f\n", ms(0, 12), ms(0, 2),
+                 ms(0, 13), ms(0, 14), ms(0, 3), ms(0, 4), ms(0, 6), ms(0, 7), ms(0, 5));
   plan->phase_ms[FMMB_T_TOTAL] = ms(0, 5);
   plan->phase_ms[FMMB_T_UPWARD] = ms(12, 2);
   plan->phase_ms[FMMB_T_M2L] = ms(2, 3);
@@ -275,8 +279,27 @@ static void run_matvec(fmmb_plan* plan, const double* q, double* r) {
       direct();
       return;
     }
+    if (e == cudaSuccess && g && std::getenv("FMMB_PRINT_GRAPH")) {
+      size_t nn = 0;
+      cudaGraphGetNodes(g, nullptr, &nn);
+      std::vector<cudaGraphNode_t> nodes(nn);
+      cudaGraphGetNodes(g, nodes.data(), &nn);
+      for (size_t i = 0; i < nn; ++i) {
+        cudaGraphNodeType ty;
+        cudaGraphNodeGetType(nodes[i], &ty);
+        if (ty != cudaGraphNodeTypeKernel) { std::fprintf(stderr, "node %zu type %d\n", i, (int)ty); continue; }
+        cudaLaunchAttributeValue v{};
+        cudaError_t ge = cudaGraphKernelNodeGetAttribute(nodes[i], cudaLaunchAttributePriority, &v);
+        cudaKernelNodeParams kp{};
+        cudaGraphKernelNodeGetParams(nodes[i], &kp);
+        std::fprintf(stderr, "node %zu kernel grid %u block %u priority %d (%s)\n", i, kp.gridDim.x, kp.blockDim.x,
+                     v.priority, cudaGetErrorName(ge));
+      }
+    }
     cudaGraphExec_t ex = nullptr;
-    if (e == cudaSuccess && g) e = cudaGraphInstantiate(&ex, g, 0);
+    // per-node priorities: the far-field chain was captured from the high-priority stream, the near field from the
+    // other one; without the flag every node runs at the priority of the launching stream
+    if (e == cudaSuccess && g) e = cudaGraphInstantiate(&ex, g, plan->graph_node_priority ? cudaGraphInstantiateFlagUseNodePriority : 0);
     if (g) cudaGraphDestroy(g);
     if (e != cudaSuccess || !ex) {          // graphs are an optimisation: fall back to plain launches
       cudaGetLastError();
@@ -502,6 +525,14 @@ int fmmb_plan_set_option(fmmb_plan* plan, const char* name, int64_t value) {
     });
   }
   if (!std::strcmp(name, "use_graph")) { plan->use_graph = value != 0; return FMMB_OK; }
+  if (!std::strcmp(name, "graph_node_priority")) {
+    return guarded([&] {
+      FMMB_CUDA(cudaSetDevice(plan->device));
+      FMMB_CUDA(cudaStreamSynchronize(plan->stream));
+      drop_graphs(plan);
+      plan->graph_node_priority = value != 0;
+    });
+  }
   if (!std::strcmp(name, "p2p_kernel") || !std::strcmp(name, "p2p_unroll")) {
     const bool kern = !std::strcmp(name, "p2p_kernel");
     if (kern ? (value < 0 || value > 3) : (value != 4 && value != 8)) {
@@ -540,6 +571,20 @@ int fmmb_plan_set_option(fmmb_plan* plan, const char* name, int64_t value) {
       FMMB_CUDA(cudaStreamSynchronize(plan->stream));
       drop_graphs(plan);
       plan->p2p_occ = (int)value;
+    });
+  }
+  if (!std::strcmp(name, "p2p_order") || !std::strcmp(name, "m2l_reduce") || !std::strcmp(name, "m2l_reduce_bps")) {
+    const bool bps = !std::strcmp(name, "m2l_reduce_bps");
+    int* which = !std::strcmp(name, "p2p_order") ? &plan->p2p_order : (bps ? &plan->m2l_reduce_bps : &plan->m2l_reduce);
+    if (bps ? (value < 1 || value > 3) : (value != 0 && value != 1)) {
+      set_error("p2p_order / m2l_reduce: 0 or 1; m2l_reduce_bps: 1..3 blocks per SM");
+      return FMMB_ERR_INVALID;
+    }
+    return guarded([&] {
+      FMMB_CUDA(cudaSetDevice(plan->device));
+      FMMB_CUDA(cudaStreamSynchronize(plan->stream));
+      drop_graphs(plan);
+      *which = (int)value;
     });
   }
   if (!std::strcmp(name, "p2p_newton")) {

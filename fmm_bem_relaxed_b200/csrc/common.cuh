@@ -272,6 +272,7 @@ struct fmmb_plan {
   std::vector<void*> peer_opened;
   unsigned long long* peer_flag_host = nullptr;       // pinned: timeout flag of the bounded flag waits, fetched per call
   std::function<void()> hook_after_owned_m2m;  // set by laplace_execute around laplace_translations
+  std::function<void()> hook_after_m2l_gemm;   // set by laplace_execute: start the near field behind the M2L GEMM
   bool call_sharded = false;         // the current call is fmmb_plan_execute_sharded
   bool cuts_ready = false;
   bool xchg_off_ready = false;
@@ -297,12 +298,21 @@ struct fmmb_plan {
   int bem_near_kernel = 1;           // cached BEM near field: 1 = eight warps per work item (bem_near_split_kernel), 0 = one
   int l2p_kernel = 1;                // 1 = four leaves per warp in body order (l2p_packed_kernel), 0 = one leaf per warp
   int p2m_kernel = 1;                // 1 = narrow transposition tile (p2m_cols_kernel), 0 = full tile (p2m_kernel)
+  int p2p_order = 0;                 // one GPU, class-major engine.  0 = the near field starts with the upward pass and
+                                     // fills whatever the far-field chain (higher stream priority) leaves free;
+                                     // 1 = it starts when the M2L GEMM has finished (measured at N = 1M: 3.09 vs 2.84 ms:
+                                     // the FP64 pipe idles under the upward pass)
+  int m2l_reduce = 1;                // 1 = column reduction staged through shared memory by TMA bulk copies, m2l_reduce_bps
+                                     // blocks per SM (leaves block slots, threads and registers to the near field);
+                                     // 0 = a block per box with its loads in flight in registers
+  int m2l_reduce_bps = 2;
   int p2p_newton = 0;                // 1 = Newton-only inverse root in the near-field pair kernel (p2p_kernel 3)
   int near_only = 0;                 // fmmb_options.near_only
   bool far_built_classes = false, far_built_blocked = false;   // which far-field structures exist (laplace_build_far)
   int p2p_chunk = 32, p2p_min_chunk = 8;  // targets per near-field work item (chosen at plan time)
   // CUDA graphs: one captured matvec per (order, charge pointer, result pointer)
   bool use_graph = true;
+  bool graph_node_priority = true;   // instantiate graphs with cudaGraphInstantiateFlagUseNodePriority
   bool capturing = false;
   struct GraphKey {
     int p; const void* q; void* r; int mode;

@@ -1542,9 +1542,16 @@ void laplace_execute(fmmb_plan* plan, const double* d_charges, double* d_results
   // One GPU: it starts right away and fills the gaps of the latency-bound upward chain.  Sharded with an owned
   // upward pass: it starts once the owned M2M sweep is enqueued (hook below), so that the short dependent kernels
   // before the multipole exchange are not queued behind its blocks and it overlaps the exchange instead.
+  // One GPU, class-major engine (p2p_order 1): it starts when the M2L GEMM has finished.  The GEMM and the pair
+  // kernel both live on the FP64 pipe, so side by side they only share it; one after the other, the rest of the
+  // far-field chain (column reduction: HBM-bound; L2L, L2P: latency-bound) runs beside the near field, on the
+  // stream with the higher priority, instead of after it.
   const bool p2m_owned = laplace_owned_upward(plan);
   const bool defer_p2p = p2m_owned && s2 != s && !plan->near_only;
-  if (!defer_p2p) launch_near_field(plan, s, s2);
+  const bool behind_gemm = !defer_p2p && s2 != s && !plan->near_only && plan->p2p_order == 1 && T.nranks == 1 &&
+                           plan->opts.evaluator != FMMB_EVAL_TREECODE && far_engine(plan) == 2 && P <= 8;
+  bool near_launched = false;
+  if (!defer_p2p && !behind_gemm) { launch_near_field(plan, s, s2); near_launched = true; }
 
   // ---- far field
   if (!plan->capturing) FMMB_CUDA(cudaEventRecord(ev[12], s));
@@ -1575,8 +1582,20 @@ void laplace_execute(fmmb_plan* plan, const double* d_charges, double* d_results
         launch_near_field(plan, s, s2);
       };
     }
-    try { laplace_translations(plan, s); } catch (...) { plan->hook_after_owned_m2m = nullptr; throw; }
+    if (behind_gemm) {
+      plan->hook_after_m2l_gemm = [&]() {
+        FMMB_CUDA(cudaEventRecord(ev[15], s));
+        FMMB_CUDA(cudaStreamWaitEvent(s2, ev[15], 0));
+        launch_near_field(plan, s, s2);
+        near_launched = true;
+      };
+    }
+    try { laplace_translations(plan, s); } catch (...) {
+      plan->hook_after_owned_m2m = nullptr; plan->hook_after_m2l_gemm = nullptr; throw;
+    }
     plan->hook_after_owned_m2m = nullptr;
+    plan->hook_after_m2l_gemm = nullptr;
+    if (behind_gemm && !near_launched) { launch_near_field(plan, s, s2); near_launched = true; }   // nothing was batched
     if (plan->opts.evaluator == FMMB_EVAL_TREECODE) {
       if (T.n_own_leaves)
         m2p_kernel<<<nblk(T.n_own_leaves, 4), 128, 4 * nc * sizeof(double2), s>>>(

@@ -396,6 +396,120 @@ m2l_reduce_kernel(int nboxes, const int* __restrict__ off, const unsigned char* 
   }
 }
 
+// The same sums (same order of additions, same bits) with a footprint that leaves most of an SM to the kernel running
+// beside it.  m2l_reduce_kernel keeps its bytes in flight in registers and takes all 32 block slots of an SM with its
+// 64-thread blocks: while it runs (0.32 ms at N = 1M, HBM-bound), the near field on the other stream -- one-warp
+// blocks that need the FP64 pipe the reduction leaves idle -- is shut out.  Here the bytes in flight live in SHARED
+// memory: every warp owns a ring of kRedStages 4 KB stages, one lane brings the next columns of the warp's box in by
+// 1-D TMA bulk copies (cp.async.bulk, completion in bytes on the stage's mbarrier; the columns of a box are
+// contiguous), the warp adds them up out of shared memory (lane = two rows).  Two blocks of four warps per SM keep
+// 96 KB per SM in flight with 8 K registers; warps never meet at a block barrier.
+constexpr int kRedStages = 4, kRedStageBytes = 4096, kRedWarps = 4;
+constexpr size_t kRedShared = (size_t)kRedWarps * kRedStages * (kRedStageBytes + sizeof(uint64_t) + sizeof(unsigned));
+
+__device__ __forceinline__ void red_mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count));
+}
+__device__ __forceinline__ void red_mbar_expect_tx(uint64_t* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)),
+               "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void red_mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
+}
+__device__ __forceinline__ void red_mbar_wait(uint64_t* bar, unsigned parity) {
+  asm volatile(
+      "{\n .reg .pred p;\n WAIT_%=:\n mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n @p bra DONE_%=;\n"
+      " bra WAIT_%=;\n DONE_%=:\n}\n" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void red_bulk_g2s(void* dst, const void* src, unsigned bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   (unsigned)__cvta_generic_to_shared(dst)), "l"(src), "r"(bytes),
+               "r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
+}
+
+__global__ void __launch_bounds__(32 * kRedWarps)
+m2l_reduce_tma_kernel(int nboxes, const int* __restrict__ off, const unsigned char* __restrict__ batched, int P,
+                      const double* __restrict__ tmp, double* __restrict__ L) {
+  extern __shared__ __align__(128) unsigned char red_sh[];
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  unsigned char* data = red_sh + (size_t)w * kRedStages * kRedStageBytes;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(red_sh + (size_t)kRedWarps * kRedStages * kRedStageBytes) + w * kRedStages;
+  unsigned* cmask = reinterpret_cast<unsigned*>(red_sh + (size_t)kRedWarps * kRedStages * (kRedStageBytes + sizeof(uint64_t))) +
+                    w * kRedStages;
+  if (lane == 0)
+    for (int s = 0; s < kRedStages; ++s) red_mbar_init(&bar[s], 1);
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  __syncwarp();
+  const int xs = xstride(P), nv = xs >> 1;            // xs is even: a column is nv double2
+  const unsigned colb = (unsigned)xs * sizeof(double);
+  // columns per chunk: a multiple of 4 (the four partial sums of m2l_reduce_kernel then line up with the chunks),
+  // at most 32 (one flag per lane)
+  const int CH = min(32, (int)(kRedStageBytes / colb) & ~3);
+  const int nw = gridDim.x * kRedWarps;
+  // a cursor walks the chunks of the warp's boxes (b = first, first + nw, ...); a box without columns is one empty chunk
+  struct Cur { int b, e, e1; };
+  auto load_box = [&](Cur& c) { if (c.b < nboxes) { c.e = off[c.b]; c.e1 = off[c.b + 1]; } };
+  auto step = [&](Cur& c, int n) { c.e += n; if (c.e >= c.e1) { c.b += nw; load_box(c); } };
+  auto issue = [&](Cur& c, int st) {
+    const int n = min(CH, c.e1 - c.e);
+    if (n > 0) {
+      const unsigned m = __ballot_sync(0xffffffffu, lane < n && batched[c.e + lane] != 0);
+      if (lane == 0) {
+        cmask[st] = m;
+        red_mbar_expect_tx(&bar[st], (unsigned)n * colb);
+        red_bulk_g2s(data + (size_t)st * kRedStageBytes, tmp + (size_t)c.e * xs, (unsigned)n * colb, &bar[st]);
+      }
+    } else if (lane == 0) {
+      red_mbar_arrive(&bar[st]);                       // keeps the phase of the stage in step with the chunk count
+    }
+    step(c, n);
+  };
+  Cur pc{(int)(blockIdx.x * kRedWarps) + w, 0, 0};
+  load_box(pc);
+  Cur cc = pc;
+  int pi = 0, ci = 0;
+  while (pi < kRedStages - 1 && pc.b < nboxes) { issue(pc, pi % kRedStages); ++pi; }
+  __syncwarp();
+  const double2 zero = make_double2(0.0, 0.0);
+  double2 s0 = zero, s1 = zero, s2 = zero, s3 = zero;
+  while (cc.b < nboxes) {
+    // the stage of chunk ci - 1 was released by the warp barrier that ended the previous turn
+    if (pc.b < nboxes) { issue(pc, pi % kRedStages); ++pi; }
+    const int n = min(CH, cc.e1 - cc.e);
+    const int st = ci % kRedStages;
+    red_mbar_wait(&bar[st], (unsigned)(ci / kRedStages) & 1u);
+    if (n > 0 && lane < nv) {
+      const unsigned m = cmask[st];
+      const double2* col = reinterpret_cast<const double2*>(data + (size_t)st * kRedStageBytes) + lane;
+      int j = 0;
+#pragma unroll 2
+      for (; j + 4 <= n; j += 4) {
+        const double2 v0 = (m >> j) & 1u ? col[(size_t)j * nv] : zero;
+        const double2 v1 = (m >> (j + 1)) & 1u ? col[(size_t)(j + 1) * nv] : zero;
+        const double2 v2 = (m >> (j + 2)) & 1u ? col[(size_t)(j + 2) * nv] : zero;
+        const double2 v3 = (m >> (j + 3)) & 1u ? col[(size_t)(j + 3) * nv] : zero;
+        s0.x += v0.x; s0.y += v0.y; s1.x += v1.x; s1.y += v1.y;
+        s2.x += v2.x; s2.y += v2.y; s3.x += v3.x; s3.y += v3.y;
+      }
+      for (; j < n; ++j)                               // only the last chunk of a box has a remainder
+        if ((m >> j) & 1u) { const double2 v = col[(size_t)j * nv]; s0.x += v.x; s0.y += v.y; }
+    }
+    if (cc.e + n >= cc.e1) {                           // last chunk of the box
+      if (lane < nv) {
+        // the padding double of an odd-sized expansion stays zero (the scratch columns do not define theirs)
+        const bool pad = 2 * lane + 1 >= P * P;
+        reinterpret_cast<double2*>(L)[(size_t)cc.b * nv + lane] =
+            make_double2((s0.x + s1.x) + (s2.x + s3.x), pad ? 0.0 : (s0.y + s1.y) + (s2.y + s3.y));
+      }
+      s0 = zero; s1 = zero; s2 = zero; s3 = zero;
+    }
+    __syncwarp();                                      // every lane is done with stage st before it is refilled
+    step(cc, n);
+    ++ci;
+  }
+}
+
 // ---- phase 2 (M2M): M[parent] = sum over its children's columns, in child order ---------------------
 __global__ void __launch_bounds__(64)
 m2m_reduce_kernel(int lo, int hi, const unsigned* __restrict__ key, const unsigned* __restrict__ cbegin,
@@ -640,9 +754,17 @@ bool m2l_batched(fmmb_plan* plan, cudaStream_t s) {
   if (!plan->capturing) FMMB_CUDA(cudaEventRecord(plan->ev[14], s));
   plan->m2l_gemm_timed = true;
   ++plan->launches;
-  int threads = pp < 64 ? 64 : (pp > 256 ? 256 : pp);
-  m2l_reduce_kernel<<<T.nboxes, threads, 0, s>>>(T.nboxes, T.m2l_off.p, C.batched.p, P,
-                                                                  C.tmp.p, plan->L.p);
+  if (plan->hook_after_m2l_gemm) plan->hook_after_m2l_gemm();   // laplace_execute: the near field starts here
+  if (plan->m2l_reduce == 1) {
+    int sms = 148;
+    FMMB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, plan->device));
+    FMMB_CUDA(cudaFuncSetAttribute(m2l_reduce_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRedShared));
+    const int grid = std::min(nblk(T.nboxes, kRedWarps), plan->m2l_reduce_bps * sms);
+    m2l_reduce_tma_kernel<<<grid, 32 * kRedWarps, kRedShared, s>>>(T.nboxes, T.m2l_off.p, C.batched.p, P, C.tmp.p, plan->L.p);
+  } else {
+    int threads = pp < 64 ? 64 : (pp > 256 ? 256 : pp);
+    m2l_reduce_kernel<<<T.nboxes, threads, 0, s>>>(T.nboxes, T.m2l_off.p, C.batched.p, P, C.tmp.p, plan->L.p);
+  }
   FMMB_CUDA(cudaGetLastError());
   ++plan->launches;
   return true;

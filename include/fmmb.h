@@ -221,6 +221,13 @@ int fmmb_plan_direct_panels(fmmb_plan* plan, const double* charges_host, int64_t
  *   "p2p_newton"   1 = Newton-only inverse root in p2p_kernel 3 (16 instead of 18 FP64 instructions per pair; the
  *                  near field is then accurate to ~1e-13 instead of round-off).  Default 0.
  *   "p2p_wps"      > 0: persistent near-field blocks, that many one-warp blocks per SM (default 0 = plain grid).
+ *   "p2p_order"    one GPU, class-major far field: 0 (default) = the near field starts with the upward pass on the
+ *                  low-priority stream; 1 = it starts behind the M2L GEMM (slower: measured 3.09 vs 2.84 ms at N = 1M).
+ *   "m2l_reduce"   1 (default) = M2L column reduction staged through shared memory by TMA bulk copies, "m2l_reduce_bps"
+ *                  (1..3, default 2) blocks of four warps per SM: leaves registers and block slots to the near field
+ *                  beside it; 0 = a block per box, loads in flight in registers.  Same bits.
+ *   "graph_node_priority"  1 (default) = cached launch graphs keep the stream priorities of their kernels
+ *                  (cudaGraphInstantiateFlagUseNodePriority): the far-field chain overtakes the near field's blocks.
  *   "p2p_unroll"   pair-loop unroll of p2p_kernel 1: 4 (default) or 8.
  *   "p2p_warps"    warps per block of the near-field pair kernel: 1 (default), 2 or 4.
  *   (measured on B200 at N = 1M: all combinations within 4 %; see profiles/README.md) */
