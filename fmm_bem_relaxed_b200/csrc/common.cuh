@@ -174,6 +174,8 @@ struct TransBatch {
   const int* slot_src_p = nullptr;   // = slot_src.p, or Tree::m2l_src.p for M2L
   DevBuf<int> sorted_slot;           // slots ordered by class (stable: slot order inside a class)
   DevBuf<int> item_class, item_start, item_count;
+  DevBuf<int4> item_desc;            // the same three per item in one word: x = class, y = start, z = count
+  DevBuf<int> sorted_src;            // source box of sorted_slot[i] (one load instead of two dependent ones)
   std::vector<int> level_item_off;   // M2M/L2L: items whose target level is l
   DevBuf<unsigned char> batched;     // M2L, per slot: handled by the batched path
   DevBuf<int> res_off, res_src;      // M2L residual pairs, target-major CSR in list order

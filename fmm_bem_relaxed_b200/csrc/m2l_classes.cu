@@ -96,7 +96,7 @@ __global__ void class_items(const int* __restrict__ count, int nclasses, int min
 }
 __global__ void fill_items(const int* __restrict__ count, const int* __restrict__ start,
                            const int* __restrict__ item_off, int nclasses, int* __restrict__ item_class,
-                           int* __restrict__ item_start, int* __restrict__ item_count) {
+                           int* __restrict__ item_start, int* __restrict__ item_count, int4* __restrict__ item_desc) {
   int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= nclasses) return;
   int ni = item_off[c + 1] - item_off[c];
@@ -105,7 +105,13 @@ __global__ void fill_items(const int* __restrict__ count, const int* __restrict_
     item_class[it] = c;
     item_start[it] = start[c] + i * kNB;
     item_count[it] = min(kNB, count[c] - i * kNB);
+    item_desc[it] = make_int4(c, start[c] + i * kNB, min(kNB, count[c] - i * kNB), 0);
   }
+}
+__global__ void gather_sorted_src(const int* __restrict__ sorted_slot, const int* __restrict__ src, int64_t n,
+                                  int* __restrict__ sorted_src) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) sorted_src[i] = src[sorted_slot[i]];
 }
 // mark slots that the batched path covers; the rest go to the per-pair kernel
 __global__ void mark_batched(const int* __restrict__ count, const int* __restrict__ start, int nclasses, int minpop,
@@ -259,9 +265,8 @@ __device__ __forceinline__ void dmma8x8x4(double& c0, double& c1, double a, doub
 // shared memory (cp.async double buffer).
 template <int P, bool ACC>
 __global__ void __launch_bounds__(256, 2)
-trans_gemm_kernel(int ldT, const double* __restrict__ Tt, int n_items, const int* __restrict__ item_class,
-                  const int* __restrict__ item_start, const int* __restrict__ item_count,
-                  const int* __restrict__ sorted_slot, const int* __restrict__ slot_src,
+trans_gemm_kernel(int ldT, const double* __restrict__ Tt, int n_items, const int4* __restrict__ item_desc,
+                  const int* __restrict__ sorted_slot, const int* __restrict__ sorted_src,
                   const double* __restrict__ X, double* __restrict__ tmp, double* __restrict__ Out) {
   using G = GemmCfg<P>;
   constexpr int PP = G::PP, XS = G::XS, KB = G::KB, RB = G::RB, CB = G::CB, LDB = G::LDB;
@@ -290,12 +295,18 @@ trans_gemm_kernel(int ldT, const double* __restrict__ Tt, int n_items, const int
     }
   }
 
-  auto stage_indices = [&](int it, int buf) {
+  // Index pipeline without a dependent global load on the path of an item: the descriptor of item it + 4 is
+  // fetched into a register while the slots / sources of item it + 3 (descriptor fetched one turn earlier) load
+  // beside the MMAs of item it; they are stored to the ring behind the MMA loop and read after the next barrier.
+  // (Before: class, count, slot and source of an item were loaded back to back in front of the MMA loop --
+  // up to three dependent L2 round trips per item on the warps that stage the indices, one on every warp.)
+  auto desc = [&](int it) { return it < i1 ? item_desc[it] : make_int4(-1, 0, 0, 0); };
+  auto stage_indices = [&](int it, int buf) {            // prologue only (blocking)
     if (threadIdx.x < kNB) {
-      int cnt = item_count[it];
-      int sl = threadIdx.x < cnt ? sorted_slot[item_start[it] + threadIdx.x] : -1;
-      s_slot[buf][threadIdx.x] = sl;
-      s_src[buf][threadIdx.x] = sl >= 0 ? slot_src[sl] : -1;
+      const int4 d = item_desc[it];
+      const bool in = threadIdx.x < d.z;
+      s_slot[buf][threadIdx.x] = in ? sorted_slot[d.y + threadIdx.x] : -1;
+      s_src[buf][threadIdx.x] = in ? sorted_src[d.y + threadIdx.x] : -1;
     }
   };
   auto stage_copy = [&](int ib, int buf) {
@@ -318,9 +329,17 @@ trans_gemm_kernel(int ldT, const double* __restrict__ Tt, int n_items, const int
   __syncthreads();
   stage_copy(0, 0);
   if (i0 + 1 < i1) stage_copy(1, 1); else cp_async_commit();
+  int cls0 = desc(i0).x, cls1 = desc(i0 + 1).x, cls2 = desc(i0 + 2).x;
+  int4 d3 = desc(i0 + 3);
   for (int it = i0; it < i1; ++it) {
     const int j = it - i0, buf = j % NBUF, ib = j % NIDX;
-    const int c = item_class[it];
+    const int c = cls0;
+    const int4 d4 = desc(it + 4);
+    int sl_r = -1, src_r = -1;
+    if (threadIdx.x < kNB && (int)threadIdx.x < d3.z) {   // d3.z = 0 behind the last item
+      sl_r = sorted_slot[d3.y + threadIdx.x];
+      src_r = sorted_src[d3.y + threadIdx.x];
+    }
     if (c != cur) {
       const double* Tc = Tt + (size_t)c * ldT * ldT;
 #pragma unroll
@@ -334,7 +353,6 @@ trans_gemm_kernel(int ldT, const double* __restrict__ Tt, int n_items, const int
     }
     cp_async_wait<1>();                 // this thread's copies of item `it` have landed (item it+1 may be in flight)
     __syncthreads();                    // ... everyone's; all warps are done with item it-1
-    if (it + 3 < i1) stage_indices(it + 3, (j + 3) % NIDX);
     if (it + 2 < i1) stage_copy((j + 2) % NIDX, (j + 2) % NBUF); else cp_async_commit();
 
     const double* Bs = smem + (size_t)buf * kNB * LDB + (size_t)(col_base + lr) * LDB + lk;
@@ -353,6 +371,11 @@ trans_gemm_kernel(int ldT, const double* __restrict__ Tt, int n_items, const int
 #pragma unroll
         for (int cb = 0; cb < CB; ++cb) dmma8x8x4(C[rb][cb][0], C[rb][cb][1], A[rb][kb], bf[cb]);
     }
+    if (threadIdx.x < kNB && it + 3 < i1) {               // ring slot of item it - 1: everyone is past its epilogue
+      s_slot[(j + 3) % NIDX][threadIdx.x] = sl_r;
+      s_src[(j + 3) % NIDX][threadIdx.x] = src_r;
+    }
+    cls0 = cls1; cls1 = cls2; cls2 = d3.x; d3 = d4;
 #pragma unroll
     for (int cb = 0; cb < CB; ++cb)
 #pragma unroll
@@ -537,9 +560,8 @@ void launch_gemm_t(const TransBatch& B, int first, int count, const double* X, d
   FMMB_CUDA(cudaGetDevice(&dev));
   FMMB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   int grid = std::min(count, 2 * sms);
-  trans_gemm_kernel<P, ACC><<<grid, 256, sh, s>>>(B.built_p * B.built_p, B.T.p, count, B.item_class.p + first,
-                                                 B.item_start.p + first, B.item_count.p + first,
-                                                 B.sorted_slot.p, B.slot_src_p, X, tmp, out);
+  trans_gemm_kernel<P, ACC><<<grid, 256, sh, s>>>(B.built_p * B.built_p, B.T.p, count, B.item_desc.p + first,
+                                                 B.sorted_slot.p, B.sorted_src.p, X, tmp, out);
   FMMB_CUDA(cudaGetLastError());
 }
 template <bool ACC>
@@ -603,9 +625,12 @@ void classify(fmmb_plan* plan, TransBatch& B, const int* tgt, const int* src, in
   B.n_classes = ncls;
   B.n_items = n_items;
   B.item_class.resize(n_items); B.item_start.resize(n_items); B.item_count.resize(n_items);
+  B.item_desc.resize(n_items);
   if (n_items)
     fill_items<<<nblk(ncls, 128), 128, 0, s>>>(count.p, start.p, item_off.p, ncls, B.item_class.p, B.item_start.p,
-                                              B.item_count.p);
+                                              B.item_count.p, B.item_desc.p);
+  B.sorted_src.resize(n);
+  if (n) gather_sorted_src<<<nblk(n, 256), 256, 0, s>>>(B.sorted_slot.p, src, n, B.sorted_src.p);
   B.class_vec.resize(ncls);
   class_vectors<<<nblk(ncls, 128), 128, 0, s>>>(start.p, ncls, B.sorted_slot.p, tgt, src, T.key.p, T.level.p,
                                                make_double3(0.5 * T.cell[0], 0.5 * T.cell[1], 0.5 * T.cell[2]),
