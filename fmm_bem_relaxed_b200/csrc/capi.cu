@@ -126,6 +126,8 @@ int fmmb_plan_create(const fmmb_kernel_desc* kernel, const fmmb_sources* sources
     FMMB_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
     FMMB_CUDA(cudaStreamCreateWithPriority(&plan->stream, cudaStreamNonBlocking, prio_hi));
     FMMB_CUDA(cudaStreamCreateWithPriority(&plan->stream2, cudaStreamNonBlocking, prio_lo));
+    if (const char* e = std::getenv("FMMB_GRAPH_NODE_PRIORITY")) plan->graph_node_priority = std::atoi(e) != 0;
+    if (const char* e = std::getenv("FMMB_M2L_REDUCE")) plan->m2l_reduce = std::atoi(e) != 0;
     for (auto& e : plan->ev) FMMB_CUDA(cudaEventCreate(&e));
     plan->charge_dim = is_stokes ? (kernel->kind == FMMB_STOKES_SPHERICAL_STRESSLET ? 6 : 3) : (is_sbem ? 3 : 1);
     plan->result_dim = is_bem ? 1 : (is_stokes || is_sbem ? 3 : 4);
@@ -573,11 +575,13 @@ int fmmb_plan_set_option(fmmb_plan* plan, const char* name, int64_t value) {
       plan->p2p_occ = (int)value;
     });
   }
-  if (!std::strcmp(name, "p2p_order") || !std::strcmp(name, "m2l_reduce") || !std::strcmp(name, "m2l_reduce_bps")) {
+  if (!std::strcmp(name, "p2p_order") || !std::strcmp(name, "m2l_reduce") || !std::strcmp(name, "m2l_reduce_bps") ||
+      !std::strcmp(name, "p2p_defer")) {
     const bool bps = !std::strcmp(name, "m2l_reduce_bps");
-    int* which = !std::strcmp(name, "p2p_order") ? &plan->p2p_order : (bps ? &plan->m2l_reduce_bps : &plan->m2l_reduce);
+    int* which = !std::strcmp(name, "p2p_order") ? &plan->p2p_order
+                 : (bps ? &plan->m2l_reduce_bps : (!std::strcmp(name, "p2p_defer") ? &plan->p2p_defer : &plan->m2l_reduce));
     if (bps ? (value < 1 || value > 3) : (value != 0 && value != 1)) {
-      set_error("p2p_order / m2l_reduce: 0 or 1; m2l_reduce_bps: 1..3 blocks per SM");
+      set_error("p2p_order / m2l_reduce / p2p_defer: 0 or 1; m2l_reduce_bps: 1..3 blocks per SM");
       return FMMB_ERR_INVALID;
     }
     return guarded([&] {

@@ -308,6 +308,8 @@ struct fmmb_plan {
                                      // blocks per SM (leaves block slots, threads and registers to the near field);
                                      // 0 = a block per box with its loads in flight in registers
   int m2l_reduce_bps = 2;
+  int p2p_defer = 1;                 // sharded plans with an owned upward pass: 1 = the near field starts behind the owned
+                                     // M2M sweep (beside the multipole exchange), 0 = with the upward pass
   int p2p_newton = 0;                // 1 = Newton-only inverse root in the near-field pair kernel (p2p_kernel 3)
   int near_only = 0;                 // fmmb_options.near_only
   bool far_built_classes = false, far_built_blocked = false;   // which far-field structures exist (laplace_build_far)

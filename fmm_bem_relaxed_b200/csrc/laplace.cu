@@ -1547,7 +1547,7 @@ void laplace_execute(fmmb_plan* plan, const double* d_charges, double* d_results
   // far-field chain (column reduction: HBM-bound; L2L, L2P: latency-bound) runs beside the near field, on the
   // stream with the higher priority, instead of after it.
   const bool p2m_owned = laplace_owned_upward(plan);
-  const bool defer_p2p = p2m_owned && s2 != s && !plan->near_only;
+  const bool defer_p2p = p2m_owned && s2 != s && !plan->near_only && plan->p2p_defer;
   const bool behind_gemm = !defer_p2p && s2 != s && !plan->near_only && plan->p2p_order == 1 && T.nranks == 1 &&
                            plan->opts.evaluator != FMMB_EVAL_TREECODE && far_engine(plan) == 2 && P <= 8;
   bool near_launched = false;
@@ -1680,6 +1680,10 @@ void build_p2p_items(fmmb_plan* plan) {
   // (multi-GPU shards, small problems): a chunk of 16 or 8 targets splits its sources 4 or 8 ways across the
   // lanes at the same lane efficiency, and the shorter items even out the tail of the grid.
   int chunk = 32, sms = 148;
+  if (const char* e = std::getenv("FMMB_P2P_CHUNK")) {   // development knob: first chunk size tried (32, 16 or 8)
+    const int v = std::atoi(e);
+    if (v == 32 || v == 16 || v == 8) chunk = v;
+  }
   FMMB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, plan->device));
   std::vector<int> h, off(nl + 1, 0);
   for (;;) {
