@@ -60,6 +60,14 @@ for mode in sys.argv[3:] or ["full", "sharded", "sharded+peer"]:
     print("rank %d mode %s own %d bodies: serial phases %s" % (rank, mode, i.own_body_end - i.own_body_begin,
           {k: round(v, 3) for k, v in acc.items()}), flush=True)
     plan.set_option("overlap_p2p", 1)
+    # where the phases lie on the clock of an overlapped matvec (plain launches), rank by rank
+    for i in range(6):
+        dist.barrier(); torch.cuda.synchronize()
+        if i == 4:
+            os.environ["FMMB_PRINT_TIMELINE"] = "1"
+        run()
+        plan.sync()
+    del os.environ["FMMB_PRINT_TIMELINE"]
     plan.set_option("use_graph", 1)
     for _ in range(4):
         run()

@@ -361,3 +361,32 @@ def test_blocked_batches_pass_their_host_side_audit(monkeypatch):
             plan = F.FMM_plan(F.LaplaceSpherical(4), pts, opts)      # build_blk_batch audits M2L, M2M, L2L (+ own / strad)
             plan.execute(rng.random(n))
             plan.close()
+
+
+@pytest.mark.parametrize("P", [1, 2, 3, 5, 7, 8])
+def test_overlap_options_change_the_schedule_not_the_bits(P):
+    """Round 2: the far-field chain and the near field overlap inside one CUDA graph.  What decides HOW
+    they overlap -- per-node priorities in the graph, the column reduction staged through shared memory by TMA bulk
+    copies (m2l_reduce 1) or with a block per box (0), one to three reduction blocks per SM, the near field started
+    with the upward pass or behind the GEMM (p2p_order) -- must not change a single bit of the result: the reduction
+    adds its columns in the same order in both kernels (odd orders: the padding double of an expansion stays zero).
+    Each setting: first call plain launches, second call captures, third replays; all against the oracle."""
+    rng = np.random.default_rng(100 + P)
+    n = 12000
+    pts = rng.random((n, 3))
+    pts[n // 2:] = 0.3 + 0.1 * rng.random((n - n // 2, 3))        # adaptive: boxes with and without M2L pairs
+    q = rng.random(n) - 0.3
+    ref = O.Oracle(pts, 48, 0.5).execute(q, P, mode=0)
+    plan = make_plan(pts, P, 48)
+    first = None
+    for opts in ({}, {"m2l_reduce": 0}, {"m2l_reduce_bps": 1}, {"m2l_reduce_bps": 3}, {"graph_node_priority": 0},
+                 {"p2p_order": 1}, {"p2p_order": 1, "m2l_reduce": 0}, {"overlap_p2p": 0}):
+        for k, v in {"m2l_reduce": 1, "m2l_reduce_bps": 2, "graph_node_priority": 1, "p2p_order": 0, "overlap_p2p": 1,
+                     **opts}.items():
+            plan.set_option(k, v)
+        for _ in range(3):
+            res = plan.execute(q)
+            if first is None:
+                first = res.copy()
+                assert_parity(res, ref)
+            assert np.array_equal(res, first), opts
