@@ -263,3 +263,30 @@ def test_reference_laplacebem_driver_unchanged():
         a = parse_gmres(run_bin("ref_LaplaceBEM", "-recursions", "5", "-p", "8", "-k", "4", "-solver_tol", "1e-6", *extra))
         b = parse_gmres(run_bin("laplace_bem", "-recursions", "5", "-p", "8", "-k", "4", "-solver_tol", "1e-6", *extra))
         assert a == b
+
+
+@pytest.mark.gpu
+def test_reference_msh_reader_feeds_the_gpu_plan(tmp_path):
+    """SURVEY 8(f) rank 4, mesh readers: the reference's MshReader.hpp (compiled unchanged into bin/ref_LaplaceBEM) reads
+    a Gmsh 2 ASCII file -- nodes written with 17 digits, a non-triangular element that the reader skips, triangles with
+    the (v1, v3, v2) order the reader turns back (MshReader.hpp:84-89) -- and the solve over the GPU plan prints exactly
+    the lines of the generated sphere with the same 512 panels."""
+    v = O.unit_sphere(4)                                  # (512, 3, 3), the panels of Triangulation::UnitSphere(4)
+    n = v.shape[0]
+    msh = tmp_path / "sphere.msh"
+    with open(msh, "w") as f:
+        f.write("$MeshFormat\n2.2 0 8\n$EndMeshFormat\n$Nodes\n%d\n" % (3 * n))
+        for i, p in enumerate(v.reshape(-1, 3)):
+            f.write("%d %.17g %.17g %.17g\n" % (i + 1, p[0], p[1], p[2]))
+        f.write("$EndNodes\n$Elements\n%d\n" % (n + 1))
+        for e in range(n):                                # element: number, type 2 (triangle), 2 tags, three nodes
+            f.write("%d 2 2 0 1 %d %d %d\n" % (e + 1, 3 * e + 1, 3 * e + 3, 3 * e + 2))
+        f.write("%d 1 2 0 1 1 2\n" % (n + 1))             # a line element: skipped by the reader
+        f.write("$EndElements\n")
+    args = ("-p", "8", "-k", "4", "-solver_tol", "1e-6")
+    out = run_bin("ref_LaplaceBEM", "-mesh", str(msh), *args)
+    assert "num_nodes: %d" % (3 * n) in out and "1 elements skipped" in out
+    its, final, niter, rel, ext = parse_gmres(out)
+    assert niter == 7 and [p for _, _, p in its] == [8, 8, 8, 7, 6, 4]
+    assert [r for _, r, _ in its] == [7.878e-04, 2.986e-04, 1.081e-04, 3.370e-05, 1.043e-05, 2.522e-06]
+    assert final == 3.1066e-07 and rel == 1.512e-02 and ext == 0.19071

@@ -380,3 +380,33 @@ def test_shipped_laplacebem_driver_compiles_its_preconditioned_branches_out(tmp_
         assert not re.findall(r"it: \d+, res:", out) and "Final residual" not in out
         m = re.search(r"relative error: ([0-9.eE+-]+)", out)
         assert m and float(m.group(1)) == rec["relative_error"] == 1.0
+
+
+def test_reference_vert_face_reader_feeds_the_gpu_plan(tmp_path):
+    """SURVEY 8(f) rank 4, mesh readers: the reference's VertFaceReader.hpp (compiled unchanged into
+    bin/ref_StokesBEM, `-vert` / `-face`, examples/StokesBEM.cpp:193-236) reads the 512-panel sphere from a .vert /
+    .face pair with 17-digit vertices; the solve over the GPU plan prints what the unmodified reference prints for the
+    same files on one CPU thread -- which is what it prints for `-recursions 4` (checked with oracle/_ref/StokesBEM)."""
+    v = O.unit_sphere(4)
+    n = v.shape[0]
+    with open(tmp_path / "s.vert", "w") as f:
+        f.write("%d\n" % (3 * n))
+        for p in v.reshape(-1, 3):
+            f.write("%.17g %.17g %.17g\n" % tuple(p))
+    with open(tmp_path / "s.face", "w") as f:
+        f.write("%d\n" % n)
+        for e in range(n):
+            f.write("%d %d %d\n" % (3 * e + 1, 3 * e + 2, 3 * e + 3))
+    out = _driver_lines("ref_StokesBEM", ["-vert", str(tmp_path / "s.vert"), "-face", str(tmp_path / "s.face"),
+                                          "-p", "8", "-k", "4", "-solver_tol", "1e-5"], tmp_path)
+    assert "# vertices: %d" % (3 * n) in out and "# elements: %d" % n in out
+    want = [(1, 3.600e-03, 7), (2, 1.190e-03, 7), (3, 5.352e-04, 6), (4, 1.876e-04, 5), (5, 8.862e-05, 5),
+            (6, 4.782e-05, 5), (7, 2.533e-05, 5)]
+    got = [(int(a), float(b), int(c)) for a, b, c in re.findall(r"it: (\d+), res: ([0-9.eE+-]+), fmm_req_p: (\d+)", out)]
+    assert len(got) == len(want), out
+    for (i, r, p), (wi, wr, wp) in zip(got, want):
+        assert (i, p) == (wi, wp) and abs(r - wr) <= 2e-3 * wr, (got, out)
+    m = re.search(r"Final residual: ([0-9.eE+-]+), after (\d+) iterations", out)
+    assert m and int(m.group(2)) == 8 and abs(float(m.group(1)) - 9.8804e-06) <= 2e-3 * 9.8804e-06, out
+    m = re.search(r"Fx: ([0-9.]+), analytical: 0\.01885", out)
+    assert m and abs(float(m.group(1)) - 0.01934) <= 2e-5, out
