@@ -158,7 +158,7 @@ class StokesSpherical(LaplaceSpherical):
 class YukawaCartesian(LaplaceSpherical):
     """Mirror of reference kernel/YukawaCartesian.hpp:14-159: K(t,s) = exp(-kappa |t-s|) / |t-s|, order p, screening
     parameter kappa (constructor YukawaCartesian(int p, double kappa = 0.125)); 1 charge, 4 results.
-    Orders 1..10.  set_p(p) means "the full order-p expansion" (the reference's own p < P path walks a wrong
+    Orders 1..16.  set_p(p) means "the full order-p expansion" (the reference's own p < P path walks a wrong
     coefficient subset)."""
     kind = capi.YUKAWA_CARTESIAN
 
@@ -169,7 +169,7 @@ class YukawaCartesian(LaplaceSpherical):
 
 class YukawaCartesianBEM(LaplaceSphericalBEM):
     """Mirror of reference kernel/YukawaCartesianBEM.hpp:8-143: YukawaCartesianBEM(int p, double kappa, unsigned k).
-    Panel sources like LaplaceSphericalBEM; scalar charges and results; orders 1..10."""
+    Panel sources like LaplaceSphericalBEM; scalar charges and results; orders 1..16."""
     kind = capi.YUKAWA_CARTESIAN_BEM
 
     def __init__(self, p=5, kappa=0.125, k=3):

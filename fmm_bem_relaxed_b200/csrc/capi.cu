@@ -211,7 +211,6 @@ void fmmb_plan_destroy(fmmb_plan* plan) {
 int fmmb_plan_set_p(fmmb_plan* plan, int p) {
   if (!plan) { set_error("null plan"); return FMMB_ERR_INVALID; }
   if (p < 1 || p > FMMB_MAX_P) { set_error("expansion order must be in 1..16"); return FMMB_ERR_INVALID; }
-  if (plan->yukawa && p > 10) { set_error("YukawaCartesian is built for orders 1..10"); return FMMB_ERR_UNSUPPORTED; }
   if (plan->peer_alloc && p > 8) {
     // the exported multipole block holds 64 doubles per box with the flag vectors and the charge vector behind it
     set_error("plans with a peer-memory exchange run orders 1..8 (the exported multipole block is sized for P = 8)");

@@ -29,8 +29,16 @@ namespace fmmb {
 const bem::Panel* bem_panels(const BemData* b);
 const int* bem_bc(const BemData* b);
 
-constexpr int kYkMaxP = 10;
-constexpr int kYkMaxT = (kYkMaxP + 1) * (kYkMaxP + 2) * (kYkMaxP + 3) / 6;   // 286
+constexpr int kYkMaxP = 16;                                                 // = FMMB_MAX_P: index tables for every order
+constexpr int kYkMaxT = (kYkMaxP + 1) * (kYkMaxP + 2) * (kYkMaxP + 3) / 6;   // 969
+// Kernels that keep per-term state in registers, local or static shared memory are compiled twice: for orders up to 10
+// (286 terms -- every BASELINE configuration) and up to 16 (969 terms), so that the common orders do not pay for the
+// arrays of the large ones (YkCap<MP>); the host picks by the plan's order (YK_MP).
+template <int MP>
+struct YkCap {
+  static constexpr int T = (MP + 1) * (MP + 2) * (MP + 3) / 6;
+  static constexpr int ACC = (T + 31) / 32, ACC128 = (T + 127) / 128;
+};
 
 struct YukawaData {
   double kappa = 0.125;
@@ -109,7 +117,7 @@ __device__ __forceinline__ void scaled_powers(int P, double dx, double dy, doubl
 }
 
 // ---- P2M: warp per leaf; lanes stage (c - x)^e / e! of 32 bodies, then lane = coefficient --------------------
-constexpr int kYkAcc = (kYkMaxT + 31) / 32;
+template <int MP>
 __global__ void __launch_bounds__(128)
 yk_p2m_kernel(const int* __restrict__ leaves, int nleaves, const unsigned* __restrict__ bb,
               const unsigned* __restrict__ be, const double4* __restrict__ center,
@@ -123,9 +131,9 @@ yk_p2m_kernel(const int* __restrict__ leaves, int nleaves, const unsigned* __res
   const int b = leaves[w];
   const double4 c = center[b];
   const unsigned b0 = bb[b], b1 = be[b];
-  double acc[kYkAcc];
+  double acc[YkCap<MP>::ACC];
 #pragma unroll
-  for (int i = 0; i < kYkAcc; ++i) acc[i] = 0.0;
+  for (int i = 0; i < YkCap<MP>::ACC; ++i) acc[i] = 0.0;
   for (unsigned base = b0; base < b1; base += 32) {
     const int cnt = (int)min(32u, b1 - base);
     __syncwarp();
@@ -136,7 +144,7 @@ yk_p2m_kernel(const int* __restrict__ leaves, int nleaves, const unsigned* __res
     }
     __syncwarp();
 #pragma unroll
-    for (int a = 0; a < kYkAcc; ++a) {
+    for (int a = 0; a < YkCap<MP>::ACC; ++a) {
       const int t = lane + 32 * a;
       if (t < nt) {
         const int i = c_yI[P][t], j = P + 1 + c_yJ[P][t], k = 2 * (P + 1) + c_yK[P][t];
@@ -151,25 +159,26 @@ yk_p2m_kernel(const int* __restrict__ leaves, int nleaves, const unsigned* __res
   }
   double* Mb = M + (size_t)b * nt;
 #pragma unroll
-  for (int a = 0; a < kYkAcc; ++a) {
+  for (int a = 0; a < YkCap<MP>::ACC; ++a) {
     const int t = lane + 32 * a;
     if (t < nt) Mb[t] = acc[a];
   }
 }
 
 // ---- M2M: block per parent of one level, children in index order -------------------------------------------
+template <int MP>
 __global__ void __launch_bounds__(128)
 yk_m2m_kernel(int lo, int hi, const unsigned* __restrict__ key, const unsigned* __restrict__ cbegin,
               const unsigned* __restrict__ cend, const double4* __restrict__ center, int P, double* __restrict__ M) {
   const int b = lo + blockIdx.x;
   if (b >= hi || (key[b] >> 31)) return;          // leaves got their multipole from P2M
-  __shared__ double Ms[kYkMaxT];
-  __shared__ double pw[3 * (kYkMaxP + 1)];
+  __shared__ double Ms[YkCap<MP>::T];
+  __shared__ double pw[3 * (MP + 1)];
   const int nt = yk_terms(P);
   const double4 cp = center[b];
-  double acc[(kYkMaxT + 127) / 128];
+  double acc[YkCap<MP>::ACC128];
 #pragma unroll
-  for (int a = 0; a < (kYkMaxT + 127) / 128; ++a) acc[a] = 0.0;
+  for (int a = 0; a < YkCap<MP>::ACC128; ++a) acc[a] = 0.0;
   for (unsigned c = cbegin[b]; c < cend[b]; ++c) {
     const double4 cc = center[c];
     __syncthreads();
@@ -177,7 +186,7 @@ yk_m2m_kernel(int lo, int hi, const unsigned* __restrict__ key, const unsigned* 
     if (threadIdx.x == 0) scaled_powers(P, cp.x - cc.x, cp.y - cc.y, cp.z - cc.z, pw);
     __syncthreads();
 #pragma unroll
-    for (int a = 0; a < (kYkMaxT + 127) / 128; ++a) {
+    for (int a = 0; a < YkCap<MP>::ACC128; ++a) {
       const int t = threadIdx.x + 128 * a;
       if (t < nt) {
         const int I = c_yI[P][t], J = c_yJ[P][t], K = c_yK[P][t];
@@ -193,7 +202,7 @@ yk_m2m_kernel(int lo, int hi, const unsigned* __restrict__ key, const unsigned* 
     }
   }
 #pragma unroll
-  for (int a = 0; a < (kYkMaxT + 127) / 128; ++a) {
+  for (int a = 0; a < YkCap<MP>::ACC128; ++a) {
     const int t = threadIdx.x + 128 * a;
     if (t < nt) M[(size_t)b * nt + t] = acc[a];
   }
@@ -232,9 +241,10 @@ __device__ void yk_coeff_table(int P, double kappa, double x, double y, double z
   __syncthreads();
 }
 
+template <int MP>
 __global__ void __launch_bounds__(128)
 yk_table_kernel(int P, double kappa, const double4* __restrict__ vec, double* __restrict__ table) {
-  __shared__ double a[kYkMaxT], b[kYkMaxT];
+  __shared__ double a[YkCap<MP>::T], b[YkCap<MP>::T];
   const double4 v = vec[blockIdx.x];
   yk_coeff_table(P, kappa, v.x, v.y, v.z, a, b);
   const int nt = yk_terms(P);
@@ -248,7 +258,7 @@ yk_table_kernel(int P, double kappa, const double4* __restrict__ vec, double* __
 // phi += sum_n a'_n M_n.  Only panels whose BC selects this set are touched; set 0 adds, set 1 subtracts.  The
 // reference's FMM evaluator is broken for this kernel class while its treecode agrees with Direct, so this
 // is the far-field path of BASELINE config 3 that is pinned to the reference.
-template <int SET>
+template <int SET, int MP>
 __global__ void __launch_bounds__(128)
 yk_bem_m2p_kernel(const int* __restrict__ leaves, int nleaves, const unsigned* __restrict__ bb,
                   const unsigned* __restrict__ be, const unsigned* __restrict__ parent, const int* __restrict__ off,
@@ -260,7 +270,7 @@ yk_bem_m2p_kernel(const int* __restrict__ leaves, int nleaves, const unsigned* _
   const int w = blockIdx.x * (blockDim.x >> 5) + wl;
   if (w >= nleaves) return;
   const int leaf = leaves[w];
-  double a[kYkMaxT], b[kYkMaxT];
+  double a[YkCap<MP>::T], b[YkCap<MP>::T];
   for (unsigned i = bb[leaf] + lane; i < be[leaf]; i += 32) {
     if (bc[i] != SET) continue;
     const double px = pan[i].c[0], py = pan[i].c[1], pz = pan[i].c[2];
@@ -307,6 +317,7 @@ yk_bem_m2p_kernel(const int* __restrict__ leaves, int nleaves, const unsigned* _
 // ---- M2P of the point kernel (treecode, reference kernel/YukawaCartesian.hpp:221-240): warp per leaf, lane per body.
 // Same lane-private table as above; the gradient uses ax_m = (m_x + 1) a_{m + e_x} for |m| < P and nothing for
 // |m| = P, which is what getCoeff's `ax[Im1x] = a[I] * i` lines leave in ax / ay / az (:388-672).
+template <int MP>
 __global__ void __launch_bounds__(128)
 yk_m2p_kernel(const int* __restrict__ leaves, int nleaves, const unsigned* __restrict__ bb,
               const unsigned* __restrict__ be, const unsigned* __restrict__ parent, const int* __restrict__ off,
@@ -317,7 +328,7 @@ yk_m2p_kernel(const int* __restrict__ leaves, int nleaves, const unsigned* __res
   const int w = blockIdx.x * (blockDim.x >> 5) + wl;
   if (w >= nleaves) return;
   const int leaf = leaves[w];
-  double a[kYkMaxT], b[kYkMaxT];
+  double a[YkCap<MP>::T], b[YkCap<MP>::T];
   for (unsigned i = bb[leaf] + lane; i < be[leaf]; i += 32) {
     const double4 p = body[i];
     double pot = 0, gx = 0, gy = 0, gz = 0;
@@ -376,17 +387,18 @@ __global__ void yk_slot_class_kernel(int n_items, const int* __restrict__ item_c
 }
 
 // ---- M2L: block per target box, sources in LR_list order; thread = output coefficient k --------------------
+template <int MP>
 __global__ void __launch_bounds__(128)
 yk_m2l_kernel(int nboxes, const int* __restrict__ off, const int* __restrict__ src, const int* __restrict__ slot_class,
               const double* __restrict__ table, const double4* __restrict__ center, int P, double kappa,
               const double* __restrict__ M, double* __restrict__ L) {
   const int b = blockIdx.x;
   if (b >= nboxes) return;
-  __shared__ double a[kYkMaxT], bt[kYkMaxT], Ms[kYkMaxT];
+  __shared__ double a[YkCap<MP>::T], bt[YkCap<MP>::T], Ms[YkCap<MP>::T];
   const int nt = yk_terms(P);
-  double acc[(kYkMaxT + 127) / 128];
+  double acc[YkCap<MP>::ACC128];
 #pragma unroll
-  for (int i = 0; i < (kYkMaxT + 127) / 128; ++i) acc[i] = 0.0;
+  for (int i = 0; i < YkCap<MP>::ACC128; ++i) acc[i] = 0.0;
   const double4 ct = center[b];
   for (int e = off[b]; e < off[b + 1]; ++e) {
     const int sb = src[e];
@@ -401,7 +413,7 @@ yk_m2l_kernel(int nboxes, const int* __restrict__ off, const int* __restrict__ s
       yk_coeff_table(P, kappa, ct.x - cs.x, ct.y - cs.y, ct.z - cs.z, a, bt);
     }
 #pragma unroll
-    for (int i = 0; i < (kYkMaxT + 127) / 128; ++i) {
+    for (int i = 0; i < YkCap<MP>::ACC128; ++i) {
       const int t = threadIdx.x + 128 * i;
       if (t < nt) {
         const int ik = c_yI[P][t], jk = c_yJ[P][t], kk = c_yK[P][t];
@@ -417,13 +429,14 @@ yk_m2l_kernel(int nboxes, const int* __restrict__ off, const int* __restrict__ s
     }
   }
 #pragma unroll
-  for (int i = 0; i < (kYkMaxT + 127) / 128; ++i) {
+  for (int i = 0; i < YkCap<MP>::ACC128; ++i) {
     const int t = threadIdx.x + 128 * i;
     if (t < nt) L[(size_t)b * nt + t] = acc[i];
   }
 }
 
 // ---- L2L: block per child of one level ------------------------------------------------------------------------
+template <int MP>
 __global__ void __launch_bounds__(128)
 yk_l2l_kernel(int lo, int hi, const unsigned* __restrict__ parent, const unsigned char* __restrict__ has_local,
               const double4* __restrict__ center, int P, double* __restrict__ L) {
@@ -431,8 +444,8 @@ yk_l2l_kernel(int lo, int hi, const unsigned* __restrict__ parent, const unsigne
   if (b >= hi) return;
   const int par = (int)parent[b];
   if (!has_local[par]) return;
-  __shared__ double Ls[kYkMaxT];
-  __shared__ double pw[3 * (kYkMaxP + 1)];
+  __shared__ double Ls[YkCap<MP>::T];
+  __shared__ double pw[3 * (MP + 1)];
   const int nt = yk_terms(P);
   const double4 cc = center[b], cp = center[par];
   for (int t = threadIdx.x; t < nt; t += blockDim.x) Ls[t] = L[(size_t)par * nt + t];
@@ -570,7 +583,7 @@ yk_direct_kernel(const double* __restrict__ spts, const double* __restrict__ q, 
 // q w_j Area and the panel normal of 32 entries, then lane = coefficient sums over the entries:
 //   set 0:  M_n += mult C_n,               C_n = dX^n / n!
 //   set 1:  M_n -= mult (n . grad_dX) C_n   (the reference writes the derivative as C_n n_d / dX_d)
-template <int SET>
+template <int SET, int MP>
 __global__ void __launch_bounds__(128)
 yk_bem_p2m_kernel(const int* __restrict__ leaves, int nleaves, const unsigned* __restrict__ bb,
                   const unsigned* __restrict__ be, const double4* __restrict__ center,
@@ -587,9 +600,9 @@ yk_bem_p2m_kernel(const int* __restrict__ leaves, int nleaves, const unsigned* _
   const unsigned b0 = bb[b], b1 = be[b];
   const int K = rule.n;
   const int nent = (int)(b1 - b0) * K;
-  double acc[kYkAcc];
+  double acc[YkCap<MP>::ACC];
 #pragma unroll
-  for (int i = 0; i < kYkAcc; ++i) acc[i] = 0.0;
+  for (int i = 0; i < YkCap<MP>::ACC; ++i) acc[i] = 0.0;
   for (int base = 0; base < nent; base += 32) {
     const int ent = base + lane;
     const int cnt = min(32, nent - base);
@@ -607,7 +620,7 @@ yk_bem_p2m_kernel(const int* __restrict__ leaves, int nleaves, const unsigned* _
     }
     __syncwarp();
 #pragma unroll
-    for (int a = 0; a < kYkAcc; ++a) {
+    for (int a = 0; a < YkCap<MP>::ACC; ++a) {
       const int t = lane + 32 * a;
       if (t < nt) {
         const int I = c_yI[P][t], J = c_yJ[P][t], Kk = c_yK[P][t];
@@ -632,7 +645,7 @@ yk_bem_p2m_kernel(const int* __restrict__ leaves, int nleaves, const unsigned* _
   }
   double* Mb = M + (size_t)b * nt;
 #pragma unroll
-  for (int a = 0; a < kYkAcc; ++a) {
+  for (int a = 0; a < YkCap<MP>::ACC; ++a) {
     const int t = lane + 32 * a;
     if (t < nt) Mb[t] = acc[a];
   }
@@ -667,6 +680,18 @@ yk_bem_l2p_kernel(const int* __restrict__ leaves, int nleaves, const unsigned* _
   }
 }
 
+// launch of a kernel compiled for orders <= 10 and <= 16 (YkCap)
+#define YK_MP(P, KERNEL, ...)                      \
+  do {                                             \
+    if ((P) <= 10) KERNEL<10> __VA_ARGS__;         \
+    else KERNEL<16> __VA_ARGS__;                   \
+  } while (0)
+// dynamic shared memory above the 48 KB default (orders 14..16 of the tile kernels)
+template <typename K>
+void yk_shared_limit(K kernel, size_t bytes) {
+  if (bytes > 48 * 1024) FMMB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+}
+
 // derivative tables of the translation classes at order P (built once per order, kept)
 const double* yk_class_tables(fmmb_plan* plan, YukawaData* d, int P, cudaStream_t s) {
   const bool use_classes = d->have_classes && plan->opts.m2l_mode != 1;
@@ -677,7 +702,7 @@ const double* yk_class_tables(fmmb_plan* plan, YukawaData* d, int P, cudaStream_
   DevBuf<double>* buf = new DevBuf<double>();
   d->tables[P] = buf;
   buf->resize((size_t)plan->cls.n_classes * nt);
-  yk_table_kernel<<<(int)plan->cls.n_classes, 128, 0, s>>>(P, d->kappa, plan->cls.class_vec.p, buf->p);
+  YK_MP(P, yk_table_kernel, <<<(int)plan->cls.n_classes, 128, 0, s>>>(P, d->kappa, plan->cls.class_vec.p, buf->p));
   FMMB_CUDA(cudaGetLastError());
   ++plan->launches;
   return buf->p;
@@ -690,7 +715,7 @@ void yk_translations(fmmb_plan* plan, YukawaData* d, int P, const double* table,
   cudaEvent_t* ev = plan->ev;
   for (int l = T.nlevels - 2; l >= 0; --l) {
     const int lo = T.level_off[l], hi = T.level_off[l + 1];
-    yk_m2m_kernel<<<hi - lo, 128, 0, s>>>(lo, hi, T.key.p, T.cbegin.p, T.cend.p, T.center.p, P, d->M.p);
+    YK_MP(P, yk_m2m_kernel, <<<hi - lo, 128, 0, s>>>(lo, hi, T.key.p, T.cbegin.p, T.cend.p, T.center.p, P, d->M.p));
     ++plan->launches;
   }
   if (!plan->capturing) FMMB_CUDA(cudaEventRecord(ev[2], s));
@@ -698,13 +723,13 @@ void yk_translations(fmmb_plan* plan, YukawaData* d, int P, const double* table,
     if (!plan->capturing) FMMB_CUDA(cudaEventRecord(ev[3], s));
     return;
   }
-  yk_m2l_kernel<<<nb, 128, 0, s>>>(nb, T.m2l_off.p, T.m2l_src.p, table ? d->slot_class.p : nullptr, table, T.center.p, P,
-                                  d->kappa, d->M.p, d->L.p);
+  YK_MP(P, yk_m2l_kernel, <<<nb, 128, 0, s>>>(nb, T.m2l_off.p, T.m2l_src.p, table ? d->slot_class.p : nullptr, table,
+                                               T.center.p, P, d->kappa, d->M.p, d->L.p));
   ++plan->launches;
   if (!plan->capturing) FMMB_CUDA(cudaEventRecord(ev[3], s));
   for (int l = 1; l < T.nlevels; ++l) {
     const int lo = T.level_off[l], hi = T.level_off[l + 1];
-    yk_l2l_kernel<<<hi - lo, 128, 0, s>>>(lo, hi, T.parent.p, T.has_local.p, T.center.p, P, d->L.p);
+    YK_MP(P, yk_l2l_kernel, <<<hi - lo, 128, 0, s>>>(lo, hi, T.parent.p, T.has_local.p, T.center.p, P, d->L.p));
     ++plan->launches;
   }
 }
@@ -713,7 +738,7 @@ void yk_translations(fmmb_plan* plan, YukawaData* d, int P, const double* table,
 
 void yukawa_setup(fmmb_plan* plan, double kappa) {
   Tree& T = plan->tree;
-  if (plan->p > kYkMaxP) throw StatusError{FMMB_ERR_UNSUPPORTED, "YukawaCartesian is built for orders 1..10"};
+  if (plan->p > kYkMaxP) throw StatusError{FMMB_ERR_UNSUPPORTED, "YukawaCartesian is built for orders 1..16"};
   YukawaData* d = new YukawaData();
   plan->yukawa = d;
   d->kappa = kappa;
@@ -734,7 +759,7 @@ void yukawa_execute(fmmb_plan* plan, const double* d_charges, double* d_results)
   Tree& T = plan->tree;
   YukawaData* d = plan->yukawa;
   const int P = plan->p;
-  if (P > kYkMaxP) throw StatusError{FMMB_ERR_UNSUPPORTED, "YukawaCartesian is built for orders 1..10"};
+  if (P > kYkMaxP) throw StatusError{FMMB_ERR_UNSUPPORTED, "YukawaCartesian is built for orders 1..16"};
   const int nt = yk_terms(P);
   const int64_t n = T.n;
   const int nb = T.nboxes;
@@ -767,19 +792,21 @@ void yukawa_execute(fmmb_plan* plan, const double* d_charges, double* d_results)
   if (!plan->capturing) FMMB_CUDA(cudaEventRecord(ev[12], s));
   {
     const size_t sh = (size_t)4 * 32 * (3 * (P + 1) + 1) * sizeof(double);
-    yk_p2m_kernel<<<nblk(T.nleaves, 4), 128, sh, s>>>(T.leaves.p, T.nleaves, T.bbegin.p, T.bend.p, T.center.p, T.body.p,
-                                                     P, d->M.p);
+    if (P <= 10) yk_shared_limit(yk_p2m_kernel<10>, sh); else yk_shared_limit(yk_p2m_kernel<16>, sh);
+    YK_MP(P, yk_p2m_kernel, <<<nblk(T.nleaves, 4), 128, sh, s>>>(T.leaves.p, T.nleaves, T.bbegin.p, T.bend.p, T.center.p,
+                                                                 T.body.p, P, d->M.p));
     ++plan->launches;
   }
   yk_translations(plan, d, P, table, s);      // treecode: stops after the upward pass
   if (plan->opts.evaluator == FMMB_EVAL_TREECODE) {
     if (T.n_own_leaves)
-      yk_m2p_kernel<<<nblk(T.n_own_leaves, 4), 128, 0, s>>>(T.own_leaves.p, T.n_own_leaves, T.bbegin.p, T.bend.p, T.parent.p,
-                                                           T.m2l_off.p, T.m2l_src.p, T.center.p, T.body.p, P, d->kappa,
-                                                           d->M.p, far);
+      YK_MP(P, yk_m2p_kernel, <<<nblk(T.n_own_leaves, 4), 128, 0, s>>>(T.own_leaves.p, T.n_own_leaves, T.bbegin.p, T.bend.p,
+                                                                       T.parent.p, T.m2l_off.p, T.m2l_src.p, T.center.p,
+                                                                       T.body.p, P, d->kappa, d->M.p, far));
     ++plan->launches;
   } else {
     const size_t sh = (size_t)4 * (nt + 32 * 3 * (P + 1)) * sizeof(double);
+    yk_shared_limit(yk_l2p_kernel, sh);
     if (T.n_own_leaves)
     yk_l2p_kernel<<<nblk(T.n_own_leaves, 4), 128, sh, s>>>(T.own_leaves.p, T.n_own_leaves, T.bbegin.p, T.bend.p,
                                                           T.center.p, T.has_local.p, T.body.p, P, d->L.p, far);
@@ -807,7 +834,7 @@ void yukawa_bem_execute(fmmb_plan* plan, const double* d_charges, double* d_resu
   YukawaData* d = plan->yukawa;
   BemData* B = plan->bem;
   const int P = plan->p;
-  if (P > kYkMaxP) throw StatusError{FMMB_ERR_UNSUPPORTED, "YukawaCartesianBEM is built for orders 1..10"};
+  if (P > kYkMaxP) throw StatusError{FMMB_ERR_UNSUPPORTED, "YukawaCartesianBEM is built for orders 1..16"};
   const int nt = yk_terms(P);
   cudaStream_t s = plan->stream;
   cudaEvent_t* ev = plan->ev;
@@ -827,25 +854,30 @@ void yukawa_bem_execute(fmmb_plan* plan, const double* d_charges, double* d_resu
   const size_t sh_l2p = (size_t)4 * (nt + 32 * 3 * (P + 1)) * sizeof(double);
   for (int set = 0; set < 2; ++set) {
     if (!bem_set_active(B, set) || plan->near_only) continue;
-    if (set == 0)
-      yk_bem_p2m_kernel<0><<<nblk(T.nleaves, 4), 128, sh_p2m, s>>>(T.leaves.p, T.nleaves, T.bbegin.p, T.bend.p, T.center.p,
-                                                                  T.body.p, bem_panels(B), bem_bc(B), rule, P, d->M.p);
-    else
-      yk_bem_p2m_kernel<1><<<nblk(T.nleaves, 4), 128, sh_p2m, s>>>(T.leaves.p, T.nleaves, T.bbegin.p, T.bend.p, T.center.p,
-                                                                  T.body.p, bem_panels(B), bem_bc(B), rule, P, d->M.p);
+#define YK_BEM_P2M(SET, MP)                                                                                             \
+  do {                                                                                                                 \
+    yk_shared_limit(yk_bem_p2m_kernel<SET, MP>, sh_p2m);                                                               \
+    yk_bem_p2m_kernel<SET, MP><<<nblk(T.nleaves, 4), 128, sh_p2m, s>>>(T.leaves.p, T.nleaves, T.bbegin.p, T.bend.p,     \
+                                                                        T.center.p, T.body.p, bem_panels(B), bem_bc(B), \
+                                                                        rule, P, d->M.p);                               \
+  } while (0)
+    if (set == 0) { if (P <= 10) YK_BEM_P2M(0, 10); else YK_BEM_P2M(0, 16); }
+    else { if (P <= 10) YK_BEM_P2M(1, 10); else YK_BEM_P2M(1, 16); }
+#undef YK_BEM_P2M
     ++plan->launches;
     yk_translations(plan, d, P, table, s);
     if (T.n_own_leaves && plan->opts.evaluator == FMMB_EVAL_TREECODE) {
-      if (set == 0)
-        yk_bem_m2p_kernel<0><<<nblk(T.n_own_leaves, 4), 128, 0, s>>>(
-            T.own_leaves.p, T.n_own_leaves, T.bbegin.p, T.bend.p, T.parent.p, T.m2l_off.p, T.m2l_src.p, T.center.p,
-            bem_panels(B), bem_bc(B), P, d->kappa, d->M.p, bem_res_far(B));
-      else
-        yk_bem_m2p_kernel<1><<<nblk(T.n_own_leaves, 4), 128, 0, s>>>(
-            T.own_leaves.p, T.n_own_leaves, T.bbegin.p, T.bend.p, T.parent.p, T.m2l_off.p, T.m2l_src.p, T.center.p,
-            bem_panels(B), bem_bc(B), P, d->kappa, d->M.p, bem_res_far(B));
+#define YK_BEM_M2P(SET, MP)                                                                                         \
+  yk_bem_m2p_kernel<SET, MP><<<nblk(T.n_own_leaves, 4), 128, 0, s>>>(                                               \
+      T.own_leaves.p, T.n_own_leaves, T.bbegin.p, T.bend.p, T.parent.p, T.m2l_off.p, T.m2l_src.p, T.center.p,       \
+      bem_panels(B), bem_bc(B), P, d->kappa, d->M.p, bem_res_far(B))
+      if (set == 0) { if (P <= 10) YK_BEM_M2P(0, 10); else YK_BEM_M2P(0, 16); }
+      else { if (P <= 10) YK_BEM_M2P(1, 10); else YK_BEM_M2P(1, 16); }
+#undef YK_BEM_M2P
       ++plan->launches;
     } else if (T.n_own_leaves) {
+      yk_shared_limit(yk_bem_l2p_kernel<0>, sh_l2p);
+      yk_shared_limit(yk_bem_l2p_kernel<1>, sh_l2p);
       if (set == 0)
         yk_bem_l2p_kernel<0><<<nblk(T.n_own_leaves, 4), 128, sh_l2p, s>>>(T.own_leaves.p, T.n_own_leaves, T.bbegin.p, T.bend.p,
                                                                          T.center.p, T.has_local.p, bem_panels(B), bem_bc(B),

@@ -49,10 +49,10 @@ typedef enum {
   FMMB_LAPLACE_SPHERICAL_BEM = 1,      /* kernel/LaplaceSphericalBEM.hpp: panels, charge 1, result 1 */
   FMMB_STOKES_SPHERICAL_STRESSLET = 2, /* kernel/StokesSpherical.hpp built with -DSTRESSLET: charge 6 (g, n),
                                           result 3 (serialrun_stresslet.cpp) */
-  FMMB_YUKAWA_CARTESIAN = 3,           /* kernel/YukawaCartesian.hpp: charge 1, result 4, orders 1..10, kappa from
+  FMMB_YUKAWA_CARTESIAN = 3,           /* kernel/YukawaCartesian.hpp: charge 1, result 4, orders 1..16, kappa from
                                           fmmb_kernel_desc */
   FMMB_YUKAWA_CARTESIAN_BEM = 4,       /* kernel/YukawaCartesianBEM.hpp: panels, charge 1, result 1, kappa, quad_k, orders
-                                          1..10.  Near field and treecode are pinned to the reference; its FMM
+                                          1..16.  Near field and treecode are pinned to the reference; its FMM
                                           evaluator is broken for this kernel, so the far field is validated against
                                           Direct only */
   FMMB_STOKES_SPHERICAL = 5,           /* kernel/StokesSpherical.hpp default build (Stokeslet): charge 3 (f), result 3 */

@@ -71,13 +71,40 @@ def test_accuracy_vs_direct_and_limits():
     assert O.rel_l2(res[:500, 0], d[:, 0]) < 5e-5
     assert O.rel_l2(res[:500, 1:], d[:, 1:]) < 2e-3
     with pytest.raises(F.FmmbError):
-        plan.kernel().set_p(11)                          # orders 1..10 are built
+        plan.kernel().set_p(17)                          # orders 1..16 are built (FMMB_MAX_P)
     with pytest.raises(F.FmmbError):
-        make_plan(pts[:1000], 12, kappa)
+        make_plan(pts[:1000], 17, kappa)
+
+
+@pytest.mark.parametrize("n,P,kappa,ncrit", [(4000, 11, 0.5, 40), (3000, 13, 0.25, 64), (2000, 16, 1.0, 50)])
+def test_orders_above_ten_vs_oracle(n, P, kappa, ncrit):
+    """Round 2: orders 11..16 (reference kernel/YukawaCartesian.hpp:102-126 takes any P; the default max_p of the
+    reference's solvers is 16, examples/BEM/SolverOptions.hpp:23).  The kernels that keep per-term state on chip are
+    compiled a second time for 969 terms (YkCap<16>).  FMM and treecode evaluators against the oracle restatement; an
+    order change across the two builds (P -> 8 -> P) gives the same bits again."""
+    pts, q = O.drand48_inputs(n)
+    orc = O.Oracle(pts, ncrit, 0.5)
+    plan = make_plan(pts, P, kappa, ncrit)
+    res = plan.execute(q)
+    ref = orc.yukawa_execute(q, P, kappa)
+    assert O.rel_l2(res[:, 0], ref[:, 0]) <= TOL
+    assert O.rel_l2(res[:, 1:], ref[:, 1:]) <= TOL
+    plan.kernel().set_p(8)
+    assert O.rel_l2(plan.execute(q), orc.yukawa_execute(q, 8, kappa)) <= TOL
+    plan.kernel().set_p(P)
+    assert np.array_equal(plan.execute(q), res)
+    opts = F.FMMOptions()
+    opts.set_mac_theta(0.5)
+    opts.set_max_per_box(ncrit)
+    opts.evaluator = F.FMMOptions.TREECODE
+    tree = F.FMM_plan(F.YukawaCartesian(P, kappa), pts, opts).execute(q)
+    tref = orc.yukawa_execute(q, P, kappa, treecode=True)
+    assert O.rel_l2(tree[:, 0], tref[:, 0]) <= TOL
+    assert O.rel_l2(tree[:, 1:], tref[:, 1:]) <= TOL
 
 
 # ---- YukawaCartesianBEM ------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("rec,P,K,kappa", [(5, 6, 4, 1.0), (6, 8, 4, 0.125), (5, 4, 3, 2.0)])
+@pytest.mark.parametrize("rec,P,K,kappa", [(5, 6, 4, 1.0), (6, 8, 4, 0.125), (5, 4, 3, 2.0), (5, 12, 4, 0.5)])
 def test_bem_matvec_vs_oracle(rec, P, K, kappa):
     """CUDA path against the oracle restatement (same algorithm: 1e-10) and against Direct (truncation error).
     The oracle's near field and treecode are pinned to the reference class; the reference's own FMM evaluator is
