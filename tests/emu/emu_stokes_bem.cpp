@@ -667,7 +667,7 @@ static int run_ykm2p() {
         if (a == 0) break;
       }
     std::vector<double> table(vec.size() * (size_t)nt);
-    emu::launch(dim3((unsigned)vec.size()), dim3(128), [&] { yk_table_kernel(P, kappa, vec.data(), table.data()); });
+    emu::launch(dim3((unsigned)vec.size()), dim3(128), [&] { yk_table_kernel<10>(P, kappa, vec.data(), table.data()); });
     std::vector<double> phi(n, 0.0);
     for (size_t k = 0; k < vec.size(); ++k) {
       double v = 0;
@@ -694,7 +694,7 @@ static int run_ykm2p() {
       std::vector<double4> body(n), g4(n, make_double4(-9, -9, -9, -9));
       for (int i = 0; i < n; ++i) body[i] = make_double4(pan[i].c[0], pan[i].c[1], pan[i].c[2], 1.0);
       emu::launch(dim3(nblocks(3, 4)), dim3(128), [&] {
-        yk_m2p_kernel(leaves.data(), 3, bb.data(), be.data(), parent.data(), off.data(), src.data(), center.data(), body.data(),
+        yk_m2p_kernel<10>(leaves.data(), 3, bb.data(), be.data(), parent.data(), off.data(), src.data(), center.data(), body.data(),
                       P, kappa, M.data(), g4.data());
       });
       std::vector<double> got4(4 * n);
@@ -704,9 +704,9 @@ static int run_ykm2p() {
     for (int set = 0; set < 2; ++set) {
       std::vector<double> got(n, 0.125), want(n, 0.125);
       emu::launch(dim3(nblocks(3, 4)), dim3(128), [&] {
-        if (set == 0) yk_bem_m2p_kernel<0>(leaves.data(), 3, bb.data(), be.data(), parent.data(), off.data(), src.data(),
+        if (set == 0) yk_bem_m2p_kernel<0, 10>(leaves.data(), 3, bb.data(), be.data(), parent.data(), off.data(), src.data(),
                                            center.data(), pan.data(), bc.data(), P, kappa, M.data(), got.data());
-        else yk_bem_m2p_kernel<1>(leaves.data(), 3, bb.data(), be.data(), parent.data(), off.data(), src.data(), center.data(),
+        else yk_bem_m2p_kernel<1, 10>(leaves.data(), 3, bb.data(), be.data(), parent.data(), off.data(), src.data(), center.data(),
                                   pan.data(), bc.data(), P, kappa, M.data(), got.data());
       });
       for (int i = 0; i < n; ++i) if (bc[i] == set) want[i] += set == 0 ? phi[i] : -phi[i];
