@@ -38,6 +38,7 @@ static void update_phase_times(fmmb_plan* plan) {
     if (cudaEventElapsedTime(&t, plan->ev[0], plan->ev[5]) != cudaSuccess) { cudaGetLastError(); t = 0; }
     for (int i = 0; i < FMMB_T_COUNT; ++i) if (i != FMMB_T_LAUNCHES && i != FMMB_T_H2D && i != FMMB_T_D2H) plan->phase_ms[i] = 0;
     plan->phase_ms[FMMB_T_TOTAL] = t;
+    plan->phase_ms[FMMB_T_LAUNCHES] = plan->launches;   // kernels inside the replayed graph (counted at its capture)
     return;
   }
   if (!plan->timed) return;
