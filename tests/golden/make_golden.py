@@ -183,6 +183,10 @@ def laplace_bem_case(name, recursions, p, k, ncrit, bc, tree=False):
 
 
 def main():
+    if "--yukawa-p12" in sys.argv:
+        # round 2: orders above 10 (the GPU engine's 969-term build); the unmodified class takes any P
+        yukawa_case("yukawa_drand48_n1500_p12", 1500, 12, 0.5, 40, 0.5)
+        return
     if "--yukawa-tree" in sys.argv:
         yukawa_case("yukawa_tree_n3000_p5", 3000, 5, 0.125, 32, 0.5, tree=True)
         return

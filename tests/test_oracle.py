@@ -169,6 +169,7 @@ def test_stokes_restatement_matches_reference(name, stresslet, P, ncrit, theta):
 @pytest.mark.parametrize("name,P,kappa,ncrit,theta", [
     ("yukawa_drand48_n3000_p5", 5, 0.125, 32, 0.5),
     ("yukawa_two_scale_n4000_p6", 6, 2.0, 12, 0.6),
+    ("yukawa_drand48_n1500_p12", 12, 0.5, 40, 0.5),      # orders above 10: tests/golden/make_golden.py --yukawa-p12
 ])
 def test_yukawa_restatement_matches_reference(name, P, kappa, ncrit, theta):
     g = dict(np.load(os.path.join(GOLDEN, name + ".npz")))

@@ -27,6 +27,7 @@ def make_plan(points, P, kappa, ncrit=64, theta=0.5):
 @pytest.mark.parametrize("name,P,kappa,ncrit,theta", [
     ("yukawa_drand48_n3000_p5", 5, 0.125, 32, 0.5),
     ("yukawa_two_scale_n4000_p6", 6, 2.0, 12, 0.6),
+    ("yukawa_drand48_n1500_p12", 12, 0.5, 40, 0.5),      # the 969-term build against the unmodified reference class
 ])
 def test_golden_fixtures(name, P, kappa, ncrit, theta):
     g = dict(np.load(os.path.join(GOLDEN, name + ".npz")))
