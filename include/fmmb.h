@@ -230,6 +230,9 @@ int fmmb_plan_direct_panels(fmmb_plan* plan, const double* charges_host, int64_t
  *                  sweep, beside the multipole exchange; 0 = with the upward pass (measured on 2 GPUs: 1.88 vs 1.59 ms).
  *   "graph_node_priority"  1 (default) = cached launch graphs keep the stream priorities of their kernels
  *                  (cudaGraphInstantiateFlagUseNodePriority): the far-field chain overtakes the near field's blocks.
+ *   "p2m_kernel"   1 (default) = P2M with a narrow transposition tile at P >= 7 (p2m_cols_kernel), 0 = full tile.
+ *   "l2p_kernel"   1 (default) = L2P with four leaves per warp in body order (l2p_packed_kernel), 0 = a leaf per warp.
+ *   "bem_near_kernel"  cached BEM near field: 1 (default) = eight warps per work item (bem_near_split_kernel), 0 = one.
  *   "p2p_unroll"   pair-loop unroll of p2p_kernel 1: 4 (default) or 8.
  *   "p2p_warps"    warps per block of the near-field pair kernel: 1 (default), 2 or 4.
  *   (measured on B200 at N = 1M: all combinations within 4 %; see profiles/README.md) */

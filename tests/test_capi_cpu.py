@@ -102,3 +102,16 @@ def test_options_mirror_reference_parser():
     assert k.P == 5
     k.set_p(8)
     assert k.P == 8
+
+
+def test_every_plan_option_is_documented_in_the_header():
+    """fmmb_plan_set_option takes its switches by name: every name the implementation compares against
+    (csrc/capi.cu) appears, quoted, in the option list of include/fmmb.h."""
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = open(os.path.join(root, "fmm_bem_relaxed_b200", "csrc", "capi.cu")).read()
+    hdr = open(os.path.join(root, "include", "fmmb.h")).read()
+    names = set(re.findall(r'strcmp\(name, "([a-z0-9_]+)"\)', src))
+    assert len(names) >= 15
+    missing = sorted(n for n in names if '"%s"' % n not in hdr)
+    assert not missing, missing
