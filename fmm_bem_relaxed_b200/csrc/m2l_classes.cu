@@ -426,7 +426,7 @@ m2l_reduce_kernel(int nboxes, const int* __restrict__ off, const unsigned char* 
 // memory: every warp owns a ring of kRedStages 4 KB stages, one lane brings the next columns of the warp's box in by
 // 1-D TMA bulk copies (cp.async.bulk, completion in bytes on the stage's mbarrier; the columns of a box are
 // contiguous), the warp adds them up out of shared memory (lane = two rows).  Two blocks of four warps per SM keep
-// 96 KB per SM in flight with 8 K registers; warps never meet at a block barrier.
+// 96 KB per SM in flight with 15 K registers (58 per thread); warps never meet at a block barrier.
 constexpr int kRedStages = 4, kRedStageBytes = 4096, kRedWarps = 4;
 constexpr size_t kRedShared = (size_t)kRedWarps * kRedStages * (kRedStageBytes + sizeof(uint64_t) + sizeof(unsigned));
 
